@@ -1,0 +1,274 @@
+"""Generate the committed golden vectors by RUNNING THE UNMODIFIED REFERENCE.
+
+Run in the authoring container only (needs /root/reference; scipy 1.18.1 /
+numpy 2.3.5 at generation time -- both versions are recorded in the files):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Outputs (small, committed):
+  tests/golden/phasescore_cases.json.gz   statistics.phasescore (statistics.py:48)
+  tests/golden/pipeline_cases.json.gz     merge_read_lengths (detect_orfs.py:54),
+                                          orf_coverage (:134), export_orf_coverages
+                                          (:206) and export_wig (:327) end to end
+
+``split_bam`` (bam.py:33) cannot be run anywhere in this image (no pysam, no
+BAM), so A1 has no golden vectors: it is covered by a line-by-line restatement
+only, and says so.
+"""
+from __future__ import annotations
+
+import gzip
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import  # noqa: E402
+
+
+def versions():
+    import scipy
+    return {"scipy": scipy.__version__, "numpy": np.__version__, "reference": "ribotricer 1.5.0"}
+
+
+# ---------------------------------------------------------------- phasescore
+KAT_PROFILES = [
+    [], [0], [1], [0, 0], [1, 0, 0], [0, 0, 0], [1, 1, 1], [1, 0, 0, 0, 0],
+    [1] + [0] * 29, [0, 0, 0, 1] + [0] * 26, [2, 2, 2, 1, 0, 0, 1, 0, 0],
+    [1, 1, 1] * 5, [0] * 30, [0, 1, 0] * 10, [0, 0, 1] * 10, [1, 0, 0] * 10,
+    [3, 1, 2, 0, 0, 0, 5, 0, 1, 2, 2, 2, 0, 4, 0, 1],
+    [0, 0, 0, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0], [0, 1, 1, 4, 1, 1, 2],
+    [5, 0, 0, 3, 1, 0, 4, 0, 0, 2, 0, 0, 6, 0, 0, 0, 1, 0, 2, 0, 0],
+    [2, 0, 0, 2, 0, 0, 1, 1, 0, 0, 0, 0, 3, 0, 0, 0, 0, 0],
+    [1, 0, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0, 0, 7],
+    [1000000, 3, 2] * 7, [500000000, 0, 1, 0, 500000000, 2, 7, 7, 7, 1, 2, 3],
+    [0, 0, 5], [0, 5, 0, 0], [0, 0, 0, 0, 0, 9],
+]
+
+
+def make_phasescore_cases(phasescore):
+    rng = np.random.default_rng(20261017)
+    profiles = [list(p) for p in KAT_PROFILES]
+    for _ in range(2400):
+        length = int(rng.integers(1, 601))
+        lam = float(rng.choice([0.005, 0.02, 0.1, 0.5, 2.0, 20.0, 200.0]))
+        kind = rng.random()
+        if kind < 0.5:      # 3-nt periodic Poisson
+            frame = int(rng.integers(0, 3))
+            w = np.full(length, 0.15 * lam)
+            w[frame::3] = 0.7 * lam
+            cov = rng.poisson(w * 3)
+        else:               # aperiodic
+            cov = rng.poisson(lam, length)
+        if rng.random() < 0.25 and length > 6:   # inject uniform codons
+            for _ in range(int(rng.integers(1, 4))):
+                p = int(rng.integers(0, length - 3))
+                cov[p:p + 3] = int(rng.integers(1, 6))
+        profiles.append([int(x) for x in cov])
+    out = []
+    for p in profiles:
+        score, valid = phasescore(p)
+        out.append({"cov": p, "score": float(score).hex(), "valid": int(valid)})
+    return out
+
+
+# ------------------------------------------------------------------ pipeline
+def appendix_a_case():
+    """SURVEY.md Appendix A, regenerated (not transcribed) from the reference."""
+    index = [
+        "ORF_ID\tORF_type\ttranscript_id\ttranscript_type\tgene_id\tgene_name\tgene_type\tchrom\tstrand\tstart_codon\tcoordinate",
+        "IGNORED\tannotated\ttxA\tprotein_coding\tgA\tGA\tprotein_coding\tchrI\t+\tATG\t101-109,201-212",
+        "IGNORED\tuORF\ttxB\tprotein_coding\tgB\tGB\tprotein_coding\tchrI\t-\tCTG\t301-318",
+        "IGNORED\tnovel\ttxC\tlncRNA\tgC\tGC\tlncRNA\tchrII\t+\tATG\t11-30",
+    ]
+    aln = [
+        (28, "+", "chrI", 89, 5), (28, "+", "chrI", 92, 3), (28, "+", "chrI", 95, 4),
+        (28, "+", "chrI", 192, 6), (28, "+", "chrII", -1, 1), (28, "+", "chrII", 2, 1),
+        (28, "+", "chrII", 5, 1), (28, "+", "chrII", 8, 1), (28, "+", "chrII", 11, 1),
+        (28, "+", "chrII", 14, 1),
+        (29, "+", "chrI", 92, 1), (29, "+", "chrI", 188, 2), (29, "+", "chrI", 195, 1),
+        (29, "+", "chrI", 197, 2), (29, "+", "chrII", 17, 7),
+        (28, "-", "chrI", 330, 2), (28, "-", "chrI", 327, 2), (28, "-", "chrI", 318, 3),
+        (29, "-", "chrI", 325, 1), (29, "-", "chrI", 324, 1),
+        (30, "+", "chrI", 150, 99),
+    ]
+    return dict(name="appendix_a", contigs=[["chrI", 400], ["chrII", 100]], index=index,
+                alignments=aln, psite_offsets={"28": 12, "29": 13})
+
+
+def random_case(name, seed, n_tx, contigs, unknown_chrom=False, odd_lengths=False):
+    rng = np.random.default_rng(seed)
+    header = ("ORF_ID\tORF_type\ttranscript_id\ttranscript_type\tgene_id\tgene_name\t"
+              "gene_type\tchrom\tstrand\tstart_codon\tcoordinate")
+    lines, orfs = [], []
+    cats = ["annotated", "uORF", "dORF", "novel", "super_uORF", "overlap_dORF"]
+    for t in range(n_tx):
+        cname, clen = contigs[int(rng.integers(0, len(contigs)))]
+        strand = "+" if rng.random() < 0.5 else "-"
+        n_ex = int(min(6, rng.geometric(0.45)))
+        pos = int(rng.integers(1, max(2, clen - 1500)))
+        exons = []
+        for _ in range(n_ex):
+            elen = int(rng.integers(1, 160)) if rng.random() < 0.9 else int(rng.integers(1, 4))
+            exons.append((pos, pos + elen - 1))
+            pos += elen + int(rng.integers(1, 120))
+        exons = [(s, e) for s, e in exons if e <= clen]
+        if not exons:
+            continue
+        total = sum(e - s + 1 for s, e in exons)
+        # nested ORFs sharing the transcript 3' end: trim k nt from the 5' end
+        n_nested = int(rng.integers(1, 4))
+        for k in range(n_nested):
+            trim = 0 if k == 0 else int(rng.integers(1, max(2, total - 3)))
+            if not odd_lengths:
+                trim -= trim % 3
+            ivs = list(exons)
+            left = trim
+            if strand == "+":
+                while left > 0 and ivs:
+                    s, e = ivs[0]
+                    if e - s + 1 <= left:
+                        left -= e - s + 1
+                        ivs.pop(0)
+                    else:
+                        ivs[0] = (s + left, e)
+                        left = 0
+            else:
+                while left > 0 and ivs:
+                    s, e = ivs[-1]
+                    if e - s + 1 <= left:
+                        left -= e - s + 1
+                        ivs.pop()
+                    else:
+                        ivs[-1] = (s, e - left)
+                        left = 0
+            if not ivs:
+                continue
+            chrom = cname
+            if unknown_chrom and rng.random() < 0.05:
+                chrom = "chrUn_absent"
+            cat = "annotated" if (k == 0 and t < n_tx // 4) else cats[int(rng.integers(1, len(cats)))]
+            # exercise orf.py:100 (intervals are sorted on load): shuffle the text order
+            txt_ivs = list(ivs)
+            if rng.random() < 0.2:
+                rng.shuffle(txt_ivs)
+            coord = ",".join(f"{s}-{e}" for s, e in txt_ivs)
+            lines.append(f"id{t}_{k}\t{cat}\ttx{t}\tprotein_coding\tg{t}\tG{t}\tprotein_coding\t"
+                         f"{chrom}\t{strand}\t{['ATG','CTG','GTG','TTG'][int(rng.integers(0,4))]}\t{coord}")
+            orfs.append((chrom, strand, ivs))
+    # annotated rows first, like prepare-orfs writes them (prepare_orfs.py:322-329)
+    order = sorted(range(len(lines)), key=lambda i: 0 if "\tannotated\t" in lines[i] else 1)
+    lines = [lines[i] for i in order]
+    orfs = [orfs[i] for i in order]
+    # reads: P-sites in frame in a subset of "expressed" ORFs + background
+    lens = [26, 27, 28, 29, 30, 31, 32]
+    offsets = {26: 12, 27: 12, 28: 12, 29: 12, 30: 13, 31: 13}   # 32 has no offset -> dropped
+    aln = {}
+
+    def add(length, strand, chrom, psite, n=1):
+        off = offsets.get(length, 12)
+        pos5 = psite - off if strand == "+" else psite + off
+        key = (length, strand, chrom, pos5)
+        aln[key] = aln.get(key, 0) + n
+
+    for chrom, strand, ivs in orfs:
+        if chrom == "chrUn_absent" or rng.random() < 0.35:
+            continue
+        expr = float(rng.gamma(0.5) * 0.6)
+        flat = [p for s, e in ivs for p in range(s, e + 1)]
+        if strand == "-":
+            flat.reverse()
+        n_reads = int(rng.poisson(expr * len(flat) / 3))
+        for _ in range(n_reads):
+            codon = int(rng.integers(0, max(1, len(flat) // 3)))
+            fr = int(rng.choice([0, 1, 2], p=[0.7, 0.15, 0.15]))
+            idx = min(len(flat) - 1, 3 * codon + fr)
+            add(int(rng.choice(lens)), strand, chrom, flat[idx])
+    for cname, clen in contigs:
+        for _ in range(int(clen * 0.02)):
+            add(int(rng.choice(lens)), "+" if rng.random() < 0.5 else "-", cname,
+                int(rng.integers(-5, clen + 20)), int(rng.integers(1, 4)))
+    aln_list = [(k[0], k[1], k[2], k[3], v) for k, v in aln.items()]
+    return dict(name=name, contigs=[list(c) for c in contigs], index=[header] + lines,
+                alignments=aln_list, psite_offsets={str(k): v for k, v in offsets.items()})
+
+
+PARAM_SETS = [
+    dict(phase_score_cutoff=0.428571428571, min_valid_codons=5, min_reads_per_codon=0,
+         min_valid_codons_ratio=0, min_density_over_orf=0.0, report_all=True),
+    dict(phase_score_cutoff=0.428571428571, min_valid_codons=5, min_reads_per_codon=0,
+         min_valid_codons_ratio=0, min_density_over_orf=0.0, report_all=False),
+    dict(phase_score_cutoff=0.3, min_valid_codons=3, min_reads_per_codon=1,
+         min_valid_codons_ratio=0.1, min_density_over_orf=0.25, report_all=True),
+    dict(phase_score_cutoff=0.0, min_valid_codons=0, min_reads_per_codon=0,
+         min_valid_codons_ratio=0.5, min_density_over_orf=1.0, report_all=False),
+]
+
+
+def run_reference_pipeline(case, ref):
+    from collections import Counter, defaultdict
+
+    from ribotricer.detect_orfs import (export_orf_coverages, export_wig,
+                                        merge_read_lengths, orf_coverage)
+    from ribotricer.orf import ORF
+
+    alignments = defaultdict(lambda: defaultdict(Counter))
+    for length, strand, chrom, pos, n in case["alignments"]:
+        alignments[length][strand][(chrom, pos)] += n
+    offsets = {int(k): v for k, v in case["psite_offsets"].items()}
+    merged = merge_read_lengths(alignments, offsets)
+    case["merged"] = sorted([s, c, p, n] for s in merged for (c, p), n in merged[s].items())
+    with tempfile.TemporaryDirectory() as tmp:
+        idx = os.path.join(tmp, "idx.tsv")
+        with open(idx, "w") as fh:
+            fh.write("\n".join(case["index"]) + "\n")
+        profiles = []
+        for line in case["index"][1:]:
+            orf = ORF.from_string(line + "\n")
+            profiles.append([orf.oid, orf_coverage(orf, merged)])
+        case["profiles"] = profiles
+        prefix = os.path.join(tmp, "out")
+        export_wig(merged, prefix)
+        case["wig"] = {}
+        for tag in ("pos", "neg"):
+            path = f"{prefix}_{tag}.wig"
+            if os.path.exists(path):
+                case["wig"][tag] = open(path).read()
+        case["tsv"] = []
+        for params in PARAM_SETS:
+            export_orf_coverages(idx, merged, prefix, **params)
+            case["tsv"].append({"params": params,
+                                "text": open(f"{prefix}_translating_ORFs.tsv").read()})
+    return case
+
+
+def main():
+    ref = ref_import.load()
+    from ribotricer.statistics import phasescore
+
+    ps = {"versions": versions(), "cases": make_phasescore_cases(phasescore)}
+    with gzip.open(os.path.join(HERE, "phasescore_cases.json.gz"), "wt") as fh:
+        json.dump(ps, fh, separators=(",", ":"))
+    print("phasescore cases:", len(ps["cases"]))
+
+    cases = [
+        appendix_a_case(),
+        random_case("yeastlike", 1001, 120, [("chrI", 6000), ("chrII", 4000), ("chrM", 900)]),
+        random_case("ragged", 1002, 90, [("c1", 5000), ("c2", 2500)], unknown_chrom=True,
+                    odd_lengths=True),
+    ]
+    done = [run_reference_pipeline(c, ref) for c in cases]
+    with gzip.open(os.path.join(HERE, "pipeline_cases.json.gz"), "wt") as fh:
+        json.dump({"versions": versions(), "cases": done}, fh, separators=(",", ":"))
+    for c in done:
+        print(c["name"], "orfs:", len(c["index"]) - 1, "alignment keys:", len(c["alignments"]))
+
+
+if __name__ == "__main__":
+    main()
