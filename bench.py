@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the detect-orfs scoring path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" is one pass of the hot path over one synthetic Ribo-seq library:
+K1 bin P-sites (+1) -> K2+K3 gather+score every candidate ORF -> K1 again with
+weight -1, which returns the resident coverage planes to zero for the next
+library (cheaper than a 24.8 GB memset).  At N=1 the workload is BASELINE.json
+configs[1] (human GENCODE-scale: 2.5 M candidate ORFs, 100 M reads).  At N>1
+every rank holds its own 2.5 M-ORF shard of an N x 2.5 M-ORF index and bins the
+same library into its own replica of the coverage (north_star item 4: ORFs
+sharded, coverage replicated, no collective on the data path) -> weak scaling.
+
+`value` is ORFs scored per second with all inputs resident in HBM; `e2e` is the
+same metric through the host-buffer C-ABI calls (pinned host read columns in,
+host result columns out, all copies inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "candidate ORFs scored/sec (P-site binning + gather + phase score + filters)"
+UNIT = "ORFs/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink ORF/read counts (debugging only)")
+    ap.add_argument("--contig-scale", type=float, default=1.0, help="shrink contigs (debugging only)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, device_index: int, period_s: float = 0.01):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self.period = period_s
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = device_index
+            if visible:
+                try:
+                    phys = int(visible.split(",")[device_index])
+                except ValueError:
+                    phys = device_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as exc:   # pragma: no cover - depends on the box
+            self.nv = None
+            self.err = str(exc)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- CPU baseline
+def _cpu_worker(args):
+    """Score a slice of ORFs exactly like the body of export_orf_coverages (detect_orfs.py:274-299)
+    with the SciPy call of statistics.py:101-107 (oracle_py.phasescore_scipy)."""
+    orfs, merged = args
+    from oracle import oracle_py as O
+
+    n = 0
+    for chrom, strand, ivs in orfs:
+        cov = O.orf_profile(chrom, strand, ivs, merged)
+        O.score_profile(cov, scorer=O.phasescore_scipy)
+        n += 1
+    return n
+
+
+def cpu_reference_run(config_name: str, seconds: float, cores: int | None = None, steps: int = 1):
+    """The reference's CPU path (faithful port: same SciPy call) on a bounded sample of the workload.
+
+    The sample is the same synthetic configuration generated at a small scale (same genome, same
+    ORF-length and reads-per-ORF distributions), scored with all host cores by multiprocessing
+    over ORF slices -- the reference itself is single-process.
+    Returns (ORFs/s per step list, description dict).
+    """
+    import multiprocessing as mp
+
+    from oracle import oracle_py as O
+    from ribotricer_b200 import synth
+
+    cores = cores or os.cpu_count() or 1
+    # ~21 ORFs/s/core for the reference: size the sample to the budget
+    n_sample = int(max(cores * 8, min(20000, seconds * cores * 12)))
+    full = synth.config(config_name)
+    scale = n_sample / full.n_orf
+    cfg = synth.config(config_name, scale)
+    idx = synth.make_index(cfg)
+    reads = synth.reads_to_numpy(synth.make_reads(cfg, idx, device="cpu"))
+    aln, _, _ = O.split_reads(reads, "forward", None, idx.contig_names)
+    merged = O.merge_read_lengths(aln, synth.TRUE_OFFSETS)
+    merged = {s: dict(t) for s, t in merged.items()}
+    orfs = []
+    for o in range(idx.n_orf):
+        a, b = idx.exon_ptr[o], idx.exon_ptr[o + 1]
+        orfs.append((idx.contig_names[idx.orf_contig[o]], "+" if idx.orf_strand[o] == 0 else "-",
+                     list(zip(idx.exon_start[a:b].tolist(), idx.exon_end[a:b].tolist()))))
+    per_step = max(cores, len(orfs) // max(1, steps))
+    rates = []
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for s in range(steps):
+            chunk = orfs[s * per_step:(s + 1) * per_step] or orfs[:per_step]
+            slices = [(chunk[i::cores * 4], merged) for i in range(cores * 4)]
+            t0 = time.perf_counter()
+            done = sum(pool.map(_cpu_worker, slices))
+            dt = time.perf_counter() - t0
+            rates.append(done / dt)
+    import scipy
+    desc = {"kind": "port", "cores": cores,
+            "sample": f"{per_step} ORFs/step of synthetic {config_name} generated at scale {scale:.2e} "
+                      f"({idx.n_orf} ORFs, {len(reads['ref_id'])} reads, mean {idx.orf_len.mean():.0f} nt); "
+                      f"oracle_py.phasescore_scipy = the reference's scipy.signal.coherence call "
+                      f"(scipy {scipy.__version__}), multiprocessing over ORF slices"}
+    return rates, desc
+
+
+def cpu_closed_form_run(config_name: str, n_orf: int = 200_000):
+    """Second CPU line: the C restatement of the same arithmetic (oracle/rt_oracle.c, OpenMP, all
+    cores) on a scaled copy of the workload -- a much tougher CPU baseline than the reference."""
+    from oracle import c_oracle as CO
+    from ribotricer_b200 import synth
+
+    full = synth.config(config_name)
+    scale = min(1.0, n_orf / full.n_orf)
+    cfg = synth.config(config_name, scale, contig_scale=max(scale, 0.01))
+    idx = synth.make_index(cfg)
+    reads = synth.reads_to_numpy(synth.make_reads(cfg, idx, device="cpu"))
+    pad = 256
+    base, plane = CO.genome_layout(idx.contig_len, pad)
+    cov, _, _ = CO.bin_reads(reads, 0, CO.make_len_table(synth.TRUE_OFFSETS), base, idx.contig_len, pad, plane)
+    t0 = time.perf_counter()
+    CO.score(idx.as_dict(), cov, base, idx.contig_len, pad, plane, [0.428571428571, 5, 0, 0, 0.0],
+             diagnostics=False)
+    dt = time.perf_counter() - t0
+    return {"value": idx.n_orf / dt, "unit": UNIT, "cores": CO.lib().orc_max_threads(), "kind": "port (closed form, C+OpenMP)",
+            "sample": f"{idx.n_orf} ORFs of synthetic {config_name} at scale {scale:.2e}, contigs shrunk to fit host RAM"}
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from ribotricer_b200 import synth
+
+    cores = os.cpu_count() or 1
+    total_steps = args.steps + args.warmup
+    budget = 150.0   # whole run within a few minutes
+    rates, desc = cpu_reference_run(args.config, budget / max(1, total_steps) * 1.0, cores, steps=total_steps)
+    timed = rates[args.warmup:] or rates
+    value = float(len(timed) / sum(1.0 / r for r in timed))   # harmonic mean = total ORFs / total time
+    full = synth.config(args.config)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.config}: synthetic human GENCODE-scale detect-orfs "
+                               f"({full.n_orf} candidate ORFs, {full.n_reads} reads); bounded sample per step"},
+        "cpu_baseline": dict(desc, value=value, unit=UNIT),
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from ribotricer_b200 import synth
+    from ribotricer_b200.engine import READ_BYTES, Engine, ScoreParams
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    # ---- workload: this rank's ORF shard + the (replicated) library
+    cfg = synth.config(args.config, args.scale, args.contig_scale)
+    shard_cfg = synth.config(args.config, args.scale, args.contig_scale)
+    shard_cfg.seed = cfg.seed + 1000 * rank          # rank r holds shard r of the N x n_orf index
+    idx = synth.make_index(shard_cfg)
+    lib_idx = idx if rank == 0 else synth.make_index(cfg)   # every rank bins the SAME library (rank 0's)
+    eng = Engine(local)
+    eng.set_genome(idx.contig_names, idx.contig_len)
+    eng.set_length_table(synth.TRUE_OFFSETS, None)
+    eng.set_index(**idx.as_dict())
+    dreads = synth.make_reads(cfg, lib_idx, device=dev)
+    n_reads = int(dreads["ref_id"].numel())
+    n_orf = idx.n_orf
+    cov = eng.new_coverage()
+    stats, len_counts = eng.new_bin_accumulators()
+    out = eng.new_score_columns(n_orf)
+    params = ScoreParams()
+    score_bytes = eng.score_bytes()
+    total_nt = eng.total_nt()
+    bin_bytes = 23 * n_reads   # 15 B columns + 8 B RMW per read (we move 18 + 8)
+    torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def step(events=None):
+        if events is not None:
+            events[0].record()
+        eng.bin_reads_device(cov, dreads, "forward", stats, len_counts, sorted_hint=True)
+        if events is not None:
+            events[1].record()
+        eng.score_device(cov, out, 0, n_orf, params)
+        if events is not None:
+            events[2].record()
+        eng.bin_reads_device(cov, dreads, "forward", stats, len_counts, sorted_hint=True, weight=-1)
+        if events is not None:
+            events[3].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = eng.launches
+    per_step_events = [[ev() for _ in range(4)] for _ in range(args.steps)]
+    t_start, t_end = ev(), ev()
+    with ClockSampler(local) as clocks:
+        barrier()
+        t_start.record()
+        for k in range(args.steps):
+            step(per_step_events[k])
+        t_end.record()
+        barrier()
+    launches = eng.launches - launches0
+    total_ms = t_start.elapsed_time(t_end)
+    bin_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in per_step_events]))
+    score_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in per_step_events]))
+    unbin_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in per_step_events]))
+    assert int(cov.abs().max().item()) == 0, "coverage did not return to zero after un-binning"
+
+    # ---- e2e: host buffers in, host buffers out, through the host-buffer C-ABI calls
+    hreads = {k: v.cpu().pin_memory() for k, v in dreads.items()}
+    del dreads
+    torch.cuda.empty_cache()
+    e2e_steps = max(3, min(args.steps, 5))
+    for _ in range(2):
+        eng.clear_coverage(cov)
+        eng.bin_reads_host(cov, hreads, "forward", sorted_hint=True)
+        res = eng.score_host(cov, 0, n_orf, params)
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(e2e_steps):
+        eng.clear_coverage(cov)
+        st_host, _ = eng.bin_reads_host(cov, hreads, "forward", sorted_hint=True)
+        res = eng.score_host(cov, 0, n_orf, params)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    h2d = READ_BYTES * n_reads
+    d2h = 29 * n_orf + 8 * (9 + 65536)
+
+    times = torch.tensor([total_ms, e2e_ms, score_ms, bin_ms, unbin_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, score_ms, bin_ms, unbin_ms = times.tolist()
+    ms_per_step = total_ms / args.steps
+    value = world * n_orf / (ms_per_step * 1e-3)
+    e2e_value = world * n_orf / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        achieved = score_bytes / (score_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"{args.config}: synthetic human GENCODE-scale detect-orfs, {n_orf} candidate ORFs "
+                            f"({total_nt} nt) per GPU, {n_reads} reads (coordinate-sorted, lengths 26-32), "
+                            f"default cutoff 0.428571428571 + all filters",
+                "orfs_per_gpu": n_orf, "reads": n_reads, "sharding": f"orf-shard x{world}, coverage replicated",
+                "l2": "inputs larger than L2 (coverage planes %.1f GB, read columns %.2f GB)" % (
+                    cov.numel() * 4 / 1e9, READ_BYTES * n_reads / 1e9),
+                "step": "bin(+1) -> gather+score -> bin(-1) (returns the resident coverage to zero)",
+            },
+            "reads_binned_per_s": world * n_reads / (ms_per_step * 1e-3),
+            "kernels_ms": {"bin_psites": bin_ms, "score_orfs": score_ms, "unbin_psites": unbin_ms},
+            "roofline": {"bound": "hbm", "kernel": "score_orfs_kernel", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                         "algorithmic_bytes": score_bytes, "peak_source": peak_src,
+                         "bin_psites": {"achieved": bin_bytes / (bin_ms * 1e-3) / 1e9,
+                                        "frac": bin_bytes / (bin_ms * 1e-3) / 1e9 / hbm_peak,
+                                        "algorithmic_bytes": bin_bytes}},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "path": "Engine.clear_coverage + bin_reads_host (rt_bin_reads_host) + score_host (rt_score_host)"},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+            "translating": int(res["status"].sum()), "valid_reads": st_host["valid"],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                rates, desc = cpu_reference_run(args.config, args.cpu_seconds)
+                line["cpu_baseline"] = dict(desc, value=float(rates[0]), unit=UNIT)
+                line["cpu_closed_form"] = cpu_closed_form_run(args.config)
+            except Exception as exc:   # the GPU numbers must still be reported
+                line["cpu_baseline"] = {"error": repr(exc)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,173 @@
+/*
+ * ribotricer_b200.h -- C ABI of the B200-native detect-orfs scoring path.
+ *
+ * The reference (smithlabcode/ribotricer v1.5.0) is pure Python and has no
+ * FFI; the boundary it offers for this path is its function surface
+ * (SURVEY.md 8(b)).  Each entry point below names the reference function it
+ * replaces (paths relative to the reference tree).  The ctypes binding a
+ * maintainer would add on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, no torch types; every function returns 0 on success or a
+ *     negative RT_E* code, and rt_last_error() gives the message;
+ *   - one rt_ctx per (process, device); a ctx is not thread-safe;
+ *   - "d_" pointers are DEVICE pointers owned by the caller (e.g. torch
+ *     tensors), "h_" pointers are HOST pointers; `stream` is a cudaStream_t
+ *     (NULL = default stream); device-pointer calls only enqueue work;
+ *   - there is no CPU fallback anywhere: without a CUDA device rt_create fails.
+ *
+ * Data layout in HBM
+ *   coverage   int32 [2][plane]   plane 0 = '+' strand, plane 1 = '-' strand,
+ *              slot(contig c, 1-based pos) = contig_base[c] + pad + pos,
+ *              contig strides rounded up to 32 elements (128 B), `pad` slots
+ *              of slack on both sides of every contig so that P-sites shifted
+ *              off a contig end (pos <= 0 or > len) keep a private slot.
+ *   reads      structure of arrays, one element per alignment record:
+ *              ref_id i32 | first i32 | last i32 | mlen u16 | flag u16 |
+ *              mapq u8 | nh u8          (18 B / read)
+ *              first/last = 0-based first/last matched reference position
+ *              (pysam get_reference_positions()[0] / [-1], bam.py:95),
+ *              mlen = number of matched positions (bam.py:99), flag = SAM flag,
+ *              nh = value of the NH tag, 0 when the tag is absent.
+ *   index      CSR over candidate ORFs in index-file order: exon_ptr[n+1],
+ *              exon_start/exon_end (1-based closed, ascending, orf.py:100),
+ *              orf_contig (-1 = contig unknown to the genome table),
+ *              orf_strand (0 '+', 1 '-', anything else = no coverage).
+ */
+#ifndef RIBOTRICER_B200_H
+#define RIBOTRICER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1
+
+/* read-length table: one int32 per matched length */
+#define RT_LEN_TABLE 65536
+#define RT_LEN_UNUSED (-1)   /* length kept by split_bam but absent from psite_offsets
+                                (dropped by merge_read_lengths, detect_orfs.py:74) */
+#define RT_LEN_FILTERED (-2) /* length not in --read_lengths (bam.py:101) */
+
+/* protocol (bam.py:105,118); any other value stores no read, like the reference */
+#define RT_PROTOCOL_FORWARD 0
+#define RT_PROTOCOL_REVERSE 1
+#define RT_PROTOCOL_NONE 2
+
+/* stats[] slots written by rt_bin_reads (bam.py:61,141-146) */
+enum {
+    RT_ST_TOTAL = 0, RT_ST_QCFAIL, RT_ST_DUPLICATE, RT_ST_SECONDARY, RT_ST_UNMAPPED,
+    RT_ST_MULTI, RT_ST_VALID,
+    RT_ST_OOB,     /* valid reads whose P-site falls outside the padded contig */
+    RT_ST_BADREF,  /* ref_id outside the contig table (reference_name is None) */
+    RT_N_STATS
+};
+
+enum {
+    RT_OK = 0, RT_EINVAL = -1, RT_ECUDA = -2, RT_ENOMEM = -3, RT_ESTATE = -4
+};
+
+typedef struct rt_ctx rt_ctx;
+
+/* filter thresholds of export_orf_coverages (detect_orfs.py:209-215,289-299) */
+typedef struct rt_score_params {
+    double phase_score_cutoff;
+    double min_valid_codons;
+    double min_reads_per_codon;
+    double min_valid_codons_ratio;
+    double min_density_over_orf;
+} rt_score_params;
+
+/* per-ORF result columns (any pointer except score/valid/count/length may be NULL) */
+typedef struct rt_score_out {
+    double*  score;      /* phase score, statistics.py:115                      */
+    int32_t* valid;      /* valid codons of the winning frame, statistics.py:110 */
+    int64_t* count;      /* read_count, detect_orfs.py:278                      */
+    int32_t* length;     /* profile length, detect_orfs.py:279                  */
+    int32_t* min_codon;  /* min over codon sums (common.py:177-179), saturated  */
+    uint8_t* status;     /* 1 = translating, detect_orfs.py:289-299             */
+    int32_t* frame_K;    /* optional diagnostics [n][3]: kept codons per frame  */
+    double*  frame_s;    /* optional diagnostics [n][3]: coherence per frame (NaN if undefined) */
+} rt_score_out;
+
+int rt_abi_version(void);
+const char* rt_last_error(const rt_ctx* ctx);   /* ctx may be NULL (creation errors) */
+
+int rt_create(int device, rt_ctx** out);
+void rt_destroy(rt_ctx* ctx);
+int rt_device_count(void);
+
+/* ---- genome table: replaces the (chrom, pos) dict keys of AlignmentDict (bam.py:29) ---- */
+int rt_set_genome(rt_ctx* ctx, int n_contig, const int64_t* h_contig_len, int pad);
+int64_t rt_plane_elems(const rt_ctx* ctx);                 /* int32 elements per strand plane */
+int rt_get_contig_base(const rt_ctx* ctx, int64_t* h_out); /* n_contig values */
+
+/* ---- read-length table: --read_lengths (bam.py:101) + psite_offsets (detect_orfs.py:74-81) ---- */
+int rt_set_length_table(rt_ctx* ctx, const int32_t* h_len_table /* RT_LEN_TABLE */);
+
+/*
+ * ---- K1: split_bam per-read loop (bam.py:71-137) fused with merge_read_lengths
+ *      (detect_orfs.py:54-83) on decoded read columns.
+ * Adds into d_cov (2*plane int32; clear it first for a fresh library),
+ * accumulates into d_stats[RT_N_STATS] and d_len_counts[RT_LEN_TABLE] (int64).
+ * `sorted_hint` != 0 promises coordinate-sorted input (a real BAM) and selects
+ * the shared-memory tile path; results are identical either way.
+ * `weight` is +1 to add a library, or -1 to take the same reads out again
+ * (coverage, stats and length counts all return to their previous values),
+ * which recycles a resident coverage buffer without a multi-GB memset.
+ */
+int rt_bin_reads(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* d_ref_id,
+                 const int32_t* d_first, const int32_t* d_last, const uint16_t* d_mlen,
+                 const uint16_t* d_flag, const uint8_t* d_mapq, const uint8_t* d_nh,
+                 int protocol, int sorted_hint, int weight, int64_t* d_stats,
+                 int64_t* d_len_counts, void* stream);
+
+/* Same with HOST columns: chunked, double-buffered H2D overlapped with the kernel;
+ * h_stats / h_len_counts receive the totals (they are overwritten, not added to).
+ * Returns after the work has completed. */
+int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_ref_id,
+                      const int32_t* h_first, const int32_t* h_last, const uint16_t* h_mlen,
+                      const uint16_t* h_flag, const uint8_t* h_mapq, const uint8_t* h_nh,
+                      int protocol, int sorted_hint, int64_t* h_stats, int64_t* h_len_counts);
+
+int rt_clear_coverage(rt_ctx* ctx, int32_t* d_cov, void* stream);
+
+/* ---- index: ORF.from_string rows (orf.py:121-182) packed as CSR; kept resident on the device ---- */
+int rt_set_index(rt_ctx* ctx, int64_t n_orf, const int64_t* h_exon_ptr, const int32_t* h_exon_start,
+                 const int32_t* h_exon_end, const int32_t* h_orf_contig, const uint8_t* h_orf_strand);
+int64_t rt_index_orfs(const rt_ctx* ctx);
+/* algorithmic bytes of scoring ORFs [lo, hi): sum of 4L + 8E + 42 */
+int64_t rt_index_score_bytes(const rt_ctx* ctx, int64_t orf_lo, int64_t orf_hi);
+/* total profile length (nt) of ORFs [lo, hi) */
+int64_t rt_index_total_nt(const rt_ctx* ctx, int64_t orf_lo, int64_t orf_hi);
+/* cut [0, n_orf) into n_shards contiguous, byte-balanced ranges; h_bounds has n_shards+1 entries */
+int rt_shard_bounds(const rt_ctx* ctx, int n_shards, int64_t* h_bounds);
+
+/*
+ * ---- K2+K3: per-ORF body of export_orf_coverages (detect_orfs.py:274-299):
+ *      orf_coverage (:134-203) + phasescore (statistics.py:48-115) +
+ *      collapse_coverage_to_codon (common.py:164-180) + status predicate.
+ * Scores ORFs [orf_lo, orf_hi); output element k belongs to ORF orf_lo + k.
+ */
+int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi,
+             const rt_score_params* params, const rt_score_out* d_out, void* stream);
+/* Same with HOST result columns (device scratch is owned by the ctx; D2H inside). */
+int rt_score_host(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi,
+                  const rt_score_params* params, const rt_score_out* h_out);
+
+/*
+ * ---- K4: the `profile` column (detect_orfs.py:322): orf_coverage of selected ORFs,
+ *      written at d_out[d_out_ptr[i] ...] (lengths as reported by rt_score).
+ */
+int rt_gather_profiles(rt_ctx* ctx, const int32_t* d_cov, int64_t n_sel, const int64_t* d_orf_ids,
+                       const int64_t* d_out_ptr, int32_t* d_out, void* stream);
+
+/* number of kernel launches issued through this ctx so far (bench.py's gpu_launches) */
+int64_t rt_launch_count(const rt_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIBOTRICER_B200_H */

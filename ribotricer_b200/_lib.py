@@ -1,0 +1,96 @@
+"""ctypes binding of libribotricer_b200.so (C ABI: include/ribotricer_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no B200 is
+visible, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libribotricer_b200.so")
+
+RT_LEN_TABLE = 65536
+RT_LEN_UNUSED = -1
+RT_LEN_FILTERED = -2
+RT_PROTOCOL_FORWARD, RT_PROTOCOL_REVERSE, RT_PROTOCOL_NONE = 0, 1, 2
+ST_NAMES = ("total", "qcfail", "duplicate", "secondary", "unmapped", "multi", "valid", "oob", "badref")
+RT_N_STATS = len(ST_NAMES)
+
+EXPORTS = (
+    "rt_abi_version", "rt_last_error", "rt_create", "rt_destroy", "rt_device_count",
+    "rt_set_genome", "rt_plane_elems", "rt_get_contig_base", "rt_set_length_table",
+    "rt_bin_reads", "rt_bin_reads_host", "rt_clear_coverage", "rt_set_index", "rt_index_orfs",
+    "rt_index_score_bytes", "rt_index_total_nt", "rt_shard_bounds", "rt_score", "rt_score_host",
+    "rt_gather_profiles", "rt_launch_count",
+)
+
+
+class ScoreParams(C.Structure):
+    _fields_ = [("phase_score_cutoff", C.c_double), ("min_valid_codons", C.c_double),
+                ("min_reads_per_codon", C.c_double), ("min_valid_codons_ratio", C.c_double),
+                ("min_density_over_orf", C.c_double)]
+
+
+class ScoreOut(C.Structure):
+    _fields_ = [("score", C.c_void_p), ("valid", C.c_void_p), ("count", C.c_void_p),
+                ("length", C.c_void_p), ("min_codon", C.c_void_p), ("status", C.c_void_p),
+                ("frame_K", C.c_void_p), ("frame_s", C.c_void_p)]
+
+
+class RtError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the C-ABI library; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RtError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C ribotricer_b200/csrc`. ribotricer_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    lib.rt_abi_version.restype = i32
+    lib.rt_last_error.restype = C.c_char_p
+    lib.rt_last_error.argtypes = [vp]
+    lib.rt_create.argtypes = [i32, C.POINTER(vp)]
+    lib.rt_destroy.argtypes = [vp]
+    lib.rt_destroy.restype = None
+    lib.rt_set_genome.argtypes = [vp, i32, vp, i32]
+    lib.rt_plane_elems.argtypes = [vp]
+    lib.rt_plane_elems.restype = i64
+    lib.rt_get_contig_base.argtypes = [vp, vp]
+    lib.rt_set_length_table.argtypes = [vp, vp]
+    lib.rt_bin_reads.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.rt_bin_reads_host.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
+    lib.rt_clear_coverage.argtypes = [vp, vp, vp]
+    lib.rt_set_index.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    lib.rt_index_orfs.argtypes = [vp]
+    lib.rt_index_orfs.restype = i64
+    lib.rt_index_score_bytes.argtypes = [vp, i64, i64]
+    lib.rt_index_score_bytes.restype = i64
+    lib.rt_index_total_nt.argtypes = [vp, i64, i64]
+    lib.rt_index_total_nt.restype = i64
+    lib.rt_shard_bounds.argtypes = [vp, i32, vp]
+    lib.rt_score.argtypes = [vp, vp, i64, i64, C.POINTER(ScoreParams), C.POINTER(ScoreOut), vp]
+    lib.rt_score_host.argtypes = [vp, vp, i64, i64, C.POINTER(ScoreParams), C.POINTER(ScoreOut)]
+    lib.rt_gather_profiles.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.rt_launch_count.argtypes = [vp]
+    lib.rt_launch_count.restype = i64
+    if lib.rt_abi_version() != 1:
+        raise RtError(f"ABI mismatch: library reports {lib.rt_abi_version()}, binding expects 1")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, ctx=None):
+    if rc != 0:
+        msg = load().rt_last_error(ctx)
+        raise RtError(f"ribotricer_b200 error {rc}: {msg.decode() if msg else '?'}")

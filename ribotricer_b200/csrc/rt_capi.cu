@@ -1,0 +1,514 @@
+// rt_capi.cu -- C ABI (include/ribotricer_b200.h) over the sm_100a kernels.
+// Host-side state: genome layout, device-resident CSR index, scratch for the host-buffer calls.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rt_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct rt_ctx {
+    int device = 0;
+    int n_sm = 0;
+    std::string err;
+    int64_t launches = 0;
+
+    // genome
+    int n_contig = 0;
+    int pad = 0;
+    int64_t plane = 0;
+    std::vector<int64_t> contig_len, contig_base;
+    long long* d_contig_len = nullptr;
+    long long* d_contig_base = nullptr;
+
+    // read-length table
+    int32_t* d_len_table = nullptr;
+    bool have_len_table = false;
+
+    // index
+    int64_t n_orf = 0;
+    uint64_t* d_orf_desc = nullptr;
+    uint64_t* d_exon_entries = nullptr;
+    std::vector<int64_t> bytes_prefix;  // n_orf + 1: prefix of 4L + 8E + 42
+    std::vector<int64_t> nt_prefix;     // n_orf + 1: prefix of L
+    unsigned long long* d_work_counter = nullptr;
+
+    // scratch for the host-buffer entry points
+    DevBuf read_slot[2];
+    cudaStream_t slot_stream[2] = {nullptr, nullptr};
+    DevBuf stats_buf, score_buf;
+};
+
+namespace {
+
+int fail(rt_ctx* ctx, int code, const char* fmt, ...) {
+    char msg[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(msg, sizeof msg, fmt, ap);
+    va_end(ap);
+    g_last_error = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define RT_CUDA(ctx, call)                                                                        \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? RT_ENOMEM : RT_ECUDA,             \
+                        "%s failed: %s", #call, cudaGetErrorString(e__));                         \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+constexpr size_t kReadBytes = 4 + 4 + 4 + 2 + 2 + 1 + 1;
+constexpr int64_t kHostChunkReads = 4 << 20;
+
+}  // namespace
+
+extern "C" {
+
+int rt_abi_version(void) { return RT_ABI_VERSION; }
+
+const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int rt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int rt_create(int device, rt_ctx** out) {
+    if (!out) return fail(nullptr, RT_EINVAL, "rt_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, RT_ECUDA, "rt_create: no CUDA device (%s); there is no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, RT_EINVAL, "rt_create: device %d out of range [0,%d)", device, n);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    RT_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, RT_ECUDA, "rt_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    rt_ctx* ctx = new rt_ctx();
+    ctx->device = device;
+    ctx->n_sm = prop.multiProcessorCount;
+    if (cudaMalloc(&ctx->d_work_counter, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_len_table, sizeof(int32_t) * RT_LEN_TABLE) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, RT_ENOMEM, "rt_create: cudaMalloc failed");
+    }
+    *out = ctx;
+    return RT_OK;
+}
+
+void rt_destroy(rt_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    cudaFree(ctx->d_contig_len);
+    cudaFree(ctx->d_contig_base);
+    cudaFree(ctx->d_len_table);
+    cudaFree(ctx->d_orf_desc);
+    cudaFree(ctx->d_exon_entries);
+    cudaFree(ctx->d_work_counter);
+    for (int s = 0; s < 2; ++s) {
+        ctx->read_slot[s].release();
+        if (ctx->slot_stream[s]) cudaStreamDestroy(ctx->slot_stream[s]);
+    }
+    ctx->stats_buf.release();
+    ctx->score_buf.release();
+    delete ctx;
+}
+
+int64_t rt_launch_count(const rt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------ genome
+int rt_set_genome(rt_ctx* ctx, int n_contig, const int64_t* h_contig_len, int pad) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_set_genome: ctx is NULL");
+    if (n_contig < 0 || (n_contig > 0 && !h_contig_len) || pad < 0 || pad > (1 << 20))
+        return fail(ctx, RT_EINVAL, "rt_set_genome: bad arguments (n_contig=%d pad=%d)", n_contig, pad);
+    DeviceGuard guard(ctx->device);
+    ctx->n_contig = n_contig;
+    ctx->pad = pad;
+    ctx->contig_len.assign(h_contig_len, h_contig_len + n_contig);
+    ctx->contig_base.assign(n_contig, 0);
+    int64_t at = 0;
+    for (int c = 0; c < n_contig; ++c) {
+        if (h_contig_len[c] < 0 || h_contig_len[c] > 0x7fffffff - 2ll * pad - 64)
+            return fail(ctx, RT_EINVAL, "rt_set_genome: contig %d length %lld unsupported", c, (long long)h_contig_len[c]);
+        ctx->contig_base[c] = at;
+        at += (h_contig_len[c] + 2ll * pad + 1 + 31) / 32 * 32;
+    }
+    ctx->plane = n_contig ? at : 32;
+    if (2 * ctx->plane >= (int64_t)rt::kZeroOff)
+        return fail(ctx, RT_EINVAL, "rt_set_genome: genome too large for the 40-bit slot encoding");
+    cudaFree(ctx->d_contig_len);
+    cudaFree(ctx->d_contig_base);
+    ctx->d_contig_len = ctx->d_contig_base = nullptr;
+    size_t bytes = sizeof(long long) * std::max(1, n_contig);
+    RT_CUDA(ctx, cudaMalloc(&ctx->d_contig_len, bytes));
+    RT_CUDA(ctx, cudaMalloc(&ctx->d_contig_base, bytes));
+    if (n_contig) {
+        RT_CUDA(ctx, cudaMemcpy(ctx->d_contig_len, ctx->contig_len.data(), bytes, cudaMemcpyHostToDevice));
+        RT_CUDA(ctx, cudaMemcpy(ctx->d_contig_base, ctx->contig_base.data(), bytes, cudaMemcpyHostToDevice));
+    }
+    // a new genome invalidates the index encoding
+    ctx->n_orf = 0;
+    return RT_OK;
+}
+
+int64_t rt_plane_elems(const rt_ctx* ctx) { return ctx ? ctx->plane : 0; }
+
+int rt_get_contig_base(const rt_ctx* ctx, int64_t* h_out) {
+    if (!ctx || !h_out) return RT_EINVAL;
+    std::copy(ctx->contig_base.begin(), ctx->contig_base.end(), h_out);
+    return RT_OK;
+}
+
+int rt_set_length_table(rt_ctx* ctx, const int32_t* h_len_table) {
+    if (!ctx || !h_len_table) return fail(ctx, RT_EINVAL, "rt_set_length_table: NULL argument");
+    DeviceGuard guard(ctx->device);
+    for (int i = 0; i < RT_LEN_TABLE; ++i)
+        if (h_len_table[i] < RT_LEN_FILTERED || h_len_table[i] > ctx->pad)
+            return fail(ctx, RT_EINVAL, "rt_set_length_table: entry %d = %d outside [-2, pad=%d]", i,
+                        h_len_table[i], ctx->pad);
+    RT_CUDA(ctx, cudaMemcpy(ctx->d_len_table, h_len_table, sizeof(int32_t) * RT_LEN_TABLE, cudaMemcpyHostToDevice));
+    ctx->have_len_table = true;
+    return RT_OK;
+}
+
+int rt_clear_coverage(rt_ctx* ctx, int32_t* d_cov, void* stream) {
+    if (!ctx || !d_cov) return fail(ctx, RT_EINVAL, "rt_clear_coverage: NULL argument");
+    if (ctx->plane == 0) return fail(ctx, RT_ESTATE, "rt_clear_coverage: call rt_set_genome first");
+    DeviceGuard guard(ctx->device);
+    RT_CUDA(ctx, cudaMemsetAsync(d_cov, 0, sizeof(int32_t) * 2 * (size_t)ctx->plane, (cudaStream_t)stream));
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------ K1
+int rt_bin_reads(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* d_ref_id, const int32_t* d_first,
+                 const int32_t* d_last, const uint16_t* d_mlen, const uint16_t* d_flag, const uint8_t* d_mapq,
+                 const uint8_t* d_nh, int protocol, int sorted_hint, int weight, int64_t* d_stats,
+                 int64_t* d_len_counts, void* stream) {
+    (void)sorted_hint;
+    if (weight != 1 && weight != -1) return fail(ctx, RT_EINVAL, "rt_bin_reads: weight must be +1 or -1");
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_bin_reads: ctx is NULL");
+    if (ctx->plane == 0) return fail(ctx, RT_ESTATE, "rt_bin_reads: call rt_set_genome first");
+    if (!ctx->have_len_table) return fail(ctx, RT_ESTATE, "rt_bin_reads: call rt_set_length_table first");
+    if (n < 0 || !d_cov || !d_stats || !d_len_counts ||
+        (n > 0 && (!d_ref_id || !d_first || !d_last || !d_mlen || !d_flag || !d_mapq || !d_nh)))
+        return fail(ctx, RT_EINVAL, "rt_bin_reads: NULL column or negative n");
+    if (n == 0) return RT_OK;
+    DeviceGuard guard(ctx->device);
+    rt::BinArgs a;
+    a.cov = d_cov;
+    a.ref_id = d_ref_id; a.first = d_first; a.last = d_last; a.mlen = d_mlen; a.flag = d_flag;
+    a.mapq = d_mapq; a.nh = d_nh;
+    a.n = n;
+    a.protocol = protocol;
+    a.weight = weight;
+    a.len_table = ctx->d_len_table;
+    a.contig_base = ctx->d_contig_base;
+    a.contig_len = ctx->d_contig_len;
+    a.n_contig = ctx->n_contig;
+    a.pad = ctx->pad;
+    a.plane = ctx->plane;
+    a.stats = reinterpret_cast<unsigned long long*>(d_stats);
+    a.len_counts = reinterpret_cast<unsigned long long*>(d_len_counts);
+    const int64_t per_block = (int64_t)rt::kBinThreads * rt::kBinReadsPerThread;
+    const int64_t blocks = (n + per_block - 1) / per_block;
+    if (blocks > 0x7fffffff) return fail(ctx, RT_EINVAL, "rt_bin_reads: n too large for one launch");
+    rt::bin_psites_kernel<<<(unsigned)blocks, rt::kBinThreads, 0, (cudaStream_t)stream>>>(a);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_ref_id, const int32_t* h_first,
+                      const int32_t* h_last, const uint16_t* h_mlen, const uint16_t* h_flag,
+                      const uint8_t* h_mapq, const uint8_t* h_nh, int protocol, int sorted_hint,
+                      int64_t* h_stats, int64_t* h_len_counts) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_bin_reads_host: ctx is NULL");
+    if (!h_stats || !h_len_counts) return fail(ctx, RT_EINVAL, "rt_bin_reads_host: NULL output");
+    DeviceGuard guard(ctx->device);
+    const size_t acc_bytes = sizeof(int64_t) * (RT_N_STATS + RT_LEN_TABLE);
+    RT_CUDA(ctx, ctx->stats_buf.reserve(acc_bytes));
+    int64_t* d_stats = static_cast<int64_t*>(ctx->stats_buf.p);
+    int64_t* d_len_counts = d_stats + RT_N_STATS;
+    for (int s = 0; s < 2; ++s)
+        if (!ctx->slot_stream[s]) RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking));
+    RT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, acc_bytes, ctx->slot_stream[0]));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[0]));
+    const int64_t chunk = std::min<int64_t>(kHostChunkReads, std::max<int64_t>(n, 1));
+    // per-slot layout: 4-byte columns first so that every column stays naturally aligned
+    const size_t slot_bytes = (size_t)chunk * kReadBytes + 64;
+    int slot = 0;
+    for (int64_t at = 0; at < n; at += chunk, slot ^= 1) {
+        const int64_t m = std::min(chunk, n - at);
+        RT_CUDA(ctx, ctx->read_slot[slot].reserve(slot_bytes));
+        char* base = static_cast<char*>(ctx->read_slot[slot].p);
+        int32_t* d_ref = reinterpret_cast<int32_t*>(base);
+        int32_t* d_first = d_ref + chunk;
+        int32_t* d_last = d_first + chunk;
+        uint16_t* d_mlen = reinterpret_cast<uint16_t*>(d_last + chunk);
+        uint16_t* d_flag = d_mlen + chunk;
+        uint8_t* d_mapq = reinterpret_cast<uint8_t*>(d_flag + chunk);
+        uint8_t* d_nh = d_mapq + chunk;
+        cudaStream_t st = ctx->slot_stream[slot];   // stream order protects the slot's previous use
+        RT_CUDA(ctx, cudaMemcpyAsync(d_ref, h_ref_id + at, 4 * m, cudaMemcpyHostToDevice, st));
+        RT_CUDA(ctx, cudaMemcpyAsync(d_first, h_first + at, 4 * m, cudaMemcpyHostToDevice, st));
+        RT_CUDA(ctx, cudaMemcpyAsync(d_last, h_last + at, 4 * m, cudaMemcpyHostToDevice, st));
+        RT_CUDA(ctx, cudaMemcpyAsync(d_mlen, h_mlen + at, 2 * m, cudaMemcpyHostToDevice, st));
+        RT_CUDA(ctx, cudaMemcpyAsync(d_flag, h_flag + at, 2 * m, cudaMemcpyHostToDevice, st));
+        RT_CUDA(ctx, cudaMemcpyAsync(d_mapq, h_mapq + at, m, cudaMemcpyHostToDevice, st));
+        RT_CUDA(ctx, cudaMemcpyAsync(d_nh, h_nh + at, m, cudaMemcpyHostToDevice, st));
+        int rc = rt_bin_reads(ctx, d_cov, m, d_ref, d_first, d_last, d_mlen, d_flag, d_mapq, d_nh, protocol,
+                              sorted_hint, 1, d_stats, d_len_counts, st);
+        if (rc != RT_OK) return rc;
+    }
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[0]));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[1]));
+    RT_CUDA(ctx, cudaMemcpy(h_stats, d_stats, sizeof(int64_t) * RT_N_STATS, cudaMemcpyDeviceToHost));
+    RT_CUDA(ctx, cudaMemcpy(h_len_counts, d_len_counts, sizeof(int64_t) * RT_LEN_TABLE, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------ index
+int rt_set_index(rt_ctx* ctx, int64_t n_orf, const int64_t* h_exon_ptr, const int32_t* h_exon_start,
+                 const int32_t* h_exon_end, const int32_t* h_orf_contig, const uint8_t* h_orf_strand) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_set_index: ctx is NULL");
+    if (ctx->plane == 0) return fail(ctx, RT_ESTATE, "rt_set_index: call rt_set_genome first");
+    if (n_orf < 0 || !h_exon_ptr || (n_orf > 0 && (!h_orf_contig || !h_orf_strand)))
+        return fail(ctx, RT_EINVAL, "rt_set_index: NULL argument");
+    DeviceGuard guard(ctx->device);
+    const int64_t max_piece = (int64_t)rt::kLenMask;
+    std::vector<uint64_t> desc((size_t)n_orf);
+    std::vector<uint64_t> entries;
+    entries.reserve((size_t)(h_exon_ptr[n_orf] - h_exon_ptr[0]) + 16);
+    ctx->bytes_prefix.assign((size_t)n_orf + 1, 0);
+    ctx->nt_prefix.assign((size_t)n_orf + 1, 0);
+    auto push = [&](int64_t off, int64_t len) {   // off < 0: zeros
+        while (len > 0) {
+            const int64_t piece = std::min(len, max_piece);
+            entries.push_back(((off < 0 ? rt::kZeroOff : (uint64_t)off) << rt::kLenBits) | (uint64_t)piece);
+            if (off >= 0) off += piece;
+            len -= piece;
+        }
+    };
+    for (int64_t o = 0; o < n_orf; ++o) {
+        const int64_t e0 = h_exon_ptr[o], e1 = h_exon_ptr[o + 1];
+        if (e1 < e0) return fail(ctx, RT_EINVAL, "rt_set_index: exon_ptr not monotone at ORF %lld", (long long)o);
+        const int c = h_orf_contig[o];
+        const int s = h_orf_strand[o];
+        const bool covered = c >= 0 && c < ctx->n_contig && (s == 0 || s == 1);
+        const size_t begin = entries.size();
+        int64_t L = 0;
+        for (int64_t e = e0; e < e1; ++e) {
+            const int64_t st = h_exon_start[e], en = h_exon_end[e];
+            if (en < st) return fail(ctx, RT_EINVAL, "rt_set_index: ORF %lld has an empty interval %lld-%lld",
+                                     (long long)o, (long long)st, (long long)en);
+            L += en - st + 1;
+            if (!covered) {
+                push(-1, en - st + 1);
+                continue;
+            }
+            // positions outside the padded contig have no slot: they read as 0 (missing dict key)
+            const int64_t lo = 1 - ctx->pad, hi = ctx->contig_len[c] + ctx->pad;
+            const int64_t a = std::max(st, lo), b = std::min(en, hi);
+            if (a > b) {
+                push(-1, en - st + 1);
+                continue;
+            }
+            if (st < a) push(-1, a - st);
+            push((int64_t)s * ctx->plane + ctx->contig_base[c] + ctx->pad + a, b - a + 1);
+            if (b < en) push(-1, en - b);
+        }
+        if (L > 0x7fffffff) return fail(ctx, RT_EINVAL, "rt_set_index: ORF %lld longer than 2^31-1 nt", (long long)o);
+        const size_t cnt = entries.size() - begin;
+        if (cnt > (size_t)rt::kMaxEntriesPerOrf)
+            return fail(ctx, RT_EINVAL, "rt_set_index: ORF %lld has too many intervals", (long long)o);
+        if (begin >= rt::kBeginMask) return fail(ctx, RT_EINVAL, "rt_set_index: index too large");
+        desc[o] = (uint64_t)begin | ((uint64_t)cnt << 40) | ((uint64_t)(s == 1) << 63);
+        ctx->nt_prefix[o + 1] = ctx->nt_prefix[o] + L;
+        ctx->bytes_prefix[o + 1] = ctx->bytes_prefix[o] + 4 * L + 8 * (e1 - e0) + 42;
+    }
+    cudaFree(ctx->d_orf_desc);
+    cudaFree(ctx->d_exon_entries);
+    ctx->d_orf_desc = ctx->d_exon_entries = nullptr;
+    ctx->n_orf = 0;
+    RT_CUDA(ctx, cudaMalloc(&ctx->d_orf_desc, sizeof(uint64_t) * std::max<size_t>(1, desc.size())));
+    RT_CUDA(ctx, cudaMalloc(&ctx->d_exon_entries, sizeof(uint64_t) * std::max<size_t>(1, entries.size())));
+    if (!desc.empty())
+        RT_CUDA(ctx, cudaMemcpy(ctx->d_orf_desc, desc.data(), sizeof(uint64_t) * desc.size(), cudaMemcpyHostToDevice));
+    if (!entries.empty())
+        RT_CUDA(ctx, cudaMemcpy(ctx->d_exon_entries, entries.data(), sizeof(uint64_t) * entries.size(),
+                                cudaMemcpyHostToDevice));
+    ctx->n_orf = n_orf;
+    return RT_OK;
+}
+
+int64_t rt_index_orfs(const rt_ctx* ctx) { return ctx ? ctx->n_orf : 0; }
+
+int64_t rt_index_score_bytes(const rt_ctx* ctx, int64_t lo, int64_t hi) {
+    if (!ctx || lo < 0 || hi > ctx->n_orf || lo > hi) return -1;
+    return ctx->bytes_prefix[hi] - ctx->bytes_prefix[lo];
+}
+
+int64_t rt_index_total_nt(const rt_ctx* ctx, int64_t lo, int64_t hi) {
+    if (!ctx || lo < 0 || hi > ctx->n_orf || lo > hi) return -1;
+    return ctx->nt_prefix[hi] - ctx->nt_prefix[lo];
+}
+
+int rt_shard_bounds(const rt_ctx* ctx, int n_shards, int64_t* h_bounds) {
+    if (!ctx || n_shards < 1 || !h_bounds) return RT_EINVAL;
+    const int64_t total = ctx->bytes_prefix.empty() ? 0 : ctx->bytes_prefix.back();
+    h_bounds[0] = 0;
+    for (int s = 1; s < n_shards; ++s) {
+        const int64_t target = (int64_t)((__int128)total * s / n_shards);
+        auto it = std::lower_bound(ctx->bytes_prefix.begin(), ctx->bytes_prefix.end(), target);
+        h_bounds[s] = std::max<int64_t>(h_bounds[s - 1], it - ctx->bytes_prefix.begin());
+        if (h_bounds[s] > ctx->n_orf) h_bounds[s] = ctx->n_orf;
+    }
+    h_bounds[n_shards] = ctx->n_orf;
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------ K2+K3
+int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, const rt_score_params* params,
+             const rt_score_out* d_out, void* stream) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_score: ctx is NULL");
+    if (!d_cov || !params || !d_out) return fail(ctx, RT_EINVAL, "rt_score: NULL argument");
+    if (orf_lo < 0 || orf_hi > ctx->n_orf || orf_lo > orf_hi)
+        return fail(ctx, RT_EINVAL, "rt_score: ORF range [%lld,%lld) outside the index [0,%lld)", (long long)orf_lo,
+                    (long long)orf_hi, (long long)ctx->n_orf);
+    if (orf_lo == orf_hi) return RT_OK;
+    if (!d_out->score || !d_out->valid || !d_out->count || !d_out->length)
+        return fail(ctx, RT_EINVAL, "rt_score: score/valid/count/length columns are required");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    RT_CUDA(ctx, cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(unsigned long long), st));
+    rt::ScoreArgs a;
+    a.cov = d_cov;
+    a.orf_desc = ctx->d_orf_desc;
+    a.exon_entries = ctx->d_exon_entries;
+    a.orf_lo = orf_lo;
+    a.orf_hi = orf_hi;
+    a.work_counter = ctx->d_work_counter;
+    a.prm = *params;
+    a.out = *d_out;
+    int per_sm = 0;
+    RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rt::score_orfs_kernel, rt::kScoreWarps * 32, 0));
+    per_sm = std::max(per_sm, 1);
+    const int64_t want = (orf_hi - orf_lo + rt::kScoreWarps * rt::kFetchBatch - 1) / (rt::kScoreWarps * rt::kFetchBatch);
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->n_sm * per_sm));
+    rt::score_orfs_kernel<<<grid, rt::kScoreWarps * 32, 0, st>>>(a);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_score_host(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, const rt_score_params* params,
+                  const rt_score_out* h_out) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_score_host: ctx is NULL");
+    if (!h_out || !params) return fail(ctx, RT_EINVAL, "rt_score_host: NULL argument");
+    if (orf_lo < 0 || orf_hi > ctx->n_orf || orf_lo > orf_hi) return fail(ctx, RT_EINVAL, "rt_score_host: bad ORF range");
+    const int64_t n = orf_hi - orf_lo;
+    if (n == 0) return RT_OK;
+    DeviceGuard guard(ctx->device);
+    // one scratch allocation, 8-byte columns first
+    const size_t bytes = (size_t)n * (8 + 8 + 24 + 4 + 4 + 4 + 12 + 1) + 256;
+    RT_CUDA(ctx, ctx->score_buf.reserve(bytes));
+    char* p = static_cast<char*>(ctx->score_buf.p);
+    rt_score_out d{};
+    d.score = reinterpret_cast<double*>(p); p += 8 * n;
+    d.count = reinterpret_cast<int64_t*>(p); p += 8 * n;
+    d.frame_s = h_out->frame_s ? reinterpret_cast<double*>(p) : nullptr; p += 24 * n;
+    d.valid = reinterpret_cast<int32_t*>(p); p += 4 * n;
+    d.length = reinterpret_cast<int32_t*>(p); p += 4 * n;
+    d.min_codon = reinterpret_cast<int32_t*>(p); p += 4 * n;
+    d.frame_K = h_out->frame_K ? reinterpret_cast<int32_t*>(p) : nullptr; p += 12 * n;
+    d.status = reinterpret_cast<uint8_t*>(p);
+    int rc = rt_score(ctx, d_cov, orf_lo, orf_hi, params, &d, nullptr);
+    if (rc != RT_OK) return rc;
+    auto back = [&](void* h, const void* dv, size_t b) -> cudaError_t {
+        return h ? cudaMemcpyAsync(h, dv, b, cudaMemcpyDeviceToHost, nullptr) : cudaSuccess;
+    };
+    RT_CUDA(ctx, back(h_out->score, d.score, 8 * n));
+    RT_CUDA(ctx, back(h_out->count, d.count, 8 * n));
+    RT_CUDA(ctx, back(h_out->valid, d.valid, 4 * n));
+    RT_CUDA(ctx, back(h_out->length, d.length, 4 * n));
+    RT_CUDA(ctx, back(h_out->min_codon, d.min_codon, 4 * n));
+    RT_CUDA(ctx, back(h_out->status, d.status, n));
+    if (d.frame_K) RT_CUDA(ctx, back(h_out->frame_K, d.frame_K, 12 * n));
+    if (d.frame_s) RT_CUDA(ctx, back(h_out->frame_s, d.frame_s, 24 * n));
+    RT_CUDA(ctx, cudaStreamSynchronize(nullptr));
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------ K4
+int rt_gather_profiles(rt_ctx* ctx, const int32_t* d_cov, int64_t n_sel, const int64_t* d_orf_ids,
+                       const int64_t* d_out_ptr, int32_t* d_out, void* stream) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_gather_profiles: ctx is NULL");
+    if (n_sel < 0 || !d_cov || (n_sel > 0 && (!d_orf_ids || !d_out_ptr || !d_out)))
+        return fail(ctx, RT_EINVAL, "rt_gather_profiles: NULL argument");
+    if (ctx->n_orf == 0 && n_sel > 0) return fail(ctx, RT_ESTATE, "rt_gather_profiles: no index");
+    if (n_sel == 0) return RT_OK;
+    DeviceGuard guard(ctx->device);
+    rt::GatherArgs a;
+    a.cov = d_cov;
+    a.orf_desc = ctx->d_orf_desc;
+    a.exon_entries = ctx->d_exon_entries;
+    a.orf_ids = d_orf_ids;
+    a.out_ptr = d_out_ptr;
+    a.out = d_out;
+    a.n_sel = n_sel;
+    const int64_t want = (n_sel + 7) / 8;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->n_sm * 8));
+    rt::gather_profiles_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+    return RT_OK;
+}
+
+}  // extern "C"

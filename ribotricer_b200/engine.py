@@ -1,0 +1,289 @@
+"""Device-side engine: one ``Engine`` per (process, GPU).
+
+Thin host layer over the C ABI (``include/ribotricer_b200.h``).  PyTorch is
+used only as plumbing: it owns the device buffers (coverage planes, read
+columns, result columns) and the CUDA stream; every computation on the path is
+one of the hand-written sm_100a kernels in ``csrc/rt_kernels.cuh``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .const import (CUTOFF, DEFAULT_PAD, MINIMUM_DENSITY_OVER_ORF, MINIMUM_READS_PER_CODON,
+                    MINIMUM_VALID_CODONS, MINIMUM_VALID_CODONS_RATIO)
+
+READ_COLUMNS = (("ref_id", np.int32), ("first", np.int32), ("last", np.int32), ("mlen", np.uint16),
+                ("flag", np.uint16), ("mapq", np.uint8), ("nh", np.uint8))
+READ_BYTES = sum(np.dtype(dt).itemsize for _, dt in READ_COLUMNS)   # 18 B / read
+
+PROTOCOLS = {"forward": _lib.RT_PROTOCOL_FORWARD, "reverse": _lib.RT_PROTOCOL_REVERSE}
+
+
+def protocol_code(protocol) -> int:
+    """bam.py:105,118 only know 'forward' and 'reverse'; anything else stores no read."""
+    if isinstance(protocol, (int, np.integer)):
+        return int(protocol)
+    return PROTOCOLS.get(protocol, _lib.RT_PROTOCOL_NONE)
+
+
+def make_len_table(psite_offsets=None, read_lengths=None) -> np.ndarray:
+    """length -> P-site offset / RT_LEN_UNUSED / RT_LEN_FILTERED.
+
+    ``read_lengths`` is split_bam's filter (bam.py:101); ``psite_offsets`` are
+    the lengths merge_read_lengths keeps (detect_orfs.py:74).
+    """
+    t = np.full(_lib.RT_LEN_TABLE, _lib.RT_LEN_UNUSED, dtype=np.int32)
+    if read_lengths is not None:
+        t[:] = _lib.RT_LEN_FILTERED
+        for length in read_lengths:
+            if 0 <= int(length) < _lib.RT_LEN_TABLE:
+                t[int(length)] = _lib.RT_LEN_UNUSED
+    for length, off in (psite_offsets or {}).items():
+        if 0 <= int(length) < _lib.RT_LEN_TABLE and t[int(length)] != _lib.RT_LEN_FILTERED:
+            t[int(length)] = int(off)
+    return t
+
+
+@dataclass
+class ScoreParams:
+    phase_score_cutoff: float = CUTOFF
+    min_valid_codons: float = MINIMUM_VALID_CODONS
+    min_reads_per_codon: float = MINIMUM_READS_PER_CODON
+    min_valid_codons_ratio: float = MINIMUM_VALID_CODONS_RATIO
+    min_density_over_orf: float = MINIMUM_DENSITY_OVER_ORF
+
+    def as_c(self) -> _lib.ScoreParams:
+        return _lib.ScoreParams(float(self.phase_score_cutoff), float(self.min_valid_codons),
+                                float(self.min_reads_per_codon), float(self.min_valid_codons_ratio),
+                                float(self.min_density_over_orf))
+
+
+def _np_ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """Owns one ``rt_ctx``.  Fails loudly without the library or a B200."""
+
+    def __init__(self, device: int = 0):
+        import torch
+
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.RtError("ribotricer_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        torch.cuda.set_device(self.device)
+        ctx = C.c_void_p()
+        _lib.check(self.lib.rt_create(self.device_index, C.byref(ctx)))
+        self.ctx = ctx
+        self.contig_names: list[str] = []
+        self.contig_len = np.zeros(0, np.int64)
+        self.contig_base = np.zeros(0, np.int64)
+        self.pad = 0
+        self.plane = 0
+        self.n_orf = 0
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.rt_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -------------------------------------------------------------- helpers
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc):
+        _lib.check(rc, self.ctx)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.rt_launch_count(self.ctx))
+
+    # --------------------------------------------------------------- genome
+    def set_genome(self, contig_names, contig_len, pad: int = DEFAULT_PAD):
+        self.contig_names = [str(c) for c in contig_names]
+        self.contig_len = np.ascontiguousarray(contig_len, dtype=np.int64)
+        if len(self.contig_names) != len(self.contig_len):
+            raise ValueError("contig_names and contig_len differ in length")
+        self.pad = int(pad)
+        self._check(self.lib.rt_set_genome(self.ctx, len(self.contig_len), _np_ptr(self.contig_len), self.pad))
+        self.plane = int(self.lib.rt_plane_elems(self.ctx))
+        self.contig_base = np.zeros(len(self.contig_len), np.int64)
+        self._check(self.lib.rt_get_contig_base(self.ctx, _np_ptr(self.contig_base)))
+        self.n_orf = 0
+
+    def contig_id(self, name: str) -> int:
+        if not hasattr(self, "_contig_lut") or len(self._contig_lut) != len(self.contig_names):
+            self._contig_lut = {n: i for i, n in enumerate(self.contig_names)}
+        return self._contig_lut.get(name, -1)
+
+    def set_length_table(self, psite_offsets=None, read_lengths=None, table: np.ndarray | None = None):
+        t = make_len_table(psite_offsets, read_lengths) if table is None else np.ascontiguousarray(table, np.int32)
+        self._check(self.lib.rt_set_length_table(self.ctx, _np_ptr(t)))
+        self.len_table = t
+
+    def new_coverage(self):
+        """Zeroed int32[2 * plane] coverage buffer (plane 0 '+', plane 1 '-')."""
+        return self.torch.zeros(2 * self.plane, dtype=self.torch.int32, device=self.device)
+
+    def clear_coverage(self, cov):
+        self._check(self.lib.rt_clear_coverage(self.ctx, C.c_void_p(cov.data_ptr()), self._stream()))
+
+    # ---------------------------------------------------------------- index
+    def set_index(self, exon_ptr, exon_start, exon_end, orf_contig, orf_strand):
+        exon_ptr = np.ascontiguousarray(exon_ptr, np.int64)
+        exon_start = np.ascontiguousarray(exon_start, np.int32)
+        exon_end = np.ascontiguousarray(exon_end, np.int32)
+        orf_contig = np.ascontiguousarray(orf_contig, np.int32)
+        orf_strand = np.ascontiguousarray(orf_strand, np.uint8)
+        n = len(orf_contig)
+        if len(exon_ptr) != n + 1 or len(orf_strand) != n or len(exon_start) != len(exon_end) \
+                or (n and exon_ptr[-1] != len(exon_start)):
+            raise ValueError("inconsistent CSR index arrays")
+        self._check(self.lib.rt_set_index(self.ctx, n, _np_ptr(exon_ptr), _np_ptr(exon_start), _np_ptr(exon_end),
+                                          _np_ptr(orf_contig), _np_ptr(orf_strand)))
+        self.n_orf = n
+
+    def score_bytes(self, lo: int = 0, hi: int | None = None) -> int:
+        hi = self.n_orf if hi is None else hi
+        return int(self.lib.rt_index_score_bytes(self.ctx, lo, hi))
+
+    def total_nt(self, lo: int = 0, hi: int | None = None) -> int:
+        hi = self.n_orf if hi is None else hi
+        return int(self.lib.rt_index_total_nt(self.ctx, lo, hi))
+
+    def shard_bounds(self, n_shards: int) -> np.ndarray:
+        b = np.zeros(n_shards + 1, np.int64)
+        self._check(self.lib.rt_shard_bounds(self.ctx, int(n_shards), _np_ptr(b)))
+        return b
+
+    # ------------------------------------------------------------------- K1
+    def upload_reads(self, cols: dict) -> dict:
+        """Host columns -> device tensors (plumbing only)."""
+        t = self.torch
+        out = {}
+        for name, dt in READ_COLUMNS:
+            a = np.ascontiguousarray(cols[name], dtype=dt)
+            # torch has no uint16 arithmetic but can hold the bytes; view as int16 for transport
+            if dt == np.uint16:
+                out[name] = t.from_numpy(a.view(np.int16)).to(self.device)
+            else:
+                out[name] = t.from_numpy(a).to(self.device)
+        return out
+
+    def new_bin_accumulators(self):
+        t = self.torch
+        return (t.zeros(_lib.RT_N_STATS, dtype=t.int64, device=self.device),
+                t.zeros(_lib.RT_LEN_TABLE, dtype=t.int64, device=self.device))
+
+    def bin_reads_device(self, cov, dcols: dict, protocol, stats, len_counts, sorted_hint: bool = False,
+                         n: int | None = None, weight: int = 1):
+        """Enqueue K1 on device-resident read columns (no host sync).  ``weight=-1`` takes the same
+        reads out again (coverage, stats and length counts return to their previous values)."""
+        n = int(dcols["ref_id"].numel()) if n is None else int(n)
+        p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        self._check(self.lib.rt_bin_reads(
+            self.ctx, p(cov), n, p(dcols["ref_id"]), p(dcols["first"]), p(dcols["last"]), p(dcols["mlen"]),
+            p(dcols["flag"]), p(dcols["mapq"]), p(dcols["nh"]), protocol_code(protocol), int(sorted_hint),
+            int(weight), p(stats), p(len_counts), self._stream()))
+
+    def bin_reads_host(self, cov, cols: dict, protocol, sorted_hint: bool = False):
+        """K1 on HOST read columns (numpy or pinned torch CPU tensors): chunked H2D inside the call.
+
+        Returns ``(stats: dict, read_length_counts: np.ndarray[RT_LEN_TABLE])``.
+        """
+        ptrs, keep = [], []
+        n = None
+        for name, dt in READ_COLUMNS:
+            a = cols[name]
+            if hasattr(a, "data_ptr"):   # torch CPU tensor (possibly pinned)
+                if a.is_cuda or not a.is_contiguous() or a.element_size() != np.dtype(dt).itemsize:
+                    raise ValueError(f"column {name}: need a contiguous CPU tensor of {np.dtype(dt).itemsize}-byte items")
+                ptrs.append(C.c_void_p(a.data_ptr()))
+                m = a.numel()
+            else:
+                a = np.ascontiguousarray(a, dtype=dt)
+                ptrs.append(_np_ptr(a))
+                m = len(a)
+            keep.append(a)
+            if n is None:
+                n = m
+            elif n != m:
+                raise ValueError("read columns differ in length")
+        stats = np.zeros(_lib.RT_N_STATS, np.int64)
+        len_counts = np.zeros(_lib.RT_LEN_TABLE, np.int64)
+        self.torch.cuda.current_stream(self.device).synchronize()   # cov may have pending work on torch's stream
+        self._check(self.lib.rt_bin_reads_host(self.ctx, C.c_void_p(cov.data_ptr()), int(n), *ptrs,
+                                               protocol_code(protocol), int(sorted_hint), _np_ptr(stats),
+                                               _np_ptr(len_counts)))
+        return dict(zip(_lib.ST_NAMES, stats.tolist())), len_counts
+
+    # ---------------------------------------------------------------- K2+K3
+    def new_score_columns(self, n: int, diagnostics: bool = False) -> dict:
+        t = self.torch
+        d = self.device
+        cols = dict(score=t.empty(n, dtype=t.float64, device=d), valid=t.empty(n, dtype=t.int32, device=d),
+                    count=t.empty(n, dtype=t.int64, device=d), length=t.empty(n, dtype=t.int32, device=d),
+                    min_codon=t.empty(n, dtype=t.int32, device=d), status=t.empty(n, dtype=t.uint8, device=d))
+        if diagnostics:
+            cols["frame_K"] = t.empty((n, 3), dtype=t.int32, device=d)
+            cols["frame_s"] = t.empty((n, 3), dtype=t.float64, device=d)
+        return cols
+
+    def score_device(self, cov, out: dict, lo: int = 0, hi: int | None = None, params: ScoreParams | None = None):
+        """Enqueue the fused gather+score kernel; ``out`` are device columns (no host sync)."""
+        hi = self.n_orf if hi is None else hi
+        prm = (params or ScoreParams()).as_c()
+        o = _lib.ScoreOut(*[C.c_void_p(out[k].data_ptr()) if k in out else None
+                            for k in ("score", "valid", "count", "length", "min_codon", "status", "frame_K", "frame_s")])
+        self._check(self.lib.rt_score(self.ctx, C.c_void_p(cov.data_ptr()), int(lo), int(hi), C.byref(prm),
+                                      C.byref(o), self._stream()))
+
+    def score_host(self, cov, lo: int = 0, hi: int | None = None, params: ScoreParams | None = None,
+                   diagnostics: bool = False) -> dict:
+        """Score ORFs [lo, hi) and return HOST numpy columns (D2H inside the C call)."""
+        hi = self.n_orf if hi is None else hi
+        n = hi - lo
+        out = dict(score=np.empty(n, np.float64), valid=np.empty(n, np.int32), count=np.empty(n, np.int64),
+                   length=np.empty(n, np.int32), min_codon=np.empty(n, np.int32), status=np.empty(n, np.uint8))
+        if diagnostics:
+            out["frame_K"] = np.empty((n, 3), np.int32)
+            out["frame_s"] = np.empty((n, 3), np.float64)
+        prm = (params or ScoreParams()).as_c()
+        o = _lib.ScoreOut(*[_np_ptr(out[k]) if k in out else None
+                            for k in ("score", "valid", "count", "length", "min_codon", "status", "frame_K", "frame_s")])
+        self.torch.cuda.current_stream(self.device).synchronize()
+        self._check(self.lib.rt_score_host(self.ctx, C.c_void_p(cov.data_ptr()), int(lo), int(hi), C.byref(prm),
+                                           C.byref(o)))
+        return out
+
+    # ------------------------------------------------------------------- K4
+    def gather_profiles(self, cov, orf_ids, lengths):
+        """Profiles of the selected ORFs: returns ``(out_ptr, flat int32 profiles)`` on the host."""
+        t = self.torch
+        orf_ids = np.ascontiguousarray(orf_ids, np.int64)
+        lengths = np.ascontiguousarray(lengths, np.int64)
+        out_ptr = np.zeros(len(orf_ids) + 1, np.int64)
+        np.cumsum(lengths, out=out_ptr[1:])
+        total = int(out_ptr[-1])
+        if len(orf_ids) == 0:
+            return out_ptr, np.zeros(0, np.int32)
+        d_ids = t.from_numpy(orf_ids).to(self.device)
+        d_ptr = t.from_numpy(out_ptr).to(self.device)
+        d_out = t.empty(max(total, 1), dtype=t.int32, device=self.device)
+        self._check(self.lib.rt_gather_profiles(self.ctx, C.c_void_p(cov.data_ptr()), len(orf_ids),
+                                                C.c_void_p(d_ids.data_ptr()), C.c_void_p(d_ptr.data_ptr()),
+                                                C.c_void_p(d_out.data_ptr()), self._stream()))
+        return out_ptr, d_out[:total].cpu().numpy()

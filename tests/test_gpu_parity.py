@@ -1,0 +1,243 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle -- the tests proper.
+
+Bar (BASELINE.json north_star): bit-exact P-site counts, read counts, lengths, valid codons and
+ordering; phase score within 1e-9 absolute; status bit-exact except near the cutoff.  ORFs whose
+best frame is an exact-arithmetic tie (hazard H1: the reference's valid_codons is then decided by
+SciPy rounding noise) are excluded from the valid_codons/status comparison and counted.
+"""
+import numpy as np
+import pytest
+
+from helpers import (DEFAULT_PARAMS, SCORE_TOL, alignments_to_reads, case_to_arrays, compare_scores,
+                     load_golden, merged_to_dense)
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import c_oracle
+    return c_oracle
+
+
+def _setup(engine, names, lens, idx, offsets, read_lengths=None, pad=64):
+    engine.set_genome(names, lens, pad=pad)
+    engine.set_length_table(offsets, read_lengths)
+    engine.set_index(**idx)
+    CO = _oracle()
+    base, plane = CO.genome_layout(lens, pad)
+    assert plane == engine.plane and (base == engine.contig_base).all()
+    return base, plane
+
+
+def test_phasescore_golden_profiles(engine):
+    """Every golden phasescore profile as a one-exon ORF on its own stretch of a contig."""
+    CO = _oracle()
+    cases = load_golden("phasescore_cases.json.gz")["cases"]
+    cases = [c for c in cases if len(c["cov"]) > 0]
+    pad = 64
+    starts, ends, pos = [], [], 1
+    for c in cases:
+        starts.append(pos)
+        ends.append(pos + len(c["cov"]) - 1)
+        pos += len(c["cov"]) + 7
+    lens = np.array([pos + 10], np.int64)
+    n = len(cases)
+    for strand in (0, 1):
+        idx = dict(exon_ptr=np.arange(n + 1, dtype=np.int64), exon_start=np.array(starts, np.int32),
+                   exon_end=np.array(ends, np.int32), orf_contig=np.zeros(n, np.int32),
+                   orf_strand=np.full(n, strand, np.uint8))
+        base, plane = _setup(engine, ["c"], lens, idx, {28: 12}, pad=pad)
+        cov = np.zeros(2 * plane, np.int32)
+        for c, s in zip(cases, starts):
+            v = np.array(c["cov"], np.int32)
+            if strand == 1:
+                v = v[::-1]
+            cov[strand * plane + base[0] + pad + s: strand * plane + base[0] + pad + s + len(v)] = v
+        d_cov = engine.torch.from_numpy(cov).to(engine.device)
+        got = engine.score_host(d_cov, diagnostics=True)
+        ref = CO.score(idx, cov, base, lens, pad, plane, DEFAULT_PARAMS)
+        tie = CO.tie_mask(ref["frame_K"], ref["frame_s"])
+        compare_scores(got, ref, tie)
+        assert (got["frame_K"] == ref["frame_K"]).all()
+        # and directly against the reference's own numbers
+        ref_s = np.array([float.fromhex(c["score"]) for c in cases])
+        ref_v = np.array([c["valid"] for c in cases])
+        assert np.abs(got["score"] - ref_s).max() <= SCORE_TOL
+        assert (got["valid"] == ref_v)[~tie].all()
+        assert tie.sum() < 0.02 * n
+
+
+def test_golden_pipeline_end_to_end(engine):
+    """reads -> K1 -> K3 -> K4 against merge_read_lengths / orf_coverage / export_orf_coverages
+    outputs of the reference (tests/golden/pipeline_cases.json.gz)."""
+    CO = _oracle()
+    for case in load_golden("pipeline_cases.json.gz")["cases"]:
+        names, lens, idx, rows = case_to_arrays(case)
+        offsets = {int(k): v for k, v in case["psite_offsets"].items()}
+        pad = 64
+        base, plane = _setup(engine, names, lens, idx, offsets, pad=pad)
+        reads = alignments_to_reads(case, names)
+        cov = engine.new_coverage()
+        stats, len_counts = engine.bin_reads_host(cov, reads, "forward")
+        ref_cov, dropped = merged_to_dense(case, names, base, pad, plane)
+        assert (cov.cpu().numpy() == ref_cov).all(), case["name"]
+        assert stats["oob"] == dropped and stats["valid"] == len(reads["ref_id"])
+        got = engine.score_host(cov, diagnostics=True)
+        ref = CO.score(idx, ref_cov, base, lens, pad, plane, DEFAULT_PARAMS)
+        tie = CO.tie_mask(ref["frame_K"], ref["frame_s"])
+        compare_scores(got, ref, tie, what=case["name"] + ": ")
+        ptr, prof = engine.gather_profiles(cov, np.arange(len(rows)), got["length"])
+        for i, (oid, p) in enumerate(case["profiles"]):
+            assert prof[ptr[i]:ptr[i + 1]].tolist() == p, oid
+        ref_rows = [r.split("\t") for r in case["tsv"][0]["text"].split("\n")[1:] if r]
+        for i, r in enumerate(ref_rows):
+            assert abs(got["score"][i] - float(r[3])) <= SCORE_TOL
+            assert got["count"][i] == int(r[4]) and got["length"][i] == int(r[5])
+            if not tie[i]:
+                assert got["valid"][i] == int(r[6])
+
+
+@pytest.mark.parametrize("protocol,read_lengths,sort", [
+    ("forward", None, True), ("reverse", None, False), ("forward", [28, 29, 30], False), ("no", None, True)])
+def test_bin_psites_matches_oracle(engine, protocol, read_lengths, sort):
+    CO = _oracle()
+    from ribotricer_b200 import synth
+
+    cfg = synth.config("tiny")
+    idx = synth.make_index(cfg)
+    reads = synth.reads_to_numpy(synth.make_reads(cfg, idx, n_reads=300_000, sort=sort))
+    reads["ref_id"][:7] = -1
+    reads["ref_id"][7:9] = 99
+    reads["flag"][9:20] = 4
+    reads["nh"][20:40] = 0
+    reads["mapq"][20:30] = 0
+    reads["mlen"][40:45] = 700      # beyond the shared-memory histogram
+    reads["first"][45:50] = 0       # P-sites shifted off the contig start stay in the pad
+    reads["last"][45:50] = 27
+    offsets = {26: 12, 27: 12, 28: 12, 29: 12, 30: 13, 31: 13}
+    pad = 16                        # small pad: some shifted P-sites fall outside -> oob
+    base, plane = _setup(engine, idx.contig_names, idx.contig_len, idx.as_dict(), offsets, read_lengths, pad=pad)
+    code = {"forward": 0, "reverse": 1}.get(protocol, 2)
+    lt = CO.make_len_table(offsets, read_lengths)
+    ref_cov, ref_stats, ref_len = CO.bin_reads(reads, code, lt, base, idx.contig_len, pad, plane)
+    cov = engine.new_coverage()
+    stats, len_counts = engine.bin_reads_host(cov, reads, protocol, sorted_hint=sort)
+    assert stats == ref_stats
+    assert (len_counts == ref_len).all()
+    assert (cov.cpu().numpy() == ref_cov).all()
+    # device-pointer entry gives the same and accumulates
+    dcols = engine.upload_reads(reads)
+    st, lc = engine.new_bin_accumulators()
+    engine.bin_reads_device(cov, dcols, protocol, st, lc, sorted_hint=sort)
+    engine.torch.cuda.synchronize()
+    assert (cov.cpu().numpy() == 2 * ref_cov).all()
+    assert dict(zip(ref_stats.keys(), st.cpu().tolist())) == ref_stats
+
+
+@pytest.mark.parametrize("name,scale,contig_scale", [("tiny", 1.0, 1.0), ("C1", 0.2, 1.0), ("C5", 0.004, 0.01)])
+def test_score_matches_oracle(engine, name, scale, contig_scale):
+    CO = _oracle()
+    from ribotricer_b200 import synth
+
+    cfg = synth.config(name, scale, contig_scale)
+    idx = synth.make_index(cfg)
+    reads = synth.reads_to_numpy(synth.make_reads(cfg, idx, n_reads=min(cfg.n_reads, 2_000_000)))
+    pad = 256
+    base, plane = _setup(engine, idx.contig_names, idx.contig_len, idx.as_dict(), synth.TRUE_OFFSETS, pad=pad)
+    cov = engine.new_coverage()
+    engine.bin_reads_host(cov, reads, "forward", sorted_hint=True)
+    ref_cov, _, _ = CO.bin_reads(reads, 0, CO.make_len_table(synth.TRUE_OFFSETS), base, idx.contig_len, pad, plane)
+    assert (cov.cpu().numpy() == ref_cov).all()
+    for params in (DEFAULT_PARAMS, [0.3, 3, 1, 0.1, 0.25]):
+        from ribotricer_b200.engine import ScoreParams
+        got = engine.score_host(cov, params=ScoreParams(*params), diagnostics=True)
+        ref = CO.score(idx.as_dict(), ref_cov, base, idx.contig_len, pad, plane, params)
+        tie = CO.tie_mask(ref["frame_K"], ref["frame_s"])
+        n_tie, n_near = compare_scores(got, ref, tie, params, what=f"{name}: ")
+        assert (got["frame_K"] == ref["frame_K"]).all()
+        assert n_tie < 0.05 * idx.n_orf
+    # sub-range scoring (what a shard does) returns the same rows
+    lo, hi = idx.n_orf // 3, idx.n_orf // 3 + 1000
+    part = engine.score_host(cov, lo, min(hi, idx.n_orf))
+    full = engine.score_host(cov)
+    for k in part:
+        assert (part[k] == full[k][lo:hi]).all()
+    # K4 on a sample of ORFs, both strands, long and short
+    sel = np.unique(np.concatenate([np.arange(0, idx.n_orf, max(1, idx.n_orf // 300)),
+                                    np.argsort(idx.orf_len)[-3:]]))
+    ptr, prof = engine.gather_profiles(cov, sel, full["length"][sel])
+    rptr, rprof = CO.gather_profiles(idx.as_dict(), sel, ref_cov, base, idx.contig_len, pad, plane)
+    assert (ptr == rptr).all() and (prof == rprof).all()
+
+
+def test_edge_cases(engine):
+    """Empty / ragged inputs: unknown contig, unknown strand, exons hanging off the contig,
+    length-1 and length-2 ORFs, 1-nt exons, lengths not a multiple of 3, tile-boundary lengths."""
+    CO = _oracle()
+    rng = np.random.default_rng(5)
+    lens = np.array([5000, 300], np.int64)
+    pad = 8
+    orfs = [
+        (0, 0, [(1, 1)]), (0, 1, [(10, 11)]), (0, 0, [(20, 22)]), (0, 1, [(30, 33)]),
+        (0, 0, [(40, 40), (42, 42), (44, 44), (46, 60)]),            # 1-nt exons
+        (-1, 0, [(1, 90)]), (0, 2, [(1, 90)]),                        # unknown contig / strand
+        (1, 0, [(-20, 30)]), (1, 1, [(280, 330)]), (1, 0, [(-50, -20)]), (1, 1, [(400, 450)]),
+        (0, 0, [(100, 100 + 767)]), (0, 1, [(100, 100 + 768)]), (0, 0, [(100, 100 + 769)]),
+        (0, 1, [(100, 100 + 770)]), (0, 0, [(100, 100 + 771)]), (0, 0, [(100, 100 + 1535)]),
+        (0, 1, [(100, 100 + 1537)]), (0, 0, [(1, 4999)]), (0, 1, [(2, 5000)]),
+        (0, 0, [(s, s + 9) for s in range(1000, 1000 + 40 * 20, 20)]),   # 40 exons > 32-entry cache
+        (0, 1, [(s, s + 6) for s in range(2000, 2000 + 70 * 9, 9)]),     # 70 exons
+    ]
+    ptr, st, en, contig, strand = [0], [], [], [], []
+    for c, s, ivs in orfs:
+        for a, b in ivs:
+            st.append(a)
+            en.append(b)
+        ptr.append(len(st))
+        contig.append(c)
+        strand.append(s)
+    idx = dict(exon_ptr=np.array(ptr, np.int64), exon_start=np.array(st, np.int32), exon_end=np.array(en, np.int32),
+               orf_contig=np.array(contig, np.int32), orf_strand=np.array(strand, np.uint8))
+    base, plane = _setup(engine, ["a", "b"], lens, idx, {28: 12}, pad=pad)
+    cov = np.zeros(2 * plane, np.int32)
+    for c in range(2):
+        for s in range(2):
+            lo = s * plane + base[c]
+            span = lens[c] + 2 * pad + 1
+            cov[lo:lo + span] = rng.poisson(0.4, span) * (rng.random(span) < 0.5)
+    cov[base[0] + pad + 200] = 2_000_000_000     # near-int32-max counts: 64-bit sums, fp64 path
+    cov[base[0] + pad + 201] = 2_000_000_000
+    cov[base[0] + pad + 203] = 1_999_999_999
+    d_cov = engine.torch.from_numpy(cov).to(engine.device)
+    got = engine.score_host(d_cov, diagnostics=True)
+    ref = CO.score(idx, cov, base, lens, pad, plane, DEFAULT_PARAMS)
+    tie = CO.tie_mask(ref["frame_K"], ref["frame_s"])
+    compare_scores(got, ref, tie)
+    assert (got["frame_K"] == ref["frame_K"]).all()
+    p, prof = engine.gather_profiles(d_cov, np.arange(len(orfs)), got["length"])
+    rp, rprof = CO.gather_profiles(idx, np.arange(len(orfs)), cov, base, lens, pad, plane)
+    assert (prof == rprof).all()
+    # empty inputs
+    engine.set_index(np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32),
+                     np.zeros(0, np.int32), np.zeros(0, np.uint8))
+    assert len(engine.score_host(d_cov)["score"]) == 0
+    empty = {k: np.zeros(0, dt) for k, dt in (("ref_id", np.int32), ("first", np.int32), ("last", np.int32),
+             ("mlen", np.uint16), ("flag", np.uint16), ("mapq", np.uint8), ("nh", np.uint8))}
+    stats, _ = engine.bin_reads_host(d_cov, empty, "forward")
+    assert stats["total"] == 0
+
+
+def test_errors_are_loud(engine):
+    from ribotricer_b200 import _lib
+
+    engine.set_genome(["a"], [1000], pad=8)
+    with pytest.raises(_lib.RtError):   # offset larger than the pad
+        engine.set_length_table({28: 12, 40: 30})
+    with pytest.raises(_lib.RtError):   # empty interval
+        engine.set_index(np.array([0, 1], np.int64), np.array([10], np.int32), np.array([5], np.int32),
+                         np.array([0], np.int32), np.array([0], np.uint8))
+    engine.set_index(np.array([0, 1], np.int64), np.array([10], np.int32), np.array([50], np.int32),
+                     np.array([0], np.int32), np.array([0], np.uint8))
+    cov = engine.new_coverage()
+    with pytest.raises(_lib.RtError):   # ORF range outside the index
+        engine.score_host(cov, 0, 5)

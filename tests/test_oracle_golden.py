@@ -1,0 +1,193 @@
+"""Pin the oracle (the checker) against outputs of the unmodified reference.
+
+The golden files were produced by tests/golden/make_golden.py, which runs
+ribotricer 1.5.0 itself (statistics.py:48, detect_orfs.py:54,134,206,327).
+"""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from helpers import (DEFAULT_PARAMS, SCORE_TOL, case_to_arrays, load_golden, merged_to_dense)
+from oracle import c_oracle as CO
+from oracle import oracle_py as O
+
+PAD = 64
+
+
+@pytest.fixture(scope="module")
+def ps_cases():
+    return load_golden("phasescore_cases.json.gz")["cases"]
+
+
+@pytest.fixture(scope="module")
+def pipe_cases():
+    return load_golden("pipeline_cases.json.gz")["cases"]
+
+
+def test_phasescore_c_oracle_matches_reference(built, ps_cases):
+    ties = 0
+    for c in ps_cases:
+        ref_s, ref_v = float.fromhex(c["score"]), c["valid"]
+        s, v = CO.phasescore(c["cov"])
+        assert abs(s - ref_s) <= 1e-12
+        K, s3 = CO.frame_spectra(c["cov"])
+        if CO.tie_mask(K[None, :], s3[None, :])[0]:
+            ties += 1
+        else:
+            assert v == ref_v, c["cov"]
+    assert ties < 0.02 * len(ps_cases)   # H1 ties are a small class
+
+
+def test_phasescore_py_oracle_matches_reference(ps_cases):
+    for c in ps_cases[::4]:
+        ref_s, ref_v = float.fromhex(c["score"]), c["valid"]
+        fr = O.frame_spectra(c["cov"])
+        s, v = O.select_frame(fr)
+        assert abs(s - ref_s) <= 1e-12
+        if not O.is_frame_tie(fr):
+            assert v == ref_v
+
+
+def test_scipy_restatement_is_the_reference(ps_cases):
+    """oracle_py.phasescore_scipy makes the same SciPy call as statistics.py:101-107, so it must
+    reproduce the reference bit for bit, ties included (same scipy build)."""
+    import scipy
+
+    gold = load_golden("phasescore_cases.json.gz")["versions"]
+    if scipy.__version__ != gold["scipy"]:
+        pytest.skip("golden vectors were generated with another scipy")
+    for c in ps_cases[:40] + ps_cases[200:260]:
+        s, v = O.phasescore_scipy(c["cov"])
+        assert s.hex() == c["score"] and v == c["valid"]
+
+
+def test_known_answers():
+    """Quirk KATs listed in SURVEY.md 8(a), produced by the reference."""
+    assert CO.phasescore([1] + [0] * 29) == (0.0, 0)                 # K==0 reset quirk
+    assert CO.phasescore([0, 0, 0, 1] + [0] * 26) == (1.0, 1)
+    assert CO.phasescore([1, 0, 0, 0, 0]) == (0.0, 0)
+    assert CO.phasescore([1, 1, 1] * 5) == (0.0, 5)                  # uniform codons
+    assert CO.phasescore([]) == (0.0, 0)
+    s, v = CO.phasescore([2, 2, 2, 1, 0, 0, 1, 0, 0])
+    assert abs(s - 0.816496580927726) < 1e-14 and v == 3
+    s, v = CO.phasescore([3, 1, 2, 0, 0, 0, 5, 0, 1, 2, 2, 2, 0, 4, 0, 1])
+    assert abs(s - 0.39247762314783674) < 1e-14 and v == 4
+
+
+def _rebuild_alignments(case):
+    from collections import Counter, defaultdict
+    aln = defaultdict(lambda: defaultdict(Counter))
+    for length, strand, chrom, pos, n in case["alignments"]:
+        aln[length][strand][(chrom, pos)] += n
+    return aln
+
+
+def test_merge_and_profiles_py_oracle(pipe_cases):
+    for case in pipe_cases:
+        offsets = {int(k): v for k, v in case["psite_offsets"].items()}
+        merged = O.merge_read_lengths(_rebuild_alignments(case), offsets)
+        got = sorted([s, c, p, n] for s in merged for (c, p), n in merged[s].items())
+        assert got == case["merged"]
+        for line, (oid, prof) in zip(case["index"][1:], case["profiles"]):
+            orf = O.parse_index_line(line + "\n")
+            assert orf["oid"] == oid
+            assert O.orf_profile(orf["chrom"], orf["strand"], orf["intervals"], merged) == prof
+
+
+def test_tsv_and_wig_py_oracle(pipe_cases, tmp_path):
+    """Whole TSV text of export_orf_coverages / export_wig; scores compared numerically,
+    everything else byte for byte."""
+    for case in pipe_cases:
+        offsets = {int(k): v for k, v in case["psite_offsets"].items()}
+        merged = O.merge_read_lengths(_rebuild_alignments(case), offsets)
+        idx = tmp_path / f"{case['name']}.tsv"
+        idx.write_text("\n".join(case["index"]) + "\n")
+        prefix = str(tmp_path / case["name"])
+        O.export_wig(merged, prefix)
+        for tag, text in case["wig"].items():
+            assert open(f"{prefix}_{tag}.wig").read() == text
+        for run in case["tsv"]:
+            O.export_orf_coverages(str(idx), merged, prefix, **run["params"])
+            got = open(f"{prefix}_translating_ORFs.tsv").read().split("\n")
+            ref = run["text"].split("\n")
+            assert got[0] == ref[0]
+            gi = 1
+            g_rows = {r.split("\t")[0]: r.split("\t") for r in got[1:] if r}
+            r_rows = {r.split("\t")[0]: r.split("\t") for r in ref[1:] if r}
+            cutoff = run["params"]["phase_score_cutoff"]
+            for oid, r in r_rows.items():
+                tie = O.is_frame_tie(O.frame_spectra(eval(r[17])))
+                near = abs(float(r[3]) - cutoff) <= SCORE_TOL
+                if oid not in g_rows:
+                    assert tie or near, oid
+                    continue
+                g = g_rows[oid]
+                assert abs(float(g[3]) - float(r[3])) <= SCORE_TOL
+                cols = [0, 1, 4, 5, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17]
+                if not tie:
+                    cols += [6, 7]
+                    if not near:
+                        cols += [2]
+                for c in cols:
+                    assert g[c] == r[c], (oid, c, g[c], r[c])
+            del gi
+
+
+def test_dense_c_oracle_matches_reference_profiles_and_scores(built, pipe_cases):
+    for case in pipe_cases:
+        names, lens, idx, rows = case_to_arrays(case)
+        base, plane = CO.genome_layout(lens, PAD)
+        cov, dropped = merged_to_dense(case, names, base, PAD, plane)
+        ptr, prof = CO.gather_profiles(idx, np.arange(len(rows)), cov, base, lens, PAD, plane)
+        for i, (oid, p) in enumerate(case["profiles"]):
+            assert prof[ptr[i]:ptr[i + 1]].tolist() == p, oid
+        run = case["tsv"][0]   # default parameters, report_all
+        out = CO.score(idx, cov, base, lens, PAD, plane, DEFAULT_PARAMS)
+        tie = CO.tie_mask(out["frame_K"], out["frame_s"])
+        ref_rows = [r.split("\t") for r in run["text"].split("\n")[1:] if r]
+        assert len(ref_rows) == len(rows)
+        for i, r in enumerate(ref_rows):
+            assert abs(out["score"][i] - float(r[3])) <= SCORE_TOL
+            assert out["count"][i] == int(r[4]) and out["length"][i] == int(r[5])
+            n_codons = max(1, int(r[5]) // 3)
+            assert repr(float(out["count"][i] / n_codons)) == r[8] or str(np.float64(out["count"][i]) / n_codons) == r[8]
+            if not tie[i]:
+                assert out["valid"][i] == int(r[6])
+                assert str(out["valid"][i] / n_codons) == r[7]
+                if abs(float(r[3]) - DEFAULT_PARAMS[0]) > SCORE_TOL:
+                    assert ("translating" if out["status"][i] else "nontranslating") == r[2]
+
+
+def test_bin_reads_c_oracle_matches_py_restatement(built):
+    """A1 has no runnable reference (pysam absent): the two restatements of bam.py:71-137
+    (dict-based Python, dense C) must at least agree with each other."""
+    from ribotricer_b200 import synth
+
+    cfg = synth.config("tiny")
+    idx = synth.make_index(cfg)
+    reads = synth.reads_to_numpy(synth.make_reads(cfg, idx, n_reads=20_000, sort=False))
+    reads["ref_id"][:5] = -1            # reference_name None
+    reads["flag"][5:10] = 4             # unmapped
+    reads["nh"][10:20] = 0              # no NH tag ...
+    reads["mapq"][10:15] = 0            # ... MAPQ 0 -> not unique
+    reads["mapq"][15:20] = 255          # ... MAPQ 255 -> unique
+    for protocol, code in (("forward", 0), ("reverse", 1), ("no", 2)):
+        for read_lengths in (None, [28, 29, 30]):
+            offsets = {28: 12, 29: 12, 30: 13, 31: 13}
+            aln, rlc, st = O.split_reads(reads, protocol, read_lengths, idx.contig_names)
+            merged = O.merge_read_lengths(aln, offsets)
+            base, plane = CO.genome_layout(idx.contig_len, PAD)
+            lt = CO.make_len_table(offsets, read_lengths)
+            cov, cst, lc = CO.bin_reads(reads, code, lt, base, idx.contig_len, PAD, plane)
+            for k in ("total", "qcfail", "duplicate", "secondary", "unmapped", "multi", "valid"):
+                assert st[k] == cst[k], (protocol, k)
+            assert {int(l): int(lc[l]) for l in np.flatnonzero(lc)} == dict(rlc)
+            dense = np.zeros_like(cov)
+            lut = {n: i for i, n in enumerate(idx.contig_names)}
+            for s in merged:
+                for (c, p), n in merged[s].items():
+                    dense[(0 if s == "+" else 1) * plane + base[lut[c]] + PAD + p] += n
+            assert (dense == cov).all()
+            assert cst["oob"] == 0
