@@ -142,7 +142,9 @@ def gather_profiles(index, orf_ids, cov, contig_base, contig_len, pad, plane):
 
 
 def tie_mask(frame_K, frame_s, tol=1e-12):
-    """Vectorised H1 classifier (same rule as oracle_py.is_frame_tie)."""
+    """Vectorised H1 classifier (same rule as oracle_py.is_frame_tie): True where the running
+    maximum of statistics.py:109 is decided between frames whose scores agree within ``tol``
+    while their K differ -- the reference's valid_codons is then SciPy rounding noise."""
     n = len(frame_K)
     best = np.zeros(n)
     valid = np.full(n, -1, np.int64)
@@ -152,10 +154,12 @@ def tie_mask(frame_K, frame_s, tol=1e-12):
         s = frame_s[:, f]
         zero = k == 0
         ok = ~zero & ~np.isnan(s)
-        close = ok & (np.abs(s - best) <= tol) & (valid != -1) & (valid != k)
-        gt = ok & (s > best)
-        tie = np.where(zero, False, np.where(close, True, np.where(gt, False, tie)))
-        best = np.where(zero, 0.0, np.where(gt, s, best))
-        valid = np.where(zero, 0, np.where(gt, k, valid))
+        with np.errstate(invalid="ignore"):
+            win = ok & (s > best + tol)
+            close = ok & ~win & (np.abs(s - best) <= tol)
+        amb = close & (valid != -1) & (valid != k)
+        tie = np.where(zero | win, False, tie | amb)
+        best = np.where(zero, 0.0, np.where(win | close, np.fmax(best, np.where(ok, s, best)), best))
+        valid = np.where(zero, 0, np.where(win, k, valid))
         valid = np.where(~zero & (valid == -1), k, valid)
     return tie

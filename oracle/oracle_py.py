@@ -271,6 +271,8 @@ def is_frame_tie(frames, tol: float = 1e-12) -> bool:
     by ~1e-17 SciPy rounding noise when the running maximum at
     statistics.py:109 meets a score equal to it in exact arithmetic while the
     K differ.  Such ORFs are excluded from bit-exact valid_codons comparison.
+    A frame only wins clearly when it beats the running maximum by more than
+    ``tol``; anything closer with a different K is a tie until a clear win.
     """
     best, valid = 0.0, -1
     tie = False
@@ -279,12 +281,12 @@ def is_frame_tie(frames, tol: float = 1e-12) -> bool:
             best, valid, tie = 0.0, 0, False
             continue
         if not math.isnan(s):
-            if abs(s - best) <= tol and valid not in (-1, k):
-                tie = True
-            elif s > best:
-                tie = False
-            if s > best:
-                best, valid = s, k
+            if s > best + tol:
+                best, valid, tie = s, k, False
+            elif abs(s - best) <= tol:
+                if valid not in (-1, k):
+                    tie = True
+                best = max(best, s)
         if valid == -1:
             valid = k
     return tie

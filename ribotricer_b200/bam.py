@@ -1,0 +1,171 @@
+"""``split_bam`` on the GPU (mirror of ribotricer/bam.py:33-153).
+
+The host keeps the BAM decode (pysam, as the north star prescribes) and turns
+every alignment record into seven small columns; the read filter cascade, the
+strand / 5'-end rule, the per-length totals and the binning itself run in the
+K1 kernel (``bin_psites_kernel``).  Because pysam is not installable in every
+environment, the same columns can also be loaded from a ``.npz`` file
+(``save_read_columns``) -- that is what the tests and the benchmark use.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .engine import READ_COLUMNS, Engine, make_len_table
+
+
+@dataclass
+class ReadColumns:
+    """Decoded alignment records (structure of arrays) + the BAM header's contig table."""
+    contig_names: list
+    contig_len: np.ndarray
+    cols: dict              # name -> numpy array, see engine.READ_COLUMNS
+    sorted_by_coordinate: bool = False
+
+    def __len__(self) -> int:
+        return len(self.cols["ref_id"])
+
+
+def save_read_columns(path: str, reads: ReadColumns) -> None:
+    np.savez(path, contig_names=np.array(reads.contig_names), contig_len=reads.contig_len,
+             sorted_by_coordinate=np.array(reads.sorted_by_coordinate), **reads.cols)
+
+
+def _matched_span(read):
+    """first/last matched reference position and their count, i.e. what
+    ``read.get_reference_positions()`` (bam.py:95) would give for [0], [-1] and len():
+    only M, = and X operations contribute positions."""
+    first, last, n = 0, 0, 0
+    pos = read.reference_start
+    for op, length in read.cigartuples or ():
+        if op in (0, 7, 8):          # M, =, X
+            if n == 0:
+                first = pos
+            last = pos + length - 1
+            n += length
+            pos += length
+        elif op in (2, 3):           # D, N consume the reference only
+            pos += length
+    return first, last, n
+
+
+def read_bam_columns(bam_path: str) -> ReadColumns:
+    """Decode a BAM into read columns with pysam (host I/O; not on the measured path)."""
+    try:
+        import pysam
+    except ImportError as exc:
+        raise RuntimeError(
+            "pysam is required to decode BAM files and is not installed here; pass decoded read columns "
+            "as a .npz file instead (ribotricer_b200.bam.save_read_columns)") from exc
+    bam = pysam.AlignmentFile(bam_path, "rb")
+    names = list(bam.references)
+    lens = np.array(bam.lengths, np.int64)
+    acc = {name: [] for name, _ in READ_COLUMNS}
+    for read in bam.fetch(until_eof=True):      # bam.py:71
+        first, last, n = _matched_span(read)
+        acc["ref_id"].append(read.reference_id if read.reference_id is not None else -1)
+        acc["first"].append(first)
+        acc["last"].append(last)
+        acc["mlen"].append(min(n, 65535))
+        acc["flag"].append(read.flag)
+        acc["mapq"].append(read.mapping_quality)
+        nh = read.get_tag("NH") if read.has_tag("NH") else 0   # common.py:53-56
+        acc["nh"].append(min(max(int(nh), 0), 255) if nh != 0 else 0)
+    so = bam.header.to_dict().get("HD", {}).get("SO", "") == "coordinate"
+    bam.close()
+    return ReadColumns(names, lens, {k: np.asarray(acc[k], dt) for k, dt in READ_COLUMNS}, so)
+
+
+def load_reads(path) -> ReadColumns:
+    """BAM (through pysam) or ``.npz`` of decoded columns."""
+    if isinstance(path, ReadColumns):
+        return path
+    if str(path).endswith(".npz"):
+        z = np.load(path, allow_pickle=False)
+        cols = {name: np.ascontiguousarray(z[name], dt) for name, dt in READ_COLUMNS}
+        so = bool(z["sorted_by_coordinate"]) if "sorted_by_coordinate" in z else False
+        return ReadColumns([str(c) for c in z["contig_names"]], np.asarray(z["contig_len"], np.int64), cols, so)
+    return read_bam_columns(path)
+
+
+class Alignments:
+    """What ``split_bam`` returns: the library's reads, resident on the GPU.
+
+    The reference returns ``alignments[length][strand][(chrom, pos)] -> count``
+    (bam.py:29,135); here the same information stays in HBM as read columns and is
+    binned on demand (per length for the metagene step, merged for scoring)."""
+
+    def __init__(self, engine: Engine, reads: ReadColumns, protocol: str, read_lengths=None):
+        self.engine = engine
+        self.reads = reads
+        self.protocol = protocol
+        self.read_lengths = None if read_lengths is None else [int(x) for x in read_lengths]
+        self.dcols = engine.upload_reads(reads.cols)
+        self.n = len(reads)
+        self.sorted = reads.sorted_by_coordinate
+        self.stats: dict = {}
+        self.read_length_counts: dict = {}
+
+    def count(self):
+        """Filter cascade + per-length totals (bam.py:73-91,136) without storing coverage."""
+        eng = self.engine
+        eng.set_length_table(None, self.read_lengths)     # no offsets: nothing is binned
+        cov = eng.torch.zeros(1, dtype=eng.torch.int32, device=eng.device)
+        stats, lc = eng.new_bin_accumulators()
+        eng.bin_reads_device(cov, self.dcols, self.protocol, stats, lc, self.sorted, n=self.n)
+        st = stats.cpu().numpy()
+        lcn = lc.cpu().numpy()
+        self.stats = dict(zip(_lib.ST_NAMES, st.tolist()))
+        rlc = defaultdict(int)
+        for length in np.flatnonzero(lcn):
+            rlc[int(length)] = int(lcn[length])
+        self.read_length_counts = rlc
+        return self.stats, rlc
+
+    def bin_into(self, cov, psite_offsets: dict, weight: int = 1):
+        """merge_read_lengths (detect_orfs.py:54-83): bin P-sites of the lengths in
+        ``psite_offsets`` into ``cov``."""
+        eng = self.engine
+        eng.set_length_table(psite_offsets, self.read_lengths)
+        stats, lc = eng.new_bin_accumulators()
+        eng.bin_reads_device(cov, self.dcols, self.protocol, stats, lc, self.sorted, n=self.n, weight=weight)
+        return stats
+
+
+def bam_summary_text(stats: dict, read_length_counts: dict) -> str:
+    """Text of ``{prefix}_bam_summary.txt`` exactly as bam.py:141-148 formats it."""
+    summary = (
+        f"summary:\n\ttotal_reads: {stats['total']}\n\tunique_mapped: {stats['valid']}\n"
+        f"\tqcfail: {stats['qcfail']}\n\tduplicate: {stats['duplicate']}\n\tsecondary: {stats['secondary']}\n"
+        f"\tunmapped:{stats['unmapped']}\n\tmulti:{stats['multi']}\n\nlength dist:\n"
+    )
+    for length in sorted(read_length_counts):
+        summary += f"\t{length}: {read_length_counts[length]}\n"
+    return summary
+
+
+def split_bam(bam_path, protocol: str, prefix: str, read_lengths=None, engine: Engine | None = None):
+    """Mirror of ``split_bam(bam_path, protocol, prefix, read_lengths=None)`` (bam.py:33-38).
+
+    Returns ``(alignments, read_length_counts)``; writes ``{prefix}_bam_summary.txt``.
+    ``bam_path`` may be a BAM, a ``.npz`` of decoded columns or a ``ReadColumns``.
+    """
+    from .detect_orfs import get_engine
+
+    reads = load_reads(bam_path)
+    eng = engine or get_engine()
+    if list(eng.contig_names) != list(reads.contig_names) or eng.pad == 0:
+        eng.set_genome(reads.contig_names, reads.contig_len)
+    alignments = Alignments(eng, reads, protocol, read_lengths)
+    stats, rlc = alignments.count()
+    with open(f"{prefix}_bam_summary.txt", "w") as output:
+        output.write(bam_summary_text(stats, rlc))
+    return alignments, rlc
+
+
+__all__ = ["ReadColumns", "Alignments", "split_bam", "load_reads", "save_read_columns", "read_bam_columns",
+           "bam_summary_text", "make_len_table"]
