@@ -32,40 +32,9 @@ constexpr int kScoreWarps = 8;                 // warps per CTA
 constexpr int kTileCodons = 256;               // codons per warp tile (8 rounds of 32 lanes)
 constexpr int kTileNt = 3 * kTileCodons;       // window starts per tile
 constexpr int kBufNt = kTileNt + 8;            // + 2 halo + zero pad, keeps 16 B multiples
-constexpr int kFetchBatch = 4;                 // ORFs claimed per atomic
-
-struct FrameAcc {
-    int K = 0;        // kept codons (statistics.py:72 negated)
-    int na = 0;       // codons (a,0,0): unit vector (1, 0)
-    int nb = 0;       // codons (0,b,0): unit vector (-1/2, +sqrt3/2)
-    int nc = 0;       // codons (0,0,c): unit vector (-1/2, -sqrt3/2)
-    int ng = 0;       // other non-uniform codons, summed in fp64 below
-    double sre = 0.0; // sum of A / sqrt(A^2 + 3 B^2),          A = 2a - b - c
-    double sim = 0.0; // sum of B / sqrt(A^2 + 3 B^2) (x sqrt3), B = b - c
-};
-
-// One codon (a,b,c) of one frame: statistics.py:72-90 in closed form.  The reference
-// normalises the triplet by |a + b w + c w^2| and SciPy's coherence then only sees the unit
-// vector u = (a + b w + c w^2) / |.| of every non-uniform kept codon (SURVEY.md 8(a) A4);
-// 2 Re = A, 2 Im = sqrt3 * B, 4 |.|^2 = A^2 + 3 B^2.
-__device__ __forceinline__ void accumulate_codon(int a, int b, int c, bool complete, FrameAcc& f) {
-    if (complete && (a | b | c) != 0) {
-        f.K++;
-        const int nz = (a != 0) + (b != 0) + (c != 0);
-        if (nz == 1) {
-            if (a != 0) f.na++;
-            else if (b != 0) f.nb++;
-            else f.nc++;
-        } else if (a != b || b != c) {
-            const double dA = (double)(2ll * a - b - c);
-            const double dB = (double)((long long)b - c);
-            const double r = rsqrt(fma(dA, dA, 3.0 * dB * dB));
-            f.sre = fma(dA, r, f.sre);
-            f.sim = fma(dB, r, f.sim);
-            f.ng++;
-        }
-    }
-}
+constexpr int kFetchBatch = 8;                 // ORFs claimed per atomic
+constexpr int kBigShift = 20;                  // a value >= 2^20 sends its tile down the 64-bit path
+constexpr int kFlushTiles = 3;                 // packed 10-bit fields hold 3 tiles (<= 9 codons/lane/tile)
 
 __device__ __forceinline__ long long warp_sum_i64(long long v) {
 #pragma unroll
@@ -85,8 +54,56 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     return v;
 }
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 __device__ __forceinline__ int ld_cov(const int32_t* p) { return __ldg(p); }
+
+// Per-lane accumulators of one frame.  w1 / w2 pack 10-bit counters and are flushed into the
+// warp-uniform totals every kFlushTiles tiles; the fp64 sums live for the whole ORF.
+//   w1 = n(a,0,0) | n(0,b,0) << 10 | n(0,0,c) << 20      unit vectors (1,0), (-1/2, +-sqrt3/2)
+//   w2 = n(general) | n(uniform) << 10
+struct FrameLane {
+    unsigned w1 = 0, w2 = 0;
+    double sre = 0.0;   // sum of A / sqrt(A^2 + 3 B^2),            A = 2a - b - c
+    double sim = 0.0;   // sum of B / sqrt(A^2 + 3 B^2) (x sqrt3),  B = b - c
+};
+
+// One complete codon (a,b,c) of one frame: statistics.py:72-90 in closed form.  The reference
+// normalises the triplet by |a + b w + c w^2| and SciPy's coherence then only sees the unit
+// vector u = (a + b w + c w^2) / |.| of every non-uniform kept codon (SURVEY.md 8(a) A4);
+// 2 Re = A, 2 Im = sqrt3 * B, 4 |.|^2 = A^2 + 3 B^2.  Codons with a single non-zero count map
+// to three constant unit vectors and are only counted.
+template <bool Big>
+__device__ __forceinline__ void accumulate_codon(int a, int b, int c, FrameLane& f) {
+    if ((a | b | c) == 0) return;                       // statistics.py:72-73
+    if ((b | c) == 0) f.w1 += 1u;
+    else if ((a | c) == 0) f.w1 += 1u << 10;
+    else if ((a | b) == 0) f.w1 += 1u << 20;
+    else if (a == b && b == c) f.w2 += 1u << 10;        // uniform: counts in K only
+    else {
+        f.w2 += 1u;
+        double dA, dB, r;
+        if (Big) {
+            dA = (double)(2ll * a - b - c);
+            dB = (double)((long long)b - c);
+            r = rsqrt(fma(dA, dA, 3.0 * dB * dB));
+        } else {
+            // |A|, |B| < 2^22: D is exact; MUFU seed (2^-22) + one Newton step -> ~1e-13 relative
+            dA = (double)(2 * a - b - c);
+            dB = (double)(b - c);
+            const double D = fma(dA, dA, (3.0 * dB) * dB);
+            const double r0 = (double)rsqrt_approx((float)D);
+            const double e = fma(-D * r0, r0, 1.0);
+            r = fma(0.5 * r0, e, r0);
+        }
+        f.sre = fma(dA, r, f.sre);
+        f.sim = fma(dB, r, f.sim);
+    }
+}
 
 // Cursor over the concatenated exons of one ORF in PROFILE order (ascending genomic
 // positions for '+', descending for '-': detect_orfs.py:176-187,201-202).  Warp-uniform.
@@ -116,6 +133,54 @@ struct ExonCursor {
     }
 };
 
+// Copy `take` coverage values of the current exon into the tile (4 loads in flight per lane).
+template <int Dir>
+__device__ __forceinline__ void stage_segment(int32_t* dst, const int32_t* src, int take, int lane, int& ormask) {
+    for (int k = lane; k < take; k += 128) {
+        int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+        v0 = ld_cov(src + Dir * k);
+        if (k + 32 < take) v1 = ld_cov(src + Dir * (k + 32));
+        if (k + 64 < take) v2 = ld_cov(src + Dir * (k + 64));
+        if (k + 96 < take) v3 = ld_cov(src + Dir * (k + 96));
+        dst[k] = v0;
+        if (k + 32 < take) dst[k + 32] = v1;
+        if (k + 64 < take) dst[k + 64] = v2;
+        if (k + 96 < take) dst[k + 96] = v3;
+        ormask |= v0 | v1 | v2 | v3;
+    }
+}
+
+// K3 over one staged tile: one lane per codon, so the three frames are three fixed register
+// sets.  Codons [0, nfull) have all three windows complete; the (at most two) codons after them
+// only exist in the last tile and are checked window by window (statistics.py:71).
+template <bool Big, typename CountT>
+__device__ __forceinline__ void score_tile(const int32_t* buf, int nvals, int ncod, int lane, FrameLane& f0,
+                                           FrameLane& f1, FrameLane& f2, CountT& cnt, CountT& mn) {
+    const int nfull = max(nvals - 2, 0) / 3;
+    for (int c = lane; c < nfull; c += 32) {
+        const int32_t* p = buf + 3 * c;
+        const int v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4];
+        const CountT cs = (CountT)(unsigned)v0 + (CountT)(unsigned)v1 + (CountT)(unsigned)v2;   // common.py:177-179
+        cnt += cs;                                                           // detect_orfs.py:278
+        mn = cs < mn ? cs : mn;
+        if ((v0 | v1 | v2 | v3 | v4) != 0) {
+            accumulate_codon<Big>(v0, v1, v2, f0);
+            accumulate_codon<Big>(v1, v2, v3, f1);
+            accumulate_codon<Big>(v2, v3, v4, f2);
+        }
+    }
+    for (int c = nfull + lane; c < ncod; c += 32) {     // ragged end of the profile
+        const int32_t* p = buf + 3 * c;
+        const int v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4];   // zero padded past nvals
+        const CountT cs = (CountT)(unsigned)v0 + (CountT)(unsigned)v1 + (CountT)(unsigned)v2;
+        cnt += cs;
+        mn = cs < mn ? cs : mn;
+        if (3 * c + 2 < nvals) accumulate_codon<Big>(v0, v1, v2, f0);
+        if (3 * c + 3 < nvals) accumulate_codon<Big>(v1, v2, v3, f1);
+        if (3 * c + 4 < nvals) accumulate_codon<Big>(v2, v3, v4, f2);
+    }
+}
+
 struct ScoreArgs {
     const int32_t* cov;
     const uint64_t* orf_desc;   // indexed by absolute ORF id
@@ -126,35 +191,55 @@ struct ScoreArgs {
     rt_score_out out;           // element k <-> ORF orf_lo + k
 };
 
-__global__ void __launch_bounds__(kScoreWarps * 32)
+// Warp-uniform totals of one frame.
+struct FrameTotals {
+    int na = 0, nb = 0, nc = 0, ng = 0, nu = 0;
+    __device__ __forceinline__ void flush(FrameLane& f) {
+        const unsigned t1 = __reduce_add_sync(kFull, f.w1);
+        const unsigned t2 = __reduce_add_sync(kFull, f.w2);
+        na += t1 & 1023;
+        nb += (t1 >> 10) & 1023;
+        nc += t1 >> 20;
+        ng += t2 & 1023;
+        nu += t2 >> 10;
+        f.w1 = f.w2 = 0;
+    }
+};
+
+__global__ void __launch_bounds__(kScoreWarps * 32, 4)
 score_orfs_kernel(const ScoreArgs args) {
     __shared__ __align__(16) int32_t s_buf[kScoreWarps][kBufNt];
     const int lane = threadIdx.x & 31;
     int32_t* buf = s_buf[threadIdx.x >> 5];
     const double kSqrt3 = 1.7320508075688772;
+    const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
 
     for (;;) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(args.work_counter, (unsigned long long)kFetchBatch);
         base = __shfl_sync(kFull, base, 0);
         if ((long long)base + args.orf_lo >= args.orf_hi) break;
+        uint64_t my_desc = 0;
+        if (lane < kFetchBatch && args.orf_lo + (long long)base + lane < args.orf_hi)
+            my_desc = __ldg(args.orf_desc + args.orf_lo + base + lane);
 
         for (int bi = 0; bi < kFetchBatch; ++bi) {
             const long long k_out = (long long)base + bi;
-            const long long orf = args.orf_lo + k_out;
-            if (orf >= args.orf_hi) break;
+            if (args.orf_lo + k_out >= args.orf_hi) break;
 
-            const uint64_t desc = __ldg(args.orf_desc + orf);
+            const uint64_t desc = __shfl_sync(kFull, my_desc, bi);
             ExonCursor cur;
             cur.entries = args.exon_entries + (desc & kBeginMask);
             cur.n = (int)((desc >> 40) & kMaxEntriesPerOrf);
             cur.rev = (desc >> 63) != 0;
 
-            FrameAcc f0, f1, f2;
-            long long count = 0;
+            FrameLane f0, f1, f2;
+            FrameTotals t0, t1, t2;
+            unsigned cnt32 = 0, mn32 = 0xffffffffu;    // per lane, flushed with the packed counters
+            long long count = 0;                       // warp-uniform totals
             long long min_codon = 0x7fffffffffffffffll;
-            long long total = 0;   // profile length so far
-            int fill = 0;
+            long long total = 0;                       // profile length so far
+            int fill = 0, ormask = 0, pending = 0;
             bool last = false;
 
             while (!last) {
@@ -165,11 +250,9 @@ score_orfs_kernel(const ScoreArgs args) {
                     if (cur.zero) {
                         for (int k = lane; k < take; k += 32) buf[fill + k] = 0;
                     } else if (cur.rev) {
-                        const int32_t* src = args.cov + cur.pos;
-                        for (int k = lane; k < take; k += 32) buf[fill + k] = ld_cov(src - k);
+                        stage_segment<-1>(buf + fill, args.cov + cur.pos, take, lane, ormask);
                     } else {
-                        const int32_t* src = args.cov + cur.pos;
-                        for (int k = lane; k < take; k += 32) buf[fill + k] = ld_cov(src + k);
+                        stage_segment<1>(buf + fill, args.cov + cur.pos, take, lane, ormask);
                     }
                     fill += take;
                     total += take;
@@ -180,17 +263,28 @@ score_orfs_kernel(const ScoreArgs args) {
                 if (last && lane < 6) buf[nvals + lane] = 0;   // nvals + 5 < kBufNt
                 __syncwarp();
 
-                // ---- K3: one lane per codon; frames are fixed per register set ----
+                // ---- K3 ----
                 const int ncod = last ? (nvals + 2) / 3 : kTileCodons;
-                for (int c = lane; c < ncod; c += 32) {
-                    const int32_t* p = buf + 3 * c;
-                    const int v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4];
-                    const long long cs = (long long)v0 + v1 + v2;     // common.py:177-179
-                    count += cs;                                      // detect_orfs.py:278
-                    min_codon = cs < min_codon ? cs : min_codon;
-                    accumulate_codon(v0, v1, v2, 3 * c + 2 < nvals, f0);   // statistics.py:71
-                    accumulate_codon(v1, v2, v3, 3 * c + 3 < nvals, f1);
-                    accumulate_codon(v2, v3, v4, 3 * c + 4 < nvals, f2);
+                const bool big = __any_sync(kFull, (ormask >> kBigShift) != 0);
+                if (!big) {
+                    score_tile<false, unsigned>(buf, nvals, ncod, lane, f0, f1, f2, cnt32, mn32);
+                } else {   // huge counts: 64-bit codon sums, reduced right away
+                    long long c64 = 0, m64 = 0x7fffffffffffffffll;
+                    score_tile<true, long long>(buf, nvals, ncod, lane, f0, f1, f2, c64, m64);
+                    count += warp_sum_i64(c64);
+                    const long long m = warp_min_i64(m64);
+                    min_codon = m < min_codon ? m : min_codon;
+                }
+                if (++pending == kFlushTiles || last) {
+                    t0.flush(f0);
+                    t1.flush(f1);
+                    t2.flush(f2);
+                    count += __reduce_add_sync(kFull, cnt32);
+                    const unsigned m = __reduce_min_sync(kFull, mn32);
+                    if (m != 0xffffffffu && (long long)m < min_codon) min_codon = m;
+                    cnt32 = 0;
+                    mn32 = 0xffffffffu;
+                    pending = 0;
                 }
                 __syncwarp();
                 if (!last) {   // carry the 2-value halo to the front of the next tile
@@ -199,81 +293,83 @@ score_orfs_kernel(const ScoreArgs args) {
                     __syncwarp();
                     if (lane < 2) buf[lane] = t;
                     fill = 2;
-                    total -= 0;
                     __syncwarp();
                 }
             }
 
-            // ---- warp reductions ----
-            FrameAcc* fr[3] = {&f0, &f1, &f2};
-            int K[3], M[3];
-            double re[3], im[3];
-            const bool any_general = __any_sync(kFull, (f0.ng | f1.ng | f2.ng) != 0);
-#pragma unroll
-            for (int f = 0; f < 3; ++f) {
-                K[f] = __reduce_add_sync(kFull, fr[f]->K);
-                const int na = __reduce_add_sync(kFull, fr[f]->na);
-                const int nb = __reduce_add_sync(kFull, fr[f]->nb);
-                const int nc = __reduce_add_sync(kFull, fr[f]->nc);
-                const int ng = __reduce_add_sync(kFull, fr[f]->ng);
-                double sre = 0.0, sim = 0.0;
-                if (any_general) {
-                    sre = warp_sum_f64(fr[f]->sre);
-                    sim = warp_sum_f64(fr[f]->sim);
+            // ---- epilogue: statistics.py:92-115 + detect_orfs.py:278-299 ----
+            const long long L = total;
+            const long long n_codons = L / 3 > 1 ? L / 3 : 1;             // detect_orfs.py:281
+            double score = 0.0, ratio = 0.0, density = 0.0;
+            int valid = 0;
+            int K0 = 0, K1 = 0, K2 = 0;
+            double s0 = kNaN, s1 = kNaN, s2 = kNaN;
+            if (L == 0) min_codon = 0;
+            if (count != 0) {
+                K0 = t0.na + t0.nb + t0.nc + t0.ng + t0.nu;
+                K1 = t1.na + t1.nb + t1.nc + t1.ng + t1.nu;
+                K2 = t2.na + t2.nb + t2.nc + t2.ng + t2.nu;
+                double re0 = 0.0, im0 = 0.0, re1 = 0.0, im1 = 0.0, re2 = 0.0, im2 = 0.0;
+                if ((t0.ng | t1.ng | t2.ng) != 0) {
+                    re0 = warp_sum_f64(f0.sre); im0 = warp_sum_f64(f0.sim);
+                    re1 = warp_sum_f64(f1.sre); im1 = warp_sum_f64(f1.sim);
+                    re2 = warp_sum_f64(f2.sre); im2 = warp_sum_f64(f2.sim);
                 }
-                M[f] = na + nb + nc + ng;
-                re[f] = sre + ((double)na - 0.5 * ((double)nb + (double)nc));
-                im[f] = kSqrt3 * (sim + 0.5 * ((double)nb - (double)nc));
-            }
-            count = warp_sum_i64(count);
-            min_codon = warp_min_i64(min_codon);
-
-            if (lane == 0) {
+                re0 += 0.5 * (double)(2 * t0.na - t0.nb - t0.nc); im0 = kSqrt3 * (im0 + 0.5 * (double)(t0.nb - t0.nc));
+                re1 += 0.5 * (double)(2 * t1.na - t1.nb - t1.nc); im1 = kSqrt3 * (im1 + 0.5 * (double)(t1.nb - t1.nc));
+                re2 += 0.5 * (double)(2 * t2.na - t2.nb - t2.nc); im2 = kSqrt3 * (im2 + 0.5 * (double)(t2.nb - t2.nc));
+                // one fp64 division sequence for all seven quotients: lanes 0-2 the coherences
+                // |sum u|^2 / (K * M), lane 3 the density, lanes 4-6 K_f / n_codons
+                double nn, dd = (double)n_codons;
+                if (lane == 0) { nn = re0 * re0 + im0 * im0; dd = (double)K0 * (double)(K0 - t0.nu); }
+                else if (lane == 1) { nn = re1 * re1 + im1 * im1; dd = (double)K1 * (double)(K1 - t1.nu); }
+                else if (lane == 2) { nn = re2 * re2 + im2 * im2; dd = (double)K2 * (double)(K2 - t2.nu); }
+                else if (lane == 3) nn = (double)count;                  // detect_orfs.py:287
+                else if (lane == 4) nn = (double)K0;                     // detect_orfs.py:285
+                else if (lane == 5) nn = (double)K1;
+                else nn = (double)K2;
+                const double q = nn / dd;                                // 0/0 -> NaN never wins
+                s0 = __shfl_sync(kFull, q, 0);
+                s1 = __shfl_sync(kFull, q, 1);
+                s2 = __shfl_sync(kFull, q, 2);
+                density = __shfl_sync(kFull, q, 3);
                 // statistics.py:64-66,92-115: running maximum with the K==0 reset quirk
                 double coh = 0.0;
-                int valid = -1;
-                double s3[3];
-#pragma unroll
-                for (int f = 0; f < 3; ++f) {
-                    if (K[f] == 0) {
-                        s3[f] = __longlong_as_double(0x7ff8000000000000ll);
-                        coh = 0.0;
-                        valid = 0;
-                        continue;
-                    }
-                    // Cxy(1/3) = |sum u|^2 / (K * M); 0/0 -> NaN never wins (all codons uniform)
-                    const double s = (re[f] * re[f] + im[f] * im[f]) / ((double)K[f] * (double)M[f]);
-                    s3[f] = s;
-                    if (s > coh) { coh = s; valid = K[f]; }
-                    if (valid == -1) valid = K[f];
-                }
-                const double score = sqrt(coh);
-                const long long L = total;
-                const long long n_codons = L / 3 > 1 ? L / 3 : 1;            // detect_orfs.py:281
-                const double ratio = (double)valid / (double)n_codons;      // :285
-                const double density = (double)count / (double)n_codons;    // :287
+                int vf = -1;          // frame whose K is `valid`; -1: valid = 0
+                bool unset = true;    // valid == -1 in the reference
+                if (K0 == 0) { coh = 0.0; vf = -1; unset = false; s0 = kNaN; }
+                else { if (s0 > coh) { coh = s0; vf = 0; unset = false; } if (unset) { vf = 0; unset = false; } }
+                if (K1 == 0) { coh = 0.0; vf = -1; unset = false; s1 = kNaN; }
+                else { if (s1 > coh) { coh = s1; vf = 1; unset = false; } if (unset) { vf = 1; unset = false; } }
+                if (K2 == 0) { coh = 0.0; vf = -1; unset = false; s2 = kNaN; }
+                else { if (s2 > coh) { coh = s2; vf = 2; unset = false; } if (unset) { vf = 2; unset = false; } }
+                score = sqrt(coh);                                       // statistics.py:115
+                valid = vf == 0 ? K0 : vf == 1 ? K1 : vf == 2 ? K2 : 0;
+                ratio = __shfl_sync(kFull, q, vf >= 0 ? 4 + vf : 4);
+                if (vf < 0) ratio = 0.0;
+            }
+            if (lane == 0) {
                 const bool ok = score >= args.prm.phase_score_cutoff &&
                                 (double)valid >= args.prm.min_valid_codons &&
                                 (L == 0 || (double)min_codon >= args.prm.min_reads_per_codon) &&
                                 ratio >= args.prm.min_valid_codons_ratio &&
-                                density >= args.prm.min_density_over_orf;   // :289-299
+                                density >= args.prm.min_density_over_orf;   // detect_orfs.py:289-299
                 args.out.score[k_out] = score;
                 args.out.valid[k_out] = valid;
                 args.out.count[k_out] = count;
                 args.out.length[k_out] = (int32_t)L;
                 if (args.out.min_codon)
-                    args.out.min_codon[k_out] =
-                        L == 0 ? 0 : (min_codon > 0x7fffffffll ? 0x7fffffff : (int32_t)min_codon);
+                    args.out.min_codon[k_out] = min_codon > 0x7fffffffll ? 0x7fffffff : (int32_t)min_codon;
                 if (args.out.status) args.out.status[k_out] = ok ? 1 : 0;
                 if (args.out.frame_K) {
-                    args.out.frame_K[3 * k_out + 0] = K[0];
-                    args.out.frame_K[3 * k_out + 1] = K[1];
-                    args.out.frame_K[3 * k_out + 2] = K[2];
+                    args.out.frame_K[3 * k_out + 0] = K0;
+                    args.out.frame_K[3 * k_out + 1] = K1;
+                    args.out.frame_K[3 * k_out + 2] = K2;
                 }
                 if (args.out.frame_s) {
-                    args.out.frame_s[3 * k_out + 0] = s3[0];
-                    args.out.frame_s[3 * k_out + 1] = s3[1];
-                    args.out.frame_s[3 * k_out + 2] = s3[2];
+                    args.out.frame_s[3 * k_out + 0] = s0;
+                    args.out.frame_s[3 * k_out + 1] = s1;
+                    args.out.frame_s[3 * k_out + 2] = s2;
                 }
             }
             __syncwarp();
@@ -347,8 +443,7 @@ constexpr int kBinThreads = 256;
 constexpr int kBinReadsPerThread = 8;
 constexpr int kLenHist = 512;   // read lengths below this are histogrammed in shared memory
 
-// Category of one read after the cascade of bam.py:77-91 and the validity test of :133.
-// 0..5 map to RT_ST_QCFAIL..RT_ST_MULTI (offset by 1), 6 = valid, 7 = bad ref, 8 = ignored.
+// Category of one read after the cascade of bam.py:77-91: one of RT_ST_QCFAIL .. RT_ST_VALID.
 __device__ __forceinline__ int classify_read(unsigned fl, unsigned mapq, unsigned nh) {
     if (fl & 0x200) return RT_ST_QCFAIL;      // bam.py:77
     if (fl & 0x400) return RT_ST_DUPLICATE;   // bam.py:80
@@ -370,15 +465,16 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
 
     const int lane = threadIdx.x & 31;
     const long long block_base = (long long)blockIdx.x * (kBinThreads * kBinReadsPerThread);
+    // per-thread 4-bit counters of categories RT_ST_QCFAIL..RT_ST_BADREF (<= 8 reads per thread)
+    unsigned packed = 0;
 #pragma unroll 2
     for (int it = 0; it < kBinReadsPerThread; ++it) {
         const long long i = block_base + (long long)it * kBinThreads + threadIdx.x;
-        const bool in = i < a.n;
-        int cat = -1;       // -1: no read
-        int len = -1;       // >= 0: counts in read_length_counts
-        if (in) {
+        int len = -1;            // >= 0: counts in read_length_counts
+        long long slot = -1;     // >= 0: coverage slot to bump
+        if (i < a.n) {
             const unsigned fl = a.flag[i];
-            cat = classify_read(fl, a.mapq[i], a.nh[i]);
+            int cat = classify_read(fl, a.mapq[i], a.nh[i]);
             if (cat == RT_ST_VALID) {
                 const int l = a.mlen[i];                        // bam.py:99
                 const int mode = __ldg(a.len_table + l);
@@ -394,50 +490,45 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
                 }
                 const int c = a.ref_id[i];
                 if (mode == RT_LEN_FILTERED || a.protocol > RT_PROTOCOL_REVERSE) {
-                    cat = -2;                                   // bam.py:101 / no protocol branch
+                    cat = 0;                                    // bam.py:101 / no protocol branch: only `total`
                 } else if (c < 0 || c >= a.n_contig) {
                     cat = RT_ST_BADREF;                         // chrom is None, bam.py:133
                 } else {
                     len = l;                                    // bam.py:136
                     if (mode >= 0) {                            // detect_orfs.py:74
                         const long long p = pos + 1 + (strand == 0 ? mode : -mode);   // bam.py:135, detect_orfs.py:78-81
-                        if (p < 1 - a.pad || p > a.contig_len[c] + a.pad) {
-                            atomicAdd(&s_stats[RT_ST_OOB], 1u);
-                        } else {
-                            atomicAdd(a.cov + ((long long)strand * a.plane + a.contig_base[c] + a.pad + p), a.weight);   // detect_orfs.py:82
-                        }
+                        if (p < 1 - a.pad || p > a.contig_len[c] + a.pad) atomicAdd(&s_stats[RT_ST_OOB], 1u);
+                        else slot = (long long)strand * a.plane + a.contig_base[c] + a.pad + p;
                     }
                 }
             }
+            if (cat) packed += 1u << (4 * (cat - 1));
         }
-        // warp-aggregated counters (bam.py:61,73-91,137)
-        const unsigned m_in = __ballot_sync(kFull, cat != -1);
-        if (m_in == 0) continue;
-#pragma unroll
-        for (int k = RT_ST_QCFAIL; k <= RT_ST_VALID; ++k) {
-            const unsigned m = __ballot_sync(kFull, cat == k);
-            if (lane == 0 && m) atomicAdd(&s_stats[k], (unsigned)__popc(m));
-        }
-        const unsigned m_bad = __ballot_sync(kFull, cat == RT_ST_BADREF);
-        if (lane == 0) {
-            atomicAdd(&s_stats[RT_ST_TOTAL], (unsigned)__popc(m_in));
-            if (m_bad) atomicAdd(&s_stats[RT_ST_BADREF], (unsigned)__popc(m_bad));
-        }
-        // read_length_counts (bam.py:136): one leader per distinct length in the warp
-        unsigned todo = __ballot_sync(kFull, len >= 0);
-        while (todo) {
-            const int leader = __ffs(todo) - 1;
-            const int l = __shfl_sync(kFull, len, leader);
-            const unsigned same = __ballot_sync(kFull, len == l);
-            if (lane == leader) {
-                if (l < kLenHist) atomicAdd(&s_len[l], (unsigned)__popc(same));
-                else atomicAdd(a.len_counts + l, (unsigned long long)((long long)a.weight * __popc(same)));
-            }
-            todo &= ~same;
+        // detect_orfs.py:82: one atomic per distinct slot in the warp (duplicated 5' ends are the
+        // rule in Ribo-seq, and adjacent in a coordinate-sorted BAM)
+        const unsigned same_slot = __match_any_sync(kFull, slot);
+        if (slot >= 0 && lane == __ffs(same_slot) - 1)
+            atomicAdd(a.cov + slot, a.weight * __popc(same_slot));
+        // bam.py:136: one shared-memory atomic per distinct read length in the warp
+        const unsigned same_len = __match_any_sync(kFull, len);
+        if (len >= 0 && lane == __ffs(same_len) - 1) {
+            if (len < kLenHist) atomicAdd(&s_len[len], (unsigned)__popc(same_len));
+            else atomicAdd(a.len_counts + len, (unsigned long long)((long long)a.weight * __popc(same_len)));
         }
     }
+    // bam.py:61,73-91,137: categories RT_ST_QCFAIL (slot 1) .. RT_ST_BADREF (slot 8), minus OOB
+    unsigned mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const unsigned v = __reduce_add_sync(kFull, (packed >> (4 * k)) & 15u);
+        if (lane == k) mine = v;
+    }
+    if (lane < 8 && mine) atomicAdd(&s_stats[1 + lane], mine);
+    if (threadIdx.x == 0) {
+        const long long left = a.n - block_base;
+        s_stats[RT_ST_TOTAL] = (unsigned)(left < kBinThreads * kBinReadsPerThread ? left : kBinThreads * kBinReadsPerThread);
+    }
     __syncthreads();
-    // RT_ST_VALID in s_stats counts reads that passed the cascade; badref/ignored were re-labelled above
     // two's-complement wrap makes weight = -1 subtract
     if (threadIdx.x < RT_N_STATS && s_stats[threadIdx.x])
         atomicAdd(a.stats + threadIdx.x, (unsigned long long)((long long)a.weight * s_stats[threadIdx.x]));

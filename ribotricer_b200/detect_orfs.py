@@ -1,0 +1,311 @@
+"""``detect-orfs`` on the GPU -- same function surface as ribotricer/detect_orfs.py.
+
+    merge_read_lengths   detect_orfs.py:54     -> K1 (bin_psites_kernel)
+    orf_coverage         detect_orfs.py:134    -> K4 (gather_profiles_kernel)
+    export_orf_coverages detect_orfs.py:206    -> K2+K3 (score_orfs_kernel) + K4 + TSV writer
+    export_wig           detect_orfs.py:327
+    detect_orfs          detect_orfs.py:354    (same positional signature; learn_cutoff.py:231 calls it)
+
+The dict-of-Counter values of the reference become device-resident objects:
+``Alignments`` (read columns in HBM) and ``MergedAlignments`` (dense P-site
+coverage planes in HBM).
+"""
+from __future__ import annotations
+
+import datetime
+import os
+import pathlib
+import sys
+from collections import Counter, defaultdict
+
+import numpy as np
+
+from .bam import Alignments, split_bam
+from .const import (CUTOFF, MINIMUM_DENSITY_OVER_ORF, MINIMUM_READS_PER_CODON, MINIMUM_VALID_CODONS,
+                    MINIMUM_VALID_CODONS_RATIO)
+from .engine import Engine, ScoreParams
+from .index import ORF, PackedIndex, parse_index
+
+_ENGINE: Engine | None = None
+_INDEX_CACHE: dict = {}
+
+TSV_COLUMNS = [
+    "ORF_ID", "ORF_type", "status", "phase_score", "read_count", "length", "valid_codons",
+    "valid_codons_ratio", "read_density", "transcript_id", "transcript_type", "gene_id", "gene_name",
+    "gene_type", "chrom", "strand", "start_codon", "profile",
+]   # detect_orfs.py:241-260
+
+
+def get_engine(device: int | None = None) -> Engine:
+    """Process-wide engine (one rt_ctx per process and GPU)."""
+    global _ENGINE
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if _ENGINE is None or _ENGINE.device_index != device or _ENGINE.ctx is None:
+        _ENGINE = Engine(device)
+    return _ENGINE
+
+
+def load_index(path: str) -> PackedIndex:
+    """Parse (once per process and file version) the candidate-ORF index."""
+    st = os.stat(path)
+    key = (os.path.abspath(path), st.st_mtime_ns, st.st_size)
+    if key not in _INDEX_CACHE:
+        _INDEX_CACHE.clear()
+        _INDEX_CACHE[key] = parse_index(path)
+    return _INDEX_CACHE[key]
+
+
+class MergedAlignments:
+    """P-site coverage of one library after offset shifting and merging over read lengths
+    (what merge_read_lengths returns, detect_orfs.py:49,72-83), as dense planes in HBM."""
+
+    def __init__(self, engine: Engine, cov):
+        self.engine = engine
+        self.cov = cov
+
+    def nonzero(self):
+        """(strand_code, contig_id, pos, count) arrays of every covered position, ordered by
+        strand, contig and position.  Plumbing for the WIG side output and for tests."""
+        eng, t = self.engine, self.engine.torch
+        out = []
+        for strand in (0, 1):
+            for c in range(len(eng.contig_len)):
+                lo = strand * eng.plane + int(eng.contig_base[c])
+                span = int(eng.contig_len[c]) + 2 * eng.pad + 1
+                seg = self.cov[lo:lo + span]
+                nz = t.nonzero(seg).flatten()
+                if nz.numel():
+                    out.append((np.full(nz.numel(), strand, np.int8), np.full(nz.numel(), c, np.int32),
+                                (nz - eng.pad).cpu().numpy(), seg[nz].cpu().numpy()))
+        if not out:
+            z = np.zeros(0, np.int64)
+            return z.astype(np.int8), z.astype(np.int32), z, z.astype(np.int32)
+        return tuple(np.concatenate(x) for x in zip(*out))
+
+    def to_dict(self):
+        """The reference's ``merged[strand][(chrom, pos)] -> count`` view (small libraries only)."""
+        merged = defaultdict(Counter)
+        s, c, p, n = self.nonzero()
+        names = self.engine.contig_names
+        for i in range(len(s)):
+            merged["+" if s[i] == 0 else "-"][(names[c[i]], int(p[i]))] = int(n[i])
+        return merged
+
+
+def merge_read_lengths(alignments: Alignments, psite_offsets: dict) -> MergedAlignments:
+    """detect_orfs.py:54-83: shift every read of a length in ``psite_offsets`` by its offset
+    ('+': pos + offset, '-': pos - offset) and sum over lengths -- one K1 launch."""
+    eng = alignments.engine
+    cov = eng.new_coverage()
+    alignments.bin_into(cov, psite_offsets)
+    return MergedAlignments(eng, cov)
+
+
+def parse_ribotricer_index(ribotricer_index: str):
+    """detect_orfs.py:86-131: the leading 'annotated' rows as ORF objects plus, per chromosome,
+    the (start, end, strand) spans that infer_protocol needs."""
+    idx = load_index(ribotricer_index)
+    annotated, refseq = [], defaultdict(list)
+    for o in range(idx.n_annotated_prefix):
+        f = idx.fields[o]
+        if f[0] != "annotated":       # detect_orfs.py:120
+            continue
+        a, b = idx.exon_ptr[o], idx.exon_ptr[o + 1]
+        ivs = list(zip(idx.exon_start[a:b].tolist(), idx.exon_end[a:b].tolist()))
+        orf = ORF(f[0], f[1], f[2], f[3], f[4], f[5], idx.chrom[o], idx.strand[o], ivs, f[6])
+        orf.row = o
+        refseq[orf.chrom].append((ivs[0][0], ivs[-1][1], 1 if orf.strand == "+" else -1))
+        annotated.append(orf)
+    return annotated, refseq
+
+
+def _aux_engine(eng: Engine) -> Engine:
+    """Second ctx on the same GPU for small auxiliary indexes (single-ORF queries, metagene
+    windows); shares the caller-owned coverage buffer, leaves the resident index alone."""
+    aux = getattr(eng, "_aux", None)
+    if aux is None or aux.ctx is None:
+        aux = Engine(eng.device_index)
+        eng._aux = aux
+    if aux.plane != eng.plane or aux.pad != eng.pad or list(aux.contig_names) != list(eng.contig_names):
+        aux.set_genome(eng.contig_names, eng.contig_len, eng.pad)
+    return aux
+
+
+def orf_coverage(orf: ORF, alignments: MergedAlignments, offset_5p: int = 0, offset_3p: int = 0) -> list:
+    """detect_orfs.py:134-203 for one ORF: coverage over the leader, every interval and the
+    trailer, reversed on the '-' strand."""
+    eng = alignments.engine
+    if orf.strand == "-":
+        offset_5p, offset_3p = offset_3p, offset_5p
+    ivs = [list(iv) for iv in orf.intervals]
+    ivs[0][0] -= offset_5p
+    ivs[-1][1] += offset_3p
+    aux = _aux_engine(eng)
+    aux.set_index(np.array([0, len(ivs)], np.int64), np.array([iv[0] for iv in ivs], np.int32),
+                  np.array([iv[1] for iv in ivs], np.int32),
+                  np.array([eng.contig_id(orf.chrom)], np.int32),
+                  np.array([0 if orf.strand == "+" else 1 if orf.strand == "-" else 2], np.uint8))
+    length = sum(iv[1] - iv[0] + 1 for iv in ivs)
+    _, prof = aux.gather_profiles(alignments.cov, np.array([0], np.int64), np.array([length], np.int64))
+    return prof.tolist()
+
+
+def export_orf_coverages(
+    ribotricer_index: str,
+    merged_alignments: MergedAlignments,
+    prefix: str,
+    phase_score_cutoff: float = CUTOFF,
+    min_valid_codons: int = MINIMUM_VALID_CODONS,
+    min_reads_per_codon: float = MINIMUM_READS_PER_CODON,
+    min_valid_codons_ratio: float = MINIMUM_VALID_CODONS_RATIO,
+    min_density_over_orf: float = MINIMUM_DENSITY_OVER_ORF,
+    report_all: bool = False,
+    orf_range: tuple | None = None,
+    write_header: bool = True,
+    path: str | None = None,
+) -> dict:
+    """detect_orfs.py:206-324: score every ORF of the index in index order and write
+    ``{prefix}_translating_ORFs.tsv`` (non-translating rows only with ``report_all``).
+
+    ``orf_range`` / ``write_header`` / ``path`` are extensions used by the multi-GPU driver
+    (each rank writes the rows of its ORF shard).  Returns the per-ORF result columns.
+    """
+    eng = merged_alignments.engine
+    idx = load_index(ribotricer_index)
+    if getattr(eng, "_resident_index", None) is not idx:
+        lut = {n: i for i, n in enumerate(eng.contig_names)}
+        eng.set_index(**idx.device_columns(lut))
+        eng._resident_index = idx
+    lo, hi = orf_range if orf_range is not None else (0, idx.n_orf)
+    params = ScoreParams(phase_score_cutoff, min_valid_codons, min_reads_per_codon, min_valid_codons_ratio,
+                         min_density_over_orf)
+    res = eng.score_host(merged_alignments.cov, lo, hi, params)
+    write_tsv(path or f"{prefix}_translating_ORFs.tsv", idx, res, merged_alignments, lo, hi, report_all, write_header)
+    return res
+
+
+def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: int, hi: int, report_all: bool,
+              write_header: bool = True, chunk_nt: int = 1 << 27):
+    """Rows exactly as detect_orfs.py:304-323 formats them: np.float64 phase score and read
+    density, Python-float ratio, ``str(list)`` profile."""
+    eng = merged.engine
+    keep = np.arange(lo, hi) if report_all else lo + np.flatnonzero(res["status"])
+    length = res["length"].astype(np.int64)
+    n_codons = np.maximum(1, length // 3)                         # detect_orfs.py:281
+    ratio = res["valid"].astype(np.float64) / n_codons           # :285
+    density = res["count"].astype(np.float64) / n_codons         # :287
+    with open(path, "w") as out:
+        if write_header:
+            out.write("\t".join(TSV_COLUMNS) + "\n")
+        at = 0
+        while at < len(keep):
+            # bounded chunks of reported ORFs so the profile buffer stays small
+            csum = np.cumsum(length[keep[at:] - lo])
+            n_take = max(1, int(np.searchsorted(csum, chunk_nt, side="right")))
+            sel = keep[at:at + n_take]
+            ptr, prof = eng.gather_profiles(merged.cov, sel, length[sel - lo])
+            rows = []
+            for j, o in enumerate(sel.tolist()):
+                k = o - lo
+                f = idx.fields[o]
+                rows.append("\t".join((
+                    idx.oid(o), f[0], "translating" if res["status"][k] else "nontranslating",
+                    str(res["score"][k]), str(int(res["count"][k])), str(int(length[k])),
+                    str(int(res["valid"][k])), repr(float(ratio[k])), str(density[k]),
+                    f[1], f[2], f[3], f[4], f[5], idx.chrom[o], idx.strand[o], f[6],
+                    str(prof[ptr[j]:ptr[j + 1]].tolist()))))
+            out.write("\n".join(rows) + "\n")
+            at += n_take
+
+
+def export_wig(merged_alignments: MergedAlignments, prefix: str) -> None:
+    """detect_orfs.py:327-351: variableStep WIG per strand, chromosomes in lexicographic order,
+    only strands that carry coverage."""
+    s, c, p, n = merged_alignments.nonzero()
+    names = merged_alignments.engine.contig_names
+    order = sorted(range(len(names)), key=lambda i: names[i])
+    for strand, tag in ((0, "pos"), (1, "neg")):
+        m = s == strand
+        if not m.any():
+            continue
+        parts = []
+        for ci in order:
+            mm = m & (c == ci)
+            if not mm.any():
+                continue
+            parts.append(f"variableStep chrom={names[ci]}\n")
+            parts.append("".join(f"{pos}\t{cnt}\n" for pos, cnt in zip(p[mm].tolist(), n[mm].tolist())))
+        with open(f"{prefix}_{tag}.wig", "w") as output:
+            output.write("".join(parts))
+
+
+def _stamp(msg: str) -> None:
+    print("{} ... {}".format(datetime.datetime.now().strftime("%b %d %H:%M:%S"), msg))
+
+
+def detect_orfs(
+    bam,
+    ribotricer_index: str,
+    prefix: str,
+    protocol: str | None,
+    read_lengths: list | None,
+    psite_offsets: dict | None,
+    phase_score_cutoff: float,
+    min_valid_codons: int,
+    min_reads_per_codon: float,
+    min_valid_codons_ratio: float,
+    min_density_over_orf: float,
+    report_all: bool,
+    meta_min_reads: int = 100000,
+) -> None:
+    """Same positional signature and side files as detect_orfs.py:354-526.
+
+    ``bam`` may be a BAM (decoded on the host with pysam), a ``.npz`` of decoded read columns
+    or a ``ReadColumns`` object.
+    """
+    from . import metagene as mg
+    from .bam import load_reads
+
+    print(datetime.datetime.now().strftime("%b %d %H:%M:%S ..... started ribotricer detect-orfs"))
+    _stamp("started parsing ribotricer index file")
+    annotated, refseq = parse_ribotricer_index(ribotricer_index)
+    pathlib.Path(os.path.dirname(prefix) or ".").mkdir(parents=True, exist_ok=True)   # common.py:103,131
+
+    reads = load_reads(bam)
+    if protocol is None:
+        _stamp("started inferring experimental design")
+        protocol = mg.infer_protocol(reads, refseq, prefix)
+    del refseq
+
+    _stamp("started reading bam file")
+    alignments, read_length_counts = split_bam(reads, protocol, prefix, read_lengths)
+
+    _stamp("started plotting read length distribution")
+    mg.plot_read_lengths(read_length_counts, prefix)
+
+    _stamp("started calculating metagene profiles. This may take a long time...")
+    metagenes = mg.metagene_coverage(annotated, alignments, read_length_counts, prefix,
+                                     meta_min_reads=meta_min_reads)
+    _stamp("started plotting metagene profiles")
+    mg.plot_metagene(metagenes, read_length_counts, prefix)
+
+    if psite_offsets is None:
+        _stamp("started inferring P-site offsets")
+        psite_offsets = mg.align_metagenes(metagenes, read_length_counts, prefix, phase_score_cutoff,
+                                           read_lengths is None)
+
+    _stamp("started shifting according to P-site offsets")
+    merged_alignments = merge_read_lengths(alignments, psite_offsets)
+
+    _stamp("started exporting wig file of alignments after shifting")
+    export_wig(merged_alignments, prefix)
+
+    _stamp("started calculating phase scores for each ORF")
+    export_orf_coverages(ribotricer_index, merged_alignments, prefix, phase_score_cutoff, min_valid_codons,
+                         min_reads_per_codon, min_valid_codons_ratio, min_density_over_orf, report_all)
+    _stamp("finished ribotricer detect-orfs")
+
+
+__all__ = ["detect_orfs", "merge_read_lengths", "orf_coverage", "export_orf_coverages", "export_wig",
+           "parse_ribotricer_index", "MergedAlignments", "get_engine", "load_index", "sys"]

@@ -176,12 +176,12 @@ def test_edge_cases(engine):
     CO = _oracle()
     rng = np.random.default_rng(5)
     lens = np.array([5000, 300], np.int64)
-    pad = 8
+    pad = 16
     orfs = [
         (0, 0, [(1, 1)]), (0, 1, [(10, 11)]), (0, 0, [(20, 22)]), (0, 1, [(30, 33)]),
         (0, 0, [(40, 40), (42, 42), (44, 44), (46, 60)]),            # 1-nt exons
         (-1, 0, [(1, 90)]), (0, 2, [(1, 90)]),                        # unknown contig / strand
-        (1, 0, [(-20, 30)]), (1, 1, [(280, 330)]), (1, 0, [(-50, -20)]), (1, 1, [(400, 450)]),
+        (1, 0, [(-30, 30)]), (1, 1, [(280, 340)]), (1, 0, [(-50, -20)]), (1, 1, [(400, 450)]),
         (0, 0, [(100, 100 + 767)]), (0, 1, [(100, 100 + 768)]), (0, 0, [(100, 100 + 769)]),
         (0, 1, [(100, 100 + 770)]), (0, 0, [(100, 100 + 771)]), (0, 0, [(100, 100 + 1535)]),
         (0, 1, [(100, 100 + 1537)]), (0, 0, [(1, 4999)]), (0, 1, [(2, 5000)]),
