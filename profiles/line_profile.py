@@ -30,7 +30,7 @@ for ln in dis.splitlines():
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
-        cur = int(m.group(2))
+        cur = (os.path.basename(m.group(1)), int(m.group(2)))
         continue
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
     if m:
@@ -54,5 +54,6 @@ for (line, _), r in zip(lines, sass):
     tot_s += s
 print(f"total warp instructions {tot_i}, samples {tot_s}")
 for line, (n, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-    text = src[line - 1].strip() if line and line <= len(src) else "?"
-    print(f"{n:>13} {100 * n / tot_i:5.1f}%  smp {100 * s / max(1, tot_s):5.1f}%  L{line}: {text[:100]}")
+    fname, ln = line if line else ("?", 0)
+    text = src[ln - 1].strip() if fname == "rt_kernels.cuh" and 0 < ln <= len(src) else fname
+    print(f"{n:>13} {100 * n / tot_i:5.1f}%  smp {100 * s / max(1, tot_s):5.1f}%  L{ln}: {text[:100]}")

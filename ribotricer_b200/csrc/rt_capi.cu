@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -58,7 +59,17 @@ struct rt_ctx {
     uint64_t* d_exon_entries = nullptr;
     std::vector<int64_t> bytes_prefix;  // n_orf + 1: prefix of 4L + 8E + 42
     std::vector<int64_t> nt_prefix;     // n_orf + 1: prefix of L
-    unsigned long long* d_work_counter = nullptr;
+    unsigned long long* d_work_counter = nullptr;   // 4 x u64: work counters of the 3 score launches + fallback count
+    int pack_lpo = 8;                                // lanes per ORF of the packed kernel (RT_PACK_LPO)
+
+    // score plan: ORFs of a range sorted by length (longest first), split by kernel
+    struct ScorePlan {
+        int64_t lo = -1, hi = -1;
+        int32_t* d_list = nullptr;      // [n_long | n_short] absolute ORF ids
+        int32_t* d_fallback = nullptr;  // capacity n_short
+        int64_t n_long = 0, n_short = 0;
+    };
+    std::vector<ScorePlan> plans;
 
     // scratch for the host-buffer entry points
     DevBuf read_slot[2];
@@ -134,10 +145,14 @@ int rt_create(int device, rt_ctx** out) {
     rt_ctx* ctx = new rt_ctx();
     ctx->device = device;
     ctx->n_sm = prop.multiProcessorCount;
-    if (cudaMalloc(&ctx->d_work_counter, sizeof(unsigned long long)) != cudaSuccess ||
+    if (cudaMalloc(&ctx->d_work_counter, 4 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&ctx->d_len_table, sizeof(int32_t) * RT_LEN_TABLE) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, RT_ENOMEM, "rt_create: cudaMalloc failed");
+    }
+    if (const char* e = getenv("RT_PACK_LPO")) {
+        const int v = atoi(e);
+        if (v == 8 || v == 16 || v == 32) ctx->pack_lpo = v;
     }
     *out = ctx;
     return RT_OK;
@@ -152,6 +167,10 @@ void rt_destroy(rt_ctx* ctx) {
     cudaFree(ctx->d_orf_desc);
     cudaFree(ctx->d_exon_entries);
     cudaFree(ctx->d_work_counter);
+    for (auto& p : ctx->plans) {
+        cudaFree(p.d_list);
+        cudaFree(p.d_fallback);
+    }
     for (int s = 0; s < 2; ++s) {
         ctx->read_slot[s].release();
         if (ctx->slot_stream[s]) cudaStreamDestroy(ctx->slot_stream[s]);
@@ -377,6 +396,11 @@ int rt_set_index(rt_ctx* ctx, int64_t n_orf, const int64_t* h_exon_ptr, const in
     cudaFree(ctx->d_exon_entries);
     ctx->d_orf_desc = ctx->d_exon_entries = nullptr;
     ctx->n_orf = 0;
+    for (auto& p : ctx->plans) {
+        cudaFree(p.d_list);
+        cudaFree(p.d_fallback);
+    }
+    ctx->plans.clear();
     RT_CUDA(ctx, cudaMalloc(&ctx->d_orf_desc, sizeof(uint64_t) * std::max<size_t>(1, desc.size())));
     RT_CUDA(ctx, cudaMalloc(&ctx->d_exon_entries, sizeof(uint64_t) * std::max<size_t>(1, entries.size())));
     if (!desc.empty())
@@ -415,6 +439,58 @@ int rt_shard_bounds(const rt_ctx* ctx, int n_shards, int64_t* h_bounds) {
 }
 
 // ------------------------------------------------------------------------------------ K2+K3
+}  // extern "C"
+
+namespace {
+
+// ORFs of [lo, hi) sorted by length, longest first: the long ones go to the generic
+// warp-per-ORF kernel, the rest to the packed kernel (several ORFs per warp).
+int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
+    for (auto& p : ctx->plans)
+        if (p.lo == lo && p.hi == hi) {
+            *out = &p;
+            return RT_OK;
+        }
+    const int64_t n = hi - lo;
+    std::vector<int32_t> ids((size_t)n);
+    for (int64_t i = 0; i < n; ++i) ids[i] = (int32_t)(lo + i);
+    const int64_t* np = ctx->nt_prefix.data();
+    std::stable_sort(ids.begin(), ids.end(), [np](int32_t x, int32_t y) {
+        return np[x + 1] - np[x] > np[y + 1] - np[y];
+    });
+    int64_t n_long = 0;
+    while (n_long < n && np[ids[n_long] + 1] - np[ids[n_long]] > rt::kPackMaxNt) ++n_long;
+    if (ctx->plans.size() >= 8) {   // bounded cache
+        cudaFree(ctx->plans.front().d_list);
+        cudaFree(ctx->plans.front().d_fallback);
+        ctx->plans.erase(ctx->plans.begin());
+    }
+    rt_ctx::ScorePlan p;
+    p.lo = lo;
+    p.hi = hi;
+    p.n_long = n_long;
+    p.n_short = n - n_long;
+    RT_CUDA(ctx, cudaMalloc(&p.d_list, sizeof(int32_t) * std::max<int64_t>(1, n)));
+    RT_CUDA(ctx, cudaMalloc(&p.d_fallback, sizeof(int32_t) * std::max<int64_t>(1, p.n_short)));
+    RT_CUDA(ctx, cudaMemcpy(p.d_list, ids.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    ctx->plans.push_back(p);
+    *out = &ctx->plans.back();
+    return RT_OK;
+}
+
+template <typename Kernel>
+unsigned persistent_grid(rt_ctx* ctx, Kernel k, int64_t work_items) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, rt::kScoreWarps * 32, 0) != cudaSuccess) per_sm = 1;
+    per_sm = std::max(per_sm, 1);
+    const int64_t want = (work_items + rt::kScoreWarps - 1) / rt::kScoreWarps;
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->n_sm * per_sm));
+}
+
+}  // namespace
+
+extern "C" {
+
 int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, const rt_score_params* params,
              const rt_score_out* d_out, void* stream) {
     if (!ctx) return fail(nullptr, RT_EINVAL, "rt_score: ctx is NULL");
@@ -427,23 +503,51 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
         return fail(ctx, RT_EINVAL, "rt_score: score/valid/count/length columns are required");
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
-    RT_CUDA(ctx, cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(unsigned long long), st));
+    rt_ctx::ScorePlan* plan = nullptr;
+    int rc = get_plan(ctx, orf_lo, orf_hi, &plan);
+    if (rc != RT_OK) return rc;
+    RT_CUDA(ctx, cudaMemsetAsync(ctx->d_work_counter, 0, 4 * sizeof(unsigned long long), st));
     rt::ScoreArgs a;
     a.cov = d_cov;
     a.orf_desc = ctx->d_orf_desc;
     a.exon_entries = ctx->d_exon_entries;
     a.orf_lo = orf_lo;
-    a.orf_hi = orf_hi;
-    a.work_counter = ctx->d_work_counter;
+    a.fallback = plan->d_fallback;
+    a.n_fallback = reinterpret_cast<unsigned*>(ctx->d_work_counter + 3);
     a.prm = *params;
     a.out = *d_out;
-    int per_sm = 0;
-    RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rt::score_orfs_kernel, rt::kScoreWarps * 32, 0));
-    per_sm = std::max(per_sm, 1);
-    const int64_t want = (orf_hi - orf_lo + rt::kScoreWarps * rt::kFetchBatch - 1) / (rt::kScoreWarps * rt::kFetchBatch);
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->n_sm * per_sm));
-    rt::score_orfs_kernel<<<grid, rt::kScoreWarps * 32, 0, st>>>(a);
-    ctx->launches++;
+    const int threads = rt::kScoreWarps * 32;
+    // 1. the long ORFs first (generic kernel, one warp per ORF)
+    if (plan->n_long > 0) {
+        a.list = plan->d_list;
+        a.n_list = plan->n_long;
+        a.n_list_dev = nullptr;
+        a.work_counter = ctx->d_work_counter + 0;
+        rt::score_orfs_kernel<<<persistent_grid(ctx, rt::score_orfs_kernel, plan->n_long), threads, 0, st>>>(a);
+        ctx->launches++;
+    }
+    // 2. everything else, several ORFs per warp
+    if (plan->n_short > 0) {
+        a.list = plan->d_list + plan->n_long;
+        a.n_list = plan->n_short;
+        a.n_list_dev = nullptr;
+        a.work_counter = ctx->d_work_counter + 1;
+        if (ctx->pack_lpo == 8) {
+            rt::score_orfs_packed_kernel<8><<<persistent_grid(ctx, rt::score_orfs_packed_kernel<8>, (plan->n_short + 3) / 4), threads, 0, st>>>(a);
+        } else if (ctx->pack_lpo == 16) {
+            rt::score_orfs_packed_kernel<16><<<persistent_grid(ctx, rt::score_orfs_packed_kernel<16>, (plan->n_short + 1) / 2), threads, 0, st>>>(a);
+        } else {
+            rt::score_orfs_packed_kernel<32><<<persistent_grid(ctx, rt::score_orfs_packed_kernel<32>, plan->n_short), threads, 0, st>>>(a);
+        }
+        ctx->launches++;
+        // 3. ORFs the packed kernel handed over (counts >= 2^20): normally none
+        a.list = plan->d_fallback;
+        a.n_list = 0;
+        a.n_list_dev = a.n_fallback;
+        a.work_counter = ctx->d_work_counter + 2;
+        rt::score_orfs_kernel<<<(unsigned)ctx->n_sm, threads, 0, st>>>(a);
+        ctx->launches++;
+    }
     RT_CUDA(ctx, cudaGetLastError());
     return RT_OK;
 }

@@ -185,10 +185,15 @@ struct ScoreArgs {
     const int32_t* cov;
     const uint64_t* orf_desc;   // indexed by absolute ORF id
     const uint64_t* exon_entries;
-    long long orf_lo, orf_hi;
+    long long orf_lo;           // output element k <-> ORF orf_lo + k
+    const int32_t* list;        // ORF ids to score (absolute), longest first
+    long long n_list;           // entries of `list` ...
+    const unsigned* n_list_dev; // ... or, when not NULL, read from the device (fallback queue)
     unsigned long long* work_counter;
+    int32_t* fallback;          // packed kernel only: ORFs handed over to the generic kernel
+    unsigned* n_fallback;
     rt_score_params prm;
-    rt_score_out out;           // element k <-> ORF orf_lo + k
+    rt_score_out out;
 };
 
 // Warp-uniform totals of one frame.
@@ -206,8 +211,10 @@ struct FrameTotals {
     }
 };
 
+// Generic kernel: one warp per ORF, any length, any counts (64-bit path for huge values).
 __global__ void __launch_bounds__(kScoreWarps * 32, 4)
 score_orfs_kernel(const ScoreArgs args) {
+    const long long n_list = args.n_list_dev ? (long long)*args.n_list_dev : args.n_list;
     __shared__ __align__(16) int32_t s_buf[kScoreWarps][kBufNt];
     const int lane = threadIdx.x & 31;
     int32_t* buf = s_buf[threadIdx.x >> 5];
@@ -218,14 +225,17 @@ score_orfs_kernel(const ScoreArgs args) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(args.work_counter, (unsigned long long)kFetchBatch);
         base = __shfl_sync(kFull, base, 0);
-        if ((long long)base + args.orf_lo >= args.orf_hi) break;
+        if ((long long)base >= n_list) break;
         uint64_t my_desc = 0;
-        if (lane < kFetchBatch && args.orf_lo + (long long)base + lane < args.orf_hi)
-            my_desc = __ldg(args.orf_desc + args.orf_lo + base + lane);
+        int my_orf = 0;
+        if (lane < kFetchBatch && (long long)base + lane < n_list) {
+            my_orf = __ldg(args.list + base + lane);
+            my_desc = __ldg(args.orf_desc + my_orf);
+        }
 
         for (int bi = 0; bi < kFetchBatch; ++bi) {
-            const long long k_out = (long long)base + bi;
-            if (args.orf_lo + k_out >= args.orf_hi) break;
+            if ((long long)base + bi >= n_list) break;
+            const long long k_out = (long long)__shfl_sync(kFull, my_orf, bi) - args.orf_lo;
 
             const uint64_t desc = __shfl_sync(kFull, my_desc, bi);
             ExonCursor cur;
@@ -374,6 +384,259 @@ score_orfs_kernel(const ScoreArgs args) {
             }
             __syncwarp();
         }
+    }
+}
+
+// ---- K3, packed: several short ORFs per warp ------------------------------------------------
+// ORFs of at most kPackMaxNt nt are scored LPO lanes per ORF, 32/LPO ORFs per warp in lock step,
+// so the per-ORF overhead (cursor, reductions, epilogue) is paid once per 32/LPO ORFs.  The host
+// sorts ORFs by length, which keeps the groups of a warp balanced.  An ORF that turns out to
+// hold a count >= 2^kBigShift is appended to the fallback queue and redone by the generic kernel.
+constexpr int kPackMaxNt = 3069;               // <= 1023 codons per frame: 10-bit packed fields never overflow
+constexpr int kPackRounds = 12;                // codon rounds per tile
+
+template <int LPO>
+__device__ __forceinline__ unsigned group_sum_u32(unsigned v) {
+#pragma unroll
+    for (int o = LPO / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+template <int LPO>
+__device__ __forceinline__ double group_sum_f64(double v) {
+#pragma unroll
+    for (int o = LPO / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+template <int LPO>
+__global__ void __launch_bounds__(kScoreWarps * 32, 4)
+score_orfs_packed_kernel(const ScoreArgs args) {
+    constexpr int G = 32 / LPO;                    // ORFs per warp
+    constexpr int TN = 3 * LPO * kPackRounds;      // window starts per tile and group
+    constexpr int BN = TN + 8;                     // + 2 halo + zero pad
+    __shared__ __align__(16) int32_t s_buf[kScoreWarps][G * BN];
+    const int lane = threadIdx.x & 31;
+    const int sl = lane % LPO;                     // lane within the group
+    const int g = lane / LPO;                      // group within the warp
+    int32_t* buf = s_buf[threadIdx.x >> 5] + g * BN;
+    const double kSqrt3 = 1.7320508075688772;
+    const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
+    const long long n_packs = (args.n_list + G - 1) / G;
+
+    for (;;) {
+        unsigned long long pack = 0;
+        if (lane == 0) pack = atomicAdd(args.work_counter, 1ull);
+        pack = __shfl_sync(kFull, pack, 0);
+        if ((long long)pack >= n_packs) break;
+
+        const long long item = (long long)pack * G + g;
+        const bool active = item < args.n_list;
+        int orf = 0;
+        uint64_t desc = 0;
+        if (active) {
+            orf = __ldg(args.list + item);
+            desc = __ldg(args.orf_desc + orf);
+        }
+        // group-uniform exon cursor (profile order: detect_orfs.py:176-187,201-202)
+        const uint64_t* entries = args.exon_entries + (desc & kBeginMask);
+        const int n_ent = (int)((desc >> 40) & kMaxEntriesPerOrf);
+        const bool rev = (desc >> 63) != 0;
+        int next = 0, rem = 0;
+        long long pos = 0;
+        bool zero = false;
+
+        FrameLane f0, f1, f2;
+        unsigned cnt32 = 0, mn32 = 0xffffffffu;
+        int total = 0, fill = 0, ormask = 0, tile_or = 0;
+        bool ended = !active || n_ent == 0;    // exon stream exhausted
+        bool done = !active;
+
+        while (__any_sync(kFull, !done)) {
+            // ---- K2: every group stages its next profile tile ----
+            while (__any_sync(kFull, !ended && fill < TN + 2)) {
+                if (!ended && fill < TN + 2) {
+                    if (rem == 0) {
+                        const uint64_t ent = __ldg(entries + (rev ? n_ent - 1 - next : next));
+                        rem = (int)(ent & kLenMask);
+                        const uint64_t off = ent >> kLenBits;
+                        zero = off == kZeroOff;
+                        pos = rev ? (long long)off + rem - 1 : (long long)off;
+                        ++next;
+                    }
+                    const int take = min(rem, TN + 2 - fill);
+                    int32_t* dst = buf + fill;
+                    if (zero) {
+                        for (int k = sl; k < take; k += LPO) dst[k] = 0;
+                    } else {
+                        const int32_t* src = args.cov + pos;
+                        const int dir = rev ? -1 : 1;
+                        for (int k = sl; k < take; k += 4 * LPO) {
+                            int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                            v0 = ld_cov(src + dir * k);
+                            if (k + LPO < take) v1 = ld_cov(src + dir * (k + LPO));
+                            if (k + 2 * LPO < take) v2 = ld_cov(src + dir * (k + 2 * LPO));
+                            if (k + 3 * LPO < take) v3 = ld_cov(src + dir * (k + 3 * LPO));
+                            dst[k] = v0;
+                            if (k + LPO < take) dst[k + LPO] = v1;
+                            if (k + 2 * LPO < take) dst[k + 2 * LPO] = v2;
+                            if (k + 3 * LPO < take) dst[k + 3 * LPO] = v3;
+                            tile_or |= v0 | v1 | v2 | v3;
+                        }
+                    }
+                    fill += take;
+                    total += take;
+                    rem -= take;
+                    pos += rev ? -take : take;
+                    if (rem == 0 && next == n_ent) ended = true;
+                }
+            }
+            const int nvals = fill;
+            if (!done && ended) {
+                for (int k = sl; k < 6; k += LPO) buf[nvals + k] = 0;   // nvals + 5 < BN
+            }
+            ormask |= tile_or;
+            const unsigned nz = __ballot_sync(kFull, tile_or != 0);
+            const bool group_nonzero = ((nz >> (g * LPO)) & ((LPO == 32) ? 0xffffffffu : ((1u << LPO) - 1u))) != 0;
+            __syncwarp();
+
+            // ---- K3 ----
+            if (!done) {
+                const int ncod = ended ? (nvals + 2) / 3 : TN / 3;
+                if (group_nonzero) {
+                    const int nfull = max(nvals - 2, 0) / 3;
+                    for (int c = sl; c < nfull; c += LPO) {
+                        const int32_t* p = buf + 3 * c;
+                        const int v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4];
+                        const unsigned cs = (unsigned)v0 + (unsigned)v1 + (unsigned)v2;   // common.py:177-179
+                        cnt32 += cs;                                                        // detect_orfs.py:278
+                        mn32 = min(mn32, cs);
+                        if ((v0 | v1 | v2 | v3 | v4) != 0) {
+                            accumulate_codon<false>(v0, v1, v2, f0);
+                            accumulate_codon<false>(v1, v2, v3, f1);
+                            accumulate_codon<false>(v2, v3, v4, f2);
+                        }
+                    }
+                    for (int c = nfull + sl; c < ncod; c += LPO) {     // ragged end (statistics.py:71)
+                        const int32_t* p = buf + 3 * c;
+                        const int v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4];
+                        const unsigned cs = (unsigned)v0 + (unsigned)v1 + (unsigned)v2;
+                        cnt32 += cs;
+                        mn32 = min(mn32, cs);
+                        if (3 * c + 2 < nvals) accumulate_codon<false>(v0, v1, v2, f0);
+                        if (3 * c + 3 < nvals) accumulate_codon<false>(v1, v2, v3, f1);
+                        if (3 * c + 4 < nvals) accumulate_codon<false>(v2, v3, v4, f2);
+                    }
+                } else if (ncod > 0) {
+                    mn32 = 0;          // an all-zero tile: every codon sum is 0, nothing else changes
+                }
+            }
+            __syncwarp();
+            // carry the 2-value halo to the front of the next tile
+            const bool more = !done && !ended;
+            int t = 0;
+            if (more && sl < 2) t = buf[TN + sl];
+            __syncwarp();
+            if (more && sl < 2) buf[sl] = t;
+            tile_or = more ? t : 0;
+            if (!done) {
+                if (ended) done = true;
+                else fill = 2;
+            }
+            __syncwarp();
+        }
+
+        // ---- group reductions (all lanes converged) ----
+        const unsigned a1_0 = group_sum_u32<LPO>(f0.w1), a2_0 = group_sum_u32<LPO>(f0.w2);
+        const unsigned a1_1 = group_sum_u32<LPO>(f1.w1), a2_1 = group_sum_u32<LPO>(f1.w2);
+        const unsigned a1_2 = group_sum_u32<LPO>(f2.w1), a2_2 = group_sum_u32<LPO>(f2.w2);
+        const unsigned count = group_sum_u32<LPO>(cnt32);
+#pragma unroll
+        for (int o = LPO / 2; o > 0; o >>= 1) {
+            mn32 = min(mn32, __shfl_xor_sync(kFull, mn32, o));
+            ormask |= __shfl_xor_sync(kFull, ormask, o);
+        }
+        const bool any_general = __any_sync(kFull, ((a2_0 | a2_1 | a2_2) & 1023u) != 0);
+        double re0 = 0.0, im0 = 0.0, re1 = 0.0, im1 = 0.0, re2 = 0.0, im2 = 0.0;
+        if (any_general) {
+            re0 = group_sum_f64<LPO>(f0.sre); im0 = group_sum_f64<LPO>(f0.sim);
+            re1 = group_sum_f64<LPO>(f1.sre); im1 = group_sum_f64<LPO>(f1.sim);
+            re2 = group_sum_f64<LPO>(f2.sre); im2 = group_sum_f64<LPO>(f2.sim);
+        }
+
+        // ---- epilogue: statistics.py:92-115 + detect_orfs.py:278-299, once for all groups ----
+        const int L = total;
+        const int n_codons = L / 3 > 1 ? L / 3 : 1;                        // detect_orfs.py:281
+        const int na0 = a1_0 & 1023, nb0 = (a1_0 >> 10) & 1023, nc0 = a1_0 >> 20, ng0 = a2_0 & 1023, nu0 = a2_0 >> 10;
+        const int na1 = a1_1 & 1023, nb1 = (a1_1 >> 10) & 1023, nc1 = a1_1 >> 20, ng1 = a2_1 & 1023, nu1 = a2_1 >> 10;
+        const int na2 = a1_2 & 1023, nb2 = (a1_2 >> 10) & 1023, nc2 = a1_2 >> 20, ng2 = a2_2 & 1023, nu2 = a2_2 >> 10;
+        const int K0 = na0 + nb0 + nc0 + ng0 + nu0;
+        const int K1 = na1 + nb1 + nc1 + ng1 + nu1;
+        const int K2 = na2 + nb2 + nc2 + ng2 + nu2;
+        re0 += 0.5 * (double)(2 * na0 - nb0 - nc0); im0 = kSqrt3 * (im0 + 0.5 * (double)(nb0 - nc0));
+        re1 += 0.5 * (double)(2 * na1 - nb1 - nc1); im1 = kSqrt3 * (im1 + 0.5 * (double)(nb1 - nc1));
+        re2 += 0.5 * (double)(2 * na2 - nb2 - nc2); im2 = kSqrt3 * (im2 + 0.5 * (double)(nb2 - nc2));
+        // one fp64 division sequence for all seven quotients of every group: sub-lanes 0-2 the
+        // coherences |sum u|^2 / (K * M), sub-lane 3 the density, sub-lanes 4-6 K_f / n_codons
+        double nn, dd = (double)n_codons;
+        if (sl == 0) { nn = re0 * re0 + im0 * im0; dd = (double)K0 * (double)(K0 - nu0); }
+        else if (sl == 1) { nn = re1 * re1 + im1 * im1; dd = (double)K1 * (double)(K1 - nu1); }
+        else if (sl == 2) { nn = re2 * re2 + im2 * im2; dd = (double)K2 * (double)(K2 - nu2); }
+        else if (sl == 3) nn = (double)count;                              // detect_orfs.py:287
+        else if (sl == 4) nn = (double)K0;                                 // detect_orfs.py:285
+        else if (sl == 5) nn = (double)K1;
+        else nn = (double)K2;
+        const double q = nn / dd;                                          // 0/0 -> NaN never wins
+        const int gb = g * LPO;
+        double s0 = __shfl_sync(kFull, q, gb + 0);
+        double s1 = __shfl_sync(kFull, q, gb + 1);
+        double s2 = __shfl_sync(kFull, q, gb + 2);
+        const double density = __shfl_sync(kFull, q, gb + 3);
+        // statistics.py:64-66,92-115: running maximum with the K==0 reset quirk
+        double coh = 0.0;
+        int vf = -1;          // frame whose K is `valid`; -1: valid = 0
+        bool unset = true;    // valid == -1 in the reference
+        if (K0 == 0) { coh = 0.0; vf = -1; unset = false; s0 = kNaN; }
+        else { if (s0 > coh) { coh = s0; vf = 0; unset = false; } if (unset) { vf = 0; unset = false; } }
+        if (K1 == 0) { coh = 0.0; vf = -1; unset = false; s1 = kNaN; }
+        else { if (s1 > coh) { coh = s1; vf = 1; unset = false; } if (unset) { vf = 1; unset = false; } }
+        if (K2 == 0) { coh = 0.0; vf = -1; unset = false; s2 = kNaN; }
+        else { if (s2 > coh) { coh = s2; vf = 2; unset = false; } if (unset) { vf = 2; unset = false; } }
+        const double score = sqrt(coh);                                    // statistics.py:115
+        const int valid = vf == 0 ? K0 : vf == 1 ? K1 : vf == 2 ? K2 : 0;
+        double ratio = __shfl_sync(kFull, q, gb + (vf >= 0 ? 4 + vf : 4));
+        if (vf < 0) ratio = 0.0;
+
+        if (active && sl == 0) {
+            if ((ormask >> kBigShift) != 0) {
+                // a huge count: 32-bit sums may have wrapped -> hand over to the generic kernel
+                args.fallback[atomicAdd(args.n_fallback, 1u)] = orf;
+            } else {
+                const long long k_out = (long long)orf - args.orf_lo;
+                const unsigned min_codon = L == 0 ? 0u : mn32;
+                const bool ok = score >= args.prm.phase_score_cutoff &&
+                                (double)valid >= args.prm.min_valid_codons &&
+                                (L == 0 || (double)min_codon >= args.prm.min_reads_per_codon) &&
+                                ratio >= args.prm.min_valid_codons_ratio &&
+                                density >= args.prm.min_density_over_orf;   // detect_orfs.py:289-299
+                args.out.score[k_out] = score;
+                args.out.valid[k_out] = valid;
+                args.out.count[k_out] = (long long)count;
+                args.out.length[k_out] = L;
+                if (args.out.min_codon) args.out.min_codon[k_out] = (int32_t)min_codon;
+                if (args.out.status) args.out.status[k_out] = ok ? 1 : 0;
+                if (args.out.frame_K) {
+                    args.out.frame_K[3 * k_out + 0] = K0;
+                    args.out.frame_K[3 * k_out + 1] = K1;
+                    args.out.frame_K[3 * k_out + 2] = K2;
+                }
+                if (args.out.frame_s) {
+                    args.out.frame_s[3 * k_out + 0] = s0;
+                    args.out.frame_s[3 * k_out + 1] = s1;
+                    args.out.frame_s[3 * k_out + 2] = s2;
+                }
+            }
+        }
+        __syncwarp();
     }
 }
 

@@ -1,0 +1,240 @@
+"""Metagene profiles and P-site offset inference (mirror of ribotricer/metagene.py), plus the
+protocol inference of ribotricer/infer_protocol.py on decoded read columns.
+
+SURVEY.md 8(f) "next #1".  The heavy part -- coverage of every read length over the first
+600 positions of every annotated CDS -- reuses the K1 and K4 kernels: one K1 pass per length
+(that length only, offset 0, i.e. raw 5' ends as in ``alignments[length]``, bam.py:135), one K4
+gather over a truncated copy of the annotated ORFs, then K1 with weight -1 to recycle the
+scratch coverage.  The per-position normalisation, the pandas-free bookkeeping and the
+cross-correlation (np.correlate, metagene.py:319) are cheap host code.
+"""
+from __future__ import annotations
+
+import sys
+from collections import OrderedDict
+
+import numpy as np
+
+from .const import CUTOFF, TYPICAL_OFFSET
+
+
+# ------------------------------------------------------------------ infer_protocol.py:34-124
+def infer_protocol(reads, refseq: dict, prefix: str, n_reads: int = 20000) -> str:
+    """'forward' or 'reverse' from the first ``n_reads`` uniquely mapped reads that overlap
+    exactly one annotated ORF span (infer_protocol.py:75-105); writes ``{prefix}_protocol.txt``.
+
+    The reference looks overlaps up in a quicksect tree (absent here); a span (start, end,
+    strand) overlaps a read when start <= read_end and end >= read_start.
+    """
+    cols = reads.cols
+    by_contig = {}
+    for chrom, spans in refseq.items():
+        arr = np.array(spans, dtype=np.int64).reshape(-1, 3)
+        by_contig[chrom] = arr[np.argsort(arr[:, 0])]
+    names = reads.contig_names
+    counts = {"++": 0, "--": 0, "+-": 0, "-+": 0}
+    iteration = 0
+    flag, mapq, nh = cols["flag"], cols["mapq"], cols["nh"]
+    for i in range(len(cols["ref_id"])):
+        if iteration > n_reads:           # infer_protocol.py:79
+            break
+        fl = int(flag[i])
+        # is_read_uniq_mapping is used bare here (infer_protocol.py:80): truthy only for True
+        if fl & 0x100:
+            continue
+        uniq = (nh[i] == 1) if nh[i] != 0 else (mapq[i] == 255)
+        if not uniq:
+            continue
+        c = int(cols["ref_id"][i])
+        if c < 0:
+            continue
+        spans = by_contig.get(names[c])
+        if spans is None:
+            continue
+        start, end = int(cols["first"][i]), int(cols["last"][i]) + 1   # reference_start / reference_end
+        hit = spans[(spans[:, 0] <= end) & (spans[:, 1] >= start)]
+        if len(hit) == 1:                 # infer_protocol.py:98-105
+            gene = "+" if hit[0, 2] == 1 else "-"
+            counts[("-" if fl & 0x10 else "+") + gene] += 1
+            iteration += 1
+    for k in counts:                      # pseudocounts, infer_protocol.py:107-110
+        counts[k] += 1
+    total = sum(counts.values())
+    fwd = counts["++"] + counts["--"]
+    rev = counts["-+"] + counts["+-"]
+    with open(f"{prefix}_protocol.txt", "w") as output:
+        output.write(
+            f"In total {total} reads checked:\n"
+            f'\tNumber of reads explained by "++, --": {fwd} ({fwd / total:.4f})\n'
+            f'\tNumber of reads explained by "+-, -+": {rev} ({rev / total:.4f})\n')
+    return "reverse" if rev > fwd else "forward"
+
+
+# ------------------------------------------------------------------ plotting.py (optional)
+def plot_read_lengths(read_length_counts, prefix):
+    try:
+        import matplotlib
+    except ImportError:
+        print("matplotlib not available: skipping the read length distribution plot")
+        return
+    matplotlib.use("Agg")
+    import matplotlib.pyplot as plt
+    fig, ax = plt.subplots()
+    lengths = sorted(read_length_counts)
+    ax.bar(lengths, [read_length_counts[x] for x in lengths])
+    ax.set_xlabel("Read length")
+    ax.set_ylabel("Number of reads")
+    fig.savefig(f"{prefix}_read_length_dist.pdf")
+    plt.close(fig)
+
+
+def plot_metagene(metagenes, read_length_counts, prefix):
+    try:
+        import matplotlib
+    except ImportError:
+        print("matplotlib not available: skipping the metagene plots")
+        return
+    matplotlib.use("Agg")
+    import matplotlib.pyplot as plt
+    from matplotlib.backends.backend_pdf import PdfPages
+    with PdfPages(f"{prefix}_metagene_plots.pdf") as pdf:
+        for length in sorted(metagenes):
+            idx, prof = metagenes[length][0]
+            fig, ax = plt.subplots()
+            ax.vlines(idx, 0, prof)
+            ax.set_title(f"{length} nt reads ({read_length_counts.get(length, 0)})")
+            pdf.savefig(fig)
+            plt.close(fig)
+
+
+# ------------------------------------------------------------------ metagene.py:95-265
+def _metagene_windows(cds, engine, max_positions, offset_5p, offset_3p):
+    """Truncated copies of the annotated ORFs covering what next_genome_pos walks
+    (metagene.py:42-92): leader + intervals + trailer in transcript direction, cut after
+    ``max_positions`` positions.  Returned as CSR arrays for the auxiliary index."""
+    ptr, st, en, contig, strand, lens = [0], [], [], [], [], []
+    for orf in cds:
+        minus = orf.strand == "-"
+        o5, o3 = (offset_3p, offset_5p) if minus else (offset_5p, offset_3p)   # metagene.py:129-130
+        ivs = [list(iv) for iv in orf.intervals]
+        ivs[0][0] -= o5                      # leader_iv joins the first interval
+        ivs[-1][1] += o3                     # trailer_iv joins the last one
+        left = max_positions
+        kept = []
+        for s, e in (reversed(ivs) if minus else ivs):
+            if left <= 0:
+                break
+            n = min(left, e - s + 1)
+            kept.append((e - n + 1, e) if minus else (s, s + n - 1))
+            left -= n
+        if minus:
+            kept.reverse()
+        for s, e in kept:
+            st.append(s)
+            en.append(e)
+        ptr.append(len(st))
+        contig.append(engine.contig_id(orf.chrom))
+        strand.append(0 if orf.strand == "+" else 1 if minus else 2)
+        lens.append(max_positions - max(left, 0))
+    return (np.array(ptr, np.int64), np.array(st, np.int32), np.array(en, np.int32),
+            np.array(contig, np.int32), np.array(strand, np.uint8), np.array(lens, np.int64))
+
+
+def metagene_coverage(cds, alignments, read_lengths: dict, prefix: str, max_positions: int = 600,
+                      offset_5p: int = 20, offset_3p: int = 0, meta_min_reads: int = 100000):
+    """metagene.py:160-265.  Returns ``{length: ((index_5p, profile_5p), (index_3p, profile_3p),
+    phasescore_5p, valid_5p, phasescore_3p, valid_3p)}`` and writes the two profile TSVs.
+    Like the reference, lengths with fewer than ``meta_min_reads`` reads are deleted from the
+    caller's ``read_lengths`` dict (metagene.py:200-202)."""
+    from .detect_orfs import _aux_engine
+    from .statistics import phasescore
+
+    for length, reads in list(read_lengths.items()):
+        if reads < meta_min_reads:
+            del read_lengths[length]
+    eng = alignments.engine
+    metagenes = {}
+    if cds and read_lengths:
+        aux = _aux_engine(eng)
+        ptr, st, en, contig, strand, lens = _metagene_windows(cds, eng, max_positions, offset_5p, offset_3p)
+        aux.set_index(ptr, st, en, contig, strand)
+        cov = eng.new_coverage()
+        sel = np.arange(len(cds), dtype=np.int64)
+        width = int(lens.max()) if len(lens) else 0
+    for length in read_lengths:
+        if not cds:
+            break
+        alignments.bin_into(cov, {length: 0})                       # alignments[length], bam.py:135
+        out_ptr, flat = aux.gather_profiles(cov, sel, lens)
+        alignments.bin_into(cov, {length: 0}, weight=-1)            # scratch back to zero
+        # ragged -> matrix aligned at the start (column k <-> index k - offset_5p)
+        mat = np.zeros((len(cds), width), np.float64)
+        have = np.arange(width)[None, :] < lens[:, None]
+        mat[have] = flat
+        mean = mat.sum(1) / np.maximum(lens, 1)                      # metagene.py:214
+        use = mean > 0
+        norm = np.where(have[use], mat[use] / mean[use, None], 0.0)
+        start_sum = norm.sum(0)
+        start_cnt = have[use].sum(0)
+        # the same vectors re-indexed to end at offset_3p (metagene.py:140-155)
+        stop = np.zeros_like(norm)
+        hs = np.zeros_like(have[use])
+        l_use = lens[use]
+        for n in np.unique(l_use):
+            rows = l_use == n
+            stop[rows, width - n:] = norm[rows, :n]
+            hs[rows, width - n:] = True
+        stop_sum = stop.sum(0)
+        stop_cnt = hs.sum(0)
+        ks, ke = start_cnt > 0, stop_cnt > 0
+        prof5 = (start_sum[ks] / start_cnt[ks]).tolist()
+        prof3 = (stop_sum[ke] / stop_cnt[ke]).tolist()
+        idx5 = (np.flatnonzero(ks) - offset_5p).tolist()
+        idx3 = (np.flatnonzero(ke) - (width - 1) + offset_3p).tolist()
+        ps5, v5 = phasescore(prof5, engine=eng)
+        ps3, v3 = phasescore(prof3, engine=eng)
+        metagenes[length] = ((idx5, prof5), (idx3, prof3), ps5, v5, ps3, v3)
+    to_write_5p = "fragment_length\toffset_5p\tprofile\tphase_score\tvalid_codons\n"
+    to_write_3p = "fragment_length\toffset_3p\tprofile\tphase_score\tvalid_codons\n"
+    for length in sorted(metagenes):
+        m = metagenes[length]
+        to_write_5p += f"{length}\t{offset_5p}\t{m[0][1]}\t{m[2]}\t{m[3]}\n"
+        to_write_3p += f"{length}\t{offset_3p}\t{m[1][1]}\t{m[4]}\t{m[5]}\n"
+    with open(f"{prefix}_metagene_profiles_5p.tsv", "w") as output:
+        output.write(to_write_5p)
+    with open(f"{prefix}_metagene_profiles_3p.tsv", "w") as output:
+        output.write(to_write_3p)
+    return metagenes
+
+
+# ------------------------------------------------------------------ metagene.py:268-328
+def align_metagenes(metagenes, read_lengths: dict, prefix: str, phase_score_cutoff: float = CUTOFF,
+                    remove_nonperiodic: bool = False):
+    """P-site offset of every read length = lag of its 5' metagene against the most abundant
+    length's + TYPICAL_OFFSET (metagene.py:309-324)."""
+    if remove_nonperiodic:
+        for length in list(metagenes):
+            if metagenes[length][2] < phase_score_cutoff:       # metagene.py:298-302
+                del read_lengths[length]
+                del metagenes[length]
+    if len(read_lengths) == 0:
+        sys.exit(f"WARNING: no periodic read length found... using cutoff {phase_score_cutoff}")
+    psite_offsets = OrderedDict()
+    base = n_reads = 0
+    for length, reads in list(read_lengths.items()):
+        if reads > n_reads:
+            base, n_reads = length, reads
+    reference = np.asarray(metagenes[base][0][1], np.float64)
+    to_write = f"relative lag to base: {base}\n"
+    for length in list(metagenes):
+        cov = np.asarray(metagenes[length][0][1], np.float64)
+        xcorr = np.correlate(reference, cov, "full")
+        origin = len(xcorr) // 2
+        bound = min(base, length)
+        xcorr = xcorr[(origin - bound):(origin + bound)]
+        lag = int(np.argmax(xcorr) - len(xcorr) // 2)
+        psite_offsets[length] = lag + TYPICAL_OFFSET
+        to_write += f"\tlag of {length}: {lag}\n"
+    with open(f"{prefix}_psite_offsets.txt", "w") as output:
+        output.write(to_write)
+    return psite_offsets
