@@ -164,6 +164,12 @@ int rt_score_host(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf
 int rt_gather_profiles(rt_ctx* ctx, const int32_t* d_cov, int64_t n_sel, const int64_t* d_orf_ids,
                        const int64_t* d_out_ptr, int32_t* d_out, void* stream);
 
+/*
+ * ---- phasescore(values) (statistics.py:48-115) of ONE sequence of doubles, e.g. a metagene
+ *      profile (metagene.py:243-244).  Host pointers; synchronous.
+ */
+int rt_phasescore_values(rt_ctx* ctx, const double* h_values, int64_t n, double* h_score, int32_t* h_valid);
+
 /* number of kernel launches issued through this ctx so far (bench.py's gpu_launches) */
 int64_t rt_launch_count(const rt_ctx* ctx);
 

@@ -15,7 +15,7 @@ import tempfile
 rep, sym = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(root, "ribotricer_b200", "libribotricer_b200.so")
+so = os.environ.get("LINE_PROFILE_SO", os.path.join(root, "ribotricer_b200", "libribotricer_b200.so"))
 with tempfile.TemporaryDirectory() as tmp:
     subprocess.check_call(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL)
     cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -35,14 +35,14 @@ for ln in dis.splitlines():
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
     if m:
         lines.append((cur, m.group(2).strip()))
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + sym], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
 H = rows[hdr]
 ie, smp = H.index("Instructions Executed"), H.index("# Samples")
 sass = rows[hdr + 1:]
 assert len(sass) == len(lines), (len(sass), len(lines))
-src = open(os.path.join(root, "ribotricer_b200", "csrc", "rt_kernels.cuh")).read().splitlines()
+src = open(os.environ.get("LINE_PROFILE_SRC", os.path.join(root, "ribotricer_b200", "csrc", "rt_kernels.cuh"))).read().splitlines()
 agg = {}
 tot_i = tot_s = 0
 for (line, _), r in zip(lines, sass):

@@ -23,7 +23,7 @@ EXPORTS = (
     "rt_set_genome", "rt_plane_elems", "rt_get_contig_base", "rt_set_length_table",
     "rt_bin_reads", "rt_bin_reads_host", "rt_clear_coverage", "rt_set_index", "rt_index_orfs",
     "rt_index_score_bytes", "rt_index_total_nt", "rt_shard_bounds", "rt_score", "rt_score_host",
-    "rt_gather_profiles", "rt_launch_count",
+    "rt_gather_profiles", "rt_launch_count", "rt_phasescore_values",
 )
 
 
@@ -82,6 +82,7 @@ def load():
     lib.rt_score.argtypes = [vp, vp, i64, i64, C.POINTER(ScoreParams), C.POINTER(ScoreOut), vp]
     lib.rt_score_host.argtypes = [vp, vp, i64, i64, C.POINTER(ScoreParams), C.POINTER(ScoreOut)]
     lib.rt_gather_profiles.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.rt_phasescore_values.argtypes = [vp, vp, i64, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     lib.rt_launch_count.argtypes = [vp]
     lib.rt_launch_count.restype = i64
     if lib.rt_abi_version() != 1:

@@ -15,6 +15,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
+from .const import DEFAULT_PAD
 from .engine import READ_COLUMNS, Engine, make_len_table
 
 
@@ -158,8 +159,9 @@ def split_bam(bam_path, protocol: str, prefix: str, read_lengths=None, engine: E
 
     reads = load_reads(bam_path)
     eng = engine or get_engine()
-    if list(eng.contig_names) != list(reads.contig_names) or eng.pad == 0:
-        eng.set_genome(reads.contig_names, reads.contig_len)
+    if (list(eng.contig_names) != list(reads.contig_names) or eng.pad != DEFAULT_PAD
+            or not np.array_equal(eng.contig_len, reads.contig_len)):
+        eng.set_genome(reads.contig_names, reads.contig_len, DEFAULT_PAD)
     alignments = Alignments(eng, reads, protocol, read_lengths)
     stats, rlc = alignments.count()
     with open(f"{prefix}_bam_summary.txt", "w") as output:

@@ -56,6 +56,9 @@ struct rt_ctx {
     // index
     int64_t n_orf = 0;
     uint64_t* d_orf_desc = nullptr;
+    int32_t* d_orf_len = nullptr;
+    cudaStream_t aux_stream = nullptr;               // long ORFs run beside the packed kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint64_t* d_exon_entries = nullptr;
     std::vector<int64_t> bytes_prefix;  // n_orf + 1: prefix of 4L + 8E + 42
     std::vector<int64_t> nt_prefix;     // n_orf + 1: prefix of L
@@ -165,8 +168,12 @@ void rt_destroy(rt_ctx* ctx) {
     cudaFree(ctx->d_contig_base);
     cudaFree(ctx->d_len_table);
     cudaFree(ctx->d_orf_desc);
+    cudaFree(ctx->d_orf_len);
     cudaFree(ctx->d_exon_entries);
     cudaFree(ctx->d_work_counter);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (auto& p : ctx->plans) {
         cudaFree(p.d_list);
         cudaFree(p.d_fallback);
@@ -393,14 +400,23 @@ int rt_set_index(rt_ctx* ctx, int64_t n_orf, const int64_t* h_exon_ptr, const in
         ctx->bytes_prefix[o + 1] = ctx->bytes_prefix[o] + 4 * L + 8 * (e1 - e0) + 42;
     }
     cudaFree(ctx->d_orf_desc);
+    cudaFree(ctx->d_orf_len);
     cudaFree(ctx->d_exon_entries);
     ctx->d_orf_desc = ctx->d_exon_entries = nullptr;
+    ctx->d_orf_len = nullptr;
     ctx->n_orf = 0;
     for (auto& p : ctx->plans) {
         cudaFree(p.d_list);
         cudaFree(p.d_fallback);
     }
     ctx->plans.clear();
+    {
+        std::vector<int32_t> lens((size_t)n_orf);
+        for (int64_t o = 0; o < n_orf; ++o) lens[o] = (int32_t)(ctx->nt_prefix[o + 1] - ctx->nt_prefix[o]);
+        RT_CUDA(ctx, cudaMalloc(&ctx->d_orf_len, sizeof(int32_t) * std::max<size_t>(1, lens.size())));
+        if (!lens.empty())
+            RT_CUDA(ctx, cudaMemcpy(ctx->d_orf_len, lens.data(), sizeof(int32_t) * lens.size(), cudaMemcpyHostToDevice));
+    }
     RT_CUDA(ctx, cudaMalloc(&ctx->d_orf_desc, sizeof(uint64_t) * std::max<size_t>(1, desc.size())));
     RT_CUDA(ctx, cudaMalloc(&ctx->d_exon_entries, sizeof(uint64_t) * std::max<size_t>(1, entries.size())));
     if (!desc.empty())
@@ -452,14 +468,25 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
             return RT_OK;
         }
     const int64_t n = hi - lo;
-    std::vector<int32_t> ids((size_t)n);
-    for (int64_t i = 0; i < n; ++i) ids[i] = (int32_t)(lo + i);
     const int64_t* np = ctx->nt_prefix.data();
-    std::stable_sort(ids.begin(), ids.end(), [np](int32_t x, int32_t y) {
-        return np[x + 1] - np[x] > np[y + 1] - np[y];
-    });
-    int64_t n_long = 0;
-    while (n_long < n && np[ids[n_long] + 1] - np[ids[n_long]] > rt::kPackMaxNt) ++n_long;
+    auto len_of = [np](int32_t x) { return np[x + 1] - np[x]; };
+    // long ORFs: all of them, longest first (they start first and run beside the packed kernel)
+    std::vector<int32_t> ids;
+    ids.reserve((size_t)n);
+    for (int64_t o = lo; o < hi; ++o)
+        if (len_of((int32_t)o) > rt::kPackMaxNt) ids.push_back((int32_t)o);
+    std::stable_sort(ids.begin(), ids.end(), [&](int32_t x, int32_t y) { return len_of(x) > len_of(y); });
+    const int64_t n_long = (int64_t)ids.size();
+    // the rest: sorted by length inside windows of kPlanWindow consecutive index rows, so that the
+    // ORFs sharing a warp have similar lengths while neighbours in the index (nested ORFs, isoforms:
+    // same exons) are still scored close in time and meet in L2
+    constexpr int64_t kPlanWindow = 2048;
+    for (int64_t w0 = lo; w0 < hi; w0 += kPlanWindow) {
+        const size_t begin = ids.size();
+        for (int64_t o = w0; o < std::min(hi, w0 + kPlanWindow); ++o)
+            if (len_of((int32_t)o) <= rt::kPackMaxNt) ids.push_back((int32_t)o);
+        std::stable_sort(ids.begin() + begin, ids.end(), [&](int32_t x, int32_t y) { return len_of(x) > len_of(y); });
+    }
     if (ctx->plans.size() >= 8) {   // bounded cache
         cudaFree(ctx->plans.front().d_list);
         cudaFree(ctx->plans.front().d_fallback);
@@ -511,20 +538,30 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
     a.cov = d_cov;
     a.orf_desc = ctx->d_orf_desc;
     a.exon_entries = ctx->d_exon_entries;
+    a.orf_len = ctx->d_orf_len;
     a.orf_lo = orf_lo;
     a.fallback = plan->d_fallback;
     a.n_fallback = reinterpret_cast<unsigned*>(ctx->d_work_counter + 3);
     a.prm = *params;
     a.out = *d_out;
     const int threads = rt::kScoreWarps * 32;
-    // 1. the long ORFs first (generic kernel, one warp per ORF)
+    // 1. the long ORFs (generic kernel, one warp per ORF) on a side stream, beside the packed kernel
     if (plan->n_long > 0) {
+        if (!ctx->aux_stream) {
+            RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+            RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        }
+        RT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        RT_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
         a.list = plan->d_list;
         a.n_list = plan->n_long;
         a.n_list_dev = nullptr;
         a.work_counter = ctx->d_work_counter + 0;
-        rt::score_orfs_kernel<<<persistent_grid(ctx, rt::score_orfs_kernel, plan->n_long), threads, 0, st>>>(a);
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((plan->n_long + 7) / 8, ctx->n_sm));
+        rt::score_orfs_kernel<<<grid, threads, 0, ctx->aux_stream>>>(a);
         ctx->launches++;
+        RT_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
     }
     // 2. everything else, several ORFs per warp
     if (plan->n_short > 0) {
@@ -548,6 +585,7 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
         rt::score_orfs_kernel<<<(unsigned)ctx->n_sm, threads, 0, st>>>(a);
         ctx->launches++;
     }
+    if (plan->n_long > 0) RT_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     RT_CUDA(ctx, cudaGetLastError());
     return RT_OK;
 }
@@ -587,6 +625,26 @@ int rt_score_host(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf
     if (d.frame_K) RT_CUDA(ctx, back(h_out->frame_K, d.frame_K, 12 * n));
     if (d.frame_s) RT_CUDA(ctx, back(h_out->frame_s, d.frame_s, 24 * n));
     RT_CUDA(ctx, cudaStreamSynchronize(nullptr));
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------ phasescore(values)
+int rt_phasescore_values(rt_ctx* ctx, const double* h_values, int64_t n, double* h_score, int32_t* h_valid) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_phasescore_values: ctx is NULL");
+    if (n < 0 || (n > 0 && !h_values) || !h_score || !h_valid)
+        return fail(ctx, RT_EINVAL, "rt_phasescore_values: NULL argument");
+    DeviceGuard guard(ctx->device);
+    const size_t bytes = sizeof(double) * (size_t)std::max<int64_t>(n, 1) + 64;
+    RT_CUDA(ctx, ctx->score_buf.reserve(bytes));
+    double* d_vals = static_cast<double*>(ctx->score_buf.p);
+    double* d_score = d_vals + std::max<int64_t>(n, 1);
+    int* d_valid = reinterpret_cast<int*>(d_score + 1);
+    if (n) RT_CUDA(ctx, cudaMemcpyAsync(d_vals, h_values, sizeof(double) * n, cudaMemcpyHostToDevice, nullptr));
+    rt::phasescore_values_kernel<<<1, 32>>>(d_vals, n, d_score, d_valid);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+    RT_CUDA(ctx, cudaMemcpy(h_score, d_score, sizeof(double), cudaMemcpyDeviceToHost));
+    RT_CUDA(ctx, cudaMemcpy(h_valid, d_valid, sizeof(int), cudaMemcpyDeviceToHost));
     return RT_OK;
 }
 

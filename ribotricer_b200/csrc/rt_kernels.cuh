@@ -185,6 +185,7 @@ struct ScoreArgs {
     const int32_t* cov;
     const uint64_t* orf_desc;   // indexed by absolute ORF id
     const uint64_t* exon_entries;
+    const int32_t* orf_len;     // profile length per ORF (absolute ORF id)
     long long orf_lo;           // output element k <-> ORF orf_lo + k
     const int32_t* list;        // ORF ids to score (absolute), longest first
     long long n_list;           // entries of `list` ...
@@ -390,10 +391,13 @@ score_orfs_kernel(const ScoreArgs args) {
 // ---- K3, packed: several short ORFs per warp ------------------------------------------------
 // ORFs of at most kPackMaxNt nt are scored LPO lanes per ORF, 32/LPO ORFs per warp in lock step,
 // so the per-ORF overhead (cursor, reductions, epilogue) is paid once per 32/LPO ORFs.  The host
-// sorts ORFs by length, which keeps the groups of a warp balanced.  An ORF that turns out to
-// hold a count >= 2^kBigShift is appended to the fallback queue and redone by the generic kernel.
+// sorts ORFs by length inside windows of the index, which keeps the groups of a warp balanced
+// and neighbouring ORFs (which share exons) close in time.  No shared memory: every lane owns
+// one codon per round, loads its three values straight from the coverage plane and gets the two
+// values after them from its right-hand neighbour by shuffle; rounds are software pipelined.
+// An ORF that turns out to hold a count >= 2^kBigShift is appended to the fallback queue and
+// redone by the generic kernel.
 constexpr int kPackMaxNt = 3069;               // <= 1023 codons per frame: 10-bit packed fields never overflow
-constexpr int kPackRounds = 12;                // codon rounds per tile
 
 template <int LPO>
 __device__ __forceinline__ unsigned group_sum_u32(unsigned v) {
@@ -408,17 +412,68 @@ __device__ __forceinline__ double group_sum_f64(double v) {
     return v;
 }
 
+// Group-uniform cursor over the exon entries of one ORF in profile coordinates.
+struct ProfileCursor {
+    const uint64_t* entries;
+    int n_ent;
+    int dir;            // +1 '+', -1 '-' (entries are then walked last to first)
+    int e = -1;         // current entry
+    int p0 = 0, p1 = 0; // profile range [p0, p1) of the current entry
+    long long addr = 0; // coverage slot of profile position p0
+    bool zero = true;
+
+    __device__ __forceinline__ void advance() {   // precondition: e + 1 < n_ent
+        ++e;
+        const uint64_t ent = __ldg(entries + (dir < 0 ? n_ent - 1 - e : e));
+        const int len = (int)(ent & kLenMask);
+        const uint64_t off = ent >> kLenBits;
+        zero = off == kZeroOff;
+        addr = dir < 0 ? (long long)off + len - 1 : (long long)off;
+        p0 = p1;
+        p1 += len;
+    }
+};
+
+// The three coverage values of codon (round r, sub-lane sl): profile positions P + 3 sl + {0,1,2}.
+template <int LPO>
+__device__ __forceinline__ void load_round(const int32_t* cov, ProfileCursor& cur, int P, int L, int sl,
+                                           int& v0, int& v1, int& v2) {
+    constexpr int RNT = 3 * LPO;
+    v0 = v1 = v2 = 0;
+    if (P >= L) return;
+    while (P >= cur.p1) cur.advance();                   // group-uniform
+    const int p = P + 3 * sl;
+    if (P + RNT <= cur.p1) {                             // the whole round lies inside this entry
+        if (!cur.zero) {
+            const int32_t* s = cov + cur.addr + (long long)cur.dir * (p - cur.p0);
+            v0 = ld_cov(s);
+            v1 = ld_cov(s + cur.dir);
+            v2 = ld_cov(s + 2 * cur.dir);
+        }
+        return;
+    }
+    // the round crosses entries or the end of the ORF: position by position
+    const int end = min(P + RNT, L);
+    for (;;) {
+        if (!cur.zero) {
+            const int32_t* s = cov + cur.addr - (long long)cur.dir * cur.p0;
+            if (p >= cur.p0 && p < cur.p1) v0 = ld_cov(s + (long long)cur.dir * p);
+            if (p + 1 >= cur.p0 && p + 1 < cur.p1) v1 = ld_cov(s + (long long)cur.dir * (p + 1));
+            if (p + 2 >= cur.p0 && p + 2 < cur.p1) v2 = ld_cov(s + (long long)cur.dir * (p + 2));
+        }
+        if (cur.p1 >= end) break;
+        cur.advance();
+    }
+}
+
 template <int LPO>
 __global__ void __launch_bounds__(kScoreWarps * 32, 4)
 score_orfs_packed_kernel(const ScoreArgs args) {
     constexpr int G = 32 / LPO;                    // ORFs per warp
-    constexpr int TN = 3 * LPO * kPackRounds;      // window starts per tile and group
-    constexpr int BN = TN + 8;                     // + 2 halo + zero pad
-    __shared__ __align__(16) int32_t s_buf[kScoreWarps][G * BN];
     const int lane = threadIdx.x & 31;
     const int sl = lane % LPO;                     // lane within the group
-    const int g = lane / LPO;                      // group within the warp
-    int32_t* buf = s_buf[threadIdx.x >> 5] + g * BN;
+    const int gb = lane - sl;                      // first lane of the group
+    const int nbr = sl + 1 == LPO ? gb : lane + 1; // right-hand neighbour (wraps to the next round)
     const double kSqrt3 = 1.7320508075688772;
     const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
     const long long n_packs = (args.n_list + G - 1) / G;
@@ -429,120 +484,52 @@ score_orfs_packed_kernel(const ScoreArgs args) {
         pack = __shfl_sync(kFull, pack, 0);
         if ((long long)pack >= n_packs) break;
 
-        const long long item = (long long)pack * G + g;
+        const long long item = (long long)pack * G + lane / LPO;
         const bool active = item < args.n_list;
-        int orf = 0;
+        int orf = 0, L = 0;
         uint64_t desc = 0;
         if (active) {
             orf = __ldg(args.list + item);
             desc = __ldg(args.orf_desc + orf);
+            L = __ldg(args.orf_len + orf);
         }
-        // group-uniform exon cursor (profile order: detect_orfs.py:176-187,201-202)
-        const uint64_t* entries = args.exon_entries + (desc & kBeginMask);
-        const int n_ent = (int)((desc >> 40) & kMaxEntriesPerOrf);
-        const bool rev = (desc >> 63) != 0;
-        int next = 0, rem = 0;
-        long long pos = 0;
-        bool zero = false;
+        ProfileCursor cur;
+        cur.entries = args.exon_entries + (desc & kBeginMask);
+        cur.n_ent = (int)((desc >> 40) & kMaxEntriesPerOrf);
+        cur.dir = (desc >> 63) != 0 ? -1 : 1;
 
         FrameLane f0, f1, f2;
         unsigned cnt32 = 0, mn32 = 0xffffffffu;
-        int total = 0, fill = 0, ormask = 0, tile_or = 0;
-        bool ended = !active || n_ent == 0;    // exon stream exhausted
-        bool done = !active;
+        int ormask = 0;
+        const int ncod = (L + 2) / 3;                           // codons incl. a trailing partial one
+        const int rounds = __reduce_max_sync(kFull, (ncod + LPO - 1) / LPO);
 
-        while (__any_sync(kFull, !done)) {
-            // ---- K2: every group stages its next profile tile ----
-            while (__any_sync(kFull, !ended && fill < TN + 2)) {
-                if (!ended && fill < TN + 2) {
-                    if (rem == 0) {
-                        const uint64_t ent = __ldg(entries + (rev ? n_ent - 1 - next : next));
-                        rem = (int)(ent & kLenMask);
-                        const uint64_t off = ent >> kLenBits;
-                        zero = off == kZeroOff;
-                        pos = rev ? (long long)off + rem - 1 : (long long)off;
-                        ++next;
+        int c0, c1, c2;
+        load_round<LPO>(args.cov, cur, 0, L, sl, c0, c1, c2);
+        for (int r = 0; r < rounds; ++r) {
+            int n0, n1, n2;
+            load_round<LPO>(args.cov, cur, (r + 1) * 3 * LPO, L, sl, n0, n1, n2);
+            // values 3 and 4 of this lane's five come from the neighbour's codon
+            const int v3 = __shfl_sync(kFull, sl == 0 ? n0 : c0, nbr);
+            const int v4 = __shfl_sync(kFull, sl == 0 ? n1 : c1, nbr);
+            const int p = 3 * (r * LPO + sl);
+            if (p < L) {
+                const unsigned cs = (unsigned)c0 + (unsigned)c1 + (unsigned)c2;   // common.py:177-179
+                cnt32 += cs;                                                        // detect_orfs.py:278
+                mn32 = min(mn32, cs);
+                ormask |= c0 | c1 | c2;
+                if ((c0 | c1 | c2 | v3 | v4) != 0) {
+                    if (p + 4 < L) {
+                        accumulate_codon<false>(c0, c1, c2, f0);
+                        accumulate_codon<false>(c1, c2, v3, f1);
+                        accumulate_codon<false>(c2, v3, v4, f2);
+                    } else {                                                        // ragged end (statistics.py:71)
+                        if (p + 2 < L) accumulate_codon<false>(c0, c1, c2, f0);
+                        if (p + 3 < L) accumulate_codon<false>(c1, c2, v3, f1);
                     }
-                    const int take = min(rem, TN + 2 - fill);
-                    int32_t* dst = buf + fill;
-                    if (zero) {
-                        for (int k = sl; k < take; k += LPO) dst[k] = 0;
-                    } else {
-                        const int32_t* src = args.cov + pos;
-                        const int dir = rev ? -1 : 1;
-                        for (int k = sl; k < take; k += 4 * LPO) {
-                            int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-                            v0 = ld_cov(src + dir * k);
-                            if (k + LPO < take) v1 = ld_cov(src + dir * (k + LPO));
-                            if (k + 2 * LPO < take) v2 = ld_cov(src + dir * (k + 2 * LPO));
-                            if (k + 3 * LPO < take) v3 = ld_cov(src + dir * (k + 3 * LPO));
-                            dst[k] = v0;
-                            if (k + LPO < take) dst[k + LPO] = v1;
-                            if (k + 2 * LPO < take) dst[k + 2 * LPO] = v2;
-                            if (k + 3 * LPO < take) dst[k + 3 * LPO] = v3;
-                            tile_or |= v0 | v1 | v2 | v3;
-                        }
-                    }
-                    fill += take;
-                    total += take;
-                    rem -= take;
-                    pos += rev ? -take : take;
-                    if (rem == 0 && next == n_ent) ended = true;
                 }
             }
-            const int nvals = fill;
-            if (!done && ended) {
-                for (int k = sl; k < 6; k += LPO) buf[nvals + k] = 0;   // nvals + 5 < BN
-            }
-            ormask |= tile_or;
-            const unsigned nz = __ballot_sync(kFull, tile_or != 0);
-            const bool group_nonzero = ((nz >> (g * LPO)) & ((LPO == 32) ? 0xffffffffu : ((1u << LPO) - 1u))) != 0;
-            __syncwarp();
-
-            // ---- K3 ----
-            if (!done) {
-                const int ncod = ended ? (nvals + 2) / 3 : TN / 3;
-                if (group_nonzero) {
-                    const int nfull = max(nvals - 2, 0) / 3;
-                    for (int c = sl; c < nfull; c += LPO) {
-                        const int32_t* p = buf + 3 * c;
-                        const int v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4];
-                        const unsigned cs = (unsigned)v0 + (unsigned)v1 + (unsigned)v2;   // common.py:177-179
-                        cnt32 += cs;                                                        // detect_orfs.py:278
-                        mn32 = min(mn32, cs);
-                        if ((v0 | v1 | v2 | v3 | v4) != 0) {
-                            accumulate_codon<false>(v0, v1, v2, f0);
-                            accumulate_codon<false>(v1, v2, v3, f1);
-                            accumulate_codon<false>(v2, v3, v4, f2);
-                        }
-                    }
-                    for (int c = nfull + sl; c < ncod; c += LPO) {     // ragged end (statistics.py:71)
-                        const int32_t* p = buf + 3 * c;
-                        const int v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4];
-                        const unsigned cs = (unsigned)v0 + (unsigned)v1 + (unsigned)v2;
-                        cnt32 += cs;
-                        mn32 = min(mn32, cs);
-                        if (3 * c + 2 < nvals) accumulate_codon<false>(v0, v1, v2, f0);
-                        if (3 * c + 3 < nvals) accumulate_codon<false>(v1, v2, v3, f1);
-                        if (3 * c + 4 < nvals) accumulate_codon<false>(v2, v3, v4, f2);
-                    }
-                } else if (ncod > 0) {
-                    mn32 = 0;          // an all-zero tile: every codon sum is 0, nothing else changes
-                }
-            }
-            __syncwarp();
-            // carry the 2-value halo to the front of the next tile
-            const bool more = !done && !ended;
-            int t = 0;
-            if (more && sl < 2) t = buf[TN + sl];
-            __syncwarp();
-            if (more && sl < 2) buf[sl] = t;
-            tile_or = more ? t : 0;
-            if (!done) {
-                if (ended) done = true;
-                else fill = 2;
-            }
-            __syncwarp();
+            c0 = n0; c1 = n1; c2 = n2;
         }
 
         // ---- group reductions (all lanes converged) ----
@@ -564,7 +551,6 @@ score_orfs_packed_kernel(const ScoreArgs args) {
         }
 
         // ---- epilogue: statistics.py:92-115 + detect_orfs.py:278-299, once for all groups ----
-        const int L = total;
         const int n_codons = L / 3 > 1 ? L / 3 : 1;                        // detect_orfs.py:281
         const int na0 = a1_0 & 1023, nb0 = (a1_0 >> 10) & 1023, nc0 = a1_0 >> 20, ng0 = a2_0 & 1023, nu0 = a2_0 >> 10;
         const int na1 = a1_1 & 1023, nb1 = (a1_1 >> 10) & 1023, nc1 = a1_1 >> 20, ng1 = a2_1 & 1023, nu1 = a2_1 >> 10;
@@ -586,7 +572,6 @@ score_orfs_packed_kernel(const ScoreArgs args) {
         else if (sl == 5) nn = (double)K1;
         else nn = (double)K2;
         const double q = nn / dd;                                          // 0/0 -> NaN never wins
-        const int gb = g * LPO;
         double s0 = __shfl_sync(kFull, q, gb + 0);
         double s1 = __shfl_sync(kFull, q, gb + 1);
         double s2 = __shfl_sync(kFull, q, gb + 2);
@@ -797,6 +782,44 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
         atomicAdd(a.stats + threadIdx.x, (unsigned long long)((long long)a.weight * s_stats[threadIdx.x]));
     for (int i = threadIdx.x; i < kLenHist; i += kBinThreads)
         if (s_len[i]) atomicAdd(a.len_counts + i, (unsigned long long)((long long)a.weight * s_len[i]));
+}
+
+// ---- phasescore of one arbitrary (float) profile --------------------------------------------
+// statistics.py:48-115 for a single sequence of doubles (the metagene profiles are floats,
+// metagene.py:243-244).  One warp; frames in turn; same closed form as accumulate_codon.
+__global__ void __launch_bounds__(32) phasescore_values_kernel(const double* __restrict__ v, long long n,
+                                                                 double* score_out, int* valid_out) {
+    const int lane = threadIdx.x;
+    const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
+    double coh = 0.0;
+    int valid = -1;
+    for (int f = 0; f < 3; ++f) {
+        int K = 0, M = 0;
+        double sre = 0.0, sim = 0.0;
+        for (long long i = f + 3ll * lane; i + 2 < n; i += 96) {     // statistics.py:68,71
+            const double a = v[i], b = v[i + 1], c = v[i + 2];
+            if (a == 0.0 && b == 0.0 && c == 0.0) continue;          // statistics.py:72-73
+            ++K;
+            const double A = 2.0 * a - b - c, B = b - c;
+            if (A == 0.0 && B == 0.0) continue;                      // uniform codon: K only
+            const double r = rsqrt(fma(A, A, 3.0 * B * B));
+            sre = fma(A, r, sre);
+            sim = fma(B, r, sim);
+            ++M;
+        }
+        K = __reduce_add_sync(kFull, K);
+        M = __reduce_add_sync(kFull, M);
+        sre = warp_sum_f64(sre);
+        sim = warp_sum_f64(sim);
+        if (K == 0) { coh = 0.0; valid = 0; continue; }              // statistics.py:94-95
+        const double s = M == 0 ? kNaN : (sre * sre + 3.0 * sim * sim) / ((double)K * (double)M);
+        if (s > coh) { coh = s; valid = K; }                         // statistics.py:109-111
+        if (valid == -1) valid = K;                                  // statistics.py:112-113
+    }
+    if (lane == 0) {
+        *score_out = sqrt(coh);                                      // statistics.py:115
+        *valid_out = valid;
+    }
 }
 
 }  // namespace rt

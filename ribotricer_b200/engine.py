@@ -123,6 +123,7 @@ class Engine:
         self.contig_base = np.zeros(len(self.contig_len), np.int64)
         self._check(self.lib.rt_get_contig_base(self.ctx, _np_ptr(self.contig_base)))
         self.n_orf = 0
+        self._resident_index = None
 
     def contig_id(self, name: str) -> int:
         if not hasattr(self, "_contig_lut") or len(self._contig_lut) != len(self.contig_names):
@@ -155,6 +156,7 @@ class Engine:
         self._check(self.lib.rt_set_index(self.ctx, n, _np_ptr(exon_ptr), _np_ptr(exon_start), _np_ptr(exon_end),
                                           _np_ptr(orf_contig), _np_ptr(orf_strand)))
         self.n_orf = n
+        self._resident_index = None
 
     def score_bytes(self, lo: int = 0, hi: int | None = None) -> int:
         hi = self.n_orf if hi is None else hi

@@ -7,6 +7,7 @@ numpy 2.3.5 at generation time -- both versions are recorded in the files):
 
 Outputs (small, committed):
   tests/golden/phasescore_cases.json.gz   statistics.phasescore (statistics.py:48)
+  tests/golden/metagene_case.json.gz      metagene_coverage / align_metagenes (metagene.py:160,268)
   tests/golden/pipeline_cases.json.gz     merge_read_lengths (detect_orfs.py:54),
                                           orf_coverage (:134), export_orf_coverages
                                           (:206) and export_wig (:327) end to end
@@ -199,6 +200,80 @@ def random_case(name, seed, n_tx, contigs, unknown_chrom=False, odd_lengths=Fals
                 alignments=aln_list, psite_offsets={str(k): v for k, v in offsets.items()})
 
 
+# ------------------------------------------------------------------ metagene / offsets
+def metagene_case(seed=1003):
+    """Annotated CDSs with planted P-site offsets; the reference's metagene_coverage
+    (metagene.py:160) and align_metagenes (metagene.py:268) produce the expected values."""
+    from collections import Counter, defaultdict
+
+    from ribotricer.metagene import align_metagenes, metagene_coverage
+    from ribotricer.orf import ORF
+
+    rng = np.random.default_rng(seed)
+    contigs = [("mA", 60000), ("mB", 45000)]
+    header = ("ORF_ID\tORF_type\ttranscript_id\ttranscript_type\tgene_id\tgene_name\t"
+              "gene_type\tchrom\tstrand\tstart_codon\tcoordinate")
+    lines, orfs = [], []
+    planted = {27: 11, 28: 12, 29: 13, 30: 13, 31: 14}
+    probs = [0.08, 0.40, 0.27, 0.20, 0.05]
+    for t in range(90):
+        cname, clen = contigs[t % 2]
+        strand = "+" if rng.random() < 0.5 else "-"
+        n_ex = int(rng.integers(1, 4))
+        pos = 200 + (t // 2) * 1200
+        total = 3 * int(rng.integers(60, 330))
+        cuts = sorted(rng.choice(np.arange(1, total), n_ex - 1, replace=False).tolist()) if n_ex > 1 else []
+        parts = [b - a for a, b in zip([0] + cuts, cuts + [total])]
+        ivs = []
+        for plen in parts:
+            ivs.append((pos, pos + plen - 1))
+            pos += plen + int(rng.integers(30, 90))
+        coord = ",".join(f"{s}-{e}" for s, e in ivs)
+        lines.append(f"id{t}\tannotated\ttx{t}\tprotein_coding\tg{t}\tG{t}\tprotein_coding\t{cname}\t{strand}\tATG\t{coord}")
+        orfs.append((cname, strand, ivs))
+    aln = {}
+    for chrom, strand, ivs in orfs:
+        flat = [p for s, e in ivs for p in range(s, e + 1)]
+        if strand == "-":
+            flat.reverse()
+        n_reads = int(rng.poisson(len(flat) * float(rng.gamma(2.0) * 0.8)))
+        for _ in range(n_reads):
+            codon = int(rng.integers(0, len(flat) // 3))
+            fr = int(rng.choice([0, 1, 2], p=[0.75, 0.15, 0.10]))
+            psite = flat[3 * codon + fr]
+            length = int(rng.choice(list(planted), p=probs))
+            pos5 = psite - planted[length] if strand == "+" else psite + planted[length]
+            key = (length, strand, chrom, pos5)
+            aln[key] = aln.get(key, 0) + 1
+    case = dict(name="metagene", contigs=[list(c) for c in contigs], index=[header] + lines,
+                alignments=[(k[0], k[1], k[2], k[3], v) for k, v in aln.items()], planted=planted,
+                meta_min_reads=1500)
+    alignments = defaultdict(lambda: defaultdict(Counter))
+    rlc = {}
+    for length, strand, chrom, pos, n in case["alignments"]:
+        alignments[length][strand][(chrom, pos)] += n
+    # insertion order of read_length_counts = order of first appearance (bam.py:136); the test
+    # feeds the reads grouped by ascending length, so mirror that here
+    for length in sorted(alignments):
+        rlc[length] = sum(sum(t.values()) for t in alignments[length].values())
+    case["read_length_counts_in"] = {str(k): v for k, v in rlc.items()}
+    cds = [ORF.from_string(line + "\n") for line in lines]
+    with tempfile.TemporaryDirectory() as tmp:
+        prefix = os.path.join(tmp, "mg")
+        metagenes = metagene_coverage(cds, alignments, rlc, prefix, meta_min_reads=case["meta_min_reads"])
+        case["kept_lengths"] = list(rlc)
+        case["metagenes"] = {
+            str(length): dict(idx5=[int(i) for i in m[0].index], prof5=[float(x) for x in m[0].tolist()],
+                              idx3=[int(i) for i in m[1].index], prof3=[float(x) for x in m[1].tolist()],
+                              ps5=float(m[2]), v5=int(m[3]), ps3=float(m[4]), v3=int(m[5]))
+            for length, m in metagenes.items()}
+        case["profiles_5p_tsv"] = open(f"{prefix}_metagene_profiles_5p.tsv").read()
+        offsets = align_metagenes(metagenes, rlc, prefix, 0.428571428571, True)
+        case["psite_offsets"] = {str(k): int(v) for k, v in offsets.items()}
+        case["psite_offsets_txt"] = open(f"{prefix}_psite_offsets.txt").read()
+    return case
+
+
 PARAM_SETS = [
     dict(phase_score_cutoff=0.428571428571, min_valid_codons=5, min_reads_per_codon=0,
          min_valid_codons_ratio=0, min_density_over_orf=0.0, report_all=True),
@@ -268,6 +343,10 @@ def main():
         json.dump({"versions": versions(), "cases": done}, fh, separators=(",", ":"))
     for c in done:
         print(c["name"], "orfs:", len(c["index"]) - 1, "alignment keys:", len(c["alignments"]))
+    mg = metagene_case()
+    with gzip.open(os.path.join(HERE, "metagene_case.json.gz"), "wt") as fh:
+        json.dump({"versions": versions(), "case": mg}, fh, separators=(",", ":"))
+    print("metagene: kept", mg["kept_lengths"], "offsets", mg["psite_offsets"], "planted", mg["planted"])
 
 
 if __name__ == "__main__":

@@ -1,0 +1,176 @@
+"""The reference-facing Python surface (detect_orfs(), its inner seams, phasescore, the metagene
+step) on the GPU, against files and values produced by the unmodified reference."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import SCORE_TOL, alignments_to_reads, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _read_columns(case, by_length=False):
+    from ribotricer_b200.bam import ReadColumns
+
+    names = [c[0] for c in case["contigs"]]
+    lens = np.array([c[1] for c in case["contigs"]], np.int64)
+    if by_length:   # reads grouped by ascending length: read_length_counts insertion order (bam.py:136)
+        case = dict(case, alignments=sorted(case["alignments"], key=lambda a: a[0]))
+    return ReadColumns(names, lens, alignments_to_reads(case, names))
+
+
+def _rows(text):
+    lines = text.split("\n")
+    return lines[0], {r.split("\t")[0]: r.split("\t") for r in lines[1:] if r}
+
+
+def test_phasescore_function(engine):
+    """statistics.phasescore mirror: int and float sequences, quirk KATs of SURVEY.md 8(a)."""
+    from oracle import oracle_py as O
+    from ribotricer_b200.statistics import phasescore
+
+    assert phasescore([], engine) == (0.0, 0)
+    assert phasescore([1] + [0] * 29, engine) == (0.0, 0)
+    assert phasescore([0, 0, 0, 1] + [0] * 26, engine) == (1.0, 1)
+    assert phasescore([1, 1, 1] * 5, engine) == (0.0, 5)
+    s, v = phasescore([3, 1, 2, 0, 0, 0, 5, 0, 1, 2, 2, 2, 0, 4, 0, 1], engine)
+    assert abs(s - 0.39247762314783674) < 1e-12 and v == 4 and isinstance(s, np.float64)
+    cases = load_golden("phasescore_cases.json.gz")["cases"]
+    for c in cases[30:400:3]:
+        fr = O.frame_spectra(c["cov"])
+        s, v = phasescore(c["cov"], engine)
+        assert abs(s - float.fromhex(c["score"])) <= SCORE_TOL
+        if not O.is_frame_tie(fr):
+            assert v == c["valid"]
+    rng = np.random.default_rng(3)
+    for _ in range(40):   # float profiles, as the metagene step produces
+        vals = [x if rng.random() < 0.8 else 0.0 for x in rng.gamma(0.7, 1.0, int(rng.integers(3, 700))).tolist()]
+        s, v = phasescore(vals, engine)
+        rs, rv = O.select_frame(O.frame_spectra(vals))
+        assert abs(s - rs) <= SCORE_TOL and v == rv
+
+
+def test_detect_orfs_end_to_end(engine, tmp_path):
+    """detect_orfs() with explicit read lengths and offsets: TSV, WIG and bam summary against the
+    files written by the reference's export_orf_coverages / export_wig (golden)."""
+    from oracle import oracle_py as O
+    from ribotricer_b200 import detect_orfs as D
+
+    D._ENGINE = engine
+    for case in load_golden("pipeline_cases.json.gz")["cases"]:
+        reads = _read_columns(case)
+        idx_path = tmp_path / f"{case['name']}_index.tsv"
+        idx_path.write_text("\n".join(case["index"]) + "\n")
+        offsets = {int(k): v for k, v in case["psite_offsets"].items()}
+        for run in case["tsv"]:
+            prm = run["params"]
+            prefix = str(tmp_path / "out" / case["name"])
+            D.detect_orfs(reads, str(idx_path), prefix, "forward", None, dict(offsets), prm["phase_score_cutoff"],
+                          prm["min_valid_codons"], prm["min_reads_per_codon"], prm["min_valid_codons_ratio"],
+                          prm["min_density_over_orf"], prm["report_all"], meta_min_reads=10 ** 9)
+            got_hdr, got = _rows(open(f"{prefix}_translating_ORFs.tsv").read())
+            ref_hdr, ref = _rows(run["text"])
+            assert got_hdr == ref_hdr
+            order_got = [k for k in got if k in ref]
+            order_ref = [k for k in ref if k in got]
+            assert order_got == order_ref                      # ORF ordering
+            n_exc = 0
+            for oid, r in ref.items():
+                tie = O.is_frame_tie(O.frame_spectra(eval(r[17])))
+                near = abs(float(r[3]) - prm["phase_score_cutoff"]) <= SCORE_TOL
+                if oid not in got:
+                    assert tie or near, oid
+                    n_exc += 1
+                    continue
+                g = got[oid]
+                assert abs(float(g[3]) - float(r[3])) <= SCORE_TOL
+                cols = [0, 1, 4, 5, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17]
+                if not tie:
+                    cols += [6, 7] + ([2] if not near else [])
+                for c in cols:
+                    assert g[c] == r[c], (case["name"], oid, c, g[c], r[c])
+            for oid in got:
+                if oid not in ref:
+                    n_exc += 1
+            assert n_exc <= max(2, len(ref) // 20)
+        # WIG: every P-site the reference wrote, except those shifted beyond the contig pad
+        for tag, text in case["wig"].items():
+            assert open(f"{prefix}_{tag}.wig").read() == text
+        summary = open(f"{prefix}_bam_summary.txt").read()
+        assert summary.startswith(f"summary:\n\ttotal_reads: {len(reads)}\n\tunique_mapped: {len(reads)}\n")
+
+
+def test_inner_seams(engine, tmp_path):
+    """split_bam -> merge_read_lengths -> orf_coverage, the reference's own seam order."""
+    from ribotricer_b200 import detect_orfs as D
+    from ribotricer_b200.bam import split_bam
+    from ribotricer_b200.index import ORF
+
+    D._ENGINE = engine
+    case = load_golden("pipeline_cases.json.gz")["cases"][1]
+    reads = _read_columns(case)
+    alignments, rlc = split_bam(reads, "forward", str(tmp_path / "s"), None, engine=engine)
+    want = {}
+    for length, _, _, _, n in case["alignments"]:
+        want[length] = want.get(length, 0) + n
+    assert dict(rlc) == want
+    offsets = {int(k): v for k, v in case["psite_offsets"].items()}
+    merged = D.merge_read_lengths(alignments, offsets)
+    got = sorted([s, c, p, n] for s, t in merged.to_dict().items() for (c, p), n in t.items())
+    assert got == [m for m in case["merged"]]
+    for line, (oid, prof) in list(zip(case["index"][1:], case["profiles"]))[:25]:
+        orf = ORF.from_string(line + "\n")
+        assert orf.oid == oid
+        assert D.orf_coverage(orf, merged) == prof
+    # leader / trailer extension (detect_orfs.py:158-199), checked against the dict semantics
+    table = merged.to_dict()
+    orf = ORF.from_string(case["index"][3] + "\n")
+    ext = D.orf_coverage(orf, merged, offset_5p=7, offset_3p=3)
+    o5, o3 = (3, 7) if orf.strand == "-" else (7, 3)
+    pos = list(range(orf.intervals[0][0] - o5, orf.intervals[0][0]))
+    for s, e in orf.intervals:
+        pos += list(range(s, e + 1))
+    pos += list(range(orf.intervals[-1][1] + 1, orf.intervals[-1][1] + o3 + 1))
+    ref = [table[orf.strand].get((orf.chrom, p), 0) for p in pos]
+    assert ext == (ref[::-1] if orf.strand == "-" else ref)
+
+
+def test_metagene_and_offset_inference(engine, tmp_path):
+    """metagene_coverage + align_metagenes against the reference's own output (golden)."""
+    from ribotricer_b200 import detect_orfs as D
+    from ribotricer_b200 import metagene as mg
+    from ribotricer_b200.bam import split_bam
+
+    D._ENGINE = engine
+    case = load_golden("metagene_case.json.gz")["case"]
+    reads = _read_columns(case, by_length=True)
+    idx_path = tmp_path / "mg_index.tsv"
+    idx_path.write_text("\n".join(case["index"]) + "\n")
+    prefix = str(tmp_path / "mg")
+    annotated, _ = D.parse_ribotricer_index(str(idx_path))
+    assert len(annotated) == len(case["index"]) - 1
+    alignments, rlc = split_bam(reads, "forward", prefix, None, engine=engine)
+    assert {str(k): v for k, v in rlc.items()} == case["read_length_counts_in"]
+    rlc = dict(sorted(rlc.items()))
+    metagenes = mg.metagene_coverage(annotated, alignments, rlc, prefix, meta_min_reads=case["meta_min_reads"])
+    assert list(rlc) == case["kept_lengths"]
+    for length, ref in case["metagenes"].items():
+        m = metagenes[int(length)]
+        assert m[0][0] == ref["idx5"] and m[1][0] == ref["idx3"]
+        assert np.allclose(m[0][1], ref["prof5"], rtol=0, atol=1e-9)
+        assert np.allclose(m[1][1], ref["prof3"], rtol=0, atol=1e-9)
+        assert abs(m[2] - ref["ps5"]) <= SCORE_TOL and m[3] == ref["v5"]
+        assert abs(m[4] - ref["ps3"]) <= SCORE_TOL and m[5] == ref["v3"]
+    offsets = mg.align_metagenes(metagenes, rlc, prefix, 0.428571428571, True)
+    assert {str(k): v for k, v in offsets.items()} == case["psite_offsets"]
+    assert open(f"{prefix}_psite_offsets.txt").read() == case["psite_offsets_txt"]
+    # and the whole default-flag path: no read lengths, no offsets given
+    D.detect_orfs(reads, str(idx_path), prefix, None, None, None, 0.428571428571, 5, 0, 0, 0.0, True,
+                  meta_min_reads=case["meta_min_reads"])
+    assert os.path.exists(f"{prefix}_translating_ORFs.tsv")
+    assert open(f"{prefix}_protocol.txt").read().startswith("In total")
+    rows = open(f"{prefix}_translating_ORFs.tsv").read().split("\n")
+    assert len(rows) == len(case["index"]) + 1
+    n_tr = sum(1 for r in rows[1:] if r.split("\t")[2:3] == ["translating"])
+    assert n_tr > 0.5 * (len(case["index"]) - 1)
