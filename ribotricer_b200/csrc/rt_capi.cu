@@ -498,7 +498,7 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
     p.n_long = n_long;
     p.n_short = n - n_long;
     RT_CUDA(ctx, cudaMalloc(&p.d_list, sizeof(int32_t) * std::max<int64_t>(1, n)));
-    RT_CUDA(ctx, cudaMalloc(&p.d_fallback, sizeof(int32_t) * std::max<int64_t>(1, p.n_short)));
+    RT_CUDA(ctx, cudaMalloc(&p.d_fallback, sizeof(int32_t) * std::max<int64_t>(1, n)));
     RT_CUDA(ctx, cudaMemcpy(p.d_list, ids.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
     ctx->plans.push_back(p);
     *out = &ctx->plans.back();
@@ -545,47 +545,33 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
     a.prm = *params;
     a.out = *d_out;
     const int threads = rt::kScoreWarps * 32;
-    // 1. the long ORFs (generic kernel, one warp per ORF) on a side stream, beside the packed kernel
-    if (plan->n_long > 0) {
-        if (!ctx->aux_stream) {
-            RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
-            RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-            RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-        }
-        RT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-        RT_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    // 1. fused gather+score: long ORFs first (one warp each), then packs of short ORFs
+    {
         a.list = plan->d_list;
-        a.n_list = plan->n_long;
-        a.n_list_dev = nullptr;
-        a.work_counter = ctx->d_work_counter + 0;
-        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((plan->n_long + 7) / 8, ctx->n_sm));
-        rt::score_orfs_kernel<<<grid, threads, 0, ctx->aux_stream>>>(a);
-        ctx->launches++;
-        RT_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
-    }
-    // 2. everything else, several ORFs per warp
-    if (plan->n_short > 0) {
-        a.list = plan->d_list + plan->n_long;
-        a.n_list = plan->n_short;
+        a.n_list = plan->n_long + plan->n_short;
+        a.n_long = plan->n_long;
         a.n_list_dev = nullptr;
         a.work_counter = ctx->d_work_counter + 1;
         if (ctx->pack_lpo == 8) {
-            rt::score_orfs_packed_kernel<8><<<persistent_grid(ctx, rt::score_orfs_packed_kernel<8>, (plan->n_short + 3) / 4), threads, 0, st>>>(a);
+            const int64_t work = plan->n_long + (plan->n_short + 3) / 4;
+            rt::score_orfs_packed_kernel<8><<<persistent_grid(ctx, rt::score_orfs_packed_kernel<8>, work), threads, 0, st>>>(a);
         } else if (ctx->pack_lpo == 16) {
-            rt::score_orfs_packed_kernel<16><<<persistent_grid(ctx, rt::score_orfs_packed_kernel<16>, (plan->n_short + 1) / 2), threads, 0, st>>>(a);
+            const int64_t work = plan->n_long + (plan->n_short + 1) / 2;
+            rt::score_orfs_packed_kernel<16><<<persistent_grid(ctx, rt::score_orfs_packed_kernel<16>, work), threads, 0, st>>>(a);
         } else {
-            rt::score_orfs_packed_kernel<32><<<persistent_grid(ctx, rt::score_orfs_packed_kernel<32>, plan->n_short), threads, 0, st>>>(a);
+            const int64_t work = plan->n_long + plan->n_short;
+            rt::score_orfs_packed_kernel<32><<<persistent_grid(ctx, rt::score_orfs_packed_kernel<32>, work), threads, 0, st>>>(a);
         }
         ctx->launches++;
-        // 3. ORFs the packed kernel handed over (counts >= 2^20): normally none
+        // 2. ORFs the fused kernel handed over (counts >= 2^20): normally none
         a.list = plan->d_fallback;
         a.n_list = 0;
+        a.n_long = 0;
         a.n_list_dev = a.n_fallback;
         a.work_counter = ctx->d_work_counter + 2;
         rt::score_orfs_kernel<<<(unsigned)ctx->n_sm, threads, 0, st>>>(a);
         ctx->launches++;
     }
-    if (plan->n_long > 0) RT_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     RT_CUDA(ctx, cudaGetLastError());
     return RT_OK;
 }

@@ -189,6 +189,7 @@ struct ScoreArgs {
     long long orf_lo;           // output element k <-> ORF orf_lo + k
     const int32_t* list;        // ORF ids to score (absolute), longest first
     long long n_list;           // entries of `list` ...
+    long long n_long;           // fused kernel: the first n_long entries take a whole warp each
     const unsigned* n_list_dev; // ... or, when not NULL, read from the device (fallback queue)
     unsigned long long* work_counter;
     int32_t* fallback;          // packed kernel only: ORFs handed over to the generic kernel
@@ -198,7 +199,7 @@ struct ScoreArgs {
 };
 
 // Warp-uniform totals of one frame.
-struct FrameTotals {
+struct TileTotals {
     int na = 0, nb = 0, nc = 0, ng = 0, nu = 0;
     __device__ __forceinline__ void flush(FrameLane& f) {
         const unsigned t1 = __reduce_add_sync(kFull, f.w1);
@@ -245,7 +246,7 @@ score_orfs_kernel(const ScoreArgs args) {
             cur.rev = (desc >> 63) != 0;
 
             FrameLane f0, f1, f2;
-            FrameTotals t0, t1, t2;
+            TileTotals t0, t1, t2;
             unsigned cnt32 = 0, mn32 = 0xffffffffu;    // per lane, flushed with the packed counters
             long long count = 0;                       // warp-uniform totals
             long long min_codon = 0x7fffffffffffffffll;
@@ -388,16 +389,19 @@ score_orfs_kernel(const ScoreArgs args) {
     }
 }
 
-// ---- K3, packed: several short ORFs per warp ------------------------------------------------
-// ORFs of at most kPackMaxNt nt are scored LPO lanes per ORF, 32/LPO ORFs per warp in lock step,
-// so the per-ORF overhead (cursor, reductions, epilogue) is paid once per 32/LPO ORFs.  The host
-// sorts ORFs by length inside windows of the index, which keeps the groups of a warp balanced
-// and neighbouring ORFs (which share exons) close in time.  No shared memory: every lane owns
-// one codon per round, loads its three values straight from the coverage plane and gets the two
+// ---- K3, fused gather + score: LPO lanes per ORF, 32/LPO ORFs per warp in lock step -----------
+// The per-ORF overhead (cursor, reductions, epilogue) is paid once per 32/LPO ORFs.  The host sorts
+// ORFs by length inside windows of the index, which keeps the groups of a warp balanced and
+// neighbouring ORFs (which share exons) close in time.  No shared memory: every lane owns one
+// codon per round, loads its three values straight from the coverage plane and gets the two
 // values after them from its right-hand neighbour by shuffle; rounds are software pipelined.
+// ORFs longer than kPackMaxNt take a whole warp each (LPO = 32) and are started first.
 // An ORF that turns out to hold a count >= 2^kBigShift is appended to the fallback queue and
-// redone by the generic kernel.
-constexpr int kPackMaxNt = 3069;               // <= 1023 codons per frame: 10-bit packed fields never overflow
+// redone by the generic kernel (64-bit sums).
+constexpr int kPackMaxNt = 3069;      // <= 1023 codons per frame: 10-bit packed fields never overflow
+constexpr int kShortLPO = 8;          // lanes per short ORF
+constexpr int kLongFlushRounds = 31;  // whole-warp ORFs: flush the 10-bit fields every 31 rounds
+constexpr int kDeferLanes = 12;       // general codons wait until this many lanes hold one
 
 template <int LPO>
 __device__ __forceinline__ unsigned group_sum_u32(unsigned v) {
@@ -412,25 +416,45 @@ __device__ __forceinline__ double group_sum_f64(double v) {
     return v;
 }
 
-// Group-uniform cursor over the exon entries of one ORF in profile coordinates.
+// Group-uniform cursor over the exon entries of one ORF in profile coordinates.  It keeps the
+// current entry and the one after it, so that a round that crosses one exon junction needs no
+// divergent code: coverage slot of profile position p = org + dir * p.
 struct ProfileCursor {
     const uint64_t* entries;
     int n_ent;
-    int dir;            // +1 '+', -1 '-' (entries are then walked last to first)
-    int e = -1;         // current entry
-    int p0 = 0, p1 = 0; // profile range [p0, p1) of the current entry
-    long long addr = 0; // coverage slot of profile position p0
+    int dir;               // +1 '+', -1 '-' (entries are then walked last to first)
+    int e = -1;            // index of the current entry
+    int p1 = 0;            // the current entry covers profile positions [.., p1)
+    long long org = 0;
     bool zero = true;
+    int q1 = 0;            // the next entry covers [p1, q1); q1 == p1 when there is none
+    long long qorg = 0;
+    bool qzero = true;
 
-    __device__ __forceinline__ void advance() {   // precondition: e + 1 < n_ent
+    __device__ __forceinline__ void fetch_next() {      // decode entry e + 1 into the q-fields
+        if (e + 1 < n_ent) {
+            const uint64_t ent = __ldg(entries + (dir < 0 ? n_ent - 2 - e : e + 1));
+            const int len = (int)(ent & kLenMask);
+            const uint64_t off = ent >> kLenBits;
+            qzero = off == kZeroOff;
+            const long long first = dir < 0 ? (long long)off + len - 1 : (long long)off;
+            qorg = first - (long long)dir * p1;
+            q1 = p1 + len;
+        } else {
+            qzero = true;
+            q1 = p1;
+        }
+    }
+    __device__ __forceinline__ void advance() {
         ++e;
-        const uint64_t ent = __ldg(entries + (dir < 0 ? n_ent - 1 - e : e));
-        const int len = (int)(ent & kLenMask);
-        const uint64_t off = ent >> kLenBits;
-        zero = off == kZeroOff;
-        addr = dir < 0 ? (long long)off + len - 1 : (long long)off;
-        p0 = p1;
-        p1 += len;
+        p1 = q1;
+        org = qorg;
+        zero = qzero;
+        fetch_next();
+    }
+    __device__ __forceinline__ void init() {
+        fetch_next();   // entry 0 -> q
+        advance();      // q -> current, entry 1 -> q
     }
 };
 
@@ -440,188 +464,294 @@ __device__ __forceinline__ void load_round(const int32_t* cov, ProfileCursor& cu
                                            int& v0, int& v1, int& v2) {
     constexpr int RNT = 3 * LPO;
     v0 = v1 = v2 = 0;
-    if (P >= L) return;
-    while (P >= cur.p1) cur.advance();                   // group-uniform
+    const bool live = P < L;                             // groups past their end only take part in the vote
+    if (live)
+        while (P >= cur.p1) cur.advance();               // group-uniform
     const int p = P + 3 * sl;
-    if (P + RNT <= cur.p1) {                             // the whole round lies inside this entry
-        if (!cur.zero) {
-            const int32_t* s = cov + cur.addr + (long long)cur.dir * (p - cur.p0);
+    const bool inside = !live || P + RNT <= cur.p1;
+    if (__all_sync(kFull, inside)) {                     // every group is inside one entry
+        if (live && !cur.zero) {
+            const int32_t* s = cov + cur.org + (long long)cur.dir * p;
             v0 = ld_cov(s);
             v1 = ld_cov(s + cur.dir);
             v2 = ld_cov(s + 2 * cur.dir);
         }
         return;
     }
-    // the round crosses entries or the end of the ORF: position by position
+    if (!live) return;
+    if (P + RNT <= cur.q1 || cur.e + 2 >= cur.n_ent) {   // at most one junction in this round
+        const bool c0 = p < cur.p1, c1 = p + 1 < cur.p1, c2 = p + 2 < cur.p1;
+        const bool k0 = c0 ? !cur.zero : (p < cur.q1 && !cur.qzero);
+        const bool k1 = c1 ? !cur.zero : (p + 1 < cur.q1 && !cur.qzero);
+        const bool k2 = c2 ? !cur.zero : (p + 2 < cur.q1 && !cur.qzero);
+        const long long d = cur.dir;
+        if (k0) v0 = ld_cov(cov + (c0 ? cur.org : cur.qorg) + d * p);
+        if (k1) v1 = ld_cov(cov + (c1 ? cur.org : cur.qorg) + d * (p + 1));
+        if (k2) v2 = ld_cov(cov + (c2 ? cur.org : cur.qorg) + d * (p + 2));
+        return;
+    }
+    // several junctions inside one round (exons shorter than a round): position by position
     const int end = min(P + RNT, L);
+    int lo = 0;
     for (;;) {
+        // current entry covers [lo', p1) with lo' = start of entry; positions below were handled
         if (!cur.zero) {
-            const int32_t* s = cov + cur.addr - (long long)cur.dir * cur.p0;
-            if (p >= cur.p0 && p < cur.p1) v0 = ld_cov(s + (long long)cur.dir * p);
-            if (p + 1 >= cur.p0 && p + 1 < cur.p1) v1 = ld_cov(s + (long long)cur.dir * (p + 1));
-            if (p + 2 >= cur.p0 && p + 2 < cur.p1) v2 = ld_cov(s + (long long)cur.dir * (p + 2));
+            const long long d = cur.dir;
+            if (p >= lo && p < cur.p1) v0 = ld_cov(cov + cur.org + d * p);
+            if (p + 1 >= lo && p + 1 < cur.p1) v1 = ld_cov(cov + cur.org + d * (p + 1));
+            if (p + 2 >= lo && p + 2 < cur.p1) v2 = ld_cov(cov + cur.org + d * (p + 2));
         }
         if (cur.p1 >= end) break;
+        lo = cur.p1;
         cur.advance();
     }
 }
 
-template <int LPO>
-__global__ void __launch_bounds__(kScoreWarps * 32, 4)
-score_orfs_packed_kernel(const ScoreArgs args) {
-    constexpr int G = 32 / LPO;                    // ORFs per warp
-    const int lane = threadIdx.x & 31;
+// General codons are parked (one slot per frame and lane) and turned into unit vectors when
+// enough lanes hold one, so that the fp64 sequence runs with most lanes active.
+struct Deferred {
+    int A0 = 0, B0 = 0, A1 = 0, B1 = 0, A2 = 0, B2 = 0;
+    unsigned has = 0;
+};
+__device__ __forceinline__ void unit_vector_add(int A, int B, FrameLane& f) {
+    // |A|, |B| < 2^22: D is exact; MUFU seed (2^-22) + one Newton step -> ~1e-13 relative
+    const double dA = (double)A, dB = (double)B;
+    const double D = fma(dA, dA, (3.0 * dB) * dB);
+    const double r0 = (double)rsqrt_approx((float)D);
+    const double e = fma(-D * r0, r0, 1.0);
+    const double r = fma(0.5 * r0, e, r0);
+    f.sre = fma(dA, r, f.sre);
+    f.sim = fma(dB, r, f.sim);
+}
+__device__ __forceinline__ void flush_deferred(Deferred& d, FrameLane& f0, FrameLane& f1, FrameLane& f2) {
+    if (d.has & 1u) unit_vector_add(d.A0, d.B0, f0);
+    if (d.has & 2u) unit_vector_add(d.A1, d.B1, f1);
+    if (d.has & 4u) unit_vector_add(d.A2, d.B2, f2);
+    d.has = 0;
+}
+// statistics.py:72-90 for one complete codon of frame F (see accumulate_codon above).
+template <int F>
+__device__ __forceinline__ void classify_codon(int a, int b, int c, FrameLane& f, Deferred& d) {
+    if ((a | b | c) == 0) return;                       // statistics.py:72-73
+    if ((b | c) == 0) f.w1 += 1u;
+    else if ((a | c) == 0) f.w1 += 1u << 10;
+    else if ((a | b) == 0) f.w1 += 1u << 20;
+    else if (a == b && b == c) f.w2 += 1u << 10;        // uniform: counts in K only
+    else {
+        f.w2 += 1u;
+        int& A = F == 0 ? d.A0 : F == 1 ? d.A1 : d.A2;
+        int& B = F == 0 ? d.B0 : F == 1 ? d.B1 : d.B2;
+        if (d.has & (1u << F)) unit_vector_add(A, B, f);   // slot taken: settle the older codon now
+        A = 2 * a - b - c;
+        B = b - c;
+        d.has |= 1u << F;
+    }
+}
+
+// Warp-uniform totals of one frame (whole-warp ORFs only).
+struct FrameTotals {
+    int na = 0, nb = 0, nc = 0, ng = 0, nu = 0;
+    __device__ __forceinline__ void flush(FrameLane& f) {
+        const unsigned t1 = __reduce_add_sync(kFull, f.w1);
+        const unsigned t2 = __reduce_add_sync(kFull, f.w2);
+        na += t1 & 1023;
+        nb += (t1 >> 10) & 1023;
+        nc += t1 >> 20;
+        ng += t2 & 1023;
+        nu += t2 >> 10;
+        f.w1 = f.w2 = 0;
+    }
+};
+
+template <int LPO, bool Long>
+__device__ __forceinline__ void score_pack(const ScoreArgs& args, long long item0, long long item_end, int lane) {
     const int sl = lane % LPO;                     // lane within the group
     const int gb = lane - sl;                      // first lane of the group
     const int nbr = sl + 1 == LPO ? gb : lane + 1; // right-hand neighbour (wraps to the next round)
     const double kSqrt3 = 1.7320508075688772;
     const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
-    const long long n_packs = (args.n_list + G - 1) / G;
 
-    for (;;) {
-        unsigned long long pack = 0;
-        if (lane == 0) pack = atomicAdd(args.work_counter, 1ull);
-        pack = __shfl_sync(kFull, pack, 0);
-        if ((long long)pack >= n_packs) break;
+    const long long item = item0 + lane / LPO;
+    const bool active = item < item_end;
+    int orf = 0, L = 0;
+    uint64_t desc = 0;
+    if (active) {
+        orf = __ldg(args.list + item);
+        desc = __ldg(args.orf_desc + orf);
+        L = __ldg(args.orf_len + orf);
+    }
+    ProfileCursor cur;
+    cur.entries = args.exon_entries + (desc & kBeginMask);
+    cur.n_ent = (int)((desc >> 40) & kMaxEntriesPerOrf);
+    cur.dir = (desc >> 63) != 0 ? -1 : 1;
+    cur.init();
 
-        const long long item = (long long)pack * G + lane / LPO;
-        const bool active = item < args.n_list;
-        int orf = 0, L = 0;
-        uint64_t desc = 0;
-        if (active) {
-            orf = __ldg(args.list + item);
-            desc = __ldg(args.orf_desc + orf);
-            L = __ldg(args.orf_len + orf);
-        }
-        ProfileCursor cur;
-        cur.entries = args.exon_entries + (desc & kBeginMask);
-        cur.n_ent = (int)((desc >> 40) & kMaxEntriesPerOrf);
-        cur.dir = (desc >> 63) != 0 ? -1 : 1;
+    FrameLane f0, f1, f2;
+    Deferred dfr;
+    FrameTotals t0, t1, t2;                       // Long only
+    long long count64 = 0;                        // Long only
+    unsigned cnt32 = 0, mn32 = 0xffffffffu;
+    int ormask = 0;
+    const int ncod = (L + 2) / 3;                 // codons incl. a trailing partial one
+    const int rounds = __reduce_max_sync(kFull, (ncod + LPO - 1) / LPO);
 
-        FrameLane f0, f1, f2;
-        unsigned cnt32 = 0, mn32 = 0xffffffffu;
-        int ormask = 0;
-        const int ncod = (L + 2) / 3;                           // codons incl. a trailing partial one
-        const int rounds = __reduce_max_sync(kFull, (ncod + LPO - 1) / LPO);
-
-        int c0, c1, c2;
-        load_round<LPO>(args.cov, cur, 0, L, sl, c0, c1, c2);
-        for (int r = 0; r < rounds; ++r) {
-            int n0, n1, n2;
-            load_round<LPO>(args.cov, cur, (r + 1) * 3 * LPO, L, sl, n0, n1, n2);
-            // values 3 and 4 of this lane's five come from the neighbour's codon
-            const int v3 = __shfl_sync(kFull, sl == 0 ? n0 : c0, nbr);
-            const int v4 = __shfl_sync(kFull, sl == 0 ? n1 : c1, nbr);
-            const int p = 3 * (r * LPO + sl);
-            if (p < L) {
-                const unsigned cs = (unsigned)c0 + (unsigned)c1 + (unsigned)c2;   // common.py:177-179
-                cnt32 += cs;                                                        // detect_orfs.py:278
-                mn32 = min(mn32, cs);
-                ormask |= c0 | c1 | c2;
-                if ((c0 | c1 | c2 | v3 | v4) != 0) {
-                    if (p + 4 < L) {
-                        accumulate_codon<false>(c0, c1, c2, f0);
-                        accumulate_codon<false>(c1, c2, v3, f1);
-                        accumulate_codon<false>(c2, v3, v4, f2);
-                    } else {                                                        // ragged end (statistics.py:71)
-                        if (p + 2 < L) accumulate_codon<false>(c0, c1, c2, f0);
-                        if (p + 3 < L) accumulate_codon<false>(c1, c2, v3, f1);
-                    }
+    int c0, c1, c2;
+    load_round<LPO>(args.cov, cur, 0, L, sl, c0, c1, c2);
+    for (int r = 0; r < rounds; ++r) {
+        int n0, n1, n2;
+        load_round<LPO>(args.cov, cur, (r + 1) * 3 * LPO, L, sl, n0, n1, n2);
+        // values 3 and 4 of this lane's five come from the neighbour's codon
+        const int v3 = __shfl_sync(kFull, sl == 0 ? n0 : c0, nbr);
+        const int v4 = __shfl_sync(kFull, sl == 0 ? n1 : c1, nbr);
+        const int p = 3 * (r * LPO + sl);
+        if (p < L) {
+            const unsigned cs = (unsigned)c0 + (unsigned)c1 + (unsigned)c2;   // common.py:177-179
+            cnt32 += cs;                                                        // detect_orfs.py:278
+            mn32 = min(mn32, cs);
+            ormask |= c0 | c1 | c2;
+            if ((c0 | c1 | c2 | v3 | v4) != 0) {
+                if (p + 4 < L) {
+                    classify_codon<0>(c0, c1, c2, f0, dfr);
+                    classify_codon<1>(c1, c2, v3, f1, dfr);
+                    classify_codon<2>(c2, v3, v4, f2, dfr);
+                } else {                                                        // ragged end (statistics.py:71)
+                    if (p + 2 < L) classify_codon<0>(c0, c1, c2, f0, dfr);
+                    if (p + 3 < L) classify_codon<1>(c1, c2, v3, f1, dfr);
                 }
             }
-            c0 = n0; c1 = n1; c2 = n2;
         }
+        if (__popc(__ballot_sync(kFull, dfr.has != 0)) >= kDeferLanes) flush_deferred(dfr, f0, f1, f2);
+        if (Long && (r % kLongFlushRounds) == kLongFlushRounds - 1) {
+            t0.flush(f0); t1.flush(f1); t2.flush(f2);
+            count64 += __reduce_add_sync(kFull, cnt32);
+            cnt32 = 0;
+        }
+        c0 = n0; c1 = n1; c2 = n2;
+    }
+    flush_deferred(dfr, f0, f1, f2);
 
-        // ---- group reductions (all lanes converged) ----
+    // ---- reductions (all lanes converged) ----
+    int na0, nb0, nc0, ng0, nu0, na1, nb1, nc1, ng1, nu1, na2, nb2, nc2, ng2, nu2;
+    long long count;
+    if (Long) {
+        t0.flush(f0); t1.flush(f1); t2.flush(f2);
+        count = count64 + __reduce_add_sync(kFull, cnt32);
+        na0 = t0.na; nb0 = t0.nb; nc0 = t0.nc; ng0 = t0.ng; nu0 = t0.nu;
+        na1 = t1.na; nb1 = t1.nb; nc1 = t1.nc; ng1 = t1.ng; nu1 = t1.nu;
+        na2 = t2.na; nb2 = t2.nb; nc2 = t2.nc; ng2 = t2.ng; nu2 = t2.nu;
+        mn32 = __reduce_min_sync(kFull, mn32);
+        ormask = (int)__reduce_or_sync(kFull, (unsigned)ormask);
+    } else {
         const unsigned a1_0 = group_sum_u32<LPO>(f0.w1), a2_0 = group_sum_u32<LPO>(f0.w2);
         const unsigned a1_1 = group_sum_u32<LPO>(f1.w1), a2_1 = group_sum_u32<LPO>(f1.w2);
         const unsigned a1_2 = group_sum_u32<LPO>(f2.w1), a2_2 = group_sum_u32<LPO>(f2.w2);
-        const unsigned count = group_sum_u32<LPO>(cnt32);
+        count = (long long)group_sum_u32<LPO>(cnt32);
 #pragma unroll
         for (int o = LPO / 2; o > 0; o >>= 1) {
             mn32 = min(mn32, __shfl_xor_sync(kFull, mn32, o));
             ormask |= __shfl_xor_sync(kFull, ormask, o);
         }
-        const bool any_general = __any_sync(kFull, ((a2_0 | a2_1 | a2_2) & 1023u) != 0);
-        double re0 = 0.0, im0 = 0.0, re1 = 0.0, im1 = 0.0, re2 = 0.0, im2 = 0.0;
-        if (any_general) {
-            re0 = group_sum_f64<LPO>(f0.sre); im0 = group_sum_f64<LPO>(f0.sim);
-            re1 = group_sum_f64<LPO>(f1.sre); im1 = group_sum_f64<LPO>(f1.sim);
-            re2 = group_sum_f64<LPO>(f2.sre); im2 = group_sum_f64<LPO>(f2.sim);
-        }
+        na0 = a1_0 & 1023; nb0 = (a1_0 >> 10) & 1023; nc0 = a1_0 >> 20; ng0 = a2_0 & 1023; nu0 = a2_0 >> 10;
+        na1 = a1_1 & 1023; nb1 = (a1_1 >> 10) & 1023; nc1 = a1_1 >> 20; ng1 = a2_1 & 1023; nu1 = a2_1 >> 10;
+        na2 = a1_2 & 1023; nb2 = (a1_2 >> 10) & 1023; nc2 = a1_2 >> 20; ng2 = a2_2 & 1023; nu2 = a2_2 >> 10;
+    }
+    const bool any_general = __any_sync(kFull, (ng0 | ng1 | ng2) != 0);
+    double re0 = 0.0, im0 = 0.0, re1 = 0.0, im1 = 0.0, re2 = 0.0, im2 = 0.0;
+    if (any_general) {
+        re0 = group_sum_f64<LPO>(f0.sre); im0 = group_sum_f64<LPO>(f0.sim);
+        re1 = group_sum_f64<LPO>(f1.sre); im1 = group_sum_f64<LPO>(f1.sim);
+        re2 = group_sum_f64<LPO>(f2.sre); im2 = group_sum_f64<LPO>(f2.sim);
+    }
 
-        // ---- epilogue: statistics.py:92-115 + detect_orfs.py:278-299, once for all groups ----
-        const int n_codons = L / 3 > 1 ? L / 3 : 1;                        // detect_orfs.py:281
-        const int na0 = a1_0 & 1023, nb0 = (a1_0 >> 10) & 1023, nc0 = a1_0 >> 20, ng0 = a2_0 & 1023, nu0 = a2_0 >> 10;
-        const int na1 = a1_1 & 1023, nb1 = (a1_1 >> 10) & 1023, nc1 = a1_1 >> 20, ng1 = a2_1 & 1023, nu1 = a2_1 >> 10;
-        const int na2 = a1_2 & 1023, nb2 = (a1_2 >> 10) & 1023, nc2 = a1_2 >> 20, ng2 = a2_2 & 1023, nu2 = a2_2 >> 10;
-        const int K0 = na0 + nb0 + nc0 + ng0 + nu0;
-        const int K1 = na1 + nb1 + nc1 + ng1 + nu1;
-        const int K2 = na2 + nb2 + nc2 + ng2 + nu2;
-        re0 += 0.5 * (double)(2 * na0 - nb0 - nc0); im0 = kSqrt3 * (im0 + 0.5 * (double)(nb0 - nc0));
-        re1 += 0.5 * (double)(2 * na1 - nb1 - nc1); im1 = kSqrt3 * (im1 + 0.5 * (double)(nb1 - nc1));
-        re2 += 0.5 * (double)(2 * na2 - nb2 - nc2); im2 = kSqrt3 * (im2 + 0.5 * (double)(nb2 - nc2));
-        // one fp64 division sequence for all seven quotients of every group: sub-lanes 0-2 the
-        // coherences |sum u|^2 / (K * M), sub-lane 3 the density, sub-lanes 4-6 K_f / n_codons
-        double nn, dd = (double)n_codons;
-        if (sl == 0) { nn = re0 * re0 + im0 * im0; dd = (double)K0 * (double)(K0 - nu0); }
-        else if (sl == 1) { nn = re1 * re1 + im1 * im1; dd = (double)K1 * (double)(K1 - nu1); }
-        else if (sl == 2) { nn = re2 * re2 + im2 * im2; dd = (double)K2 * (double)(K2 - nu2); }
-        else if (sl == 3) nn = (double)count;                              // detect_orfs.py:287
-        else if (sl == 4) nn = (double)K0;                                 // detect_orfs.py:285
-        else if (sl == 5) nn = (double)K1;
-        else nn = (double)K2;
-        const double q = nn / dd;                                          // 0/0 -> NaN never wins
-        double s0 = __shfl_sync(kFull, q, gb + 0);
-        double s1 = __shfl_sync(kFull, q, gb + 1);
-        double s2 = __shfl_sync(kFull, q, gb + 2);
-        const double density = __shfl_sync(kFull, q, gb + 3);
-        // statistics.py:64-66,92-115: running maximum with the K==0 reset quirk
-        double coh = 0.0;
-        int vf = -1;          // frame whose K is `valid`; -1: valid = 0
-        bool unset = true;    // valid == -1 in the reference
-        if (K0 == 0) { coh = 0.0; vf = -1; unset = false; s0 = kNaN; }
-        else { if (s0 > coh) { coh = s0; vf = 0; unset = false; } if (unset) { vf = 0; unset = false; } }
-        if (K1 == 0) { coh = 0.0; vf = -1; unset = false; s1 = kNaN; }
-        else { if (s1 > coh) { coh = s1; vf = 1; unset = false; } if (unset) { vf = 1; unset = false; } }
-        if (K2 == 0) { coh = 0.0; vf = -1; unset = false; s2 = kNaN; }
-        else { if (s2 > coh) { coh = s2; vf = 2; unset = false; } if (unset) { vf = 2; unset = false; } }
-        const double score = sqrt(coh);                                    // statistics.py:115
-        const int valid = vf == 0 ? K0 : vf == 1 ? K1 : vf == 2 ? K2 : 0;
-        double ratio = __shfl_sync(kFull, q, gb + (vf >= 0 ? 4 + vf : 4));
-        if (vf < 0) ratio = 0.0;
+    // ---- epilogue: statistics.py:92-115 + detect_orfs.py:278-299, once for all groups ----
+    const int n_codons = L / 3 > 1 ? L / 3 : 1;                        // detect_orfs.py:281
+    const int K0 = na0 + nb0 + nc0 + ng0 + nu0;
+    const int K1 = na1 + nb1 + nc1 + ng1 + nu1;
+    const int K2 = na2 + nb2 + nc2 + ng2 + nu2;
+    re0 += 0.5 * (double)(2 * na0 - nb0 - nc0); im0 = kSqrt3 * (im0 + 0.5 * (double)(nb0 - nc0));
+    re1 += 0.5 * (double)(2 * na1 - nb1 - nc1); im1 = kSqrt3 * (im1 + 0.5 * (double)(nb1 - nc1));
+    re2 += 0.5 * (double)(2 * na2 - nb2 - nc2); im2 = kSqrt3 * (im2 + 0.5 * (double)(nb2 - nc2));
+    // one fp64 division sequence for all seven quotients of every group: sub-lanes 0-2 the
+    // coherences |sum u|^2 / (K * M), sub-lane 3 the density, sub-lanes 4-6 K_f / n_codons
+    double nn, dd = (double)n_codons;
+    if (sl == 0) { nn = re0 * re0 + im0 * im0; dd = (double)K0 * (double)(K0 - nu0); }
+    else if (sl == 1) { nn = re1 * re1 + im1 * im1; dd = (double)K1 * (double)(K1 - nu1); }
+    else if (sl == 2) { nn = re2 * re2 + im2 * im2; dd = (double)K2 * (double)(K2 - nu2); }
+    else if (sl == 3) nn = (double)count;                              // detect_orfs.py:287
+    else if (sl == 4) nn = (double)K0;                                 // detect_orfs.py:285
+    else if (sl == 5) nn = (double)K1;
+    else nn = (double)K2;
+    const double q = nn / dd;                                          // 0/0 -> NaN never wins
+    double s0 = __shfl_sync(kFull, q, gb + 0);
+    double s1 = __shfl_sync(kFull, q, gb + 1);
+    double s2 = __shfl_sync(kFull, q, gb + 2);
+    const double density = __shfl_sync(kFull, q, gb + 3);
+    // statistics.py:64-66,92-115: running maximum with the K==0 reset quirk
+    double coh = 0.0;
+    int vf = -1;          // frame whose K is `valid`; -1: valid = 0
+    bool unset = true;    // valid == -1 in the reference
+    if (K0 == 0) { coh = 0.0; vf = -1; unset = false; s0 = kNaN; }
+    else { if (s0 > coh) { coh = s0; vf = 0; unset = false; } if (unset) { vf = 0; unset = false; } }
+    if (K1 == 0) { coh = 0.0; vf = -1; unset = false; s1 = kNaN; }
+    else { if (s1 > coh) { coh = s1; vf = 1; unset = false; } if (unset) { vf = 1; unset = false; } }
+    if (K2 == 0) { coh = 0.0; vf = -1; unset = false; s2 = kNaN; }
+    else { if (s2 > coh) { coh = s2; vf = 2; unset = false; } if (unset) { vf = 2; unset = false; } }
+    const double score = sqrt(coh);                                    // statistics.py:115
+    const int valid = vf == 0 ? K0 : vf == 1 ? K1 : vf == 2 ? K2 : 0;
+    double ratio = __shfl_sync(kFull, q, gb + (vf >= 0 ? 4 + vf : 4));
+    if (vf < 0) ratio = 0.0;
 
-        if (active && sl == 0) {
-            if ((ormask >> kBigShift) != 0) {
-                // a huge count: 32-bit sums may have wrapped -> hand over to the generic kernel
-                args.fallback[atomicAdd(args.n_fallback, 1u)] = orf;
-            } else {
-                const long long k_out = (long long)orf - args.orf_lo;
-                const unsigned min_codon = L == 0 ? 0u : mn32;
-                const bool ok = score >= args.prm.phase_score_cutoff &&
-                                (double)valid >= args.prm.min_valid_codons &&
-                                (L == 0 || (double)min_codon >= args.prm.min_reads_per_codon) &&
-                                ratio >= args.prm.min_valid_codons_ratio &&
-                                density >= args.prm.min_density_over_orf;   // detect_orfs.py:289-299
-                args.out.score[k_out] = score;
-                args.out.valid[k_out] = valid;
-                args.out.count[k_out] = (long long)count;
-                args.out.length[k_out] = L;
-                if (args.out.min_codon) args.out.min_codon[k_out] = (int32_t)min_codon;
-                if (args.out.status) args.out.status[k_out] = ok ? 1 : 0;
-                if (args.out.frame_K) {
-                    args.out.frame_K[3 * k_out + 0] = K0;
-                    args.out.frame_K[3 * k_out + 1] = K1;
-                    args.out.frame_K[3 * k_out + 2] = K2;
-                }
-                if (args.out.frame_s) {
-                    args.out.frame_s[3 * k_out + 0] = s0;
-                    args.out.frame_s[3 * k_out + 1] = s1;
-                    args.out.frame_s[3 * k_out + 2] = s2;
-                }
+    if (active && sl == 0) {
+        if ((ormask >> kBigShift) != 0) {
+            // a huge count: 32-bit sums may have wrapped -> hand over to the generic kernel
+            args.fallback[atomicAdd(args.n_fallback, 1u)] = orf;
+        } else {
+            const long long k_out = (long long)orf - args.orf_lo;
+            const unsigned min_codon = L == 0 ? 0u : mn32;
+            const bool ok = score >= args.prm.phase_score_cutoff &&
+                            (double)valid >= args.prm.min_valid_codons &&
+                            (L == 0 || (double)min_codon >= args.prm.min_reads_per_codon) &&
+                            ratio >= args.prm.min_valid_codons_ratio &&
+                            density >= args.prm.min_density_over_orf;   // detect_orfs.py:289-299
+            args.out.score[k_out] = score;
+            args.out.valid[k_out] = valid;
+            args.out.count[k_out] = count;
+            args.out.length[k_out] = L;
+            if (args.out.min_codon) args.out.min_codon[k_out] = (int32_t)min_codon;
+            if (args.out.status) args.out.status[k_out] = ok ? 1 : 0;
+            if (args.out.frame_K) {
+                args.out.frame_K[3 * k_out + 0] = K0;
+                args.out.frame_K[3 * k_out + 1] = K1;
+                args.out.frame_K[3 * k_out + 2] = K2;
+            }
+            if (args.out.frame_s) {
+                args.out.frame_s[3 * k_out + 0] = s0;
+                args.out.frame_s[3 * k_out + 1] = s1;
+                args.out.frame_s[3 * k_out + 2] = s2;
             }
         }
-        __syncwarp();
+    }
+    __syncwarp();
+}
+
+// Work items: [0, n_long) one long ORF per warp, then packs of 32/LPO short ORFs.
+template <int LPO>
+__global__ void __launch_bounds__(kScoreWarps * 32, 4)
+score_orfs_packed_kernel(const ScoreArgs args) {
+    constexpr int G = 32 / LPO;
+    const int lane = threadIdx.x & 31;
+    const long long n_short = args.n_list - args.n_long;
+    const long long n_work = args.n_long + (n_short + G - 1) / G;
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(args.work_counter, 1ull);
+        w = __shfl_sync(kFull, w, 0);
+        if ((long long)w >= n_work) break;
+        if ((long long)w < args.n_long) {
+            score_pack<32, true>(args, (long long)w, (long long)w + 1, lane);
+        } else {
+            score_pack<LPO, false>(args, args.n_long + ((long long)w - args.n_long) * G, args.n_list, lane);
+        }
     }
 }
 

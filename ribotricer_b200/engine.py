@@ -124,6 +124,7 @@ class Engine:
         self._check(self.lib.rt_get_contig_base(self.ctx, _np_ptr(self.contig_base)))
         self.n_orf = 0
         self._resident_index = None
+        self._contig_lut = {n: i for i, n in enumerate(self.contig_names)}
 
     def contig_id(self, name: str) -> int:
         if not hasattr(self, "_contig_lut") or len(self._contig_lut) != len(self.contig_names):
