@@ -845,53 +845,71 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
     const long long block_base = (long long)blockIdx.x * (kBinThreads * kBinReadsPerThread);
     // per-thread 4-bit counters of categories RT_ST_QCFAIL..RT_ST_BADREF (<= 8 reads per thread)
     unsigned packed = 0;
-#pragma unroll 2
-    for (int it = 0; it < kBinReadsPerThread; ++it) {
-        const long long i = block_base + (long long)it * kBinThreads + threadIdx.x;
-        int len = -1;            // >= 0: counts in read_length_counts
-        long long slot = -1;     // >= 0: coverage slot to bump
-        if (i < a.n) {
-            const unsigned fl = a.flag[i];
-            int cat = classify_read(fl, a.mapq[i], a.nh[i]);
-            if (cat == RT_ST_VALID) {
-                const int l = a.mlen[i];                        // bam.py:99
-                const int mode = __ldg(a.len_table + l);
-                const bool rev = (fl & 0x10) != 0;              // bam.py:94
-                int strand;
-                long long pos;
-                if (a.protocol == RT_PROTOCOL_FORWARD) {        // bam.py:105-117
-                    strand = rev ? 1 : 0;
-                    pos = rev ? a.last[i] : a.first[i];
-                } else {                                        // bam.py:118-131
-                    strand = rev ? 0 : 1;
-                    pos = rev ? a.first[i] : a.last[i];
-                }
-                const int c = a.ref_id[i];
-                if (mode == RT_LEN_FILTERED || a.protocol > RT_PROTOCOL_REVERSE) {
-                    cat = 0;                                    // bam.py:101 / no protocol branch: only `total`
-                } else if (c < 0 || c >= a.n_contig) {
-                    cat = RT_ST_BADREF;                         // chrom is None, bam.py:133
-                } else {
-                    len = l;                                    // bam.py:136
-                    if (mode >= 0) {                            // detect_orfs.py:74
-                        const long long p = pos + 1 + (strand == 0 ? mode : -mode);   // bam.py:135, detect_orfs.py:78-81
-                        if (p < 1 - a.pad || p > a.contig_len[c] + a.pad) atomicAdd(&s_stats[RT_ST_OOB], 1u);
-                        else slot = (long long)strand * a.plane + a.contig_base[c] + a.pad + p;
+    constexpr int kBatch = 4;     // reads per thread whose columns are in flight together
+#pragma unroll 1
+    for (int it0 = 0; it0 < kBinReadsPerThread; it0 += kBatch) {
+        // ---- all column loads of the batch first (7 x kBatch independent, coalesced loads) ----
+        unsigned fl[kBatch], mq[kBatch], nh[kBatch], ml[kBatch];
+        int fi[kBatch], la[kBatch], rid[kBatch];
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const long long i = block_base + (long long)(it0 + j) * kBinThreads + threadIdx.x;
+            const bool in = i < a.n;
+            fl[j] = in ? a.flag[i] : 0u;
+            mq[j] = in ? a.mapq[i] : 0u;
+            nh[j] = in ? a.nh[i] : 0u;
+            ml[j] = in ? a.mlen[i] : 0u;
+            fi[j] = in ? a.first[i] : 0;
+            la[j] = in ? a.last[i] : 0;
+            rid[j] = in ? a.ref_id[i] : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const long long i = block_base + (long long)(it0 + j) * kBinThreads + threadIdx.x;
+            int len = -1;            // >= 0: counts in read_length_counts
+            long long slot = -1;     // >= 0: coverage slot to bump
+            if (i < a.n) {
+                int cat = classify_read(fl[j], mq[j], nh[j]);
+                if (cat == RT_ST_VALID) {
+                    const int l = (int)ml[j];                       // bam.py:99
+                    const int mode = __ldg(a.len_table + l);
+                    const bool rev = (fl[j] & 0x10) != 0;           // bam.py:94
+                    int strand;
+                    long long pos;
+                    if (a.protocol == RT_PROTOCOL_FORWARD) {        // bam.py:105-117
+                        strand = rev ? 1 : 0;
+                        pos = rev ? la[j] : fi[j];
+                    } else {                                        // bam.py:118-131
+                        strand = rev ? 0 : 1;
+                        pos = rev ? fi[j] : la[j];
+                    }
+                    const int c = rid[j];
+                    if (mode == RT_LEN_FILTERED || a.protocol > RT_PROTOCOL_REVERSE) {
+                        cat = 0;                                    // bam.py:101 / no protocol branch: only `total`
+                    } else if (c < 0 || c >= a.n_contig) {
+                        cat = RT_ST_BADREF;                         // chrom is None, bam.py:133
+                    } else {
+                        len = l;                                    // bam.py:136
+                        if (mode >= 0) {                            // detect_orfs.py:74
+                            const long long p = pos + 1 + (strand == 0 ? mode : -mode);   // bam.py:135, detect_orfs.py:78-81
+                            if (p < 1 - a.pad || p > __ldg(a.contig_len + c) + a.pad) atomicAdd(&s_stats[RT_ST_OOB], 1u);
+                            else slot = (long long)strand * a.plane + __ldg(a.contig_base + c) + a.pad + p;
+                        }
                     }
                 }
+                if (cat) packed += 1u << (4 * (cat - 1));
             }
-            if (cat) packed += 1u << (4 * (cat - 1));
-        }
-        // detect_orfs.py:82: one atomic per distinct slot in the warp (duplicated 5' ends are the
-        // rule in Ribo-seq, and adjacent in a coordinate-sorted BAM)
-        const unsigned same_slot = __match_any_sync(kFull, slot);
-        if (slot >= 0 && lane == __ffs(same_slot) - 1)
-            atomicAdd(a.cov + slot, a.weight * __popc(same_slot));
-        // bam.py:136: one shared-memory atomic per distinct read length in the warp
-        const unsigned same_len = __match_any_sync(kFull, len);
-        if (len >= 0 && lane == __ffs(same_len) - 1) {
-            if (len < kLenHist) atomicAdd(&s_len[len], (unsigned)__popc(same_len));
-            else atomicAdd(a.len_counts + len, (unsigned long long)((long long)a.weight * __popc(same_len)));
+            // detect_orfs.py:82: one atomic per distinct slot in the warp (duplicated 5' ends are the
+            // rule in Ribo-seq, and adjacent in a coordinate-sorted BAM)
+            const unsigned same_slot = __match_any_sync(kFull, slot);
+            if (slot >= 0 && lane == __ffs(same_slot) - 1)
+                atomicAdd(a.cov + slot, a.weight * __popc(same_slot));
+            // bam.py:136: one shared-memory atomic per distinct read length in the warp
+            const unsigned same_len = __match_any_sync(kFull, len);
+            if (len >= 0 && lane == __ffs(same_len) - 1) {
+                if (len < kLenHist) atomicAdd(&s_len[len], (unsigned)__popc(same_len));
+                else atomicAdd(a.len_counts + len, (unsigned long long)((long long)a.weight * __popc(same_len)));
+            }
         }
     }
     // bam.py:61,73-91,137: categories RT_ST_QCFAIL (slot 1) .. RT_ST_BADREF (slot 8), minus OOB

@@ -210,7 +210,7 @@ def metagene_case(seed=1003):
     from ribotricer.orf import ORF
 
     rng = np.random.default_rng(seed)
-    contigs = [("mA", 60000), ("mB", 45000)]
+    contigs = [("mA", 60000), ("mB", 60000)]
     header = ("ORF_ID\tORF_type\ttranscript_id\ttranscript_type\tgene_id\tgene_name\t"
               "gene_type\tchrom\tstrand\tstart_codon\tcoordinate")
     lines, orfs = [], []
