@@ -52,6 +52,7 @@ struct rt_ctx {
     // read-length table
     int32_t* d_len_table = nullptr;
     bool have_len_table = false;
+    int len_base = 20;   // first of the 16 read lengths K1 counts in registers
 
     // index
     int64_t n_orf = 0;
@@ -241,6 +242,12 @@ int rt_set_length_table(rt_ctx* ctx, const int32_t* h_len_table) {
                         h_len_table[i], ctx->pad);
     RT_CUDA(ctx, cudaMemcpy(ctx->d_len_table, h_len_table, sizeof(int32_t) * RT_LEN_TABLE, cudaMemcpyHostToDevice));
     ctx->have_len_table = true;
+    ctx->len_base = 20;
+    for (int i = 0; i < RT_LEN_TABLE; ++i)
+        if (h_len_table[i] >= 0) {
+            ctx->len_base = i;
+            break;
+        }
     return RT_OK;
 }
 
@@ -274,6 +281,7 @@ int rt_bin_reads(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* d_ref_id
     a.n = n;
     a.protocol = protocol;
     a.weight = weight;
+    a.len_base = ctx->len_base;
     a.len_table = ctx->d_len_table;
     a.contig_base = ctx->d_contig_base;
     a.contig_len = ctx->d_contig_len;

@@ -398,7 +398,7 @@ score_orfs_kernel(const ScoreArgs args) {
 // ORFs longer than kPackMaxNt take a whole warp each (LPO = 32) and are started first.
 // An ORF that turns out to hold a count >= 2^kBigShift is appended to the fallback queue and
 // redone by the generic kernel (64-bit sums).
-constexpr int kPackMaxNt = 3069;      // <= 1023 codons per frame: 10-bit packed fields never overflow
+constexpr int kPackMaxNt = 3045;      // <= 127 rounds of 8 lanes: the 7-bit per-lane fields never overflow
 constexpr int kShortLPO = 8;          // lanes per short ORF
 constexpr int kLongFlushRounds = 31;  // whole-warp ORFs: flush the 10-bit fields every 31 rounds
 constexpr int kDeferLanes = 12;       // general codons wait until this many lanes hold one
@@ -548,6 +548,52 @@ __device__ __forceinline__ void classify_codon(int a, int b, int c, FrameLane& f
     }
 }
 
+// Single-non-zero codons by table: m5 = non-zero mask of the lane's five values (bit j <-> value j).
+// Window f sees bits f..f+2; when exactly one of them is set the codon is (a,0,0), (0,b,0) or
+// (0,0,c) and maps to a constant unit vector, so it only bumps the 7-bit counter 3 f + kind of
+// the packed 64-bit accumulator.  One table lookup and one 64-bit add settle all three frames.
+__device__ __forceinline__ unsigned long long single_codon_lut_entry(unsigned m5) {
+    unsigned long long e = 0;
+    for (int f = 0; f < 3; ++f) {
+        const unsigned wm = (m5 >> f) & 7u;
+        if (wm == 1u) e += 1ull << (7 * (3 * f + 0));
+        else if (wm == 2u) e += 1ull << (7 * (3 * f + 1));
+        else if (wm == 4u) e += 1ull << (7 * (3 * f + 2));
+    }
+    return e;
+}
+// A codon with at least two non-zero counts: uniform (K only) or general (parked for the fp64 pass).
+// acc2 packs 7-bit counters: 2 F = general, 2 F + 1 = uniform.
+template <int F>
+__device__ __forceinline__ void multi_codon(int a, int b, int c, unsigned long long& acc2, FrameLane& f, Deferred& d) {
+    if (a == b && b == c) {
+        acc2 += 1ull << (7 * (2 * F + 1));
+    } else {
+        acc2 += 1ull << (7 * (2 * F));
+        int& A = F == 0 ? d.A0 : F == 1 ? d.A1 : d.A2;
+        int& B = F == 0 ? d.B0 : F == 1 ? d.B1 : d.B2;
+        if (d.has & (1u << F)) unit_vector_add(A, B, f);   // slot taken: settle the older codon now
+        A = 2 * a - b - c;
+        B = b - c;
+        d.has |= 1u << F;
+    }
+}
+// 7-bit packed accumulators -> the 10-bit words the reductions use (w1 = na | nb<<10 | nc<<20, w2 = ng | nu<<10).
+__device__ __forceinline__ void unpack_acc(unsigned long long& acc1, unsigned long long& acc2, FrameLane& f0,
+                                           FrameLane& f1, FrameLane& f2) {
+    auto w1 = [&](int f) {
+        const unsigned x = (unsigned)(acc1 >> (21 * f));
+        return (x & 127u) | (((x >> 7) & 127u) << 10) | (((x >> 14) & 127u) << 20);
+    };
+    auto w2 = [&](int f) {
+        const unsigned x = (unsigned)(acc2 >> (14 * f));
+        return (x & 127u) | (((x >> 7) & 127u) << 10);
+    };
+    f0.w1 += w1(0); f1.w1 += w1(1); f2.w1 += w1(2);
+    f0.w2 += w2(0); f1.w2 += w2(1); f2.w2 += w2(2);
+    acc1 = acc2 = 0;
+}
+
 // Warp-uniform totals of one frame (whole-warp ORFs only).
 struct FrameTotals {
     int na = 0, nb = 0, nc = 0, ng = 0, nu = 0;
@@ -564,7 +610,8 @@ struct FrameTotals {
 };
 
 template <int LPO, bool Long>
-__device__ __forceinline__ void score_pack(const ScoreArgs& args, long long item0, long long item_end, int lane) {
+__device__ __forceinline__ void score_pack(const ScoreArgs& args, const unsigned long long* lut, long long item0,
+                                           long long item_end, int lane) {
     const int sl = lane % LPO;                     // lane within the group
     const int gb = lane - sl;                      // first lane of the group
     const int nbr = sl + 1 == LPO ? gb : lane + 1; // right-hand neighbour (wraps to the next round)
@@ -587,6 +634,7 @@ __device__ __forceinline__ void score_pack(const ScoreArgs& args, long long item
     cur.init();
 
     FrameLane f0, f1, f2;
+    unsigned long long acc1 = 0, acc2 = 0;        // 7-bit packed codon counters (see single_codon_lut_entry)
     Deferred dfr;
     FrameTotals t0, t1, t2;                       // Long only
     long long count64 = 0;                        // Long only
@@ -611,9 +659,15 @@ __device__ __forceinline__ void score_pack(const ScoreArgs& args, long long item
             ormask |= c0 | c1 | c2;
             if ((c0 | c1 | c2 | v3 | v4) != 0) {
                 if (p + 4 < L) {
-                    classify_codon<0>(c0, c1, c2, f0, dfr);
-                    classify_codon<1>(c1, c2, v3, f1, dfr);
-                    classify_codon<2>(c2, v3, v4, f2, dfr);
+                    const unsigned m5 = min((unsigned)c0, 1u) | (min((unsigned)c1, 1u) << 1) | (min((unsigned)c2, 1u) << 2) |
+                                        (min((unsigned)v3, 1u) << 3) | (min((unsigned)v4, 1u) << 4);
+                    acc1 += lut[m5];
+                    const unsigned multi = ((m5 & (m5 >> 1)) | (m5 & (m5 >> 2)) | ((m5 >> 1) & (m5 >> 2))) & 7u;
+                    if (multi) {
+                        if (multi & 1u) multi_codon<0>(c0, c1, c2, acc2, f0, dfr);
+                        if (multi & 2u) multi_codon<1>(c1, c2, v3, acc2, f1, dfr);
+                        if (multi & 4u) multi_codon<2>(c2, v3, v4, acc2, f2, dfr);
+                    }
                 } else {                                                        // ragged end (statistics.py:71)
                     if (p + 2 < L) classify_codon<0>(c0, c1, c2, f0, dfr);
                     if (p + 3 < L) classify_codon<1>(c1, c2, v3, f1, dfr);
@@ -622,6 +676,7 @@ __device__ __forceinline__ void score_pack(const ScoreArgs& args, long long item
         }
         if (__popc(__ballot_sync(kFull, dfr.has != 0)) >= kDeferLanes) flush_deferred(dfr, f0, f1, f2);
         if (Long && (r % kLongFlushRounds) == kLongFlushRounds - 1) {
+            unpack_acc(acc1, acc2, f0, f1, f2);
             t0.flush(f0); t1.flush(f1); t2.flush(f2);
             count64 += __reduce_add_sync(kFull, cnt32);
             cnt32 = 0;
@@ -629,6 +684,7 @@ __device__ __forceinline__ void score_pack(const ScoreArgs& args, long long item
         c0 = n0; c1 = n1; c2 = n2;
     }
     flush_deferred(dfr, f0, f1, f2);
+    unpack_acc(acc1, acc2, f0, f1, f2);
 
     // ---- reductions (all lanes converged) ----
     int na0, nb0, nc0, ng0, nu0, na1, nb1, nc1, ng1, nu1, na2, nb2, nc2, ng2, nu2;
@@ -739,6 +795,9 @@ template <int LPO>
 __global__ void __launch_bounds__(kScoreWarps * 32, 4)
 score_orfs_packed_kernel(const ScoreArgs args) {
     constexpr int G = 32 / LPO;
+    __shared__ unsigned long long s_lut[32];
+    if (threadIdx.x < 32) s_lut[threadIdx.x] = single_codon_lut_entry(threadIdx.x);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long n_short = args.n_list - args.n_long;
     const long long n_work = args.n_long + (n_short + G - 1) / G;
@@ -748,9 +807,9 @@ score_orfs_packed_kernel(const ScoreArgs args) {
         w = __shfl_sync(kFull, w, 0);
         if ((long long)w >= n_work) break;
         if ((long long)w < args.n_long) {
-            score_pack<32, true>(args, (long long)w, (long long)w + 1, lane);
+            score_pack<32, true>(args, s_lut, (long long)w, (long long)w + 1, lane);
         } else {
-            score_pack<LPO, false>(args, args.n_long + ((long long)w - args.n_long) * G, args.n_list, lane);
+            score_pack<LPO, false>(args, s_lut, args.n_long + ((long long)w - args.n_long) * G, args.n_list, lane);
         }
     }
 }
@@ -807,6 +866,7 @@ struct BinArgs {
     long long n;
     int protocol;
     int weight;                    // +1 bin, -1 un-bin
+    int len_base;                  // lengths [len_base, len_base + 16) are counted in registers
     const int32_t* len_table;      // RT_LEN_TABLE
     const long long* contig_base;  // n_contig
     const long long* contig_len;   // n_contig
@@ -845,6 +905,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
     const long long block_base = (long long)blockIdx.x * (kBinThreads * kBinReadsPerThread);
     // per-thread 4-bit counters of categories RT_ST_QCFAIL..RT_ST_BADREF (<= 8 reads per thread)
     unsigned packed = 0;
+    unsigned long long len_packed = 0;
     constexpr int kBatch = 4;     // reads per thread whose columns are in flight together
 #pragma unroll 1
     for (int it0 = 0; it0 < kBinReadsPerThread; it0 += kBatch) {
@@ -899,17 +960,36 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
                 }
                 if (cat) packed += 1u << (4 * (cat - 1));
             }
-            // detect_orfs.py:82: one atomic per distinct slot in the warp (duplicated 5' ends are the
-            // rule in Ribo-seq, and adjacent in a coordinate-sorted BAM)
-            const unsigned same_slot = __match_any_sync(kFull, slot);
-            if (slot >= 0 && lane == __ffs(same_slot) - 1)
-                atomicAdd(a.cov + slot, a.weight * __popc(same_slot));
-            // bam.py:136: one shared-memory atomic per distinct read length in the warp
-            const unsigned same_len = __match_any_sync(kFull, len);
-            if (len >= 0 && lane == __ffs(same_len) - 1) {
-                if (len < kLenHist) atomicAdd(&s_len[len], (unsigned)__popc(same_len));
-                else atomicAdd(a.len_counts + len, (unsigned long long)((long long)a.weight * __popc(same_len)));
+            // detect_orfs.py:82: duplicated 5' ends are the rule in Ribo-seq and adjacent in a
+            // coordinate-sorted BAM: the first lane of every run of equal slots adds the run length
+            const long long prev = __shfl_up_sync(kFull, slot, 1);
+            const bool head = lane == 0 || slot != prev;
+            const unsigned heads = __ballot_sync(kFull, head);
+            if (head && slot >= 0) {
+                const unsigned after = lane == 31 ? 0u : heads >> (lane + 1);
+                const int run = after ? __ffs(after) : 32 - lane;
+                atomicAdd(a.cov + slot, a.weight * run);
             }
+            // bam.py:136: per-thread 4-bit counters for the 16 lengths from len_base on
+            if (len >= 0) {
+                const unsigned d = (unsigned)(len - a.len_base);
+                if (d < 16u) len_packed += 1ull << (4 * d);
+                else if (len < kLenHist) atomicAdd(&s_len[len], 1u);
+                else atomicAdd(a.len_counts + len, (unsigned long long)(long long)a.weight);
+            }
+        }
+    }
+    {   // flush the register length counters: one REDUX per length, one shared atomic per lane
+        unsigned mine_len = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const unsigned v = __reduce_add_sync(kFull, (unsigned)(len_packed >> (4 * k)) & 15u);
+            if (lane == k) mine_len = v;
+        }
+        const int l = a.len_base + lane;
+        if (lane < 16 && mine_len && l >= 0) {
+            if (l < kLenHist) atomicAdd(&s_len[l], mine_len);
+            else atomicAdd(a.len_counts + l, (unsigned long long)((long long)a.weight * mine_len));
         }
     }
     // bam.py:61,73-91,137: categories RT_ST_QCFAIL (slot 1) .. RT_ST_BADREF (slot 8), minus OOB
