@@ -241,3 +241,85 @@ def test_errors_are_loud(engine):
     cov = engine.new_coverage()
     with pytest.raises(_lib.RtError):   # ORF range outside the index
         engine.score_host(cov, 0, 5)
+
+
+def test_full_config1_against_oracle(engine):
+    """BASELINE.json configs[0] at full size (yeast R64 scale: 100 k ORFs, 10 M reads): every ORF
+    against the C oracle (seconds on the CPU)."""
+    CO = _oracle()
+    from ribotricer_b200 import synth
+
+    cfg = synth.config("C1")
+    idx = synth.make_index(cfg)
+    dreads = synth.make_reads(cfg, idx, device=engine.device)
+    reads = synth.reads_to_numpy(dreads)
+    pad = 256
+    base, plane = _setup(engine, idx.contig_names, idx.contig_len, idx.as_dict(), synth.TRUE_OFFSETS, pad=pad)
+    cov = engine.new_coverage()
+    stats, lens = engine.bin_reads_host(cov, reads, "forward", sorted_hint=True)
+    ref_cov, ref_stats, ref_len = CO.bin_reads(reads, 0, CO.make_len_table(synth.TRUE_OFFSETS), base, idx.contig_len,
+                                               pad, plane)
+    assert stats == ref_stats and (lens == ref_len).all()
+    assert (cov.cpu().numpy() == ref_cov).all()
+    got = engine.score_host(cov, diagnostics=True)
+    ref = CO.score(idx.as_dict(), ref_cov, base, idx.contig_len, pad, plane, DEFAULT_PARAMS)
+    tie = CO.tie_mask(ref["frame_K"], ref["frame_s"])
+    n_tie, n_near = compare_scores(got, ref, tie, what="C1: ")
+    assert (got["frame_K"] == ref["frame_K"]).all()
+    assert n_tie < 0.02 * idx.n_orf
+    assert np.abs(got["score"] - ref["score"]).max() < 1e-11
+
+
+def test_full_config2_properties(engine):
+    """BASELINE.json configs[1] at full size (2.5 M ORFs, 100 M reads, 24.7 GB coverage) through
+    size-independent properties: un-binning returns the planes to zero; binning the library
+    twice doubles every count and leaves score and valid codons unchanged (the phase score is
+    scale invariant); shard results concatenate to the full result; a 20 k-ORF sample agrees
+    with the oracle run on the gathered profiles."""
+    CO = _oracle()
+    from ribotricer_b200 import synth
+
+    t = engine.torch
+    cfg = synth.config("C2")
+    idx = synth.make_index(cfg)
+    dreads = synth.make_reads(cfg, idx, device=engine.device)
+    engine.set_genome(idx.contig_names, idx.contig_len)
+    engine.set_length_table(synth.TRUE_OFFSETS, None)
+    engine.set_index(**idx.as_dict())
+    cov = engine.new_coverage()
+    st, lc = engine.new_bin_accumulators()
+    engine.bin_reads_device(cov, dreads, "forward", st, lc, sorted_hint=True)
+    one = engine.score_host(cov)
+    stats1 = st.cpu().numpy().copy()
+    assert stats1[0] == cfg.n_reads and stats1[6] + stats1[1:6].sum() == cfg.n_reads
+    assert int(cov.sum(dtype=t.int64).item()) == int(stats1[6] - stats1[7])      # every valid in-range read is one count
+    engine.bin_reads_device(cov, dreads, "forward", st, lc, sorted_hint=True)
+    two = engine.score_host(cov)
+    assert (two["count"] == 2 * one["count"]).all() and (two["min_codon"] == 2 * one["min_codon"]).all()
+    assert (two["valid"] == one["valid"]).all() and (two["length"] == one["length"]).all()
+    assert np.abs(two["score"] - one["score"]).max() <= 1e-12
+    assert (two["status"] == one["status"])[np.abs(one["score"] - 0.428571428571) > 1e-9].all()
+    engine.bin_reads_device(cov, dreads, "forward", st, lc, sorted_hint=True, weight=-1)
+    engine.bin_reads_device(cov, dreads, "forward", st, lc, sorted_hint=True, weight=-1)
+    assert int(cov.abs().max().item()) == 0 and int(st.abs().max().item()) == 0 and int(lc.abs().max().item()) == 0
+    # shards
+    engine.bin_reads_device(cov, dreads, "forward", st, lc, sorted_hint=True)
+    bounds = engine.shard_bounds(8)
+    assert bounds[0] == 0 and bounds[-1] == idx.n_orf and (np.diff(bounds) > 0).all()
+    parts = [engine.score_host(cov, int(bounds[i]), int(bounds[i + 1])) for i in range(8)]
+    for k in one:
+        assert np.array_equal(np.concatenate([p[k] for p in parts]), one[k], equal_nan=True), k
+    # sample against the oracle, through the gathered profiles (bit-exact integers, score 1e-9)
+    rng = np.random.default_rng(11)
+    sel = np.sort(np.concatenate([rng.choice(idx.n_orf, 20000, replace=False), np.argsort(idx.orf_len)[-20:]]))
+    sel = np.unique(sel)
+    ptr, prof = engine.gather_profiles(cov, sel, one["length"][sel])
+    for j in range(0, len(sel), 7):
+        o = sel[j]
+        p = prof[ptr[j]:ptr[j + 1]]
+        assert len(p) == idx.orf_len[o] and int(p.sum()) == one["count"][o]
+        K, s3 = CO.frame_spectra(p)
+        s, v = CO.phasescore(p)
+        assert abs(s - one["score"][o]) <= SCORE_TOL
+        if not CO.tie_mask(K[None, :], s3[None, :])[0]:
+            assert v == one["valid"][o]
