@@ -170,6 +170,36 @@ int rt_gather_profiles(rt_ctx* ctx, const int32_t* d_cov, int64_t n_sel, const i
  */
 int rt_phasescore_values(rt_ctx* ctx, const double* h_values, int64_t n, double* h_score, int32_t* h_valid);
 
+/*
+ * ---- native host I/O (no GPU involved; SURVEY.md 8(f) "next #3") -------------------------------
+ * rt_index_load parses a prepare-orfs index (prepare_orfs.py:370-404) with the rules of
+ * ORF.from_string (orf.py:121-182): 11 tab-separated columns (otherwise RT_ESTATE and the
+ * reference's "unexpected number of columns" message in rt_io_last_error), intervals sorted by
+ * start (orf.py:100), leading rows containing "annotated" counted (detect_orfs.py:104-118).
+ * rt_tsv_* write {prefix}_translating_ORFs.tsv rows exactly as detect_orfs.py:304-323 formats them.
+ */
+typedef struct rt_index rt_index;
+typedef struct rt_tsv rt_tsv;
+const char* rt_io_last_error(void);
+int rt_index_load(const char* path, rt_index** out);
+void rt_index_free(rt_index* ix);
+int64_t rt_index_n_orf(const rt_index* ix);
+int64_t rt_index_n_exon(const rt_index* ix);
+int64_t rt_index_n_annotated_prefix(const rt_index* ix);
+int rt_index_n_chrom(const rt_index* ix);                    /* distinct chrom names, first-appearance order */
+const char* rt_index_chrom_name(const rt_index* ix, int i);
+/* copy the columns out (any pointer may be NULL): exon_ptr[n+1], exon_start/end[E], orf_chrom[n], orf_strand[n] */
+int rt_index_copy(const rt_index* ix, int64_t* exon_ptr, int32_t* exon_start, int32_t* exon_end,
+                  int32_t* orf_chrom, uint8_t* orf_strand);
+/* raw text of column k (1 = ORF_type .. 9 = start_codon) of row `orf`; not NUL terminated */
+const char* rt_index_field(const rt_index* ix, int64_t orf, int k, int* len);
+int rt_tsv_open(const char* path, int write_header, rt_tsv** out);
+int rt_tsv_write(rt_tsv* t, const rt_index* ix, int64_t n_sel, const int64_t* orf_ids, int64_t orf_lo,
+                 const double* score, const int32_t* valid, const int64_t* count, const int32_t* length,
+                 const uint8_t* status, const int64_t* prof_ptr, const int32_t* prof);
+int rt_tsv_close(rt_tsv* t);
+int rt_repr_double(double x, char* buf, int cap);            /* Python float repr (shortest round trip) */
+
 /* number of kernel launches issued through this ctx so far (bench.py's gpu_launches) */
 int64_t rt_launch_count(const rt_ctx* ctx);
 

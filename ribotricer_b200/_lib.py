@@ -23,7 +23,10 @@ EXPORTS = (
     "rt_set_genome", "rt_plane_elems", "rt_get_contig_base", "rt_set_length_table",
     "rt_bin_reads", "rt_bin_reads_host", "rt_clear_coverage", "rt_set_index", "rt_index_orfs",
     "rt_index_score_bytes", "rt_index_total_nt", "rt_shard_bounds", "rt_score", "rt_score_host",
-    "rt_gather_profiles", "rt_launch_count", "rt_phasescore_values",
+    "rt_gather_profiles", "rt_launch_count", "rt_phasescore_values", "rt_io_last_error", "rt_index_load",
+    "rt_index_free", "rt_index_n_orf", "rt_index_n_exon", "rt_index_n_annotated_prefix", "rt_index_n_chrom",
+    "rt_index_chrom_name", "rt_index_copy", "rt_index_field", "rt_tsv_open", "rt_tsv_write", "rt_tsv_close",
+    "rt_repr_double",
 )
 
 
@@ -84,6 +87,23 @@ def load():
     lib.rt_gather_profiles.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.rt_phasescore_values.argtypes = [vp, vp, i64, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     lib.rt_launch_count.argtypes = [vp]
+    lib.rt_io_last_error.restype = C.c_char_p
+    lib.rt_index_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.rt_index_free.argtypes = [vp]
+    lib.rt_index_free.restype = None
+    for name in ("rt_index_n_orf", "rt_index_n_exon", "rt_index_n_annotated_prefix"):
+        getattr(lib, name).argtypes = [vp]
+        getattr(lib, name).restype = i64
+    lib.rt_index_n_chrom.argtypes = [vp]
+    lib.rt_index_chrom_name.argtypes = [vp, i32]
+    lib.rt_index_chrom_name.restype = C.c_char_p
+    lib.rt_index_copy.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.rt_index_field.argtypes = [vp, i64, i32, C.POINTER(C.c_int)]
+    lib.rt_index_field.restype = vp
+    lib.rt_tsv_open.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
+    lib.rt_tsv_write.argtypes = [vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.rt_tsv_close.argtypes = [vp]
+    lib.rt_repr_double.argtypes = [C.c_double, C.c_char_p, i32]
     lib.rt_launch_count.restype = i64
     if lib.rt_abi_version() != 1:
         raise RtError(f"ABI mismatch: library reports {lib.rt_abi_version()}, binding expects 1")

@@ -1,0 +1,308 @@
+// rt_host_io.cpp -- native host I/O around the GPU path (SURVEY.md 8(f) "next #3"):
+//   * candidate-ORF index loader: ORF.from_string rules (orf.py:121-182), interval sort (orf.py:100),
+//     annotated prefix (detect_orfs.py:104-118) -> CSR arrays, without one Python object per row;
+//   * {prefix}_translating_ORFs.tsv writer: rows formatted exactly as detect_orfs.py:304-323 prints
+//     them (np.float64 / Python float shortest repr, str(list) profile).
+// No GPU is involved; these entry points also work on a CPU-only box.
+#include <algorithm>
+#include <charconv>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ribotricer_b200.h"
+
+struct rt_index {
+    std::string text;                    // the whole file; fields point into it
+    std::vector<int64_t> exon_ptr{0};
+    std::vector<int32_t> exon_start, exon_end;
+    std::vector<int32_t> orf_chrom;      // index into chrom_names
+    std::vector<uint8_t> orf_strand;     // 0 '+', 1 '-', 2 anything else
+    std::vector<uint32_t> field_off;     // 10 per ORF: offsets of fields 1..9 and of the end of field 9 ... see field()
+    std::vector<uint32_t> field_len;     // 9 per ORF: lengths of fields 1..9
+    std::vector<uint64_t> line_field;    // per ORF: offset of field 1 (64-bit, files > 4 GB)
+    std::vector<std::string> chrom_names;
+    int64_t n_annotated_prefix = 0;
+    std::string error;
+};
+
+struct rt_tsv {
+    FILE* fh = nullptr;
+    std::string buf;
+};
+
+namespace {
+
+thread_local std::string g_io_error;
+
+// Shortest round-trip repr of a double in Python's float.__repr__ / numpy float64.__str__ style.
+void append_repr(std::string& out, double x) {
+    if (x != x) { out += "nan"; return; }
+    if (x == 1.0 / 0.0) { out += "inf"; return; }
+    if (x == -1.0 / 0.0) { out += "-inf"; return; }
+    char tmp[64];
+    auto res = std::to_chars(tmp, tmp + sizeof tmp, x, std::chars_format::scientific);   // d[.ddd]e[+-]XX, shortest
+    const char* p = tmp;
+    if (*p == '-') { out += '-'; ++p; }
+    const char* e = std::find(p, (const char*)res.ptr, 'e');
+    std::string digits;
+    for (const char* q = p; q < e; ++q)
+        if (*q != '.') digits += *q;
+    int exp10 = 0;
+    std::from_chars(e + 1 + (e[1] == '+' ? 1 : 0), res.ptr, exp10);
+    const int nd = (int)digits.size();
+    if (exp10 < -4 || exp10 >= 16) {            // repr switches to exponent notation here
+        out += digits[0];
+        if (nd > 1) { out += '.'; out.append(digits, 1, std::string::npos); }
+        out += 'e';
+        out += exp10 < 0 ? '-' : '+';
+        const int a = exp10 < 0 ? -exp10 : exp10;
+        if (a < 10) out += '0';
+        out += std::to_string(a);
+    } else if (exp10 < 0) {
+        out += "0.";
+        out.append((size_t)(-exp10 - 1), '0');
+        out += digits;
+    } else if (nd <= exp10 + 1) {
+        out += digits;
+        out.append((size_t)(exp10 + 1 - nd), '0');
+        out += ".0";
+    } else {
+        out.append(digits, 0, (size_t)exp10 + 1);
+        out += '.';
+        out.append(digits, (size_t)exp10 + 1, std::string::npos);
+    }
+}
+
+void append_int(std::string& out, long long v) {
+    char tmp[24];
+    auto res = std::to_chars(tmp, tmp + sizeof tmp, v);
+    out.append(tmp, res.ptr);
+}
+
+bool parse_int(const char*& p, const char* end, long long& v) {   // Python int(): optional blanks and sign
+    while (p < end && (*p == ' ')) ++p;
+    bool neg = false;
+    if (p < end && (*p == '-' || *p == '+')) { neg = *p == '-'; ++p; }
+    if (p >= end || *p < '0' || *p > '9') return false;
+    long long x = 0;
+    while (p < end && *p >= '0' && *p <= '9') { x = x * 10 + (*p - '0'); ++p; }
+    while (p < end && (*p == ' ' || *p == '\r' || *p == '\n')) ++p;
+    v = neg ? -x : x;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rt_io_last_error(void) { return g_io_error.c_str(); }
+
+int rt_index_load(const char* path, rt_index** out) {
+    if (!path || !out) return RT_EINVAL;
+    *out = nullptr;
+    FILE* fh = fopen(path, "rb");
+    if (!fh) { g_io_error = std::string("cannot open ") + path; return RT_EINVAL; }
+    rt_index* ix = new rt_index();
+    fseek(fh, 0, SEEK_END);
+    const long size = ftell(fh);
+    fseek(fh, 0, SEEK_SET);
+    ix->text.resize((size_t)size);
+    if (size > 0 && fread(&ix->text[0], 1, (size_t)size, fh) != (size_t)size) {
+        fclose(fh); delete ix; g_io_error = "short read"; return RT_EINVAL;
+    }
+    fclose(fh);
+    const char* base = ix->text.data();
+    const char* end = base + ix->text.size();
+    const char* p = (const char*)memchr(base, '\n', ix->text.size());   // skip the header (detect_orfs.py:273)
+    p = p ? p + 1 : end;
+    std::unordered_map<std::string, int> chrom_id;
+    bool in_prefix = true;
+    std::vector<std::pair<long long, long long>> ivs;
+    int64_t row = 0;
+    while (p < end) {
+        const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* line_end = eol ? eol : end;
+        // split on tabs: exactly 11 fields (orf.py:144-151)
+        const char* f[12];
+        int nf = 0;
+        f[0] = p;
+        for (const char* q = p; q < line_end && nf < 11; ++q)
+            if (*q == '\t') f[++nf] = q + 1;
+        int tabs = 0;
+        for (const char* q = p; q < line_end; ++q) tabs += *q == '\t';
+        if (tabs != 10) {
+            g_io_error = "Error: unexpected number of columns found for index file\nplease run ribotricer prepare-orfs to regenerate";
+            delete ix;
+            return RT_ESTATE;
+        }
+        f[11] = line_end + 1;
+        if (in_prefix) {   // detect_orfs.py:104-105 tests the whole line for the substring
+            static const char kAnn[] = "annotated";
+            if (std::search(p, line_end, kAnn, kAnn + 9) != line_end) ix->n_annotated_prefix++;
+            else in_prefix = false;
+        }
+        // coordinate = start-end[,start-end...] (orf.py:166-170)
+        ivs.clear();
+        const char* c = f[10];
+        while (c < line_end) {
+            const char* grp_end = (const char*)memchr(c, ',', (size_t)(line_end - c));
+            if (!grp_end) grp_end = line_end;
+            const char* dash = (const char*)memchr(c + 1, '-', (size_t)(grp_end - c - 1));   // a leading '-' is a sign
+            long long s = 0, e = 0;
+            const char* q = c;
+            bool ok = dash != nullptr && parse_int(q, dash, s) && q == dash;
+            q = dash ? dash + 1 : c;
+            ok = ok && parse_int(q, grp_end, e) && q == grp_end;
+            if (!ok || s < INT32_MIN || s > INT32_MAX || e < INT32_MIN || e > INT32_MAX) {
+                g_io_error = "bad coordinate in index row " + std::to_string(row + 1);
+                delete ix;
+                return RT_EINVAL;
+            }
+            ivs.emplace_back(s, e);
+            c = grp_end + 1;
+        }
+        std::stable_sort(ivs.begin(), ivs.end(), [](const auto& a, const auto& b) { return a.first < b.first; });   // orf.py:100
+        for (auto& iv : ivs) {
+            ix->exon_start.push_back((int32_t)iv.first);
+            ix->exon_end.push_back((int32_t)iv.second);
+        }
+        ix->exon_ptr.push_back((int64_t)ix->exon_start.size());
+        ix->line_field.push_back((uint64_t)(f[1] - base));
+        for (int k = 1; k <= 9; ++k) ix->field_len.push_back((uint32_t)(f[k + 1] - 1 - f[k]));
+        std::string chrom(f[7], f[8] - 1);
+        auto it = chrom_id.find(chrom);
+        if (it == chrom_id.end()) {
+            it = chrom_id.emplace(chrom, (int)ix->chrom_names.size()).first;
+            ix->chrom_names.push_back(chrom);
+        }
+        ix->orf_chrom.push_back(it->second);
+        const size_t slen = (size_t)(f[9] - 1 - f[8]);
+        ix->orf_strand.push_back(slen == 1 && *f[8] == '+' ? 0 : slen == 1 && *f[8] == '-' ? 1 : 2);
+        ++row;
+        p = line_end + 1;
+    }
+    *out = ix;
+    return RT_OK;
+}
+
+void rt_index_free(rt_index* ix) { delete ix; }
+int64_t rt_index_n_orf(const rt_index* ix) { return ix ? (int64_t)ix->orf_chrom.size() : 0; }
+int64_t rt_index_n_exon(const rt_index* ix) { return ix ? (int64_t)ix->exon_start.size() : 0; }
+int64_t rt_index_n_annotated_prefix(const rt_index* ix) { return ix ? ix->n_annotated_prefix : 0; }
+int rt_index_n_chrom(const rt_index* ix) { return ix ? (int)ix->chrom_names.size() : 0; }
+const char* rt_index_chrom_name(const rt_index* ix, int i) {
+    return ix && i >= 0 && i < (int)ix->chrom_names.size() ? ix->chrom_names[i].c_str() : nullptr;
+}
+
+int rt_index_copy(const rt_index* ix, int64_t* exon_ptr, int32_t* exon_start, int32_t* exon_end, int32_t* orf_chrom,
+                  uint8_t* orf_strand) {
+    if (!ix) return RT_EINVAL;
+    if (exon_ptr) std::copy(ix->exon_ptr.begin(), ix->exon_ptr.end(), exon_ptr);
+    if (exon_start) std::copy(ix->exon_start.begin(), ix->exon_start.end(), exon_start);
+    if (exon_end) std::copy(ix->exon_end.begin(), ix->exon_end.end(), exon_end);
+    if (orf_chrom) std::copy(ix->orf_chrom.begin(), ix->orf_chrom.end(), orf_chrom);
+    if (orf_strand) std::copy(ix->orf_strand.begin(), ix->orf_strand.end(), orf_strand);
+    return RT_OK;
+}
+
+// Field k (1..9: ORF_type .. start_codon) of row `orf`; not NUL terminated.
+const char* rt_index_field(const rt_index* ix, int64_t orf, int k, int* len) {
+    if (!ix || orf < 0 || orf >= (int64_t)ix->orf_chrom.size() || k < 1 || k > 9) return nullptr;
+    uint64_t off = ix->line_field[orf];
+    for (int j = 1; j < k; ++j) off += ix->field_len[9 * orf + (j - 1)] + 1;
+    if (len) *len = (int)ix->field_len[9 * orf + (k - 1)];
+    return ix->text.data() + off;
+}
+
+int rt_tsv_open(const char* path, int write_header, rt_tsv** out) {
+    if (!path || !out) return RT_EINVAL;
+    FILE* fh = fopen(path, "wb");
+    if (!fh) { g_io_error = std::string("cannot open ") + path; return RT_EINVAL; }
+    rt_tsv* t = new rt_tsv();
+    t->fh = fh;
+    if (write_header)   // detect_orfs.py:241-260
+        fputs("ORF_ID\tORF_type\tstatus\tphase_score\tread_count\tlength\tvalid_codons\tvalid_codons_ratio\t"
+              "read_density\ttranscript_id\ttranscript_type\tgene_id\tgene_name\tgene_type\tchrom\tstrand\t"
+              "start_codon\tprofile\n", fh);
+    *out = t;
+    return RT_OK;
+}
+
+// Rows of the selected ORFs (absolute ids, ascending = index order).  Result columns are indexed by
+// (orf - orf_lo); prof_ptr[i]..prof_ptr[i+1] delimit the profile of orf_ids[i] in `prof`.
+int rt_tsv_write(rt_tsv* t, const rt_index* ix, int64_t n_sel, const int64_t* orf_ids, int64_t orf_lo,
+                 const double* score, const int32_t* valid, const int64_t* count, const int32_t* length,
+                 const uint8_t* status, const int64_t* prof_ptr, const int32_t* prof) {
+    if (!t || !ix || n_sel < 0 || (n_sel && (!orf_ids || !score || !valid || !count || !length || !status || !prof_ptr || !prof)))
+        return RT_EINVAL;
+    std::string& b = t->buf;
+    for (int64_t i = 0; i < n_sel; ++i) {
+        const int64_t o = orf_ids[i], k = o - orf_lo;
+        if (o < 0 || o >= (int64_t)ix->orf_chrom.size() || k < 0) return RT_EINVAL;
+        int flen[10];
+        const char* f[10];
+        for (int j = 1; j <= 9; ++j) f[j] = rt_index_field(ix, o, j, &flen[j]);
+        const int64_t e0 = ix->exon_ptr[o], e1 = ix->exon_ptr[o + 1];
+        long long L = 0;
+        for (int64_t e = e0; e < e1; ++e) L += (long long)ix->exon_end[e] - ix->exon_start[e] + 1;
+        // oid = tid_start_end_len (orf.py:101-103)
+        b.append(f[2], flen[2]); b += '_';
+        append_int(b, e1 > e0 ? ix->exon_start[e0] : 0); b += '_';
+        append_int(b, e1 > e0 ? ix->exon_end[e1 - 1] : 0); b += '_';
+        append_int(b, L); b += '\t';
+        b.append(f[1], flen[1]); b += '\t';
+        b += status[k] ? "translating" : "nontranslating"; b += '\t';
+        append_repr(b, score[k]); b += '\t';
+        append_int(b, count[k]); b += '\t';
+        append_int(b, length[k]); b += '\t';
+        append_int(b, valid[k]); b += '\t';
+        const long long n_codons = length[k] / 3 > 1 ? length[k] / 3 : 1;        // detect_orfs.py:281
+        append_repr(b, (double)valid[k] / (double)n_codons); b += '\t';           // :285
+        append_repr(b, (double)count[k] / (double)n_codons); b += '\t';           // :287
+        b.append(f[2], flen[2]); b += '\t';
+        b.append(f[3], flen[3]); b += '\t';
+        b.append(f[4], flen[4]); b += '\t';
+        b.append(f[5], flen[5]); b += '\t';
+        b.append(f[6], flen[6]); b += '\t';
+        b.append(f[7], flen[7]); b += '\t';
+        b.append(f[8], flen[8]); b += '\t';
+        b.append(f[9], flen[9]); b += '\t';
+        b += '[';
+        for (int64_t q = prof_ptr[i]; q < prof_ptr[i + 1]; ++q) {
+            if (q > prof_ptr[i]) b += ", ";
+            append_int(b, prof[q]);
+        }
+        b += "]\n";
+        if (b.size() > (1u << 22)) {
+            if (fwrite(b.data(), 1, b.size(), t->fh) != b.size()) return RT_EINVAL;
+            b.clear();
+        }
+    }
+    if (!b.empty()) {
+        if (fwrite(b.data(), 1, b.size(), t->fh) != b.size()) return RT_EINVAL;
+        b.clear();
+    }
+    return RT_OK;
+}
+
+int rt_tsv_close(rt_tsv* t) {
+    if (!t) return RT_EINVAL;
+    const int rc = fclose(t->fh);
+    delete t;
+    return rc == 0 ? RT_OK : RT_EINVAL;
+}
+
+// For tests: Python-style repr of a double into buf (NUL terminated).
+int rt_repr_double(double x, char* buf, int cap) {
+    std::string s;
+    append_repr(s, x);
+    if ((int)s.size() + 1 > cap) return RT_EINVAL;
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+}  // extern "C"

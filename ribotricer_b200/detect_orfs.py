@@ -24,7 +24,7 @@ from .bam import Alignments, split_bam
 from .const import (CUTOFF, MINIMUM_DENSITY_OVER_ORF, MINIMUM_READS_PER_CODON, MINIMUM_VALID_CODONS,
                     MINIMUM_VALID_CODONS_RATIO)
 from .engine import Engine, ScoreParams
-from .index import ORF, PackedIndex, parse_index
+from .index import ORF, NativeIndex, PackedIndex, parse_index
 
 _ENGINE: Engine | None = None
 _INDEX_CACHE: dict = {}
@@ -52,7 +52,7 @@ def load_index(path: str) -> PackedIndex:
     key = (os.path.abspath(path), st.st_mtime_ns, st.st_size)
     if key not in _INDEX_CACHE:
         _INDEX_CACHE.clear()
-        _INDEX_CACHE[key] = parse_index(path)
+        _INDEX_CACHE[key] = NativeIndex(path)     # native loader; parse_index() is the Python statement of the rules
     return _INDEX_CACHE[key]
 
 
@@ -195,28 +195,52 @@ def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: i
     n_codons = np.maximum(1, length // 3)                         # detect_orfs.py:281
     ratio = res["valid"].astype(np.float64) / n_codons           # :285
     density = res["count"].astype(np.float64) / n_codons         # :287
-    with open(path, "w") as out:
+    native = isinstance(idx, NativeIndex)
+    if native:
+        import ctypes as C
+
+        lib = eng.lib
+        handle = C.c_void_p()
+        if lib.rt_tsv_open(str(path).encode(), int(write_header), C.byref(handle)) != 0:
+            raise OSError(lib.rt_io_last_error().decode())
+        cols = {k: np.ascontiguousarray(res[k]) for k in ("score", "valid", "count", "length", "status")}
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    else:
+        out = open(path, "w")
         if write_header:
             out.write("\t".join(TSV_COLUMNS) + "\n")
+    try:
         at = 0
         while at < len(keep):
             # bounded chunks of reported ORFs so the profile buffer stays small
             csum = np.cumsum(length[keep[at:] - lo])
             n_take = max(1, int(np.searchsorted(csum, chunk_nt, side="right")))
-            sel = keep[at:at + n_take]
+            sel = np.ascontiguousarray(keep[at:at + n_take], np.int64)
             ptr, prof = eng.gather_profiles(merged.cov, sel, length[sel - lo])
-            rows = []
-            for j, o in enumerate(sel.tolist()):
-                k = o - lo
-                f = idx.fields[o]
-                rows.append("\t".join((
-                    idx.oid(o), f[0], "translating" if res["status"][k] else "nontranslating",
-                    str(res["score"][k]), str(int(res["count"][k])), str(int(length[k])),
-                    str(int(res["valid"][k])), repr(float(ratio[k])), str(density[k]),
-                    f[1], f[2], f[3], f[4], f[5], idx.chrom[o], idx.strand[o], f[6],
-                    str(prof[ptr[j]:ptr[j + 1]].tolist()))))
-            out.write("\n".join(rows) + "\n")
+            if native:
+                prof = np.ascontiguousarray(prof, np.int32)
+                rc = lib.rt_tsv_write(handle, idx.handle, len(sel), p(sel), int(lo), p(cols["score"]), p(cols["valid"]),
+                                      p(cols["count"]), p(cols["length"]), p(cols["status"]), p(ptr), p(prof))
+                if rc != 0:
+                    raise OSError(f"rt_tsv_write failed ({rc}): {lib.rt_io_last_error().decode()}")
+            else:
+                rows = []
+                for j, o in enumerate(sel.tolist()):
+                    k = o - lo
+                    f = idx.fields[o]
+                    rows.append("\t".join((
+                        idx.oid(o), f[0], "translating" if res["status"][k] else "nontranslating",
+                        str(res["score"][k]), str(int(res["count"][k])), str(int(length[k])),
+                        str(int(res["valid"][k])), repr(float(ratio[k])), str(density[k]),
+                        f[1], f[2], f[3], f[4], f[5], idx.chrom[o], idx.strand[o], f[6],
+                        str(prof[ptr[j]:ptr[j + 1]].tolist()))))
+                out.write("\n".join(rows) + "\n")
             at += n_take
+    finally:
+        if native:
+            lib.rt_tsv_close(handle)
+        else:
+            out.close()
 
 
 def export_wig(merged_alignments: MergedAlignments, prefix: str) -> None:

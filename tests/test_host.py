@@ -48,3 +48,103 @@ def test_index_parser_matches_reference_rules(tmp_path):
     cols = idx.device_columns({"chrI": 0})
     assert cols["orf_contig"].tolist() == [0, 0] and cols["orf_strand"].tolist() == [0, 1]
     assert idx.device_columns({})["orf_contig"].tolist() == [-1, -1]
+
+
+def test_native_index_loader_matches_python_rules(tmp_path, built):
+    """csrc/rt_host_io.cpp against the Python statement of orf.py:121-182 on the golden indexes
+    (shuffled interval order, unknown chromosomes) and on a synthetic 3,000-row index."""
+    import pytest
+
+    from helpers import load_golden
+    from ribotricer_b200 import synth
+    from ribotricer_b200.index import NativeIndex, parse_index
+
+    paths = []
+    for case in load_golden("pipeline_cases.json.gz")["cases"]:
+        p = tmp_path / f"{case['name']}.tsv"
+        p.write_text("\n".join(case["index"]) + "\n")
+        paths.append(str(p))
+    p = tmp_path / "synth.tsv"
+    synth.make_index(synth.config("tiny")).write_tsv(str(p))
+    paths.append(str(p))
+    for path in paths:
+        py, nat = parse_index(path), NativeIndex(path)
+        assert nat.n_orf == py.n_orf and nat.n_annotated_prefix == py.n_annotated_prefix
+        for k in ("exon_ptr", "exon_start", "exon_end"):
+            assert (getattr(nat, k) == getattr(py, k)).all(), k
+        assert nat.contig_table() == py.contig_table()
+        lut = {c: i for i, c in enumerate(py.contig_table()[:-1])}      # last chromosome unknown to the "BAM"
+        a, b = nat.device_columns(lut), py.device_columns(lut)
+        for k in a:
+            assert (a[k] == b[k]).all(), k
+        for o in list(range(0, py.n_orf, max(1, py.n_orf // 50))) + [py.n_orf - 1]:
+            assert nat.fields[o] == py.fields[o] and nat.chrom[o] == py.chrom[o] and nat.strand[o] == py.strand[o]
+            assert nat.oid(o) == py.oid(o)
+        assert (nat.lengths() == py.lengths()).all()
+    bad = tmp_path / "bad.tsv"
+    bad.write_text("h\na\tb\tc\n")
+    with pytest.raises(SystemExit) as exc:
+        NativeIndex(str(bad))
+    assert "unexpected number of columns" in str(exc.value)
+
+
+def test_native_tsv_writer_matches_reference_formatting(tmp_path, built):
+    """rt_tsv_write rows against the rows the reference wrote (golden TSV text): feeding the
+    writer the reference's own numbers must reproduce its text byte for byte (float repr, int/int
+    ratio, np.float64 density, list repr of the profile)."""
+    import ctypes as C
+
+    from helpers import load_golden
+    from ribotricer_b200 import _lib
+    from ribotricer_b200.index import NativeIndex
+
+    lib = _lib.load()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    for case in load_golden("pipeline_cases.json.gz")["cases"]:
+        path = tmp_path / f"{case['name']}.tsv"
+        path.write_text("\n".join(case["index"]) + "\n")
+        idx = NativeIndex(str(path))
+        for run in case["tsv"]:
+            ref_lines = run["text"].split("\n")
+            rows = [r.split("\t") for r in ref_lines[1:] if r]
+            # rows are in index order; oids can repeat, so match them sequentially
+            sel, o = [], 0
+            for r in rows:
+                while idx.oid(o) != r[0] or "\t".join(idx.fields[o][1:6]) != "\t".join(r[9:14]):
+                    o += 1
+                sel.append(o)
+                o += 1
+            sel = np.array(sel, np.int64)
+            n = idx.n_orf
+            score, valid = np.zeros(n), np.zeros(n, np.int32)
+            count, length, status = np.zeros(n, np.int64), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+            profs = []
+            for o, r in zip(sel, rows):
+                score[o], count[o], length[o], valid[o] = float(r[3]), int(r[4]), int(r[5]), int(r[6])
+                status[o] = r[2] == "translating"
+                profs.append(np.array(eval(r[17]), np.int32))
+            ptr = np.zeros(len(sel) + 1, np.int64)
+            np.cumsum([len(x) for x in profs], out=ptr[1:])
+            prof = np.concatenate(profs) if profs else np.zeros(0, np.int32)
+            out = tmp_path / "out.tsv"
+            h = C.c_void_p()
+            assert lib.rt_tsv_open(str(out).encode(), 1, C.byref(h)) == 0
+            assert lib.rt_tsv_write(h, idx.handle, len(sel), p(sel), 0, p(score), p(valid), p(count), p(length),
+                                    p(status), p(ptr), p(prof)) == 0
+            assert lib.rt_tsv_close(h) == 0
+            assert out.read_text() == run["text"]
+
+
+def test_repr_double_is_python_repr(built):
+    import ctypes as C
+
+    from ribotricer_b200 import _lib
+
+    lib = _lib.load()
+    buf = C.create_string_buffer(64)
+    rng = np.random.default_rng(2)
+    vals = [0.0, 1.0, 0.5, 1e-5, 1e-4, 123456789.0, 1e15, 1e16, 1.5e16, 1e22, 1 / 3, 5e-324, 1.7976931348623157e308,
+            0.1 + 0.2, 100.0] + rng.random(3000).tolist() + (10.0 ** rng.uniform(-12, 22, 3000)).tolist()
+    for v in vals:
+        lib.rt_repr_double(float(v), buf, 64)
+        assert buf.value.decode() == repr(float(v)) == str(np.float64(v))
