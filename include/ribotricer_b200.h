@@ -200,6 +200,25 @@ int rt_tsv_write(rt_tsv* t, const rt_index* ix, int64_t n_sel, const int64_t* or
 int rt_tsv_close(rt_tsv* t);
 int rt_repr_double(double x, char* buf, int cap);            /* Python float repr (shortest round trip) */
 
+/*
+ * ---- native BAM/BGZF decode to read columns (no GPU involved; SURVEY.md 8(f) "next #2") -------
+ * Replaces the pysam passes of split_bam (bam.py:65-71) on the host: per record ref_id, flag,
+ * mapq, the first/last/count of matched reference positions (get_reference_positions() semantics of
+ * bam.py:95-99: M, = and X operations only) and the NH tag (0 if absent, common.py:53-56).
+ * BGZF blocks are inflated with `n_threads` threads (<= 0: all cores).
+ */
+typedef struct rt_bam rt_bam;
+const char* rt_bam_last_error(void);
+int rt_bam_load(const char* path, int n_threads, rt_bam** out);
+void rt_bam_free(rt_bam* b);
+int64_t rt_bam_n_reads(const rt_bam* b);
+int rt_bam_n_ref(const rt_bam* b);
+const char* rt_bam_ref_name(const rt_bam* b, int i);
+int64_t rt_bam_ref_len(const rt_bam* b, int i);
+int rt_bam_sorted(const rt_bam* b);                          /* @HD SO:coordinate */
+int rt_bam_copy(const rt_bam* b, int32_t* ref_id, int32_t* first, int32_t* last, uint16_t* mlen,
+                uint16_t* flag, uint8_t* mapq, uint8_t* nh); /* any pointer may be NULL */
+
 /* number of kernel launches issued through this ctx so far (bench.py's gpu_launches) */
 int64_t rt_launch_count(const rt_ctx* ctx);
 

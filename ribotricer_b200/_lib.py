@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libribotricer_b200.so")
+LIB_PATH = os.environ.get("RT_LIB_PATH") or os.path.join(HERE, "libribotricer_b200.so")   # override: kernel A/B runs
 
 RT_LEN_TABLE = 65536
 RT_LEN_UNUSED = -1
@@ -26,7 +26,8 @@ EXPORTS = (
     "rt_gather_profiles", "rt_launch_count", "rt_phasescore_values", "rt_io_last_error", "rt_index_load",
     "rt_index_free", "rt_index_n_orf", "rt_index_n_exon", "rt_index_n_annotated_prefix", "rt_index_n_chrom",
     "rt_index_chrom_name", "rt_index_copy", "rt_index_field", "rt_tsv_open", "rt_tsv_write", "rt_tsv_close",
-    "rt_repr_double",
+    "rt_repr_double", "rt_bam_last_error", "rt_bam_load", "rt_bam_free", "rt_bam_n_reads", "rt_bam_n_ref",
+    "rt_bam_ref_name", "rt_bam_ref_len", "rt_bam_sorted", "rt_bam_copy",
 )
 
 
@@ -104,6 +105,19 @@ def load():
     lib.rt_tsv_write.argtypes = [vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.rt_tsv_close.argtypes = [vp]
     lib.rt_repr_double.argtypes = [C.c_double, C.c_char_p, i32]
+    lib.rt_bam_last_error.restype = C.c_char_p
+    lib.rt_bam_load.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
+    lib.rt_bam_free.argtypes = [vp]
+    lib.rt_bam_free.restype = None
+    lib.rt_bam_n_reads.argtypes = [vp]
+    lib.rt_bam_n_reads.restype = i64
+    lib.rt_bam_n_ref.argtypes = [vp]
+    lib.rt_bam_ref_name.argtypes = [vp, i32]
+    lib.rt_bam_ref_name.restype = C.c_char_p
+    lib.rt_bam_ref_len.argtypes = [vp, i32]
+    lib.rt_bam_ref_len.restype = i64
+    lib.rt_bam_sorted.argtypes = [vp]
+    lib.rt_bam_copy.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     lib.rt_launch_count.restype = i64
     if lib.rt_abi_version() != 1:
         raise RtError(f"ABI mismatch: library reports {lib.rt_abi_version()}, binding expects 1")

@@ -81,8 +81,31 @@ def read_bam_columns(bam_path: str) -> ReadColumns:
     return ReadColumns(names, lens, {k: np.asarray(acc[k], dt) for k, dt in READ_COLUMNS}, so)
 
 
+def read_bam_columns_native(bam_path: str, n_threads: int = 0) -> ReadColumns:
+    """Decode a BAM with the native BGZF/BAM reader (csrc/rt_bam.cpp, multi-threaded inflate);
+    same columns as ``read_bam_columns``, no pysam needed."""
+    import ctypes as C
+
+    lib = _lib.load()
+    handle = C.c_void_p()
+    if lib.rt_bam_load(str(bam_path).encode(), int(n_threads), C.byref(handle)) != 0:
+        raise OSError(f"cannot decode {bam_path}: {lib.rt_bam_last_error().decode()}")
+    try:
+        n = int(lib.rt_bam_n_reads(handle))
+        cols = {name: np.zeros(n, dt) for name, dt in READ_COLUMNS}
+        lib.rt_bam_copy(handle, *[cols[name].ctypes.data_as(C.c_void_p) for name, _ in READ_COLUMNS])
+        n_ref = lib.rt_bam_n_ref(handle)
+        names = [lib.rt_bam_ref_name(handle, i).decode() for i in range(n_ref)]
+        lens = np.array([lib.rt_bam_ref_len(handle, i) for i in range(n_ref)], np.int64)
+        return ReadColumns(names, lens, cols, bool(lib.rt_bam_sorted(handle)))
+    finally:
+        lib.rt_bam_free(handle)
+
+
 def load_reads(path) -> ReadColumns:
-    """BAM (through pysam) or ``.npz`` of decoded columns."""
+    """BAM (native decoder; ``RIBOTRICER_B200_PYSAM=1`` forces pysam) or ``.npz`` of decoded columns."""
+    import os
+
     if isinstance(path, ReadColumns):
         return path
     if str(path).endswith(".npz"):
@@ -90,7 +113,9 @@ def load_reads(path) -> ReadColumns:
         cols = {name: np.ascontiguousarray(z[name], dt) for name, dt in READ_COLUMNS}
         so = bool(z["sorted_by_coordinate"]) if "sorted_by_coordinate" in z else False
         return ReadColumns([str(c) for c in z["contig_names"]], np.asarray(z["contig_len"], np.int64), cols, so)
-    return read_bam_columns(path)
+    if os.environ.get("RIBOTRICER_B200_PYSAM") == "1":
+        return read_bam_columns(path)
+    return read_bam_columns_native(path)
 
 
 class Alignments:

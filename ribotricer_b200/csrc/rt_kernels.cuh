@@ -401,7 +401,10 @@ score_orfs_kernel(const ScoreArgs args) {
 constexpr int kPackMaxNt = 3045;      // <= 127 rounds of 8 lanes: the 7-bit per-lane fields never overflow
 constexpr int kShortLPO = 8;          // lanes per short ORF
 constexpr int kLongFlushRounds = 31;  // whole-warp ORFs: flush the 10-bit fields every 31 rounds
-constexpr int kDeferLanes = 12;       // general codons wait until this many lanes hold one
+#ifndef RT_DEFER_LANES
+#define RT_DEFER_LANES 0
+#endif
+constexpr int kDeferLanes = RT_DEFER_LANES;   // general codons wait until this many lanes hold one (0: no parking)
 
 template <int LPO>
 __device__ __forceinline__ unsigned group_sum_u32(unsigned v) {
@@ -570,6 +573,10 @@ __device__ __forceinline__ void multi_codon(int a, int b, int c, unsigned long l
         acc2 += 1ull << (7 * (2 * F + 1));
     } else {
         acc2 += 1ull << (7 * (2 * F));
+        if (kDeferLanes == 0) {
+            unit_vector_add(2 * a - b - c, b - c, f);
+            return;
+        }
         int& A = F == 0 ? d.A0 : F == 1 ? d.A1 : d.A2;
         int& B = F == 0 ? d.B0 : F == 1 ? d.B1 : d.B2;
         if (d.has & (1u << F)) unit_vector_add(A, B, f);   // slot taken: settle the older codon now
@@ -674,7 +681,7 @@ __device__ __forceinline__ void score_pack(const ScoreArgs& args, const unsigned
                 }
             }
         }
-        if (__popc(__ballot_sync(kFull, dfr.has != 0)) >= kDeferLanes) flush_deferred(dfr, f0, f1, f2);
+        if (kDeferLanes > 0 && __popc(__ballot_sync(kFull, dfr.has != 0)) >= kDeferLanes) flush_deferred(dfr, f0, f1, f2);
         if (Long && (r % kLongFlushRounds) == kLongFlushRounds - 1) {
             unpack_acc(acc1, acc2, f0, f1, f2);
             t0.flush(f0); t1.flush(f1); t2.flush(f2);

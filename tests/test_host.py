@@ -148,3 +148,76 @@ def test_repr_double_is_python_repr(built):
     for v in vals:
         lib.rt_repr_double(float(v), buf, 64)
         assert buf.value.decode() == repr(float(v)) == str(np.float64(v))
+
+
+def _expected_span(pos, cigar):
+    """get_reference_positions() semantics (bam.py:95-99): positions of M, = and X only."""
+    positions, cur = [], pos
+    for op, length in cigar:
+        if op in "M=X":
+            positions.extend(range(cur, cur + length))
+            cur += length
+        elif op in "DN":
+            cur += length
+    if not positions:
+        return 0, 0, 0
+    return positions[0], positions[-1], len(positions)
+
+
+def test_native_bam_decoder(tmp_path, built):
+    """csrc/rt_bam.cpp on BAM files written by tests/bam_writer.py: CIGARs with every operation,
+    NH tags of every integer type hidden among other aux fields, unmapped records, records that
+    straddle BGZF blocks, multi-threaded and single-threaded."""
+    import bam_writer as W
+    import pytest
+    from ribotricer_b200.bam import load_reads, read_bam_columns_native
+
+    rng = np.random.default_rng(4)
+    refs = [("chrI", 230218), ("chrII", 813184), ("chrM", 85779)]
+    recs, exp = [], []
+    for i in range(30000):
+        kind = rng.random()
+        if kind < 0.03:                       # unmapped, no CIGAR
+            flag, ref_id, pos, cigar = 4, -1, -1, []
+        else:
+            flag = int(rng.choice([0, 16, 256, 272, 1024, 512, 2048, 0, 16, 0]))
+            ref_id = int(rng.integers(0, len(refs)))
+            pos = int(rng.integers(0, refs[ref_id][1] - 500))
+            cigar = []
+            if rng.random() < 0.3:
+                cigar.append(("S", int(rng.integers(1, 6))))
+            for k in range(int(rng.integers(1, 7))):
+                cigar.append((str(rng.choice(list("MMMM=XIDN"))), int(rng.integers(1, 40))))
+            if rng.random() < 0.2:
+                cigar.append((str(rng.choice(list("SHP"))), int(rng.integers(1, 5))))
+        mapq = int(rng.choice([0, 1, 3, 255, 60]))
+        aux, nh = b"", 0
+        if rng.random() < 0.5:
+            aux += W.aux_field("NM", "i", int(rng.integers(0, 5))) + W.aux_field("MD", "Z", "10A5^AC6")
+        if rng.random() < 0.3:
+            aux += W.aux_field("XS", "A", "+") + W.aux_field("ZB", "Bs", [1, -2, 3]) + W.aux_field("XF", "f", 1.5)
+        if rng.random() < 0.8:
+            typ = str(rng.choice(list("cCsSiI")))
+            nh = int(rng.choice([1, 1, 1, 2, 3, 10, 100, 300 if typ in "sSiI" else 7]))
+            aux += W.aux_field("NH", typ, nh)
+        if rng.random() < 0.3:
+            aux += W.aux_field("HI", "C", 1) + W.aux_field("ZZ", "BI", list(range(int(rng.integers(0, 9)))))
+        recs.append(W.record(ref_id, pos, mapq, flag, cigar, name=b"read%d" % i, aux=aux))
+        first, last, n = _expected_span(pos, cigar)
+        exp.append((ref_id, first, last, n, flag, mapq, min(nh, 255)))
+    path = tmp_path / "t.bam"
+    W.write_bam(str(path), refs, recs, sorted_header=True, block_payload=4099)   # odd size: records split everywhere
+    exp = np.array(exp, np.int64)
+    for threads in (1, 4):
+        rc = read_bam_columns_native(str(path), threads)
+        assert rc.contig_names == [r[0] for r in refs] and rc.contig_len.tolist() == [r[1] for r in refs]
+        assert rc.sorted_by_coordinate and len(rc) == len(recs)
+        for j, name in enumerate(("ref_id", "first", "last", "mlen", "flag", "mapq", "nh")):
+            assert (rc.cols[name].astype(np.int64) == exp[:, j]).all(), name
+    W.write_bam(str(path), refs, recs[:100], sorted_header=False)
+    rc = load_reads(str(path))
+    assert not rc.sorted_by_coordinate and len(rc) == 100
+    bad = tmp_path / "bad.bam"
+    bad.write_bytes(b"not a bam file at all")
+    with pytest.raises(OSError):
+        read_bam_columns_native(str(bad))
