@@ -4,9 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One "step" is one pass of the hot path over one synthetic Ribo-seq library:
-K1 bin P-sites (+1) -> K2+K3 gather+score every candidate ORF -> K1 again with
-weight -1, which returns the resident coverage planes to zero for the next
-library (cheaper than a 24.8 GB memset).  At N=1 the workload is BASELINE.json
+K1 bin P-sites -> K2+K3 gather+score every candidate ORF -> sparse clear of the
+slots K1 touched, which returns the resident coverage planes to zero for the next
+library (a fraction of a millisecond instead of a 24.7 GB memset).  At N=1 the workload is BASELINE.json
 configs[1] (human GENCODE-scale: 2.5 M candidate ORFs, 100 M reads).  At N>1
 every rank holds its own 2.5 M-ORF shard of an N x 2.5 M-ORF index and bins the
 same library into its own replica of the coverage (north_star item 4: ORFs
@@ -269,6 +269,7 @@ def run_ours(args):
     n_reads = int(dreads["ref_id"].numel())
     n_orf = idx.n_orf
     cov = eng.new_coverage()
+    eng.track_touched(True)
     stats, len_counts = eng.new_bin_accumulators()
     out = eng.new_score_columns(n_orf)
     params = ScoreParams()
@@ -288,7 +289,7 @@ def run_ours(args):
         eng.score_device(cov, out, 0, n_orf, params)
         if events is not None:
             events[2].record()
-        eng.bin_reads_device(cov, dreads, "forward", stats, len_counts, sorted_hint=True, weight=-1)
+        eng.clear_touched(cov)      # zero exactly the slots this library touched
         if events is not None:
             events[3].record()
 
@@ -315,7 +316,7 @@ def run_ours(args):
     bin_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in per_step_events]))
     score_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in per_step_events]))
     unbin_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in per_step_events]))
-    assert int(cov.abs().max().item()) == 0, "coverage did not return to zero after un-binning"
+    assert int(cov.abs().max().item()) == 0, "coverage did not return to zero after the sparse clear"
 
     # ---- e2e: host buffers in, host buffers out, through the host-buffer C-ABI calls
     hreads = {k: v.cpu().pin_memory() for k, v in dreads.items()}
@@ -323,14 +324,14 @@ def run_ours(args):
     torch.cuda.empty_cache()
     e2e_steps = max(3, min(args.steps, 5))
     for _ in range(2):
-        eng.clear_coverage(cov)
+        eng.clear_touched(cov)
         eng.bin_reads_host(cov, hreads, "forward", sorted_hint=True)
         res = eng.score_host(cov, 0, n_orf, params)
     barrier()
     e0, e1 = ev(), ev()
     e0.record()
     for _ in range(e2e_steps):
-        eng.clear_coverage(cov)
+        eng.clear_touched(cov)
         st_host, _ = eng.bin_reads_host(cov, hreads, "forward", sorted_hint=True)
         res = eng.score_host(cov, 0, n_orf, params)
     e1.record()
@@ -368,10 +369,10 @@ def run_ours(args):
                 "orfs_per_gpu": n_orf, "reads": n_reads, "sharding": f"orf-shard x{world}, coverage replicated",
                 "l2": "inputs larger than L2 (coverage planes %.1f GB, read columns %.2f GB)" % (
                     cov.numel() * 4 / 1e9, READ_BYTES * n_reads / 1e9),
-                "step": "bin(+1) -> gather+score -> bin(-1) (returns the resident coverage to zero)",
+                "step": "bin P-sites -> gather+score -> sparse clear of the touched slots (resident coverage back to zero)",
             },
             "reads_binned_per_s": world * n_reads / (ms_per_step * 1e-3),
-            "kernels_ms": {"bin_psites": bin_ms, "score_orfs": score_ms, "unbin_psites": unbin_ms},
+            "kernels_ms": {"bin_psites": bin_ms, "score_orfs": score_ms, "clear_touched": unbin_ms},
             "roofline": {"bound": "hbm", "kernel": "score_orfs_packed_kernel<8> (+ fallback launch)", "achieved": achieved,
                          "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "traffic_source": traffic_src,
@@ -381,7 +382,7 @@ def run_ours(args):
                                         "algorithmic_bytes": bin_bytes}},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "path": "Engine.clear_coverage + bin_reads_host (rt_bin_reads_host) + score_host (rt_score_host)"},
+                    "path": "Engine.clear_touched + bin_reads_host (rt_bin_reads_host) + score_host (rt_score_host)"},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "translating": int(res["status"].sum()), "valid_reads": st_host["valid"],

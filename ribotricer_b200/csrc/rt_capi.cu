@@ -79,6 +79,12 @@ struct rt_ctx {
     DevBuf read_slot[2];
     cudaStream_t slot_stream[2] = {nullptr, nullptr};
     DevBuf stats_buf, score_buf;
+
+    // sparse clear: slots touched by K1 since the last rt_clear_touched
+    bool track_touched = false;
+    DevBuf touched_buf;
+    unsigned long long* d_n_touched = nullptr;
+    int64_t touched_reserved = 0;    // reads binned (weight +1) since the last clear
 };
 
 namespace {
@@ -113,6 +119,22 @@ struct DeviceGuard {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
+
+// The touched-slot list holds one entry per read binned since the last clear; grow it keeping its content.
+int ensure_touched_capacity(rt_ctx* ctx, int64_t reads) {
+    const size_t need = sizeof(unsigned long long) * (size_t)reads;
+    if (need <= ctx->touched_buf.cap) return RT_OK;
+    DevBuf bigger;
+    RT_CUDA(ctx, bigger.reserve(std::max(need, ctx->touched_buf.cap * 2)));
+    if (ctx->touched_buf.p) {
+        RT_CUDA(ctx, cudaDeviceSynchronize());
+        RT_CUDA(ctx, cudaMemcpy(bigger.p, ctx->touched_buf.p, sizeof(unsigned long long) * (size_t)ctx->touched_reserved,
+                                cudaMemcpyDeviceToDevice));
+        ctx->touched_buf.release();
+    }
+    ctx->touched_buf = bigger;
+    return RT_OK;
+}
 
 constexpr size_t kReadBytes = 4 + 4 + 4 + 2 + 2 + 1 + 1;
 constexpr int64_t kHostChunkReads = 4 << 20;
@@ -185,6 +207,8 @@ void rt_destroy(rt_ctx* ctx) {
     }
     ctx->stats_buf.release();
     ctx->score_buf.release();
+    ctx->touched_buf.release();
+    cudaFree(ctx->d_n_touched);
     delete ctx;
 }
 
@@ -259,6 +283,33 @@ int rt_clear_coverage(rt_ctx* ctx, int32_t* d_cov, void* stream) {
     return RT_OK;
 }
 
+int rt_track_touched(rt_ctx* ctx, int enable) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_track_touched: ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    if (enable && !ctx->d_n_touched) {
+        RT_CUDA(ctx, cudaMalloc(&ctx->d_n_touched, sizeof(unsigned long long)));
+        RT_CUDA(ctx, cudaMemset(ctx->d_n_touched, 0, sizeof(unsigned long long)));
+    }
+    ctx->track_touched = enable != 0;
+    return RT_OK;
+}
+
+int rt_clear_touched(rt_ctx* ctx, int32_t* d_cov, void* stream) {
+    if (!ctx || !d_cov) return fail(ctx, RT_EINVAL, "rt_clear_touched: NULL argument");
+    if (!ctx->d_n_touched) return fail(ctx, RT_ESTATE, "rt_clear_touched: call rt_track_touched(ctx, 1) first");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->touched_buf.p) {
+        rt::clear_touched_kernel<<<(unsigned)ctx->n_sm * 8, 256, 0, st>>>(
+            d_cov, static_cast<const unsigned long long*>(ctx->touched_buf.p), ctx->d_n_touched);
+        ctx->launches++;
+        RT_CUDA(ctx, cudaGetLastError());
+    }
+    RT_CUDA(ctx, cudaMemsetAsync(ctx->d_n_touched, 0, sizeof(unsigned long long), st));
+    ctx->touched_reserved = 0;
+    return RT_OK;
+}
+
 // ------------------------------------------------------------------------------------ K1
 int rt_bin_reads(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* d_ref_id, const int32_t* d_first,
                  const int32_t* d_last, const uint16_t* d_mlen, const uint16_t* d_flag, const uint8_t* d_mapq,
@@ -290,6 +341,15 @@ int rt_bin_reads(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* d_ref_id
     a.plane = ctx->plane;
     a.stats = reinterpret_cast<unsigned long long*>(d_stats);
     a.len_counts = reinterpret_cast<unsigned long long*>(d_len_counts);
+    a.touched = nullptr;
+    a.n_touched = nullptr;
+    if (ctx->track_touched && weight == 1) {
+        int rc = ensure_touched_capacity(ctx, ctx->touched_reserved + n);
+        if (rc != RT_OK) return rc;
+        ctx->touched_reserved += n;
+        a.touched = static_cast<unsigned long long*>(ctx->touched_buf.p);
+        a.n_touched = ctx->d_n_touched;
+    }
     const int64_t per_block = (int64_t)rt::kBinThreads * rt::kBinReadsPerThread;
     const int64_t blocks = (n + per_block - 1) / per_block;
     if (blocks > 0x7fffffff) return fail(ctx, RT_EINVAL, "rt_bin_reads: n too large for one launch");
@@ -314,6 +374,10 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
         if (!ctx->slot_stream[s]) RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking));
     RT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, acc_bytes, ctx->slot_stream[0]));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[0]));
+    if (ctx->track_touched) {   // one growth up front instead of one per chunk
+        int rc = ensure_touched_capacity(ctx, ctx->touched_reserved + n);
+        if (rc != RT_OK) return rc;
+    }
     const int64_t chunk = std::min<int64_t>(kHostChunkReads, std::max<int64_t>(n, 1));
     // per-slot layout: 4-byte columns first so that every column stays naturally aligned
     const size_t slot_bytes = (size_t)chunk * kReadBytes + 64;

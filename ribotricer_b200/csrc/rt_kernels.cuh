@@ -874,6 +874,8 @@ struct BinArgs {
     int protocol;
     int weight;                    // +1 bin, -1 un-bin
     int len_base;                  // lengths [len_base, len_base + 16) are counted in registers
+    unsigned long long* touched;   // optional: every slot that received an atomic (duplicates allowed)
+    unsigned long long* n_touched;
     const int32_t* len_table;      // RT_LEN_TABLE
     const long long* contig_base;  // n_contig
     const long long* contig_len;   // n_contig
@@ -904,6 +906,10 @@ __device__ __forceinline__ int classify_read(unsigned fl, unsigned mapq, unsigne
 __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a) {
     __shared__ unsigned int s_stats[RT_N_STATS];
     __shared__ unsigned int s_len[kLenHist];
+    __shared__ unsigned long long s_touch[kBinThreads * kBinReadsPerThread];
+    __shared__ unsigned int s_ntouch;
+    __shared__ unsigned long long s_touch_base;
+    if (threadIdx.x == 0) s_ntouch = 0;
     for (int i = threadIdx.x; i < kLenHist; i += kBinThreads) s_len[i] = 0;
     if (threadIdx.x < RT_N_STATS) s_stats[threadIdx.x] = 0;
     __syncthreads();
@@ -977,6 +983,13 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
                 const int run = after ? __ffs(after) : 32 - lane;
                 atomicAdd(a.cov + slot, a.weight * run);
             }
+            if (a.touched) {   // remember the slot so the planes can be cleared sparsely afterwards
+                const unsigned writers = __ballot_sync(kFull, head && slot >= 0);
+                unsigned base = 0;
+                if (lane == 0 && writers) base = atomicAdd(&s_ntouch, (unsigned)__popc(writers));
+                base = __shfl_sync(kFull, base, 0);
+                if (head && slot >= 0) s_touch[base + __popc(writers & ((1u << lane) - 1u))] = (unsigned long long)slot;
+            }
             // bam.py:136: per-thread 4-bit counters for the 16 lengths from len_base on
             if (len >= 0) {
                 const unsigned d = (unsigned)(len - a.len_base);
@@ -1012,11 +1025,25 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
         s_stats[RT_ST_TOTAL] = (unsigned)(left < kBinThreads * kBinReadsPerThread ? left : kBinThreads * kBinReadsPerThread);
     }
     __syncthreads();
+    if (a.touched) {   // one global atomic per block, then a coalesced copy of the block's slots
+        if (threadIdx.x == 0) s_touch_base = atomicAdd(a.n_touched, (unsigned long long)s_ntouch);
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < s_ntouch; i += kBinThreads) a.touched[s_touch_base + i] = s_touch[i];
+    }
     // two's-complement wrap makes weight = -1 subtract
     if (threadIdx.x < RT_N_STATS && s_stats[threadIdx.x])
         atomicAdd(a.stats + threadIdx.x, (unsigned long long)((long long)a.weight * s_stats[threadIdx.x]));
     for (int i = threadIdx.x; i < kLenHist; i += kBinThreads)
         if (s_len[i]) atomicAdd(a.len_counts + i, (unsigned long long)((long long)a.weight * s_len[i]));
+}
+
+// Sparse clear: zero exactly the slots K1 touched since the last clear (duplicates are harmless).
+__global__ void __launch_bounds__(256) clear_touched_kernel(int32_t* cov, const unsigned long long* __restrict__ touched,
+                                                             const unsigned long long* __restrict__ n_touched) {
+    const unsigned long long n = *n_touched;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        cov[touched[i]] = 0;
 }
 
 // ---- phasescore of one arbitrary (float) profile --------------------------------------------

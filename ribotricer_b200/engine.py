@@ -143,6 +143,14 @@ class Engine:
     def clear_coverage(self, cov):
         self._check(self.lib.rt_clear_coverage(self.ctx, C.c_void_p(cov.data_ptr()), self._stream()))
 
+    def track_touched(self, enable: bool = True):
+        """Make K1 remember the slots it bumps, so ``clear_touched`` can zero just those."""
+        self._check(self.lib.rt_track_touched(self.ctx, int(enable)))
+
+    def clear_touched(self, cov):
+        """Sparse clear of a recycled coverage buffer (see ``rt_clear_touched``)."""
+        self._check(self.lib.rt_clear_touched(self.ctx, C.c_void_p(cov.data_ptr()), self._stream()))
+
     # ---------------------------------------------------------------- index
     def set_index(self, exon_ptr, exon_start, exon_end, orf_contig, orf_strand):
         exon_ptr = np.ascontiguousarray(exon_ptr, np.int64)

@@ -323,3 +323,36 @@ def test_full_config2_properties(engine):
         assert abs(s - one["score"][o]) <= SCORE_TOL
         if not CO.tie_mask(K[None, :], s3[None, :])[0]:
             assert v == one["valid"][o]
+
+
+def test_sparse_clear(engine):
+    """rt_track_touched / rt_clear_touched: after binning through both entry points the sparse
+    clear must leave the planes exactly zero, and a second library must bin as if freshly cleared."""
+    CO = _oracle()
+    from ribotricer_b200 import synth
+
+    cfg = synth.config("tiny")
+    idx = synth.make_index(cfg)
+    pad = 64
+    base, plane = _setup(engine, idx.contig_names, idx.contig_len, idx.as_dict(), synth.TRUE_OFFSETS, pad=pad)
+    lt = CO.make_len_table(synth.TRUE_OFFSETS)
+    cov = engine.new_coverage()
+    engine.track_touched(True)
+    try:
+        for rep, (n, sort) in enumerate(((250_000, True), (90_000, False), (400_000, True))):
+            reads = synth.reads_to_numpy(synth.make_reads(cfg, idx, n_reads=n, sort=sort, seed_offset=rep))
+            ref_cov, ref_stats, _ = CO.bin_reads(reads, 0, lt, base, idx.contig_len, pad, plane)
+            if rep % 2 == 0:
+                stats, _ = engine.bin_reads_host(cov, reads, "forward", sorted_hint=sort)
+                assert stats == ref_stats
+            else:
+                st, lc = engine.new_bin_accumulators()
+                half = n // 2
+                for part in (slice(0, half), slice(half, n)):     # two launches accumulate one list
+                    d = engine.upload_reads({k: v[part] for k, v in reads.items()})
+                    engine.bin_reads_device(cov, d, "forward", st, lc, sorted_hint=sort)
+            assert (cov.cpu().numpy() == ref_cov).all()
+            engine.clear_touched(cov)
+            assert int(cov.abs().max().item()) == 0
+    finally:
+        engine.track_touched(False)
