@@ -874,7 +874,7 @@ struct BinArgs {
     int protocol;
     int weight;                    // +1 bin, -1 un-bin
     int len_base;                  // lengths [len_base, len_base + 16) are counted in registers
-    unsigned long long* touched;   // optional: every slot that received an atomic (duplicates allowed)
+    unsigned long long* touched;   // optional: every 32 B sector (slot >> 3) that received an atomic (duplicates allowed)
     unsigned long long* n_touched;
     const int32_t* len_table;      // RT_LEN_TABLE
     const long long* contig_base;  // n_contig
@@ -983,12 +983,15 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
                 const int run = after ? __ffs(after) : 32 - lane;
                 atomicAdd(a.cov + slot, a.weight * run);
             }
-            if (a.touched) {   // remember the slot so the planes can be cleared sparsely afterwards
-                const unsigned writers = __ballot_sync(kFull, head && slot >= 0);
+            if (a.touched) {   // remember the 32 B sector so the planes can be cleared sparsely afterwards
+                const long long sec = slot >= 0 ? slot >> 3 : -1;
+                const long long prev_sec = __shfl_up_sync(kFull, sec, 1);
+                const bool shead = sec >= 0 && (lane == 0 || sec != prev_sec);
+                const unsigned writers = __ballot_sync(kFull, shead);
                 unsigned base = 0;
                 if (lane == 0 && writers) base = atomicAdd(&s_ntouch, (unsigned)__popc(writers));
                 base = __shfl_sync(kFull, base, 0);
-                if (head && slot >= 0) s_touch[base + __popc(writers & ((1u << lane) - 1u))] = (unsigned long long)slot;
+                if (shead) s_touch[base + __popc(writers & ((1u << lane) - 1u))] = (unsigned long long)sec;
             }
             // bam.py:136: per-thread 4-bit counters for the 16 lengths from len_base on
             if (len >= 0) {
@@ -1037,13 +1040,20 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
         if (s_len[i]) atomicAdd(a.len_counts + i, (unsigned long long)((long long)a.weight * s_len[i]));
 }
 
-// Sparse clear: zero exactly the slots K1 touched since the last clear (duplicates are harmless).
+// Sparse clear: zero the 32-byte sectors (8 slots) K1 touched since the last clear.  Whole sectors
+// are safe to zero because only K1 writes the planes and they started from zero; duplicates in the
+// list are harmless.
 __global__ void __launch_bounds__(256) clear_touched_kernel(int32_t* cov, const unsigned long long* __restrict__ touched,
                                                              const unsigned long long* __restrict__ n_touched) {
     const unsigned long long n = *n_touched;
+    int4* sectors = reinterpret_cast<int4*>(cov);
+    const int4 z = make_int4(0, 0, 0, 0);
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x)
-        cov[touched[i]] = 0;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long sec = touched[i];
+        sectors[2 * sec] = z;
+        sectors[2 * sec + 1] = z;
+    }
 }
 
 // ---- phasescore of one arbitrary (float) profile --------------------------------------------
