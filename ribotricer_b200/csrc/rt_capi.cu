@@ -65,6 +65,19 @@ struct rt_ctx {
     std::vector<int64_t> nt_prefix;     // n_orf + 1: prefix of L
     unsigned long long* d_work_counter = nullptr;   // 4 x u64: work counters of the 3 score launches + fallback count
     int pack_lpo = 8;                                // lanes per ORF of the packed kernel (RT_PACK_LPO)
+    bool use_atoms = true;                           // two-phase scoring (RT_SCORE_PATH=scan selects the scan kernel)
+
+    // two-phase scoring: atoms (coverage intervals no ORF exon boundary splits) and per-ORF atom refs
+    int64_t n_atoms = 0;
+    uint64_t* d_atoms = nullptr;                     // (slot offset << 24) | len
+    uint64_t* d_orf_refs_desc = nullptr;             // per ORF: ref begin | n_refs << 40 | reverse << 63
+    uint64_t* d_ref_ent = nullptr;                   // refs in profile order
+    uint32_t* d_ref_atom = nullptr;
+    rt::AtomSummary* d_summaries = nullptr;          // per-library scratch, written by phase A
+    std::vector<uint64_t> h_atoms;                   // host copies used to build per-range atom lists
+    std::vector<uint64_t> h_orf_refs_desc;
+    std::vector<uint32_t> h_ref_atom;
+    std::vector<uint64_t> h_ref_ent;
 
     // score plan: ORFs of a range sorted by length (longest first), split by kernel
     struct ScorePlan {
@@ -72,6 +85,8 @@ struct rt_ctx {
         int32_t* d_list = nullptr;      // [n_long | n_short] absolute ORF ids
         int32_t* d_fallback = nullptr;  // capacity n_short
         int64_t n_long = 0, n_short = 0;
+        int32_t* d_atom_list = nullptr; // atoms the range touches, similar lengths adjacent
+        int64_t n_atom_list = 0;
     };
     std::vector<ScorePlan> plans;
 
@@ -136,6 +151,96 @@ int ensure_touched_capacity(rt_ctx* ctx, int64_t reads) {
     return RT_OK;
 }
 
+// Two-phase scoring, host side: cut the exon entries of all ORFs at every entry boundary into atoms
+// (no ORF exon boundary falls inside an atom; atoms longer than kAtomMaxNt are chopped) and express
+// every ORF as its sequence of atoms in profile order.
+int build_atoms(rt_ctx* ctx, const std::vector<uint64_t>& desc, const std::vector<uint64_t>& entries) {
+    const uint64_t kZero = rt::kZeroOff;
+    std::vector<uint64_t> pts;
+    pts.reserve(entries.size() * 2);
+    for (uint64_t ent : entries) {
+        const uint64_t off = ent >> rt::kLenBits, len = ent & rt::kLenMask;
+        if (off == kZero) continue;
+        pts.push_back(off);
+        pts.push_back(off + len);
+    }
+    std::sort(pts.begin(), pts.end());
+    pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
+    // which elementary intervals [pts[i], pts[i+1]) are covered by an entry
+    std::vector<int32_t> diff(pts.size() + 1, 0);
+    auto idx_of = [&](uint64_t v) { return (size_t)(std::lower_bound(pts.begin(), pts.end(), v) - pts.begin()); };
+    for (uint64_t ent : entries) {
+        const uint64_t off = ent >> rt::kLenBits, len = ent & rt::kLenMask;
+        if (off == kZero) continue;
+        diff[idx_of(off)]++;
+        diff[idx_of(off + len)]--;
+    }
+    // atoms of interval i are [atom_begin[i], atom_begin[i+1])
+    std::vector<uint32_t> atom_begin(pts.size() + 1, 0);
+    ctx->h_atoms.clear();
+    int64_t cover = 0;
+    for (size_t i = 0; i + 1 < pts.size(); ++i) {
+        cover += diff[i];
+        atom_begin[i] = (uint32_t)ctx->h_atoms.size();
+        if (cover > 0) {
+            uint64_t at = pts[i];
+            while (at < pts[i + 1]) {
+                const uint64_t piece = std::min<uint64_t>(pts[i + 1] - at, (uint64_t)rt::kAtomMaxNt);
+                ctx->h_atoms.push_back((at << rt::kLenBits) | piece);
+                at += piece;
+            }
+        }
+    }
+    if (!pts.empty()) atom_begin[pts.size() - 1] = atom_begin[pts.size()] = (uint32_t)ctx->h_atoms.size();
+    if (ctx->h_atoms.size() >= 0xffffffffull) return fail(ctx, RT_EINVAL, "rt_set_index: too many atoms");
+    // per-ORF refs in profile order
+    const size_t n_orf = desc.size();
+    ctx->h_orf_refs_desc.assign(n_orf, 0);
+    ctx->h_ref_ent.clear();
+    ctx->h_ref_atom.clear();
+    ctx->h_ref_ent.reserve(entries.size() * 3 / 2);
+    ctx->h_ref_atom.reserve(entries.size() * 3 / 2);
+    for (size_t o = 0; o < n_orf; ++o) {
+        const uint64_t begin = desc[o] & rt::kBeginMask;
+        const int n_ent = (int)((desc[o] >> 40) & rt::kMaxEntriesPerOrf);
+        const bool rev = (desc[o] >> 63) != 0;
+        const size_t ref_begin = ctx->h_ref_ent.size();
+        for (int k = 0; k < n_ent; ++k) {
+            const uint64_t ent = entries[begin + (rev ? n_ent - 1 - k : k)];
+            const uint64_t off = ent >> rt::kLenBits, len = ent & rt::kLenMask;
+            if (off == kZero) {
+                ctx->h_ref_ent.push_back(ent);
+                ctx->h_ref_atom.push_back(0xffffffffu);   // reads-as-zero stretch: no atom
+                continue;
+            }
+            const uint32_t a0 = atom_begin[idx_of(off)], a1 = atom_begin[idx_of(off + len)];
+            for (uint32_t a = 0; a < a1 - a0; ++a) {
+                const uint32_t atom = rev ? a1 - 1 - a : a0 + a;
+                ctx->h_ref_ent.push_back(ctx->h_atoms[atom]);
+                ctx->h_ref_atom.push_back(atom);
+            }
+        }
+        const size_t cnt = ctx->h_ref_ent.size() - ref_begin;
+        if (cnt > (size_t)rt::kMaxEntriesPerOrf) return fail(ctx, RT_EINVAL, "rt_set_index: ORF %zu has too many atoms", o);
+        ctx->h_orf_refs_desc[o] = (uint64_t)ref_begin | ((uint64_t)cnt << 40) | ((uint64_t)rev << 63);
+    }
+    ctx->n_atoms = (int64_t)ctx->h_atoms.size();
+    auto upload = [&](auto** dptr, const auto& vec) -> cudaError_t {
+        using T = typename std::remove_reference<decltype(vec)>::type::value_type;
+        cudaError_t e = cudaMalloc(dptr, sizeof(T) * std::max<size_t>(1, vec.size()));
+        if (e == cudaSuccess && !vec.empty()) e = cudaMemcpy(*dptr, vec.data(), sizeof(T) * vec.size(), cudaMemcpyHostToDevice);
+        return e;
+    };
+    RT_CUDA(ctx, upload(&ctx->d_atoms, ctx->h_atoms));
+    RT_CUDA(ctx, upload(&ctx->d_orf_refs_desc, ctx->h_orf_refs_desc));
+    RT_CUDA(ctx, upload(&ctx->d_ref_ent, ctx->h_ref_ent));
+    RT_CUDA(ctx, upload(&ctx->d_ref_atom, ctx->h_ref_atom));
+    RT_CUDA(ctx, cudaMalloc(&ctx->d_summaries, sizeof(rt::AtomSummary) * std::max<size_t>(1, ctx->h_atoms.size())));
+    ctx->h_ref_ent.clear();
+    ctx->h_ref_ent.shrink_to_fit();
+    return RT_OK;
+}
+
 constexpr size_t kReadBytes = 4 + 4 + 4 + 2 + 2 + 1 + 1;
 constexpr int64_t kHostChunkReads = 4 << 20;
 
@@ -176,6 +281,7 @@ int rt_create(int device, rt_ctx** out) {
         delete ctx;
         return fail(nullptr, RT_ENOMEM, "rt_create: cudaMalloc failed");
     }
+    if (const char* e = getenv("RT_SCORE_PATH")) ctx->use_atoms = strcmp(e, "scan") != 0;
     if (const char* e = getenv("RT_PACK_LPO")) {
         const int v = atoi(e);
         if (v == 8 || v == 16 || v == 32) ctx->pack_lpo = v;
@@ -193,6 +299,11 @@ void rt_destroy(rt_ctx* ctx) {
     cudaFree(ctx->d_orf_desc);
     cudaFree(ctx->d_orf_len);
     cudaFree(ctx->d_exon_entries);
+    cudaFree(ctx->d_atoms);
+    cudaFree(ctx->d_orf_refs_desc);
+    cudaFree(ctx->d_ref_ent);
+    cudaFree(ctx->d_ref_atom);
+    cudaFree(ctx->d_summaries);
     cudaFree(ctx->d_work_counter);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -200,6 +311,7 @@ void rt_destroy(rt_ctx* ctx) {
     for (auto& p : ctx->plans) {
         cudaFree(p.d_list);
         cudaFree(p.d_fallback);
+        cudaFree(p.d_atom_list);
     }
     for (int s = 0; s < 2; ++s) {
         ctx->read_slot[s].release();
@@ -480,8 +592,18 @@ int rt_set_index(rt_ctx* ctx, int64_t n_orf, const int64_t* h_exon_ptr, const in
     for (auto& p : ctx->plans) {
         cudaFree(p.d_list);
         cudaFree(p.d_fallback);
+        cudaFree(p.d_atom_list);
     }
     ctx->plans.clear();
+    cudaFree(ctx->d_atoms);
+    cudaFree(ctx->d_orf_refs_desc);
+    cudaFree(ctx->d_ref_ent);
+    cudaFree(ctx->d_ref_atom);
+    cudaFree(ctx->d_summaries);
+    ctx->d_atoms = ctx->d_orf_refs_desc = ctx->d_ref_ent = nullptr;
+    ctx->d_ref_atom = nullptr;
+    ctx->d_summaries = nullptr;
+    ctx->n_atoms = 0;
     {
         std::vector<int32_t> lens((size_t)n_orf);
         for (int64_t o = 0; o < n_orf; ++o) lens[o] = (int32_t)(ctx->nt_prefix[o + 1] - ctx->nt_prefix[o]);
@@ -496,6 +618,10 @@ int rt_set_index(rt_ctx* ctx, int64_t n_orf, const int64_t* h_exon_ptr, const in
     if (!entries.empty())
         RT_CUDA(ctx, cudaMemcpy(ctx->d_exon_entries, entries.data(), sizeof(uint64_t) * entries.size(),
                                 cudaMemcpyHostToDevice));
+    {
+        int rc = build_atoms(ctx, desc, entries);
+        if (rc != RT_OK) return rc;
+    }
     ctx->n_orf = n_orf;
     return RT_OK;
 }
@@ -562,6 +688,7 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
     if (ctx->plans.size() >= 8) {   // bounded cache
         cudaFree(ctx->plans.front().d_list);
         cudaFree(ctx->plans.front().d_fallback);
+        cudaFree(ctx->plans.front().d_atom_list);
         ctx->plans.erase(ctx->plans.begin());
     }
     rt_ctx::ScorePlan p;
@@ -572,6 +699,30 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
     RT_CUDA(ctx, cudaMalloc(&p.d_list, sizeof(int32_t) * std::max<int64_t>(1, n)));
     RT_CUDA(ctx, cudaMalloc(&p.d_fallback, sizeof(int32_t) * std::max<int64_t>(1, n)));
     RT_CUDA(ctx, cudaMemcpy(p.d_list, ids.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    {   // atoms the ORFs of the range refer to; sorted by length inside windows so that the four atoms of
+        // a warp are balanced while genomic neighbours stay close in time
+        std::vector<uint8_t> used((size_t)ctx->n_atoms, 0);
+        for (int64_t o = lo; o < hi; ++o) {
+            const uint64_t d = ctx->h_orf_refs_desc[o];
+            const uint64_t b = d & rt::kBeginMask, c = (d >> 40) & rt::kMaxEntriesPerOrf;
+            for (uint64_t k = b; k < b + c; ++k)
+                if (ctx->h_ref_atom[k] != 0xffffffffu) used[ctx->h_ref_atom[k]] = 1;
+        }
+        std::vector<int32_t> alist;
+        for (int64_t a = 0; a < ctx->n_atoms; ++a)
+            if (used[a]) alist.push_back((int32_t)a);
+        constexpr size_t kAtomWindow = 4096;
+        for (size_t w0 = 0; w0 < alist.size(); w0 += kAtomWindow) {
+            auto b = alist.begin() + w0, e = alist.begin() + std::min(alist.size(), w0 + kAtomWindow);
+            std::stable_sort(b, e, [&](int32_t x, int32_t y) {
+                return (ctx->h_atoms[x] & rt::kLenMask) > (ctx->h_atoms[y] & rt::kLenMask);
+            });
+        }
+        p.n_atom_list = (int64_t)alist.size();
+        RT_CUDA(ctx, cudaMalloc(&p.d_atom_list, sizeof(int32_t) * std::max<size_t>(1, alist.size())));
+        if (!alist.empty())
+            RT_CUDA(ctx, cudaMemcpy(p.d_atom_list, alist.data(), sizeof(int32_t) * alist.size(), cudaMemcpyHostToDevice));
+    }
     ctx->plans.push_back(p);
     *out = &ctx->plans.back();
     return RT_OK;
@@ -617,6 +768,45 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
     a.prm = *params;
     a.out = *d_out;
     const int threads = rt::kScoreWarps * 32;
+    if (ctx->use_atoms) {
+        // phase A: every atom the range touches is scanned once
+        if (plan->n_atom_list > 0) {
+            rt::AtomArgs aa;
+            aa.cov = d_cov;
+            aa.atoms = ctx->d_atoms;
+            aa.list = plan->d_atom_list;
+            aa.n_list = plan->n_atom_list;
+            aa.work_counter = ctx->d_work_counter + 0;
+            aa.out = ctx->d_summaries;
+            rt::atom_summary_kernel<8><<<persistent_grid(ctx, rt::atom_summary_kernel<8>, (plan->n_atom_list + 3) / 4), threads, 0, st>>>(aa);
+            ctx->launches++;
+        }
+        // phase B: one thread per ORF composes its atoms
+        rt::ComposeArgs ca;
+        ca.cov = d_cov;
+        ca.orf_refs_desc = ctx->d_orf_refs_desc;
+        ca.ref_ent = ctx->d_ref_ent;
+        ca.ref_atom = ctx->d_ref_atom;
+        ca.summaries = ctx->d_summaries;
+        ca.orf_len = ctx->d_orf_len;
+        ca.orf_lo = orf_lo;
+        ca.list = plan->d_list;
+        ca.n_list = plan->n_long + plan->n_short;
+        ca.fallback = plan->d_fallback;
+        ca.n_fallback = a.n_fallback;
+        ca.prm = *params;
+        ca.out = *d_out;
+        rt::score_from_atoms_kernel<<<(unsigned)((ca.n_list + 255) / 256), 256, 0, st>>>(ca);
+        ctx->launches++;
+        // ORFs holding counts >= 2^20: redone by the generic kernel (normally none)
+        a.list = plan->d_fallback;
+        a.n_list = 0;
+        a.n_long = 0;
+        a.n_list_dev = a.n_fallback;
+        a.work_counter = ctx->d_work_counter + 2;
+        rt::score_orfs_kernel<<<(unsigned)ctx->n_sm, threads, 0, st>>>(a);
+        ctx->launches++;
+    } else {
     // 1. fused gather+score: long ORFs first (one warp each), then packs of short ORFs
     {
         a.list = plan->d_list;
@@ -643,6 +833,7 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
         a.work_counter = ctx->d_work_counter + 2;
         rt::score_orfs_kernel<<<(unsigned)ctx->n_sm, threads, 0, st>>>(a);
         ctx->launches++;
+    }
     }
     RT_CUDA(ctx, cudaGetLastError());
     return RT_OK;

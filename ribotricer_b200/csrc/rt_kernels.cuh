@@ -821,6 +821,365 @@ score_orfs_packed_kernel(const ScoreArgs args) {
     }
 }
 
+// ---- K3, two-phase: atom summaries + per-ORF composition -----------------------------------------
+// Candidate ORFs overlap massively (nested ORFs share their 3' exons, isoforms share exons), so the
+// index is cut at every exon boundary of every ORF into ATOMS: maximal coverage intervals that no
+// ORF exon boundary splits.  Every ORF is a sequence of atoms (plus "reads-as-zero" stretches).
+//   phase A (atom_summary_kernel): every atom is scanned ONCE per library -- windows that lie fully
+//            inside the atom are classified exactly like the scan kernel does and summed by local
+//            frame (window start offset mod 3);
+//   phase B (score_from_atoms_kernel): one thread per ORF adds the summaries of its atoms with the
+//            frame rotation that the atom's profile offset implies, evaluates the two windows that
+//            straddle every seam between consecutive atoms from the raw coverage, and runs the
+//            epilogue (statistics.py:92-115, detect_orfs.py:278-299).
+// The work per library is proportional to the UNION of the exons instead of the sum over ORFs.
+// '-' strand: a profile window (v0,v1,v2) is the reversed genomic triple and u(v0,v1,v2) =
+// w^2 conj(u(v2,v1,v0)), so |sum u| is what the '+'-oriented sums give; only the frame mapping of
+// a local frame differs (see score_from_atoms_kernel).
+constexpr int kAtomMaxNt = 3045;       // <= 127 rounds of 8 lanes (7-bit packed per-lane fields)
+
+struct AtomSummary {                   // 96 bytes
+    unsigned K[3];                     // kept (non-all-zero) windows by local frame
+    unsigned U[3];                     // uniform windows among them (count in K only)
+    double re[3];                      // sum of unit vectors, '+' orientation
+    double im[3];                      //   (imaginary part without its sqrt3 factor)
+    unsigned mn[3];                    // min window sum by local frame (0xffffffff: no window)
+    unsigned flags;                    // bit 0: a value >= 2^kBigShift (32-bit sums may have wrapped)
+    long long count;                   // sum of all values of the atom
+};
+
+struct AtomArgs {
+    const int32_t* cov;
+    const uint64_t* atoms;             // (slot offset << 24) | len, len <= kAtomMaxNt
+    const int32_t* list;               // atom ids to summarise, similar lengths adjacent
+    long long n_list;
+    unsigned long long* work_counter;
+    AtomSummary* out;                  // indexed by atom id
+};
+
+template <int LPO>
+__global__ void __launch_bounds__(kScoreWarps * 32, 4)
+atom_summary_kernel(const AtomArgs args) {
+    constexpr int G = 32 / LPO;
+    constexpr int RNT = 3 * LPO;
+    __shared__ unsigned long long s_lut[32];
+    if (threadIdx.x < 32) s_lut[threadIdx.x] = single_codon_lut_entry(threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int sl = lane % LPO;
+    const int gb = lane - sl;
+    const int nbr = sl + 1 == LPO ? gb : lane + 1;
+    const long long n_packs = (args.n_list + G - 1) / G;
+    for (;;) {
+        unsigned long long pack = 0;
+        if (lane == 0) pack = atomicAdd(args.work_counter, 1ull);
+        pack = __shfl_sync(kFull, pack, 0);
+        if ((long long)pack >= n_packs) break;
+        const long long item = (long long)pack * G + lane / LPO;
+        const bool active = item < args.n_list;
+        int atom = 0, len = 0;
+        const int32_t* src = args.cov;
+        if (active) {
+            atom = __ldg(args.list + item);
+            const uint64_t ent = __ldg(args.atoms + atom);
+            len = (int)(ent & kLenMask);
+            src = args.cov + (ent >> kLenBits);
+        }
+        FrameLane f0, f1, f2;
+        unsigned long long acc1 = 0, acc2 = 0;
+        Deferred dfr;
+        unsigned cnt32 = 0, mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu;
+        int ormask = 0;
+        const int rounds = __reduce_max_sync(kFull, ((len + 2) / 3 + LPO - 1) / LPO);
+        auto load3 = [&](int P, int& v0, int& v1, int& v2) {
+            const int p = P + 3 * sl;
+            v0 = v1 = v2 = 0;
+            if (__all_sync(kFull, P >= len || P + RNT <= len)) {
+                if (P < len) { v0 = ld_cov(src + p); v1 = ld_cov(src + p + 1); v2 = ld_cov(src + p + 2); }
+            } else {
+                if (p < len) v0 = ld_cov(src + p);
+                if (p + 1 < len) v1 = ld_cov(src + p + 1);
+                if (p + 2 < len) v2 = ld_cov(src + p + 2);
+            }
+        };
+        int c0, c1, c2;
+        load3(0, c0, c1, c2);
+        for (int r = 0; r < rounds; ++r) {
+            int n0, n1, n2;
+            load3((r + 1) * RNT, n0, n1, n2);
+            const int v3 = __shfl_sync(kFull, sl == 0 ? n0 : c0, nbr);
+            const int v4 = __shfl_sync(kFull, sl == 0 ? n1 : c1, nbr);
+            const int p = 3 * (r * LPO + sl);
+            if (p < len) {
+                cnt32 += (unsigned)c0 + (unsigned)c1 + (unsigned)c2;
+                ormask |= c0 | c1 | c2;
+                if (p + 4 < len) {                               // all three windows lie inside the atom
+                    const unsigned s0 = (unsigned)c0 + (unsigned)c1 + (unsigned)c2;
+                    const unsigned s1 = (unsigned)c1 + (unsigned)c2 + (unsigned)v3;
+                    const unsigned s2 = (unsigned)c2 + (unsigned)v3 + (unsigned)v4;
+                    mn0 = min(mn0, s0); mn1 = min(mn1, s1); mn2 = min(mn2, s2);
+                    if ((c0 | c1 | c2 | v3 | v4) != 0) {
+                        const unsigned m5 = min((unsigned)c0, 1u) | (min((unsigned)c1, 1u) << 1) | (min((unsigned)c2, 1u) << 2) |
+                                            (min((unsigned)v3, 1u) << 3) | (min((unsigned)v4, 1u) << 4);
+                        acc1 += s_lut[m5];
+                        const unsigned multi = ((m5 & (m5 >> 1)) | (m5 & (m5 >> 2)) | ((m5 >> 1) & (m5 >> 2))) & 7u;
+                        if (multi) {
+                            if (multi & 1u) multi_codon<0>(c0, c1, c2, acc2, f0, dfr);
+                            if (multi & 2u) multi_codon<1>(c1, c2, v3, acc2, f1, dfr);
+                            if (multi & 4u) multi_codon<2>(c2, v3, v4, acc2, f2, dfr);
+                        }
+                    }
+                } else {                                         // ragged end of the atom
+                    if (p + 2 < len) { mn0 = min(mn0, (unsigned)c0 + (unsigned)c1 + (unsigned)c2); classify_codon<0>(c0, c1, c2, f0, dfr); }
+                    if (p + 3 < len) { mn1 = min(mn1, (unsigned)c1 + (unsigned)c2 + (unsigned)v3); classify_codon<1>(c1, c2, v3, f1, dfr); }
+                }
+            }
+            c0 = n0; c1 = n1; c2 = n2;
+        }
+        flush_deferred(dfr, f0, f1, f2);
+        unpack_acc(acc1, acc2, f0, f1, f2);
+        const unsigned a1_0 = group_sum_u32<LPO>(f0.w1), a2_0 = group_sum_u32<LPO>(f0.w2);
+        const unsigned a1_1 = group_sum_u32<LPO>(f1.w1), a2_1 = group_sum_u32<LPO>(f1.w2);
+        const unsigned a1_2 = group_sum_u32<LPO>(f2.w1), a2_2 = group_sum_u32<LPO>(f2.w2);
+        const unsigned count = group_sum_u32<LPO>(cnt32);
+#pragma unroll
+        for (int o = LPO / 2; o > 0; o >>= 1) {
+            mn0 = min(mn0, __shfl_xor_sync(kFull, mn0, o));
+            mn1 = min(mn1, __shfl_xor_sync(kFull, mn1, o));
+            mn2 = min(mn2, __shfl_xor_sync(kFull, mn2, o));
+            ormask |= __shfl_xor_sync(kFull, ormask, o);
+        }
+        const bool any_general = __any_sync(kFull, ((a2_0 | a2_1 | a2_2) & 1023u) != 0);
+        double re0 = 0.0, im0 = 0.0, re1 = 0.0, im1 = 0.0, re2 = 0.0, im2 = 0.0;
+        if (any_general) {
+            re0 = group_sum_f64<LPO>(f0.sre); im0 = group_sum_f64<LPO>(f0.sim);
+            re1 = group_sum_f64<LPO>(f1.sre); im1 = group_sum_f64<LPO>(f1.sim);
+            re2 = group_sum_f64<LPO>(f2.sre); im2 = group_sum_f64<LPO>(f2.sim);
+        }
+        if (active && sl == 0) {
+            AtomSummary s;
+            const int na0 = a1_0 & 1023, nb0 = (a1_0 >> 10) & 1023, nc0 = a1_0 >> 20, ng0 = a2_0 & 1023, nu0 = a2_0 >> 10;
+            const int na1 = a1_1 & 1023, nb1 = (a1_1 >> 10) & 1023, nc1 = a1_1 >> 20, ng1 = a2_1 & 1023, nu1 = a2_1 >> 10;
+            const int na2 = a1_2 & 1023, nb2 = (a1_2 >> 10) & 1023, nc2 = a1_2 >> 20, ng2 = a2_2 & 1023, nu2 = a2_2 >> 10;
+            s.K[0] = na0 + nb0 + nc0 + ng0 + nu0; s.K[1] = na1 + nb1 + nc1 + ng1 + nu1; s.K[2] = na2 + nb2 + nc2 + ng2 + nu2;
+            s.U[0] = nu0; s.U[1] = nu1; s.U[2] = nu2;
+            s.re[0] = re0 + 0.5 * (double)(2 * na0 - nb0 - nc0); s.im[0] = im0 + 0.5 * (double)(nb0 - nc0);
+            s.re[1] = re1 + 0.5 * (double)(2 * na1 - nb1 - nc1); s.im[1] = im1 + 0.5 * (double)(nb1 - nc1);
+            s.re[2] = re2 + 0.5 * (double)(2 * na2 - nb2 - nc2); s.im[2] = im2 + 0.5 * (double)(nb2 - nc2);
+            s.mn[0] = mn0; s.mn[1] = mn1; s.mn[2] = mn2;
+            s.flags = (ormask >> kBigShift) != 0 ? 1u : 0u;
+            s.count = (long long)count;
+            args.out[atom] = s;
+        }
+        __syncwarp();
+    }
+}
+
+struct ComposeArgs {
+    const int32_t* cov;
+    const uint64_t* orf_refs_desc;     // per ORF: ref begin (40 bits) | n_refs (23 bits) << 40 | reverse << 63
+    const uint64_t* ref_ent;           // (slot offset << 24) | len in PROFILE order; offset kZeroOff: zeros
+    const uint32_t* ref_atom;          // atom id of the ref (unused for zero refs)
+    const AtomSummary* summaries;
+    const int32_t* orf_len;
+    long long orf_lo;
+    const int32_t* list;               // ORF ids to score
+    long long n_list;
+    int32_t* fallback;                 // ORFs holding counts >= 2^kBigShift: redone by the generic kernel
+    unsigned* n_fallback;
+    rt_score_params prm;
+    rt_score_out out;
+};
+
+// Values at profile positions of an ORF addressed as (ref index, offset inside the ref).
+struct RefWalker {
+    const int32_t* cov;
+    const uint64_t* ref_ent;
+    int n;
+    bool rev;
+    int j = -1, len = 0;
+    long long off = 0;
+    bool zero = true;
+    __device__ __forceinline__ void seek(int jj) {
+        j = jj;
+        const uint64_t ent = __ldg(ref_ent + jj);
+        len = (int)(ent & kLenMask);
+        const uint64_t o = ent >> kLenBits;
+        zero = o == kZeroOff;
+        off = (long long)o;
+    }
+    // value at offset t of ref jj, moving on to the following refs when t runs past the end;
+    // returns false past the end of the ORF
+    __device__ __forceinline__ bool get(int jj, int t, int& v) {
+        if (jj != j) seek(jj);
+        while (t >= len) {
+            if (j + 1 >= n) return false;
+            t -= len;
+            seek(j + 1);
+        }
+        v = zero ? 0 : ld_cov(cov + (rev ? off + len - 1 - t : off + t));
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs args) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= args.n_list) return;
+    const int orf = __ldg(args.list + i);
+    const uint64_t desc = __ldg(args.orf_refs_desc + orf);
+    const uint64_t begin = desc & kBeginMask;
+    const int n_refs = (int)((desc >> 40) & kMaxEntriesPerOrf);
+    const bool rev = (desc >> 63) != 0;
+    const int L = __ldg(args.orf_len + orf);
+    const double kSqrt3 = 1.7320508075688772;
+    const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
+
+    unsigned K[3] = {0, 0, 0}, U[3] = {0, 0, 0};
+    double RE[3] = {0.0, 0.0, 0.0}, IM[3] = {0.0, 0.0, 0.0};
+    unsigned mn = 0xffffffffu;
+    long long count = 0;
+    int ormask = 0;
+    bool big = false;
+    RefWalker w;
+    w.cov = args.cov;
+    w.ref_ent = args.ref_ent + begin;
+    w.n = n_refs;
+    w.rev = rev;
+
+    // one window of the profile starting at position p = (values v0,v1,v2): statistics.py:72-90
+    auto window = [&](int p, int v0, int v1, int v2) {
+        const int f = p % 3;
+        ormask |= v0 | v1 | v2;
+        if (f == 0) mn = min(mn, (unsigned)v0 + (unsigned)v1 + (unsigned)v2);
+        if ((v0 | v1 | v2) == 0) return;
+        // '+'-oriented triple (a,b,c): the profile of a '-' ORF runs against the plane
+        const int a = rev ? v2 : v0, b = v1, c = rev ? v0 : v2;
+        double re, im;
+        if ((b | c) == 0) { re = 1.0; im = 0.0; }
+        else if ((a | c) == 0) { re = -0.5; im = 0.5; }
+        else if ((a | b) == 0) { re = -0.5; im = -0.5; }
+        else if (a == b && b == c) { re = 0.0; im = 0.0; }
+        else {
+            const double dA = (double)(2ll * a - b - c), dB = (double)((long long)b - c);
+            const double r = rsqrt(fma(dA, dA, 3.0 * dB * dB));
+            re = dA * r;
+            im = dB * r;
+        }
+        const bool uniform = a == b && b == c;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (q == f) { K[q] += 1u; U[q] += uniform ? 1u : 0u; RE[q] += re; IM[q] += im; }
+    };
+
+    int P = 0;                           // profile offset of the current ref
+    for (int j = 0; j < n_refs; ++j) {
+        const uint64_t ent = __ldg(args.ref_ent + begin + j);
+        const int len = (int)(ent & kLenMask);
+        if ((ent >> kLenBits) != kZeroOff) {
+            const AtomSummary* s = args.summaries + __ldg(args.ref_atom + begin + j);
+            const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(s));          // K[0..2], U[0]
+            const uint2 q1 = __ldg(reinterpret_cast<const uint2*>(s) + 2);      // U[1], U[2]
+            const unsigned sK[3] = {q0.x, q0.y, q0.z}, sU[3] = {q0.w, q1.x, q1.y};
+            double sre[3], sim[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { sre[q] = __ldg(&s->re[q]); sim[q] = __ldg(&s->im[q]); }
+            const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(&s->mn[0]));  // mn[0..2], flags
+            const unsigned smn[3] = {q2.x, q2.y, q2.z};
+            big |= (q2.w & 1u) != 0;
+            count += __ldg(&s->count);
+            // local frame fl (window start offset inside the atom, mod 3) -> profile frame f:
+            //   '+': f = (fl + P) mod 3          '-': f = (len + P - fl) mod 3
+            const int base = rev ? (len + P) % 3 : P % 3;
+#pragma unroll
+            for (int fl = 0; fl < 3; ++fl) {
+                const int f = rev ? (base - fl + 3) % 3 : (base + fl) % 3;
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    if (q == f) { K[q] += sK[fl]; U[q] += sU[fl]; RE[q] += sre[fl]; IM[q] += sim[fl]; }
+                if (f == 0) mn = min(mn, smn[fl]);
+            }
+        }
+        else if (len >= 3 && (3 - P % 3) % 3 <= len - 3) {
+            mn = 0;     // a reads-as-zero stretch that holds a whole frame-0 codon
+        }
+        // the two windows that start in this ref and reach into the following ones
+        for (int t = max(len - 2, 0); t < len; ++t) {
+            const int p = P + t;
+            if (p + 2 >= L) break;                                       // incomplete (statistics.py:71)
+            int v0 = 0, v1 = 0, v2 = 0;
+            w.get(j, t, v0);
+            w.get(j, t + 1, v1);
+            w.get(j, t + 2, v2);
+            window(p, v0, v1, v2);
+        }
+        P += len;
+    }
+    // trailing partial codon (common.py:177-179): sum of the last L % 3 values
+    if (L % 3 != 0) {
+        unsigned sum = 0;
+        int Pj = 0, j = 0;
+        // locate the ref holding position L - L % 3 by walking from the start of the last refs
+        int p = L - L % 3;
+        Pj = 0;
+        for (j = 0; j < n_refs; ++j) {
+            const int len = (int)(__ldg(args.ref_ent + begin + j) & kLenMask);
+            if (p < Pj + len) break;
+            Pj += len;
+        }
+        for (int k = 0; k < L % 3; ++k) {
+            int v = 0;
+            w.get(j, p - Pj + k, v);
+            sum += (unsigned)v;
+            ormask |= v;
+        }
+        mn = min(mn, sum);
+    }
+    big |= (ormask >> kBigShift) != 0;
+    if (big) {
+        args.fallback[atomicAdd(args.n_fallback, 1u)] = orf;
+        return;
+    }
+
+    // ---- epilogue: statistics.py:92-115 + detect_orfs.py:278-299 ----
+    const int n_codons = L / 3 > 1 ? L / 3 : 1;                          // detect_orfs.py:281
+    double s3[3];
+    double coh = 0.0;
+    int valid = -1;
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+        if (K[f] == 0) { s3[f] = kNaN; coh = 0.0; valid = 0; continue; }   // statistics.py:94-95
+        const double im = kSqrt3 * IM[f];
+        const double s = (RE[f] * RE[f] + im * im) / ((double)K[f] * (double)(K[f] - U[f]));   // 0/0 -> NaN never wins
+        s3[f] = s;
+        if (s > coh) { coh = s; valid = (int)K[f]; }                     // statistics.py:109-111
+        if (valid == -1) valid = (int)K[f];                              // statistics.py:112-113
+    }
+    const double score = sqrt(coh);                                      // statistics.py:115
+    const double ratio = (double)valid / (double)n_codons;               // detect_orfs.py:285
+    const double density = (double)count / (double)n_codons;             // detect_orfs.py:287
+    const unsigned min_codon = L == 0 ? 0u : mn;
+    const bool ok = score >= args.prm.phase_score_cutoff && (double)valid >= args.prm.min_valid_codons &&
+                    (L == 0 || (double)min_codon >= args.prm.min_reads_per_codon) &&
+                    ratio >= args.prm.min_valid_codons_ratio && density >= args.prm.min_density_over_orf;
+    const long long k_out = (long long)orf - args.orf_lo;
+    args.out.score[k_out] = score;
+    args.out.valid[k_out] = valid;
+    args.out.count[k_out] = count;
+    args.out.length[k_out] = L;
+    if (args.out.min_codon) args.out.min_codon[k_out] = (int32_t)min_codon;
+    if (args.out.status) args.out.status[k_out] = ok ? 1 : 0;
+    if (args.out.frame_K) {
+        args.out.frame_K[3 * k_out + 0] = (int)K[0];
+        args.out.frame_K[3 * k_out + 1] = (int)K[1];
+        args.out.frame_K[3 * k_out + 2] = (int)K[2];
+    }
+    if (args.out.frame_s) {
+        args.out.frame_s[3 * k_out + 0] = s3[0];
+        args.out.frame_s[3 * k_out + 1] = s3[1];
+        args.out.frame_s[3 * k_out + 2] = s3[2];
+    }
+}
+
 // ---- K4 -------------------------------------------------------------------------------------
 struct GatherArgs {
     const int32_t* cov;
@@ -886,6 +1245,9 @@ struct BinArgs {
     unsigned long long* len_counts;  // RT_LEN_TABLE
 };
 
+#ifndef RT_BIN_BATCH
+#define RT_BIN_BATCH 4
+#endif
 constexpr int kBinThreads = 256;
 constexpr int kBinReadsPerThread = 8;
 constexpr int kLenHist = 512;   // read lengths below this are histogrammed in shared memory
@@ -919,7 +1281,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
     // per-thread 4-bit counters of categories RT_ST_QCFAIL..RT_ST_BADREF (<= 8 reads per thread)
     unsigned packed = 0;
     unsigned long long len_packed = 0;
-    constexpr int kBatch = 4;     // reads per thread whose columns are in flight together
+    constexpr int kBatch = RT_BIN_BATCH;     // reads per thread whose columns are in flight together
 #pragma unroll 1
     for (int it0 = 0; it0 < kBinReadsPerThread; it0 += kBatch) {
         // ---- all column loads of the batch first (7 x kBatch independent, coalesced loads) ----
@@ -1048,8 +1410,17 @@ __global__ void __launch_bounds__(256) clear_touched_kernel(int32_t* cov, const 
     const unsigned long long n = *n_touched;
     int4* sectors = reinterpret_cast<int4*>(cov);
     const int4 z = make_int4(0, 0, 0, 0);
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {       // four independent list loads in flight
+        const unsigned long long s0 = touched[i], s1 = touched[i + stride], s2 = touched[i + 2 * stride],
+                                 s3 = touched[i + 3 * stride];
+        sectors[2 * s0] = z; sectors[2 * s0 + 1] = z;
+        sectors[2 * s1] = z; sectors[2 * s1 + 1] = z;
+        sectors[2 * s2] = z; sectors[2 * s2 + 1] = z;
+        sectors[2 * s3] = z; sectors[2 * s3 + 1] = z;
+    }
+    for (; i < n; i += stride) {
         const unsigned long long sec = touched[i];
         sectors[2 * sec] = z;
         sectors[2 * sec + 1] = z;
