@@ -1083,9 +1083,10 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
             double sre[3], sim[3];
 #pragma unroll
             for (int q = 0; q < 3; ++q) { sre[q] = __ldg(&s->re[q]); sim[q] = __ldg(&s->im[q]); }
-            const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(&s->mn[0]));  // mn[0..2], flags
-            const unsigned smn[3] = {q2.x, q2.y, q2.z};
-            big |= (q2.w & 1u) != 0;
+            const uint2 q2 = __ldg(reinterpret_cast<const uint2*>(&s->mn[0]));  // mn[0], mn[1]   (byte offset 72)
+            const uint2 q3 = __ldg(reinterpret_cast<const uint2*>(&s->mn[2]));  // mn[2], flags
+            const unsigned smn[3] = {q2.x, q2.y, q3.x};
+            big |= (q3.y & 1u) != 0;
             count += __ldg(&s->count);
             // local frame fl (window start offset inside the atom, mod 3) -> profile frame f:
             //   '+': f = (fl + P) mod 3          '-': f = (len + P - fl) mod 3
