@@ -18,7 +18,7 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.environ.get("LINE_PROFILE_SO", os.path.join(root, "ribotricer_b200", "libribotricer_b200.so"))
 with tempfile.TemporaryDirectory() as tmp:
     subprocess.check_call(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL)
-    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+    cubin = max((f for f in os.listdir(tmp) if f.endswith(".cubin")), key=lambda f: os.path.getsize(os.path.join(tmp, f)))
     dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
 # per-function list of (line, sass text)
 lines, cur, infn = [], None, False

@@ -1022,15 +1022,27 @@ struct RefWalker {
     }
 };
 
+// kGL lanes per ORF, one lane per atom ref (ORFs with more refs loop): the dependent loads of the
+// refs (entry -> summary -> seam values) run side by side instead of one after the other.
+constexpr int kGL = 4;
+
 __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs args) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= args.n_list) return;
-    const int orf = __ldg(args.list + i);
-    const uint64_t desc = __ldg(args.orf_refs_desc + orf);
-    const uint64_t begin = desc & kBeginMask;
-    const int n_refs = (int)((desc >> 40) & kMaxEntriesPerOrf);
-    const bool rev = (desc >> 63) != 0;
-    const int L = __ldg(args.orf_len + orf);
+    const int lane = threadIdx.x & 31;
+    const int q = lane % kGL;                 // lane within the group
+    const int gb = lane - q;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kGL;
+    const bool active = i < args.n_list;
+    int orf = 0, L = 0, n_refs = 0;
+    uint64_t begin = 0;
+    bool rev = false;
+    if (active) {
+        orf = __ldg(args.list + i);
+        const uint64_t desc = __ldg(args.orf_refs_desc + orf);
+        begin = desc & kBeginMask;
+        n_refs = (int)((desc >> 40) & kMaxEntriesPerOrf);
+        rev = (desc >> 63) != 0;
+        L = __ldg(args.orf_len + orf);
+    }
     const double kSqrt3 = 1.7320508075688772;
     const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
 
@@ -1067,14 +1079,28 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
         }
         const bool uniform = a == b && b == c;
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
-            if (q == f) { K[q] += 1u; U[q] += uniform ? 1u : 0u; RE[q] += re; IM[q] += im; }
+        for (int x = 0; x < 3; ++x)
+            if (x == f) { K[x] += 1u; U[x] += uniform ? 1u : 0u; RE[x] += re; IM[x] += im; }
     };
 
-    int P = 0;                           // profile offset of the current ref
-    for (int j = 0; j < n_refs; ++j) {
-        const uint64_t ent = __ldg(args.ref_ent + begin + j);
+    const int max_refs = __reduce_max_sync(kFull, n_refs);
+    int carry = 0;                        // profile offset of the first ref of this chunk
+    for (int j0 = 0; j0 < max_refs; j0 += kGL) {
+        const int j = j0 + q;
+        const bool have = j < n_refs;
+        uint64_t ent = 0;
+        if (have) ent = __ldg(args.ref_ent + begin + j);
         const int len = (int)(ent & kLenMask);
+        // exclusive prefix of the ref lengths inside the group
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < kGL; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, incl, o);
+            if (q >= o) incl += t;
+        }
+        const int P = carry + incl - len;
+        carry += __shfl_sync(kFull, incl, gb + kGL - 1);
+        if (!have) continue;
         if ((ent >> kLenBits) != kZeroOff) {
             const AtomSummary* s = args.summaries + __ldg(args.ref_atom + begin + j);
             const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(s));          // K[0..2], U[0]
@@ -1082,7 +1108,7 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
             const unsigned sK[3] = {q0.x, q0.y, q0.z}, sU[3] = {q0.w, q1.x, q1.y};
             double sre[3], sim[3];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { sre[q] = __ldg(&s->re[q]); sim[q] = __ldg(&s->im[q]); }
+            for (int x = 0; x < 3; ++x) { sre[x] = __ldg(&s->re[x]); sim[x] = __ldg(&s->im[x]); }
             const uint2 q2 = __ldg(reinterpret_cast<const uint2*>(&s->mn[0]));  // mn[0], mn[1]   (byte offset 72)
             const uint2 q3 = __ldg(reinterpret_cast<const uint2*>(&s->mn[2]));  // mn[2], flags
             const unsigned smn[3] = {q2.x, q2.y, q3.x};
@@ -1095,12 +1121,11 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
             for (int fl = 0; fl < 3; ++fl) {
                 const int f = rev ? (base - fl + 3) % 3 : (base + fl) % 3;
 #pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    if (q == f) { K[q] += sK[fl]; U[q] += sU[fl]; RE[q] += sre[fl]; IM[q] += sim[fl]; }
+                for (int x = 0; x < 3; ++x)
+                    if (x == f) { K[x] += sK[fl]; U[x] += sU[fl]; RE[x] += sre[fl]; IM[x] += sim[fl]; }
                 if (f == 0) mn = min(mn, smn[fl]);
             }
-        }
-        else if (len >= 3 && (3 - P % 3) % 3 <= len - 3) {
+        } else if (len >= 3 && (3 - P % 3) % 3 <= len - 3) {
             mn = 0;     // a reads-as-zero stretch that holds a whole frame-0 codon
         }
         // the two windows that start in this ref and reach into the following ones
@@ -1113,28 +1138,42 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
             w.get(j, t + 2, v2);
             window(p, v0, v1, v2);
         }
-        P += len;
     }
-    // trailing partial codon (common.py:177-179): sum of the last L % 3 values
-    if (L % 3 != 0) {
+    // trailing partial codon (common.py:177-179): sum of the last L % 3 values -- they lie in the last refs
+    if (active && q == 0 && L % 3 != 0) {
         unsigned sum = 0;
-        int Pj = 0, j = 0;
-        // locate the ref holding position L - L % 3 by walking from the start of the last refs
-        int p = L - L % 3;
-        Pj = 0;
-        for (j = 0; j < n_refs; ++j) {
-            const int len = (int)(__ldg(args.ref_ent + begin + j) & kLenMask);
-            if (p < Pj + len) break;
-            Pj += len;
+        int jj = n_refs - 1, back = L % 3;        // walk back from the end of the profile
+        int start_in = 0;
+        for (;;) {
+            const int len = (int)(__ldg(args.ref_ent + begin + jj) & kLenMask);
+            if (len >= back) { start_in = len - back; break; }
+            back -= len;
+            --jj;
         }
         for (int k = 0; k < L % 3; ++k) {
             int v = 0;
-            w.get(j, p - Pj + k, v);
+            w.get(jj, start_in + k, v);
             sum += (unsigned)v;
             ormask |= v;
         }
         mn = min(mn, sum);
     }
+    // ---- group reduction ----
+#pragma unroll
+    for (int o = kGL / 2; o > 0; o >>= 1) {
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            K[x] += __shfl_xor_sync(kFull, K[x], o);
+            U[x] += __shfl_xor_sync(kFull, U[x], o);
+            RE[x] += __shfl_xor_sync(kFull, RE[x], o);
+            IM[x] += __shfl_xor_sync(kFull, IM[x], o);
+        }
+        mn = min(mn, __shfl_xor_sync(kFull, mn, o));
+        count += __shfl_xor_sync(kFull, count, o);
+        ormask |= __shfl_xor_sync(kFull, ormask, o);
+        big |= __shfl_xor_sync(kFull, (int)big, o) != 0;
+    }
+    if (!active || q != 0) return;
     big |= (ormask >> kBigShift) != 0;
     if (big) {
         args.fallback[atomicAdd(args.n_fallback, 1u)] = orf;
