@@ -796,7 +796,7 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
         ca.n_fallback = a.n_fallback;
         ca.prm = *params;
         ca.out = *d_out;
-        rt::score_from_atoms_kernel<<<(unsigned)((ca.n_list * rt::kGL + 255) / 256), 256, 0, st>>>(ca);
+        rt::score_from_atoms_kernel<<<(unsigned)((ca.n_list + 255) / 256), 256, 0, st>>>(ca);
         ctx->launches++;
         // ORFs holding counts >= 2^20: redone by the generic kernel (normally none)
         a.list = plan->d_fallback;

@@ -838,15 +838,18 @@ score_orfs_packed_kernel(const ScoreArgs args) {
 // a local frame differs (see score_from_atoms_kernel).
 constexpr int kAtomMaxNt = 3045;       // <= 127 rounds of 8 lanes (7-bit packed per-lane fields)
 
-struct AtomSummary {                   // 96 bytes
-    unsigned K[3];                     // kept (non-all-zero) windows by local frame
-    unsigned U[3];                     // uniform windows among them (count in K only)
-    double re[3];                      // sum of unit vectors, '+' orientation
+struct AtomSummary {                   // 96 bytes, six 16-byte chunks
+    double re[3];                      // sum of unit vectors by local frame, '+' orientation
     double im[3];                      //   (imaginary part without its sqrt3 factor)
+    int edge[4];                       // first two and last two values of the atom, ascending slots
+                                       //   (edge[1] = edge[2] = 0 for a one-value atom)
     unsigned mn[3];                    // min window sum by local frame (0xffffffff: no window)
+    unsigned count;                    // sum of all values of the atom
+    unsigned short K[3];               // kept (non-all-zero) windows by local frame
+    unsigned short U[3];               // uniform windows among them (count in K only)
     unsigned flags;                    // bit 0: a value >= 2^kBigShift (32-bit sums may have wrapped)
-    long long count;                   // sum of all values of the atom
 };
+static_assert(sizeof(AtomSummary) == 96, "AtomSummary layout");
 
 struct AtomArgs {
     const int32_t* cov;
@@ -961,14 +964,20 @@ atom_summary_kernel(const AtomArgs args) {
             const int na0 = a1_0 & 1023, nb0 = (a1_0 >> 10) & 1023, nc0 = a1_0 >> 20, ng0 = a2_0 & 1023, nu0 = a2_0 >> 10;
             const int na1 = a1_1 & 1023, nb1 = (a1_1 >> 10) & 1023, nc1 = a1_1 >> 20, ng1 = a2_1 & 1023, nu1 = a2_1 >> 10;
             const int na2 = a1_2 & 1023, nb2 = (a1_2 >> 10) & 1023, nc2 = a1_2 >> 20, ng2 = a2_2 & 1023, nu2 = a2_2 >> 10;
-            s.K[0] = na0 + nb0 + nc0 + ng0 + nu0; s.K[1] = na1 + nb1 + nc1 + ng1 + nu1; s.K[2] = na2 + nb2 + nc2 + ng2 + nu2;
-            s.U[0] = nu0; s.U[1] = nu1; s.U[2] = nu2;
+            s.K[0] = (unsigned short)(na0 + nb0 + nc0 + ng0 + nu0);
+            s.K[1] = (unsigned short)(na1 + nb1 + nc1 + ng1 + nu1);
+            s.K[2] = (unsigned short)(na2 + nb2 + nc2 + ng2 + nu2);
+            s.U[0] = (unsigned short)nu0; s.U[1] = (unsigned short)nu1; s.U[2] = (unsigned short)nu2;
             s.re[0] = re0 + 0.5 * (double)(2 * na0 - nb0 - nc0); s.im[0] = im0 + 0.5 * (double)(nb0 - nc0);
             s.re[1] = re1 + 0.5 * (double)(2 * na1 - nb1 - nc1); s.im[1] = im1 + 0.5 * (double)(nb1 - nc1);
             s.re[2] = re2 + 0.5 * (double)(2 * na2 - nb2 - nc2); s.im[2] = im2 + 0.5 * (double)(nb2 - nc2);
             s.mn[0] = mn0; s.mn[1] = mn1; s.mn[2] = mn2;
             s.flags = (ormask >> kBigShift) != 0 ? 1u : 0u;
-            s.count = (long long)count;
+            s.count = count;
+            s.edge[0] = ld_cov(src);
+            s.edge[1] = len >= 2 ? ld_cov(src + 1) : 0;
+            s.edge[2] = len >= 2 ? ld_cov(src + len - 2) : 0;
+            s.edge[3] = ld_cov(src + len - 1);
             args.out[atom] = s;
         }
         __syncwarp();
@@ -991,58 +1000,19 @@ struct ComposeArgs {
     rt_score_out out;
 };
 
-// Values at profile positions of an ORF addressed as (ref index, offset inside the ref).
-struct RefWalker {
-    const int32_t* cov;
-    const uint64_t* ref_ent;
-    int n;
-    bool rev;
-    int j = -1, len = 0;
-    long long off = 0;
-    bool zero = true;
-    __device__ __forceinline__ void seek(int jj) {
-        j = jj;
-        const uint64_t ent = __ldg(ref_ent + jj);
-        len = (int)(ent & kLenMask);
-        const uint64_t o = ent >> kLenBits;
-        zero = o == kZeroOff;
-        off = (long long)o;
-    }
-    // value at offset t of ref jj, moving on to the following refs when t runs past the end;
-    // returns false past the end of the ORF
-    __device__ __forceinline__ bool get(int jj, int t, int& v) {
-        if (jj != j) seek(jj);
-        while (t >= len) {
-            if (j + 1 >= n) return false;
-            t -= len;
-            seek(j + 1);
-        }
-        v = zero ? 0 : ld_cov(cov + (rev ? off + len - 1 - t : off + t));
-        return true;
-    }
-};
-
-// kGL lanes per ORF, one lane per atom ref (ORFs with more refs loop): the dependent loads of the
-// refs (entry -> summary -> seam values) run side by side instead of one after the other.
-constexpr int kGL = 4;
-
+// One thread per ORF streams the summaries of its atoms: no raw coverage is read any more.  The
+// windows that straddle atom seams are rebuilt from the edge values kept in the summaries: while
+// the profile streams by, (x, y) are its last two values, and every value that enters a new atom
+// completes one window that is not interior to any atom.
 __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs args) {
-    const int lane = threadIdx.x & 31;
-    const int q = lane % kGL;                 // lane within the group
-    const int gb = lane - q;
-    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kGL;
-    const bool active = i < args.n_list;
-    int orf = 0, L = 0, n_refs = 0;
-    uint64_t begin = 0;
-    bool rev = false;
-    if (active) {
-        orf = __ldg(args.list + i);
-        const uint64_t desc = __ldg(args.orf_refs_desc + orf);
-        begin = desc & kBeginMask;
-        n_refs = (int)((desc >> 40) & kMaxEntriesPerOrf);
-        rev = (desc >> 63) != 0;
-        L = __ldg(args.orf_len + orf);
-    }
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= args.n_list) return;
+    const int orf = __ldg(args.list + i);
+    const uint64_t desc = __ldg(args.orf_refs_desc + orf);
+    const uint64_t begin = desc & kBeginMask;
+    const int n_refs = (int)((desc >> 40) & kMaxEntriesPerOrf);
+    const bool rev = (desc >> 63) != 0;
+    const int L = __ldg(args.orf_len + orf);
     const double kSqrt3 = 1.7320508075688772;
     const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
 
@@ -1052,13 +1022,8 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
     long long count = 0;
     int ormask = 0;
     bool big = false;
-    RefWalker w;
-    w.cov = args.cov;
-    w.ref_ent = args.ref_ent + begin;
-    w.n = n_refs;
-    w.rev = rev;
 
-    // one window of the profile starting at position p = (values v0,v1,v2): statistics.py:72-90
+    // one seam window of the profile starting at position p = (values v0,v1,v2): statistics.py:72-90
     auto window = [&](int p, int v0, int v1, int v2) {
         const int f = p % 3;
         ormask |= v0 | v1 | v2;
@@ -1079,41 +1044,38 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
         }
         const bool uniform = a == b && b == c;
 #pragma unroll
-        for (int x = 0; x < 3; ++x)
-            if (x == f) { K[x] += 1u; U[x] += uniform ? 1u : 0u; RE[x] += re; IM[x] += im; }
+        for (int q = 0; q < 3; ++q)
+            if (q == f) { K[q] += 1u; U[q] += uniform ? 1u : 0u; RE[q] += re; IM[q] += im; }
     };
 
-    const int max_refs = __reduce_max_sync(kFull, n_refs);
-    int carry = 0;                        // profile offset of the first ref of this chunk
-    for (int j0 = 0; j0 < max_refs; j0 += kGL) {
-        const int j = j0 + q;
-        const bool have = j < n_refs;
-        uint64_t ent = 0;
-        if (have) ent = __ldg(args.ref_ent + begin + j);
+    int P = 0;             // profile offset of the current ref
+    int x = 0, y = 0;      // profile values at P - 2 and P - 1
+    uint64_t ent = n_refs ? __ldg(args.ref_ent + begin) : 0;
+    unsigned atom = n_refs ? __ldg(args.ref_atom + begin) : 0;
+    for (int j = 0; j < n_refs; ++j) {
         const int len = (int)(ent & kLenMask);
-        // exclusive prefix of the ref lengths inside the group
-        int incl = len;
-#pragma unroll
-        for (int o = 1; o < kGL; o <<= 1) {
-            const int t = __shfl_up_sync(kFull, incl, o);
-            if (q >= o) incl += t;
+        const bool zero = (ent >> kLenBits) == kZeroOff;
+        const AtomSummary* s = args.summaries + atom;
+        if (j + 1 < n_refs) {     // next ref's entry and atom id while this summary is in flight
+            ent = __ldg(args.ref_ent + begin + j + 1);
+            atom = __ldg(args.ref_atom + begin + j + 1);
         }
-        const int P = carry + incl - len;
-        carry += __shfl_sync(kFull, incl, gb + kGL - 1);
-        if (!have) continue;
-        if ((ent >> kLenBits) != kZeroOff) {
-            const AtomSummary* s = args.summaries + __ldg(args.ref_atom + begin + j);
-            const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(s));          // K[0..2], U[0]
-            const uint2 q1 = __ldg(reinterpret_cast<const uint2*>(s) + 2);      // U[1], U[2]
-            const unsigned sK[3] = {q0.x, q0.y, q0.z}, sU[3] = {q0.w, q1.x, q1.y};
-            double sre[3], sim[3];
-#pragma unroll
-            for (int x = 0; x < 3; ++x) { sre[x] = __ldg(&s->re[x]); sim[x] = __ldg(&s->im[x]); }
-            const uint2 q2 = __ldg(reinterpret_cast<const uint2*>(&s->mn[0]));  // mn[0], mn[1]   (byte offset 72)
-            const uint2 q3 = __ldg(reinterpret_cast<const uint2*>(&s->mn[2]));  // mn[2], flags
-            const unsigned smn[3] = {q2.x, q2.y, q3.x};
-            big |= (q3.y & 1u) != 0;
-            count += __ldg(&s->count);
+        int a0 = 0, a1 = 0, z0 = 0, z1 = 0;    // first two / last two values of the ref in profile order
+        if (!zero) {
+            const double2 r01 = __ldg(reinterpret_cast<const double2*>(s));          // re[0], re[1]
+            const double2 r2i0 = __ldg(reinterpret_cast<const double2*>(s) + 1);     // re[2], im[0]
+            const double2 i12 = __ldg(reinterpret_cast<const double2*>(s) + 2);      // im[1], im[2]
+            const int4 edge = __ldg(reinterpret_cast<const int4*>(s) + 3);
+            const uint4 mc = __ldg(reinterpret_cast<const uint4*>(s) + 4);           // mn[0..2], count
+            const uint4 ku = __ldg(reinterpret_cast<const uint4*>(s) + 5);           // K, U (u16 x 6), flags
+            const double sre[3] = {r01.x, r01.y, r2i0.x}, sim[3] = {r2i0.y, i12.x, i12.y};
+            const unsigned smn[3] = {mc.x, mc.y, mc.z};
+            const unsigned sK[3] = {ku.x & 0xffffu, ku.x >> 16, ku.y & 0xffffu};
+            const unsigned sU[3] = {ku.y >> 16, ku.z & 0xffffu, ku.z >> 16};
+            big |= (ku.w & 1u) != 0;
+            count += mc.w;
+            if (rev) { a0 = edge.w; a1 = edge.z; z0 = edge.y; z1 = edge.x; }
+            else { a0 = edge.x; a1 = edge.y; z0 = edge.z; z1 = edge.w; }
             // local frame fl (window start offset inside the atom, mod 3) -> profile frame f:
             //   '+': f = (fl + P) mod 3          '-': f = (len + P - fl) mod 3
             const int base = rev ? (len + P) % 3 : P % 3;
@@ -1121,59 +1083,28 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
             for (int fl = 0; fl < 3; ++fl) {
                 const int f = rev ? (base - fl + 3) % 3 : (base + fl) % 3;
 #pragma unroll
-                for (int x = 0; x < 3; ++x)
-                    if (x == f) { K[x] += sK[fl]; U[x] += sU[fl]; RE[x] += sre[fl]; IM[x] += sim[fl]; }
+                for (int q = 0; q < 3; ++q)
+                    if (q == f) { K[q] += sK[fl]; U[q] += sU[fl]; RE[q] += sre[fl]; IM[q] += sim[fl]; }
                 if (f == 0) mn = min(mn, smn[fl]);
             }
         } else if (len >= 3 && (3 - P % 3) % 3 <= len - 3) {
             mn = 0;     // a reads-as-zero stretch that holds a whole frame-0 codon
         }
-        // the two windows that start in this ref and reach into the following ones
-        for (int t = max(len - 2, 0); t < len; ++t) {
-            const int p = P + t;
-            if (p + 2 >= L) break;                                       // incomplete (statistics.py:71)
-            int v0 = 0, v1 = 0, v2 = 0;
-            w.get(j, t, v0);
-            w.get(j, t + 1, v1);
-            w.get(j, t + 2, v2);
-            window(p, v0, v1, v2);
+        // seam windows: the ones that END on the first and on the second value of this ref
+        if (P >= 2) window(P - 2, x, y, a0);
+        if (len >= 2) {
+            if (P >= 1) window(P - 1, y, a0, a1);
+            x = z0;
+            y = z1;
+        } else {
+            x = y;
+            y = a0;
         }
+        P += len;
     }
-    // trailing partial codon (common.py:177-179): sum of the last L % 3 values -- they lie in the last refs
-    if (active && q == 0 && L % 3 != 0) {
-        unsigned sum = 0;
-        int jj = n_refs - 1, back = L % 3;        // walk back from the end of the profile
-        int start_in = 0;
-        for (;;) {
-            const int len = (int)(__ldg(args.ref_ent + begin + jj) & kLenMask);
-            if (len >= back) { start_in = len - back; break; }
-            back -= len;
-            --jj;
-        }
-        for (int k = 0; k < L % 3; ++k) {
-            int v = 0;
-            w.get(jj, start_in + k, v);
-            sum += (unsigned)v;
-            ormask |= v;
-        }
-        mn = min(mn, sum);
-    }
-    // ---- group reduction ----
-#pragma unroll
-    for (int o = kGL / 2; o > 0; o >>= 1) {
-#pragma unroll
-        for (int x = 0; x < 3; ++x) {
-            K[x] += __shfl_xor_sync(kFull, K[x], o);
-            U[x] += __shfl_xor_sync(kFull, U[x], o);
-            RE[x] += __shfl_xor_sync(kFull, RE[x], o);
-            IM[x] += __shfl_xor_sync(kFull, IM[x], o);
-        }
-        mn = min(mn, __shfl_xor_sync(kFull, mn, o));
-        count += __shfl_xor_sync(kFull, count, o);
-        ormask |= __shfl_xor_sync(kFull, ormask, o);
-        big |= __shfl_xor_sync(kFull, (int)big, o) != 0;
-    }
-    if (!active || q != 0) return;
+    // trailing partial codon (common.py:177-179): the last L % 3 values are x, y
+    if (L % 3 == 1) { mn = min(mn, (unsigned)y); ormask |= y; }
+    else if (L % 3 == 2) { mn = min(mn, (unsigned)x + (unsigned)y); ormask |= x | y; }
     big |= (ormask >> kBigShift) != 0;
     if (big) {
         args.fallback[atomicAdd(args.n_fallback, 1u)] = orf;
