@@ -778,7 +778,11 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
             aa.n_list = plan->n_atom_list;
             aa.work_counter = ctx->d_work_counter + 0;
             aa.out = ctx->d_summaries;
-            rt::atom_summary_kernel<8><<<persistent_grid(ctx, rt::atom_summary_kernel<8>, (plan->n_atom_list + 3) / 4), threads, 0, st>>>(aa);
+            // the per-frame minima only matter for --min_reads_per_codon > 0 or when the caller asks for min_codon
+            const bool want_min = d_out->min_codon != nullptr || params->min_reads_per_codon > 0.0;
+            const unsigned grid = persistent_grid(ctx, rt::atom_summary_kernel<8, true>, (plan->n_atom_list + 3) / 4);
+            if (want_min) rt::atom_summary_kernel<8, true><<<grid, threads, 0, st>>>(aa);
+            else rt::atom_summary_kernel<8, false><<<grid, threads, 0, st>>>(aa);
             ctx->launches++;
         }
         // phase B: one thread per ORF composes its atoms
@@ -857,7 +861,7 @@ int rt_score_host(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf
     d.frame_s = h_out->frame_s ? reinterpret_cast<double*>(p) : nullptr; p += 24 * n;
     d.valid = reinterpret_cast<int32_t*>(p); p += 4 * n;
     d.length = reinterpret_cast<int32_t*>(p); p += 4 * n;
-    d.min_codon = reinterpret_cast<int32_t*>(p); p += 4 * n;
+    d.min_codon = h_out->min_codon ? reinterpret_cast<int32_t*>(p) : nullptr; p += 4 * n;
     d.frame_K = h_out->frame_K ? reinterpret_cast<int32_t*>(p) : nullptr; p += 12 * n;
     d.status = reinterpret_cast<uint8_t*>(p);
     int rc = rt_score(ctx, d_cov, orf_lo, orf_hi, params, &d, nullptr);

@@ -860,7 +860,7 @@ struct AtomArgs {
     AtomSummary* out;                  // indexed by atom id
 };
 
-template <int LPO>
+template <int LPO, bool WantMin>
 __global__ void __launch_bounds__(kScoreWarps * 32, 4)
 atom_summary_kernel(const AtomArgs args) {
     constexpr int G = 32 / LPO;
@@ -894,33 +894,34 @@ atom_summary_kernel(const AtomArgs args) {
         unsigned cnt32 = 0, mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu;
         int ormask = 0;
         const int rounds = __reduce_max_sync(kFull, ((len + 2) / 3 + LPO - 1) / LPO);
-        auto load3 = [&](int P, int& v0, int& v1, int& v2) {
-            const int p = P + 3 * sl;
-            v0 = v1 = v2 = 0;
-            if (__all_sync(kFull, P >= len || P + RNT <= len)) {
-                if (P < len) { v0 = ld_cov(src + p); v1 = ld_cov(src + p + 1); v2 = ld_cov(src + p + 2); }
-            } else {
-                if (p < len) v0 = ld_cov(src + p);
-                if (p + 1 < len) v1 = ld_cov(src + p + 1);
-                if (p + 2 < len) v2 = ld_cov(src + p + 2);
-            }
+        // lane's three values of round r sit at src + 3 sl + r RNT; `left` = values from there to the atom's end
+        const int32_t* ptr = src + 3 * sl;
+        int left = len - 3 * sl;
+        auto load3 = [&](int& v0, int& v1, int& v2) {
+            v0 = left > 0 ? ld_cov(ptr) : 0;
+            v1 = left > 1 ? ld_cov(ptr + 1) : 0;
+            v2 = left > 2 ? ld_cov(ptr + 2) : 0;
+            ptr += RNT;
+            left -= RNT;
         };
         int c0, c1, c2;
-        load3(0, c0, c1, c2);
-        for (int r = 0; r < rounds; ++r) {
+        load3(c0, c1, c2);
+        int p = 3 * sl;
+        for (int r = 0; r < rounds; ++r, p += RNT) {
             int n0, n1, n2;
-            load3((r + 1) * RNT, n0, n1, n2);
+            load3(n0, n1, n2);
             const int v3 = __shfl_sync(kFull, sl == 0 ? n0 : c0, nbr);
             const int v4 = __shfl_sync(kFull, sl == 0 ? n1 : c1, nbr);
-            const int p = 3 * (r * LPO + sl);
             if (p < len) {
                 cnt32 += (unsigned)c0 + (unsigned)c1 + (unsigned)c2;
                 ormask |= c0 | c1 | c2;
                 if (p + 4 < len) {                               // all three windows lie inside the atom
-                    const unsigned s0 = (unsigned)c0 + (unsigned)c1 + (unsigned)c2;
-                    const unsigned s1 = (unsigned)c1 + (unsigned)c2 + (unsigned)v3;
-                    const unsigned s2 = (unsigned)c2 + (unsigned)v3 + (unsigned)v4;
-                    mn0 = min(mn0, s0); mn1 = min(mn1, s1); mn2 = min(mn2, s2);
+                    if (WantMin) {
+                        const unsigned s0 = (unsigned)c0 + (unsigned)c1 + (unsigned)c2;
+                        const unsigned s1 = (unsigned)c1 + (unsigned)c2 + (unsigned)v3;
+                        const unsigned s2 = (unsigned)c2 + (unsigned)v3 + (unsigned)v4;
+                        mn0 = min(mn0, s0); mn1 = min(mn1, s1); mn2 = min(mn2, s2);
+                    }
                     if ((c0 | c1 | c2 | v3 | v4) != 0) {
                         const unsigned m5 = min((unsigned)c0, 1u) | (min((unsigned)c1, 1u) << 1) | (min((unsigned)c2, 1u) << 2) |
                                             (min((unsigned)v3, 1u) << 3) | (min((unsigned)v4, 1u) << 4);
@@ -933,8 +934,8 @@ atom_summary_kernel(const AtomArgs args) {
                         }
                     }
                 } else {                                         // ragged end of the atom
-                    if (p + 2 < len) { mn0 = min(mn0, (unsigned)c0 + (unsigned)c1 + (unsigned)c2); classify_codon<0>(c0, c1, c2, f0, dfr); }
-                    if (p + 3 < len) { mn1 = min(mn1, (unsigned)c1 + (unsigned)c2 + (unsigned)v3); classify_codon<1>(c1, c2, v3, f1, dfr); }
+                    if (p + 2 < len) { if (WantMin) mn0 = min(mn0, (unsigned)c0 + (unsigned)c1 + (unsigned)c2); classify_codon<0>(c0, c1, c2, f0, dfr); }
+                    if (p + 3 < len) { if (WantMin) mn1 = min(mn1, (unsigned)c1 + (unsigned)c2 + (unsigned)v3); classify_codon<1>(c1, c2, v3, f1, dfr); }
                 }
             }
             c0 = n0; c1 = n1; c2 = n2;
@@ -947,9 +948,11 @@ atom_summary_kernel(const AtomArgs args) {
         const unsigned count = group_sum_u32<LPO>(cnt32);
 #pragma unroll
         for (int o = LPO / 2; o > 0; o >>= 1) {
-            mn0 = min(mn0, __shfl_xor_sync(kFull, mn0, o));
-            mn1 = min(mn1, __shfl_xor_sync(kFull, mn1, o));
-            mn2 = min(mn2, __shfl_xor_sync(kFull, mn2, o));
+            if (WantMin) {
+                mn0 = min(mn0, __shfl_xor_sync(kFull, mn0, o));
+                mn1 = min(mn1, __shfl_xor_sync(kFull, mn1, o));
+                mn2 = min(mn2, __shfl_xor_sync(kFull, mn2, o));
+            }
             ormask |= __shfl_xor_sync(kFull, ormask, o);
         }
         const bool any_general = __any_sync(kFull, ((a2_0 | a2_1 | a2_2) & 1023u) != 0);

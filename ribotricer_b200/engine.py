@@ -242,12 +242,16 @@ class Engine:
         return dict(zip(_lib.ST_NAMES, stats.tolist())), len_counts
 
     # ---------------------------------------------------------------- K2+K3
-    def new_score_columns(self, n: int, diagnostics: bool = False) -> dict:
+    def new_score_columns(self, n: int, diagnostics: bool = False, min_codon: bool | None = None) -> dict:
+        """Device result columns.  ``min_codon`` (the minimum codon sum, an extra the reference never
+        prints) is only produced on request or with ``diagnostics``."""
         t = self.torch
         d = self.device
         cols = dict(score=t.empty(n, dtype=t.float64, device=d), valid=t.empty(n, dtype=t.int32, device=d),
                     count=t.empty(n, dtype=t.int64, device=d), length=t.empty(n, dtype=t.int32, device=d),
-                    min_codon=t.empty(n, dtype=t.int32, device=d), status=t.empty(n, dtype=t.uint8, device=d))
+                    status=t.empty(n, dtype=t.uint8, device=d))
+        if min_codon or (min_codon is None and diagnostics):
+            cols["min_codon"] = t.empty(n, dtype=t.int32, device=d)
         if diagnostics:
             cols["frame_K"] = t.empty((n, 3), dtype=t.int32, device=d)
             cols["frame_s"] = t.empty((n, 3), dtype=t.float64, device=d)
@@ -263,12 +267,15 @@ class Engine:
                                       C.byref(o), self._stream()))
 
     def score_host(self, cov, lo: int = 0, hi: int | None = None, params: ScoreParams | None = None,
-                   diagnostics: bool = False) -> dict:
-        """Score ORFs [lo, hi) and return HOST numpy columns (D2H inside the C call)."""
+                   diagnostics: bool = False, min_codon: bool | None = None) -> dict:
+        """Score ORFs [lo, hi) and return HOST numpy columns (D2H inside the C call).  ``min_codon``
+        (minimum codon sum, not a reference output) is produced on request or with ``diagnostics``."""
         hi = self.n_orf if hi is None else hi
         n = hi - lo
         out = dict(score=np.empty(n, np.float64), valid=np.empty(n, np.int32), count=np.empty(n, np.int64),
-                   length=np.empty(n, np.int32), min_codon=np.empty(n, np.int32), status=np.empty(n, np.uint8))
+                   length=np.empty(n, np.int32), status=np.empty(n, np.uint8))
+        if min_codon or (min_codon is None and diagnostics):
+            out["min_codon"] = np.empty(n, np.int32)
         if diagnostics:
             out["frame_K"] = np.empty((n, 3), np.int32)
             out["frame_s"] = np.empty((n, 3), np.float64)

@@ -289,12 +289,12 @@ def test_full_config2_properties(engine):
     cov = engine.new_coverage()
     st, lc = engine.new_bin_accumulators()
     engine.bin_reads_device(cov, dreads, "forward", st, lc, sorted_hint=True)
-    one = engine.score_host(cov)
+    one = engine.score_host(cov, min_codon=True)
     stats1 = st.cpu().numpy().copy()
     assert stats1[0] == cfg.n_reads and stats1[6] + stats1[1:6].sum() == cfg.n_reads
     assert int(cov.sum(dtype=t.int64).item()) == int(stats1[6] - stats1[7])      # every valid in-range read is one count
     engine.bin_reads_device(cov, dreads, "forward", st, lc, sorted_hint=True)
-    two = engine.score_host(cov)
+    two = engine.score_host(cov, min_codon=True)
     assert (two["count"] == 2 * one["count"]).all() and (two["min_codon"] == 2 * one["min_codon"]).all()
     assert (two["valid"] == one["valid"]).all() and (two["length"] == one["length"]).all()
     assert np.abs(two["score"] - one["score"]).max() <= 1e-12
