@@ -306,7 +306,7 @@ def test_full_config2_properties(engine):
     engine.bin_reads_device(cov, dreads, "forward", st, lc, sorted_hint=True)
     bounds = engine.shard_bounds(8)
     assert bounds[0] == 0 and bounds[-1] == idx.n_orf and (np.diff(bounds) > 0).all()
-    parts = [engine.score_host(cov, int(bounds[i]), int(bounds[i + 1])) for i in range(8)]
+    parts = [engine.score_host(cov, int(bounds[i]), int(bounds[i + 1]), min_codon=True) for i in range(8)]
     for k in one:
         assert np.array_equal(np.concatenate([p[k] for p in parts]), one[k], equal_nan=True), k
     # sample against the oracle, through the gathered profiles (bit-exact integers, score 1e-9)
