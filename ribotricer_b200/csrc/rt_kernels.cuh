@@ -1223,7 +1223,10 @@ struct BinArgs {
 #define RT_BIN_BATCH 4
 #endif
 constexpr int kBinThreads = 256;
-constexpr int kBinReadsPerThread = 8;
+#ifndef RT_BIN_RPT
+#define RT_BIN_RPT 8
+#endif
+constexpr int kBinReadsPerThread = RT_BIN_RPT;
 constexpr int kLenHist = 512;   // read lengths below this are histogrammed in shared memory
 
 // Category of one read after the cascade of bam.py:77-91: one of RT_ST_QCFAIL .. RT_ST_VALID.
