@@ -356,3 +356,54 @@ def test_sparse_clear(engine):
             assert int(cov.abs().max().item()) == 0
     finally:
         engine.track_touched(False)
+
+
+def test_two_phase_path_agrees_with_scan_path_at_full_size(built):
+    """The default two-phase (atom) path and the scan path (RT_SCORE_PATH=scan) are independent
+    kernels; on the full C2 configuration every integer column must agree, scores within 1e-9, and
+    every ORF whose valid_codons differ must be a frame tie according to the oracle."""
+    import os
+
+    CO = _oracle()
+    from ribotricer_b200 import synth
+    from ribotricer_b200.engine import Engine
+
+    cfg = synth.config("C2")
+    idx = synth.make_index(cfg)
+    results = {}
+    cov = None
+    for path in ("atoms", "scan"):
+        os.environ["RT_SCORE_PATH"] = path
+        try:
+            eng = Engine(0)
+        finally:
+            os.environ.pop("RT_SCORE_PATH", None)
+        eng.set_genome(idx.contig_names, idx.contig_len)
+        eng.set_length_table(synth.TRUE_OFFSETS, None)
+        eng.set_index(**idx.as_dict())
+        if cov is None:
+            dreads = synth.make_reads(cfg, idx, device=eng.device)
+            cov = eng.new_coverage()
+            st, lc = eng.new_bin_accumulators()
+            eng.bin_reads_device(cov, dreads, "forward", st, lc, sorted_hint=True)
+            del dreads
+        results[path] = eng.score_host(cov, diagnostics=True)
+        if path == "scan":
+            keep = eng
+        else:
+            eng.close()
+    a, s = results["atoms"], results["scan"]
+    for k in ("count", "length", "min_codon", "frame_K"):
+        assert np.array_equal(a[k], s[k]), k
+    assert np.abs(a["score"] - s["score"]).max() <= SCORE_TOL
+    diff = np.flatnonzero(a["valid"] != s["valid"])
+    assert len(diff) < 0.001 * idx.n_orf
+    if len(diff):
+        ptr, prof = keep.gather_profiles(cov, diff, a["length"][diff])
+        for j in range(len(diff)):
+            K, s3 = CO.frame_spectra(prof[ptr[j]:ptr[j + 1]])
+            assert CO.tie_mask(K[None, :], s3[None, :])[0], int(diff[j])
+    same = a["valid"] == s["valid"]
+    near = np.abs(a["score"] - 0.428571428571) <= SCORE_TOL
+    assert (a["status"] == s["status"])[same & ~near].all()
+    keep.close()
