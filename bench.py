@@ -352,10 +352,13 @@ def run_ours(args):
         achieved = score_bytes / (score_ms * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of the scoring kernel from the committed ncu capture
         traffic, traffic_src = None, None
+        scan_path = os.environ.get("RT_SCORE_PATH") == "scan"
+        kernel_names = ("score_orfs_packed_kernel",) if scan_path else ("atom_summary_kernel", "score_from_atoms_kernel")
         try:
-            t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["score_orfs_packed_kernel"]
-            if t.get("workload") == args.config and args.scale == 1.0:
-                traffic, traffic_src = t["dram_bytes"], t["source"]
+            t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if all(t[k].get("workload") == args.config for k in kernel_names) and args.scale == 1.0:
+                traffic = sum(t[k]["dram_bytes"] for k in kernel_names)
+                traffic_src = "; ".join(t[k]["source"] for k in kernel_names)
         except Exception:
             pass
         line = {
@@ -373,7 +376,7 @@ def run_ours(args):
             },
             "reads_binned_per_s": world * n_reads / (ms_per_step * 1e-3),
             "kernels_ms": {"bin_psites": bin_ms, "score_orfs": score_ms, "clear_touched": unbin_ms},
-            "roofline": {"bound": "hbm", "kernel": "score_orfs_packed_kernel<8> (+ fallback launch)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": " + ".join(kernel_names) + " (+ fallback launch)", "achieved": achieved,
                          "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "traffic_source": traffic_src,
                          "algorithmic_bytes": score_bytes, "peak_source": peak_src,
