@@ -38,8 +38,12 @@ def main():
                     ("default flags (protocol, lengths and offsets inferred)", dict(read_lengths=None, psite_offsets=None, report_all=False))):
         prefix = os.path.join(tmp, "run", "lib")
         t0 = time.perf_counter()
-        D.detect_orfs(reads_path, index_path, prefix, "forward" if kw["psite_offsets"] else None, kw["read_lengths"],
-                      kw["psite_offsets"], 0.428571428571, 5, 0, 0, 0.0, kw["report_all"])
+        try:
+            D.detect_orfs(reads_path, index_path, prefix, "forward" if kw["psite_offsets"] else None, kw["read_lengths"],
+                          kw["psite_offsets"], 0.428571428571, 5, 0, 0, 0.0, kw["report_all"])
+        except SystemExit as exc:   # e.g. "no periodic read length found" (metagene.py:304-307)
+            out[tag] = {"seconds": round(time.perf_counter() - t0, 3), "sys.exit": str(exc)}
+            continue
         dt = time.perf_counter() - t0
         rows = sum(1 for _ in open(prefix + "_translating_ORFs.tsv")) - 1
         out[tag] = {"seconds": round(dt, 3), "rows": rows, "tsv_MB": round(os.path.getsize(prefix + "_translating_ORFs.tsv") / 1e6, 1)}
