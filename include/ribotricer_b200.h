@@ -206,6 +206,10 @@ int rt_tsv_write(rt_tsv* t, const rt_index* ix, int64_t n_sel, const int64_t* or
                  const uint8_t* status, const int64_t* prof_ptr, const int32_t* prof);
 int rt_tsv_close(rt_tsv* t);
 int rt_repr_double(double x, char* buf, int cap);            /* Python float repr (shortest round trip) */
+/* WIG side output (detect_orfs.py:327-351): one "variableStep chrom=" block per call */
+int rt_wig_open(const char* path, rt_tsv** out);
+int rt_wig_block(rt_tsv* t, const char* chrom, int64_t n, const int64_t* pos, const int32_t* count);
+int rt_wig_close(rt_tsv* t);
 
 /*
  * ---- native BAM/BGZF decode to read columns (no GPU involved; SURVEY.md 8(f) "next #2") -------

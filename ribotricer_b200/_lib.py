@@ -26,7 +26,7 @@ EXPORTS = (
     "rt_gather_profiles", "rt_launch_count", "rt_phasescore_values", "rt_io_last_error", "rt_index_load",
     "rt_index_free", "rt_index_n_orf", "rt_index_n_exon", "rt_index_n_annotated_prefix", "rt_index_n_chrom",
     "rt_index_chrom_name", "rt_index_copy", "rt_index_field", "rt_tsv_open", "rt_tsv_write", "rt_tsv_close",
-    "rt_repr_double", "rt_bam_last_error", "rt_bam_load", "rt_bam_free", "rt_bam_n_reads", "rt_bam_n_ref",
+    "rt_repr_double", "rt_wig_open", "rt_wig_block", "rt_wig_close", "rt_bam_last_error", "rt_bam_load", "rt_bam_free", "rt_bam_n_reads", "rt_bam_n_ref",
     "rt_bam_ref_name", "rt_bam_ref_len", "rt_bam_sorted", "rt_bam_copy",
 )
 
@@ -107,6 +107,9 @@ def load():
     lib.rt_tsv_write.argtypes = [vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.rt_tsv_close.argtypes = [vp]
     lib.rt_repr_double.argtypes = [C.c_double, C.c_char_p, i32]
+    lib.rt_wig_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.rt_wig_block.argtypes = [vp, C.c_char_p, i64, vp, vp]
+    lib.rt_wig_close.argtypes = [vp]
     lib.rt_bam_last_error.restype = C.c_char_p
     lib.rt_bam_load.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
     lib.rt_bam_free.argtypes = [vp]

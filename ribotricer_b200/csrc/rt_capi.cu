@@ -668,13 +668,25 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
     const int64_t n = hi - lo;
     const int64_t* np = ctx->nt_prefix.data();
     auto len_of = [np](int32_t x) { return np[x + 1] - np[x]; };
-    // long ORFs: all of them, longest first (they start first and run beside the packed kernel)
     std::vector<int32_t> ids;
     ids.reserve((size_t)n);
+    int64_t n_long = 0;
+    if (ctx->use_atoms) {
+        // two-phase path: one thread per ORF walks its atom refs, so the ORFs sharing a warp should hold
+        // similar numbers of refs; sort by that inside windows of the index (neighbours share atoms)
+        auto refs_of = [&](int32_t x) { return (ctx->h_orf_refs_desc[x] >> 40) & (uint64_t)rt::kMaxEntriesPerOrf; };
+        constexpr int64_t kPlanWindow = 2048;
+        for (int64_t w0 = lo; w0 < hi; w0 += kPlanWindow) {
+            const size_t begin = ids.size();
+            for (int64_t o = w0; o < std::min(hi, w0 + kPlanWindow); ++o) ids.push_back((int32_t)o);
+            std::stable_sort(ids.begin() + begin, ids.end(), [&](int32_t x, int32_t y) { return refs_of(x) > refs_of(y); });
+        }
+    } else {
+    // long ORFs: all of them, longest first (they start first and run beside the packed kernel)
     for (int64_t o = lo; o < hi; ++o)
         if (len_of((int32_t)o) > rt::kPackMaxNt) ids.push_back((int32_t)o);
     std::stable_sort(ids.begin(), ids.end(), [&](int32_t x, int32_t y) { return len_of(x) > len_of(y); });
-    const int64_t n_long = (int64_t)ids.size();
+    n_long = (int64_t)ids.size();
     // the rest: sorted by length inside windows of kPlanWindow consecutive index rows, so that the
     // ORFs sharing a warp have similar lengths while neighbours in the index (nested ORFs, isoforms:
     // same exons) are still scored close in time and meet in L2
@@ -684,6 +696,7 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
         for (int64_t o = w0; o < std::min(hi, w0 + kPlanWindow); ++o)
             if (len_of((int32_t)o) <= rt::kPackMaxNt) ids.push_back((int32_t)o);
         std::stable_sort(ids.begin() + begin, ids.end(), [&](int32_t x, int32_t y) { return len_of(x) > len_of(y); });
+    }
     }
     if (ctx->plans.size() >= 8) {   // bounded cache
         cudaFree(ctx->plans.front().d_list);

@@ -306,3 +306,35 @@ int rt_repr_double(double x, char* buf, int cap) {
 }
 
 }  // extern "C"
+
+// ---- WIG writer (detect_orfs.py:327-351): one "variableStep chrom=" block per call ------------------
+extern "C" {
+
+int rt_wig_open(const char* path, rt_tsv** out) { return rt_tsv_open(path, 0, out); }
+
+int rt_wig_block(rt_tsv* t, const char* chrom, int64_t n, const int64_t* pos, const int32_t* count) {
+    if (!t || !chrom || n < 0 || (n && (!pos || !count))) return RT_EINVAL;
+    std::string& b = t->buf;
+    b += "variableStep chrom=";
+    b += chrom;
+    b += '\n';
+    for (int64_t i = 0; i < n; ++i) {
+        append_int(b, pos[i]);
+        b += '\t';
+        append_int(b, count[i]);
+        b += '\n';
+        if (b.size() > (1u << 22)) {
+            if (fwrite(b.data(), 1, b.size(), t->fh) != b.size()) return RT_EINVAL;
+            b.clear();
+        }
+    }
+    if (!b.empty()) {
+        if (fwrite(b.data(), 1, b.size(), t->fh) != b.size()) return RT_EINVAL;
+        b.clear();
+    }
+    return RT_OK;
+}
+
+int rt_wig_close(rt_tsv* t) { return rt_tsv_close(t); }
+
+}  // extern "C"

@@ -246,22 +246,35 @@ def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: i
 def export_wig(merged_alignments: MergedAlignments, prefix: str) -> None:
     """detect_orfs.py:327-351: variableStep WIG per strand, chromosomes in lexicographic order,
     only strands that carry coverage."""
+    import ctypes as C
+
     s, c, p, n = merged_alignments.nonzero()
-    names = merged_alignments.engine.contig_names
+    eng = merged_alignments.engine
+    names = eng.contig_names
     order = sorted(range(len(names)), key=lambda i: names[i])
+    lib = eng.lib
     for strand, tag in ((0, "pos"), (1, "neg")):
         m = s == strand
         if not m.any():
             continue
-        parts = []
-        for ci in order:
-            mm = m & (c == ci)
-            if not mm.any():
-                continue
-            parts.append(f"variableStep chrom={names[ci]}\n")
-            parts.append("".join(f"{pos}\t{cnt}\n" for pos, cnt in zip(p[mm].tolist(), n[mm].tolist())))
-        with open(f"{prefix}_{tag}.wig", "w") as output:
-            output.write("".join(parts))
+        handle = C.c_void_p()
+        if lib.rt_wig_open(f"{prefix}_{tag}.wig".encode(), C.byref(handle)) != 0:
+            raise OSError(lib.rt_io_last_error().decode())
+        try:
+            cs, ps, ns = c[m], p[m], n[m]          # already ordered by contig id and position
+            bounds = np.searchsorted(cs, np.arange(len(names) + 1))
+            for ci in order:
+                a, b = int(bounds[ci]), int(bounds[ci + 1])
+                if a == b:
+                    continue
+                pos = np.ascontiguousarray(ps[a:b], np.int64)
+                cnt = np.ascontiguousarray(ns[a:b], np.int32)
+                rc = lib.rt_wig_block(handle, names[ci].encode(), b - a, pos.ctypes.data_as(C.c_void_p),
+                                      cnt.ctypes.data_as(C.c_void_p))
+                if rc != 0:
+                    raise OSError("rt_wig_block failed")
+        finally:
+            lib.rt_wig_close(handle)
 
 
 def _stamp(msg: str) -> None:
