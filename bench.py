@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--contig-scale", type=float, default=1.0, help="shrink contigs (debugging only)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layout", default="compact", choices=["compact", "dense"],
+                    help="coverage layout: exon union of the index (default) or genome-wide planes")
     return ap.parse_args()
 
 
@@ -270,8 +272,11 @@ def run_ours(args):
     dreads = synth.make_reads(cfg, lib_idx, device=dev)
     n_reads = int(dreads["ref_id"].numel())
     n_orf = idx.n_orf
+    if args.layout == "compact":
+        eng.set_layout("compact")   # coverage over the exon union of the index (scoring needs nothing else)
+    else:
+        eng.track_touched(True)
     cov = eng.new_coverage()
-    eng.track_touched(True)
     stats, len_counts = eng.new_bin_accumulators()
     out = eng.new_score_columns(n_orf)
     params = ScoreParams()
@@ -291,7 +296,7 @@ def run_ours(args):
         eng.score_device(cov, out, 0, n_orf, params)
         if events is not None:
             events[2].record()
-        eng.clear_touched(cov)      # zero exactly the slots this library touched
+        eng.clear_touched(cov)      # dense: zero exactly the sectors this library touched; compact: memset
         if events is not None:
             events[3].record()
 
@@ -372,12 +377,14 @@ def run_ours(args):
                             f"({total_nt} nt) per GPU, {n_reads} reads (coordinate-sorted, lengths 26-32), "
                             f"default cutoff 0.428571428571 + all filters",
                 "orfs_per_gpu": n_orf, "reads": n_reads, "sharding": f"orf-shard x{world}, coverage replicated",
-                "l2": "inputs larger than L2 (coverage planes %.1f GB, read columns %.2f GB)" % (
+                "l2": "inputs larger than L2 (coverage buffer %.1f GB, read columns %.2f GB)" % (
                     cov.numel() * 4 / 1e9, READ_BYTES * n_reads / 1e9),
-                "step": "bin P-sites -> gather+score -> sparse clear of the touched slots (resident coverage back to zero)",
+                "coverage_layout": args.layout,
+                "step": "bin P-sites -> gather+score -> clear (resident coverage back to zero: memset of the compact "
+                        "buffer, or sparse clear of the touched sectors of the dense planes)",
             },
             "reads_binned_per_s": world * n_reads / (ms_per_step * 1e-3),
-            "kernels_ms": {"bin_psites": bin_ms, "score_orfs": score_ms, "clear_touched": unbin_ms},
+            "kernels_ms": {"bin_psites": bin_ms, "score_orfs": score_ms, "clear": unbin_ms},
             "roofline": {"bound": "hbm", "kernel": " + ".join(kernel_names) + " (+ fallback launch)", "achieved": achieved,
                          "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "traffic_source": traffic_src,

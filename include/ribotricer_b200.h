@@ -134,6 +134,21 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
 
 int rt_clear_coverage(rt_ctx* ctx, int32_t* d_cov, void* stream);
 
+/*
+ * Coverage layout.  RT_LAYOUT_DENSE (default): the genome-wide planes described at the top, needed
+ * by the WIG export and the metagene windows.  RT_LAYOUT_COMPACT (after rt_set_index): the buffer
+ * holds only the slots some candidate ORF reads -- the union of all exon intervals, in genome order,
+ * back to back (human GENCODE index: 1.8 GB instead of 24.7 GB).  K1 maps a P-site to its compact
+ * slot through a bitmap+rank table and drops P-sites no ORF can see; scoring and rt_gather_profiles
+ * return exactly what they return on the dense planes.  The layout applies to every later call that
+ * takes d_cov; rt_coverage_elems gives the int32 element count a buffer of the current layout needs.
+ * In the compact layout rt_clear_touched is a plain memset of that buffer.
+ */
+#define RT_LAYOUT_DENSE 0
+#define RT_LAYOUT_COMPACT 1
+int rt_set_layout(rt_ctx* ctx, int layout);
+int64_t rt_coverage_elems(const rt_ctx* ctx);
+
 /* Sparse clear for a resident coverage buffer that is recycled library after library: with tracking
  * on, K1 (weight +1) appends every slot it bumps to a ctx-owned list (8 B per read at most) and
  * rt_clear_touched zeroes exactly those slots -- a fraction of a millisecond instead of a

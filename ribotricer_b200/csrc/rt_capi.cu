@@ -74,6 +74,13 @@ struct rt_ctx {
     uint64_t* d_ref_ent = nullptr;                   // refs in profile order
     uint32_t* d_ref_atom = nullptr;
     rt::AtomSummary* d_summaries = nullptr;          // per-library scratch, written by phase A
+    // compact layout: the coverage buffer holds the exon union only (atoms back to back, genome order)
+    int layout = RT_LAYOUT_DENSE;
+    int64_t compact_elems = 0;                       // int32 elements of a compact coverage buffer (with guard)
+    uint2* d_cmap = nullptr;                         // per 32 dense slots: member mask | compact index after the last member
+    uint64_t* d_atoms_c = nullptr;                   // the same tables with compact slot offsets
+    uint64_t* d_ref_ent_c = nullptr;
+    uint64_t* d_exon_entries_c = nullptr;
     std::vector<uint64_t> h_atoms;                   // host copies used to build per-range atom lists
     std::vector<uint64_t> h_orf_refs_desc;
     std::vector<uint32_t> h_ref_atom;
@@ -225,6 +232,21 @@ int build_atoms(rt_ctx* ctx, const std::vector<uint64_t>& desc, const std::vecto
         ctx->h_orf_refs_desc[o] = (uint64_t)ref_begin | ((uint64_t)cnt << 40) | ((uint64_t)rev << 63);
     }
     ctx->n_atoms = (int64_t)ctx->h_atoms.size();
+    // compact layout: atom i starts at the sum of the lengths of the atoms before it
+    std::vector<uint64_t> atoms_c(ctx->h_atoms.size()), ref_ent_c(ctx->h_ref_ent.size()), entries_c(entries.size());
+    uint64_t cat = 0;
+    for (size_t i = 0; i < atoms_c.size(); ++i) {
+        const uint64_t len = ctx->h_atoms[i] & rt::kLenMask;
+        atoms_c[i] = (cat << rt::kLenBits) | len;
+        cat += len;
+    }
+    ctx->compact_elems = (int64_t)((cat + 31) / 32 * 32 + 32);
+    for (size_t k = 0; k < ref_ent_c.size(); ++k)
+        ref_ent_c[k] = ctx->h_ref_atom[k] == 0xffffffffu ? ctx->h_ref_ent[k] : atoms_c[ctx->h_ref_atom[k]];
+    for (size_t k = 0; k < entries.size(); ++k) {
+        const uint64_t off = entries[k] >> rt::kLenBits, len = entries[k] & rt::kLenMask;
+        entries_c[k] = off == kZero ? entries[k] : ((atoms_c[atom_begin[idx_of(off)]] >> rt::kLenBits) << rt::kLenBits) | len;
+    }
     auto upload = [&](auto** dptr, const auto& vec) -> cudaError_t {
         using T = typename std::remove_reference<decltype(vec)>::type::value_type;
         cudaError_t e = cudaMalloc(dptr, sizeof(T) * std::max<size_t>(1, vec.size()));
@@ -235,6 +257,9 @@ int build_atoms(rt_ctx* ctx, const std::vector<uint64_t>& desc, const std::vecto
     RT_CUDA(ctx, upload(&ctx->d_orf_refs_desc, ctx->h_orf_refs_desc));
     RT_CUDA(ctx, upload(&ctx->d_ref_ent, ctx->h_ref_ent));
     RT_CUDA(ctx, upload(&ctx->d_ref_atom, ctx->h_ref_atom));
+    RT_CUDA(ctx, upload(&ctx->d_atoms_c, atoms_c));
+    RT_CUDA(ctx, upload(&ctx->d_ref_ent_c, ref_ent_c));
+    RT_CUDA(ctx, upload(&ctx->d_exon_entries_c, entries_c));
     RT_CUDA(ctx, cudaMalloc(&ctx->d_summaries, sizeof(rt::AtomSummary) * std::max<size_t>(1, ctx->h_atoms.size())));
     ctx->h_ref_ent.clear();
     ctx->h_ref_ent.shrink_to_fit();
@@ -304,6 +329,10 @@ void rt_destroy(rt_ctx* ctx) {
     cudaFree(ctx->d_ref_ent);
     cudaFree(ctx->d_ref_atom);
     cudaFree(ctx->d_summaries);
+    cudaFree(ctx->d_cmap);
+    cudaFree(ctx->d_atoms_c);
+    cudaFree(ctx->d_ref_ent_c);
+    cudaFree(ctx->d_exon_entries_c);
     cudaFree(ctx->d_work_counter);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -358,6 +387,7 @@ int rt_set_genome(rt_ctx* ctx, int n_contig, const int64_t* h_contig_len, int pa
     }
     // a new genome invalidates the index encoding
     ctx->n_orf = 0;
+    ctx->layout = RT_LAYOUT_DENSE;
     return RT_OK;
 }
 
@@ -391,8 +421,38 @@ int rt_clear_coverage(rt_ctx* ctx, int32_t* d_cov, void* stream) {
     if (!ctx || !d_cov) return fail(ctx, RT_EINVAL, "rt_clear_coverage: NULL argument");
     if (ctx->plane == 0) return fail(ctx, RT_ESTATE, "rt_clear_coverage: call rt_set_genome first");
     DeviceGuard guard(ctx->device);
-    RT_CUDA(ctx, cudaMemsetAsync(d_cov, 0, sizeof(int32_t) * 2 * (size_t)ctx->plane, (cudaStream_t)stream));
+    const size_t elems = ctx->layout == RT_LAYOUT_COMPACT ? (size_t)ctx->compact_elems : 2 * (size_t)ctx->plane;
+    RT_CUDA(ctx, cudaMemsetAsync(d_cov, 0, sizeof(int32_t) * elems, (cudaStream_t)stream));
     return RT_OK;
+}
+
+int rt_set_layout(rt_ctx* ctx, int layout) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_set_layout: ctx is NULL");
+    if (layout != RT_LAYOUT_DENSE && layout != RT_LAYOUT_COMPACT) return fail(ctx, RT_EINVAL, "rt_set_layout: unknown layout %d", layout);
+    if (layout == RT_LAYOUT_COMPACT) {
+        if (ctx->n_orf == 0) return fail(ctx, RT_ESTATE, "rt_set_layout: the compact layout is derived from the index; call rt_set_index first");
+        if (ctx->compact_elems >= 0xffffffffll) return fail(ctx, RT_EINVAL, "rt_set_layout: exon union too large for 32-bit compact slots");
+        DeviceGuard guard(ctx->device);
+        if (!ctx->d_cmap) {
+            const size_t words = (size_t)(2 * ctx->plane / 32);
+            RT_CUDA(ctx, cudaMalloc(&ctx->d_cmap, sizeof(uint2) * words));
+            RT_CUDA(ctx, cudaMemset(ctx->d_cmap, 0, sizeof(uint2) * words));
+            if (ctx->n_atoms > 0) {
+                const unsigned grid = (unsigned)std::min<int64_t>((ctx->n_atoms + 7) / 8, (int64_t)ctx->n_sm * 16);
+                rt::build_cmap_kernel<<<grid, 256>>>(ctx->d_atoms, ctx->d_atoms_c, ctx->n_atoms, ctx->d_cmap);
+                ctx->launches++;
+                RT_CUDA(ctx, cudaGetLastError());
+                RT_CUDA(ctx, cudaDeviceSynchronize());
+            }
+        }
+    }
+    ctx->layout = layout;
+    return RT_OK;
+}
+
+int64_t rt_coverage_elems(const rt_ctx* ctx) {
+    if (!ctx) return 0;
+    return ctx->layout == RT_LAYOUT_COMPACT ? ctx->compact_elems : 2 * ctx->plane;
 }
 
 int rt_track_touched(rt_ctx* ctx, int enable) {
@@ -408,9 +468,14 @@ int rt_track_touched(rt_ctx* ctx, int enable) {
 
 int rt_clear_touched(rt_ctx* ctx, int32_t* d_cov, void* stream) {
     if (!ctx || !d_cov) return fail(ctx, RT_EINVAL, "rt_clear_touched: NULL argument");
-    if (!ctx->d_n_touched) return fail(ctx, RT_ESTATE, "rt_clear_touched: call rt_track_touched(ctx, 1) first");
+    if (!ctx->d_n_touched && ctx->layout != RT_LAYOUT_COMPACT)
+        return fail(ctx, RT_ESTATE, "rt_clear_touched: call rt_track_touched(ctx, 1) first");
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->layout == RT_LAYOUT_COMPACT) {   // the whole buffer is the exon union: a plain memset is the sparse clear
+        RT_CUDA(ctx, cudaMemsetAsync(d_cov, 0, sizeof(int32_t) * (size_t)ctx->compact_elems, st));
+        return RT_OK;
+    }
     if (ctx->touched_buf.p) {
         rt::clear_touched_kernel<<<(unsigned)ctx->n_sm * 8, 256, 0, st>>>(
             d_cov, static_cast<const unsigned long long*>(ctx->touched_buf.p), ctx->d_n_touched);
@@ -455,7 +520,8 @@ int rt_bin_reads(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* d_ref_id
     a.len_counts = reinterpret_cast<unsigned long long*>(d_len_counts);
     a.touched = nullptr;
     a.n_touched = nullptr;
-    if (ctx->track_touched && weight == 1) {
+    a.cmap = ctx->layout == RT_LAYOUT_COMPACT ? ctx->d_cmap : nullptr;
+    if (ctx->track_touched && weight == 1 && !a.cmap) {
         int rc = ensure_touched_capacity(ctx, ctx->touched_reserved + n);
         if (rc != RT_OK) return rc;
         ctx->touched_reserved += n;
@@ -486,7 +552,7 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
         if (!ctx->slot_stream[s]) RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking));
     RT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, acc_bytes, ctx->slot_stream[0]));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[0]));
-    if (ctx->track_touched) {   // one growth up front instead of one per chunk
+    if (ctx->track_touched && ctx->layout != RT_LAYOUT_COMPACT) {   // one growth up front instead of one per chunk
         int rc = ensure_touched_capacity(ctx, ctx->touched_reserved + n);
         if (rc != RT_OK) return rc;
     }
@@ -600,6 +666,14 @@ int rt_set_index(rt_ctx* ctx, int64_t n_orf, const int64_t* h_exon_ptr, const in
     cudaFree(ctx->d_ref_ent);
     cudaFree(ctx->d_ref_atom);
     cudaFree(ctx->d_summaries);
+    cudaFree(ctx->d_cmap);
+    cudaFree(ctx->d_atoms_c);
+    cudaFree(ctx->d_ref_ent_c);
+    cudaFree(ctx->d_exon_entries_c);
+    ctx->d_cmap = nullptr;
+    ctx->d_atoms_c = ctx->d_ref_ent_c = ctx->d_exon_entries_c = nullptr;
+    ctx->layout = RT_LAYOUT_DENSE;
+    ctx->compact_elems = 0;
     ctx->d_atoms = ctx->d_orf_refs_desc = ctx->d_ref_ent = nullptr;
     ctx->d_ref_atom = nullptr;
     ctx->d_summaries = nullptr;
@@ -773,7 +847,8 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
     rt::ScoreArgs a;
     a.cov = d_cov;
     a.orf_desc = ctx->d_orf_desc;
-    a.exon_entries = ctx->d_exon_entries;
+    const bool compact = ctx->layout == RT_LAYOUT_COMPACT;
+    a.exon_entries = compact ? ctx->d_exon_entries_c : ctx->d_exon_entries;
     a.orf_len = ctx->d_orf_len;
     a.orf_lo = orf_lo;
     a.fallback = plan->d_fallback;
@@ -786,7 +861,7 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
         if (plan->n_atom_list > 0) {
             rt::AtomArgs aa;
             aa.cov = d_cov;
-            aa.atoms = ctx->d_atoms;
+            aa.atoms = compact ? ctx->d_atoms_c : ctx->d_atoms;
             aa.list = plan->d_atom_list;
             aa.n_list = plan->n_atom_list;
             aa.work_counter = ctx->d_work_counter + 0;
@@ -802,7 +877,7 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
         rt::ComposeArgs ca;
         ca.cov = d_cov;
         ca.orf_refs_desc = ctx->d_orf_refs_desc;
-        ca.ref_ent = ctx->d_ref_ent;
+        ca.ref_ent = compact ? ctx->d_ref_ent_c : ctx->d_ref_ent;
         ca.ref_atom = ctx->d_ref_atom;
         ca.summaries = ctx->d_summaries;
         ca.orf_len = ctx->d_orf_len;
@@ -926,7 +1001,7 @@ int rt_gather_profiles(rt_ctx* ctx, const int32_t* d_cov, int64_t n_sel, const i
     rt::GatherArgs a;
     a.cov = d_cov;
     a.orf_desc = ctx->d_orf_desc;
-    a.exon_entries = ctx->d_exon_entries;
+    a.exon_entries = ctx->layout == RT_LAYOUT_COMPACT ? ctx->d_exon_entries_c : ctx->d_exon_entries;
     a.orf_ids = d_orf_ids;
     a.out_ptr = d_out_ptr;
     a.out = d_out;

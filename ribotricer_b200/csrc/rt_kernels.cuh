@@ -1209,6 +1209,7 @@ struct BinArgs {
     int len_base;                  // lengths [len_base, len_base + 16) are counted in registers
     unsigned long long* touched;   // optional: every 32 B sector (slot >> 3) that received an atomic (duplicates allowed)
     unsigned long long* n_touched;
+    const uint2* cmap;             // compact layout: per 32 dense slots (member mask, compact index after the last member)
     const int32_t* len_table;      // RT_LEN_TABLE
     const long long* contig_base;  // n_contig
     const long long* contig_len;   // n_contig
@@ -1312,6 +1313,11 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
                 }
                 if (cat) packed += 1u << (4 * (cat - 1));
             }
+            if (a.cmap && slot >= 0) {   // compact layout: rank of the slot inside the exon union, or no slot at all
+                const uint2 m = __ldg(a.cmap + (slot >> 5));
+                const unsigned above = m.x >> (unsigned)(slot & 31);
+                slot = (above & 1u) ? (long long)m.y - __popc(above) : -1;
+            }
             // detect_orfs.py:82: duplicated 5' ends are the rule in Ribo-seq and adjacent in a
             // coordinate-sorted BAM: the first lane of every run of equal slots adds the run length
             const long long prev = __shfl_up_sync(kFull, slot, 1);
@@ -1377,6 +1383,26 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
         atomicAdd(a.stats + threadIdx.x, (unsigned long long)((long long)a.weight * s_stats[threadIdx.x]));
     for (int i = threadIdx.x; i < kLenHist; i += kBinThreads)
         if (s_len[i]) atomicAdd(a.len_counts + i, (unsigned long long)((long long)a.weight * s_len[i]));
+}
+
+// Compact layout: one (mask, top) word per 32 dense slots.  A member slot with bit b maps to
+// top - popc(mask >> b): members keep their genome order and sit back to back in the compact buffer.
+__global__ void __launch_bounds__(256) build_cmap_kernel(const uint64_t* __restrict__ atoms, const uint64_t* __restrict__ atoms_c,
+                                                          long long n_atoms, uint2* cmap) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp; i < n_atoms; i += n_warps) {
+        const unsigned long long off = atoms[i] >> kLenBits, len = atoms[i] & kLenMask, cb = atoms_c[i] >> kLenBits;
+        const unsigned long long w0 = off >> 5, w1 = (off + len - 1) >> 5;
+        for (unsigned long long w = w0 + lane; w <= w1; w += 32) {
+            const unsigned long long lo = max(off, w << 5), hi = min(off + len, (w << 5) + 32);   // [lo, hi)
+            const unsigned nbits = (unsigned)(hi - lo);
+            const unsigned mask = (nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u)) << (unsigned)(lo & 31);
+            atomicOr(&cmap[w].x, mask);
+            atomicMax(&cmap[w].y, (unsigned)(cb + (hi - off)));
+        }
+    }
 }
 
 // Sparse clear: zero the 32-byte sectors (8 slots) K1 touched since the last clear.  Whole sectors

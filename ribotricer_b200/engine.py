@@ -123,6 +123,7 @@ class Engine:
         self.contig_base = np.zeros(len(self.contig_len), np.int64)
         self._check(self.lib.rt_get_contig_base(self.ctx, _np_ptr(self.contig_base)))
         self.n_orf = 0
+        self.layout = "dense"
         self._resident_index = None
         self._contig_lut = {n: i for i, n in enumerate(self.contig_names)}
 
@@ -137,8 +138,17 @@ class Engine:
         self.len_table = t
 
     def new_coverage(self):
-        """Zeroed int32[2 * plane] coverage buffer (plane 0 '+', plane 1 '-')."""
-        return self.torch.zeros(2 * self.plane, dtype=self.torch.int32, device=self.device)
+        """Zeroed int32 coverage buffer of the current layout (dense: [2 * plane], plane 0 '+', plane 1 '-')."""
+        return self.torch.zeros(self.coverage_elems(), dtype=self.torch.int32, device=self.device)
+
+    def set_layout(self, layout: str):
+        """'dense' = genome-wide planes (default; WIG / metagene need it); 'compact' = exon union of the
+        index only (``rt_set_layout``): same scores, a 13x smaller buffer for the human index."""
+        self._check(self.lib.rt_set_layout(self.ctx, {"dense": 0, "compact": 1}[layout]))
+        self.layout = layout
+
+    def coverage_elems(self) -> int:
+        return int(self.lib.rt_coverage_elems(self.ctx))
 
     def clear_coverage(self, cov):
         self._check(self.lib.rt_clear_coverage(self.ctx, C.c_void_p(cov.data_ptr()), self._stream()))
@@ -165,6 +175,7 @@ class Engine:
         self._check(self.lib.rt_set_index(self.ctx, n, _np_ptr(exon_ptr), _np_ptr(exon_start), _np_ptr(exon_end),
                                           _np_ptr(orf_contig), _np_ptr(orf_strand)))
         self.n_orf = n
+        self.layout = "dense"
         self._resident_index = None
 
     def score_bytes(self, lo: int = 0, hi: int | None = None) -> int:

@@ -407,3 +407,75 @@ def test_two_phase_path_agrees_with_scan_path_at_full_size(built):
     near = np.abs(a["score"] - 0.428571428571) <= SCORE_TOL
     assert (a["status"] == s["status"])[same & ~near].all()
     keep.close()
+
+
+@pytest.mark.parametrize("name,scale,contig_scale,sort", [("tiny", 1.0, 1.0, True), ("C1", 0.2, 1.0, True),
+                                                         ("C5", 0.004, 0.01, False)])
+def test_compact_layout_matches_dense_and_oracle(engine, name, scale, contig_scale, sort):
+    """RT_LAYOUT_COMPACT (coverage over the exon union only): stats and length counts are those of the
+    dense planes, every compact slot holds the dense slot's count, and scores / gathered profiles are
+    bit-identical to the dense layout's (and so to the oracle's)."""
+    CO = _oracle()
+    from ribotricer_b200 import synth
+    from ribotricer_b200.engine import ScoreParams
+
+    cfg = synth.config(name, scale, contig_scale)
+    idx = synth.make_index(cfg)
+    reads = synth.reads_to_numpy(synth.make_reads(cfg, idx, n_reads=min(cfg.n_reads, 1_000_000), sort=sort))
+    pad = 256
+    base, plane = _setup(engine, idx.contig_names, idx.contig_len, idx.as_dict(), synth.TRUE_OFFSETS, pad=pad)
+    dense = engine.new_coverage()
+    stats_d, len_d = engine.bin_reads_host(dense, reads, "forward", sorted_hint=sort)
+    ref_d = engine.score_host(dense, diagnostics=True, min_codon=True)
+    sel = np.unique(np.concatenate([np.arange(0, idx.n_orf, max(1, idx.n_orf // 200)), np.argsort(idx.orf_len)[-3:]]))
+    ptr_d, prof_d = engine.gather_profiles(dense, sel, ref_d["length"][sel])
+    engine.set_layout("compact")
+    try:
+        n_c = engine.coverage_elems()
+        assert n_c < 2 * plane + 64
+        cov = engine.new_coverage()
+        assert cov.numel() == n_c
+        stats_c, len_c = engine.bin_reads_host(cov, reads, "forward", sorted_hint=sort)
+        assert stats_c == stats_d and (len_c == len_d).all()
+        # every read that lands in the exon union is kept, nothing else
+        ref_cov, _, _ = CO.bin_reads(reads, 0, CO.make_len_table(synth.TRUE_OFFSETS), base, idx.contig_len, pad, plane)
+        member = np.zeros(2 * plane, bool)
+        d = idx.as_dict()
+        for o in range(idx.n_orf):
+            c, s = d["orf_contig"][o], d["orf_strand"][o]
+            if c < 0 or s > 1:
+                continue
+            for e in range(d["exon_ptr"][o], d["exon_ptr"][o + 1]):
+                a = max(int(d["exon_start"][e]), 1 - pad)
+                b = min(int(d["exon_end"][e]), int(idx.contig_len[c]) + pad)
+                if a <= b:
+                    member[s * plane + base[c] + pad + a: s * plane + base[c] + pad + b + 1] = True
+        got = cov.cpu().numpy()
+        n_member = int(member.sum())
+        assert n_member <= n_c <= n_member + 64
+        assert (got[:n_member] == ref_cov[member]).all() and not got[n_member:].any()
+        for params in (DEFAULT_PARAMS, [0.3, 3, 1, 0.1, 0.25]):
+            one = engine.score_host(cov, params=ScoreParams(*params), diagnostics=True, min_codon=True)
+            engine.set_layout("dense")
+            two = engine.score_host(dense, params=ScoreParams(*params), diagnostics=True, min_codon=True)
+            engine.set_layout("compact")
+            for k in one:
+                assert np.array_equal(one[k], two[k], equal_nan=True), k
+        ptr_c, prof_c = engine.gather_profiles(cov, sel, ref_d["length"][sel])
+        assert (ptr_c == ptr_d).all() and (prof_c == prof_d).all()
+        # recycling: the sparse clear of a compact buffer is a memset
+        engine.clear_touched(cov)
+        assert int(cov.abs().max().item()) == 0
+        st, lc = engine.new_bin_accumulators()
+        engine.bin_reads_device(cov, engine.upload_reads(reads), "forward", st, lc, sorted_hint=sort)
+        assert (cov.cpu().numpy() == got).all()
+    finally:
+        engine.set_layout("dense")
+
+
+def test_compact_layout_needs_an_index(engine):
+    from ribotricer_b200._lib import RtError
+
+    engine.set_genome(["c"], [1000], pad=32)
+    with pytest.raises(RtError, match="rt_set_index first"):
+        engine.set_layout("compact")
