@@ -860,13 +860,49 @@ struct AtomArgs {
     AtomSummary* out;                  // indexed by atom id
 };
 
+// Unit vectors by table.  The unit vector of a codon (a,b,c) depends only on x = a - c and y = b - c
+// (A = 2x - y, B = y); for counts below kUvMax every window of the lane indexes one shared-memory
+// table of (A, B) / sqrt(A^2 + 3 B^2) -- all-zero and uniform codons hit the (0,0) entry -- so the
+// three windows of a round are settled by three loads and six fp64 adds with every lane active,
+// instead of a divergent classify / rsqrt sequence that few lanes take.
+constexpr int kUvMax = 16;                         // table covers counts 0 .. kUvMax - 1
+constexpr int kUvSide = 2 * kUvMax - 1;            // x, y in [-(kUvMax-1), kUvMax-1]
+constexpr int kUvStride = 2 * kUvMax;              // row stride (power of two: the index is two shifts and adds)
+constexpr int kUvEntries = kUvSide * kUvStride;
+constexpr int kUvCenter = (kUvMax - 1) * kUvStride + (kUvMax - 1);
+
+__device__ __forceinline__ void fill_uv_table(double2* tab) {
+    for (int i = threadIdx.x; i < kUvEntries; i += blockDim.x) {
+        const int x = i / kUvStride - (kUvMax - 1), y = i % kUvStride - (kUvMax - 1);
+        const double A = (double)(2 * x - y), B = (double)y;
+        const double D = A * A + 3.0 * B * B;
+        double2 e = make_double2(0.0, 0.0);
+        if (D > 0.0) {
+            const double n = sqrt(D);
+            e = make_double2(A / n, B / n);
+        }
+        tab[i] = e;
+    }
+}
+
+// One complete window of local frame F outside the table's range (or at the ragged end of an atom).
+template <int F>
+__device__ __forceinline__ void slow_window(int x, int y, int z, unsigned& accK, unsigned& accM, FrameLane& f) {
+    if ((x | y | z) == 0) return;                       // statistics.py:72-73
+    accK += 1u << (10 * F);
+    const int A = 2 * x - y - z, B = y - z;
+    if ((A | B) == 0) return;                           // uniform: counts in K only
+    accM += 1u << (10 * F);
+    unit_vector_add(A, B, f);
+}
+
 template <int LPO, bool WantMin>
 __global__ void __launch_bounds__(kScoreWarps * 32, 4)
 atom_summary_kernel(const AtomArgs args) {
     constexpr int G = 32 / LPO;
     constexpr int RNT = 3 * LPO;
-    __shared__ unsigned long long s_lut[32];
-    if (threadIdx.x < 32) s_lut[threadIdx.x] = single_codon_lut_entry(threadIdx.x);
+    __shared__ double2 s_uv[kUvEntries];
+    fill_uv_table(s_uv);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int sl = lane % LPO;
@@ -888,9 +924,8 @@ atom_summary_kernel(const AtomArgs args) {
             len = (int)(ent & kLenMask);
             src = args.cov + (ent >> kLenBits);
         }
-        FrameLane f0, f1, f2;
-        unsigned long long acc1 = 0, acc2 = 0;
-        Deferred dfr;
+        FrameLane f0, f1, f2;                  // only the fp64 sums are used here
+        unsigned accK = 0, accM = 0;           // 10-bit fields by local frame: kept windows, non-uniform windows
         unsigned cnt32 = 0, mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu;
         int ormask = 0;
         const int rounds = __reduce_max_sync(kFull, ((len + 2) / 3 + LPO - 1) / LPO);
@@ -914,7 +949,8 @@ atom_summary_kernel(const AtomArgs args) {
             const int v4 = __shfl_sync(kFull, sl == 0 ? n1 : c1, nbr);
             if (p < len) {
                 cnt32 += (unsigned)c0 + (unsigned)c1 + (unsigned)c2;
-                ormask |= c0 | c1 | c2;
+                const int o3 = c0 | c1 | c2;
+                ormask |= o3;
                 if (p + 4 < len) {                               // all three windows lie inside the atom
                     if (WantMin) {
                         const unsigned s0 = (unsigned)c0 + (unsigned)c1 + (unsigned)c2;
@@ -922,29 +958,34 @@ atom_summary_kernel(const AtomArgs args) {
                         const unsigned s2 = (unsigned)c2 + (unsigned)v3 + (unsigned)v4;
                         mn0 = min(mn0, s0); mn1 = min(mn1, s1); mn2 = min(mn2, s2);
                     }
-                    if ((c0 | c1 | c2 | v3 | v4) != 0) {
-                        const unsigned m5 = min((unsigned)c0, 1u) | (min((unsigned)c1, 1u) << 1) | (min((unsigned)c2, 1u) << 2) |
-                                            (min((unsigned)v3, 1u) << 3) | (min((unsigned)v4, 1u) << 4);
-                        acc1 += s_lut[m5];
-                        const unsigned multi = ((m5 & (m5 >> 1)) | (m5 & (m5 >> 2)) | ((m5 >> 1) & (m5 >> 2))) & 7u;
-                        if (multi) {
-                            if (multi & 1u) multi_codon<0>(c0, c1, c2, acc2, f0, dfr);
-                            if (multi & 2u) multi_codon<1>(c1, c2, v3, acc2, f1, dfr);
-                            if (multi & 4u) multi_codon<2>(c2, v3, v4, acc2, f2, dfr);
+                    const int o5 = o3 | v3 | v4;
+                    if (o5 != 0) {
+                        if ((unsigned)o5 < (unsigned)kUvMax) {
+                            const int i0 = (c0 - c2) * kUvStride + (c1 - c2) + kUvCenter;
+                            const int i1 = (c1 - v3) * kUvStride + (c2 - v3) + kUvCenter;
+                            const int i2 = (c2 - v4) * kUvStride + (v3 - v4) + kUvCenter;
+                            const double2 u0 = s_uv[i0], u1 = s_uv[i1], u2 = s_uv[i2];
+                            f0.sre += u0.x; f0.sim += u0.y;
+                            f1.sre += u1.x; f1.sim += u1.y;
+                            f2.sre += u2.x; f2.sim += u2.y;
+                            accK += min((unsigned)o3, 1u) + (min((unsigned)(c1 | c2 | v3), 1u) << 10) +
+                                    (min((unsigned)(c2 | v3 | v4), 1u) << 20);
+                            accM += min((unsigned)(i0 ^ kUvCenter), 1u) + (min((unsigned)(i1 ^ kUvCenter), 1u) << 10) +
+                                    (min((unsigned)(i2 ^ kUvCenter), 1u) << 20);
+                        } else {
+                            slow_window<0>(c0, c1, c2, accK, accM, f0);
+                            slow_window<1>(c1, c2, v3, accK, accM, f1);
+                            slow_window<2>(c2, v3, v4, accK, accM, f2);
                         }
                     }
                 } else {                                         // ragged end of the atom
-                    if (p + 2 < len) { if (WantMin) mn0 = min(mn0, (unsigned)c0 + (unsigned)c1 + (unsigned)c2); classify_codon<0>(c0, c1, c2, f0, dfr); }
-                    if (p + 3 < len) { if (WantMin) mn1 = min(mn1, (unsigned)c1 + (unsigned)c2 + (unsigned)v3); classify_codon<1>(c1, c2, v3, f1, dfr); }
+                    if (p + 2 < len) { if (WantMin) mn0 = min(mn0, (unsigned)c0 + (unsigned)c1 + (unsigned)c2); slow_window<0>(c0, c1, c2, accK, accM, f0); }
+                    if (p + 3 < len) { if (WantMin) mn1 = min(mn1, (unsigned)c1 + (unsigned)c2 + (unsigned)v3); slow_window<1>(c1, c2, v3, accK, accM, f1); }
                 }
             }
             c0 = n0; c1 = n1; c2 = n2;
         }
-        flush_deferred(dfr, f0, f1, f2);
-        unpack_acc(acc1, acc2, f0, f1, f2);
-        const unsigned a1_0 = group_sum_u32<LPO>(f0.w1), a2_0 = group_sum_u32<LPO>(f0.w2);
-        const unsigned a1_1 = group_sum_u32<LPO>(f1.w1), a2_1 = group_sum_u32<LPO>(f1.w2);
-        const unsigned a1_2 = group_sum_u32<LPO>(f2.w1), a2_2 = group_sum_u32<LPO>(f2.w2);
+        const unsigned K = group_sum_u32<LPO>(accK), M = group_sum_u32<LPO>(accM);
         const unsigned count = group_sum_u32<LPO>(cnt32);
 #pragma unroll
         for (int o = LPO / 2; o > 0; o >>= 1) {
@@ -955,25 +996,21 @@ atom_summary_kernel(const AtomArgs args) {
             }
             ormask |= __shfl_xor_sync(kFull, ormask, o);
         }
-        const bool any_general = __any_sync(kFull, ((a2_0 | a2_1 | a2_2) & 1023u) != 0);
         double re0 = 0.0, im0 = 0.0, re1 = 0.0, im1 = 0.0, re2 = 0.0, im2 = 0.0;
-        if (any_general) {
+        if (__any_sync(kFull, M != 0)) {
             re0 = group_sum_f64<LPO>(f0.sre); im0 = group_sum_f64<LPO>(f0.sim);
             re1 = group_sum_f64<LPO>(f1.sre); im1 = group_sum_f64<LPO>(f1.sim);
             re2 = group_sum_f64<LPO>(f2.sre); im2 = group_sum_f64<LPO>(f2.sim);
         }
         if (active && sl == 0) {
             AtomSummary s;
-            const int na0 = a1_0 & 1023, nb0 = (a1_0 >> 10) & 1023, nc0 = a1_0 >> 20, ng0 = a2_0 & 1023, nu0 = a2_0 >> 10;
-            const int na1 = a1_1 & 1023, nb1 = (a1_1 >> 10) & 1023, nc1 = a1_1 >> 20, ng1 = a2_1 & 1023, nu1 = a2_1 >> 10;
-            const int na2 = a1_2 & 1023, nb2 = (a1_2 >> 10) & 1023, nc2 = a1_2 >> 20, ng2 = a2_2 & 1023, nu2 = a2_2 >> 10;
-            s.K[0] = (unsigned short)(na0 + nb0 + nc0 + ng0 + nu0);
-            s.K[1] = (unsigned short)(na1 + nb1 + nc1 + ng1 + nu1);
-            s.K[2] = (unsigned short)(na2 + nb2 + nc2 + ng2 + nu2);
-            s.U[0] = (unsigned short)nu0; s.U[1] = (unsigned short)nu1; s.U[2] = (unsigned short)nu2;
-            s.re[0] = re0 + 0.5 * (double)(2 * na0 - nb0 - nc0); s.im[0] = im0 + 0.5 * (double)(nb0 - nc0);
-            s.re[1] = re1 + 0.5 * (double)(2 * na1 - nb1 - nc1); s.im[1] = im1 + 0.5 * (double)(nb1 - nc1);
-            s.re[2] = re2 + 0.5 * (double)(2 * na2 - nb2 - nc2); s.im[2] = im2 + 0.5 * (double)(nb2 - nc2);
+            s.K[0] = (unsigned short)(K & 1023u); s.K[1] = (unsigned short)((K >> 10) & 1023u); s.K[2] = (unsigned short)(K >> 20);
+            s.U[0] = (unsigned short)((K & 1023u) - (M & 1023u));
+            s.U[1] = (unsigned short)(((K >> 10) & 1023u) - ((M >> 10) & 1023u));
+            s.U[2] = (unsigned short)((K >> 20) - (M >> 20));
+            s.re[0] = re0; s.im[0] = im0;
+            s.re[1] = re1; s.im[1] = im1;
+            s.re[2] = re2; s.im[2] = im2;
             s.mn[0] = mn0; s.mn[1] = mn1; s.mn[2] = mn2;
             s.flags = (ormask >> kBigShift) != 0 ? 1u : 0u;
             s.count = count;

@@ -442,7 +442,7 @@ def test_compact_layout_matches_dense_and_oracle(engine, name, scale, contig_sca
         member = np.zeros(2 * plane, bool)
         d = idx.as_dict()
         for o in range(idx.n_orf):
-            c, s = d["orf_contig"][o], d["orf_strand"][o]
+            c, s = int(d["orf_contig"][o]), int(d["orf_strand"][o])
             if c < 0 or s > 1:
                 continue
             for e in range(d["exon_ptr"][o], d["exon_ptr"][o + 1]):
