@@ -65,6 +65,7 @@ struct rt_ctx {
     std::vector<int64_t> nt_prefix;     // n_orf + 1: prefix of L
     unsigned long long* d_work_counter = nullptr;   // 4 x u64: work counters of the 3 score launches + fallback count
     int pack_lpo = 8;                                // lanes per ORF of the packed kernel (RT_PACK_LPO)
+    int atom_lpo = 4;                                // lanes per atom in phase A (RT_ATOM_LPO)
     bool use_atoms = true;                           // two-phase scoring (RT_SCORE_PATH=scan selects the scan kernel)
 
     // two-phase scoring: atoms (coverage intervals no ORF exon boundary splits) and per-ORF atom refs
@@ -74,6 +75,7 @@ struct rt_ctx {
     uint64_t* d_ref_ent = nullptr;                   // refs in profile order
     uint32_t* d_ref_atom = nullptr;
     rt::AtomSummary* d_summaries = nullptr;          // per-library scratch, written by phase A
+    uint8_t* d_atom_nonzero = nullptr;               // per-library scratch: atom holds at least one read
     // compact layout: the coverage buffer holds the exon union only (atoms back to back, genome order)
     int layout = RT_LAYOUT_DENSE;
     int64_t compact_elems = 0;                       // int32 elements of a compact coverage buffer (with guard)
@@ -261,6 +263,7 @@ int build_atoms(rt_ctx* ctx, const std::vector<uint64_t>& desc, const std::vecto
     RT_CUDA(ctx, upload(&ctx->d_ref_ent_c, ref_ent_c));
     RT_CUDA(ctx, upload(&ctx->d_exon_entries_c, entries_c));
     RT_CUDA(ctx, cudaMalloc(&ctx->d_summaries, sizeof(rt::AtomSummary) * std::max<size_t>(1, ctx->h_atoms.size())));
+    RT_CUDA(ctx, cudaMalloc(&ctx->d_atom_nonzero, std::max<size_t>(1, ctx->h_atoms.size())));
     ctx->h_ref_ent.clear();
     ctx->h_ref_ent.shrink_to_fit();
     return RT_OK;
@@ -307,6 +310,10 @@ int rt_create(int device, rt_ctx** out) {
         return fail(nullptr, RT_ENOMEM, "rt_create: cudaMalloc failed");
     }
     if (const char* e = getenv("RT_SCORE_PATH")) ctx->use_atoms = strcmp(e, "scan") != 0;
+    if (const char* e = getenv("RT_ATOM_LPO")) {
+        const int v = atoi(e);
+        if (v == 2 || v == 4 || v == 8) ctx->atom_lpo = v;
+    }
     if (const char* e = getenv("RT_PACK_LPO")) {
         const int v = atoi(e);
         if (v == 8 || v == 16 || v == 32) ctx->pack_lpo = v;
@@ -329,6 +336,7 @@ void rt_destroy(rt_ctx* ctx) {
     cudaFree(ctx->d_ref_ent);
     cudaFree(ctx->d_ref_atom);
     cudaFree(ctx->d_summaries);
+    cudaFree(ctx->d_atom_nonzero);
     cudaFree(ctx->d_cmap);
     cudaFree(ctx->d_atoms_c);
     cudaFree(ctx->d_ref_ent_c);
@@ -666,6 +674,8 @@ int rt_set_index(rt_ctx* ctx, int64_t n_orf, const int64_t* h_exon_ptr, const in
     cudaFree(ctx->d_ref_ent);
     cudaFree(ctx->d_ref_atom);
     cudaFree(ctx->d_summaries);
+    cudaFree(ctx->d_atom_nonzero);
+    ctx->d_atom_nonzero = nullptr;
     cudaFree(ctx->d_cmap);
     cudaFree(ctx->d_atoms_c);
     cudaFree(ctx->d_ref_ent_c);
@@ -866,11 +876,18 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
             aa.n_list = plan->n_atom_list;
             aa.work_counter = ctx->d_work_counter + 0;
             aa.out = ctx->d_summaries;
+            aa.nonzero = ctx->d_atom_nonzero;
             // the per-frame minima only matter for --min_reads_per_codon > 0 or when the caller asks for min_codon
             const bool want_min = d_out->min_codon != nullptr || params->min_reads_per_codon > 0.0;
-            const unsigned grid = persistent_grid(ctx, rt::atom_summary_kernel<8, true>, (plan->n_atom_list + 3) / 4);
-            if (want_min) rt::atom_summary_kernel<8, true><<<grid, threads, 0, st>>>(aa);
-            else rt::atom_summary_kernel<8, false><<<grid, threads, 0, st>>>(aa);
+            auto launch = [&](auto kmin, auto knomin, int lpo) {
+                const int g = 32 / lpo;
+                const unsigned grid = persistent_grid(ctx, kmin, (plan->n_atom_list + g - 1) / g);
+                if (want_min) kmin<<<grid, threads, 0, st>>>(aa);
+                else knomin<<<grid, threads, 0, st>>>(aa);
+            };
+            if (ctx->atom_lpo == 2) launch(rt::atom_summary_kernel<2, true>, rt::atom_summary_kernel<2, false>, 2);
+            else if (ctx->atom_lpo == 4) launch(rt::atom_summary_kernel<4, true>, rt::atom_summary_kernel<4, false>, 4);
+            else launch(rt::atom_summary_kernel<8, true>, rt::atom_summary_kernel<8, false>, 8);
             ctx->launches++;
         }
         // phase B: one thread per ORF composes its atoms
@@ -880,6 +897,8 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
         ca.ref_ent = compact ? ctx->d_ref_ent_c : ctx->d_ref_ent;
         ca.ref_atom = ctx->d_ref_atom;
         ca.summaries = ctx->d_summaries;
+        ca.atom_nonzero = ctx->d_atom_nonzero;
+        ca.want_min = (d_out->min_codon != nullptr || params->min_reads_per_codon > 0.0) ? 1 : 0;
         ca.orf_len = ctx->d_orf_len;
         ca.orf_lo = orf_lo;
         ca.list = plan->d_list;

@@ -843,11 +843,13 @@ struct AtomSummary {                   // 96 bytes, six 16-byte chunks
     double im[3];                      //   (imaginary part without its sqrt3 factor)
     int edge[4];                       // first two and last two values of the atom, ascending slots
                                        //   (edge[1] = edge[2] = 0 for a one-value atom)
-    unsigned mn[3];                    // min window sum by local frame (0xffffffff: no window)
+    unsigned kpack;                    // kept (non-all-zero) windows by local frame, 10 bits each;
+                                       //   bit 31: a value >= 2^kBigShift (32-bit sums may have wrapped)
+    unsigned upack;                    // uniform windows among them (count in K only), 10 bits each
     unsigned count;                    // sum of all values of the atom
-    unsigned short K[3];               // kept (non-all-zero) windows by local frame
-    unsigned short U[3];               // uniform windows among them (count in K only)
-    unsigned flags;                    // bit 0: a value >= 2^kBigShift (32-bit sums may have wrapped)
+    unsigned spare0;
+    unsigned mn[3];                    // min window sum by local frame (0xffffffff: no window); only read
+    unsigned spare1;                   //   when the minima are wanted (the first 80 bytes are enough otherwise)
 };
 static_assert(sizeof(AtomSummary) == 96, "AtomSummary layout");
 
@@ -857,7 +859,8 @@ struct AtomArgs {
     const int32_t* list;               // atom ids to summarise, similar lengths adjacent
     long long n_list;
     unsigned long long* work_counter;
-    AtomSummary* out;                  // indexed by atom id
+    AtomSummary* out;                  // indexed by atom id; not written for an atom whose values are all zero
+    uint8_t* nonzero;                  // indexed by atom id: 0 = every value of the atom is zero
 };
 
 // Unit vectors by table.  The unit vector of a codon (a,b,c) depends only on x = a - c and y = b - c
@@ -1003,22 +1006,23 @@ atom_summary_kernel(const AtomArgs args) {
             re2 = group_sum_f64<LPO>(f2.sre); im2 = group_sum_f64<LPO>(f2.sim);
         }
         if (active && sl == 0) {
-            AtomSummary s;
-            s.K[0] = (unsigned short)(K & 1023u); s.K[1] = (unsigned short)((K >> 10) & 1023u); s.K[2] = (unsigned short)(K >> 20);
-            s.U[0] = (unsigned short)((K & 1023u) - (M & 1023u));
-            s.U[1] = (unsigned short)(((K >> 10) & 1023u) - ((M >> 10) & 1023u));
-            s.U[2] = (unsigned short)((K >> 20) - (M >> 20));
-            s.re[0] = re0; s.im[0] = im0;
-            s.re[1] = re1; s.im[1] = im1;
-            s.re[2] = re2; s.im[2] = im2;
-            s.mn[0] = mn0; s.mn[1] = mn1; s.mn[2] = mn2;
-            s.flags = (ormask >> kBigShift) != 0 ? 1u : 0u;
-            s.count = count;
-            s.edge[0] = ld_cov(src);
-            s.edge[1] = len >= 2 ? ld_cov(src + 1) : 0;
-            s.edge[2] = len >= 2 ? ld_cov(src + len - 2) : 0;
-            s.edge[3] = ld_cov(src + len - 1);
-            args.out[atom] = s;
+            args.nonzero[atom] = ormask != 0;
+            if (ormask != 0) {
+                AtomSummary s;
+                s.kpack = K | ((ormask >> kBigShift) != 0 ? 0x80000000u : 0u);
+                s.upack = K - M;                         // field-wise: no borrow, every M field <= its K field
+                s.count = count;
+                s.spare0 = s.spare1 = 0;
+                s.re[0] = re0; s.im[0] = im0;
+                s.re[1] = re1; s.im[1] = im1;
+                s.re[2] = re2; s.im[2] = im2;
+                s.mn[0] = mn0; s.mn[1] = mn1; s.mn[2] = mn2;
+                s.edge[0] = ld_cov(src);
+                s.edge[1] = len >= 2 ? ld_cov(src + 1) : 0;
+                s.edge[2] = len >= 2 ? ld_cov(src + len - 2) : 0;
+                s.edge[3] = ld_cov(src + len - 1);
+                args.out[atom] = s;
+            }
         }
         __syncwarp();
     }
@@ -1030,6 +1034,8 @@ struct ComposeArgs {
     const uint64_t* ref_ent;           // (slot offset << 24) | len in PROFILE order; offset kZeroOff: zeros
     const uint32_t* ref_atom;          // atom id of the ref (unused for zero refs)
     const AtomSummary* summaries;
+    const uint8_t* atom_nonzero;       // written by phase A: 0 = the atom reads as zeros, its summary is stale
+    int want_min;                      // per-frame minima needed (min_codon column or --min_reads_per_codon > 0)
     const int32_t* orf_len;
     long long orf_lo;
     const int32_t* list;               // ORF ids to score
@@ -1090,15 +1096,30 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
 
     int P = 0;             // profile offset of the current ref
     int x = 0, y = 0;      // profile values at P - 2 and P - 1
-    uint64_t ent = n_refs ? __ldg(args.ref_ent + begin) : 0;
-    unsigned atom = n_refs ? __ldg(args.ref_atom + begin) : 0;
+    // software pipeline: (entry, atom id) two refs ahead, the atom's non-zero flag one ref ahead
+    uint64_t ent = 0, ent_n = 0;
+    unsigned atom = 0, atom_n = 0;
+    bool nz = false;
+    if (n_refs > 0) {
+        ent = __ldg(args.ref_ent + begin);
+        atom = __ldg(args.ref_atom + begin);
+    }
+    if (n_refs > 1) {
+        ent_n = __ldg(args.ref_ent + begin + 1);
+        atom_n = __ldg(args.ref_atom + begin + 1);
+    }
+    if (n_refs > 0 && (ent >> kLenBits) != kZeroOff) nz = __ldg(args.atom_nonzero + atom) != 0;
     for (int j = 0; j < n_refs; ++j) {
         const int len = (int)(ent & kLenMask);
-        const bool zero = (ent >> kLenBits) == kZeroOff;
+        const bool zero = !nz;                  // reads-as-zero stretch or an atom without a single read
         const AtomSummary* s = args.summaries + atom;
-        if (j + 1 < n_refs) {     // next ref's entry and atom id while this summary is in flight
-            ent = __ldg(args.ref_ent + begin + j + 1);
-            atom = __ldg(args.ref_atom + begin + j + 1);
+        ent = ent_n;
+        atom = atom_n;
+        nz = false;
+        if (j + 1 < n_refs && (ent >> kLenBits) != kZeroOff) nz = __ldg(args.atom_nonzero + atom) != 0;
+        if (j + 2 < n_refs) {
+            ent_n = __ldg(args.ref_ent + begin + j + 2);
+            atom_n = __ldg(args.ref_atom + begin + j + 2);
         }
         int a0 = 0, a1 = 0, z0 = 0, z1 = 0;    // first two / last two values of the ref in profile order
         if (!zero) {
@@ -1106,14 +1127,15 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
             const double2 r2i0 = __ldg(reinterpret_cast<const double2*>(s) + 1);     // re[2], im[0]
             const double2 i12 = __ldg(reinterpret_cast<const double2*>(s) + 2);      // im[1], im[2]
             const int4 edge = __ldg(reinterpret_cast<const int4*>(s) + 3);
-            const uint4 mc = __ldg(reinterpret_cast<const uint4*>(s) + 4);           // mn[0..2], count
-            const uint4 ku = __ldg(reinterpret_cast<const uint4*>(s) + 5);           // K, U (u16 x 6), flags
+            const uint4 ku = __ldg(reinterpret_cast<const uint4*>(s) + 4);           // kpack, upack, count
+            uint4 mc = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
+            if (args.want_min) mc = __ldg(reinterpret_cast<const uint4*>(s) + 5);    // mn[0..2]
             const double sre[3] = {r01.x, r01.y, r2i0.x}, sim[3] = {r2i0.y, i12.x, i12.y};
             const unsigned smn[3] = {mc.x, mc.y, mc.z};
-            const unsigned sK[3] = {ku.x & 0xffffu, ku.x >> 16, ku.y & 0xffffu};
-            const unsigned sU[3] = {ku.y >> 16, ku.z & 0xffffu, ku.z >> 16};
-            big |= (ku.w & 1u) != 0;
-            count += mc.w;
+            const unsigned sK[3] = {ku.x & 1023u, (ku.x >> 10) & 1023u, (ku.x >> 20) & 1023u};
+            const unsigned sU[3] = {ku.y & 1023u, (ku.y >> 10) & 1023u, (ku.y >> 20) & 1023u};
+            big |= (ku.x >> 31) != 0;
+            count += ku.z;
             if (rev) { a0 = edge.w; a1 = edge.z; z0 = edge.y; z1 = edge.x; }
             else { a0 = edge.x; a1 = edge.y; z0 = edge.z; z1 = edge.w; }
             // local frame fl (window start offset inside the atom, mod 3) -> profile frame f:
