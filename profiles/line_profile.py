@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Join an ncu SASS source page with nvdisasm line info -> per-source-line instruction counts.
 
-usage: line_profile.py <report.ncu-rep> <kernel-symbol-substring> [top]
+usage: line_profile.py <report.ncu-rep> <kernel-symbol-substring> [top] [ncu-kernel-regex]
+(the regex selects the kernel inside a report that holds several, e.g. "bin_psites")
 Needs: ncu, cuobjdump, nvdisasm; the .so must be the one that was profiled (-lineinfo build).
 """
 import csv
@@ -35,12 +36,15 @@ for ln in dis.splitlines():
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
     if m:
         lines.append((cur, m.group(2).strip()))
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+flt = ["-k", "regex:" + sys.argv[4]] if len(sys.argv) > 4 else []
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + flt, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
 H = rows[hdr]
 ie, smp = H.index("Instructions Executed"), H.index("# Samples")
 sass = rows[hdr + 1:]
+end = next((i for i, r in enumerate(sass) if r and r[0] == 'Kernel Name'), len(sass))   # a report may repeat the kernel
+sass = sass[:end]
 assert len(sass) == len(lines), (len(sass), len(lines))
 src = open(os.environ.get("LINE_PROFILE_SRC", os.path.join(root, "ribotricer_b200", "csrc", "rt_kernels.cuh"))).read().splitlines()
 agg = {}

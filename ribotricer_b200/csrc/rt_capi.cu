@@ -46,8 +46,7 @@ struct rt_ctx {
     int pad = 0;
     int64_t plane = 0;
     std::vector<int64_t> contig_len, contig_base;
-    long long* d_contig_len = nullptr;
-    long long* d_contig_base = nullptr;
+    int2* d_contig_tab = nullptr;                    // per contig: (length, first slot >> 5)
 
     // read-length table
     int32_t* d_len_table = nullptr;
@@ -79,6 +78,7 @@ struct rt_ctx {
     // compact layout: the coverage buffer holds the exon union only (atoms back to back, genome order)
     int layout = RT_LAYOUT_DENSE;
     int64_t compact_elems = 0;                       // int32 elements of a compact coverage buffer (with guard)
+    unsigned* d_cbits = nullptr;                     // one bit per cmap word: the word has members
     uint2* d_cmap = nullptr;                         // per 32 dense slots: member mask | compact index after the last member
     uint64_t* d_atoms_c = nullptr;                   // the same tables with compact slot offsets
     uint64_t* d_ref_ent_c = nullptr;
@@ -325,8 +325,7 @@ int rt_create(int device, rt_ctx** out) {
 void rt_destroy(rt_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
-    cudaFree(ctx->d_contig_len);
-    cudaFree(ctx->d_contig_base);
+    cudaFree(ctx->d_contig_tab);
     cudaFree(ctx->d_len_table);
     cudaFree(ctx->d_orf_desc);
     cudaFree(ctx->d_orf_len);
@@ -338,6 +337,7 @@ void rt_destroy(rt_ctx* ctx) {
     cudaFree(ctx->d_summaries);
     cudaFree(ctx->d_atom_nonzero);
     cudaFree(ctx->d_cmap);
+    cudaFree(ctx->d_cbits);
     cudaFree(ctx->d_atoms_c);
     cudaFree(ctx->d_ref_ent_c);
     cudaFree(ctx->d_exon_entries_c);
@@ -381,18 +381,14 @@ int rt_set_genome(rt_ctx* ctx, int n_contig, const int64_t* h_contig_len, int pa
         at += (h_contig_len[c] + 2ll * pad + 1 + 31) / 32 * 32;
     }
     ctx->plane = n_contig ? at : 32;
-    if (2 * ctx->plane >= (int64_t)rt::kZeroOff)
-        return fail(ctx, RT_EINVAL, "rt_set_genome: genome too large for the 40-bit slot encoding");
-    cudaFree(ctx->d_contig_len);
-    cudaFree(ctx->d_contig_base);
-    ctx->d_contig_len = ctx->d_contig_base = nullptr;
-    size_t bytes = sizeof(long long) * std::max(1, n_contig);
-    RT_CUDA(ctx, cudaMalloc(&ctx->d_contig_len, bytes));
-    RT_CUDA(ctx, cudaMalloc(&ctx->d_contig_base, bytes));
-    if (n_contig) {
-        RT_CUDA(ctx, cudaMemcpy(ctx->d_contig_len, ctx->contig_len.data(), bytes, cudaMemcpyHostToDevice));
-        RT_CUDA(ctx, cudaMemcpy(ctx->d_contig_base, ctx->contig_base.data(), bytes, cudaMemcpyHostToDevice));
-    }
+    if (2 * ctx->plane >= (int64_t)rt::kZeroOff || 2 * ctx->plane / 32 >= 0xffffffffll)
+        return fail(ctx, RT_EINVAL, "rt_set_genome: genome too large (2 x plane must stay below 2^37 slots)");
+    cudaFree(ctx->d_contig_tab);
+    ctx->d_contig_tab = nullptr;
+    std::vector<int2> tab((size_t)std::max(1, n_contig));
+    for (int c = 0; c < n_contig; ++c) tab[c] = make_int2((int)h_contig_len[c], (int)(ctx->contig_base[c] >> 5));
+    RT_CUDA(ctx, cudaMalloc(&ctx->d_contig_tab, sizeof(int2) * tab.size()));
+    RT_CUDA(ctx, cudaMemcpy(ctx->d_contig_tab, tab.data(), sizeof(int2) * tab.size(), cudaMemcpyHostToDevice));
     // a new genome invalidates the index encoding
     ctx->n_orf = 0;
     ctx->layout = RT_LAYOUT_DENSE;
@@ -450,8 +446,12 @@ int rt_set_layout(rt_ctx* ctx, int layout) {
                 rt::build_cmap_kernel<<<grid, 256>>>(ctx->d_atoms, ctx->d_atoms_c, ctx->n_atoms, ctx->d_cmap);
                 ctx->launches++;
                 RT_CUDA(ctx, cudaGetLastError());
-                RT_CUDA(ctx, cudaDeviceSynchronize());
             }
+            RT_CUDA(ctx, cudaMalloc(&ctx->d_cbits, sizeof(unsigned) * ((words + 31) / 32)));
+            rt::build_cbits_kernel<<<(unsigned)((words + 255) / 256), 256>>>(ctx->d_cmap, (long long)words, ctx->d_cbits);
+            ctx->launches++;
+            RT_CUDA(ctx, cudaGetLastError());
+            RT_CUDA(ctx, cudaDeviceSynchronize());
         }
     }
     ctx->layout = layout;
@@ -519,16 +519,16 @@ int rt_bin_reads(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* d_ref_id
     a.weight = weight;
     a.len_base = ctx->len_base;
     a.len_table = ctx->d_len_table;
-    a.contig_base = ctx->d_contig_base;
-    a.contig_len = ctx->d_contig_len;
+    a.contig_tab = ctx->d_contig_tab;
     a.n_contig = ctx->n_contig;
     a.pad = ctx->pad;
-    a.plane = ctx->plane;
+    a.plane_words = (unsigned)(ctx->plane >> 5);
     a.stats = reinterpret_cast<unsigned long long*>(d_stats);
     a.len_counts = reinterpret_cast<unsigned long long*>(d_len_counts);
     a.touched = nullptr;
     a.n_touched = nullptr;
     a.cmap = ctx->layout == RT_LAYOUT_COMPACT ? ctx->d_cmap : nullptr;
+    a.cbits = ctx->d_cbits;
     if (ctx->track_touched && weight == 1 && !a.cmap) {
         int rc = ensure_touched_capacity(ctx, ctx->touched_reserved + n);
         if (rc != RT_OK) return rc;
@@ -539,7 +539,8 @@ int rt_bin_reads(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* d_ref_id
     const int64_t per_block = (int64_t)rt::kBinThreads * rt::kBinReadsPerThread;
     const int64_t blocks = (n + per_block - 1) / per_block;
     if (blocks > 0x7fffffff) return fail(ctx, RT_EINVAL, "rt_bin_reads: n too large for one launch");
-    rt::bin_psites_kernel<<<(unsigned)blocks, rt::kBinThreads, 0, (cudaStream_t)stream>>>(a);
+    if (a.cmap) rt::bin_psites_kernel<true><<<(unsigned)blocks, rt::kBinThreads, 0, (cudaStream_t)stream>>>(a);
+    else rt::bin_psites_kernel<false><<<(unsigned)blocks, rt::kBinThreads, 0, (cudaStream_t)stream>>>(a);
     ctx->launches++;
     RT_CUDA(ctx, cudaGetLastError());
     return RT_OK;
@@ -677,10 +678,12 @@ int rt_set_index(rt_ctx* ctx, int64_t n_orf, const int64_t* h_exon_ptr, const in
     cudaFree(ctx->d_atom_nonzero);
     ctx->d_atom_nonzero = nullptr;
     cudaFree(ctx->d_cmap);
+    cudaFree(ctx->d_cbits);
     cudaFree(ctx->d_atoms_c);
     cudaFree(ctx->d_ref_ent_c);
     cudaFree(ctx->d_exon_entries_c);
     ctx->d_cmap = nullptr;
+    ctx->d_cbits = nullptr;
     ctx->d_atoms_c = ctx->d_ref_ent_c = ctx->d_exon_entries_c = nullptr;
     ctx->layout = RT_LAYOUT_DENSE;
     ctx->compact_elems = 0;

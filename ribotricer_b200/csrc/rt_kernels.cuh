@@ -8,6 +8,7 @@
 // All "file:line" citations are relative to the reference tree.
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
 #include <stdint.h>
 
 #include "ribotricer_b200.h"
@@ -942,12 +943,13 @@ atom_summary_kernel(const AtomArgs args) {
             ptr += RNT;
             left -= RNT;
         };
-        int c0, c1, c2;
+        int c0, c1, c2, n0, n1, n2;                  // rounds r and r + 1; round r + 2 is loaded while r is processed
         load3(c0, c1, c2);
+        load3(n0, n1, n2);
         int p = 3 * sl;
         for (int r = 0; r < rounds; ++r, p += RNT) {
-            int n0, n1, n2;
-            load3(n0, n1, n2);
+            int m0, m1, m2;
+            load3(m0, m1, m2);
             const int v3 = __shfl_sync(kFull, sl == 0 ? n0 : c0, nbr);
             const int v4 = __shfl_sync(kFull, sl == 0 ? n1 : c1, nbr);
             if (p < len) {
@@ -987,6 +989,7 @@ atom_summary_kernel(const AtomArgs args) {
                 }
             }
             c0 = n0; c1 = n1; c2 = n2;
+            n0 = m0; n1 = m1; n2 = m2;
         }
         const unsigned K = group_sum_u32<LPO>(accK), M = group_sum_u32<LPO>(accM);
         const unsigned count = group_sum_u32<LPO>(cnt32);
@@ -1269,12 +1272,12 @@ struct BinArgs {
     unsigned long long* touched;   // optional: every 32 B sector (slot >> 3) that received an atomic (duplicates allowed)
     unsigned long long* n_touched;
     const uint2* cmap;             // compact layout: per 32 dense slots (member mask, compact index after the last member)
+    const unsigned* cbits;         // compact layout: one bit per cmap word, set when the word has members (L2 resident)
     const int32_t* len_table;      // RT_LEN_TABLE
-    const long long* contig_base;  // n_contig
-    const long long* contig_len;   // n_contig
+    const int2* contig_tab;        // n_contig x (length, first slot of the contig >> 5)
     int n_contig;
     int pad;
-    long long plane;
+    unsigned plane_words;          // plane >> 5
     unsigned long long* stats;       // RT_N_STATS
     unsigned long long* len_counts;  // RT_LEN_TABLE
 };
@@ -1290,18 +1293,30 @@ constexpr int kBinReadsPerThread = RT_BIN_RPT;
 constexpr int kLenHist = 512;   // read lengths below this are histogrammed in shared memory
 
 // Category of one read after the cascade of bam.py:77-91: one of RT_ST_QCFAIL .. RT_ST_VALID.
+// The four flag tests are one lookup: index = unmapped | secondary << 1 | qcfail << 2 | duplicate << 3.
+__host__ __device__ constexpr unsigned long long flag_cascade_lut() {
+    unsigned long long t = 0;
+    for (int i = 0; i < 16; ++i) {
+        int cat = 0;
+        if (i & 4) cat = RT_ST_QCFAIL;           // bam.py:77
+        else if (i & 8) cat = RT_ST_DUPLICATE;   // bam.py:80
+        else if (i & 2) cat = RT_ST_SECONDARY;   // bam.py:83
+        else if (i & 1) cat = RT_ST_UNMAPPED;    // bam.py:86
+        t |= (unsigned long long)cat << (4 * i);
+    }
+    return t;
+}
 __device__ __forceinline__ int classify_read(unsigned fl, unsigned mapq, unsigned nh) {
-    if (fl & 0x200) return RT_ST_QCFAIL;      // bam.py:77
-    if (fl & 0x400) return RT_ST_DUPLICATE;   // bam.py:80
-    if (fl & 0x100) return RT_ST_SECONDARY;   // bam.py:83
-    if (fl & 0x4) return RT_ST_UNMAPPED;      // bam.py:86
-    // is_read_uniq_mapping, common.py:33-69 (None is falsy -> counted as multi, bam.py:89)
-    bool uniq;
-    if (nh != 0) uniq = nh == 1;              // common.py:54-56
-    else uniq = mapq == 255;                  // common.py:59-69: every other branch is falsy
-    return uniq ? RT_ST_VALID : RT_ST_MULTI;
+    constexpr unsigned long long kLut = flag_cascade_lut();
+    const unsigned idx = ((fl >> 2) & 1u) | ((fl >> 7) & 0xeu);
+    const int cat = (int)((kLut >> (4 * idx)) & 15ull);
+    // is_read_uniq_mapping, common.py:33-69 (None is falsy -> counted as multi, bam.py:89):
+    // NH present decides (common.py:54-56), else only MAPQ 255 is unique (common.py:59-69)
+    const bool uniq = nh != 0 ? nh == 1 : mapq == 255;
+    return cat ? cat : (uniq ? RT_ST_VALID : RT_ST_MULTI);
 }
 
+template <bool Compact>
 __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a) {
     __shared__ unsigned int s_stats[RT_N_STATS];
     __shared__ unsigned int s_len[kLenHist];
@@ -1313,6 +1328,8 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
     if (threadIdx.x < RT_N_STATS) s_stats[threadIdx.x] = 0;
     __syncthreads();
 
+    using slot_t = typename std::conditional<Compact, unsigned, long long>::type;
+    constexpr slot_t kNone = (slot_t)-1;
     const int lane = threadIdx.x & 31;
     const long long block_base = (long long)blockIdx.x * (kBinThreads * kBinReadsPerThread);
     // per-thread 4-bit counters of categories RT_ST_QCFAIL..RT_ST_BADREF (<= 8 reads per thread)
@@ -1340,55 +1357,62 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
         for (int j = 0; j < kBatch; ++j) {
             const long long i = block_base + (long long)(it0 + j) * kBinThreads + threadIdx.x;
             int len = -1;            // >= 0: counts in read_length_counts
-            long long slot = -1;     // >= 0: coverage slot to bump
+            slot_t slot = kNone;     // coverage slot to bump
             if (i < a.n) {
                 int cat = classify_read(fl[j], mq[j], nh[j]);
                 if (cat == RT_ST_VALID) {
                     const int l = (int)ml[j];                       // bam.py:99
                     const int mode = __ldg(a.len_table + l);
                     const bool rev = (fl[j] & 0x10) != 0;           // bam.py:94
-                    int strand;
-                    long long pos;
-                    if (a.protocol == RT_PROTOCOL_FORWARD) {        // bam.py:105-117
-                        strand = rev ? 1 : 0;
-                        pos = rev ? la[j] : fi[j];
-                    } else {                                        // bam.py:118-131
-                        strand = rev ? 0 : 1;
-                        pos = rev ? fi[j] : la[j];
-                    }
+                    // forward protocol: '+' reads sit on their 5' end = first position (bam.py:105-117);
+                    // reverse protocol swaps the strand and takes the other end (bam.py:118-131)
+                    const bool minus = rev == (a.protocol == RT_PROTOCOL_FORWARD);
+                    const int pos = minus ? la[j] : fi[j];
                     const int c = rid[j];
                     if (mode == RT_LEN_FILTERED || a.protocol > RT_PROTOCOL_REVERSE) {
                         cat = 0;                                    // bam.py:101 / no protocol branch: only `total`
-                    } else if (c < 0 || c >= a.n_contig) {
+                    } else if ((unsigned)c >= (unsigned)a.n_contig) {
                         cat = RT_ST_BADREF;                         // chrom is None, bam.py:133
                     } else {
                         len = l;                                    // bam.py:136
                         if (mode >= 0) {                            // detect_orfs.py:74
-                            const long long p = pos + 1 + (strand == 0 ? mode : -mode);   // bam.py:135, detect_orfs.py:78-81
-                            if (p < 1 - a.pad || p > __ldg(a.contig_len + c) + a.pad) atomicAdd(&s_stats[RT_ST_OOB], 1u);
-                            else slot = (long long)strand * a.plane + __ldg(a.contig_base + c) + a.pad + p;
+                            const int2 ct = __ldg(a.contig_tab + c);
+                            // 1-based P-site p = pos + 1 +- offset (bam.py:135, detect_orfs.py:78-81);
+                            // q = p + pad - 1 is its 0-based place in the padded contig
+                            const unsigned q = (unsigned)(pos + (minus ? -mode : mode) + a.pad);
+                            if (q >= (unsigned)(ct.x + 2 * a.pad)) {
+                                atomicAdd(&s_stats[RT_ST_OOB], 1u);
+                            } else {
+                                const unsigned in_contig = q + 1u;                      // pad + p
+                                const unsigned w = (minus ? a.plane_words : 0u) + (unsigned)ct.y + (in_contig >> 5);
+                                const unsigned bit = in_contig & 31u;
+                                if (Compact) {   // rank of the slot inside the exon union, or no slot at all
+                                    if ((__ldg(a.cbits + (w >> 5)) >> (w & 31u)) & 1u) {
+                                        const uint2 m = __ldg(a.cmap + w);
+                                        const unsigned above = m.x >> bit;
+                                        if (above & 1u) slot = (slot_t)(m.y - (unsigned)__popc(above));
+                                    }
+                                } else {
+                                    slot = (slot_t)(((unsigned long long)w << 5) | bit);
+                                }
+                            }
                         }
                     }
                 }
                 if (cat) packed += 1u << (4 * (cat - 1));
             }
-            if (a.cmap && slot >= 0) {   // compact layout: rank of the slot inside the exon union, or no slot at all
-                const uint2 m = __ldg(a.cmap + (slot >> 5));
-                const unsigned above = m.x >> (unsigned)(slot & 31);
-                slot = (above & 1u) ? (long long)m.y - __popc(above) : -1;
-            }
             // detect_orfs.py:82: duplicated 5' ends are the rule in Ribo-seq and adjacent in a
             // coordinate-sorted BAM: the first lane of every run of equal slots adds the run length
-            const long long prev = __shfl_up_sync(kFull, slot, 1);
+            const slot_t prev = __shfl_up_sync(kFull, slot, 1);
             const bool head = lane == 0 || slot != prev;
             const unsigned heads = __ballot_sync(kFull, head);
-            if (head && slot >= 0) {
+            if (head && slot != kNone) {
                 const unsigned after = lane == 31 ? 0u : heads >> (lane + 1);
                 const int run = after ? __ffs(after) : 32 - lane;
                 atomicAdd(a.cov + slot, a.weight * run);
             }
-            if (a.touched) {   // remember the 32 B sector so the planes can be cleared sparsely afterwards
-                const long long sec = slot >= 0 ? slot >> 3 : -1;
+            if (!Compact && a.touched) {   // remember the 32 B sector so the planes can be cleared sparsely afterwards
+                const long long sec = slot != kNone ? (long long)(slot >> 3) : -1;
                 const long long prev_sec = __shfl_up_sync(kFull, sec, 1);
                 const bool shead = sec >= 0 && (lane == 0 || sec != prev_sec);
                 const unsigned writers = __ballot_sync(kFull, shead);
@@ -1432,7 +1456,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
         s_stats[RT_ST_TOTAL] = (unsigned)(left < kBinThreads * kBinReadsPerThread ? left : kBinThreads * kBinReadsPerThread);
     }
     __syncthreads();
-    if (a.touched) {   // one global atomic per block, then a coalesced copy of the block's slots
+    if (!Compact && a.touched) {   // one global atomic per block, then a coalesced copy of the block's slots
         if (threadIdx.x == 0) s_touch_base = atomicAdd(a.n_touched, (unsigned long long)s_ntouch);
         __syncthreads();
         for (unsigned i = threadIdx.x; i < s_ntouch; i += kBinThreads) a.touched[s_touch_base + i] = s_touch[i];
@@ -1462,6 +1486,13 @@ __global__ void __launch_bounds__(256) build_cmap_kernel(const uint64_t* __restr
             atomicMax(&cmap[w].y, (unsigned)(cb + (hi - off)));
         }
     }
+}
+
+__global__ void __launch_bounds__(256) build_cbits_kernel(const uint2* __restrict__ cmap, long long n_words, unsigned* cbits) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool member = w < n_words && cmap[w].x != 0u;
+    const unsigned bits = __ballot_sync(kFull, member);
+    if ((threadIdx.x & 31) == 0 && w < n_words) cbits[w >> 5] = bits;
 }
 
 // Sparse clear: zero the 32-byte sectors (8 slots) K1 touched since the last clear.  Whole sectors
