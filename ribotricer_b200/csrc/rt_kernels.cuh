@@ -900,8 +900,17 @@ __device__ __forceinline__ void slow_window(int x, int y, int z, unsigned& accK,
     unit_vector_add(A, B, f);
 }
 
+#ifndef RT_ATOM_MINBLOCKS
+#define RT_ATOM_MINBLOCKS 4
+#endif
+// Packs of G atoms are handed out through an atomic counter (the atoms of a plan window are sorted
+// by length, so a static split leaves warps idle).  The chain counter -> list[] -> atoms[] ->
+// coverage is four dependent memory round trips; it is software pipelined ACROSS packs: while pack k
+// is scanned the warp already holds the atom id of pack k+1, fetches its descriptor and the atom id
+// of pack k+2, and has the counter bump for pack k+3 in flight; the first coverage loads of pack
+// k+1 are issued before the reductions and the summary store of pack k.
 template <int LPO, bool WantMin>
-__global__ void __launch_bounds__(kScoreWarps * 32, 4)
+__global__ void __launch_bounds__(kScoreWarps * 32, RT_ATOM_MINBLOCKS)
 atom_summary_kernel(const AtomArgs args) {
     constexpr int G = 32 / LPO;
     constexpr int RNT = 3 * LPO;
@@ -911,41 +920,59 @@ atom_summary_kernel(const AtomArgs args) {
     const int lane = threadIdx.x & 31;
     const int sl = lane % LPO;
     const int gb = lane - sl;
+    const int grp = lane / LPO;
     const int nbr = sl + 1 == LPO ? gb : lane + 1;
     const long long n_packs = (args.n_list + G - 1) / G;
-    for (;;) {
-        unsigned long long pack = 0;
-        if (lane == 0) pack = atomicAdd(args.work_counter, 1ull);
-        pack = __shfl_sync(kFull, pack, 0);
-        if ((long long)pack >= n_packs) break;
-        const long long item = (long long)pack * G + lane / LPO;
-        const bool active = item < args.n_list;
-        int atom = 0, len = 0;
-        const int32_t* src = args.cov;
-        if (active) {
-            atom = __ldg(args.list + item);
-            const uint64_t ent = __ldg(args.atoms + atom);
-            len = (int)(ent & kLenMask);
-            src = args.cov + (ent >> kLenBits);
-        }
+    auto load_atom = [&](long long pk) -> int {           // atom id of this lane's group in pack pk, -1: none
+        const long long it = pk * G + grp;
+        return (pk < n_packs && it < args.n_list) ? __ldg(args.list + it) : -1;
+    };
+
+    // lane's three values of round r sit at src + 3 sl + r RNT; `left` = values from there to the atom's end
+    const int32_t* ptr = args.cov;
+    int left = 0;
+    auto load3 = [&](int& v0, int& v1, int& v2) {
+        v0 = left > 0 ? ld_cov(ptr) : 0;
+        v1 = left > 1 ? ld_cov(ptr + 1) : 0;
+        v2 = left > 2 ? ld_cov(ptr + 2) : 0;
+        ptr += RNT;
+        left -= RNT;
+    };
+
+    // ---- pipeline prologue: packs k, k+1, k+2 of this warp ----
+    unsigned long long raw = 0;
+    if (lane == 0) raw = atomicAdd(args.work_counter, 3ull);
+    raw = __shfl_sync(kFull, raw, 0);
+    long long pack = (long long)raw, pack1 = pack + 1;
+    unsigned long long raw2 = raw + 2;                    // lane 0's copy is the one that is read
+    int atom = load_atom(pack);
+    int atom1 = load_atom(pack1);
+    int len = 0;
+    const int32_t* src = args.cov;
+    if (atom >= 0) {
+        const uint64_t ent = __ldg(args.atoms + atom);
+        len = (int)(ent & kLenMask);
+        src = args.cov + (ent >> kLenBits);
+    }
+    int c0, c1, c2, n0, n1, n2;                           // rounds r and r + 1; round r + 2 is loaded while r is processed
+    ptr = src + 3 * sl;
+    left = len - 3 * sl;
+    load3(c0, c1, c2);
+    load3(n0, n1, n2);
+
+    while (pack < n_packs) {
+        // ---- descriptor of pack k+1, atom id of pack k+2, counter bump for pack k+3 ----
+        uint64_t ent1 = 0;
+        if (atom1 >= 0) ent1 = __ldg(args.atoms + atom1);
+        const long long pack2 = (long long)__shfl_sync(kFull, raw2, 0);
+        const int atom2 = load_atom(pack2);
+        if (lane == 0) raw2 = atomicAdd(args.work_counter, 1ull);
+
         FrameLane f0, f1, f2;                  // only the fp64 sums are used here
         unsigned accK = 0, accM = 0;           // 10-bit fields by local frame: kept windows, non-uniform windows
         unsigned cnt32 = 0, mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu;
         int ormask = 0;
         const int rounds = __reduce_max_sync(kFull, ((len + 2) / 3 + LPO - 1) / LPO);
-        // lane's three values of round r sit at src + 3 sl + r RNT; `left` = values from there to the atom's end
-        const int32_t* ptr = src + 3 * sl;
-        int left = len - 3 * sl;
-        auto load3 = [&](int& v0, int& v1, int& v2) {
-            v0 = left > 0 ? ld_cov(ptr) : 0;
-            v1 = left > 1 ? ld_cov(ptr + 1) : 0;
-            v2 = left > 2 ? ld_cov(ptr + 2) : 0;
-            ptr += RNT;
-            left -= RNT;
-        };
-        int c0, c1, c2, n0, n1, n2;                  // rounds r and r + 1; round r + 2 is loaded while r is processed
-        load3(c0, c1, c2);
-        load3(n0, n1, n2);
         int p = 3 * sl;
         for (int r = 0; r < rounds; ++r, p += RNT) {
             int m0, m1, m2;
@@ -991,6 +1018,22 @@ atom_summary_kernel(const AtomArgs args) {
             c0 = n0; c1 = n1; c2 = n2;
             n0 = m0; n1 = m1; n2 = m2;
         }
+
+        // ---- pack k+1 becomes current: its first two rounds are requested before pack k is reduced ----
+        const int atom_done = atom, len_done = len;
+        const int32_t* src_done = src;
+        atom = atom1;
+        len = (int)(ent1 & kLenMask);
+        src = args.cov + (ent1 >> kLenBits);
+        ptr = src + 3 * sl;
+        left = len - 3 * sl;
+        load3(c0, c1, c2);
+        load3(n0, n1, n2);
+        atom1 = atom2;
+        pack = pack1;
+        pack1 = pack2;
+
+        // ---- reductions and summary of the pack just scanned ----
         const unsigned K = group_sum_u32<LPO>(accK), M = group_sum_u32<LPO>(accM);
         const unsigned count = group_sum_u32<LPO>(cnt32);
 #pragma unroll
@@ -1008,8 +1051,8 @@ atom_summary_kernel(const AtomArgs args) {
             re1 = group_sum_f64<LPO>(f1.sre); im1 = group_sum_f64<LPO>(f1.sim);
             re2 = group_sum_f64<LPO>(f2.sre); im2 = group_sum_f64<LPO>(f2.sim);
         }
-        if (active && sl == 0) {
-            args.nonzero[atom] = ormask != 0;
+        if (atom_done >= 0 && sl == 0) {
+            args.nonzero[atom_done] = ormask != 0;
             if (ormask != 0) {
                 AtomSummary s;
                 s.kpack = K | ((ormask >> kBigShift) != 0 ? 0x80000000u : 0u);
@@ -1020,11 +1063,11 @@ atom_summary_kernel(const AtomArgs args) {
                 s.re[1] = re1; s.im[1] = im1;
                 s.re[2] = re2; s.im[2] = im2;
                 s.mn[0] = mn0; s.mn[1] = mn1; s.mn[2] = mn2;
-                s.edge[0] = ld_cov(src);
-                s.edge[1] = len >= 2 ? ld_cov(src + 1) : 0;
-                s.edge[2] = len >= 2 ? ld_cov(src + len - 2) : 0;
-                s.edge[3] = ld_cov(src + len - 1);
-                args.out[atom] = s;
+                s.edge[0] = ld_cov(src_done);
+                s.edge[1] = len_done >= 2 ? ld_cov(src_done + 1) : 0;
+                s.edge[2] = len_done >= 2 ? ld_cov(src_done + len_done - 2) : 0;
+                s.edge[3] = ld_cov(src_done + len_done - 1);
+                args.out[atom_done] = s;
             }
         }
         __syncwarp();

@@ -277,19 +277,41 @@ class Engine:
         self._check(self.lib.rt_score(self.ctx, C.c_void_p(cov.data_ptr()), int(lo), int(hi), C.byref(prm),
                                       C.byref(o), self._stream()))
 
+    def new_host_score_columns(self, n: int, diagnostics: bool = False, min_codon: bool = False) -> dict:
+        """Page-locked HOST result columns for ``score_host(..., out=...)``: the D2H copies inside
+        ``rt_score_host`` then run at full PCIe speed instead of being staged through pageable memory."""
+        t = self.torch
+        spec = dict(score=(t.float64, ()), valid=(t.int32, ()), count=(t.int64, ()), length=(t.int32, ()),
+                    status=(t.uint8, ()))
+        if min_codon or diagnostics:
+            spec["min_codon"] = (t.int32, ())
+        if diagnostics:
+            spec["frame_K"] = (t.int32, (3,))
+            spec["frame_s"] = (t.float64, (3,))
+        return {k: t.empty((n,) + shape, dtype=dt).pin_memory().numpy() for k, (dt, shape) in spec.items()}
+
     def score_host(self, cov, lo: int = 0, hi: int | None = None, params: ScoreParams | None = None,
-                   diagnostics: bool = False, min_codon: bool | None = None) -> dict:
+                   diagnostics: bool = False, min_codon: bool | None = None, out: dict | None = None) -> dict:
         """Score ORFs [lo, hi) and return HOST numpy columns (D2H inside the C call).  ``min_codon``
-        (minimum codon sum, not a reference output) is produced on request or with ``diagnostics``."""
+        (minimum codon sum, not a reference output) is produced on request or with ``diagnostics``.
+        ``out`` (from ``new_host_score_columns``) is filled and returned instead of fresh arrays."""
         hi = self.n_orf if hi is None else hi
         n = hi - lo
-        out = dict(score=np.empty(n, np.float64), valid=np.empty(n, np.int32), count=np.empty(n, np.int64),
-                   length=np.empty(n, np.int32), status=np.empty(n, np.uint8))
-        if min_codon or (min_codon is None and diagnostics):
-            out["min_codon"] = np.empty(n, np.int32)
-        if diagnostics:
-            out["frame_K"] = np.empty((n, 3), np.int32)
-            out["frame_s"] = np.empty((n, 3), np.float64)
+        if out is not None:
+            for k in ("score", "valid", "count", "length"):
+                if k not in out:
+                    raise ValueError(f"out lacks the required column {k!r}")
+            for k, a in out.items():
+                if len(a) != n or not a.flags["C_CONTIGUOUS"]:
+                    raise ValueError(f"out[{k!r}] must be a contiguous array of {n} rows")
+        else:
+            out = dict(score=np.empty(n, np.float64), valid=np.empty(n, np.int32), count=np.empty(n, np.int64),
+                       length=np.empty(n, np.int32), status=np.empty(n, np.uint8))
+            if min_codon or (min_codon is None and diagnostics):
+                out["min_codon"] = np.empty(n, np.int32)
+            if diagnostics:
+                out["frame_K"] = np.empty((n, 3), np.int32)
+                out["frame_s"] = np.empty((n, 3), np.float64)
         prm = (params or ScoreParams()).as_c()
         o = _lib.ScoreOut(*[_np_ptr(out[k]) if k in out else None
                             for k in ("score", "valid", "count", "length", "min_codon", "status", "frame_K", "frame_s")])
