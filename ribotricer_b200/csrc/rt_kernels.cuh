@@ -922,10 +922,11 @@ atom_summary_kernel(const AtomArgs args) {
     const int gb = lane - sl;
     const int grp = lane / LPO;
     const int nbr = sl + 1 == LPO ? gb : lane + 1;
-    const long long n_packs = (args.n_list + G - 1) / G;
-    auto load_atom = [&](long long pk) -> int {           // atom id of this lane's group in pack pk, -1: none
-        const long long it = pk * G + grp;
-        return (pk < n_packs && it < args.n_list) ? __ldg(args.list + it) : -1;
+    const unsigned n_list = (unsigned)args.n_list;        // < 2^32 atoms (rt_set_index)
+    const unsigned n_packs = (n_list + G - 1) / G;
+    auto load_atom = [&](unsigned pk) -> int {            // atom id of this lane's group in pack pk, -1: none
+        const unsigned it = pk * G + grp;
+        return (pk < n_packs && it < n_list) ? __ldg(args.list + it) : -1;
     };
 
     // lane's three values of round r sit at src + 3 sl + r RNT; `left` = values from there to the atom's end
@@ -943,8 +944,8 @@ atom_summary_kernel(const AtomArgs args) {
     unsigned long long raw = 0;
     if (lane == 0) raw = atomicAdd(args.work_counter, 3ull);
     raw = __shfl_sync(kFull, raw, 0);
-    long long pack = (long long)raw, pack1 = pack + 1;
-    unsigned long long raw2 = raw + 2;                    // lane 0's copy is the one that is read
+    unsigned pack = (unsigned)min(raw, 0xfffffff0ull), pack1 = pack + 1;
+    unsigned raw2 = pack + 2;                             // lane 0's copy is the one that is read
     int atom = load_atom(pack);
     int atom1 = load_atom(pack1);
     int len = 0;
@@ -954,19 +955,23 @@ atom_summary_kernel(const AtomArgs args) {
         len = (int)(ent & kLenMask);
         src = args.cov + (ent >> kLenBits);
     }
-    int c0, c1, c2, n0, n1, n2;                           // rounds r and r + 1; round r + 2 is loaded while r is processed
+    // Three register sets hold rounds r, r + 1, r + 2 and are refilled in turn (the round loop is unrolled
+    // by three so that no register is ever copied: a copy would wait for its load).  A set is requested
+    // right after it has been consumed, two rounds before its first two values are needed again.
+    int a0, a1, a2, b0, b1, b2, c0, c1, c2;
     ptr = src + 3 * sl;
     left = len - 3 * sl;
+    load3(a0, a1, a2);
+    load3(b0, b1, b2);
     load3(c0, c1, c2);
-    load3(n0, n1, n2);
 
     while (pack < n_packs) {
         // ---- descriptor of pack k+1, atom id of pack k+2, counter bump for pack k+3 ----
         uint64_t ent1 = 0;
         if (atom1 >= 0) ent1 = __ldg(args.atoms + atom1);
-        const long long pack2 = (long long)__shfl_sync(kFull, raw2, 0);
+        const unsigned pack2 = __shfl_sync(kFull, raw2, 0);
         const int atom2 = load_atom(pack2);
-        if (lane == 0) raw2 = atomicAdd(args.work_counter, 1ull);
+        if (lane == 0) raw2 = (unsigned)min(atomicAdd(args.work_counter, 1ull), 0xfffffff0ull);
 
         FrameLane f0, f1, f2;                  // only the fp64 sums are used here
         unsigned accK = 0, accM = 0;           // 10-bit fields by local frame: kept windows, non-uniform windows
@@ -974,49 +979,54 @@ atom_summary_kernel(const AtomArgs args) {
         int ormask = 0;
         const int rounds = __reduce_max_sync(kFull, ((len + 2) / 3 + LPO - 1) / LPO);
         int p = 3 * sl;
-        for (int r = 0; r < rounds; ++r, p += RNT) {
-            int m0, m1, m2;
-            load3(m0, m1, m2);
-            const int v3 = __shfl_sync(kFull, sl == 0 ? n0 : c0, nbr);
-            const int v4 = __shfl_sync(kFull, sl == 0 ? n1 : c1, nbr);
+        // one round: the lane's values (u0,u1,u2) at profile offsets p..p+2 of its atom, (w0,w1) = the same
+        // lane's first two values of the next round (what the last lane of a group hands to the first)
+        auto round = [&](int& u0, int& u1, int& u2, const int w0, const int w1) {
+            const int v3 = __shfl_sync(kFull, sl == 0 ? w0 : u0, nbr);
+            const int v4 = __shfl_sync(kFull, sl == 0 ? w1 : u1, nbr);
             if (p < len) {
-                cnt32 += (unsigned)c0 + (unsigned)c1 + (unsigned)c2;
-                const int o3 = c0 | c1 | c2;
+                cnt32 += (unsigned)u0 + (unsigned)u1 + (unsigned)u2;
+                const int o3 = u0 | u1 | u2;
                 ormask |= o3;
                 if (p + 4 < len) {                               // all three windows lie inside the atom
                     if (WantMin) {
-                        const unsigned s0 = (unsigned)c0 + (unsigned)c1 + (unsigned)c2;
-                        const unsigned s1 = (unsigned)c1 + (unsigned)c2 + (unsigned)v3;
-                        const unsigned s2 = (unsigned)c2 + (unsigned)v3 + (unsigned)v4;
+                        const unsigned s0 = (unsigned)u0 + (unsigned)u1 + (unsigned)u2;
+                        const unsigned s1 = (unsigned)u1 + (unsigned)u2 + (unsigned)v3;
+                        const unsigned s2 = (unsigned)u2 + (unsigned)v3 + (unsigned)v4;
                         mn0 = min(mn0, s0); mn1 = min(mn1, s1); mn2 = min(mn2, s2);
                     }
                     const int o5 = o3 | v3 | v4;
                     if (o5 != 0) {
                         if ((unsigned)o5 < (unsigned)kUvMax) {
-                            const int i0 = (c0 - c2) * kUvStride + (c1 - c2) + kUvCenter;
-                            const int i1 = (c1 - v3) * kUvStride + (c2 - v3) + kUvCenter;
-                            const int i2 = (c2 - v4) * kUvStride + (v3 - v4) + kUvCenter;
-                            const double2 u0 = s_uv[i0], u1 = s_uv[i1], u2 = s_uv[i2];
-                            f0.sre += u0.x; f0.sim += u0.y;
-                            f1.sre += u1.x; f1.sim += u1.y;
-                            f2.sre += u2.x; f2.sim += u2.y;
-                            accK += min((unsigned)o3, 1u) + (min((unsigned)(c1 | c2 | v3), 1u) << 10) +
-                                    (min((unsigned)(c2 | v3 | v4), 1u) << 20);
+                            const int i0 = (u0 - u2) * kUvStride + (u1 - u2) + kUvCenter;
+                            const int i1 = (u1 - v3) * kUvStride + (u2 - v3) + kUvCenter;
+                            const int i2 = (u2 - v4) * kUvStride + (v3 - v4) + kUvCenter;
+                            const double2 t0 = s_uv[i0], t1 = s_uv[i1], t2 = s_uv[i2];
+                            f0.sre += t0.x; f0.sim += t0.y;
+                            f1.sre += t1.x; f1.sim += t1.y;
+                            f2.sre += t2.x; f2.sim += t2.y;
+                            accK += min((unsigned)o3, 1u) + (min((unsigned)(u1 | u2 | v3), 1u) << 10) +
+                                    (min((unsigned)(u2 | v3 | v4), 1u) << 20);
                             accM += min((unsigned)(i0 ^ kUvCenter), 1u) + (min((unsigned)(i1 ^ kUvCenter), 1u) << 10) +
                                     (min((unsigned)(i2 ^ kUvCenter), 1u) << 20);
                         } else {
-                            slow_window<0>(c0, c1, c2, accK, accM, f0);
-                            slow_window<1>(c1, c2, v3, accK, accM, f1);
-                            slow_window<2>(c2, v3, v4, accK, accM, f2);
+                            slow_window<0>(u0, u1, u2, accK, accM, f0);
+                            slow_window<1>(u1, u2, v3, accK, accM, f1);
+                            slow_window<2>(u2, v3, v4, accK, accM, f2);
                         }
                     }
                 } else {                                         // ragged end of the atom
-                    if (p + 2 < len) { if (WantMin) mn0 = min(mn0, (unsigned)c0 + (unsigned)c1 + (unsigned)c2); slow_window<0>(c0, c1, c2, accK, accM, f0); }
-                    if (p + 3 < len) { if (WantMin) mn1 = min(mn1, (unsigned)c1 + (unsigned)c2 + (unsigned)v3); slow_window<1>(c1, c2, v3, accK, accM, f1); }
+                    if (p + 2 < len) { if (WantMin) mn0 = min(mn0, (unsigned)u0 + (unsigned)u1 + (unsigned)u2); slow_window<0>(u0, u1, u2, accK, accM, f0); }
+                    if (p + 3 < len) { if (WantMin) mn1 = min(mn1, (unsigned)u1 + (unsigned)u2 + (unsigned)v3); slow_window<1>(u1, u2, v3, accK, accM, f1); }
                 }
             }
-            c0 = n0; c1 = n1; c2 = n2;
-            n0 = m0; n1 = m1; n2 = m2;
+            p += RNT;
+            load3(u0, u1, u2);                                   // this set's next turn: three rounds on
+        };
+        for (int r = 0; r < rounds; r += 3) {
+            round(a0, a1, a2, b0, b1);
+            if (r + 1 < rounds) round(b0, b1, b2, c0, c1);
+            if (r + 2 < rounds) round(c0, c1, c2, a0, a1);
         }
 
         // ---- pack k+1 becomes current: its first two rounds are requested before pack k is reduced ----
@@ -1027,8 +1037,9 @@ atom_summary_kernel(const AtomArgs args) {
         src = args.cov + (ent1 >> kLenBits);
         ptr = src + 3 * sl;
         left = len - 3 * sl;
+        load3(a0, a1, a2);
+        load3(b0, b1, b2);
         load3(c0, c1, c2);
-        load3(n0, n1, n2);
         atom1 = atom2;
         pack = pack1;
         pack1 = pack2;
