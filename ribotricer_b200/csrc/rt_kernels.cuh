@@ -61,7 +61,11 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     return r;
 }
 
+#ifdef RT_PLAIN_LD
+__device__ __forceinline__ int ld_cov(const int32_t* p) { return *p; }
+#else
 __device__ __forceinline__ int ld_cov(const int32_t* p) { return __ldg(p); }
+#endif
 
 // Per-lane accumulators of one frame.  w1 / w2 pack 10-bit counters and are flushed into the
 // warp-uniform totals every kFlushTiles tiles; the fp64 sums live for the whole ORF.
@@ -909,6 +913,10 @@ __device__ __forceinline__ void slow_window(int x, int y, int z, unsigned& accK,
 // is scanned the warp already holds the atom id of pack k+1, fetches its descriptor and the atom id
 // of pack k+2, and has the counter bump for pack k+3 in flight; the first coverage loads of pack
 // k+1 are issued before the reductions and the summary store of pack k.
+#ifndef RT_ATOM_PF_DIST
+#define RT_ATOM_PF_DIST 0
+#endif
+constexpr unsigned kPfDist = RT_ATOM_PF_DIST;          // packs of look-ahead of the cooperative L2 prefetch (0: off)
 template <int LPO, bool WantMin>
 __global__ void __launch_bounds__(kScoreWarps * 32, RT_ATOM_MINBLOCKS)
 atom_summary_kernel(const AtomArgs args) {
@@ -948,6 +956,10 @@ atom_summary_kernel(const AtomArgs args) {
     unsigned raw2 = pack + 2;                             // lane 0's copy is the one that is read
     int atom = load_atom(pack);
     int atom1 = load_atom(pack1);
+    // cooperative L2 prefetch: packs are handed out in order, so the atoms of pack id + kPfDist will be
+    // scanned soon by SOME warp; every warp requests their lines now (two table lookups, one per turn)
+    int pf_atom = -1;
+    uint64_t pf_ent = 0;
     int len = 0;
     const int32_t* src = args.cov;
     if (atom >= 0) {
@@ -966,6 +978,17 @@ atom_summary_kernel(const AtomArgs args) {
     load3(c0, c1, c2);
 
     while (pack < n_packs) {
+        if (kPfDist > 0) {
+            const int pf_len = (int)(pf_ent & kLenMask);
+            const int32_t* pf_src = args.cov + (pf_ent >> kLenBits);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {                 // 128-byte lines 0..3 LPO-1 of the atom; longer atoms pipeline by themselves
+                const int o = 32 * (sl + q * LPO);
+                if (o < pf_len) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_src + o));
+            }
+            pf_ent = pf_atom >= 0 ? __ldg(args.atoms + pf_atom) : 0ull;
+            pf_atom = load_atom(pack + kPfDist);
+        }
         // ---- descriptor of pack k+1, atom id of pack k+2, counter bump for pack k+3 ----
         uint64_t ent1 = 0;
         if (atom1 >= 0) ent1 = __ldg(args.atoms + atom1);
