@@ -359,14 +359,18 @@ def run_ours(args):
     if rank == 0:
         achieved = score_bytes / (score_ms * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of the scoring kernel from the committed ncu capture
-        traffic, traffic_src = None, None
+        traffic, traffic_src, bin_traffic = None, None, None
         scan_path = os.environ.get("RT_SCORE_PATH") == "scan"
         kernel_names = ("score_orfs_packed_kernel",) if scan_path else ("atom_summary_kernel", "score_from_atoms_kernel")
         try:
             t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            if all(t[k].get("workload") == args.config for k in kernel_names) and args.scale == 1.0:
+            same = lambda e: e.get("workload") == args.config and e.get("layout", "dense") == args.layout  # noqa: E731
+            if all(same(t[k]) for k in kernel_names) and args.scale == 1.0:
                 traffic = sum(t[k]["dram_bytes"] for k in kernel_names)
-                traffic_src = "; ".join(t[k]["source"] for k in kernel_names)
+                traffic_src = "; ".join(sorted({t[k]["source"].split(" (")[0] for k in kernel_names})) + \
+                    " (ncu --set full, one launch of each kernel inside bench.py's step)"
+            if same(t.get("bin_psites_kernel", {})) and args.scale == 1.0:
+                bin_traffic = t["bin_psites_kernel"]["dram_bytes"]
         except Exception:
             pass
         line = {
@@ -392,7 +396,7 @@ def run_ours(args):
                          "algorithmic_bytes": score_bytes, "peak_source": peak_src,
                          "bin_psites": {"achieved": bin_bytes / (bin_ms * 1e-3) / 1e9,
                                         "frac": bin_bytes / (bin_ms * 1e-3) / 1e9 / hbm_peak,
-                                        "algorithmic_bytes": bin_bytes}},
+                                        "algorithmic_bytes": bin_bytes, "traffic": bin_traffic}},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "path": "Engine.clear_touched + bin_reads_host (rt_bin_reads_host) + score_host (rt_score_host)"},
