@@ -230,7 +230,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------- our arm
@@ -411,13 +411,27 @@ def run_ours(args):
                 line["cpu_closed_form"] = cpu_closed_form_run(args.config)
             except Exception as exc:   # the GPU numbers must still be reported
                 line["cpu_baseline"] = {"error": repr(exc)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    """The contract is ONE JSON line on stdout: libraries that write to fd 1 on their own (NCCL prints
+    its version banner there) are sent to stderr instead, see main()."""
+    (_JSON_OUT or sys.stdout).write(json.dumps(line) + "\n")
+    (_JSON_OUT or sys.stdout).flush()
+
+
 def main():
+    global _JSON_OUT
     args = parse_args()
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")   # the real stdout, for the JSON line only
+    os.dup2(2, 1)                           # everything else that writes to fd 1 goes to stderr
     if args.impl == "reference":
         run_reference(args)
     else:
