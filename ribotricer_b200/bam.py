@@ -9,7 +9,7 @@ environment, the same columns can also be loaded from a ``.npz`` file
 """
 from __future__ import annotations
 
-from collections import defaultdict
+from collections import Counter, defaultdict
 from dataclasses import dataclass
 
 import numpy as np
@@ -160,6 +160,23 @@ class Alignments:
         stats, lc = eng.new_bin_accumulators()
         eng.bin_reads_device(cov, self.dcols, self.protocol, stats, lc, self.sorted, n=self.n, weight=weight)
         return stats
+
+
+    def to_dict(self):
+        """The reference's ``alignments[length][strand][(chrom, pos)] -> count`` view (bam.py:29,135),
+        rebuilt by binning one read length at a time with offset 0.  Small libraries / tests only."""
+        from .detect_orfs import MergedAlignments
+
+        if not self.read_length_counts:
+            self.count()
+        eng = self.engine
+        out = defaultdict(lambda: defaultdict(Counter))
+        for length in sorted(self.read_length_counts):
+            cov = eng.new_coverage()
+            self.bin_into(cov, {length: 0})
+            for strand, ctr in MergedAlignments(eng, cov).to_dict().items():
+                out[length][strand] = ctr
+        return out
 
 
 def bam_summary_text(stats: dict, read_length_counts: dict) -> str:

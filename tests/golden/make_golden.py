@@ -12,9 +12,11 @@ Outputs (small, committed):
                                           orf_coverage (:134), export_orf_coverages
                                           (:206) and export_wig (:327) end to end
 
-``split_bam`` (bam.py:33) cannot be run anywhere in this image (no pysam, no
-BAM), so A1 has no golden vectors: it is covered by a line-by-line restatement
-only, and says so.
+  tests/golden/split_bam_case.json.gz     split_bam (bam.py:33-153) on a real BAM (bytes included)
+
+``split_bam`` needs pysam, which is absent from this image: it runs UNMODIFIED on top of
+oracle/pysam_restated.py, a pure-Python restatement of the handful of pysam calls it makes
+(``python tests/golden/make_golden.py split_bam`` regenerates only that file).
 """
 from __future__ import annotations
 
@@ -286,6 +288,85 @@ PARAM_SETS = [
 ]
 
 
+def split_bam_case(seed=1004):
+    """A BAM with every branch of bam.py:71-137 / common.py:33-69 in it, and what the unmodified
+    reference ``split_bam`` returns for it under several (protocol, read_lengths) settings."""
+    import base64
+    import io
+    from contextlib import redirect_stdout
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bam_writer as W
+
+    from ribotricer.bam import split_bam
+
+    rng = np.random.default_rng(seed)
+    refs = [("chrA", 5000), ("chrB", 3000), ("chrUn_1", 800)]
+    cigars = [
+        lambda L: [("M", L)],
+        lambda L: [("M", L // 2), ("N", int(rng.integers(50, 400))), ("M", L - L // 2)],
+        lambda L: [("S", 2), ("M", L), ("S", 1)],
+        lambda L: [("M", 10), ("I", 2), ("M", L - 10)],
+        lambda L: [("M", 8), ("D", 3), ("M", L - 8)],
+        lambda L: [("H", 5), ("=", L - 4), ("X", 1), ("M", 3)],
+        lambda L: [("M", 5), ("N", 100), ("M", 5), ("N", 80), ("M", L - 10)],
+    ]
+    flags = [0, 0, 0, 16, 16, 16, 256, 272, 512, 1024, 1040, 4, 20, 2048, 2064, 1, 83, 99, 147, 163, 528]
+    recs = []
+    hot = [(0, int(p)) for p in rng.integers(100, 4000, 12)] + [(1, int(p)) for p in rng.integers(100, 2500, 8)]
+    for k in range(1400):
+        if rng.random() < 0.55:                      # stacked 5' ends, the rule in Ribo-seq
+            ref_id, pos = hot[int(rng.integers(len(hot)))]
+            pos += int(rng.integers(0, 3))
+        else:
+            ref_id = int(rng.choice([0, 0, 0, 1, 1, 2]))
+            pos = int(rng.integers(0, refs[ref_id][1] - 700))
+        L = int(rng.integers(24, 36))
+        flag = int(rng.choice(flags))
+        mapq = int(rng.choice([255, 255, 255, 60, 3, 1, 0]))
+        tag_kind = int(rng.integers(0, 8))
+        aux = b""
+        if tag_kind == 0:
+            aux = W.aux_field("NH", "C", 1)
+        elif tag_kind == 1:
+            aux = W.aux_field("NH", "c", int(rng.choice([1, 2, 7])))
+        elif tag_kind == 2:
+            aux = W.aux_field("XS", "Z", "x") + W.aux_field("NH", "S", int(rng.choice([1, 300])))
+        elif tag_kind == 3:
+            aux = W.aux_field("NM", "i", 1) + W.aux_field("NH", "i", int(rng.choice([1, 4])))
+        elif tag_kind == 4:
+            aux = W.aux_field("AS", "C", 30) + W.aux_field("ZB", "Bs", [1, -2, 3])
+        if flag & 4:
+            ref_out, pos_out = (-1, -1) if rng.random() < 0.5 else (ref_id, pos)
+        else:
+            ref_out, pos_out = ref_id, pos
+        if k % 97 == 0 and not flag & 4:
+            ref_out = -1                             # mapped flag but no reference: chrom is None (bam.py:133)
+        cigar = cigars[int(rng.integers(len(cigars)))](L)
+        recs.append((ref_out if ref_out >= 0 else 1 << 30, pos_out,
+                     W.record(ref_out, pos_out, mapq, flag, cigar, name=b"r%d" % k, aux=aux)))
+    recs.sort(key=lambda r: (r[0], r[1]))
+    case = {"name": "split_bam", "refs": refs, "n_records": len(recs), "runs": []}
+    with tempfile.TemporaryDirectory() as tmp:
+        bam = os.path.join(tmp, "lib.bam")
+        W.write_bam(bam, refs, [r[2] for r in recs], sorted_header=True, block_payload=7001)
+        case["bam_b64"] = base64.b64encode(open(bam, "rb").read()).decode()
+        for protocol, read_lengths in (("forward", None), ("reverse", None), ("forward", [28, 29, 30]),
+                                       ("reverse", [26, 31, 33]), ("no", None)):
+            prefix = os.path.join(tmp, "out")
+            sink = io.StringIO()
+            with redirect_stdout(sink):              # is_read_uniq_mapping prints its warning per read
+                alignments, rlc = split_bam(bam, protocol, prefix, read_lengths)
+            flat = sorted([int(length), strand, chrom, int(pos), int(n)]
+                          for length, by_strand in alignments.items()
+                          for strand, ctr in by_strand.items() for (chrom, pos), n in ctr.items())
+            case["runs"].append({"protocol": protocol, "read_lengths": read_lengths, "alignments": flat,
+                                 "read_length_counts": {str(k): int(v) for k, v in rlc.items()},
+                                 "summary": open(f"{prefix}_bam_summary.txt").read(),
+                                 "warnings": sink.getvalue().count("WARNING")})
+    return case
+
+
 def run_reference_pipeline(case, ref):
     from collections import Counter, defaultdict
 
@@ -325,6 +406,15 @@ def run_reference_pipeline(case, ref):
 
 def main():
     ref = ref_import.load()
+    if "split_bam" in sys.argv[1:] or len(sys.argv) == 1:
+        sb = split_bam_case()
+        with gzip.open(os.path.join(HERE, "split_bam_case.json.gz"), "wt") as fh:
+            json.dump({"versions": versions(), "case": sb}, fh, separators=(",", ":"))
+        for r in sb["runs"]:
+            print("split_bam", r["protocol"], r["read_lengths"], "keys:", len(r["alignments"]),
+                  r["summary"].split("\n\nlength")[0].replace("\n\t", " "))
+        if len(sys.argv) > 1:
+            return
     from ribotricer.statistics import phasescore
 
     ps = {"versions": versions(), "cases": make_phasescore_cases(phasescore)}

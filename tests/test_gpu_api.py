@@ -174,3 +174,34 @@ def test_metagene_and_offset_inference(engine, tmp_path):
     assert len(rows) == len(case["index"]) + 1
     n_tr = sum(1 for r in rows[1:] if r.split("\t")[2:3] == ["translating"])
     assert n_tr > 0.5 * (len(case["index"]) - 1)
+
+
+@pytest.mark.gpu
+def test_split_bam_matches_reference(engine, tmp_path):
+    """A1 end to end on the GPU path: native BAM decode -> K1, against what the UNMODIFIED reference
+    split_bam (bam.py:33-153, run over oracle/pysam_restated.py) returned for the same BAM bytes."""
+    import base64
+
+    from ribotricer_b200 import bam as B
+    from ribotricer_b200.detect_orfs import merge_read_lengths
+
+    case = load_golden("split_bam_case.json.gz")["case"]
+    path = tmp_path / "golden.bam"
+    path.write_bytes(base64.b64decode(case["bam_b64"]))
+    for run in case["runs"]:
+        prefix = str(tmp_path / "out")
+        alignments, rlc = B.split_bam(str(path), run["protocol"], prefix, run["read_lengths"], engine=engine)
+        assert {str(k): int(v) for k, v in rlc.items()} == run["read_length_counts"]
+        assert open(prefix + "_bam_summary.txt").read() == run["summary"]
+        flat = sorted([int(length), strand, chrom, int(pos), int(n)] for length, by in alignments.to_dict().items()
+                      for strand, ctr in by.items() for (chrom, pos), n in ctr.items())
+        assert flat == run["alignments"], (run["protocol"], run["read_lengths"])
+        # merged over lengths with offsets (detect_orfs.py:54-83) == the same merge of the reference's dict
+        offsets = {int(k): 12 + (int(k) % 3) for k in run["read_length_counts"]}
+        merged = merge_read_lengths(alignments, offsets).to_dict()
+        want = {"+": {}, "-": {}}
+        for length, strand, chrom, pos, n in run["alignments"]:
+            key = (chrom, pos + offsets[length] if strand == "+" else pos - offsets[length])
+            want[strand][key] = want[strand].get(key, 0) + n
+        for strand in "+-":
+            assert dict(merged.get(strand, {})) == want[strand]

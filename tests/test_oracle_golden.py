@@ -191,3 +191,53 @@ def test_bin_reads_c_oracle_matches_py_restatement(built):
                     dense[(0 if s == "+" else 1) * plane + base[lut[c]] + PAD + p] += n
             assert (dense == cov).all()
             assert cst["oob"] == 0
+
+
+# ---- A1: split_bam (bam.py:33-153), pinned against the unmodified reference run on a real BAM ----
+def _golden_bam(tmp_path):
+    import base64
+
+    case = load_golden("split_bam_case.json.gz")["case"]
+    path = tmp_path / "golden.bam"
+    path.write_bytes(base64.b64decode(case["bam_b64"]))
+    return case, str(path)
+
+
+def test_split_bam_oracle_matches_reference(built, tmp_path):
+    """The A1 restatement (oracle_py.split_reads) on the columns the native decoder produces must
+    reproduce what the reference's own split_bam returned for the same BAM bytes: alignments by
+    (length, strand, chrom, pos), read_length_counts and the text of {prefix}_bam_summary.txt."""
+    from ribotricer_b200.bam import bam_summary_text, read_bam_columns_native
+
+    case, path = _golden_bam(tmp_path)
+    rc = read_bam_columns_native(path, 2)
+    assert [list(x) for x in zip(rc.contig_names, rc.contig_len.tolist())] == [list(r) for r in case["refs"]]
+    assert len(rc) == case["n_records"]
+    for run in case["runs"]:
+        alignments, rlc, st = O.split_reads(rc.cols, run["protocol"], run["read_lengths"], rc.contig_names)
+        flat = sorted([int(length), strand, chrom, int(pos), int(n)] for length, by in alignments.items()
+                      for strand, ctr in by.items() for (chrom, pos), n in ctr.items())
+        assert flat == run["alignments"], (run["protocol"], run["read_lengths"])
+        assert {str(k): int(v) for k, v in rlc.items()} == run["read_length_counts"]
+        assert bam_summary_text(st, rlc) == run["summary"]
+
+
+def test_native_decoder_matches_restated_pysam(built, tmp_path):
+    """Two independent BAM readers -- csrc/rt_bam.cpp and oracle/pysam_restated.py (pure Python, the
+    one the golden run used as ``pysam``) -- must yield the same seven columns for every record."""
+    from oracle import pysam_restated
+    from ribotricer_b200.bam import read_bam_columns_native
+
+    case, path = _golden_bam(tmp_path)
+    rc = read_bam_columns_native(path, 3)
+    bam = pysam_restated.AlignmentFile(path, "rb")
+    assert bam.count(until_eof=True) == len(rc)
+    for i, read in enumerate(bam.fetch(until_eof=True)):
+        pos = read.get_reference_positions()
+        nh = dict(read.get_tags()).get("NH", 0)
+        want = (read.reference_id, pos[0] if pos else -1, pos[-1] if pos else -1, len(pos), read.flag,
+                read.mapping_quality, min(nh, 255))
+        got = tuple(int(rc.cols[k][i]) for k in ("ref_id", "first", "last", "mlen", "flag", "mapq", "nh"))
+        if not pos:
+            want, got = want[:1] + want[3:], got[:1] + got[3:]
+        assert got == want, i
