@@ -479,3 +479,71 @@ def test_compact_layout_needs_an_index(engine):
     engine.set_genome(["c"], [1000], pad=32)
     with pytest.raises(RtError, match="rt_set_index first"):
         engine.set_layout("compact")
+
+
+def test_edge_cases_compact_layout(engine):
+    """The ragged index of test_edge_cases (unknown contig / strand, exons hanging off the contig ends,
+    1-nt exons, 70-exon ORFs, whole-contig ORFs) in the compact layout, with reads that land in the
+    pads, off the contigs and on unknown references: K1 keeps exactly the P-sites some ORF reads,
+    scores and profiles equal the dense layout's and the oracle's, and weight -1 undoes a library."""
+    CO = _oracle()
+    rng = np.random.default_rng(11)
+    lens = np.array([5000, 300], np.int64)
+    pad = 16
+    orfs = [
+        (0, 0, [(1, 1)]), (0, 1, [(10, 11)]), (0, 0, [(20, 22)]), (0, 1, [(30, 33)]),
+        (0, 0, [(40, 40), (42, 42), (44, 44), (46, 60)]),
+        (-1, 0, [(1, 90)]), (0, 2, [(1, 90)]),
+        (1, 0, [(-30, 30)]), (1, 1, [(280, 340)]), (1, 0, [(-50, -20)]), (1, 1, [(400, 450)]),
+        (0, 0, [(100, 100 + 767)]), (0, 1, [(100, 100 + 770)]), (0, 0, [(1, 4999)]), (0, 1, [(2, 5000)]),
+        (0, 0, [(s, s + 9) for s in range(1000, 1000 + 40 * 20, 20)]),
+        (0, 1, [(s, s + 6) for s in range(2000, 2000 + 70 * 9, 9)]),
+        (1, 0, [(5, 7), (9, 9), (11, 40)]), (1, 1, [(250, 300)]),
+    ]
+    ptr, st, en, contig, strand = [0], [], [], [], []
+    for c, s, ivs in orfs:
+        for a, b in ivs:
+            st.append(a)
+            en.append(b)
+        ptr.append(len(st))
+        contig.append(c)
+        strand.append(s)
+    idx = dict(exon_ptr=np.array(ptr, np.int64), exon_start=np.array(st, np.int32), exon_end=np.array(en, np.int32),
+               orf_contig=np.array(contig, np.int32), orf_strand=np.array(strand, np.uint8))
+    offsets = {27: 11, 28: 12, 29: 12, 30: 13}
+    base, plane = _setup(engine, ["a", "b"], lens, idx, offsets, pad=pad)
+    n = 60_000
+    ref_id = rng.choice([0, 0, 0, 1, 1, -1, 5], n).astype(np.int32)
+    mlen = rng.integers(26, 32, n).astype(np.uint16)
+    first = np.where(ref_id == 1, rng.integers(-40, 340, n), rng.integers(-40, 5040, n)).astype(np.int32)
+    reads = dict(ref_id=ref_id, first=first, last=(first + mlen - 1).astype(np.int32), mlen=mlen,
+                 flag=rng.choice([0, 16, 0, 16, 4, 256, 1024], n).astype(np.uint16),
+                 mapq=rng.choice([255, 255, 3], n).astype(np.uint8), nh=rng.choice([0, 1, 1, 2], n).astype(np.uint8))
+    lt = CO.make_len_table(offsets)
+    for protocol, code in (("forward", 0), ("reverse", 1)):
+        ref_cov, ref_stats, ref_len = CO.bin_reads(reads, code, lt, base, lens, pad, plane)
+        ref = CO.score(idx, ref_cov, base, lens, pad, plane, DEFAULT_PARAMS)
+        tie = CO.tie_mask(ref["frame_K"], ref["frame_s"])
+        _, rprof = CO.gather_profiles(idx, np.arange(len(orfs)), ref_cov, base, lens, pad, plane)
+        engine.set_layout("dense")
+        dense = engine.new_coverage()
+        stats_d, _ = engine.bin_reads_host(dense, reads, protocol)
+        assert stats_d == ref_stats and (dense.cpu().numpy() == ref_cov).all()
+        got_d = engine.score_host(dense, diagnostics=True, min_codon=True)
+        engine.set_layout("compact")
+        try:
+            cov = engine.new_coverage()
+            stats_c, len_c = engine.bin_reads_host(cov, reads, protocol)
+            assert stats_c == ref_stats and (len_c == ref_len).all()
+            got = engine.score_host(cov, diagnostics=True, min_codon=True)
+            compare_scores(got, ref, tie)
+            for k in got:
+                assert np.array_equal(got[k], got_d[k], equal_nan=True), k
+            _, prof = engine.gather_profiles(cov, np.arange(len(orfs)), got["length"])
+            assert (prof == rprof).all()
+            assert int(cov.sum().item()) <= int(ref_cov.sum()) and int(cov.sum().item()) > 0
+            st, lc = engine.new_bin_accumulators()           # take the library out again
+            engine.bin_reads_device(cov, engine.upload_reads(reads), protocol, st, lc, weight=-1)
+            assert int(cov.abs().max().item()) == 0
+        finally:
+            engine.set_layout("dense")
