@@ -744,8 +744,8 @@ int rt_shard_bounds(const rt_ctx* ctx, int n_shards, int64_t* h_bounds) {
 
 namespace {
 
-// ORFs of [lo, hi) sorted by length, longest first: the long ones go to the generic
-// warp-per-ORF kernel, the rest to the packed kernel (several ORFs per warp).
+// Work lists of the ORF range [lo, hi), cached per range: the ORF order for the scoring kernel and the
+// atoms the range touches for phase A.
 int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
     for (auto& p : ctx->plans)
         if (p.lo == lo && p.hi == hi) {
@@ -769,21 +769,21 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
             std::stable_sort(ids.begin() + begin, ids.end(), [&](int32_t x, int32_t y) { return refs_of(x) > refs_of(y); });
         }
     } else {
-    // long ORFs: all of them, longest first (they start first and run beside the packed kernel)
-    for (int64_t o = lo; o < hi; ++o)
-        if (len_of((int32_t)o) > rt::kPackMaxNt) ids.push_back((int32_t)o);
-    std::stable_sort(ids.begin(), ids.end(), [&](int32_t x, int32_t y) { return len_of(x) > len_of(y); });
-    n_long = (int64_t)ids.size();
-    // the rest: sorted by length inside windows of kPlanWindow consecutive index rows, so that the
-    // ORFs sharing a warp have similar lengths while neighbours in the index (nested ORFs, isoforms:
-    // same exons) are still scored close in time and meet in L2
-    constexpr int64_t kPlanWindow = 2048;
-    for (int64_t w0 = lo; w0 < hi; w0 += kPlanWindow) {
-        const size_t begin = ids.size();
-        for (int64_t o = w0; o < std::min(hi, w0 + kPlanWindow); ++o)
-            if (len_of((int32_t)o) <= rt::kPackMaxNt) ids.push_back((int32_t)o);
-        std::stable_sort(ids.begin() + begin, ids.end(), [&](int32_t x, int32_t y) { return len_of(x) > len_of(y); });
-    }
+        // scan path.  Long ORFs: all of them, longest first (they start first and run beside the packed kernel)
+        for (int64_t o = lo; o < hi; ++o)
+            if (len_of((int32_t)o) > rt::kPackMaxNt) ids.push_back((int32_t)o);
+        std::stable_sort(ids.begin(), ids.end(), [&](int32_t x, int32_t y) { return len_of(x) > len_of(y); });
+        n_long = (int64_t)ids.size();
+        // the rest: sorted by length inside windows of kPlanWindow consecutive index rows, so that the
+        // ORFs sharing a warp have similar lengths while neighbours in the index (nested ORFs, isoforms:
+        // same exons) are still scored close in time and meet in L2
+        constexpr int64_t kPlanWindow = 2048;
+        for (int64_t w0 = lo; w0 < hi; w0 += kPlanWindow) {
+            const size_t begin = ids.size();
+            for (int64_t o = w0; o < std::min(hi, w0 + kPlanWindow); ++o)
+                if (len_of((int32_t)o) <= rt::kPackMaxNt) ids.push_back((int32_t)o);
+            std::stable_sort(ids.begin() + begin, ids.end(), [&](int32_t x, int32_t y) { return len_of(x) > len_of(y); });
+        }
     }
     if (ctx->plans.size() >= 8) {   // bounded cache
         cudaFree(ctx->plans.front().d_list);
