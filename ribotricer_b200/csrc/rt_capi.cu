@@ -762,10 +762,17 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
         // two-phase path: one thread per ORF walks its atom refs, so the ORFs sharing a warp should hold
         // similar numbers of refs; sort by that inside windows of the index (neighbours share atoms)
         auto refs_of = [&](int32_t x) { return (ctx->h_orf_refs_desc[x] >> 40) & (uint64_t)rt::kMaxEntriesPerOrf; };
+        // ORFs with very many refs (giant transcripts) are serial work for one thread: they go first so that
+        // they run beside everything else instead of forming the tail of the launch
+        constexpr uint64_t kManyRefs = 64;
+        for (int64_t o = lo; o < hi; ++o)
+            if (refs_of((int32_t)o) > kManyRefs) ids.push_back((int32_t)o);
+        std::stable_sort(ids.begin(), ids.end(), [&](int32_t x, int32_t y) { return refs_of(x) > refs_of(y); });
         constexpr int64_t kPlanWindow = 2048;
         for (int64_t w0 = lo; w0 < hi; w0 += kPlanWindow) {
             const size_t begin = ids.size();
-            for (int64_t o = w0; o < std::min(hi, w0 + kPlanWindow); ++o) ids.push_back((int32_t)o);
+            for (int64_t o = w0; o < std::min(hi, w0 + kPlanWindow); ++o)
+                if (refs_of((int32_t)o) <= kManyRefs) ids.push_back((int32_t)o);
             std::stable_sort(ids.begin() + begin, ids.end(), [&](int32_t x, int32_t y) { return refs_of(x) > refs_of(y); });
         }
     } else {
