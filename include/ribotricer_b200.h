@@ -135,6 +135,28 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
                       const uint16_t* h_flag, const uint8_t* h_mapq, const uint8_t* h_nh,
                       int protocol, int sorted_hint, int64_t* h_stats, int64_t* h_len_counts);
 
+/*
+ * ---- K1 on PACKED read records: 11 B/read over PCIe instead of 18.  `first`, `last`, `mlen` are the
+ * columns above; `meta` (u8) replaces flag, mapq and nh -- bits 0-2 hold the outcome of the filter
+ * cascade (bam.py:77-91 + common.py:33-69), decided on the host: 0 = passed, else RT_ST_QCFAIL ..
+ * RT_ST_MULTI; bit 3 = is_reverse -- and ref_id is run-length coded: reads [run_start[r],
+ * run_start[r+1]) belong to reference run_ref[r] (a coordinate-sorted BAM has one run per reference).
+ * rt_pack_read_meta builds meta and the run table from the columns (RT_ESTATE if there are more than
+ * run_cap runs: the input is not grouped by reference, use rt_bin_reads_host).  Results are identical
+ * to rt_bin_reads on the same reads.  `read_base` = number of the launch's first read in the run table.
+ */
+int rt_pack_read_meta(int64_t n, const int32_t* h_ref_id, const uint16_t* h_flag, const uint8_t* h_mapq,
+                      const uint8_t* h_nh, uint8_t* h_meta, int64_t run_cap, int64_t* h_run_start /* run_cap+1 */,
+                      int32_t* h_run_ref /* run_cap */, int64_t* n_runs);
+int rt_bin_reads_packed(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* d_first, const int32_t* d_last,
+                        const uint16_t* d_mlen, const uint8_t* d_meta, int64_t read_base, int64_t n_runs,
+                        const int64_t* d_run_start, const int32_t* d_run_ref, int protocol, int weight,
+                        int64_t* d_stats, int64_t* d_len_counts, void* stream);
+int rt_bin_reads_packed_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_first, const int32_t* h_last,
+                             const uint16_t* h_mlen, const uint8_t* h_meta, int64_t n_runs,
+                             const int64_t* h_run_start, const int32_t* h_run_ref, int protocol,
+                             int64_t* h_stats, int64_t* h_len_counts);
+
 int rt_clear_coverage(rt_ctx* ctx, int32_t* d_cov, void* stream);
 
 /*

@@ -338,3 +338,47 @@ int rt_wig_block(rt_tsv* t, const char* chrom, int64_t n, const int64_t* pos, co
 int rt_wig_close(rt_tsv* t) { return rt_tsv_close(t); }
 
 }  // extern "C"
+
+// ---- packed read records (11 B/read instead of 18): the filter cascade is decided here, on the host ----
+#include <thread>
+
+extern "C" {
+
+int rt_pack_read_meta(int64_t n, const int32_t* ref_id, const uint16_t* flag, const uint8_t* mapq, const uint8_t* nh,
+                      uint8_t* meta, int64_t run_cap, int64_t* run_start, int32_t* run_ref, int64_t* n_runs) {
+    if (n < 0 || !n_runs || (n > 0 && (!ref_id || !flag || !mapq || !nh || !meta || !run_start || !run_ref)))
+        return RT_EINVAL;
+    // bam.py:77-91 + common.py:33-69, same order as classify_read() in rt_kernels.cuh
+    auto work = [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; ++i) {
+            const unsigned f = flag[i];
+            unsigned code;
+            if (f & 0x200) code = RT_ST_QCFAIL;
+            else if (f & 0x400) code = RT_ST_DUPLICATE;
+            else if (f & 0x100) code = RT_ST_SECONDARY;
+            else if (f & 0x4) code = RT_ST_UNMAPPED;
+            else code = (nh[i] != 0 ? nh[i] == 1 : mapq[i] == 255) ? 0u : (unsigned)RT_ST_MULTI;
+            meta[i] = (uint8_t)(code | ((f & 0x10) ? 8u : 0u));
+        }
+    };
+    const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(std::thread::hardware_concurrency(), n / (1 << 20)));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_thr; ++t) pool.emplace_back(work, n * t / n_thr, n * (t + 1) / n_thr);
+    for (auto& th : pool) th.join();
+    int64_t r = 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (i == 0 || ref_id[i] != ref_id[i - 1]) {
+            if (r >= run_cap) {
+                g_io_error = "rt_pack_read_meta: more reference runs than run_cap (input not grouped by reference?)";
+                return RT_ESTATE;
+            }
+            run_start[r] = i;
+            run_ref[r] = ref_id[i];
+            ++r;
+        }
+    if (n > 0) run_start[r] = n;
+    *n_runs = r;
+    return RT_OK;
+}
+
+}  // extern "C"

@@ -1342,6 +1342,13 @@ struct BinArgs {
     const uint16_t* flag;
     const uint8_t* mapq;
     const uint8_t* nh;
+    // packed records (Packed = true): `meta` replaces flag/mapq/nh (bits 0-2: RT_ST_QCFAIL..RT_ST_MULTI decided on the
+    // host, 0 = passed the cascade; bit 3: is_reverse) and ref_id is run-length coded over GLOBAL read numbers
+    const uint8_t* meta;
+    const long long* run_start;    // n_runs + 1
+    const int32_t* run_ref;        // n_runs
+    int n_runs;
+    long long read_base;           // global number of this launch's first read
     long long n;
     int protocol;
     int weight;                    // +1 bin, -1 un-bin
@@ -1393,13 +1400,25 @@ __device__ __forceinline__ int classify_read(unsigned fl, unsigned mapq, unsigne
     return cat ? cat : (uniq ? RT_ST_VALID : RT_ST_MULTI);
 }
 
-template <bool Compact>
+template <bool Compact, bool Packed>
 __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a) {
     __shared__ unsigned int s_stats[RT_N_STATS];
     __shared__ unsigned int s_len[kLenHist];
-    __shared__ unsigned long long s_touch[kBinThreads * kBinReadsPerThread];
+    __shared__ unsigned long long s_touch[Compact ? 1 : kBinThreads * kBinReadsPerThread];
     __shared__ unsigned int s_ntouch;
     __shared__ unsigned long long s_touch_base;
+    __shared__ int s_run;          // Packed: run of the block's first read, and whether the block sits inside it
+    __shared__ int s_one_run;
+    if (Packed && threadIdx.x == 0) {
+        const long long g0 = a.read_base + (long long)blockIdx.x * (kBinThreads * kBinReadsPerThread);
+        int lo = 0, hi = a.n_runs - 1;                       // last run with run_start <= g0
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (a.run_start[mid] <= g0) lo = mid; else hi = mid - 1;
+        }
+        s_run = lo;
+        s_one_run = g0 + kBinThreads * kBinReadsPerThread <= a.run_start[lo + 1];
+    }
     if (threadIdx.x == 0) s_ntouch = 0;
     for (int i = threadIdx.x; i < kLenHist; i += kBinThreads) s_len[i] = 0;
     if (threadIdx.x < RT_N_STATS) s_stats[threadIdx.x] = 0;
@@ -1422,13 +1441,19 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
         for (int j = 0; j < kBatch; ++j) {
             const long long i = block_base + (long long)(it0 + j) * kBinThreads + threadIdx.x;
             const bool in = i < a.n;
-            fl[j] = in ? a.flag[i] : 0u;
-            mq[j] = in ? a.mapq[i] : 0u;
-            nh[j] = in ? a.nh[i] : 0u;
+            if (Packed) {
+                fl[j] = in ? a.meta[i] : 0u;
+                mq[j] = nh[j] = 0u;
+                rid[j] = 0;
+            } else {
+                fl[j] = in ? a.flag[i] : 0u;
+                mq[j] = in ? a.mapq[i] : 0u;
+                nh[j] = in ? a.nh[i] : 0u;
+                rid[j] = in ? a.ref_id[i] : 0;
+            }
             ml[j] = in ? a.mlen[i] : 0u;
             fi[j] = in ? a.first[i] : 0;
             la[j] = in ? a.last[i] : 0;
-            rid[j] = in ? a.ref_id[i] : 0;
         }
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
@@ -1436,16 +1461,31 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
             int len = -1;            // >= 0: counts in read_length_counts
             slot_t slot = kNone;     // coverage slot to bump
             if (i < a.n) {
-                int cat = classify_read(fl[j], mq[j], nh[j]);
+                int cat;
+                bool rev;
+                if (Packed) {
+                    cat = (fl[j] & 7u) ? (int)(fl[j] & 7u) : RT_ST_VALID;
+                    rev = (fl[j] & 8u) != 0;
+                } else {
+                    cat = classify_read(fl[j], mq[j], nh[j]);
+                    rev = (fl[j] & 0x10) != 0;                      // bam.py:94
+                }
                 if (cat == RT_ST_VALID) {
                     const int l = (int)ml[j];                       // bam.py:99
                     const int mode = __ldg(a.len_table + l);
-                    const bool rev = (fl[j] & 0x10) != 0;           // bam.py:94
                     // forward protocol: '+' reads sit on their 5' end = first position (bam.py:105-117);
                     // reverse protocol swaps the strand and takes the other end (bam.py:118-131)
                     const bool minus = rev == (a.protocol == RT_PROTOCOL_FORWARD);
                     const int pos = minus ? la[j] : fi[j];
-                    const int c = rid[j];
+                    int c = rid[j];
+                    if (Packed) {
+                        int r = s_run;
+                        if (!s_one_run) {
+                            const long long g = a.read_base + i;
+                            while (r + 1 < a.n_runs && g >= __ldg(a.run_start + r + 1)) ++r;
+                        }
+                        c = __ldg(a.run_ref + r);
+                    }
                     if (mode == RT_LEN_FILTERED || a.protocol > RT_PROTOCOL_REVERSE) {
                         cat = 0;                                    // bam.py:101 / no protocol branch: only `total`
                     } else if ((unsigned)c >= (unsigned)a.n_contig) {
