@@ -31,7 +31,7 @@ txt = subprocess.run([py, os.path.join(HERE, "summarize.py"), rep], capture_outp
 open(os.path.join(HERE, f"{tag}_step_kernels.txt"), "w").write(txt)
 
 # 2. per-line profiles: (mangled symbol substring, ncu regex, file tag)
-KERNELS = [("bin_psites_kernelILb1E", "bin_psites", "bin_psites_kernel"),
+KERNELS = [("bin_psites_kernelILb1ELb0E", "bin_psites", "bin_psites_kernel"),
            ("atom_summary_kernelILi4ELb0E", "atom_summary", "atom_summary_kernel"),
            ("score_from_atoms_kernel", "score_from_atoms", "score_from_atoms_kernel")]
 for sym, rx, name in KERNELS:
