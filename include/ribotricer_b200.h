@@ -269,6 +269,9 @@ int64_t rt_bam_ref_len(const rt_bam* b, int i);
 int rt_bam_sorted(const rt_bam* b);                          /* @HD SO:coordinate */
 int rt_bam_copy(const rt_bam* b, int32_t* ref_id, int32_t* first, int32_t* last, uint16_t* mlen,
                 uint16_t* flag, uint8_t* mapq, uint8_t* nh); /* any pointer may be NULL */
+/* the decoded reads as packed records (rt_pack_read_meta on the decoder's own columns): meta[n_reads] and the
+ * run table; first / last / mlen come from rt_bam_copy */
+int rt_bam_pack(const rt_bam* b, uint8_t* meta, int64_t run_cap, int64_t* run_start, int32_t* run_ref, int64_t* n_runs);
 
 /* number of kernel launches issued through this ctx so far (bench.py's gpu_launches) */
 int64_t rt_launch_count(const rt_ctx* ctx);

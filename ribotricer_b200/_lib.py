@@ -27,7 +27,7 @@ EXPORTS = (
     "rt_index_free", "rt_index_n_orf", "rt_index_n_exon", "rt_index_n_annotated_prefix", "rt_index_n_chrom",
     "rt_index_chrom_name", "rt_index_copy", "rt_index_field", "rt_tsv_open", "rt_tsv_write", "rt_tsv_close",
     "rt_repr_double", "rt_wig_open", "rt_wig_block", "rt_wig_close", "rt_bam_last_error", "rt_bam_load", "rt_bam_free", "rt_bam_n_reads", "rt_bam_n_ref",
-    "rt_bam_ref_name", "rt_bam_ref_len", "rt_bam_sorted", "rt_bam_copy",
+    "rt_bam_ref_name", "rt_bam_ref_len", "rt_bam_sorted", "rt_bam_copy", "rt_bam_pack",
 )
 
 
@@ -129,6 +129,7 @@ def load():
     lib.rt_bam_ref_len.restype = i64
     lib.rt_bam_sorted.argtypes = [vp]
     lib.rt_bam_copy.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.rt_bam_pack.argtypes = [vp, vp, i64, vp, vp, C.POINTER(i64)]
     lib.rt_launch_count.restype = i64
     if lib.rt_abi_version() != 1:
         raise RtError(f"ABI mismatch: library reports {lib.rt_abi_version()}, binding expects 1")

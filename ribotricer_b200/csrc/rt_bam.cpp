@@ -296,4 +296,10 @@ int rt_bam_copy(const rt_bam* b, int32_t* ref_id, int32_t* first, int32_t* last,
     return RT_OK;
 }
 
+int rt_bam_pack(const rt_bam* b, uint8_t* meta, int64_t run_cap, int64_t* run_start, int32_t* run_ref, int64_t* n_runs) {
+    if (!b) return RT_EINVAL;
+    return rt_pack_read_meta((int64_t)b->ref_id.size(), b->ref_id.data(), b->flag.data(), b->mapq.data(), b->nh.data(),
+                             meta, run_cap, run_start, run_ref, n_runs);
+}
+
 }  // extern "C"
