@@ -95,6 +95,10 @@ struct rt_ctx {
         int32_t* d_fallback = nullptr;  // capacity n_short
         int64_t n_long = 0, n_short = 0;
         int32_t* d_atom_list = nullptr; // atoms the range touches, similar lengths adjacent
+        rt::RefSegment* d_segs = nullptr;      // segments of the ORFs with more than kSegRefs refs
+        rt::ComposeAcc* d_partials = nullptr;  // one per segment
+        unsigned* d_seg_done = nullptr;        // one per long ORF
+        int64_t n_segs = 0;
         int64_t n_atom_list = 0;
     };
     std::vector<ScorePlan> plans;
@@ -264,9 +268,7 @@ int build_atoms(rt_ctx* ctx, const std::vector<uint64_t>& desc, const std::vecto
     RT_CUDA(ctx, upload(&ctx->d_exon_entries_c, entries_c));
     RT_CUDA(ctx, cudaMalloc(&ctx->d_summaries, sizeof(rt::AtomSummary) * std::max<size_t>(1, ctx->h_atoms.size())));
     RT_CUDA(ctx, cudaMalloc(&ctx->d_atom_nonzero, std::max<size_t>(1, ctx->h_atoms.size())));
-    ctx->h_ref_ent.clear();
-    ctx->h_ref_ent.shrink_to_fit();
-    return RT_OK;
+    return RT_OK;   // h_ref_ent stays: get_plan needs the ref lengths to cut long ORFs into segments
 }
 
 constexpr size_t kReadBytes = 4 + 4 + 4 + 2 + 2 + 1 + 1;
@@ -350,6 +352,9 @@ void rt_destroy(rt_ctx* ctx) {
         cudaFree(p.d_list);
         cudaFree(p.d_fallback);
         cudaFree(p.d_atom_list);
+        cudaFree(p.d_segs);
+        cudaFree(p.d_partials);
+        cudaFree(p.d_seg_done);
     }
     for (int s = 0; s < 2; ++s) {
         ctx->read_slot[s].release();
@@ -760,6 +765,9 @@ int rt_set_index(rt_ctx* ctx, int64_t n_orf, const int64_t* h_exon_ptr, const in
         cudaFree(p.d_list);
         cudaFree(p.d_fallback);
         cudaFree(p.d_atom_list);
+        cudaFree(p.d_segs);
+        cudaFree(p.d_partials);
+        cudaFree(p.d_seg_done);
     }
     ctx->plans.clear();
     cudaFree(ctx->d_atoms);
@@ -849,22 +857,47 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
     auto len_of = [np](int32_t x) { return np[x + 1] - np[x]; };
     std::vector<int32_t> ids;
     ids.reserve((size_t)n);
+    std::vector<rt::RefSegment> segs;
+    int n_long_orfs = 0;
     int64_t n_long = 0;
     if (ctx->use_atoms) {
         // two-phase path: one thread per ORF walks its atom refs, so the ORFs sharing a warp should hold
         // similar numbers of refs; sort by that inside windows of the index (neighbours share atoms)
         auto refs_of = [&](int32_t x) { return (ctx->h_orf_refs_desc[x] >> 40) & (uint64_t)rt::kMaxEntriesPerOrf; };
-        // ORFs with very many refs (giant transcripts) are serial work for one thread: they go first so that
-        // they run beside everything else instead of forming the tail of the launch
-        constexpr uint64_t kManyRefs = 64;
-        for (int64_t o = lo; o < hi; ++o)
-            if (refs_of((int32_t)o) > kManyRefs) ids.push_back((int32_t)o);
-        std::stable_sort(ids.begin(), ids.end(), [&](int32_t x, int32_t y) { return refs_of(x) > refs_of(y); });
+        // ORFs with more than kSegRefs refs (giant transcripts) would be long serial chains for one thread:
+        // they are cut into segments of about kSegRefs refs, each scored by its own thread (cuts only after a
+        // ref of >= 2 values, so that a segment can start from that ref's last two values)
         constexpr int64_t kPlanWindow = 2048;
         for (int64_t w0 = lo; w0 < hi; w0 += kPlanWindow) {
             const size_t begin = ids.size();
-            for (int64_t o = w0; o < std::min(hi, w0 + kPlanWindow); ++o)
-                if (refs_of((int32_t)o) <= kManyRefs) ids.push_back((int32_t)o);
+            for (int64_t o = w0; o < std::min(hi, w0 + kPlanWindow); ++o) {
+                const uint64_t n_refs = refs_of((int32_t)o);
+                if (n_refs <= (uint64_t)rt::kSegRefs) {
+                    ids.push_back((int32_t)o);
+                    continue;
+                }
+                const uint64_t rb = ctx->h_orf_refs_desc[o] & rt::kBeginMask;
+                const size_t first_slot = segs.size();
+                int P = 0, seg_P0 = 0;
+                uint64_t seg_begin = 0;
+                for (uint64_t k = 0; k < n_refs; ++k) {
+                    const int len = (int)(ctx->h_ref_ent[rb + k] & rt::kLenMask);
+                    const bool cut_here = k > seg_begin && k - seg_begin >= (uint64_t)rt::kSegRefs &&
+                                          (int)(ctx->h_ref_ent[rb + k - 1] & rt::kLenMask) >= 2;
+                    if (cut_here) {
+                        segs.push_back({(int)o, (unsigned)(rb + seg_begin), (int)(k - seg_begin), seg_P0, (int)segs.size(), 0, 0, n_long_orfs});
+                        seg_begin = k;
+                        seg_P0 = P;
+                    }
+                    P += len;
+                }
+                segs.push_back({(int)o, (unsigned)(rb + seg_begin), (int)(n_refs - seg_begin), seg_P0, (int)segs.size(), 0, 0, n_long_orfs});
+                for (size_t q = first_slot; q < segs.size(); ++q) {
+                    segs[q].first_slot = (int)first_slot;
+                    segs[q].n_seg = (int)(segs.size() - first_slot);
+                }
+                ++n_long_orfs;
+            }
             std::stable_sort(ids.begin() + begin, ids.end(), [&](int32_t x, int32_t y) { return refs_of(x) > refs_of(y); });
         }
     } else {
@@ -888,16 +921,28 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
         cudaFree(ctx->plans.front().d_list);
         cudaFree(ctx->plans.front().d_fallback);
         cudaFree(ctx->plans.front().d_atom_list);
+        cudaFree(ctx->plans.front().d_segs);
+        cudaFree(ctx->plans.front().d_partials);
+        cudaFree(ctx->plans.front().d_seg_done);
         ctx->plans.erase(ctx->plans.begin());
     }
     rt_ctx::ScorePlan p;
     p.lo = lo;
     p.hi = hi;
     p.n_long = n_long;
-    p.n_short = n - n_long;
+    p.n_short = (int64_t)ids.size() - n_long;
+    p.n_segs = (int64_t)segs.size();
+    if (!segs.empty()) {
+        if (ctx->h_ref_ent.size() >= 0xffffffffull) return fail(ctx, RT_EINVAL, "rt_score: too many atom references for 32-bit segment offsets");
+        RT_CUDA(ctx, cudaMalloc(&p.d_segs, sizeof(rt::RefSegment) * segs.size()));
+        RT_CUDA(ctx, cudaMemcpy(p.d_segs, segs.data(), sizeof(rt::RefSegment) * segs.size(), cudaMemcpyHostToDevice));
+        RT_CUDA(ctx, cudaMalloc(&p.d_partials, sizeof(rt::ComposeAcc) * segs.size()));
+        RT_CUDA(ctx, cudaMalloc(&p.d_seg_done, sizeof(unsigned) * (size_t)n_long_orfs));
+        RT_CUDA(ctx, cudaMemset(p.d_seg_done, 0, sizeof(unsigned) * (size_t)n_long_orfs));
+    }
     RT_CUDA(ctx, cudaMalloc(&p.d_list, sizeof(int32_t) * std::max<int64_t>(1, n)));
     RT_CUDA(ctx, cudaMalloc(&p.d_fallback, sizeof(int32_t) * std::max<int64_t>(1, n)));
-    RT_CUDA(ctx, cudaMemcpy(p.d_list, ids.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    if (!ids.empty()) RT_CUDA(ctx, cudaMemcpy(p.d_list, ids.data(), sizeof(int32_t) * ids.size(), cudaMemcpyHostToDevice));
     {   // atoms the ORFs of the range refer to; sorted by length inside windows so that the four atoms of
         // a warp are balanced while genomic neighbours stay close in time
         std::vector<uint8_t> used((size_t)ctx->n_atoms, 0);
@@ -1009,7 +1054,11 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
         ca.n_fallback = a.n_fallback;
         ca.prm = *params;
         ca.out = *d_out;
-        rt::score_from_atoms_kernel<<<(unsigned)((ca.n_list + 255) / 256), 256, 0, st>>>(ca);
+        ca.segs = plan->d_segs;
+        ca.n_segs = plan->n_segs;
+        ca.partials = plan->d_partials;
+        ca.seg_done = plan->d_seg_done;
+        rt::score_from_atoms_kernel<<<(unsigned)((ca.n_segs + ca.n_list + 255) / 256), 256, 0, st>>>(ca);
         ctx->launches++;
         // ORFs holding counts >= 2^20: redone by the generic kernel (normally none)
         a.list = plan->d_fallback;

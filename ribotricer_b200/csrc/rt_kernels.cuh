@@ -1122,25 +1122,101 @@ struct ComposeArgs {
     long long n_list;
     int32_t* fallback;                 // ORFs holding counts >= 2^kBigShift: redone by the generic kernel
     unsigned* n_fallback;
+    // ORFs with more than kSegRefs refs are cut into segments that run in parallel
+    const struct RefSegment* segs;     // work items [0, n_segs) of the launch; the ORFs of `list` follow
+    long long n_segs;
+    struct ComposeAcc* partials;       // one per segment
+    unsigned* seg_done;                // per long ORF: segments finished so far (self-resetting)
     rt_score_params prm;
     rt_score_out out;
 };
+constexpr int kSegRefs = 48;           // refs per segment of a long ORF
 
-// One thread per ORF streams the summaries of its atoms: no raw coverage is read any more.  The
-// windows that straddle atom seams are rebuilt from the edge values kept in the summaries: while
-// the profile streams by, (x, y) are its last two values, and every value that enters a new atom
-// completes one window that is not interior to any atom.
-__global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs args) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= args.n_list) return;
-    const int orf = __ldg(args.list + i);
-    const uint64_t desc = __ldg(args.orf_refs_desc + orf);
-    const uint64_t begin = desc & kBeginMask;
-    const int n_refs = (int)((desc >> 40) & kMaxEntriesPerOrf);
-    const bool rev = (desc >> 63) != 0;
-    const int L = __ldg(args.orf_len + orf);
+// ---- phase B ----------------------------------------------------------------------------------
+// Per-frame sums of one ORF (or of one segment of a long ORF) in PROFILE frames.
+struct ComposeAcc {
+    unsigned K[3], U[3];
+    double RE[3], IM[3];
+    unsigned mn;
+    int big;
+    long long count;
+};
+static_assert(sizeof(ComposeAcc) == 88, "ComposeAcc layout");
+
+// A slice of the atom references of a long ORF (more than kSegRefs refs), scored by its own thread.
+struct RefSegment {
+    int orf;
+    unsigned ref_begin;        // absolute index of the segment's first ref
+    int n_refs;
+    int P0;                    // profile offset of that ref
+    int slot;                  // where the partial sums go (ComposeArgs::partials)
+    int first_slot, n_seg;     // the ORF's segments occupy partial slots [first_slot, first_slot + n_seg)
+    int long_idx;              // index of the ORF among the long ORFs (ComposeArgs::seg_done)
+};
+
+// statistics.py:92-115 + detect_orfs.py:278-299 on the finished sums of one ORF.
+__device__ __forceinline__ void finish_orf(const ComposeArgs& args, int orf, int L, const unsigned* K, const unsigned* U,
+                                           const double* RE, const double* IM, unsigned mn, long long count) {
     const double kSqrt3 = 1.7320508075688772;
     const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
+    const int n_codons = L / 3 > 1 ? L / 3 : 1;                          // detect_orfs.py:281
+    double s3[3];
+    double coh = 0.0;
+    int valid = -1;
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+        if (K[f] == 0) { s3[f] = kNaN; coh = 0.0; valid = 0; continue; }   // statistics.py:94-95
+        const double im = kSqrt3 * IM[f];
+        const double s = (RE[f] * RE[f] + im * im) / ((double)K[f] * (double)(K[f] - U[f]));   // 0/0 -> NaN never wins
+        s3[f] = s;
+        if (s > coh) { coh = s; valid = (int)K[f]; }                     // statistics.py:109-111
+        if (valid == -1) valid = (int)K[f];                              // statistics.py:112-113
+    }
+    const double score = sqrt(coh);                                      // statistics.py:115
+    const double ratio = (double)valid / (double)n_codons;               // detect_orfs.py:285
+    const double density = (double)count / (double)n_codons;             // detect_orfs.py:287
+    const unsigned min_codon = L == 0 ? 0u : mn;
+    const bool ok = score >= args.prm.phase_score_cutoff && (double)valid >= args.prm.min_valid_codons &&
+                    (L == 0 || (double)min_codon >= args.prm.min_reads_per_codon) &&
+                    ratio >= args.prm.min_valid_codons_ratio && density >= args.prm.min_density_over_orf;
+    const long long k_out = (long long)orf - args.orf_lo;
+    args.out.score[k_out] = score;
+    args.out.valid[k_out] = valid;
+    args.out.count[k_out] = count;
+    args.out.length[k_out] = L;
+    if (args.out.min_codon) args.out.min_codon[k_out] = (int32_t)min_codon;
+    if (args.out.status) args.out.status[k_out] = ok ? 1 : 0;
+    if (args.out.frame_K) {
+        args.out.frame_K[3 * k_out + 0] = (int)K[0];
+        args.out.frame_K[3 * k_out + 1] = (int)K[1];
+        args.out.frame_K[3 * k_out + 2] = (int)K[2];
+    }
+    if (args.out.frame_s) {
+        args.out.frame_s[3 * k_out + 0] = s3[0];
+        args.out.frame_s[3 * k_out + 1] = s3[1];
+        args.out.frame_s[3 * k_out + 2] = s3[2];
+    }
+}
+
+// One thread per ORF -- or per segment of a long ORF; the segments are the first work items of the launch --
+// streams the summaries of its atoms: no raw coverage is read any more.  The windows that straddle atom
+// seams are rebuilt from the edge values kept in the summaries: while the profile streams by, (x, y) are
+// its last two values, and every value that enters a new atom completes one window that is not interior to
+// any atom.  A segment starts from the last two values of the ref before it (the host only cuts after refs
+// of >= 2 values) and leaves its sums in `partials`; the thread that finishes an ORF's last outstanding
+// segment adds the partial sums up in segment order and scores the ORF.
+__global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs args) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= args.n_segs + args.n_list) return;
+    const bool Seg = i < args.n_segs;
+    RefSegment seg{};
+    if (Seg) seg = args.segs[i];
+    const int orf = Seg ? seg.orf : __ldg(args.list + (i - args.n_segs));
+    const uint64_t desc = __ldg(args.orf_refs_desc + orf);
+    const uint64_t begin = Seg ? (uint64_t)seg.ref_begin : (desc & kBeginMask);
+    const int n_refs = Seg ? seg.n_refs : (int)((desc >> 40) & kMaxEntriesPerOrf);
+    const bool rev = (desc >> 63) != 0;
+    const int L = __ldg(args.orf_len + orf);
 
     unsigned K[3] = {0, 0, 0}, U[3] = {0, 0, 0};
     double RE[3] = {0.0, 0.0, 0.0}, IM[3] = {0.0, 0.0, 0.0};
@@ -1174,8 +1250,19 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
             if (q == f) { K[q] += 1u; U[q] += uniform ? 1u : 0u; RE[q] += re; IM[q] += im; }
     };
 
-    int P = 0;             // profile offset of the current ref
-    int x = 0, y = 0;      // profile values at P - 2 and P - 1
+    int P = Seg ? seg.P0 : 0;   // profile offset of the current ref
+    int x = 0, y = 0;           // profile values at P - 2 and P - 1
+    if (Seg && seg.P0 > 0) {    // the ref before the segment holds >= 2 values: its last two in profile order
+        const uint64_t pe = __ldg(args.ref_ent + begin - 1);
+        if ((pe >> kLenBits) != kZeroOff) {
+            const unsigned pa = __ldg(args.ref_atom + begin - 1);
+            if (__ldg(args.atom_nonzero + pa) != 0) {
+                const int4 edge = __ldg(reinterpret_cast<const int4*>(args.summaries + pa) + 3);
+                if (rev) { x = edge.y; y = edge.x; }
+                else { x = edge.z; y = edge.w; }
+            }
+        }
+    }
     // software pipeline: (entry, atom id) two refs ahead, the atom's non-zero flag one ref ahead
     uint64_t ent = 0, ent_n = 0;
     unsigned atom = 0, atom_n = 0;
@@ -1244,53 +1331,44 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
         }
         P += len;
     }
-    // trailing partial codon (common.py:177-179): the last L % 3 values are x, y
-    if (L % 3 == 1) { mn = min(mn, (unsigned)y); ormask |= y; }
-    else if (L % 3 == 2) { mn = min(mn, (unsigned)x + (unsigned)y); ormask |= x | y; }
+    if (!Seg || seg.slot == seg.first_slot + seg.n_seg - 1) {
+        // trailing partial codon (common.py:177-179): the last L % 3 values are x, y
+        if (L % 3 == 1) { mn = min(mn, (unsigned)y); ormask |= y; }
+        else if (L % 3 == 2) { mn = min(mn, (unsigned)x + (unsigned)y); ormask |= x | y; }
+    }
     big |= (ormask >> kBigShift) != 0;
+    if (Seg) {
+        ComposeAcc acc;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) { acc.K[f] = K[f]; acc.U[f] = U[f]; acc.RE[f] = RE[f]; acc.IM[f] = IM[f]; }
+        acc.mn = mn;
+        acc.big = big ? 1 : 0;
+        acc.count = count;
+        args.partials[seg.slot] = acc;
+        __threadfence();
+        if (atomicAdd(args.seg_done + seg.long_idx, 1u) != (unsigned)(seg.n_seg - 1)) return;
+        // this thread finished the ORF's last outstanding segment: add the partial sums in segment order
+        __threadfence();
+        args.seg_done[seg.long_idx] = 0;                    // ready for the next launch
+#pragma unroll
+        for (int f = 0; f < 3; ++f) { K[f] = 0; U[f] = 0; RE[f] = 0.0; IM[f] = 0.0; }
+        mn = 0xffffffffu;
+        count = 0;
+        big = false;
+        for (int sidx = seg.first_slot; sidx < seg.first_slot + seg.n_seg; ++sidx) {
+            const volatile ComposeAcc* pa = args.partials + sidx;
+#pragma unroll
+            for (int f = 0; f < 3; ++f) { K[f] += pa->K[f]; U[f] += pa->U[f]; RE[f] += pa->RE[f]; IM[f] += pa->IM[f]; }
+            mn = min(mn, pa->mn);
+            big |= pa->big != 0;
+            count += pa->count;
+        }
+    }
     if (big) {
         args.fallback[atomicAdd(args.n_fallback, 1u)] = orf;
         return;
     }
-
-    // ---- epilogue: statistics.py:92-115 + detect_orfs.py:278-299 ----
-    const int n_codons = L / 3 > 1 ? L / 3 : 1;                          // detect_orfs.py:281
-    double s3[3];
-    double coh = 0.0;
-    int valid = -1;
-#pragma unroll
-    for (int f = 0; f < 3; ++f) {
-        if (K[f] == 0) { s3[f] = kNaN; coh = 0.0; valid = 0; continue; }   // statistics.py:94-95
-        const double im = kSqrt3 * IM[f];
-        const double s = (RE[f] * RE[f] + im * im) / ((double)K[f] * (double)(K[f] - U[f]));   // 0/0 -> NaN never wins
-        s3[f] = s;
-        if (s > coh) { coh = s; valid = (int)K[f]; }                     // statistics.py:109-111
-        if (valid == -1) valid = (int)K[f];                              // statistics.py:112-113
-    }
-    const double score = sqrt(coh);                                      // statistics.py:115
-    const double ratio = (double)valid / (double)n_codons;               // detect_orfs.py:285
-    const double density = (double)count / (double)n_codons;             // detect_orfs.py:287
-    const unsigned min_codon = L == 0 ? 0u : mn;
-    const bool ok = score >= args.prm.phase_score_cutoff && (double)valid >= args.prm.min_valid_codons &&
-                    (L == 0 || (double)min_codon >= args.prm.min_reads_per_codon) &&
-                    ratio >= args.prm.min_valid_codons_ratio && density >= args.prm.min_density_over_orf;
-    const long long k_out = (long long)orf - args.orf_lo;
-    args.out.score[k_out] = score;
-    args.out.valid[k_out] = valid;
-    args.out.count[k_out] = count;
-    args.out.length[k_out] = L;
-    if (args.out.min_codon) args.out.min_codon[k_out] = (int32_t)min_codon;
-    if (args.out.status) args.out.status[k_out] = ok ? 1 : 0;
-    if (args.out.frame_K) {
-        args.out.frame_K[3 * k_out + 0] = (int)K[0];
-        args.out.frame_K[3 * k_out + 1] = (int)K[1];
-        args.out.frame_K[3 * k_out + 2] = (int)K[2];
-    }
-    if (args.out.frame_s) {
-        args.out.frame_s[3 * k_out + 0] = s3[0];
-        args.out.frame_s[3 * k_out + 1] = s3[1];
-        args.out.frame_s[3 * k_out + 2] = s3[2];
-    }
+    finish_orf(args, orf, L, K, U, RE, IM, mn, count);
 }
 
 // ---- K4 -------------------------------------------------------------------------------------
