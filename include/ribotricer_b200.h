@@ -212,6 +212,14 @@ int rt_gather_profiles(rt_ctx* ctx, const int32_t* d_cov, int64_t n_sel, const i
                        const int64_t* d_out_ptr, int32_t* d_out, void* stream);
 
 /*
+ * ---- count_orfs (count_orfs.py:28-89) on device results: coverage sums over intervals of the DENSE planes,
+ *      added per group (gene).  d_iv_off = slot offset of the interval's first position (strand * plane +
+ *      contig_base + pad + start), d_sums[n_group] int64 is added to (zero it first).  SURVEY.md 8(f) #4.
+ */
+int rt_interval_sums(rt_ctx* ctx, const int32_t* d_cov, int64_t n_iv, const int64_t* d_iv_off, const int32_t* d_iv_len,
+                     const int32_t* d_iv_group, int64_t* d_sums, void* stream);
+
+/*
  * ---- phasescore(values) (statistics.py:48-115) of ONE sequence of doubles, e.g. a metagene
  *      profile (metagene.py:243-244).  Host pointers; synchronous.
  */

@@ -102,5 +102,27 @@ def detect_orfs_cmd(bam, ribotricer_index, prefix, stranded, read_lengths, psite
                 min_read_density, report_all, meta_min_reads)
 
 
+
+@cli.command("count-orfs", context_settings=CONTEXT_SETTINGS, help="Count reads for detected ORFs at gene level")
+@click.option("--ribotricer_index",
+              help="Path to the index file of ribotricer\nThis file should be generated using ribotricer prepare-orfs",
+              required=True)
+@click.option("--detected_orfs",
+              help="Path to the detected orfs file\nThis file should be generated using ribotricer detect-orfs",
+              required=True)
+@click.option("--features", help="ORF types separated with comma", required=True)
+@click.option("--out", help="Path to output file", required=True)
+@click.option("--report_all", help=("Whether output all ORFs including those non-translating ones"), is_flag=True)
+def count_orfs_cmd(ribotricer_index, detected_orfs, features, out, report_all) -> None:
+    """cli.py:292-339 of the reference (same flags and checks); the table is count_orfs.py:28-89."""
+    from .count_orfs import count_orfs
+
+    if not os.path.isfile(ribotricer_index):
+        sys.exit("Error: ribotricer index file not found")
+    if not os.path.isfile(detected_orfs):
+        sys.exit("Error: detected orfs file not found")
+    count_orfs(ribotricer_index, detected_orfs, set(x.strip() for x in features.split(",")), out, report_all)
+
+
 if __name__ == "__main__":
     cli()

@@ -1184,4 +1184,23 @@ int rt_gather_profiles(rt_ctx* ctx, const int32_t* d_cov, int64_t n_sel, const i
     return RT_OK;
 }
 
+// ------------------------------------------------------------------------------------ interval sums
+int rt_interval_sums(rt_ctx* ctx, const int32_t* d_cov, int64_t n_iv, const int64_t* d_iv_off, const int32_t* d_iv_len,
+                     const int32_t* d_iv_group, int64_t* d_sums, void* stream) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_interval_sums: ctx is NULL");
+    if (n_iv < 0 || !d_cov || !d_sums || (n_iv > 0 && (!d_iv_off || !d_iv_len || !d_iv_group)))
+        return fail(ctx, RT_EINVAL, "rt_interval_sums: NULL argument");
+    if (ctx->layout != RT_LAYOUT_DENSE)
+        return fail(ctx, RT_ESTATE, "rt_interval_sums: interval offsets address the dense planes; switch the layout back first");
+    if (n_iv == 0) return RT_OK;
+    DeviceGuard guard(ctx->device);
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_iv + 7) / 8, (int64_t)ctx->n_sm * 8));
+    rt::interval_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_cov, n_iv, reinterpret_cast<const long long*>(d_iv_off),
+                                                                   d_iv_len, d_iv_group,
+                                                                   reinterpret_cast<unsigned long long*>(d_sums));
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+    return RT_OK;
+}
+
 }  // extern "C"

@@ -1410,6 +1410,26 @@ __global__ void __launch_bounds__(256) gather_profiles_kernel(const GatherArgs a
     }
 }
 
+// ---- interval sums (count_orfs.py:28-89 on device results) ------------------------------------
+// One warp per interval of the dense planes: its coverage sum is added to the group (= gene) it belongs to.
+__global__ void __launch_bounds__(256) interval_sum_kernel(const int32_t* __restrict__ cov, long long n_iv,
+                                                            const long long* __restrict__ iv_off,
+                                                            const int32_t* __restrict__ iv_len,
+                                                            const int32_t* __restrict__ iv_group,
+                                                            unsigned long long* sums) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp0; i < n_iv; i += nwarps) {
+        const int32_t* src = cov + iv_off[i];
+        const int len = iv_len[i];
+        long long acc = 0;
+        for (int k = lane; k < len; k += 32) acc += ld_cov(src + k);
+        acc = warp_sum_i64(acc);
+        if (lane == 0 && acc != 0) atomicAdd(sums + iv_group[i], (unsigned long long)acc);
+    }
+}
+
 // ---- K1 -------------------------------------------------------------------------------------
 struct BinArgs {
     int32_t* cov;

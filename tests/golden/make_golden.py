@@ -13,6 +13,7 @@ Outputs (small, committed):
                                           (:206) and export_wig (:327) end to end
 
   tests/golden/split_bam_case.json.gz     split_bam (bam.py:33-153) on a real BAM (bytes included)
+  tests/golden/count_orfs_cases.json.gz   count_orfs (count_orfs.py:28-89) on the pipeline cases' TSVs
 
 ``split_bam`` needs pysam, which is absent from this image: it runs UNMODIFIED on top of
 oracle/pysam_restated.py, a pure-Python restatement of the handful of pysam calls it makes
@@ -367,6 +368,33 @@ def split_bam_case(seed=1004):
     return case
 
 
+def count_orfs_cases():
+    """count_orfs (count_orfs.py:28-89) of the unmodified reference on the index + TSV text of the committed
+    pipeline cases, for several feature sets and both report_all settings."""
+    from ribotricer.count_orfs import count_orfs
+
+    pipe = json.load(gzip.open(os.path.join(HERE, "pipeline_cases.json.gz"), "rt"))["cases"]
+    out = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for case in pipe:
+            idx = os.path.join(tmp, "idx.tsv")
+            with open(idx, "w") as fh:
+                fh.write("\n".join(case["index"]) + "\n")
+            types = sorted({line.split("\t")[1] for line in case["index"][1:]})
+            feature_sets = [["annotated"], [t for t in types if t != "annotated"], types]
+            for k, tsv in enumerate(case["tsv"]):
+                tsv_path = os.path.join(tmp, "in.tsv")
+                with open(tsv_path, "w") as fh:
+                    fh.write(tsv["text"])
+                for features in feature_sets:
+                    for report_all in (False, True):
+                        dst = os.path.join(tmp, "counts.tsv")
+                        count_orfs(idx, tsv_path, set(features), dst, report_all)
+                        out.append({"case": case["name"], "tsv": k, "features": features, "report_all": report_all,
+                                    "text": open(dst).read()})
+    return out
+
+
 def run_reference_pipeline(case, ref):
     from collections import Counter, defaultdict
 
@@ -413,8 +441,13 @@ def main():
         for r in sb["runs"]:
             print("split_bam", r["protocol"], r["read_lengths"], "keys:", len(r["alignments"]),
                   r["summary"].split("\n\nlength")[0].replace("\n\t", " "))
-        if len(sys.argv) > 1:
-            return
+    if "count_orfs" in sys.argv[1:]:      # (a full run does this last, after the pipeline cases it reads)
+        cc = count_orfs_cases()
+        with gzip.open(os.path.join(HERE, "count_orfs_cases.json.gz"), "wt") as fh:
+            json.dump({"versions": versions(), "cases": cc}, fh, separators=(",", ":"))
+        print("count_orfs cases:", len(cc), "non-trivial:", sum(c["text"].count("\n") > 1 for c in cc))
+    if len(sys.argv) > 1:
+        return
     from ribotricer.statistics import phasescore
 
     ps = {"versions": versions(), "cases": make_phasescore_cases(phasescore)}
@@ -437,6 +470,10 @@ def main():
     with gzip.open(os.path.join(HERE, "metagene_case.json.gz"), "wt") as fh:
         json.dump({"versions": versions(), "case": mg}, fh, separators=(",", ":"))
     print("metagene: kept", mg["kept_lengths"], "offsets", mg["psite_offsets"], "planted", mg["planted"])
+    cc = count_orfs_cases()
+    with gzip.open(os.path.join(HERE, "count_orfs_cases.json.gz"), "wt") as fh:
+        json.dump({"versions": versions(), "cases": cc}, fh, separators=(",", ":"))
+    print("count_orfs cases:", len(cc))
 
 
 if __name__ == "__main__":

@@ -205,3 +205,41 @@ def test_split_bam_matches_reference(engine, tmp_path):
             want[strand][key] = want[strand].get(key, 0) + n
         for strand in "+-":
             assert dict(merged.get(strand, {})) == want[strand]
+
+
+@pytest.mark.gpu
+def test_count_orfs_device_matches_reference(engine, tmp_path):
+    """count_orfs on device results (coverage planes + status column, no profile text) against the table
+    the reference's count_orfs (count_orfs.py:28-89) wrote from the corresponding TSV."""
+    from helpers import case_to_arrays, merged_to_dense
+    from oracle import c_oracle as CO
+    from ribotricer_b200.count_orfs import count_orfs_device
+    from ribotricer_b200.index import load_native_index
+
+    pipe = {c["name"]: c for c in load_golden("pipeline_cases.json.gz")["cases"]}
+    state = {}
+    for c in load_golden("count_orfs_cases.json.gz")["cases"]:
+        case = pipe[c["case"]]
+        if c["case"] not in state:
+            names, lens, _, _ = case_to_arrays(case)
+            pad = 64
+            base, plane = CO.genome_layout(lens, pad)
+            dense, dropped = merged_to_dense(case, names, base, pad, plane)
+            assert dropped == 0
+            path = tmp_path / f"{c['case']}.tsv"
+            path.write_text("\n".join(case["index"]) + "\n")
+            idx = load_native_index(str(path))
+            oid_row = {idx.oid(o): o for o in range(idx.n_orf)}
+            state[c["case"]] = (names, lens, pad, dense, idx, oid_row)
+        names, lens, pad, dense, idx, oid_row = state[c["case"]]
+        engine.set_genome(names, lens, pad=pad)
+        cov = engine.torch.from_numpy(dense).to(engine.device)
+        run = case["tsv"][c["tsv"]]
+        status = np.zeros(idx.n_orf, bool)
+        for line in run["text"].splitlines()[1:]:
+            f = line.split("\t")
+            status[oid_row[f[0]]] = f[2] == "translating"
+        out = tmp_path / "counts.tsv"
+        count_orfs_device(engine, cov, idx, status, set(c["features"]), str(out), c["report_all"],
+                          rows_written="all" if run["params"]["report_all"] else "translating")
+        assert out.read_text() == c["text"], (c["case"], c["tsv"], c["features"], c["report_all"])

@@ -281,3 +281,23 @@ def test_bam_pack_matches_pack_read_meta(tmp_path, built):
     k = C.c_int64(0)
     assert lib.rt_pack_read_meta(n, p(rc.cols["ref_id"]), p(rc.cols["flag"]), p(rc.cols["mapq"]), p(rc.cols["nh"]),
                                  p(meta), 1, p(np.zeros(2, np.int64)), p(np.zeros(1, np.int32)), C.byref(k)) != 0
+
+
+def test_count_orfs_text_matches_reference(tmp_path, built):
+    """ribotricer_b200.count_orfs.count_orfs (same signature as count_orfs.py:28) on the golden TSVs."""
+    from helpers import load_golden
+    from ribotricer_b200.count_orfs import count_orfs
+
+    pipe = {c["name"]: c for c in load_golden("pipeline_cases.json.gz")["cases"]}
+    n = 0
+    for c in load_golden("count_orfs_cases.json.gz")["cases"]:
+        case = pipe[c["case"]]
+        idx = tmp_path / "idx.tsv"
+        idx.write_text("\n".join(case["index"]) + "\n")
+        tsv = tmp_path / "in.tsv"
+        tsv.write_text(case["tsv"][c["tsv"]]["text"])
+        out = tmp_path / "counts.tsv"
+        count_orfs(str(idx), str(tsv), set(c["features"]), str(out), c["report_all"])
+        assert out.read_text() == c["text"], (c["case"], c["tsv"], c["features"], c["report_all"])
+        n += 1
+    assert n == 72
