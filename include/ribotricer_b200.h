@@ -220,6 +220,14 @@ int rt_interval_sums(rt_ctx* ctx, const int32_t* d_cov, int64_t n_iv, const int6
                      const int32_t* d_iv_group, int64_t* d_sums, void* stream);
 
 /*
+ * ---- learn-cutoff bootstrap (learn_cutoff.py:88-98): out[r] = np.median(values[idx[:, r]]) for a row-major
+ *      index matrix idx[n_sel][reps] (the caller draws it with NumPy's legacy generator, as the reference
+ *      does, so that the replicates are the same).  Host pointers; synchronous.  SURVEY.md 8(f) #4.
+ */
+int rt_bootstrap_medians(rt_ctx* ctx, const double* h_values, int64_t n, const int64_t* h_idx, int64_t n_sel,
+                         int64_t reps, double* h_out);
+
+/*
  * ---- phasescore(values) (statistics.py:48-115) of ONE sequence of doubles, e.g. a metagene
  *      profile (metagene.py:243-244).  Host pointers; synchronous.
  */

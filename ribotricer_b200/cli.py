@@ -124,5 +124,58 @@ def count_orfs_cmd(ribotricer_index, detected_orfs, features, out, report_all) -
     count_orfs(ribotricer_index, detected_orfs, set(x.strip() for x in features.split(",")), out, report_all)
 
 
+def _split_list(text: str) -> list:
+    """Comma separated option value -> items with surrounding blanks removed (common.py:148-161)."""
+    return [item.strip(" ") for item in text.split(",")]
+
+
+@cli.command("learn-cutoff", context_settings=CONTEXT_SETTINGS, help="Learn phase score cutoff from BAM/TSV file")
+@click.option("--ribo_bams", help="Path(s) to Ribo-seq BAM file separated by comma")
+@click.option("--rna_bams", help="Path(s) to RNA-seq BAM file separated by comma")
+@click.option("--ribo_tsvs", help="Path(s) to Ribo-seq *_translating_ORFs.tsv file separated by comma")
+@click.option("--rna_tsvs", help="Path(s) to RNA-seq *_translating_ORFs.tsv file separated by comma")
+@click.option("--ribotricer_index",
+              help=("Path to the index file of ribotricer\n"
+                    "This file should be generated using ribotricer prepare-orfs (required for BAM input)"))
+@click.option("--prefix", help="Prefix to output file")
+@click.option("--filter_by_tx_annotation", help="transcript_type to filter regions by", type=str,
+              default="protein_coding", show_default=True)
+@click.option("--phase_score_cutoff", type=float, default=CUTOFF, show_default=True,
+              help="Phase score cutoff for determining active translation (required for BAM input)")
+@click.option("--min_valid_codons", type=int, default=MINIMUM_VALID_CODONS, show_default=True,
+              help="Minimum number of codons with non-zero reads for determining active translation (required for BAM input)")
+@click.option("--sampling_ratio", type=float, default=0.33, show_default=True,
+              help="Number of protein coding regions to sample per bootstrap")
+@click.option("--n_bootstraps", type=int, default=20000, show_default=True, help="Number of bootstraps")
+def determine_cutoff_cmd(ribo_bams, rna_bams, ribo_tsvs, rna_tsvs, ribotricer_index, prefix, filter_by_tx_annotation,
+                         phase_score_cutoff, min_valid_codons, sampling_ratio, n_bootstraps) -> None:
+    """cli.py:435-560 of the reference: same flags, checks and messages."""
+    from .learn_cutoff import determine_cutoff_bam, determine_cutoff_tsv
+
+    filter_by = _split_list(filter_by_tx_annotation)
+    if ribo_bams and ribo_tsvs:
+        sys.exit("Error: --ribo-bams and --rna_bams cannot be specified together")
+    if rna_bams and rna_tsvs:
+        sys.exit("Error: --rna-bams and --rna_tsvs cannot be specified together")
+    if (ribo_bams and rna_tsvs) or (rna_bams and ribo_tsvs):
+        sys.exit("Error: BAM and TSV inputs cannot be specified together")
+    if ribotricer_index and not os.path.isfile(ribotricer_index):
+        sys.exit("Error: ribotricer index file not found")
+    if ribo_bams:
+        ribo_list, rna_list = _split_list(ribo_bams), (_split_list(rna_bams) if rna_bams else [])
+        if ribo_list and rna_list:
+            if not prefix:
+                sys.exit("Error: --prefix required with BAM inputs")
+            if not ribotricer_index:
+                sys.exit("Error: --ribotricer_index required with BAM inputs")
+            determine_cutoff_bam(ribo_list, rna_list, ribotricer_index, prefix, [], [], filter_by, sampling_ratio,
+                                 n_bootstraps, phase_score_cutoff, min_valid_codons, report_all=True)
+            return
+        determine_cutoff_tsv([], [], filter_by, sampling_ratio, n_bootstraps)
+        return
+    determine_cutoff_tsv(_split_list(ribo_tsvs) if ribo_tsvs else [], _split_list(rna_tsvs) if rna_tsvs else [],
+                         filter_by, sampling_ratio, n_bootstraps)
+
+
 if __name__ == "__main__":
     cli()

@@ -1203,4 +1203,39 @@ int rt_interval_sums(rt_ctx* ctx, const int32_t* d_cov, int64_t n_iv, const int6
     return RT_OK;
 }
 
+// ------------------------------------------------------------------------------------ bootstrap medians
+int rt_bootstrap_medians(rt_ctx* ctx, const double* h_values, int64_t n, const int64_t* h_idx, int64_t n_sel, int64_t reps,
+                         double* h_out) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_bootstrap_medians: ctx is NULL");
+    if (n <= 0 || n_sel <= 0 || reps <= 0 || !h_values || !h_idx || !h_out)
+        return fail(ctx, RT_EINVAL, "rt_bootstrap_medians: empty or NULL argument");
+    if (reps > 0x7fffffff) return fail(ctx, RT_EINVAL, "rt_bootstrap_medians: too many replicates");
+    for (int64_t i = 0; i < n_sel * reps; ++i)
+        if (h_idx[i] < 0 || h_idx[i] >= n) return fail(ctx, RT_EINVAL, "rt_bootstrap_medians: index %lld outside [0,%lld)", (long long)h_idx[i], (long long)n);
+    DeviceGuard guard(ctx->device);
+    const size_t key_bytes = sizeof(unsigned long long) * (size_t)n_sel;
+    const bool in_smem = key_bytes <= 160 * 1024;
+    DevBuf vals, idx, outb, scratch;
+    auto cleanup = [&]() { vals.release(); idx.release(); outb.release(); scratch.release(); };
+    cudaError_t e = vals.reserve(sizeof(double) * (size_t)n);
+    if (e == cudaSuccess) e = idx.reserve(sizeof(int64_t) * (size_t)(n_sel * reps));
+    if (e == cudaSuccess) e = outb.reserve(sizeof(double) * (size_t)reps);
+    if (e == cudaSuccess && !in_smem) e = scratch.reserve(key_bytes * (size_t)reps);
+    if (e == cudaSuccess) e = cudaMemcpy(vals.p, h_values, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(idx.p, h_idx, sizeof(int64_t) * (size_t)(n_sel * reps), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && in_smem)
+        e = cudaFuncSetAttribute(rt::bootstrap_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)key_bytes);
+    if (e == cudaSuccess) {
+        rt::bootstrap_median_kernel<<<(unsigned)reps, 256, in_smem ? key_bytes : 0>>>(
+            static_cast<const double*>(vals.p), static_cast<const long long*>(idx.p), n_sel, reps,
+            static_cast<unsigned long long*>(scratch.p), in_smem ? 1 : 0, static_cast<double*>(outb.p));
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(h_out, outb.p, sizeof(double) * (size_t)reps, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? RT_ENOMEM : RT_ECUDA, "rt_bootstrap_medians: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
 }  // extern "C"

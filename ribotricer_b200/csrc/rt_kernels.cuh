@@ -1430,6 +1430,54 @@ __global__ void __launch_bounds__(256) interval_sum_kernel(const int32_t* __rest
     }
 }
 
+// ---- bootstrap medians (learn_cutoff.py:88-98) -------------------------------------------------
+// np.median(values[idx], axis=0) for idx of shape (n_sel, reps): one block per replicate gathers its n_sel
+// values as order-preserving 64-bit keys (shared memory when they fit, else a global scratch row) and finds
+// the middle order statistic(s) by a 64-step bisection on the key bits -- no sort.
+__device__ __forceinline__ unsigned long long f64_key(double v) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+    const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+__global__ void __launch_bounds__(256) bootstrap_median_kernel(const double* __restrict__ values,
+                                                                const long long* __restrict__ idx, long long n_sel,
+                                                                long long reps, unsigned long long* scratch,
+                                                                int keys_in_smem, double* out) {
+    extern __shared__ unsigned long long s_keys[];
+    __shared__ long long s_part[8];
+    const long long r = blockIdx.x;
+    unsigned long long* keys = keys_in_smem ? s_keys : scratch + r * n_sel;
+    for (long long i = threadIdx.x; i < n_sel; i += blockDim.x) keys[i] = f64_key(values[idx[i * reps + r]]);
+    __syncthreads();
+    auto count_below = [&](unsigned long long cand) {      // block-wide number of keys < cand
+        long long c = 0;
+        for (long long i = threadIdx.x; i < n_sel; i += blockDim.x) c += keys[i] < cand;
+        c = warp_sum_i64(c);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = c;
+        __syncthreads();
+        long long tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += s_part[w];
+        __syncthreads();
+        return tot;
+    };
+    auto kth = [&](long long k) {                          // k-th smallest key (0-based): largest R with count(< R) <= k
+        unsigned long long res = 0;
+        for (int bit = 63; bit >= 0; --bit) {
+            const unsigned long long cand = res | (1ull << bit);
+            if (count_below(cand) <= k) res = cand;
+        }
+        return res;
+    };
+    double med;
+    if (n_sel & 1) med = key_f64(kth(n_sel / 2));
+    else med = (key_f64(kth(n_sel / 2 - 1)) + key_f64(kth(n_sel / 2))) * 0.5;     // np.mean of the two middle values
+    if (threadIdx.x == 0) out[r] = med;
+}
+
 // ---- K1 -------------------------------------------------------------------------------------
 struct BinArgs {
     int32_t* cov;

@@ -14,6 +14,7 @@ Outputs (small, committed):
 
   tests/golden/split_bam_case.json.gz     split_bam (bam.py:33-153) on a real BAM (bytes included)
   tests/golden/count_orfs_cases.json.gz   count_orfs (count_orfs.py:28-89) on the pipeline cases' TSVs
+  tests/golden/learn_cutoff_cases.json.gz determine_cutoff_tsv (learn_cutoff.py:35-144) stdout
 
 ``split_bam`` needs pysam, which is absent from this image: it runs UNMODIFIED on top of
 oracle/pysam_restated.py, a pure-Python restatement of the handful of pysam calls it makes
@@ -395,6 +396,46 @@ def count_orfs_cases():
     return out
 
 
+def learn_cutoff_cases():
+    """determine_cutoff_tsv (learn_cutoff.py:35-144) of the unmodified reference: its stdout for Ribo-seq /
+    RNA-seq TSV pairs built from the committed pipeline cases (the RNA-seq TSV is the Ribo-seq one with the
+    phase_score column permuted, so that the two differ while holding the same ORFs)."""
+    import io
+    from contextlib import redirect_stdout
+
+    from ribotricer.learn_cutoff import determine_cutoff_tsv
+
+    pipe = {c["name"]: c for c in json.load(gzip.open(os.path.join(HERE, "pipeline_cases.json.gz"), "rt"))["cases"]}
+    out = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, reps, ratio, filter_by, n_files in (("yeastlike", 300, 0.33, None, 1), ("ragged", 257, 0.5, ["protein_coding", "lncRNA"], 2),
+                                                     ("yeastlike", 64, 0.9, ["Protein_Coding"], 2)):
+            text = pipe[name]["tsv"][0]["text"]                 # report_all=True: every ORF of the index
+            lines = text.rstrip("\n").split("\n")
+            rows = [ln.split("\t") for ln in lines[1:]]
+            rng = np.random.default_rng(len(rows) + reps)
+            ribo_files, rna_files, rna_texts = [], [], []
+            for k in range(n_files):
+                ribo = os.path.join(tmp, f"ribo{k}.tsv")
+                with open(ribo, "w") as fh:
+                    fh.write(text)
+                perm = rng.permutation(len(rows))
+                rna_rows = [r[:3] + [rows[perm[i]][3]] + r[4:] for i, r in enumerate(rows)]
+                rna_text = "\n".join([lines[0]] + ["\t".join(r) for r in rna_rows]) + "\n"
+                rna = os.path.join(tmp, f"rna{k}.tsv")
+                with open(rna, "w") as fh:
+                    fh.write(rna_text)
+                ribo_files.append(ribo)
+                rna_files.append(rna)
+                rna_texts.append(rna_text)
+            sink = io.StringIO()
+            with redirect_stdout(sink):
+                determine_cutoff_tsv(ribo_files, rna_files, filter_by, ratio, reps)
+            out.append({"case": name, "reps": reps, "sampling_ratio": ratio, "filter_by": filter_by, "n_files": n_files,
+                        "rna_texts": rna_texts, "stdout": sink.getvalue()})
+    return out
+
+
 def run_reference_pipeline(case, ref):
     from collections import Counter, defaultdict
 
@@ -446,6 +487,11 @@ def main():
         with gzip.open(os.path.join(HERE, "count_orfs_cases.json.gz"), "wt") as fh:
             json.dump({"versions": versions(), "cases": cc}, fh, separators=(",", ":"))
         print("count_orfs cases:", len(cc), "non-trivial:", sum(c["text"].count("\n") > 1 for c in cc))
+    if "learn_cutoff" in sys.argv[1:]:
+        lc = learn_cutoff_cases()
+        with gzip.open(os.path.join(HERE, "learn_cutoff_cases.json.gz"), "wt") as fh:
+            json.dump({"versions": versions(), "cases": lc}, fh, separators=(",", ":"))
+        print("learn_cutoff cases:", len(lc), lc[0]["stdout"].replace("\n", " | ")[:400])
     if len(sys.argv) > 1:
         return
     from ribotricer.statistics import phasescore
@@ -474,6 +520,10 @@ def main():
     with gzip.open(os.path.join(HERE, "count_orfs_cases.json.gz"), "wt") as fh:
         json.dump({"versions": versions(), "cases": cc}, fh, separators=(",", ":"))
     print("count_orfs cases:", len(cc))
+    lc = learn_cutoff_cases()
+    with gzip.open(os.path.join(HERE, "learn_cutoff_cases.json.gz"), "wt") as fh:
+        json.dump({"versions": versions(), "cases": lc}, fh, separators=(",", ":"))
+    print("learn_cutoff cases:", len(lc))
 
 
 if __name__ == "__main__":

@@ -243,3 +243,29 @@ def test_count_orfs_device_matches_reference(engine, tmp_path):
         count_orfs_device(engine, cov, idx, status, set(c["features"]), str(out), c["report_all"],
                           rows_written="all" if run["params"]["report_all"] else "translating")
         assert out.read_text() == c["text"], (c["case"], c["tsv"], c["features"], c["report_all"])
+
+
+@pytest.mark.gpu
+def test_learn_cutoff_matches_reference(engine, tmp_path, capsys):
+    """determine_cutoff_tsv: same replicates (NumPy legacy generator, seed 42), medians from the GPU, same
+    printed report as the reference's learn_cutoff.py:35-144; plus the median kernel against np.median."""
+    from ribotricer_b200 import learn_cutoff as L
+
+    pipe = {c["name"]: c for c in load_golden("pipeline_cases.json.gz")["cases"]}
+    for c in load_golden("learn_cutoff_cases.json.gz")["cases"]:
+        ribo, rna = [], []
+        for k in range(c["n_files"]):
+            a, b = tmp_path / f"ribo{k}.tsv", tmp_path / f"rna{k}.tsv"
+            a.write_text(pipe[c["case"]]["tsv"][0]["text"])
+            b.write_text(c["rna_texts"][k])
+            ribo.append(str(a))
+            rna.append(str(b))
+        capsys.readouterr()
+        L.determine_cutoff_tsv(ribo, rna, c["filter_by"], c["sampling_ratio"], c["reps"], engine=engine)
+        assert capsys.readouterr().out == c["stdout"]
+    rng = np.random.default_rng(9)
+    for n, n_sel, reps in ((50, 1, 7), (1000, 333, 40), (4000, 2000, 9), (30000, 25001, 3)):   # the last one: global scratch
+        vals = np.where(rng.random(n) < 0.3, 0.0, rng.random(n)) * rng.choice([1.0, -1.0, 1e-300, 1e300], n)
+        idx = rng.integers(0, n, (n_sel, reps))
+        got = L._bootstrap_medians(engine, vals, idx)
+        assert np.array_equal(got, np.median(vals[idx], axis=0))
