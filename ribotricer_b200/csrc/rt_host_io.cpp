@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -234,15 +235,17 @@ int rt_tsv_open(const char* path, int write_header, rt_tsv** out) {
 
 // Rows of the selected ORFs (absolute ids, ascending = index order).  Result columns are indexed by
 // (orf - orf_lo); prof_ptr[i]..prof_ptr[i+1] delimit the profile of orf_ids[i] in `prof`.
-int rt_tsv_write(rt_tsv* t, const rt_index* ix, int64_t n_sel, const int64_t* orf_ids, int64_t orf_lo,
+}  // extern "C"
+
+namespace {
+
+// Rows [i0, i1) of the selection, formatted as detect_orfs.py:304-323 prints them.
+bool format_rows(std::string& b, const rt_index* ix, int64_t i0, int64_t i1, const int64_t* orf_ids, int64_t orf_lo,
                  const double* score, const int32_t* valid, const int64_t* count, const int32_t* length,
                  const uint8_t* status, const int64_t* prof_ptr, const int32_t* prof) {
-    if (!t || !ix || n_sel < 0 || (n_sel && (!orf_ids || !score || !valid || !count || !length || !status || !prof_ptr || !prof)))
-        return RT_EINVAL;
-    std::string& b = t->buf;
-    for (int64_t i = 0; i < n_sel; ++i) {
+    for (int64_t i = i0; i < i1; ++i) {
         const int64_t o = orf_ids[i], k = o - orf_lo;
-        if (o < 0 || o >= (int64_t)ix->orf_chrom.size() || k < 0) return RT_EINVAL;
+        if (o < 0 || o >= (int64_t)ix->orf_chrom.size() || k < 0) return false;
         int flen[10];
         const char* f[10];
         for (int j = 1; j <= 9; ++j) f[j] = rt_index_field(ix, o, j, &flen[j]);
@@ -277,14 +280,43 @@ int rt_tsv_write(rt_tsv* t, const rt_index* ix, int64_t n_sel, const int64_t* or
             append_int(b, prof[q]);
         }
         b += "]\n";
-        if (b.size() > (1u << 22)) {
-            if (fwrite(b.data(), 1, b.size(), t->fh) != b.size()) return RT_EINVAL;
-            b.clear();
-        }
     }
-    if (!b.empty()) {
-        if (fwrite(b.data(), 1, b.size(), t->fh) != b.size()) return RT_EINVAL;
-        b.clear();
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_tsv_write(rt_tsv* t, const rt_index* ix, int64_t n_sel, const int64_t* orf_ids, int64_t orf_lo,
+                 const double* score, const int32_t* valid, const int64_t* count, const int32_t* length,
+                 const uint8_t* status, const int64_t* prof_ptr, const int32_t* prof) {
+    if (!t || !ix || n_sel < 0 || (n_sel && (!orf_ids || !score || !valid || !count || !length || !status || !prof_ptr || !prof)))
+        return RT_EINVAL;
+    // the profile column is most of the text: rows are formatted by several threads in slices balanced by
+    // profile length and written in order
+    const int64_t total = n_sel ? prof_ptr[n_sel] - prof_ptr[0] : 0;
+    const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)16,
+                                                                  (total + n_sel * 40) / (1 << 21)}));
+    std::vector<int64_t> cut(n_thr + 1, n_sel);
+    cut[0] = 0;
+    for (int k = 1; k < n_thr; ++k) {
+        const int64_t target = prof_ptr[0] + total * k / n_thr;
+        cut[k] = std::lower_bound(prof_ptr, prof_ptr + n_sel, target) - prof_ptr;
+        if (cut[k] < cut[k - 1]) cut[k] = cut[k - 1];
+    }
+    std::vector<std::string> parts(n_thr);
+    std::vector<char> ok(n_thr, 1);
+    std::vector<std::thread> pool;
+    for (int k = 1; k < n_thr; ++k)
+        pool.emplace_back([&, k]() {
+            ok[k] = format_rows(parts[k], ix, cut[k], cut[k + 1], orf_ids, orf_lo, score, valid, count, length, status, prof_ptr, prof);
+        });
+    ok[0] = format_rows(parts[0], ix, cut[0], cut[1], orf_ids, orf_lo, score, valid, count, length, status, prof_ptr, prof);
+    for (auto& th : pool) th.join();
+    for (int k = 0; k < n_thr; ++k) {
+        if (!ok[k]) return RT_EINVAL;
+        if (!parts[k].empty() && fwrite(parts[k].data(), 1, parts[k].size(), t->fh) != parts[k].size()) return RT_EINVAL;
     }
     return RT_OK;
 }
