@@ -286,6 +286,28 @@ class Engine:
         out["n"] = n
         return out
 
+    def upload_packed(self, packed: dict) -> dict:
+        """Packed host records (``pack_reads``) -> device tensors, run table included (plumbing only)."""
+        t = self.torch
+
+        def dev(a):
+            if hasattr(a, "data_ptr"):
+                return a.to(self.device)
+            a = np.ascontiguousarray(a)
+            return t.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a).to(self.device)
+
+        out = {k: dev(packed[k]) for k in ("first", "last", "mlen", "meta", "run_start", "run_ref")}
+        out["n"] = int(packed["n"])
+        return out
+
+    def bin_reads_packed_device(self, cov, dpacked: dict, protocol, stats, len_counts, weight: int = 1):
+        """Enqueue K1 on device-resident PACKED records (11 B/read; no host sync)."""
+        p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        self._check(self.lib.rt_bin_reads_packed(
+            self.ctx, p(cov), int(dpacked["n"]), p(dpacked["first"]), p(dpacked["last"]), p(dpacked["mlen"]),
+            p(dpacked["meta"]), 0, int(dpacked["run_ref"].numel()), p(dpacked["run_start"]), p(dpacked["run_ref"]),
+            protocol_code(protocol), int(weight), p(stats), p(len_counts), self._stream()))
+
     def bin_reads_packed_host(self, cov, packed: dict, protocol):
         """K1 on packed HOST records (see ``pack_reads``): chunked H2D of 11 B/read inside the call.
         Returns ``(stats, read_length_counts)`` exactly like ``bin_reads_host``."""

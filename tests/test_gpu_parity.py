@@ -579,6 +579,10 @@ def test_packed_records_match_columns(engine, layout):
             stats_g, len_g = engine.bin_reads_packed_host(got, packed, protocol)
             assert stats_g == stats_w and (len_g == len_w).all()
             assert engine.torch.equal(got, want)
+            dev = engine.new_coverage()                    # the same records resident on the device
+            st, lc = engine.new_bin_accumulators()
+            engine.bin_reads_packed_device(dev, engine.upload_packed(packed), protocol, st, lc)
+            assert engine.torch.equal(dev, want) and dict(zip(stats_w.keys(), st.cpu().tolist())) == stats_w
         # unsorted input has one run per read, far more than the table holds: refused, not mis-binned
         shuffled = {k: v[rng.permutation(n)] for k, v in reads.items()}
         with pytest.raises(RtError, match="not grouped by reference"):
