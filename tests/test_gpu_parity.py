@@ -583,6 +583,9 @@ def test_packed_records_match_columns(engine, layout):
             st, lc = engine.new_bin_accumulators()
             engine.bin_reads_packed_device(dev, engine.upload_packed(packed), protocol, st, lc)
             assert engine.torch.equal(dev, want) and dict(zip(stats_w.keys(), st.cpu().tolist())) == stats_w
+        empty = engine.pack_reads({k: v[:0] for k, v in reads.items()})        # no reads at all
+        stats_e, len_e = engine.bin_reads_packed_host(engine.new_coverage(), empty, "forward")
+        assert stats_e["total"] == 0 and not len_e.any()
         # unsorted input has one run per read, far more than the table holds: refused, not mis-binned
         shuffled = {k: v[rng.permutation(n)] for k, v in reads.items()}
         with pytest.raises(RtError, match="not grouped by reference"):
