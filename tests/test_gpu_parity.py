@@ -600,3 +600,82 @@ def test_packed_records_match_columns(engine, layout):
         assert stats_g == stats_w and engine.torch.equal(got, want)
     finally:
         engine.set_layout("dense")
+
+
+def test_random_many_exon_orfs_both_layouts(engine):
+    """Randomised soak (fixed seed): ORFs of up to 200 exons of 1-40 nt with gaps of 0-7 nt, nested ORFs that
+    share their tails, both strands, coverage densities from 0.02 to 30 per nt (table path, slow path,
+    segmented phase B, one-value atoms at segment cuts) against the C oracle; the compact layout must return
+    bit-identical columns."""
+    CO = _oracle()
+    from helpers import compare_scores as _cmp
+    n_bad = 0
+    rng = np.random.default_rng(12345)
+    n_bad = 0
+    for trial in range(16):
+        L = int(rng.integers(3000, 20000))
+        lens = np.array([L, int(rng.integers(500, 3000))], np.int64)
+        pad = int(rng.choice([8, 16, 64]))
+        orfs = []
+        for _ in range(int(rng.integers(5, 40))):
+            c = int(rng.integers(0, 2)); s = int(rng.integers(0, 2))
+            n_ex = int(rng.choice([1, 2, 5, 30, 60, 120, 200]))
+            pos = int(rng.integers(1, max(2, lens[c] // 3)))
+            ivs = []
+            for _ in range(n_ex):
+                ln = int(rng.choice([1, 1, 2, 3, 5, 9, 40]))
+                if pos + ln - 1 > lens[c] + pad - 1:
+                    break
+                ivs.append((pos, pos + ln - 1))
+                pos += ln + int(rng.choice([0, 0, 1, 2, 7]))   # gap 0 = adjacent exons (separate entries)
+            if not ivs:
+                continue
+            orfs.append((c, s, ivs))
+            for k in range(int(rng.integers(0, 3))):            # nested ORFs sharing the tail
+                cut = int(rng.integers(0, len(ivs)))
+                a, b = ivs[cut]
+                a2 = int(rng.integers(a, b + 1))
+                orfs.append((c, s, [(a2, b)] + ivs[cut + 1:]))
+        ptr, st, en, contig, strand = [0], [], [], [], []
+        for c, s, ivs in orfs:
+            for a, b in ivs:
+                st.append(a); en.append(b)
+            ptr.append(len(st)); contig.append(c); strand.append(s)
+        idx = dict(exon_ptr=np.array(ptr, np.int64), exon_start=np.array(st, np.int32), exon_end=np.array(en, np.int32),
+                   orf_contig=np.array(contig, np.int32), orf_strand=np.array(strand, np.uint8))
+        engine.set_genome(["a", "b"], lens, pad=pad)
+        engine.set_length_table({28: min(12, pad)}, None)
+        engine.set_index(**idx)
+        base, plane = CO.genome_layout(lens, pad)
+        cov = np.zeros(2 * plane, np.int32)
+        dens = float(rng.choice([0.02, 0.3, 2.0, 30.0]))
+        for c in range(2):
+            for s in range(2):
+                lo = s * plane + base[c]; span = lens[c] + 2 * pad + 1
+                cov[lo:lo + span] = rng.poisson(dens, span) * (rng.random(span) < rng.choice([0.1, 0.5, 1.0]))
+        d_cov = engine.torch.from_numpy(cov).to(engine.device)
+        got = engine.score_host(d_cov, diagnostics=True, min_codon=True)
+        ref = CO.score(idx, cov, base, lens, pad, plane, DEFAULT_PARAMS)
+        tie = CO.tie_mask(ref["frame_K"], ref["frame_s"])
+        try:
+            _cmp(got, ref, tie)
+            assert (got["frame_K"] == ref["frame_K"]).all()
+            # compact layout through K1-free path: copy dense values of member slots
+            engine.set_layout("compact")
+            ccov = engine.new_coverage()
+            member = np.zeros(2 * plane, bool)
+            for o in range(len(contig)):
+                for e in range(ptr[o], ptr[o + 1]):
+                    a = max(st[e], 1 - pad); b = min(en[e], int(lens[contig[o]]) + pad)
+                    if a <= b:
+                        member[strand[o] * plane + base[contig[o]] + pad + a: strand[o] * plane + base[contig[o]] + pad + b + 1] = True
+            ccov[:int(member.sum())] = engine.torch.from_numpy(cov[member]).to(engine.device)
+            got_c = engine.score_host(ccov, diagnostics=True, min_codon=True)
+            for k in got:
+                assert np.array_equal(got[k], got_c[k], equal_nan=True), ("compact", k)
+            engine.set_layout("dense")
+        except AssertionError as exc:
+            n_bad += 1
+            print("trial", trial, "FAILED:", exc, "orfs", len(orfs), "max exons", max(len(i) for _, _, i in orfs))
+            engine.set_layout("dense")
+    assert n_bad == 0
