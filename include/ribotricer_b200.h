@@ -31,7 +31,9 @@
  *              first/last = 0-based first/last matched reference position
  *              (pysam get_reference_positions()[0] / [-1], bam.py:95),
  *              mlen = number of matched positions (bam.py:99), flag = SAM flag,
- *              nh = value of the NH tag, 0 when the tag is absent.
+ *              nh = the NH tag as common.py:53-56 tests it: 0 = absent, 1 = present and equal
+ *              to 1, any other value = present and different from 1 (rt_bam_* stores 2..254 as
+ *              is and 255 for values <= 0, > 254 or of a non-numeric type).
  *   index      CSR over candidate ORFs in index-file order: exon_ptr[n+1],
  *              exon_start/exon_end (1-based closed, ascending, orf.py:100),
  *              orf_contig (-1 = contig unknown to the genome table),
@@ -46,13 +48,16 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 1
+#define RT_ABI_VERSION 2
 
-/* read-length table: one int32 per matched length */
+/* read-length table: one int32 per matched length = the P-site offset of that length (may be negative:
+ * align_metagenes returns lag + 12 with lag in [-min(base, length), ...), metagene.py:319-324; |offset| <=
+ * RT_MAX_OFFSET) or one of two sentinels that lie outside the range of offsets */
 #define RT_LEN_TABLE 65536
-#define RT_LEN_UNUSED (-1)   /* length kept by split_bam but absent from psite_offsets
-                                (dropped by merge_read_lengths, detect_orfs.py:74) */
-#define RT_LEN_FILTERED (-2) /* length not in --read_lengths (bam.py:101) */
+#define RT_MAX_OFFSET 65535
+#define RT_LEN_UNUSED (-2147483647 - 1)  /* length kept by split_bam but absent from psite_offsets
+                                            (dropped by merge_read_lengths, detect_orfs.py:74) */
+#define RT_LEN_FILTERED (-2147483647)    /* length not in --read_lengths (bam.py:101) */
 
 /* protocol (bam.py:105,118); any other value stores no read, like the reference */
 #define RT_PROTOCOL_FORWARD 0
@@ -271,7 +276,8 @@ int rt_wig_close(rt_tsv* t);
  * ---- native BAM/BGZF decode to read columns (no GPU involved; SURVEY.md 8(f) "next #2") -------
  * Replaces the pysam passes of split_bam (bam.py:65-71) on the host: per record ref_id, flag,
  * mapq, the first/last/count of matched reference positions (get_reference_positions() semantics of
- * bam.py:95-99: M, = and X operations only) and the NH tag (0 if absent, common.py:53-56).
+ * bam.py:95-99: M, = and X operations only) and the NH tag (see `nh` above, common.py:53-56).
+ * Records whose fields run past their block_size are rejected ("corrupt BAM record").
  * BGZF blocks are inflated with `n_threads` threads (<= 0: all cores).
  */
 typedef struct rt_bam rt_bam;
@@ -285,6 +291,9 @@ int64_t rt_bam_ref_len(const rt_bam* b, int i);
 int rt_bam_sorted(const rt_bam* b);                          /* @HD SO:coordinate */
 int rt_bam_copy(const rt_bam* b, int32_t* ref_id, int32_t* first, int32_t* last, uint16_t* mlen,
                 uint16_t* flag, uint8_t* mapq, uint8_t* nh); /* any pointer may be NULL */
+/* reference_start / reference_end of every record as infer_protocol.py:84-85 reads them (host-side protocol
+ * inference only; ref_end = -1 where pysam gives None: unmapped flag or no CIGAR) */
+int rt_bam_copy_span(const rt_bam* b, int32_t* pos, int32_t* ref_end);
 /* the decoded reads as packed records (rt_pack_read_meta on the decoder's own columns): meta[n_reads] and the
  * run table; first / last / mlen come from rt_bam_copy */
 int rt_bam_pack(const rt_bam* b, uint8_t* meta, int64_t run_cap, int64_t* run_start, int32_t* run_ref, int64_t* n_runs);

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librt_oracle.so")
 ST_NAMES = ("total", "qcfail", "duplicate", "secondary", "unmapped", "multi", "valid", "oob", "badref")
 LEN_TABLE = 65536
-LEN_UNUSED, LEN_FILTERED = -1, -2
+LEN_UNUSED, LEN_FILTERED = -2147483648, -2147483647
 
 _lib = None
 
@@ -44,7 +44,7 @@ def _p(a):
 
 
 def make_len_table(psite_offsets: dict | None, read_lengths=None) -> np.ndarray:
-    """len -> offset (>=0), LEN_UNUSED (kept, not merged) or LEN_FILTERED."""
+    """len -> offset (any sign), LEN_UNUSED (kept, not merged) or LEN_FILTERED."""
     t = np.full(LEN_TABLE, LEN_UNUSED, dtype=np.int32)
     if read_lengths is not None:
         t[:] = LEN_FILTERED

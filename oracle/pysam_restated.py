@@ -8,6 +8,7 @@ image and not installable offline.  ``split_bam`` (bam.py:33-153) and ``is_read_
     pysam.AlignmentFile(path, "rb")   .count(until_eof=True)  .fetch(until_eof=True)  .close()
     AlignedSegment: is_qcfail, is_duplicate, is_secondary, is_unmapped, is_reverse, flag,
                     mapping_quality, reference_name, get_tags(), get_reference_positions()
+and ``infer_protocol`` (infer_protocol.py:34-124) additionally ``reference_start`` / ``reference_end``.
 
 Every one of them is defined by the SAM/BAM specification (SAMv1 section 4.2) plus pysam's
 documented behaviour: ``get_reference_positions()`` lists the reference positions of the aligned
@@ -15,6 +16,9 @@ bases, i.e. of CIGAR operations M, = and X (insertions and soft clips have no re
 and are left out because ``full_length`` defaults to False; D and N advance the reference without
 yielding positions).  With this module installed as ``pysam`` the UNMODIFIED reference
 ``split_bam`` runs here on real BAM bytes, which is how tests/golden/split_bam_case.json.gz was made.
+``reference_end`` follows pysam's property (libcalignedsegment.pyx): ``None`` when the read carries the unmapped
+flag or has no CIGAR, otherwise htslib's ``bam_endpos``: ``pos`` + the reference length of the CIGAR (operations
+M, D, N, = and X), counting at least 1.
 It shares no code with the product's decoder (ribotricer_b200/csrc/rt_bam.cpp).
 """
 from __future__ import annotations
@@ -41,6 +45,13 @@ class AlignedSegment:
     is_secondary = property(lambda self: bool(self.flag & 0x100))
     is_unmapped = property(lambda self: bool(self.flag & 0x4))
     is_reverse = property(lambda self: bool(self.flag & 0x10))
+
+    @property
+    def reference_end(self):
+        if self.flag & 0x4 or not self.cigartuples:
+            return None
+        rlen = sum(n for op, n in self.cigartuples if op in (0, 2, 3, 7, 8))
+        return self.reference_start + (rlen or 1)
 
     @property
     def reference_name(self):

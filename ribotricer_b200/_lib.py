@@ -12,8 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RT_LIB_PATH") or os.path.join(HERE, "libribotricer_b200.so")   # override: kernel A/B runs
 
 RT_LEN_TABLE = 65536
-RT_LEN_UNUSED = -1
-RT_LEN_FILTERED = -2
+RT_MAX_OFFSET = 65535
+RT_LEN_UNUSED = -2147483648
+RT_LEN_FILTERED = -2147483647
 RT_PROTOCOL_FORWARD, RT_PROTOCOL_REVERSE, RT_PROTOCOL_NONE = 0, 1, 2
 ST_NAMES = ("total", "qcfail", "duplicate", "secondary", "unmapped", "multi", "valid", "oob", "badref")
 RT_N_STATS = len(ST_NAMES)
@@ -27,7 +28,7 @@ EXPORTS = (
     "rt_index_free", "rt_index_n_orf", "rt_index_n_exon", "rt_index_n_annotated_prefix", "rt_index_n_chrom",
     "rt_index_chrom_name", "rt_index_copy", "rt_index_field", "rt_tsv_open", "rt_tsv_write", "rt_tsv_close",
     "rt_repr_double", "rt_wig_open", "rt_wig_block", "rt_wig_close", "rt_bam_last_error", "rt_bam_load", "rt_bam_free", "rt_bam_n_reads", "rt_bam_n_ref",
-    "rt_bam_ref_name", "rt_bam_ref_len", "rt_bam_sorted", "rt_bam_copy", "rt_bam_pack",
+    "rt_bam_ref_name", "rt_bam_ref_len", "rt_bam_sorted", "rt_bam_copy", "rt_bam_copy_span", "rt_bam_pack",
 )
 
 
@@ -131,10 +132,11 @@ def load():
     lib.rt_bam_ref_len.restype = i64
     lib.rt_bam_sorted.argtypes = [vp]
     lib.rt_bam_copy.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.rt_bam_copy_span.argtypes = [vp, vp, vp]
     lib.rt_bam_pack.argtypes = [vp, vp, i64, vp, vp, C.POINTER(i64)]
     lib.rt_launch_count.restype = i64
-    if lib.rt_abi_version() != 1:
-        raise RtError(f"ABI mismatch: library reports {lib.rt_abi_version()}, binding expects 1")
+    if lib.rt_abi_version() != 2:
+        raise RtError(f"ABI mismatch: library reports {lib.rt_abi_version()}, binding expects 2")
     _lib = lib
     return lib
 

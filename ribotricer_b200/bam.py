@@ -24,7 +24,8 @@ class ReadColumns:
     """Decoded alignment records (structure of arrays) + the BAM header's contig table."""
     contig_names: list
     contig_len: np.ndarray
-    cols: dict              # name -> numpy array, see engine.READ_COLUMNS
+    cols: dict              # name -> numpy array, see engine.READ_COLUMNS; optional host-only extras "pos" and
+                            # "ref_end" (reference_start / reference_end, -1 = None) for infer_protocol
     sorted_by_coordinate: bool = False
 
     def __len__(self) -> int:
@@ -34,6 +35,20 @@ class ReadColumns:
 def save_read_columns(path: str, reads: ReadColumns) -> None:
     np.savez(path, contig_names=np.array(reads.contig_names), contig_len=reads.contig_len,
              sorted_by_coordinate=np.array(reads.sorted_by_coordinate), **reads.cols)
+
+
+def encode_nh(tags: dict) -> int:
+    """The ``nh`` column: how ``dict(read.get_tags())["NH"] == 1`` (common.py:53-56) turns out.
+    0 = no NH tag, 1 = equal to 1, anything else = present and different from 1."""
+    if "NH" not in tags:
+        return 0
+    v = tags["NH"]
+    if isinstance(v, (int, float)) and not isinstance(v, bool):
+        if v == 1:
+            return 1
+        if isinstance(v, int) and 2 <= v <= 254:
+            return int(v)
+    return 255
 
 
 def _matched_span(read):
@@ -66,6 +81,7 @@ def read_bam_columns(bam_path: str) -> ReadColumns:
     names = list(bam.references)
     lens = np.array(bam.lengths, np.int64)
     acc = {name: [] for name, _ in READ_COLUMNS}
+    acc["pos"], acc["ref_end"] = [], []
     for read in bam.fetch(until_eof=True):      # bam.py:71
         first, last, n = _matched_span(read)
         acc["ref_id"].append(read.reference_id if read.reference_id is not None else -1)
@@ -74,11 +90,14 @@ def read_bam_columns(bam_path: str) -> ReadColumns:
         acc["mlen"].append(min(n, 65535))
         acc["flag"].append(read.flag)
         acc["mapq"].append(read.mapping_quality)
-        nh = read.get_tag("NH") if read.has_tag("NH") else 0   # common.py:53-56
-        acc["nh"].append(min(max(int(nh), 0), 255) if nh != 0 else 0)
+        acc["nh"].append(encode_nh(dict(read.get_tags())))     # common.py:53-56
+        acc["pos"].append(read.reference_start)
+        acc["ref_end"].append(-1 if read.reference_end is None else read.reference_end)
     so = bam.header.to_dict().get("HD", {}).get("SO", "") == "coordinate"
     bam.close()
-    return ReadColumns(names, lens, {k: np.asarray(acc[k], dt) for k, dt in READ_COLUMNS}, so)
+    cols = {k: np.asarray(acc[k], dt) for k, dt in READ_COLUMNS}
+    cols["pos"], cols["ref_end"] = np.asarray(acc["pos"], np.int32), np.asarray(acc["ref_end"], np.int32)
+    return ReadColumns(names, lens, cols, so)
 
 
 def read_bam_columns_native(bam_path: str, n_threads: int = 0) -> ReadColumns:
@@ -94,6 +113,8 @@ def read_bam_columns_native(bam_path: str, n_threads: int = 0) -> ReadColumns:
         n = int(lib.rt_bam_n_reads(handle))
         cols = {name: np.zeros(n, dt) for name, dt in READ_COLUMNS}
         lib.rt_bam_copy(handle, *[cols[name].ctypes.data_as(C.c_void_p) for name, _ in READ_COLUMNS])
+        cols["pos"], cols["ref_end"] = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        lib.rt_bam_copy_span(handle, cols["pos"].ctypes.data_as(C.c_void_p), cols["ref_end"].ctypes.data_as(C.c_void_p))
         n_ref = lib.rt_bam_n_ref(handle)
         names = [lib.rt_bam_ref_name(handle, i).decode() for i in range(n_ref)]
         lens = np.array([lib.rt_bam_ref_len(handle, i) for i in range(n_ref)], np.int64)
@@ -111,6 +132,9 @@ def load_reads(path) -> ReadColumns:
     if str(path).endswith(".npz"):
         z = np.load(path, allow_pickle=False)
         cols = {name: np.ascontiguousarray(z[name], dt) for name, dt in READ_COLUMNS}
+        for extra in ("pos", "ref_end"):
+            if extra in z:
+                cols[extra] = np.ascontiguousarray(z[extra], np.int32)
         so = bool(z["sorted_by_coordinate"]) if "sorted_by_coordinate" in z else False
         return ReadColumns([str(c) for c in z["contig_names"]], np.asarray(z["contig_len"], np.int64), cols, so)
     if os.environ.get("RIBOTRICER_B200_PYSAM") == "1":

@@ -5,7 +5,12 @@
 //   ref_id  = reference_id                       flag = flag        mapq = mapping_quality
 //   first / last / mlen = get_reference_positions()[0] / [-1] / len()   (bam.py:95-99): reference
 //             positions of M, = and X operations only (D and N advance the reference, S I H P do not)
-//   nh      = integer value of the NH aux tag, 0 when absent (common.py:53-56), saturated at 255
+//   nh      = the NH aux tag as is_read_uniq_mapping sees it (common.py:53-56: `dict(get_tags())["NH"] == 1`):
+//             0 = absent, 1 = present and equal to 1, anything else = present and different from 1
+//             (2..254 the value itself; 255 for values <= 0, > 254 or of a non-numeric type).  When the tag
+//             occurs twice the LAST one counts, as in dict().
+//   pos / ref_end = reference_start / reference_end of infer_protocol.py:84-85 (ref_end = -1 for None:
+//             unmapped flag or no CIGAR; else pos + reference length of the CIGAR, at least 1 as in htslib)
 // BGZF blocks are inflated in parallel (zlib raw inflate), records are cut sequentially and
 // decoded in parallel.  No GPU is involved.
 #include <sys/mman.h>
@@ -28,7 +33,7 @@
 struct rt_bam {
     std::vector<std::string> ref_names;
     std::vector<int64_t> ref_lens;
-    std::vector<int32_t> ref_id, first, last;
+    std::vector<int32_t> ref_id, first, last, pos, ref_end;
     std::vector<uint16_t> mlen, flag;
     std::vector<uint8_t> mapq, nh;
     bool sorted = false;
@@ -94,14 +99,19 @@ void parallel_for(int n_threads, size_t n, const std::function<void(size_t, size
 }
 
 // Decode one alignment record (after its block_size field) into slot i of the columns.
-void decode_record(const uint8_t* r, uint32_t len, rt_bam& out, size_t i) {
+// Returns false when the fixed fields, the CIGAR or an aux field run past the record (untrusted input).
+bool decode_record(const uint8_t* r, uint32_t len, rt_bam& out, size_t i) {
     const int32_t ref = rdi32(r), pos = rdi32(r + 4);
     const uint32_t l_name = r[8];
     const uint32_t n_cigar = rd16(r + 12);
     const int32_t l_seq = rdi32(r + 16);
+    if (l_seq < 0) return false;
+    const uint64_t fixed = 32ull + l_name + 4ull * n_cigar + ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq;
+    if (fixed > len) return false;
     out.ref_id[i] = ref;
     out.mapq[i] = r[9];
-    out.flag[i] = rd16(r + 14);
+    const uint16_t flag = rd16(r + 14);
+    out.flag[i] = flag;
     const uint8_t* cig = r + 32 + l_name;
     int64_t cur = pos, first = 0, last = 0, n = 0;
     for (uint32_t k = 0; k < n_cigar; ++k) {
@@ -118,48 +128,57 @@ void decode_record(const uint8_t* r, uint32_t len, rt_bam& out, size_t i) {
     out.first[i] = (int32_t)first;
     out.last[i] = (int32_t)last;
     out.mlen[i] = (uint16_t)std::min<int64_t>(n, 65535);
-    // aux fields: find NH with an integer type
+    out.pos[i] = pos;
+    const int64_t rlen = cur - pos;
+    out.ref_end[i] = ((flag & 4) || n_cigar == 0) ? -1 : (int32_t)(pos + (rlen ? rlen : 1));
+    // aux fields: the NH tag as `dict(read.get_tags())["NH"] == 1` sees it
     const uint8_t* end = r + len;
-    const uint8_t* a = cig + 4 * (size_t)n_cigar + (size_t)((l_seq + 1) / 2) + (size_t)l_seq;
-    if (l_seq < 0 || a > end) a = end;                    // malformed record: no aux fields
-    long long nh = 0;
-    bool have = false;
+    const uint8_t* a = r + fixed;
+    int nh = 0;                                           // 0 absent, 1 equal to 1, else present and not 1
     while (a + 3 <= end) {
         const uint8_t t0 = a[0], t1 = a[1], ty = a[2];
         a += 3;
-        long long val = 0;
-        bool is_int = true;
         size_t adv = 0;
         switch (ty) {
-            case 'A': adv = 1; is_int = false; break;
-            case 'c': val = (int8_t)a[0]; adv = 1; break;
-            case 'C': val = a[0]; adv = 1; break;
-            case 's': val = (int16_t)rd16(a); adv = 2; break;
-            case 'S': val = rd16(a); adv = 2; break;
-            case 'i': val = rdi32(a); adv = 4; break;
-            case 'I': val = rd32(a); adv = 4; break;
-            case 'f': adv = 4; is_int = false; break;
+            case 'A': case 'c': case 'C': adv = 1; break;
+            case 's': case 'S': adv = 2; break;
+            case 'i': case 'I': case 'f': adv = 4; break;
             case 'Z': case 'H': {
                 const uint8_t* z = (const uint8_t*)memchr(a, 0, (size_t)(end - a));
-                adv = z ? (size_t)(z - a) + 1 : (size_t)(end - a);
-                is_int = false;
+                if (!z) return false;
+                adv = (size_t)(z - a) + 1;
                 break;
             }
             case 'B': {
-                if (a + 5 > end) { a = end; continue; }
+                if (a + 5 > end) return false;
                 const uint8_t sub = a[0];
                 const uint32_t cnt = rd32(a + 1);
                 const size_t w = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
                 adv = 5 + (size_t)cnt * w;
-                is_int = false;
                 break;
             }
-            default: a = end; continue;               // unknown type: stop scanning
+            default: return false;                    // unknown aux type
         }
-        if (t0 == 'N' && t1 == 'H' && is_int && !have) { nh = val; have = true; }
+        if (adv > (size_t)(end - a)) return false;
+        if (t0 == 'N' && t1 == 'H') {
+            long long val = 0;
+            bool numeric = true;
+            switch (ty) {
+                case 'c': val = (int8_t)a[0]; break;
+                case 'C': val = a[0]; break;
+                case 's': val = (int16_t)rd16(a); break;
+                case 'S': val = rd16(a); break;
+                case 'i': val = rdi32(a); break;
+                case 'I': val = rd32(a); break;
+                case 'f': { float f; memcpy(&f, a, 4); val = f == 1.0f ? 1 : 0; break; }   // 1.0 == 1 in Python
+                default: numeric = false;
+            }
+            nh = !numeric ? 255 : val == 1 ? 1 : (val >= 2 && val <= 254) ? (int)val : 255;
+        }
         a += adv;
     }
-    out.nh[i] = have ? (uint8_t)std::min<long long>(std::max<long long>(nh, 0), 255) : 0;
+    out.nh[i] = (uint8_t)nh;
+    return true;
 }
 
 }  // namespace
@@ -261,10 +280,14 @@ int rt_bam_load(const char* path, int n_threads, rt_bam** out) {
         const size_t base_i = bam->ref_id.size(), m = rec_off.size();
         bam->ref_id.resize(base_i + m); bam->first.resize(base_i + m); bam->last.resize(base_i + m);
         bam->mlen.resize(base_i + m); bam->flag.resize(base_i + m); bam->mapq.resize(base_i + m); bam->nh.resize(base_i + m);
+        bam->pos.resize(base_i + m); bam->ref_end.resize(base_i + m);
+        std::atomic<bool> rec_ok{true};
         parallel_for(n_threads, m, [&](size_t lo, size_t hi) {
             for (size_t k = lo; k < hi; ++k)
-                decode_record(buf.data() + rec_off[k] + 4, rd32(buf.data() + rec_off[k]), *bam, base_i + k);
+                if (!decode_record(buf.data() + rec_off[k] + 4, rd32(buf.data() + rec_off[k]), *bam, base_i + k))
+                    rec_ok = false;
         });
+        if (!rec_ok) { delete bam; return fail("corrupt BAM record"); }
         buf.erase(buf.begin(), buf.begin() + (ptrdiff_t)p);
     }
     if (size) munmap((void*)base, size);
@@ -293,6 +316,13 @@ int rt_bam_copy(const rt_bam* b, int32_t* ref_id, int32_t* first, int32_t* last,
     if (flag) std::copy(b->flag.begin(), b->flag.end(), flag);
     if (mapq) std::copy(b->mapq.begin(), b->mapq.end(), mapq);
     if (nh) std::copy(b->nh.begin(), b->nh.end(), nh);
+    return RT_OK;
+}
+
+int rt_bam_copy_span(const rt_bam* b, int32_t* pos, int32_t* ref_end) {
+    if (!b) return RT_EINVAL;
+    if (pos) std::copy(b->pos.begin(), b->pos.end(), pos);
+    if (ref_end) std::copy(b->ref_end.begin(), b->ref_end.end(), ref_end);
     return RT_OK;
 }
 

@@ -65,6 +65,9 @@ struct rt_ctx {
     unsigned long long* d_work_counter = nullptr;   // 4 x u64: work counters of the 3 score launches + fallback count
     int pack_lpo = 8;                                // lanes per ORF of the packed kernel (RT_PACK_LPO)
     int atom_lpo = 4;                                // lanes per atom in phase A (RT_ATOM_LPO)
+    bool use_ref_kernel = true;                      // phase B with one lane per atom reference (RT_PHASE_B=thread: one thread per ORF)
+    bool use_pass_kernel = true;                     // compact layout: streamed phase A (RT_PHASE_A=atoms selects the per-atom kernel)
+    int pass_warps = 16, pass_stages = 2;            // RT_PASS_WARPS (1..32), RT_PASS_STAGES (1..4)
     bool use_atoms = true;                           // two-phase scoring (RT_SCORE_PATH=scan selects the scan kernel)
 
     // two-phase scoring: atoms (coverage intervals no ORF exon boundary splits) and per-ORF atom refs
@@ -84,6 +87,7 @@ struct rt_ctx {
     uint64_t* d_ref_ent_c = nullptr;
     uint64_t* d_exon_entries_c = nullptr;
     std::vector<uint64_t> h_atoms;                   // host copies used to build per-range atom lists
+    std::vector<uint64_t> h_atoms_c;                 // ... with compact slot offsets
     std::vector<uint64_t> h_orf_refs_desc;
     std::vector<uint32_t> h_ref_atom;
     std::vector<uint64_t> h_ref_ent;
@@ -100,6 +104,12 @@ struct rt_ctx {
         unsigned* d_seg_done = nullptr;        // one per long ORF
         int64_t n_segs = 0;
         int64_t n_atom_list = 0;
+        rt::PassDesc* d_passes = nullptr;      // compact layout: runs of adjacent atoms for atom_pass_kernel
+        int64_t n_passes = 0;
+        rt::RefRec* d_refs = nullptr;          // compose_refs_kernel: one slot per atom reference, groups of 32
+        rt::RefWarp* d_ref_warps = nullptr;
+        rt::LongAcc* d_long_acc = nullptr;     // one per ORF with more than 32 references
+        int64_t n_ref_warps = 0;
     };
     std::vector<ScorePlan> plans;
 
@@ -239,7 +249,9 @@ int build_atoms(rt_ctx* ctx, const std::vector<uint64_t>& desc, const std::vecto
     }
     ctx->n_atoms = (int64_t)ctx->h_atoms.size();
     // compact layout: atom i starts at the sum of the lengths of the atoms before it
-    std::vector<uint64_t> atoms_c(ctx->h_atoms.size()), ref_ent_c(ctx->h_ref_ent.size()), entries_c(entries.size());
+    std::vector<uint64_t>& atoms_c = ctx->h_atoms_c;
+    atoms_c.assign(ctx->h_atoms.size(), 0);
+    std::vector<uint64_t> ref_ent_c(ctx->h_ref_ent.size()), entries_c(entries.size());
     uint64_t cat = 0;
     for (size_t i = 0; i < atoms_c.size(); ++i) {
         const uint64_t len = ctx->h_atoms[i] & rt::kLenMask;
@@ -255,7 +267,7 @@ int build_atoms(rt_ctx* ctx, const std::vector<uint64_t>& desc, const std::vecto
     }
     auto upload = [&](auto** dptr, const auto& vec) -> cudaError_t {
         using T = typename std::remove_reference<decltype(vec)>::type::value_type;
-        cudaError_t e = cudaMalloc(dptr, sizeof(T) * std::max<size_t>(1, vec.size()));
+        cudaError_t e = cudaMalloc(dptr, sizeof(T) * (vec.size() + 4));   // slack: atom_pass_kernel copies descriptor pairs
         if (e == cudaSuccess && !vec.empty()) e = cudaMemcpy(*dptr, vec.data(), sizeof(T) * vec.size(), cudaMemcpyHostToDevice);
         return e;
     };
@@ -317,6 +329,10 @@ int rt_create(int device, rt_ctx** out) {
         const int v = atoi(e);
         if (v == 2 || v == 4 || v == 8) ctx->atom_lpo = v;
     }
+    if (const char* e = getenv("RT_PHASE_A")) ctx->use_pass_kernel = strcmp(e, "atoms") != 0;
+    if (const char* e = getenv("RT_PHASE_B")) ctx->use_ref_kernel = strcmp(e, "thread") != 0;
+    if (const char* e = getenv("RT_PASS_WARPS")) ctx->pass_warps = std::min(32, std::max(1, atoi(e)));
+    if (const char* e = getenv("RT_PASS_STAGES")) ctx->pass_stages = std::min(3, std::max(1, atoi(e)));
     if (const char* e = getenv("RT_PACK_LPO")) {
         const int v = atoi(e);
         if (v == 8 || v == 16 || v == 32) ctx->pack_lpo = v;
@@ -355,6 +371,10 @@ void rt_destroy(rt_ctx* ctx) {
         cudaFree(p.d_segs);
         cudaFree(p.d_partials);
         cudaFree(p.d_seg_done);
+        cudaFree(p.d_passes);
+        cudaFree(p.d_refs);
+        cudaFree(p.d_ref_warps);
+        cudaFree(p.d_long_acc);
     }
     for (int s = 0; s < 2; ++s) {
         ctx->read_slot[s].release();
@@ -381,7 +401,7 @@ int rt_set_genome(rt_ctx* ctx, int n_contig, const int64_t* h_contig_len, int pa
     ctx->contig_base.assign(n_contig, 0);
     int64_t at = 0;
     for (int c = 0; c < n_contig; ++c) {
-        if (h_contig_len[c] < 0 || h_contig_len[c] > 0x7fffffff - 2ll * pad - 64)
+        if (h_contig_len[c] < 0 || h_contig_len[c] > 0x7fffffff - 2ll * pad - 64 - 2ll * RT_MAX_OFFSET)   // K1 adds an offset in 32 bits
             return fail(ctx, RT_EINVAL, "rt_set_genome: contig %d length %lld unsupported", c, (long long)h_contig_len[c]);
         ctx->contig_base[c] = at;
         at += (h_contig_len[c] + 2ll * pad + 1 + 31) / 32 * 32;
@@ -413,14 +433,14 @@ int rt_set_length_table(rt_ctx* ctx, const int32_t* h_len_table) {
     if (!ctx || !h_len_table) return fail(ctx, RT_EINVAL, "rt_set_length_table: NULL argument");
     DeviceGuard guard(ctx->device);
     for (int i = 0; i < RT_LEN_TABLE; ++i)
-        if (h_len_table[i] < RT_LEN_FILTERED || h_len_table[i] > ctx->pad)
-            return fail(ctx, RT_EINVAL, "rt_set_length_table: entry %d = %d outside [-2, pad=%d]", i,
-                        h_len_table[i], ctx->pad);
+        if (h_len_table[i] > RT_LEN_FILTERED && (h_len_table[i] < -RT_MAX_OFFSET || h_len_table[i] > RT_MAX_OFFSET))
+            return fail(ctx, RT_EINVAL, "rt_set_length_table: entry %d = %d is neither a sentinel nor an offset in [-%d, %d]", i,
+                        h_len_table[i], RT_MAX_OFFSET, RT_MAX_OFFSET);
     RT_CUDA(ctx, cudaMemcpy(ctx->d_len_table, h_len_table, sizeof(int32_t) * RT_LEN_TABLE, cudaMemcpyHostToDevice));
     ctx->have_len_table = true;
     ctx->len_base = 20;
     for (int i = 0; i < RT_LEN_TABLE; ++i)
-        if (h_len_table[i] >= 0) {
+        if (h_len_table[i] > RT_LEN_FILTERED) {
             ctx->len_base = i;
             break;
         }
@@ -768,6 +788,10 @@ int rt_set_index(rt_ctx* ctx, int64_t n_orf, const int64_t* h_exon_ptr, const in
         cudaFree(p.d_segs);
         cudaFree(p.d_partials);
         cudaFree(p.d_seg_done);
+        cudaFree(p.d_passes);
+        cudaFree(p.d_refs);
+        cudaFree(p.d_ref_warps);
+        cudaFree(p.d_long_acc);
     }
     ctx->plans.clear();
     cudaFree(ctx->d_atoms);
@@ -924,6 +948,10 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
         cudaFree(ctx->plans.front().d_segs);
         cudaFree(ctx->plans.front().d_partials);
         cudaFree(ctx->plans.front().d_seg_done);
+        cudaFree(ctx->plans.front().d_passes);
+        cudaFree(ctx->plans.front().d_refs);
+        cudaFree(ctx->plans.front().d_ref_warps);
+        cudaFree(ctx->plans.front().d_long_acc);
         ctx->plans.erase(ctx->plans.begin());
     }
     rt_ctx::ScorePlan p;
@@ -955,6 +983,30 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
         std::vector<int32_t> alist;
         for (int64_t a = 0; a < ctx->n_atoms; ++a)
             if (used[a]) alist.push_back((int32_t)a);
+        {   // passes of the streamed phase A: consecutive atom ids are adjacent in the compact buffer
+            std::vector<rt::PassDesc> passes;
+            const uint64_t* ac = ctx->h_atoms_c.data();
+            size_t i = 0;
+            while (i < alist.size()) {
+                const uint32_t a0 = (uint32_t)alist[i];
+                uint32_t n = 0, pieces = 0, slots = 0;
+                while (i < alist.size() && n < (uint32_t)rt::kPassPieces && (uint32_t)alist[i] == a0 + n) {
+                    const uint32_t len = (uint32_t)(ac[a0 + n] & rt::kLenMask);
+                    const uint32_t np = (len + rt::kPieceNt - 1) / rt::kPieceNt;
+                    if (pieces + np > (uint32_t)rt::kPassPieces) break;
+                    pieces += np;
+                    slots += len;
+                    ++n;
+                    ++i;
+                }
+                const uint64_t s0 = ac[a0] >> rt::kLenBits, q0 = s0 & ~3ull, q1 = (s0 + slots + 3) & ~3ull;
+                passes.push_back({a0, n | ((uint32_t)((q1 - q0) >> 2) << 8), (uint32_t)(q0 >> 2), (uint32_t)(s0 - q0)});
+            }
+            p.n_passes = (int64_t)passes.size();
+            RT_CUDA(ctx, cudaMalloc(&p.d_passes, sizeof(rt::PassDesc) * std::max<size_t>(1, passes.size())));
+            if (!passes.empty())
+                RT_CUDA(ctx, cudaMemcpy(p.d_passes, passes.data(), sizeof(rt::PassDesc) * passes.size(), cudaMemcpyHostToDevice));
+        }
         constexpr size_t kAtomWindow = 4096;
         for (size_t w0 = 0; w0 < alist.size(); w0 += kAtomWindow) {
             auto b = alist.begin() + w0, e = alist.begin() + std::min(alist.size(), w0 + kAtomWindow);
@@ -966,6 +1018,50 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
         RT_CUDA(ctx, cudaMalloc(&p.d_atom_list, sizeof(int32_t) * std::max<size_t>(1, alist.size())));
         if (!alist.empty())
             RT_CUDA(ctx, cudaMemcpy(p.d_atom_list, alist.data(), sizeof(int32_t) * alist.size(), cudaMemcpyHostToDevice));
+    }
+    if (ctx->use_atoms) {   // phase B work list: the atom references of the range in index order, in groups of 32 slots
+        std::vector<rt::RefRec> refs;
+        std::vector<rt::RefWarp> warps;
+        refs.reserve((size_t)(ctx->h_ref_ent.size() / std::max<int64_t>(1, ctx->n_orf) * n * 9 / 8 + 64));
+        const rt::RefRec pad_rec{0xffffffffu, 0u, 0u, -1};
+        int n_long = 0;
+        auto pad_group = [&]() {
+            while (refs.size() % 32) refs.push_back(pad_rec);
+            warps.resize(refs.size() / 32, rt::RefWarp{-1, 0});
+        };
+        for (int64_t o = lo; o < hi; ++o) {
+            const uint64_t d = ctx->h_orf_refs_desc[o];
+            const uint64_t rb = d & rt::kBeginMask, cnt = (d >> 40) & (uint64_t)rt::kMaxEntriesPerOrf;
+            const uint32_t rev = (uint32_t)(d >> 63);
+            if (cnt > 32 || refs.size() % 32 + std::max<uint64_t>(cnt, 1) > 32) pad_group();
+            const size_t w0 = refs.size() / 32;
+            uint64_t P = 0;
+            for (uint64_t k = 0; k < cnt; ++k) {
+                const uint32_t len = (uint32_t)(ctx->h_ref_ent[rb + k] & rt::kLenMask);
+                refs.push_back({ctx->h_ref_atom[rb + k], len | (rev << 31), (uint32_t)P, (int32_t)o});
+                P += len;
+            }
+            if (cnt == 0) refs.push_back({0xffffffffu, rev << 31, 0u, (int32_t)o});   // an ORF without intervals still gets its row
+            if (cnt > 32) {
+                pad_group();
+                const int groups = (int)(refs.size() / 32 - w0);
+                for (size_t g = w0; g < warps.size(); ++g) warps[g] = rt::RefWarp{n_long, groups};
+                ++n_long;
+            }
+        }
+        pad_group();
+        p.n_ref_warps = (int64_t)warps.size();
+        RT_CUDA(ctx, cudaMalloc(&p.d_refs, sizeof(rt::RefRec) * std::max<size_t>(1, refs.size())));
+        RT_CUDA(ctx, cudaMalloc(&p.d_ref_warps, sizeof(rt::RefWarp) * std::max<size_t>(1, warps.size())));
+        if (!refs.empty()) {
+            RT_CUDA(ctx, cudaMemcpy(p.d_refs, refs.data(), sizeof(rt::RefRec) * refs.size(), cudaMemcpyHostToDevice));
+            RT_CUDA(ctx, cudaMemcpy(p.d_ref_warps, warps.data(), sizeof(rt::RefWarp) * warps.size(), cudaMemcpyHostToDevice));
+        }
+        std::vector<rt::LongAcc> acc((size_t)std::max(1, n_long));
+        memset(acc.data(), 0, sizeof(rt::LongAcc) * acc.size());
+        for (auto& a : acc) a.mn = 0xffffffffu;
+        RT_CUDA(ctx, cudaMalloc(&p.d_long_acc, sizeof(rt::LongAcc) * acc.size()));
+        RT_CUDA(ctx, cudaMemcpy(p.d_long_acc, acc.data(), sizeof(rt::LongAcc) * acc.size(), cudaMemcpyHostToDevice));
     }
     ctx->plans.push_back(p);
     *out = &ctx->plans.back();
@@ -1026,6 +1122,40 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
             aa.nonzero = ctx->d_atom_nonzero;
             // the per-frame minima only matter for --min_reads_per_codon > 0 or when the caller asks for min_codon
             const bool want_min = d_out->min_codon != nullptr || params->min_reads_per_codon > 0.0;
+            if (compact && ctx->use_pass_kernel) {
+                // streamed phase A: the compact buffer is read once, front to back, through TMA into shared memory
+                rt::PassArgs pa;
+                pa.cov = d_cov;
+                pa.atoms = ctx->d_atoms_c;
+                pa.passes = plan->d_passes;
+                pa.n_passes = (unsigned)plan->n_passes;
+                pa.out = ctx->d_summaries;
+                pa.nonzero = ctx->d_atom_nonzero;
+                const int warps = ctx->pass_warps, stages = ctx->pass_stages;
+                const size_t smem = rt::kUvEntries * sizeof(double2) + (size_t)warps * stages * rt::kPassStageBytes;
+                auto go = [&](auto kern) -> cudaError_t {
+                    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e != cudaSuccess) return e;
+                    const int64_t want = (plan->n_passes + warps - 1) / warps;
+                    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, ctx->n_sm));
+                    kern<<<grid, warps * 32, smem, st>>>(pa);
+                    return cudaSuccess;
+                };
+                cudaError_t e;
+                auto by_threads = [&](auto k512, auto k768, auto k1024) {
+                    return warps <= 16 ? go(k512) : warps <= 24 ? go(k768) : go(k1024);
+                };
+#define RT_PASS_CASE(S)                                                                                              \
+    (want_min ? by_threads(rt::atom_pass_kernel<S, true, 512>, rt::atom_pass_kernel<S, true, 768>,                  \
+                           rt::atom_pass_kernel<S, true, 1024>)                                                      \
+              : by_threads(rt::atom_pass_kernel<S, false, 512>, rt::atom_pass_kernel<S, false, 768>,                \
+                           rt::atom_pass_kernel<S, false, 1024>))
+                if (stages == 1) e = RT_PASS_CASE(1);
+                else if (stages == 2) e = RT_PASS_CASE(2);
+                else e = RT_PASS_CASE(3);
+#undef RT_PASS_CASE
+                RT_CUDA(ctx, e);
+            } else {
             auto launch = [&](auto kmin, auto knomin, int lpo) {
                 const int g = 32 / lpo;
                 const unsigned grid = persistent_grid(ctx, kmin, (plan->n_atom_list + g - 1) / g);
@@ -1035,6 +1165,7 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
             if (ctx->atom_lpo == 2) launch(rt::atom_summary_kernel<2, true>, rt::atom_summary_kernel<2, false>, 2);
             else if (ctx->atom_lpo == 4) launch(rt::atom_summary_kernel<4, true>, rt::atom_summary_kernel<4, false>, 4);
             else launch(rt::atom_summary_kernel<8, true>, rt::atom_summary_kernel<8, false>, 8);
+            }
             ctx->launches++;
         }
         // phase B: one thread per ORF composes its atoms
@@ -1058,7 +1189,25 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
         ca.n_segs = plan->n_segs;
         ca.partials = plan->d_partials;
         ca.seg_done = plan->d_seg_done;
-        rt::score_from_atoms_kernel<<<(unsigned)((ca.n_segs + ca.n_list + 255) / 256), 256, 0, st>>>(ca);
+        if (ctx->use_ref_kernel) {
+            rt::RefComposeArgs ra;
+            ra.refs = plan->d_refs;
+            ra.warps = plan->d_ref_warps;
+            ra.n_warps = plan->n_ref_warps;
+            ra.summaries = ctx->d_summaries;
+            ra.atom_nonzero = ctx->d_atom_nonzero;
+            ra.want_min = ca.want_min;
+            ra.orf_len = ctx->d_orf_len;
+            ra.orf_lo = orf_lo;
+            ra.fallback = plan->d_fallback;
+            ra.n_fallback = a.n_fallback;
+            ra.long_acc = plan->d_long_acc;
+            ra.prm = *params;
+            ra.out = *d_out;
+            if (ra.n_warps > 0) rt::compose_refs_kernel<<<(unsigned)((ra.n_warps + 7) / 8), 256, 0, st>>>(ra);
+        } else {
+            rt::score_from_atoms_kernel<<<(unsigned)((ca.n_segs + ca.n_list + 255) / 256), 256, 0, st>>>(ca);
+        }
         ctx->launches++;
         // ORFs holding counts >= 2^20: redone by the generic kernel (normally none)
         a.list = plan->d_fallback;

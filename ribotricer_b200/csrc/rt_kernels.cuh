@@ -841,11 +841,14 @@ score_orfs_packed_kernel(const ScoreArgs args) {
 // '-' strand: a profile window (v0,v1,v2) is the reversed genomic triple and u(v0,v1,v2) =
 // w^2 conj(u(v2,v1,v0)), so |sum u| is what the '+'-oriented sums give; only the frame mapping of
 // a local frame differs (see score_from_atoms_kernel).
-constexpr int kAtomMaxNt = 3045;       // <= 127 rounds of 8 lanes (7-bit packed per-lane fields)
+constexpr int kPieceNt = 33;           // values per lane and pass of atom_pass_kernel (odd multiple of 3: frames stay
+                                       //   static per window and consecutive pieces fall into distinct banks)
+constexpr int kPassPieces = 32;        // pieces (= lanes) per pass
+constexpr int kAtomMaxNt = kPieceNt * kPassPieces;   // 1,056: an atom never spans two passes; <= 352 windows per frame
 
 struct AtomSummary {                   // 96 bytes, six 16-byte chunks
-    double re[3];                      // sum of unit vectors by local frame, '+' orientation
-    double im[3];                      //   (imaginary part without its sqrt3 factor)
+    long long re[3];                   // sum of unit vectors by local frame, '+' orientation, in units of 2^-42 (uv_grid:
+    long long im[3];                   //   exact); imaginary part without its sqrt3 factor
     int edge[4];                       // first two and last two values of the atom, ascending slots
                                        //   (edge[1] = edge[2] = 0 for a one-value atom)
     unsigned kpack;                    // kept (non-all-zero) windows by local frame, 10 bits each;
@@ -875,21 +878,31 @@ struct AtomArgs {
 // instead of a divergent classify / rsqrt sequence that few lanes take.
 constexpr int kUvMax = 16;                         // table covers counts 0 .. kUvMax - 1
 constexpr int kUvSide = 2 * kUvMax - 1;            // x, y in [-(kUvMax-1), kUvMax-1]
-constexpr int kUvStride = 2 * kUvMax;              // row stride (power of two: the index is two shifts and adds)
+constexpr int kUvStride = 2 * kUvMax + 5;          // row stride 37 = 5 mod 8: the all-zero entry and the three entries of a single count
+                                                   //   of 1 -- (1,0,0), (0,1,0), (0,0,1) -- fall into four different bank groups; with the
+                                                   //   power of two of round 1 every (a,0,0) entry shared its banks with the all-zero one
 constexpr int kUvEntries = kUvSide * kUvStride;
 constexpr int kUvCenter = (kUvMax - 1) * kUvStride + (kUvMax - 1);
 
+// The unit vector of a non-uniform codon, ROUNDED TO A GRID of 2^-42: (A, B) / sqrt(A^2 + 3 B^2) with the exactly
+// rounded IEEE sqrt and divisions, then to the nearest multiple of 2^-42 (adding and subtracting 1.5 * 2^10, whose
+// ulp is 2^-42).  Sums of up to 1,024 such values are EXACT in fp64 (every partial sum is a multiple of 2^-42 below
+// 2^10), so the per-atom sums do not depend on the order of summation: any lane / tile / layout decomposition of
+// phase A gives bit-identical summaries, and phase B adds them as 64-bit integers (units of 2^-42).  The rounding
+// moves a score by less than 2^-43 (the sums are divided by the number of codons).
+constexpr double kUvGridMagic = 1536.0;
+constexpr double kUvGridScale = 4398046511104.0;      // 2^42
+__device__ __forceinline__ double2 uv_grid(double A, double B) {     // (A, B) != (0, 0); |A|, |B| < 2^22: D is exact
+    const double n = sqrt(fma(A, A, (3.0 * B) * B));
+    const double re = __dadd_rn(__dadd_rn(A / n, kUvGridMagic), -kUvGridMagic);
+    const double im = __dadd_rn(__dadd_rn(B / n, kUvGridMagic), -kUvGridMagic);
+    return make_double2(re, im);
+}
 __device__ __forceinline__ void fill_uv_table(double2* tab) {
     for (int i = threadIdx.x; i < kUvEntries; i += blockDim.x) {
         const int x = i / kUvStride - (kUvMax - 1), y = i % kUvStride - (kUvMax - 1);
         const double A = (double)(2 * x - y), B = (double)y;
-        const double D = A * A + 3.0 * B * B;
-        double2 e = make_double2(0.0, 0.0);
-        if (D > 0.0) {
-            const double n = sqrt(D);
-            e = make_double2(A / n, B / n);
-        }
-        tab[i] = e;
+        tab[i] = (x | y) != 0 ? uv_grid(A, B) : make_double2(0.0, 0.0);
     }
 }
 
@@ -901,7 +914,9 @@ __device__ __forceinline__ void slow_window(int x, int y, int z, unsigned& accK,
     const int A = 2 * x - y - z, B = y - z;
     if ((A | B) == 0) return;                           // uniform: counts in K only
     accM += 1u << (10 * F);
-    unit_vector_add(A, B, f);
+    const double2 u = uv_grid((double)A, (double)B);
+    f.sre += u.x;
+    f.sim += u.y;
 }
 
 #ifndef RT_ATOM_MINBLOCKS
@@ -1093,15 +1108,298 @@ atom_summary_kernel(const AtomArgs args) {
                 s.upack = K - M;                         // field-wise: no borrow, every M field <= its K field
                 s.count = count;
                 s.spare0 = s.spare1 = 0;
-                s.re[0] = re0; s.im[0] = im0;
-                s.re[1] = re1; s.im[1] = im1;
-                s.re[2] = re2; s.im[2] = im2;
+                s.re[0] = __double2ll_rn(re0 * kUvGridScale); s.im[0] = __double2ll_rn(im0 * kUvGridScale);
+                s.re[1] = __double2ll_rn(re1 * kUvGridScale); s.im[1] = __double2ll_rn(im1 * kUvGridScale);
+                s.re[2] = __double2ll_rn(re2 * kUvGridScale); s.im[2] = __double2ll_rn(im2 * kUvGridScale);
                 s.mn[0] = mn0; s.mn[1] = mn1; s.mn[2] = mn2;
                 s.edge[0] = ld_cov(src_done);
                 s.edge[1] = len_done >= 2 ? ld_cov(src_done + 1) : 0;
                 s.edge[2] = len_done >= 2 ? ld_cov(src_done + len_done - 2) : 0;
                 s.edge[3] = ld_cov(src_done + len_done - 1);
                 args.out[atom_done] = s;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- phase A, streamed: atom_pass_kernel --------------------------------------------------------
+// In the compact layout the atoms lie back to back, so phase A is one sequential read of the coverage buffer.
+// The host cuts the atom list into PASSES: runs of consecutive atoms, adjacent in memory, of at most kPassPieces
+// PIECES (a piece = kPieceNt consecutive values of ONE atom, starting a multiple of kPieceNt after the atom's
+// first value).  Every warp owns a ring of shared-memory stages; one elected lane brings the coverage span of a
+// pass (and its atom descriptors) in with cp.async.bulk (TMA, 1-D) completing on the stage's mbarrier, a few passes
+// ahead of the one being scanned.  One lane per piece: the lane reads its kPieceNt + 2 values from shared memory
+// (consecutive pieces are 33 words apart: conflict-free), zeroes what lies beyond its atom's end and settles its
+// 33 windows in straight-line code -- window q is local frame q mod 3, a compile-time constant, and every window
+// is one table lookup (see fill_uv_table) and two exact fp64 adds.  With the tail zeroed the only windows a lane
+// gets wrong are the two that start on the atom's last two values; they depend on those two values alone, and
+// because the sums are exact (uv_grid) the atom's head lane simply subtracts them again.  The pieces of an atom sit
+// on consecutive lanes and are added up by a segmented shuffle reduction; the head lane writes the summary.
+struct PassDesc {                      // 16 bytes, everything the elected lane needs to issue the two copies
+    uint32_t atom0;                    // first atom of the pass
+    uint32_t n_atoms_cov16;            // atoms of the pass (<= kPassPieces) | 16-byte units of coverage to copy << 8
+    uint32_t slot0_q;                  // first coverage slot to copy (slot of atom0's first value, rounded down to 4) >> 2
+    uint32_t slot0_r;                  // slot of atom0's first value minus that (0..3)
+};
+struct PassArgs {
+    const int32_t* cov;
+    const uint64_t* atoms;             // (slot offset << 24) | len; allocated with slack (descriptor pairs are copied)
+    const PassDesc* passes;
+    unsigned n_passes;
+    AtomSummary* out;
+    uint8_t* nonzero;
+};
+constexpr int kPassBufSlots = kAtomMaxNt + 4 + 36;                   // + alignment slack + the reads past a short tail
+constexpr int kPassEntSlots = kPassPieces + 2;                       // atom descriptors of a pass (16-byte aligned copy)
+constexpr int kPassStageBytes = kPassBufSlots * 4 + kPassEntSlots * 8 + 16 + 16;   // values | descriptors | PassDesc | mbarrier
+static_assert(kPassStageBytes % 16 == 0 && (kPassBufSlots * 4) % 16 == 0, "stage layout");
+constexpr int kGroupNt = kPieceNt / 3;                               // a lane settles its piece in three groups of 11 windows
+static_assert(kGroupNt * 3 == kPieceNt, "piece = three groups");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// n += (x != 0) as one compare and one predicated add
+__device__ __forceinline__ void count_nonzero(unsigned& n, int x) {
+    asm("{\n.reg .pred p;\nsetp.ne.s32 p, %1, 0;\n@p add.u32 %0, %0, 1;\n}" : "+r"(n) : "r"(x));
+}
+
+template <int STAGES, bool WantMin, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) atom_pass_kernel(const PassArgs args) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    double2* s_uv = reinterpret_cast<double2*>(s_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    unsigned char* my = s_raw + ((kUvEntries * sizeof(double2) + 15) & ~(size_t)15) + (size_t)warp * STAGES * kPassStageBytes;
+    auto st_buf = [&](int s) { return reinterpret_cast<int32_t*>(my + (size_t)s * kPassStageBytes); };
+    auto st_ent = [&](int s) { return reinterpret_cast<uint64_t*>(my + (size_t)s * kPassStageBytes + kPassBufSlots * 4); };
+    auto st_desc = [&](int s) { return reinterpret_cast<uint4*>(my + (size_t)s * kPassStageBytes + kPassBufSlots * 4 + kPassEntSlots * 8); };
+    auto st_bar = [&](int s) { return reinterpret_cast<uint64_t*>(my + (size_t)s * kPassStageBytes + kPassBufSlots * 4 + kPassEntSlots * 8 + 16); };
+    fill_uv_table(s_uv);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(st_bar(s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const unsigned G = gridDim.x * (unsigned)n_warps, g = blockIdx.x * (unsigned)n_warps + (unsigned)warp;
+    const unsigned n_mine = g < args.n_passes ? (args.n_passes - g + G - 1) / G : 0u;     // passes g, g + G, ...
+    // lane 0: bring pass number `it` of this warp into stage it % STAGES
+    auto issue = [&](unsigned it, const uint4 d) {
+        const int s = (int)(it % STAGES);
+        const unsigned cov_bytes = (d.y >> 8) * 16u;
+        const unsigned e0 = d.x & ~1u;
+        const unsigned ent_bytes = ((d.x + (d.y & 255u) + 1u) & ~1u) * 8u - e0 * 8u;
+        *st_desc(s) = d;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(st_bar(s), cov_bytes + ent_bytes);
+        tma_load_1d(st_buf(s), args.cov + ((size_t)d.z << 2), cov_bytes, st_bar(s));
+        tma_load_1d(st_ent(s), args.atoms + e0, ent_bytes, st_bar(s));
+    };
+    auto load_desc = [&](unsigned it) -> uint4 {
+        return it < n_mine ? __ldg(reinterpret_cast<const uint4*>(args.passes) + (size_t)g + (size_t)it * G) : make_uint4(0, 0, 0, 0);
+    };
+    uint4 d_next = make_uint4(0, 0, 0, 0);      // lane 0: descriptor of the next pass to issue
+    if (lane == 0) {
+        for (unsigned it = 0; it + 1 < (unsigned)STAGES && it < n_mine; ++it) issue(it, load_desc(it));
+        d_next = load_desc(STAGES - 1);
+    }
+
+    for (unsigned it = 0; it < n_mine; ++it) {
+        const int s = (int)(it % STAGES);
+        if (lane == 0) {       // the stage of pass it - 1 is free (the __syncwarp below): refill it with pass it + STAGES - 1
+            const unsigned nx = it + STAGES - 1;
+            if (nx < n_mine) issue(nx, d_next);
+            d_next = load_desc(nx + 1);
+        }
+        __syncwarp();
+        mbar_wait(st_bar(s), (it / STAGES) & 1u);
+        const int32_t* buf = st_buf(s);
+        const uint4 d = *st_desc(s);
+        const int n_atoms = (int)(d.y & 255u);
+        const uint64_t a0 = (uint64_t)d.z << 2;                                        // slot of buf[0]
+
+        // ---- pieces -> lanes ----
+        uint64_t ent = 0;
+        int np = 0;
+        if (lane < n_atoms) {
+            ent = st_ent(s)[(d.x & 1u) + lane];
+            np = ((int)(ent & kLenMask) + kPieceNt - 1) / kPieceNt;
+        }
+        int incl = np;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int excl = incl - np;
+        const unsigned heads = __reduce_or_sync(kFull, np > 0 ? 1u << excl : 0u);     // bit = first lane of an atom
+        const int total = __shfl_sync(kFull, incl, 31);
+        const int max_np = (int)__reduce_max_sync(kFull, (unsigned)np);
+        const bool active = lane < total;
+        const int k = __popc(heads & (0xffffffffu >> (31 - lane))) - 1;               // my atom (lane index of its descriptor)
+        const uint64_t entk = __shfl_sync(kFull, ent, k);
+        const int first_lane = __shfl_sync(kFull, excl, k);
+        const int end_lane = __shfl_sync(kFull, incl, k);                              // pieces of my atom: [first_lane, end_lane)
+        const int len = (int)(entk & kLenMask);
+        const int off = (lane - first_lane) * kPieceNt;
+        const int rem = active ? len - off : 0;                                        // values from my first one to the atom's end
+        const int abase = (int)((entk >> kLenBits) - a0);                              // atom's first value in buf
+        const int base = active ? abase + off : 0;
+        const int32_t* mine = buf + base;
+
+        unsigned cnt = 0;
+        int orm = 0, e0v = 0, e1v = 0;
+        double re0 = 0.0, im0 = 0.0, re1 = 0.0, im1 = 0.0, re2 = 0.0, im2 = 0.0;
+        unsigned K0 = 0, K1 = 0, K2 = 0, M0 = 0, M1 = 0, M2 = 0;
+        unsigned mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu;
+        const char* center = reinterpret_cast<const char*>(s_uv + kUvCenter);
+        int h0 = mine[0], h1 = mine[1];                                                // the two values a group inherits
+        if (rem < 2) { if (rem < 1) h0 = 0; h1 = 0; }
+        e0v = h0;
+        e1v = h1;
+#pragma unroll
+        for (int gq = 0; gq < 3; ++gq) {
+            // values gq * 11 .. gq * 11 + 12 of the piece; what lies beyond the atom's end reads as zero
+            int v[kGroupNt + 2];
+            v[0] = h0;
+            v[1] = h1;
+#pragma unroll
+            for (int t = 2; t < kGroupNt + 2; ++t) v[t] = mine[gq * kGroupNt + t];
+            const int left = rem - gq * kGroupNt;                                      // values from v[0] to the atom's end
+            if (left < kGroupNt + 2) {
+#pragma unroll
+                for (int t = 2; t < kGroupNt + 2; ++t)
+                    if (t >= left) v[t] = 0;
+            }
+            h0 = v[kGroupNt];
+            h1 = v[kGroupNt + 1];
+            int og = 0;
+#pragma unroll
+            for (int t = 0; t < kGroupNt; ++t) {
+                cnt += (unsigned)v[t];
+                og |= v[t];
+            }
+            orm |= og;
+            if ((unsigned)(og | h0 | h1) < (unsigned)kUvMax) {
+#pragma unroll
+                for (int q = 0; q < kGroupNt; ++q) {
+                    const int a = v[q], b = v[q + 1], c = v[q + 2];
+                    const int i16 = (a * kUvStride + b - c * (kUvStride + 1)) * 16;
+                    const double2 u = *reinterpret_cast<const double2*>(center + i16);
+                    constexpr int kF0 = 0;
+                    const int f = (gq * kGroupNt + q) % 3 + kF0;
+                    if (f == 0) { re0 += u.x; im0 += u.y; count_nonzero(K0, a | b | c); count_nonzero(M0, i16); }
+                    else if (f == 1) { re1 += u.x; im1 += u.y; count_nonzero(K1, a | b | c); count_nonzero(M1, i16); }
+                    else { re2 += u.x; im2 += u.y; count_nonzero(K2, a | b | c); count_nonzero(M2, i16); }
+                    if (WantMin) {
+                        const unsigned sum = q + 2 < left ? (unsigned)a + (unsigned)b + (unsigned)c : 0xffffffffu;
+                        if (f == 0) mn0 = min(mn0, sum);
+                        else if (f == 1) mn1 = min(mn1, sum);
+                        else mn2 = min(mn2, sum);
+                    }
+                }
+            } else {
+                // a count outside the table: the same windows through uv_grid (same values as the table holds)
+#pragma unroll 1
+                for (int q = 0; q < kGroupNt; ++q) {
+                    const int p = gq * kGroupNt + q;
+                    const int a = p < rem ? mine[p] : 0, b = p + 1 < rem ? mine[p + 1] : 0, c = p + 2 < rem ? mine[p + 2] : 0;
+                    const unsigned kq = (a | b | c) != 0 ? 1u : 0u;
+                    const int A = 2 * a - b - c, B = b - c;
+                    const unsigned mq = (A | B) != 0 ? 1u : 0u;
+                    double2 u = make_double2(0.0, 0.0);
+                    if (mq) u = uv_grid((double)A, (double)B);
+                    const unsigned sum = p + 2 < rem ? (unsigned)a + (unsigned)b + (unsigned)c : 0xffffffffu;
+                    const int f = p % 3;
+                    if (f == 0) { re0 += u.x; im0 += u.y; K0 += kq; M0 += mq; if (WantMin) mn0 = min(mn0, sum); }
+                    else if (f == 1) { re1 += u.x; im1 += u.y; K1 += kq; M1 += mq; if (WantMin) mn1 = min(mn1, sum); }
+                    else { re2 += u.x; im2 += u.y; K2 += kq; M2 += mq; if (WantMin) mn2 = min(mn2, sum); }
+                }
+            }
+        }
+
+        // ---- add up the pieces of every atom (consecutive lanes) ----
+        unsigned Kp = K0 | (K1 << 10) | (K2 << 20), Mp = M0 | (M1 << 10) | (M2 << 20);
+        for (int o = 1; o < max_np; o <<= 1) {
+            const bool take = lane + o < end_lane;
+            const double t0 = __shfl_down_sync(kFull, re0, o), t1 = __shfl_down_sync(kFull, im0, o);
+            const double t2 = __shfl_down_sync(kFull, re1, o), t3 = __shfl_down_sync(kFull, im1, o);
+            const double t4 = __shfl_down_sync(kFull, re2, o), t5 = __shfl_down_sync(kFull, im2, o);
+            const unsigned tk = __shfl_down_sync(kFull, Kp, o), tm = __shfl_down_sync(kFull, Mp, o);
+            const unsigned tc = __shfl_down_sync(kFull, cnt, o);
+            const int to = __shfl_down_sync(kFull, orm, o);
+            if (take) {
+                re0 += t0; im0 += t1; re1 += t2; im1 += t3; re2 += t4; im2 += t5;
+                Kp += tk; Mp += tm; cnt += tc; orm |= to;
+            }
+            if (WantMin) {
+                const unsigned u0 = __shfl_down_sync(kFull, mn0, o), u1 = __shfl_down_sync(kFull, mn1, o);
+                const unsigned u2 = __shfl_down_sync(kFull, mn2, o);
+                if (take) { mn0 = min(mn0, u0); mn1 = min(mn1, u1); mn2 = min(mn2, u2); }
+            }
+        }
+
+        // ---- head lane: take the two windows that run over the atom's end out again, write the summary ----
+        if (active && lane == first_lane) {
+            const unsigned atom = d.x + (unsigned)k;
+            args.nonzero[atom] = orm != 0;
+            if (orm != 0) {
+                const int z1 = buf[abase + len - 1];                       // last value
+                const int z0 = len >= 2 ? buf[abase + len - 2] : 0;        // the one before it
+                if (z1 != 0) {                                             // window (z1, 0, 0) at len - 1: u = (1, 0)
+                    const int f = (len - 1) % 3;
+                    if (f == 0) re0 -= 1.0; else if (f == 1) re1 -= 1.0; else re2 -= 1.0;
+                    Kp -= 1u << (10 * f);
+                    Mp -= 1u << (10 * f);
+                }
+                if (len >= 2 && (z0 | z1) != 0) {                          // window (z0, z1, 0) at len - 2
+                    const int f = (len - 2) % 3;
+                    double2 u;
+                    if ((unsigned)(z0 | z1) < (unsigned)kUvMax) u = s_uv[kUvCenter + z0 * kUvStride + z1];
+                    else u = uv_grid((double)(2 * z0 - z1), (double)z1);
+                    if (f == 0) { re0 -= u.x; im0 -= u.y; } else if (f == 1) { re1 -= u.x; im1 -= u.y; } else { re2 -= u.x; im2 -= u.y; }
+                    Kp -= 1u << (10 * f);
+                    Mp -= 1u << (10 * f);
+                }
+                AtomSummary sm;
+                sm.re[0] = __double2ll_rn(re0 * kUvGridScale); sm.re[1] = __double2ll_rn(re1 * kUvGridScale);
+                sm.re[2] = __double2ll_rn(re2 * kUvGridScale);
+                sm.im[0] = __double2ll_rn(im0 * kUvGridScale); sm.im[1] = __double2ll_rn(im1 * kUvGridScale);
+                sm.im[2] = __double2ll_rn(im2 * kUvGridScale);
+                sm.edge[0] = e0v;
+                sm.edge[1] = e1v;                                          // zero when len == 1
+                sm.edge[2] = z0;
+                sm.edge[3] = z1;
+                sm.kpack = Kp | ((orm >> kBigShift) != 0 ? 0x80000000u : 0u);
+                sm.upack = Kp - Mp;                                        // field-wise: every M field <= its K field
+                sm.count = cnt;
+                sm.spare0 = sm.spare1 = 0;
+                sm.mn[0] = mn0; sm.mn[1] = mn1; sm.mn[2] = mn2;
+                args.out[atom] = sm;
             }
         }
         __syncwarp();
@@ -1136,7 +1434,7 @@ constexpr int kSegRefs = 48;           // refs per segment of a long ORF
 // Per-frame sums of one ORF (or of one segment of a long ORF) in PROFILE frames.
 struct ComposeAcc {
     unsigned K[3], U[3];
-    double RE[3], IM[3];
+    long long RE[3], IM[3];            // sums of unit vectors in units of 2^-42 (uv_grid): exact
     unsigned mn;
     int big;
     long long count;
@@ -1155,8 +1453,9 @@ struct RefSegment {
 };
 
 // statistics.py:92-115 + detect_orfs.py:278-299 on the finished sums of one ORF.
-__device__ __forceinline__ void finish_orf(const ComposeArgs& args, int orf, int L, const unsigned* K, const unsigned* U,
-                                           const double* RE, const double* IM, unsigned mn, long long count) {
+template <typename Args>
+__device__ __forceinline__ void finish_orf(const Args& args, int orf, int L, const unsigned* K, const unsigned* U,
+                                           const long long* RE, const long long* IM, unsigned mn, long long count) {
     const double kSqrt3 = 1.7320508075688772;
     const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
     const int n_codons = L / 3 > 1 ? L / 3 : 1;                          // detect_orfs.py:281
@@ -1166,8 +1465,9 @@ __device__ __forceinline__ void finish_orf(const ComposeArgs& args, int orf, int
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
         if (K[f] == 0) { s3[f] = kNaN; coh = 0.0; valid = 0; continue; }   // statistics.py:94-95
-        const double im = kSqrt3 * IM[f];
-        const double s = (RE[f] * RE[f] + im * im) / ((double)K[f] * (double)(K[f] - U[f]));   // 0/0 -> NaN never wins
+        const double re = (double)RE[f] * (1.0 / kUvGridScale);               // the sums are exact integers (units of 2^-42)
+        const double im = kSqrt3 * ((double)IM[f] * (1.0 / kUvGridScale));
+        const double s = (re * re + im * im) / ((double)K[f] * (double)(K[f] - U[f]));   // 0/0 -> NaN never wins
         s3[f] = s;
         if (s > coh) { coh = s; valid = (int)K[f]; }                     // statistics.py:109-111
         if (valid == -1) valid = (int)K[f];                              // statistics.py:112-113
@@ -1219,11 +1519,12 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
     const int L = __ldg(args.orf_len + orf);
 
     unsigned K[3] = {0, 0, 0}, U[3] = {0, 0, 0};
-    double RE[3] = {0.0, 0.0, 0.0}, IM[3] = {0.0, 0.0, 0.0};
+    long long RE[3] = {0, 0, 0}, IM[3] = {0, 0, 0};          // units of 2^-42: integer sums, no rounding, any order
     unsigned mn = 0xffffffffu;
     long long count = 0;
     int ormask = 0;
     bool big = false;
+    constexpr long long kOne = 1ll << 42, kHalf = 1ll << 41;
 
     // one seam window of the profile starting at position p = (values v0,v1,v2): statistics.py:72-90
     auto window = [&](int p, int v0, int v1, int v2) {
@@ -1233,16 +1534,15 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
         if ((v0 | v1 | v2) == 0) return;
         // '+'-oriented triple (a,b,c): the profile of a '-' ORF runs against the plane
         const int a = rev ? v2 : v0, b = v1, c = rev ? v0 : v2;
-        double re, im;
-        if ((b | c) == 0) { re = 1.0; im = 0.0; }
-        else if ((a | c) == 0) { re = -0.5; im = 0.5; }
-        else if ((a | b) == 0) { re = -0.5; im = -0.5; }
-        else if (a == b && b == c) { re = 0.0; im = 0.0; }
+        long long re, im;
+        if ((b | c) == 0) { re = kOne; im = 0; }
+        else if ((a | c) == 0) { re = -kHalf; im = kHalf; }
+        else if ((a | b) == 0) { re = -kHalf; im = -kHalf; }
+        else if (a == b && b == c) { re = 0; im = 0; }
         else {
-            const double dA = (double)(2ll * a - b - c), dB = (double)((long long)b - c);
-            const double r = rsqrt(fma(dA, dA, 3.0 * dB * dB));
-            re = dA * r;
-            im = dB * r;
+            const double2 u = uv_grid((double)(2ll * a - b - c), (double)((long long)b - c));
+            re = __double2ll_rn(u.x * kUvGridScale);
+            im = __double2ll_rn(u.y * kUvGridScale);
         }
         const bool uniform = a == b && b == c;
 #pragma unroll
@@ -1290,14 +1590,14 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
         }
         int a0 = 0, a1 = 0, z0 = 0, z1 = 0;    // first two / last two values of the ref in profile order
         if (!zero) {
-            const double2 r01 = __ldg(reinterpret_cast<const double2*>(s));          // re[0], re[1]
-            const double2 r2i0 = __ldg(reinterpret_cast<const double2*>(s) + 1);     // re[2], im[0]
-            const double2 i12 = __ldg(reinterpret_cast<const double2*>(s) + 2);      // im[1], im[2]
+            const longlong2 r01 = __ldg(reinterpret_cast<const longlong2*>(s));          // re[0], re[1]
+            const longlong2 r2i0 = __ldg(reinterpret_cast<const longlong2*>(s) + 1);     // re[2], im[0]
+            const longlong2 i12 = __ldg(reinterpret_cast<const longlong2*>(s) + 2);      // im[1], im[2]
             const int4 edge = __ldg(reinterpret_cast<const int4*>(s) + 3);
             const uint4 ku = __ldg(reinterpret_cast<const uint4*>(s) + 4);           // kpack, upack, count
             uint4 mc = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
             if (args.want_min) mc = __ldg(reinterpret_cast<const uint4*>(s) + 5);    // mn[0..2]
-            const double sre[3] = {r01.x, r01.y, r2i0.x}, sim[3] = {r2i0.y, i12.x, i12.y};
+            const long long sre[3] = {r01.x, r01.y, r2i0.x}, sim[3] = {r2i0.y, i12.x, i12.y};
             const unsigned smn[3] = {mc.x, mc.y, mc.z};
             const unsigned sK[3] = {ku.x & 1023u, (ku.x >> 10) & 1023u, (ku.x >> 20) & 1023u};
             const unsigned sU[3] = {ku.y & 1023u, (ku.y >> 10) & 1023u, (ku.y >> 20) & 1023u};
@@ -1351,7 +1651,7 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
         __threadfence();
         args.seg_done[seg.long_idx] = 0;                    // ready for the next launch
 #pragma unroll
-        for (int f = 0; f < 3; ++f) { K[f] = 0; U[f] = 0; RE[f] = 0.0; IM[f] = 0.0; }
+        for (int f = 0; f < 3; ++f) { K[f] = 0; U[f] = 0; RE[f] = 0; IM[f] = 0; }
         mn = 0xffffffffu;
         count = 0;
         big = false;
@@ -1363,6 +1663,224 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
             big |= pa->big != 0;
             count += pa->count;
         }
+    }
+    if (big) {
+        args.fallback[atomicAdd(args.n_fallback, 1u)] = orf;
+        return;
+    }
+    finish_orf(args, orf, L, K, U, RE, IM, mn, count);
+}
+
+// ---- phase B, one lane per atom reference: compose_refs_kernel ---------------------------------------
+// The host lays the atom references of the requested ORFs out in index order, 16 bytes each, with the profile
+// offset of every reference precomputed, and pads so that an ORF of up to 32 references never straddles a group of
+// 32 slots.  A warp takes one group: every lane loads its reference and the summary of its atom (coalesced /
+// independent loads, no serial walk), turns the summary into sums by PROFILE frame, rebuilds the two windows that
+// straddle the seam with the reference before it from the edge values of the neighbouring lanes, and the lanes of
+// an ORF are added up by a segmented shuffle reduction -- the sums are 64-bit integers (uv_grid), so the order of
+// summation is immaterial.  ORFs with more than 32 references fill whole groups; each group adds its sums to the
+// ORF's accumulator with integer atomics and the group that arrives last scores the ORF.
+struct RefRec {                        // 16 bytes
+    uint32_t atom;                     // atom id; 0xffffffff: a stretch that reads as zeros
+    uint32_t len_rev;                  // values of the reference | (ORF on the '-' strand) << 31
+    uint32_t P;                        // profile offset of the reference's first value
+    int32_t orf;                       // absolute ORF id; -1: padding
+};
+struct RefWarp {                       // per group of 32 slots
+    int32_t long_idx;                  // >= 0: the group belongs to long ORF number long_idx (more than 32 references)
+    int32_t n_groups;                  //        ... which spans this many groups
+};
+struct LongAcc {                       // accumulator of one long ORF; all-zero except mn = 0xffffffff between launches
+    unsigned long long RE[3], IM[3];
+    unsigned long long count;
+    unsigned K[3], U[3];
+    unsigned mn, big, done, pad;
+};
+static_assert(sizeof(LongAcc) == 96, "LongAcc layout");
+struct RefComposeArgs {
+    const RefRec* refs;
+    const RefWarp* warps;
+    long long n_warps;
+    const AtomSummary* summaries;
+    const uint8_t* atom_nonzero;
+    int want_min;
+    const int32_t* orf_len;
+    long long orf_lo;
+    int32_t* fallback;
+    unsigned* n_fallback;
+    LongAcc* long_acc;
+    rt_score_params prm;
+    rt_score_out out;
+};
+constexpr int kMaxExactCodons = 1 << 20;      // per frame: the 21-bit packed K / U fields of the reduction
+
+__global__ void __launch_bounds__(256) compose_refs_kernel(const RefComposeArgs args) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= args.n_warps) return;
+    const int lane = threadIdx.x & 31;
+    const long long slot = w * 32 + lane;
+    const uint4 rr = __ldg(reinterpret_cast<const uint4*>(args.refs) + slot);
+    const RefWarp rw = args.warps[w];
+    const int orf = (int)rr.w;
+    const bool valid = orf >= 0;
+    const unsigned atom = rr.x;
+    const int len = (int)(rr.y & 0x7fffffffu);
+    const bool rev = (rr.y >> 31) != 0;
+    const int P = (int)rr.z;
+    const bool nz = valid && atom != 0xffffffffu && __ldg(args.atom_nonzero + atom) != 0;
+    const int L = valid ? __ldg(args.orf_len + orf) : 0;
+    constexpr long long kOne = 1ll << 42, kHalf = 1ll << 41;
+
+    unsigned K[3] = {0, 0, 0}, U[3] = {0, 0, 0};
+    long long RE[3] = {0, 0, 0}, IM[3] = {0, 0, 0};
+    unsigned mn = 0xffffffffu;
+    long long count = 0;
+    int ormask = 0;
+    bool big = false;
+    int a0 = 0, a1 = 0, z0 = 0, z1 = 0;         // first two / last two values of the reference in profile order
+    if (nz) {
+        const AtomSummary* s = args.summaries + atom;
+        const longlong2 r01 = __ldg(reinterpret_cast<const longlong2*>(s));          // re[0], re[1]
+        const longlong2 r2i0 = __ldg(reinterpret_cast<const longlong2*>(s) + 1);     // re[2], im[0]
+        const longlong2 i12 = __ldg(reinterpret_cast<const longlong2*>(s) + 2);      // im[1], im[2]
+        const int4 edge = __ldg(reinterpret_cast<const int4*>(s) + 3);
+        const uint4 ku = __ldg(reinterpret_cast<const uint4*>(s) + 4);               // kpack, upack, count
+        uint4 mc = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
+        if (args.want_min) mc = __ldg(reinterpret_cast<const uint4*>(s) + 5);        // mn[0..2]
+        const long long sre[3] = {r01.x, r01.y, r2i0.x}, sim[3] = {r2i0.y, i12.x, i12.y};
+        const unsigned smn[3] = {mc.x, mc.y, mc.z};
+        const unsigned sK[3] = {ku.x & 1023u, (ku.x >> 10) & 1023u, (ku.x >> 20) & 1023u};
+        const unsigned sU[3] = {ku.y & 1023u, (ku.y >> 10) & 1023u, (ku.y >> 20) & 1023u};
+        big = (ku.x >> 31) != 0;
+        count = ku.z;
+        if (rev) { a0 = edge.w; a1 = edge.z; z0 = edge.y; z1 = edge.x; }
+        else { a0 = edge.x; a1 = edge.y; z0 = edge.z; z1 = edge.w; }
+        // local frame fl (window start offset inside the atom, mod 3) -> profile frame f:
+        //   '+': f = (fl + P) mod 3          '-': f = (len + P - fl) mod 3
+        const int base = rev ? (len + P) % 3 : P % 3;
+#pragma unroll
+        for (int fl = 0; fl < 3; ++fl) {
+            const int f = rev ? (base - fl + 3) % 3 : (base + fl) % 3;
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (q == f) { K[q] += sK[fl]; U[q] += sU[fl]; RE[q] += sre[fl]; IM[q] += sim[fl]; }
+            if (f == 0) mn = min(mn, smn[fl]);
+        }
+    } else if (valid && len >= 3 && (3 - P % 3) % 3 <= len - 3) {
+        mn = 0;     // a stretch without a read that holds a whole frame-0 codon
+    }
+
+    // ---- the last two profile values before this reference: from the lanes to the left ----
+    int p_z0 = __shfl_up_sync(kFull, z0, 1), p_z1 = __shfl_up_sync(kFull, z1, 1), p_len = __shfl_up_sync(kFull, len, 1);
+    int pp_z1 = __shfl_up_sync(kFull, z1, 2);
+    if (valid && P > 0 && lane < 2) {
+        // only in the groups of a long ORF: the references before this one sit in the group to the left
+        auto fetch_tail = [&](long long sl, int& tz0, int& tz1, int& tlen) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(args.refs) + sl);
+            tlen = (int)(q.y & 0x7fffffffu);
+            tz0 = tz1 = 0;
+            if (q.x != 0xffffffffu && __ldg(args.atom_nonzero + q.x) != 0) {
+                const int4 e = __ldg(reinterpret_cast<const int4*>(args.summaries + q.x) + 3);
+                if ((q.y >> 31) != 0) { tz0 = e.y; tz1 = e.x; } else { tz0 = e.z; tz1 = e.w; }
+            }
+        };
+        int d0, d1, dl;
+        if (lane == 0) {
+            fetch_tail(slot - 1, p_z0, p_z1, p_len);
+            if (p_len < 2 && P >= 2) { fetch_tail(slot - 2, d0, pp_z1, dl); }
+        } else if (p_len < 2 && P >= 2) {
+            fetch_tail(slot - 2, d0, pp_z1, dl);
+        }
+    }
+    // one seam window of the profile starting at position p = (values v0,v1,v2): statistics.py:72-90
+    auto window = [&](int p, int v0, int v1, int v2) {
+        const int f = p % 3;
+        ormask |= v0 | v1 | v2;
+        if (f == 0) mn = min(mn, (unsigned)v0 + (unsigned)v1 + (unsigned)v2);
+        if ((v0 | v1 | v2) == 0) return;
+        // '+'-oriented triple (a,b,c): the profile of a '-' ORF runs against the plane
+        const int a = rev ? v2 : v0, b = v1, c = rev ? v0 : v2;
+        long long re, im;
+        if ((b | c) == 0) { re = kOne; im = 0; }
+        else if ((a | c) == 0) { re = -kHalf; im = kHalf; }
+        else if ((a | b) == 0) { re = -kHalf; im = -kHalf; }
+        else if (a == b && b == c) { re = 0; im = 0; }
+        else {
+            const double2 u = uv_grid((double)(2ll * a - b - c), (double)((long long)b - c));
+            re = __double2ll_rn(u.x * kUvGridScale);
+            im = __double2ll_rn(u.y * kUvGridScale);
+        }
+        const bool uniform = a == b && b == c;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (q == f) { K[q] += 1u; U[q] += uniform ? 1u : 0u; RE[q] += re; IM[q] += im; }
+    };
+    if (valid) {
+        const int y = p_z1, x = p_len >= 2 ? p_z0 : pp_z1;
+        if (P >= 2) window(P - 2, x, y, a0);                 // the window that ENDS on the first value of this reference
+        if (len >= 2 && P >= 1) window(P - 1, y, a0, a1);    // ... and on its second value
+        if (P + len == L) {
+            // last reference: trailing partial codon (common.py:177-179); the last L % 3 values are (tx,) ty
+            const int ty = len >= 1 ? z1 : p_z1, tx = len >= 2 ? z0 : (len == 1 ? (P >= 1 ? p_z1 : 0) : (p_len >= 2 ? p_z0 : pp_z1));
+            if (L % 3 == 1) { mn = min(mn, (unsigned)ty); ormask |= ty; }
+            else if (L % 3 == 2) { mn = min(mn, (unsigned)tx + (unsigned)ty); ormask |= tx | ty; }
+        }
+    }
+    big |= (ormask >> kBigShift) != 0;
+    if (valid && L > 3 * kMaxExactCodons) big = true;
+
+    // ---- add up the lanes of every ORF (consecutive lanes) ----
+    const int left_orf = __shfl_up_sync(kFull, orf, 1);
+    const unsigned heads = __ballot_sync(kFull, lane == 0 || orf != left_orf);
+    const unsigned after = lane == 31 ? 0u : heads >> (lane + 1);
+    const int end_lane = after ? lane + __ffs(after) : 32;              // lanes [.., end_lane) share my ORF
+    const bool head = ((heads >> lane) & 1u) != 0;
+    const int max_run = (int)__reduce_max_sync(kFull, head ? (unsigned)(end_lane - lane) : 0u);
+    unsigned long long Kp = (unsigned long long)K[0] | ((unsigned long long)K[1] << 21) | ((unsigned long long)K[2] << 42);
+    unsigned long long Up = (unsigned long long)U[0] | ((unsigned long long)U[1] << 21) | ((unsigned long long)U[2] << 42);
+    unsigned flags = big ? 1u : 0u;
+    for (int o = 1; o < max_run; o <<= 1) {
+        const bool take = lane + o < end_lane;
+        const long long t0 = __shfl_down_sync(kFull, RE[0], o), t1 = __shfl_down_sync(kFull, RE[1], o);
+        const long long t2 = __shfl_down_sync(kFull, RE[2], o), t3 = __shfl_down_sync(kFull, IM[0], o);
+        const long long t4 = __shfl_down_sync(kFull, IM[1], o), t5 = __shfl_down_sync(kFull, IM[2], o);
+        const unsigned long long tk = __shfl_down_sync(kFull, Kp, o), tu = __shfl_down_sync(kFull, Up, o);
+        const long long tc = __shfl_down_sync(kFull, count, o);
+        const unsigned tm = __shfl_down_sync(kFull, mn, o), tf = __shfl_down_sync(kFull, flags, o);
+        if (take) {
+            RE[0] += t0; RE[1] += t1; RE[2] += t2; IM[0] += t3; IM[1] += t4; IM[2] += t5;
+            Kp += tk; Up += tu; count += tc; mn = min(mn, tm); flags |= tf;
+        }
+    }
+    if (!head || !valid) return;
+    const unsigned kMask = (1u << 21) - 1u;
+    K[0] = (unsigned)Kp & kMask; K[1] = (unsigned)(Kp >> 21) & kMask; K[2] = (unsigned)(Kp >> 42) & kMask;
+    U[0] = (unsigned)Up & kMask; U[1] = (unsigned)(Up >> 21) & kMask; U[2] = (unsigned)(Up >> 42) & kMask;
+    big = flags != 0;
+    if (rw.long_idx >= 0) {
+        // one group of a long ORF: integer atomics into the ORF's accumulator; the last group to arrive scores it
+        LongAcc* acc = args.long_acc + rw.long_idx;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            atomicAdd(&acc->RE[f], (unsigned long long)RE[f]);
+            atomicAdd(&acc->IM[f], (unsigned long long)IM[f]);
+            atomicAdd(&acc->K[f], K[f]);
+            atomicAdd(&acc->U[f], U[f]);
+        }
+        atomicAdd(&acc->count, (unsigned long long)count);
+        atomicMin(&acc->mn, mn);
+        if (big) atomicOr(&acc->big, 1u);
+        __threadfence();
+        if (atomicAdd(&acc->done, 1u) != (unsigned)(rw.n_groups - 1)) return;
+        __threadfence();
+        volatile LongAcc* va = acc;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            RE[f] = (long long)va->RE[f]; IM[f] = (long long)va->IM[f]; K[f] = va->K[f]; U[f] = va->U[f];
+            va->RE[f] = 0; va->IM[f] = 0; va->K[f] = 0; va->U[f] = 0;
+        }
+        count = (long long)va->count; mn = va->mn; big = va->big != 0;
+        va->count = 0; va->mn = 0xffffffffu; va->big = 0; va->done = 0;      // ready for the next launch
     }
     if (big) {
         args.fallback[atomicAdd(args.n_fallback, 1u)] = orf;
@@ -1638,7 +2156,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
                         cat = RT_ST_BADREF;                         // chrom is None, bam.py:133
                     } else {
                         len = l;                                    // bam.py:136
-                        if (mode >= 0) {                            // detect_orfs.py:74
+                        if (mode != RT_LEN_UNUSED) {                // detect_orfs.py:74 (the offset may be negative)
                             const int2 ct = __ldg(a.contig_tab + c);
                             // 1-based P-site p = pos + 1 +- offset (bam.py:135, detect_orfs.py:78-81);
                             // q = p + pad - 1 is its 0-based place in the padded contig

@@ -20,43 +20,56 @@ from .const import CUTOFF, TYPICAL_OFFSET
 
 # ------------------------------------------------------------------ infer_protocol.py:34-124
 def infer_protocol(reads, refseq: dict, prefix: str, n_reads: int = 20000) -> str:
-    """'forward' or 'reverse' from the first ``n_reads`` uniquely mapped reads that overlap
-    exactly one annotated ORF span (infer_protocol.py:75-105); writes ``{prefix}_protocol.txt``.
+    """'forward' or 'reverse' from the first ``n_reads`` (+1, infer_protocol.py:79) uniquely mapped reads that
+    overlap exactly one annotated ORF span (infer_protocol.py:75-105); writes ``{prefix}_protocol.txt``.
 
-    The reference looks overlaps up in a quicksect tree (absent here); a span (start, end,
-    strand) overlaps a read when start <= read_end and end >= read_start.
+    The reference looks overlaps up in a quicksect tree, whose ``find`` is inclusive on both ends: a span
+    (start, end, strand) is returned for the query (reference_start, reference_end) when start <= reference_end and
+    end >= reference_start.  ``reads.cols`` may carry the host-only columns "pos" / "ref_end" (both BAM decoders
+    fill them); without them (synthetic columns) reference_start / reference_end are first / last + 1, which is
+    what they are for every CIGAR that neither starts nor ends in a deletion or skip.
     """
     cols = reads.cols
     by_contig = {}
     for chrom, spans in refseq.items():
         arr = np.array(spans, dtype=np.int64).reshape(-1, 3)
-        by_contig[chrom] = arr[np.argsort(arr[:, 0])]
+        by_contig[chrom] = arr[np.argsort(arr[:, 0], kind="stable")]
     names = reads.contig_names
     counts = {"++": 0, "--": 0, "+-": 0, "-+": 0}
+    n = len(cols["ref_id"])
+    flag_all, mapq_all, nh_all, ref_all = cols["flag"], cols["mapq"], cols["nh"], cols["ref_id"]
+    if "pos" in cols and "ref_end" in cols:
+        start_all, end_all = cols["pos"], cols["ref_end"]
+    else:
+        start_all = cols["first"]
+        end_all = np.where(flag_all & 0x4, -1, cols["last"].astype(np.int64) + 1)
     iteration = 0
-    flag, mapq, nh = cols["flag"], cols["mapq"], cols["nh"]
-    for i in range(len(cols["ref_id"])):
+    chunk = 1 << 16
+    for lo in range(0, n, chunk):
         if iteration > n_reads:           # infer_protocol.py:79
             break
-        fl = int(flag[i])
-        # is_read_uniq_mapping is used bare here (infer_protocol.py:80): truthy only for True
-        if fl & 0x100:
-            continue
-        uniq = (nh[i] == 1) if nh[i] != 0 else (mapq[i] == 255)
-        if not uniq:
-            continue
-        c = int(cols["ref_id"][i])
-        if c < 0:
-            continue
-        spans = by_contig.get(names[c])
-        if spans is None:
-            continue
-        start, end = int(cols["first"][i]), int(cols["last"][i]) + 1   # reference_start / reference_end
-        hit = spans[(spans[:, 0] <= end) & (spans[:, 1] >= start)]
-        if len(hit) == 1:                 # infer_protocol.py:98-105
-            gene = "+" if hit[0, 2] == 1 else "-"
-            counts[("-" if fl & 0x10 else "+") + gene] += 1
-            iteration += 1
+        hi = min(n, lo + chunk)
+        fl = flag_all[lo:hi].astype(np.int64)
+        nh = nh_all[lo:hi]
+        # is_read_uniq_mapping is used bare here (infer_protocol.py:80): truthy only for True, i.e. not secondary
+        # and (NH == 1, or no NH tag and MAPQ 255); None (no tag, other MAPQ) is falsy
+        uniq = ((fl & 0x100) == 0) & np.where(nh != 0, nh == 1, mapq_all[lo:hi] == 255)
+        ref = ref_all[lo:hi]
+        ok = uniq & (ref >= 0) & (ref < len(names)) & (end_all[lo:hi] >= 0)     # chrom / mapped_end not None (:87)
+        for i in (lo + np.flatnonzero(ok)).tolist():
+            if iteration > n_reads:
+                break
+            spans = by_contig.get(names[int(ref_all[i])])
+            if spans is None:
+                continue
+            start, end = int(start_all[i]), int(end_all[i])
+            # spans are sorted by start: candidates end before the first span that starts after `end`
+            k = int(np.searchsorted(spans[:, 0], end, side="right"))
+            hit = spans[:k][spans[:k, 1] >= start]
+            if len(hit) == 1:                 # infer_protocol.py:98-105
+                gene = "+" if hit[0, 2] == 1 else "-"
+                counts[("-" if int(flag_all[i]) & 0x10 else "+") + gene] += 1
+                iteration += 1
     for k in counts:                      # pseudocounts, infer_protocol.py:107-110
         counts[k] += 1
     total = sum(counts.values())

@@ -176,6 +176,24 @@ def make_index(cfg: SynthConfig) -> SynthIndex:
     room = np.maximum(1, clen[tx_contig] - tx_span - 1)
     tx_start = 1 + np.floor(rng.random(n_tx_all) * room).astype(np.int64)
     tx_strand = (rng.random(n_tx_all) < 0.5).astype(np.uint8)
+    # Transcripts that overlap an annotated transcript are isoforms of that gene: they take its strand.  (Randomly
+    # placed transcripts overlap far more often than real genes do; with independent strands the reads of a highly
+    # expressed overlapping transcript make the first-20,000-reads heuristic of infer_protocol.py:75-105 a coin
+    # flip, which no real stranded library does.)
+    n_annot_tx = min(cfg.annotated_rows, n_tx_all)
+    if n_annot_tx:
+        tx_end = tx_start + tx_span - 1
+        for c in np.unique(tx_contig[:n_annot_tx]):
+            ann = np.flatnonzero(tx_contig[:n_annot_tx] == c)
+            ann = ann[np.argsort(tx_start[ann], kind="stable")]
+            a_start, a_end, a_strand = tx_start[ann], tx_end[ann], tx_strand[ann]
+            other = n_annot_tx + np.flatnonzero(tx_contig[n_annot_tx:] == c)
+            j = np.searchsorted(a_start, tx_end[other], side="right") - 1      # last annotated span starting at or before my end
+            for back in range(3):
+                jj = j - back
+                hit = (jj >= 0) & (a_end[np.maximum(jj, 0)] >= tx_start[other])
+                tx_strand[other[hit]] = a_strand[jj[hit]]
+                other, j = other[~hit], j[~hit]
     ex_start_g = tx_start[ex_tx] + ex_off_in_span
     ex_end_g = ex_start_g + ex_len - 1
     # ORFs: regular transcripts get nested ORFs (trim multiples of 3 from the 5' end)

@@ -15,6 +15,8 @@ Outputs (small, committed):
   tests/golden/split_bam_case.json.gz     split_bam (bam.py:33-153) on a real BAM (bytes included)
   tests/golden/count_orfs_cases.json.gz   count_orfs (count_orfs.py:28-89) on the pipeline cases' TSVs
   tests/golden/learn_cutoff_cases.json.gz determine_cutoff_tsv (learn_cutoff.py:35-144) stdout
+  tests/golden/infer_protocol_case.json.gz infer_protocol (infer_protocol.py:34-124) + parse_ribotricer_index
+                                          (detect_orfs.py:86-131) on a real BAM (bytes included)
 
 ``split_bam`` needs pysam, which is absent from this image: it runs UNMODIFIED on top of
 oracle/pysam_restated.py, a pure-Python restatement of the handful of pysam calls it makes
@@ -369,6 +371,122 @@ def split_bam_case(seed=1004):
     return case
 
 
+def infer_protocol_case(seed=1006):
+    """A BAM + index on which the UNMODIFIED ``parse_ribotricer_index`` (detect_orfs.py:86-131) and
+    ``infer_protocol`` (infer_protocol.py:34-124) run (pysam and quicksect restated, see oracle/ref_import.py):
+    reads whose mapping strand follows their gene under a reverse-stranded protocol plus noise, every branch of
+    is_read_uniq_mapping as infer_protocol uses it (bare truthiness), unmapped-flag reads that still carry
+    coordinates, reads without CIGAR, spliced / clipped / indel CIGARs (reference_end counts D and N), overlapping
+    annotated spans on opposite strands (len(interval) != 1), a read name-sorted after the annotated block."""
+    import base64
+    import io
+    from contextlib import redirect_stdout
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bam_writer as W
+
+    from ribotricer.detect_orfs import parse_ribotricer_index
+    from ribotricer.infer_protocol import infer_protocol
+
+    rng = np.random.default_rng(seed)
+    refs = [("chrA", 30000), ("chrB", 16000), ("chrUn_2", 900)]
+    header = ("ORF_ID\tORF_type\ttranscript_id\ttranscript_type\tgene_id\tgene_name\t"
+              "gene_type\tchrom\tstrand\tstart_codon\tcoordinate")
+    lines, genes = [], []
+    pos = {"chrA": 300, "chrB": 200}
+    for t in range(44):
+        chrom = "chrA" if t % 3 else "chrB"
+        strand = "+" if rng.random() < 0.5 else "-"
+        n_ex = int(rng.integers(1, 4))
+        start = pos[chrom]
+        ivs, at = [], start
+        for _ in range(n_ex):
+            ln = 3 * int(rng.integers(20, 70))
+            ivs.append((at, at + ln - 1))
+            at += ln + int(rng.integers(40, 160))
+        pos[chrom] = ivs[-1][1] + int(rng.integers(-150, 500))     # negative: the next span overlaps this one
+        cat = "annotated"
+        name = f"G{t}"
+        if t == 30:            # still inside the leading block ("annotated" occurs in the line) but another category
+            cat, name = "uORF", "annotated_like"
+        coord = ",".join(f"{a}-{b}" for a, b in ivs)
+        lines.append(f"id{t}\t{cat}\ttx{t}\tprotein_coding\tg{t}\t{name}\tprotein_coding\t{chrom}\t{strand}\tATG\t{coord}")
+        if cat == "annotated":
+            genes.append((chrom, ivs[0][0], ivs[-1][1], strand))
+    # rows after the leading block are never read (detect_orfs.py:104-118), even an annotated one
+    lines.append("idX\tnovel\ttxX\tlncRNA\tgX\tGX\tlncRNA\tchrA\t+\tCTG\t25000-25299")
+    lines.append("idY\tannotated\ttxY\tprotein_coding\tgY\tGY\tprotein_coding\tchrA\t-\tATG\t26000-26299")
+    cigars = [
+        lambda L: [("M", L)],
+        lambda L: [("M", L // 2), ("N", int(rng.integers(50, 300))), ("M", L - L // 2)],
+        lambda L: [("S", 2), ("M", L), ("S", 1)],
+        lambda L: [("M", 10), ("I", 2), ("M", L - 10)],
+        lambda L: [("M", 8), ("D", 3), ("M", L - 8)],
+        lambda L: [("M", L - 4), ("D", 2)],            # ends in a deletion: reference_end > last matched + 1
+        lambda L: [("N", 7), ("M", L)],                # starts in a skip: reference_start < first matched
+        lambda L: [("S", L)],                          # no reference-consuming operation: reference_end = pos + 1
+        lambda L: [],                                  # no CIGAR: reference_end is None
+    ]
+    cig_p = [0.55, 0.12, 0.08, 0.05, 0.05, 0.04, 0.04, 0.04, 0.03]
+    recs = []
+    for k in range(3200):
+        L = int(rng.integers(24, 36))
+        if rng.random() < 0.8:
+            chrom, g0, g1, gs = genes[int(rng.integers(len(genes)))]
+            ref_id = 0 if chrom == "chrA" else 1
+            p0 = int(rng.integers(max(0, g0 - 40), g1 + 10))
+            # reverse-stranded library: reads map opposite to their gene, with 15 % noise
+            minus = (gs == "+") != (rng.random() < 0.15)
+        else:
+            ref_id = int(rng.choice([0, 1, 2]))
+            p0 = int(rng.integers(0, refs[ref_id][1] - 400))
+            minus = bool(rng.random() < 0.5)
+        flag = 16 if minus else 0
+        r = rng.random()
+        if r < 0.04: flag |= 256
+        elif r < 0.07: flag |= 4
+        elif r < 0.10: flag |= 512
+        elif r < 0.13: flag |= 1024
+        elif r < 0.15: flag |= 2048
+        mapq = int(rng.choice([255, 255, 255, 60, 3, 1, 0]))
+        kind = int(rng.integers(0, 12))
+        aux = b""
+        if kind in (0, 1, 2): aux = W.aux_field("NH", "C", 1)
+        elif kind == 3: aux = W.aux_field("NH", "c", int(rng.choice([1, 2, 0, -1])))
+        elif kind == 4: aux = W.aux_field("XS", "Z", "x") + W.aux_field("NH", "S", int(rng.choice([1, 300])))
+        elif kind == 5: aux = W.aux_field("NH", "i", int(rng.choice([1, 4])))
+        elif kind == 6: aux = W.aux_field("NH", "A", "1")
+        elif kind == 7: aux = W.aux_field("NH", "f", float(rng.choice([1.0, 2.0])))
+        elif kind == 8: aux = W.aux_field("NH", "C", 2) + W.aux_field("NH", "C", 1)     # dict(): the last one counts
+        elif kind == 9: aux = W.aux_field("NH", "Z", "1")
+        ref_out = ref_id if k % 131 else -1
+        cigar = cigars[int(rng.choice(len(cigars), p=cig_p))](L)
+        recs.append((ref_out if ref_out >= 0 else 1 << 30, p0,
+                     W.record(ref_out, p0, mapq, flag, cigar, name=b"q%d" % k, aux=aux, l_seq=L)))
+    recs.sort(key=lambda x: (x[0], x[1]))
+    case = {"name": "infer_protocol", "refs": refs, "index": [header] + lines, "n_records": len(recs), "runs": []}
+    with tempfile.TemporaryDirectory() as tmp:
+        bam = os.path.join(tmp, "lib.bam")
+        W.write_bam(bam, refs, [r[2] for r in recs], sorted_header=True, block_payload=9001)
+        case["bam_b64"] = base64.b64encode(open(bam, "rb").read()).decode()
+        idx = os.path.join(tmp, "idx.tsv")
+        with open(idx, "w") as fh:
+            fh.write("\n".join(case["index"]) + "\n")
+        annotated, refseq = parse_ribotricer_index(idx)
+        case["annotated_oids"] = [o.oid for o in annotated]
+        case["refseq"] = {c: sorted([iv.start, iv.end, iv.data] for iv in tree.items) for c, tree in refseq.items()}
+        for n_reads in (20000, 150, 0):
+            prefix = os.path.join(tmp, f"out{n_reads}")
+            sink = io.StringIO()
+            with redirect_stdout(sink):
+                protocol = infer_protocol(bam, refseq, prefix, n_reads)
+            case["runs"].append({"n_reads": n_reads, "protocol": protocol,
+                                 "text": open(f"{prefix}_protocol.txt").read(),
+                                 "warnings": sink.getvalue().count("WARNING")})
+        # the same library with every strand flipped must read as the other protocol
+    return case
+
+
 def count_orfs_cases():
     """count_orfs (count_orfs.py:28-89) of the unmodified reference on the index + TSV text of the committed
     pipeline cases, for several feature sets and both report_all settings."""
@@ -482,6 +600,12 @@ def main():
         for r in sb["runs"]:
             print("split_bam", r["protocol"], r["read_lengths"], "keys:", len(r["alignments"]),
                   r["summary"].split("\n\nlength")[0].replace("\n\t", " "))
+    if "infer_protocol" in sys.argv[1:] or len(sys.argv) == 1:
+        ip = infer_protocol_case()
+        with gzip.open(os.path.join(HERE, "infer_protocol_case.json.gz"), "wt") as fh:
+            json.dump({"versions": versions(), "case": ip}, fh, separators=(",", ":"))
+        for r in ip["runs"]:
+            print("infer_protocol", r["n_reads"], r["protocol"], r["text"].replace("\n", " | "), "warnings:", r["warnings"])
     if "count_orfs" in sys.argv[1:]:      # (a full run does this last, after the pipeline cases it reads)
         cc = count_orfs_cases()
         with gzip.open(os.path.join(HERE, "count_orfs_cases.json.gz"), "wt") as fh:

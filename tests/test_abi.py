@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in header_symbols():
         assert hasattr(lib, name), name
-    assert _lib.load().rt_abi_version() == 1
+    assert _lib.load().rt_abi_version() == 2
 
 
 def test_no_cpu_fallback(built):
@@ -65,3 +65,7 @@ def test_len_table_rules():
     t = make_len_table({28: 12, 31: 13}, [28, 29])
     assert t[28] == 12 and t[29] == _lib.RT_LEN_UNUSED and t[30] == _lib.RT_LEN_FILTERED
     assert t[31] == _lib.RT_LEN_FILTERED   # an offset for a length split_bam never kept is moot
+    # inferred offsets can be negative (metagene.py:319-324): they are offsets, not sentinels
+    t = make_len_table({28: -1, 29: -2, 30: -5, 31: 0}, None)
+    assert [int(t[k]) for k in (28, 29, 30, 31)] == [-1, -2, -5, 0] and t[32] == _lib.RT_LEN_UNUSED
+    assert _lib.RT_LEN_UNUSED < -_lib.RT_MAX_OFFSET and _lib.RT_LEN_FILTERED < -_lib.RT_MAX_OFFSET

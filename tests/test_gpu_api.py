@@ -269,3 +269,34 @@ def test_learn_cutoff_matches_reference(engine, tmp_path, capsys):
         idx = rng.integers(0, n, (n_sel, reps))
         got = L._bootstrap_medians(engine, vals, idx)
         assert np.array_equal(got, np.median(vals[idx], axis=0))
+
+
+@pytest.mark.gpu
+def test_default_flags_on_full_config1(engine, tmp_path):
+    """detect_orfs() with NOTHING given (protocol, read lengths and P-site offsets all inferred) on the full
+    BASELINE configs[0] library (100 k ORFs, 10 M reads).  The unmodified reference's infer_protocol says
+    "forward" on this library (profiles/r2_protocol_heuristic_new_synth.txt) and its metagene_coverage /
+    align_metagenes recover the planted offsets {26-29: 12, 30-32: 13} (measured with the
+    reference); the inferred run must find the same and write the very TSV of the run with explicit offsets."""
+    from ribotricer_b200 import detect_orfs as D
+    from ribotricer_b200 import synth
+    from ribotricer_b200.bam import ReadColumns
+
+    D._ENGINE = engine
+    cfg = synth.config("C1")
+    idx = synth.make_index(cfg)
+    index_path = str(tmp_path / "index.tsv")
+    idx.write_tsv(index_path)
+    cols = synth.reads_to_numpy(synth.make_reads(cfg, idx, device=engine.device))
+    reads = ReadColumns(idx.contig_names, idx.contig_len, cols, True)
+    inferred, explicit = str(tmp_path / "inferred"), str(tmp_path / "explicit")
+    D.detect_orfs(reads, index_path, inferred, None, None, None, 0.428571428571, 5, 0, 0, 0.0, False)
+    assert open(f"{inferred}_protocol.txt").read().startswith("In total 20005 reads checked")
+    lags = dict(line.strip().replace("lag of ", "").split(": ") for line in open(f"{inferred}_psite_offsets.txt").read().split("\n")[1:] if line)
+    assert {int(k): int(v) + 12 for k, v in lags.items()} == synth.TRUE_OFFSETS
+    D.detect_orfs(reads, index_path, explicit, "forward", None, dict(synth.TRUE_OFFSETS), 0.428571428571, 5, 0, 0, 0.0, False)
+    a, b = open(f"{inferred}_translating_ORFs.tsv", "rb").read(), open(f"{explicit}_translating_ORFs.tsv", "rb").read()
+    assert a == b
+    assert a.count(b"\n") > 20_000      # header + the translating rows
+    for tag in ("pos", "neg"):
+        assert open(f"{inferred}_{tag}.wig", "rb").read() == open(f"{explicit}_{tag}.wig", "rb").read()

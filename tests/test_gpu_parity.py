@@ -97,9 +97,13 @@ def test_golden_pipeline_end_to_end(engine):
                 assert got["valid"][i] == int(r[6])
 
 
-@pytest.mark.parametrize("protocol,read_lengths,sort", [
-    ("forward", None, True), ("reverse", None, False), ("forward", [28, 29, 30], False), ("no", None, True)])
-def test_bin_psites_matches_oracle(engine, protocol, read_lengths, sort):
+NEGATIVE_OFFSETS = {26: -1, 27: -2, 28: 12, 29: -5, 30: 0, 31: 300}   # what align_metagenes may return (lag + 12 < 0)
+
+
+@pytest.mark.parametrize("protocol,read_lengths,sort,offsets", [
+    ("forward", None, True, None), ("reverse", None, False, None), ("forward", [28, 29, 30], False, None),
+    ("no", None, True, None), ("forward", None, True, NEGATIVE_OFFSETS), ("reverse", [26, 27, 29, 31], False, NEGATIVE_OFFSETS)])
+def test_bin_psites_matches_oracle(engine, protocol, read_lengths, sort, offsets):
     CO = _oracle()
     from ribotricer_b200 import synth
 
@@ -114,7 +118,7 @@ def test_bin_psites_matches_oracle(engine, protocol, read_lengths, sort):
     reads["mlen"][40:45] = 700      # beyond the shared-memory histogram
     reads["first"][45:50] = 0       # P-sites shifted off the contig start stay in the pad
     reads["last"][45:50] = 27
-    offsets = {26: 12, 27: 12, 28: 12, 29: 12, 30: 13, 31: 13}
+    offsets = offsets or {26: 12, 27: 12, 28: 12, 29: 12, 30: 13, 31: 13}
     pad = 16                        # small pad: some shifted P-sites fall outside -> oob
     base, plane = _setup(engine, idx.contig_names, idx.contig_len, idx.as_dict(), offsets, read_lengths, pad=pad)
     code = {"forward": 0, "reverse": 1}.get(protocol, 2)
@@ -231,8 +235,11 @@ def test_errors_are_loud(engine):
     from ribotricer_b200 import _lib
 
     engine.set_genome(["a"], [1000], pad=8)
-    with pytest.raises(_lib.RtError):   # offset larger than the pad
-        engine.set_length_table({28: 12, 40: 30})
+    engine.set_length_table({28: 12, 40: 30, 41: -7})   # offsets beyond the pad or below zero are offsets like any other
+    with pytest.raises(_lib.RtError):   # ... up to RT_MAX_OFFSET
+        engine.set_length_table({28: 12, 40: _lib.RT_MAX_OFFSET + 1})
+    with pytest.raises(_lib.RtError):
+        engine.set_length_table({28: -_lib.RT_MAX_OFFSET - 1})
     with pytest.raises(_lib.RtError):   # empty interval
         engine.set_index(np.array([0, 1], np.int64), np.array([10], np.int32), np.array([5], np.int32),
                          np.array([0], np.int32), np.array([0], np.uint8))

@@ -241,3 +241,42 @@ def test_native_decoder_matches_restated_pysam(built, tmp_path):
         if not pos:
             want, got = want[:1] + want[3:], got[:1] + got[3:]
         assert got == want, i
+
+
+# ---- infer_protocol (infer_protocol.py:34-124) + parse_ribotricer_index (detect_orfs.py:86-131) ----
+def test_infer_protocol_matches_reference(built, tmp_path):
+    """The unmodified reference functions (pysam and quicksect restated) ran on these BAM bytes and this
+    index when the golden file was made; the product's decoder + parse_ribotricer_index + infer_protocol
+    must give the same annotated rows, the same gene spans, the same protocol and the same
+    {prefix}_protocol.txt text for every n_reads setting."""
+    import base64
+
+    from ribotricer_b200 import metagene
+    from ribotricer_b200.bam import read_bam_columns_native
+    from ribotricer_b200.detect_orfs import parse_ribotricer_index
+
+    case = load_golden("infer_protocol_case.json.gz")["case"]
+    bam = tmp_path / "lib.bam"
+    bam.write_bytes(base64.b64decode(case["bam_b64"]))
+    idx = tmp_path / "idx.tsv"
+    idx.write_text("\n".join(case["index"]) + "\n")
+    reads = read_bam_columns_native(str(bam), 2)
+    assert len(reads) == case["n_records"]
+    assert "pos" in reads.cols and "ref_end" in reads.cols
+    annotated, refseq = parse_ribotricer_index(str(idx))
+    assert [o.oid for o in annotated] == case["annotated_oids"]
+    assert {c: sorted([int(a), int(b), int(s)] for a, b, s in v) for c, v in refseq.items()} == case["refseq"]
+    for run in case["runs"]:
+        prefix = str(tmp_path / f"out{run['n_reads']}")
+        assert metagene.infer_protocol(reads, refseq, prefix, run["n_reads"]) == run["protocol"]
+        assert open(f"{prefix}_protocol.txt").read() == run["text"], run["n_reads"]
+    # the pure-Python BAM reader the golden run used must see the same reference_start / reference_end
+    from oracle import pysam_restated
+
+    for i, read in enumerate(pysam_restated.AlignmentFile(str(bam), "rb").fetch(until_eof=True)):
+        end = -1 if read.reference_end is None else read.reference_end
+        assert (int(reads.cols["pos"][i]), int(reads.cols["ref_end"][i])) == (read.reference_start, end), i
+        nh = dict(read.get_tags()).get("NH")
+        want = (nh == 1) if nh is not None else None
+        got = None if reads.cols["nh"][i] == 0 else bool(reads.cols["nh"][i] == 1)
+        assert got == want, (i, nh)
