@@ -273,7 +273,9 @@ bool format_rows(std::string& b, const rt_index* ix, int64_t i0, int64_t i1, con
         b.append(f[6], flen[6]); b += '\t';
         b.append(f[7], flen[7]); b += '\t';
         b.append(f[8], flen[8]); b += '\t';
-        b.append(f[9], flen[9]); b += '\t';
+        if (flen[9] >= 3) b.append(f[9], 3);                                     // ORF.start_codon (orf.py:108-119): seq[:3],
+        else b += "None";                                                        //   None when the field holds fewer than 3 characters
+        b += '\t';
         b += '[';
         for (int64_t q = prof_ptr[i]; q < prof_ptr[i + 1]; ++q) {
             if (q > prof_ptr[i]) b += ", ";

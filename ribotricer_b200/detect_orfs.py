@@ -232,7 +232,8 @@ def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: i
                         idx.oid(o), f[0], "translating" if res["status"][k] else "nontranslating",
                         str(res["score"][k]), str(int(res["count"][k])), str(int(length[k])),
                         str(int(res["valid"][k])), repr(float(ratio[k])), str(density[k]),
-                        f[1], f[2], f[3], f[4], f[5], idx.chrom[o], idx.strand[o], f[6],
+                        f[1], f[2], f[3], f[4], f[5], idx.chrom[o], idx.strand[o],
+                        f[6][:3] if len(f[6]) >= 3 else "None",          # ORF.start_codon, orf.py:108-119
                         str(prof[ptr[j]:ptr[j + 1]].tolist()))))
                 out.write("\n".join(rows) + "\n")
             at += n_take

@@ -176,7 +176,10 @@ def metagene_coverage(cds, alignments, read_lengths: dict, prefix: str, max_posi
         width = int(lens.max()) if len(lens) else 0
     for length in read_lengths:
         if not cds:
-            break
+            # no annotated ORF: the reference's per-ORF loop never runs and every length gets empty profiles
+            # with phasescore([]) = (0.0, 0) (metagene.py:204-252); align_metagenes then ends in its sys.exit
+            metagenes[length] = (([], []), ([], []), 0.0, 0, 0.0, 0)
+            continue
         alignments.bin_into(cov, {length: 0})                       # alignments[length], bam.py:135
         out_ptr, flat = aux.gather_profiles(cov, sel, lens)
         alignments.bin_into(cov, {length: 0}, weight=-1)            # scratch back to zero

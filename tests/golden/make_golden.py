@@ -487,6 +487,21 @@ def infer_protocol_case(seed=1006):
     return case
 
 
+def start_codon_case():
+    """Index rows whose start_codon field is not three characters long: the TSV prints ORF.start_codon
+    (orf.py:108-119), i.e. seq[:3] or the string None, not the raw field."""
+    header = ("ORF_ID\tORF_type\ttranscript_id\ttranscript_type\tgene_id\tgene_name\t"
+              "gene_type\tchrom\tstrand\tstart_codon\tcoordinate")
+    codons = ["ATG", "AT", "", "ATGCC", "N", "CTGA"]
+    lines = [f"x{k}\t{'annotated' if k < 2 else 'uORF'}\tt{k}\tprotein_coding\tg{k}\tG{k}\tprotein_coding\tc1\t"
+             f"{'+' if k % 2 == 0 else '-'}\t{c}\t{100 + 60 * k}-{100 + 60 * k + 29}" for k, c in enumerate(codons)]
+    aln = [(28, "+" if k % 2 == 0 else "-", "c1", 100 + 60 * k + 3 * j - (12 if k % 2 == 0 else -12 - 2), 1 + (j % 3))
+           for k in range(len(codons)) for j in range(8)]
+    case = dict(name="start_codon", contigs=[["c1", 600]], index=[header] + lines, alignments=aln,
+                psite_offsets={"28": 12})
+    return case
+
+
 def count_orfs_cases():
     """count_orfs (count_orfs.py:28-89) of the unmodified reference on the index + TSV text of the committed
     pipeline cases, for several feature sets and both report_all settings."""
@@ -600,6 +615,11 @@ def main():
         for r in sb["runs"]:
             print("split_bam", r["protocol"], r["read_lengths"], "keys:", len(r["alignments"]),
                   r["summary"].split("\n\nlength")[0].replace("\n\t", " "))
+    if "start_codon" in sys.argv[1:] or len(sys.argv) == 1:
+        sc = run_reference_pipeline(start_codon_case(), ref)
+        with gzip.open(os.path.join(HERE, "start_codon_case.json.gz"), "wt") as fh:
+            json.dump({"versions": versions(), "cases": [sc]}, fh, separators=(",", ":"))
+        print("start_codon:", [r.split("\t")[16] for r in sc["tsv"][0]["text"].split("\n")[1:] if r])
     if "infer_protocol" in sys.argv[1:] or len(sys.argv) == 1:
         ip = infer_protocol_case()
         with gzip.open(os.path.join(HERE, "infer_protocol_case.json.gz"), "wt") as fh:

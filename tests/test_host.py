@@ -100,7 +100,8 @@ def test_native_tsv_writer_matches_reference_formatting(tmp_path, built):
 
     lib = _lib.load()
     p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-    for case in load_golden("pipeline_cases.json.gz")["cases"]:
+    # + rows whose start_codon field is not three characters long (the TSV prints ORF.start_codon, orf.py:108-119)
+    for case in load_golden("pipeline_cases.json.gz")["cases"] + load_golden("start_codon_case.json.gz")["cases"]:
         path = tmp_path / f"{case['name']}.tsv"
         path.write_text("\n".join(case["index"]) + "\n")
         idx = NativeIndex(str(path))
