@@ -47,6 +47,7 @@ struct rt_ctx {
     int64_t plane = 0;
     std::vector<int64_t> contig_len, contig_base;
     int2* d_contig_tab = nullptr;                    // per contig: (length, first slot >> 5)
+    double2* d_uv_table = nullptr;                   // unit vectors of small codons (rt::fill_uv_table), for phase B's seam windows
 
     // read-length table
     int32_t* d_len_table = nullptr;
@@ -324,6 +325,15 @@ int rt_create(int device, rt_ctx** out) {
         delete ctx;
         return fail(nullptr, RT_ENOMEM, "rt_create: cudaMalloc failed");
     }
+    if (cudaMalloc(&ctx->d_uv_table, sizeof(double2) * rt::kUvEntries) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, RT_ENOMEM, "rt_create: cudaMalloc failed");
+    }
+    rt::fill_uv_table_kernel<<<1, 256>>>(ctx->d_uv_table);
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, RT_ECUDA, "rt_create: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     if (const char* e = getenv("RT_SCORE_PATH")) ctx->use_atoms = strcmp(e, "scan") != 0;
     if (const char* e = getenv("RT_ATOM_LPO")) {
         const int v = atoi(e);
@@ -345,6 +355,7 @@ void rt_destroy(rt_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
     cudaFree(ctx->d_contig_tab);
+    cudaFree(ctx->d_uv_table);
     cudaFree(ctx->d_len_table);
     cudaFree(ctx->d_orf_desc);
     cudaFree(ctx->d_orf_len);
@@ -1036,12 +1047,17 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
             if (cnt > 32 || refs.size() % 32 + std::max<uint64_t>(cnt, 1) > 32) pad_group();
             const size_t w0 = refs.size() / 32;
             uint64_t P = 0;
+            const uint64_t L = (uint64_t)(ctx->nt_prefix[o + 1] - ctx->nt_prefix[o]);
+            auto flags_of = [&](uint64_t len) -> uint32_t {
+                return ((uint32_t)(P % 3) << rt::kRefPmod3Shift) | (P >= 1 ? rt::kRefPge1 : 0u) | (P >= 2 ? rt::kRefPge2 : 0u) |
+                       (P + len == L ? rt::kRefLast : 0u) | ((uint32_t)(L % 3) << rt::kRefLmod3Shift) | (rev ? rt::kRefRev : 0u);
+            };
             for (uint64_t k = 0; k < cnt; ++k) {
                 const uint32_t len = (uint32_t)(ctx->h_ref_ent[rb + k] & rt::kLenMask);
-                refs.push_back({ctx->h_ref_atom[rb + k], len | (rev << 31), (uint32_t)P, (int32_t)o});
+                refs.push_back({ctx->h_ref_atom[rb + k], len | flags_of(len), (uint32_t)((len + P) % 3), (int32_t)o});
                 P += len;
             }
-            if (cnt == 0) refs.push_back({0xffffffffu, rev << 31, 0u, (int32_t)o});   // an ORF without intervals still gets its row
+            if (cnt == 0) refs.push_back({0xffffffffu, flags_of(0), 0u, (int32_t)o});   // an ORF without intervals still gets its row
             if (cnt > 32) {
                 pad_group();
                 const int groups = (int)(refs.size() / 32 - w0);
@@ -1196,6 +1212,7 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
             ra.n_warps = plan->n_ref_warps;
             ra.summaries = ctx->d_summaries;
             ra.atom_nonzero = ctx->d_atom_nonzero;
+            ra.uv_table = ctx->d_uv_table;
             ra.want_min = ca.want_min;
             ra.orf_len = ctx->d_orf_len;
             ra.orf_lo = orf_lo;

@@ -1682,10 +1682,17 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
 // ORF's accumulator with integer atomics and the group that arrives last scores the ORF.
 struct RefRec {                        // 16 bytes
     uint32_t atom;                     // atom id; 0xffffffff: a stretch that reads as zeros
-    uint32_t len_rev;                  // values of the reference | (ORF on the '-' strand) << 31
-    uint32_t P;                        // profile offset of the reference's first value
+    uint32_t len_flags;                // values of the reference (24 bits) and what the kernel needs of its profile offset P and
+                                       //   of the ORF's length L, precomputed: see kRef* below
+    uint32_t aux;                      // (len + P) mod 3
     int32_t orf;                       // absolute ORF id; -1: padding
 };
+constexpr uint32_t kRefLenMask = (1u << 24) - 1u;
+constexpr int kRefPmod3Shift = 24;     // 2 bits: P mod 3
+constexpr uint32_t kRefPge1 = 1u << 26, kRefPge2 = 1u << 27;
+constexpr uint32_t kRefLast = 1u << 28;    // P + len == L
+constexpr int kRefLmod3Shift = 29;     // 2 bits: L mod 3
+constexpr uint32_t kRefRev = 1u << 31;     // ORF on the '-' strand
 struct RefWarp {                       // per group of 32 slots
     int32_t long_idx;                  // >= 0: the group belongs to long ORF number long_idx (more than 32 references)
     int32_t n_groups;                  //        ... which spans this many groups
@@ -1703,6 +1710,7 @@ struct RefComposeArgs {
     long long n_warps;
     const AtomSummary* summaries;
     const uint8_t* atom_nonzero;
+    const double2* uv_table;           // fill_uv_table in global memory (seam windows)
     int want_min;
     const int32_t* orf_len;
     long long orf_lo;
@@ -1714,6 +1722,66 @@ struct RefComposeArgs {
 };
 constexpr int kMaxExactCodons = 1 << 20;      // per frame: the 21-bit packed K / U fields of the reduction
 
+__global__ void __launch_bounds__(256) fill_uv_table_kernel(double2* tab) { fill_uv_table(tab); }
+
+// v[i] for i in {0, 1, 2} without indexing registers: p0 = (i == 0), p1 = (i == 1)
+template <typename T>
+__device__ __forceinline__ T sel3(bool p0, bool p1, T v0, T v1, T v2) { return p0 ? v0 : (p1 ? v1 : v2); }
+
+// statistics.py:92-115 + detect_orfs.py:278-299 on the finished sums of one ORF; the two quotients of the filter
+// predicate are only formed when their thresholds can reject anything
+template <typename Args>
+__device__ __forceinline__ void finish_orf_lean(const Args& args, int orf, int L, const unsigned* K, const unsigned* U,
+                                                const long long* RE, const long long* IM, unsigned mn, long long count) {
+    const double kSqrt3 = 1.7320508075688772;
+    const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
+    const int n_codons = L / 3 > 1 ? L / 3 : 1;                          // detect_orfs.py:281
+    double s3[3];
+    double coh = 0.0;
+    int valid = -1;
+#pragma unroll 1
+    for (int f = 0; f < 3; ++f) {
+        const unsigned Kf = sel3(f == 0, f == 1, K[0], K[1], K[2]), Uf = sel3(f == 0, f == 1, U[0], U[1], U[2]);
+        double s = kNaN;
+        if (Kf == 0) { coh = 0.0; valid = 0; }                            // statistics.py:94-95
+        else {
+            const double re = (double)sel3(f == 0, f == 1, RE[0], RE[1], RE[2]) * (1.0 / kUvGridScale);
+            const double im = kSqrt3 * ((double)sel3(f == 0, f == 1, IM[0], IM[1], IM[2]) * (1.0 / kUvGridScale));
+            s = (re * re + im * im) / ((double)Kf * (double)(Kf - Uf));   // 0/0 -> NaN never wins
+            if (s > coh) { coh = s; valid = (int)Kf; }                    // statistics.py:109-111
+            if (valid == -1) valid = (int)Kf;                             // statistics.py:112-113
+        }
+        if (f == 0) s3[0] = s; else if (f == 1) s3[1] = s; else s3[2] = s;
+    }
+    const double score = sqrt(coh);                                      // statistics.py:115
+    bool ok = score >= args.prm.phase_score_cutoff && (double)valid >= args.prm.min_valid_codons &&
+              (L == 0 || (double)(L == 0 ? 0u : mn) >= args.prm.min_reads_per_codon);
+    if (args.prm.min_valid_codons_ratio > 0.0)                           // detect_orfs.py:285 (valid >= 0: a threshold <= 0 always passes)
+        ok = ok && (double)valid / (double)n_codons >= args.prm.min_valid_codons_ratio;
+    else ok = ok && !(args.prm.min_valid_codons_ratio != args.prm.min_valid_codons_ratio);
+    if (args.prm.min_density_over_orf > 0.0)                             // detect_orfs.py:287
+        ok = ok && (double)count / (double)n_codons >= args.prm.min_density_over_orf;
+    else ok = ok && !(args.prm.min_density_over_orf != args.prm.min_density_over_orf);
+    const unsigned min_codon = L == 0 ? 0u : mn;
+    const long long k_out = (long long)orf - args.orf_lo;
+    args.out.score[k_out] = score;
+    args.out.valid[k_out] = valid;
+    args.out.count[k_out] = count;
+    args.out.length[k_out] = L;
+    if (args.out.min_codon) args.out.min_codon[k_out] = (int32_t)min_codon;
+    if (args.out.status) args.out.status[k_out] = ok ? 1 : 0;
+    if (args.out.frame_K) {
+        args.out.frame_K[3 * k_out + 0] = (int)K[0];
+        args.out.frame_K[3 * k_out + 1] = (int)K[1];
+        args.out.frame_K[3 * k_out + 2] = (int)K[2];
+    }
+    if (args.out.frame_s) {
+        args.out.frame_s[3 * k_out + 0] = s3[0];
+        args.out.frame_s[3 * k_out + 1] = s3[1];
+        args.out.frame_s[3 * k_out + 2] = s3[2];
+    }
+}
+
 __global__ void __launch_bounds__(256) compose_refs_kernel(const RefComposeArgs args) {
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= args.n_warps) return;
@@ -1724,11 +1792,26 @@ __global__ void __launch_bounds__(256) compose_refs_kernel(const RefComposeArgs 
     const int orf = (int)rr.w;
     const bool valid = orf >= 0;
     const unsigned atom = rr.x;
-    const int len = (int)(rr.y & 0x7fffffffu);
-    const bool rev = (rr.y >> 31) != 0;
-    const int P = (int)rr.z;
-    const bool nz = valid && atom != 0xffffffffu && __ldg(args.atom_nonzero + atom) != 0;
-    const int L = valid ? __ldg(args.orf_len + orf) : 0;
+    const int len = (int)(rr.y & kRefLenMask);
+    const bool rev = (rr.y & kRefRev) != 0;
+    const int pm3 = (int)((rr.y >> kRefPmod3Shift) & 3u);                 // P mod 3
+    const bool p_ge1 = (rr.y & kRefPge1) != 0, p_ge2 = (rr.y & kRefPge2) != 0, last = (rr.y & kRefLast) != 0;
+    const int lm3 = (int)((rr.y >> kRefLmod3Shift) & 3u);                 // L mod 3
+    // the summary is requested together with the atom's "holds a read" byte, not after it
+    const bool has_atom = valid && atom != 0xffffffffu;
+    const AtomSummary* s = args.summaries + (has_atom ? atom : 0u);
+    const bool nz = has_atom && __ldg(args.atom_nonzero + atom) != 0;
+    longlong2 r01 = make_longlong2(0, 0), r2i0 = r01, i12 = r01;
+    int4 edge = make_int4(0, 0, 0, 0);
+    uint4 ku = make_uint4(0, 0, 0, 0), mc = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
+    if (has_atom) {
+        r01 = __ldg(reinterpret_cast<const longlong2*>(s));          // re[0], re[1]
+        r2i0 = __ldg(reinterpret_cast<const longlong2*>(s) + 1);     // re[2], im[0]
+        i12 = __ldg(reinterpret_cast<const longlong2*>(s) + 2);      // im[1], im[2]
+        edge = __ldg(reinterpret_cast<const int4*>(s) + 3);
+        ku = __ldg(reinterpret_cast<const uint4*>(s) + 4);           // kpack, upack, count
+        if (args.want_min) mc = __ldg(reinterpret_cast<const uint4*>(s) + 5);        // mn[0..2]
+    }
     constexpr long long kOne = 1ll << 42, kHalf = 1ll << 41;
 
     unsigned K[3] = {0, 0, 0}, U[3] = {0, 0, 0};
@@ -1739,95 +1822,89 @@ __global__ void __launch_bounds__(256) compose_refs_kernel(const RefComposeArgs 
     bool big = false;
     int a0 = 0, a1 = 0, z0 = 0, z1 = 0;         // first two / last two values of the reference in profile order
     if (nz) {
-        const AtomSummary* s = args.summaries + atom;
-        const longlong2 r01 = __ldg(reinterpret_cast<const longlong2*>(s));          // re[0], re[1]
-        const longlong2 r2i0 = __ldg(reinterpret_cast<const longlong2*>(s) + 1);     // re[2], im[0]
-        const longlong2 i12 = __ldg(reinterpret_cast<const longlong2*>(s) + 2);      // im[1], im[2]
-        const int4 edge = __ldg(reinterpret_cast<const int4*>(s) + 3);
-        const uint4 ku = __ldg(reinterpret_cast<const uint4*>(s) + 4);               // kpack, upack, count
-        uint4 mc = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
-        if (args.want_min) mc = __ldg(reinterpret_cast<const uint4*>(s) + 5);        // mn[0..2]
-        const long long sre[3] = {r01.x, r01.y, r2i0.x}, sim[3] = {r2i0.y, i12.x, i12.y};
-        const unsigned smn[3] = {mc.x, mc.y, mc.z};
-        const unsigned sK[3] = {ku.x & 1023u, (ku.x >> 10) & 1023u, (ku.x >> 20) & 1023u};
-        const unsigned sU[3] = {ku.y & 1023u, (ku.y >> 10) & 1023u, (ku.y >> 20) & 1023u};
         big = (ku.x >> 31) != 0;
         count = ku.z;
         if (rev) { a0 = edge.w; a1 = edge.z; z0 = edge.y; z1 = edge.x; }
         else { a0 = edge.x; a1 = edge.y; z0 = edge.z; z1 = edge.w; }
         // local frame fl (window start offset inside the atom, mod 3) -> profile frame f:
-        //   '+': f = (fl + P) mod 3          '-': f = (len + P - fl) mod 3
-        const int base = rev ? (len + P) % 3 : P % 3;
-#pragma unroll
-        for (int fl = 0; fl < 3; ++fl) {
-            const int f = rev ? (base - fl + 3) % 3 : (base + fl) % 3;
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-                if (q == f) { K[q] += sK[fl]; U[q] += sU[fl]; RE[q] += sre[fl]; IM[q] += sim[fl]; }
-            if (f == 0) mn = min(mn, smn[fl]);
-        }
-    } else if (valid && len >= 3 && (3 - P % 3) % 3 <= len - 3) {
+        //   '+': f = (fl + P) mod 3, so profile frame q holds local frame (q - P) mod 3
+        //   '-': f = (len + P - fl) mod 3, so profile frame q holds local frame (len + P - q) mod 3
+        const int b = rev ? (int)(rr.z & 3u) : pm3;
+        const int i0 = rev ? b : (b == 0 ? 0 : 3 - b);
+        const int i1 = rev ? (i0 == 0 ? 2 : i0 - 1) : (i0 == 2 ? 0 : i0 + 1);
+        const int i2 = 3 - i0 - i1;
+        const bool p00 = i0 == 0, p01 = i0 == 1, p10 = i1 == 0, p11 = i1 == 1, p20 = i2 == 0, p21 = i2 == 1;
+        RE[0] = sel3(p00, p01, r01.x, r01.y, r2i0.x); IM[0] = sel3(p00, p01, r2i0.y, i12.x, i12.y);
+        RE[1] = sel3(p10, p11, r01.x, r01.y, r2i0.x); IM[1] = sel3(p10, p11, r2i0.y, i12.x, i12.y);
+        RE[2] = sel3(p20, p21, r01.x, r01.y, r2i0.x); IM[2] = sel3(p20, p21, r2i0.y, i12.x, i12.y);
+        K[0] = (ku.x >> (10 * i0)) & 1023u; K[1] = (ku.x >> (10 * i1)) & 1023u; K[2] = (ku.x >> (10 * i2)) & 1023u;
+        U[0] = (ku.y >> (10 * i0)) & 1023u; U[1] = (ku.y >> (10 * i1)) & 1023u; U[2] = (ku.y >> (10 * i2)) & 1023u;
+        mn = sel3(p00, p01, mc.x, mc.y, mc.z);                           // minimum of the profile-frame-0 windows
+    } else if (valid && len >= 3 && (pm3 == 0 ? 0 : 3 - pm3) <= len - 3) {
         mn = 0;     // a stretch without a read that holds a whole frame-0 codon
     }
 
     // ---- the last two profile values before this reference: from the lanes to the left ----
     int p_z0 = __shfl_up_sync(kFull, z0, 1), p_z1 = __shfl_up_sync(kFull, z1, 1), p_len = __shfl_up_sync(kFull, len, 1);
     int pp_z1 = __shfl_up_sync(kFull, z1, 2);
-    if (valid && P > 0 && lane < 2) {
+    if (valid && p_ge1 && lane < 2) {
         // only in the groups of a long ORF: the references before this one sit in the group to the left
         auto fetch_tail = [&](long long sl, int& tz0, int& tz1, int& tlen) {
             const uint4 q = __ldg(reinterpret_cast<const uint4*>(args.refs) + sl);
-            tlen = (int)(q.y & 0x7fffffffu);
+            tlen = (int)(q.y & kRefLenMask);
             tz0 = tz1 = 0;
             if (q.x != 0xffffffffu && __ldg(args.atom_nonzero + q.x) != 0) {
                 const int4 e = __ldg(reinterpret_cast<const int4*>(args.summaries + q.x) + 3);
-                if ((q.y >> 31) != 0) { tz0 = e.y; tz1 = e.x; } else { tz0 = e.z; tz1 = e.w; }
+                if ((q.y & kRefRev) != 0) { tz0 = e.y; tz1 = e.x; } else { tz0 = e.z; tz1 = e.w; }
             }
         };
-        int d0, d1, dl;
+        int d0, dl;
         if (lane == 0) {
             fetch_tail(slot - 1, p_z0, p_z1, p_len);
-            if (p_len < 2 && P >= 2) { fetch_tail(slot - 2, d0, pp_z1, dl); }
-        } else if (p_len < 2 && P >= 2) {
+            if (p_len < 2 && p_ge2) fetch_tail(slot - 2, d0, pp_z1, dl);
+        } else if (p_len < 2 && p_ge2) {
             fetch_tail(slot - 2, d0, pp_z1, dl);
         }
     }
-    // one seam window of the profile starting at position p = (values v0,v1,v2): statistics.py:72-90
-    auto window = [&](int p, int v0, int v1, int v2) {
-        const int f = p % 3;
-        ormask |= v0 | v1 | v2;
-        if (f == 0) mn = min(mn, (unsigned)v0 + (unsigned)v1 + (unsigned)v2);
-        if ((v0 | v1 | v2) == 0) return;
-        // '+'-oriented triple (a,b,c): the profile of a '-' ORF runs against the plane
-        const int a = rev ? v2 : v0, b = v1, c = rev ? v0 : v2;
-        long long re, im;
-        if ((b | c) == 0) { re = kOne; im = 0; }
-        else if ((a | c) == 0) { re = -kHalf; im = kHalf; }
-        else if ((a | b) == 0) { re = -kHalf; im = -kHalf; }
-        else if (a == b && b == c) { re = 0; im = 0; }
-        else {
-            const double2 u = uv_grid((double)(2ll * a - b - c), (double)((long long)b - c));
-            re = __double2ll_rn(u.x * kUvGridScale);
-            im = __double2ll_rn(u.y * kUvGridScale);
-        }
-        const bool uniform = a == b && b == c;
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-            if (q == f) { K[q] += 1u; U[q] += uniform ? 1u : 0u; RE[q] += re; IM[q] += im; }
-    };
     if (valid) {
+        // the two seam windows: the one that ENDS on the first value of this reference (profile position P - 2) and
+        // the one that ends on its second value (P - 1); statistics.py:72-90
         const int y = p_z1, x = p_len >= 2 ? p_z0 : pp_z1;
-        if (P >= 2) window(P - 2, x, y, a0);                 // the window that ENDS on the first value of this reference
-        if (len >= 2 && P >= 1) window(P - 1, y, a0, a1);    // ... and on its second value
-        if (P + len == L) {
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
+            if (k == 0 ? !p_ge2 : !(len >= 2 && p_ge1)) continue;
+            const int v0 = k == 0 ? x : y, v1 = k == 0 ? y : a0, v2 = k == 0 ? a0 : a1;
+            const int f = k == 0 ? (pm3 == 2 ? 0 : pm3 + 1) : (pm3 == 0 ? 2 : pm3 - 1);     // (P - 2) mod 3, (P - 1) mod 3
+            if (f == 0) mn = min(mn, (unsigned)v0 + (unsigned)v1 + (unsigned)v2);
+            if ((v0 | v1 | v2) == 0) continue;
+            ormask |= v0 | v1 | v2;
+            // '+'-oriented triple (a,b,c): the profile of a '-' ORF runs against the plane
+            const int a = rev ? v2 : v0, bb = v1, c = rev ? v0 : v2;
+            long long re, im;
+            unsigned uni = 0;
+            if ((bb | c) == 0) { re = kOne; im = 0; }
+            else if ((a | c) == 0) { re = -kHalf; im = kHalf; }
+            else if ((a | bb) == 0) { re = -kHalf; im = -kHalf; }
+            else if (a == bb && bb == c) { re = 0; im = 0; uni = 1; }
+            else {
+                double2 u;
+                if ((unsigned)(a | bb | c) < (unsigned)kUvMax) u = __ldg(args.uv_table + kUvCenter + (a - c) * kUvStride + (bb - c));
+                else u = uv_grid((double)(2ll * a - bb - c), (double)((long long)bb - c));
+                re = __double2ll_rn(u.x * kUvGridScale);
+                im = __double2ll_rn(u.y * kUvGridScale);
+            }
+            if (f == 0) { K[0] += 1u; U[0] += uni; RE[0] += re; IM[0] += im; }
+            else if (f == 1) { K[1] += 1u; U[1] += uni; RE[1] += re; IM[1] += im; }
+            else { K[2] += 1u; U[2] += uni; RE[2] += re; IM[2] += im; }
+        }
+        if (last) {
             // last reference: trailing partial codon (common.py:177-179); the last L % 3 values are (tx,) ty
-            const int ty = len >= 1 ? z1 : p_z1, tx = len >= 2 ? z0 : (len == 1 ? (P >= 1 ? p_z1 : 0) : (p_len >= 2 ? p_z0 : pp_z1));
-            if (L % 3 == 1) { mn = min(mn, (unsigned)ty); ormask |= ty; }
-            else if (L % 3 == 2) { mn = min(mn, (unsigned)tx + (unsigned)ty); ormask |= tx | ty; }
+            const int ty = len >= 1 ? z1 : p_z1, tx = len >= 2 ? z0 : (len == 1 ? (p_ge1 ? p_z1 : 0) : (p_len >= 2 ? p_z0 : pp_z1));
+            if (lm3 == 1) { mn = min(mn, (unsigned)ty); ormask |= ty; }
+            else if (lm3 == 2) { mn = min(mn, (unsigned)tx + (unsigned)ty); ormask |= tx | ty; }
         }
     }
     big |= (ormask >> kBigShift) != 0;
-    if (valid && L > 3 * kMaxExactCodons) big = true;
 
     // ---- add up the lanes of every ORF (consecutive lanes) ----
     const int left_orf = __shfl_up_sync(kFull, orf, 1);
@@ -1853,10 +1930,11 @@ __global__ void __launch_bounds__(256) compose_refs_kernel(const RefComposeArgs 
         }
     }
     if (!head || !valid) return;
+    const int L = __ldg(args.orf_len + orf);
     const unsigned kMask = (1u << 21) - 1u;
     K[0] = (unsigned)Kp & kMask; K[1] = (unsigned)(Kp >> 21) & kMask; K[2] = (unsigned)(Kp >> 42) & kMask;
     U[0] = (unsigned)Up & kMask; U[1] = (unsigned)(Up >> 21) & kMask; U[2] = (unsigned)(Up >> 42) & kMask;
-    big = flags != 0;
+    big = flags != 0 || L > 3 * kMaxExactCodons;
     if (rw.long_idx >= 0) {
         // one group of a long ORF: integer atomics into the ORF's accumulator; the last group to arrive scores it
         LongAcc* acc = args.long_acc + rw.long_idx;
@@ -1886,7 +1964,7 @@ __global__ void __launch_bounds__(256) compose_refs_kernel(const RefComposeArgs 
         args.fallback[atomicAdd(args.n_fallback, 1u)] = orf;
         return;
     }
-    finish_orf(args, orf, L, K, U, RE, IM, mn, count);
+    finish_orf_lean(args, orf, L, K, U, RE, IM, mn, count);
 }
 
 // ---- K4 -------------------------------------------------------------------------------------
