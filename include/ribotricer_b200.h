@@ -120,8 +120,9 @@ int rt_set_length_table(rt_ctx* ctx, const int32_t* h_len_table /* RT_LEN_TABLE 
  *      (detect_orfs.py:54-83) on decoded read columns.
  * Adds into d_cov (2*plane int32; clear it first for a fresh library),
  * accumulates into d_stats[RT_N_STATS] and d_len_counts[RT_LEN_TABLE] (int64).
- * `sorted_hint` != 0 promises coordinate-sorted input (a real BAM) and selects
- * the shared-memory tile path; results are identical either way.
+ * `sorted_hint` != 0 promises reads grouped by reference (a coordinate-sorted BAM); the device-pointer
+ * entry ignores it, the host-pointer entry uses it to ship packed records (below).  Results are identical
+ * either way.
  * `weight` is +1 to add a library, or -1 to take the same reads out again
  * (coverage, stats and length counts all return to their previous values),
  * which recycles a resident coverage buffer without a multi-GB memset.
@@ -132,9 +133,11 @@ int rt_bin_reads(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* d_ref_id
                  int protocol, int sorted_hint, int weight, int64_t* d_stats,
                  int64_t* d_len_counts, void* stream);
 
-/* Same with HOST columns: chunked, double-buffered H2D overlapped with the kernel;
- * h_stats / h_len_counts receive the totals (they are overwritten, not added to).
- * Returns after the work has completed. */
+/* Same with HOST columns (what a BAM decoder produces, 18 B/read): chunked, double-buffered H2D overlapped with the
+ * kernel; h_stats / h_len_counts receive the totals (they are overwritten, not added to).  With `sorted_hint` every
+ * chunk crosses PCIe as 11 B/read packed records: host threads evaluate the filter cascade of chunk k+1 into one
+ * meta byte per read and run-length code its ref_id while chunk k is on the wire (a chunk that turns out not to be
+ * grouped by reference is sent as plain columns).  Returns after the work has completed. */
 int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_ref_id,
                       const int32_t* h_first, const int32_t* h_last, const uint16_t* h_mlen,
                       const uint16_t* h_flag, const uint8_t* h_mapq, const uint8_t* h_nh,
@@ -215,6 +218,24 @@ int rt_score_host(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf
  */
 int rt_gather_profiles(rt_ctx* ctx, const int32_t* d_cov, int64_t n_sel, const int64_t* d_orf_ids,
                        const int64_t* d_out_ptr, int32_t* d_out, void* stream);
+
+/*
+ * ---- a library binned into the DENSE planes, copied into a buffer of the COMPACT layout (after rt_set_index; the
+ *      layout setting of the ctx does not matter): lets export_orf_coverages (detect_orfs.py:206-324) score with the
+ *      compact-layout kernels a coverage that export_wig (detect_orfs.py:327-351) needed genome-wide.
+ */
+int rt_compact_from_dense(rt_ctx* ctx, const int32_t* d_dense, int32_t* d_compact, void* stream);
+
+/*
+ * ---- export_wig (detect_orfs.py:327-351), device side: the non-zero slots of d_cov[0, n_slots) in slot order.
+ *      rt_wig_count writes the number of non-zero slots of every tile (rt_wig_tiles(n_slots) tiles); the caller
+ *      turns the counts into exclusive offsets (int64) and rt_wig_fill writes slot numbers (relative to d_cov) and
+ *      counts at those offsets.  Replaces the sorted (chrom, pos) key walk of the reference.
+ */
+int64_t rt_wig_tiles(int64_t n_slots);
+int rt_wig_count(rt_ctx* ctx, const int32_t* d_cov, int64_t n_slots, uint32_t* d_tile_counts, void* stream);
+int rt_wig_fill(rt_ctx* ctx, const int32_t* d_cov, int64_t n_slots, const int64_t* d_tile_offsets, int64_t* d_out_slot,
+                int32_t* d_out_count, void* stream);
 
 /*
  * ---- count_orfs (count_orfs.py:28-89) on device results: coverage sums over intervals of the DENSE planes,

@@ -228,6 +228,7 @@ def split_bam(bam_path, protocol: str, prefix: str, read_lengths=None, engine: E
     if (list(eng.contig_names) != list(reads.contig_names) or eng.pad != DEFAULT_PAD
             or not np.array_equal(eng.contig_len, reads.contig_len)):
         eng.set_genome(reads.contig_names, reads.contig_len, DEFAULT_PAD)
+    eng.ensure_dense()
     alignments = Alignments(eng, reads, protocol, read_lengths)
     stats, rlc = alignments.count()
     with open(f"{prefix}_bam_summary.txt", "w") as output:

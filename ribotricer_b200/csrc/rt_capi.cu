@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rt_kernels.cuh"
@@ -115,6 +116,13 @@ struct rt_ctx {
     std::vector<ScorePlan> plans;
 
     // scratch for the host-buffer entry points
+    struct HostStage {                               // page-locked staging of one chunk's meta bytes and run table
+        uint8_t* meta = nullptr;
+        int64_t* run_start = nullptr;
+        int32_t* run_ref = nullptr;
+        cudaEvent_t copied = nullptr;
+        bool busy = false;
+    } host_stage[2];
     DevBuf read_slot[2];
     cudaStream_t slot_stream[2] = {nullptr, nullptr};
     DevBuf stats_buf, score_buf;
@@ -287,6 +295,46 @@ int build_atoms(rt_ctx* ctx, const std::vector<uint64_t>& desc, const std::vecto
 constexpr size_t kReadBytes = 4 + 4 + 4 + 2 + 2 + 1 + 1;
 constexpr size_t kPackedReadBytes = 4 + 4 + 2 + 1;
 constexpr int64_t kHostChunkReads = 4 << 20;
+constexpr int64_t kChunkRunCap = 4096;            // reference runs per chunk of a library that is grouped by reference
+
+// bam.py:77-91 + common.py:33-69 on the host for reads [0, m) of a chunk (same order as classify_read() in
+// rt_kernels.cuh) and the run-length code of ref_id, by several threads.  Returns the number of runs, or -1 when
+// there are more than `cap` (the chunk is not grouped by reference).
+int64_t pack_chunk(const int32_t* ref_id, const uint16_t* flag, const uint8_t* mapq, const uint8_t* nh, int64_t m, uint8_t* meta,
+                   int64_t* run_start, int32_t* run_ref, int64_t cap, int n_threads) {
+    n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, m / (1 << 16)));
+    std::vector<std::vector<int64_t>> starts((size_t)n_threads);
+    auto work = [&](int t) {
+        const int64_t a = m * t / n_threads, b = m * (t + 1) / n_threads;
+        for (int64_t i = a; i < b; ++i) {
+            const unsigned f = flag[i];
+            unsigned code;
+            if (f & 0x200) code = RT_ST_QCFAIL;
+            else if (f & 0x400) code = RT_ST_DUPLICATE;
+            else if (f & 0x100) code = RT_ST_SECONDARY;
+            else if (f & 0x4) code = RT_ST_UNMAPPED;
+            else code = (nh[i] != 0 ? nh[i] == 1 : mapq[i] == 255) ? 0u : (unsigned)RT_ST_MULTI;
+            meta[i] = (uint8_t)(code | ((f & 0x10) ? 8u : 0u));
+            if (i == 0 || ref_id[i] != ref_id[i - 1]) {
+                if ((int64_t)starts[t].size() <= cap) starts[t].push_back(i);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    int64_t r = 0;
+    for (int t = 0; t < n_threads; ++t)
+        for (int64_t i : starts[t]) {
+            if (r >= cap) return -1;
+            run_start[r] = i;
+            run_ref[r] = ref_id[i];
+            ++r;
+        }
+    run_start[r] = m;
+    return r;
+}
 
 }  // namespace
 
@@ -388,6 +436,10 @@ void rt_destroy(rt_ctx* ctx) {
         cudaFree(p.d_long_acc);
     }
     for (int s = 0; s < 2; ++s) {
+        if (ctx->host_stage[s].meta) cudaFreeHost(ctx->host_stage[s].meta);
+        if (ctx->host_stage[s].run_start) cudaFreeHost(ctx->host_stage[s].run_start);
+        if (ctx->host_stage[s].run_ref) cudaFreeHost(ctx->host_stage[s].run_ref);
+        if (ctx->host_stage[s].copied) cudaEventDestroy(ctx->host_stage[s].copied);
         ctx->read_slot[s].release();
         if (ctx->slot_stream[s]) cudaStreamDestroy(ctx->slot_stream[s]);
     }
@@ -626,6 +678,8 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
                       int64_t* h_stats, int64_t* h_len_counts) {
     if (!ctx) return fail(nullptr, RT_EINVAL, "rt_bin_reads_host: ctx is NULL");
     if (!h_stats || !h_len_counts) return fail(ctx, RT_EINVAL, "rt_bin_reads_host: NULL output");
+    if (n > 0 && (!h_ref_id || !h_first || !h_last || !h_mlen || !h_flag || !h_mapq || !h_nh))
+        return fail(ctx, RT_EINVAL, "rt_bin_reads_host: NULL column");
     DeviceGuard guard(ctx->device);
     const size_t acc_bytes = sizeof(int64_t) * (RT_N_STATS + RT_LEN_TABLE);
     RT_CUDA(ctx, ctx->stats_buf.reserve(acc_bytes));
@@ -640,34 +694,73 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
         if (rc != RT_OK) return rc;
     }
     const int64_t chunk = std::min<int64_t>(kHostChunkReads, std::max<int64_t>(n, 1));
+    // Host columns are the 18 B/read a BAM decoder produces.  With `sorted_hint` (reads grouped by reference) every
+    // chunk is turned into 11 B/read packed records on the way: while chunk k is on the wire, host threads evaluate
+    // the filter cascade of chunk k+1 into one meta byte per read and run-length code its ref_id into a page-locked
+    // staging slot; first / last / mlen are copied straight from the caller's columns.  A chunk with too many
+    // reference runs (not grouped after all) is sent as plain columns.
+    const int n_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    if (sorted_hint)
+        for (int s = 0; s < 2; ++s) {
+            rt_ctx::HostStage& hs = ctx->host_stage[s];
+            if (!hs.meta) {
+                RT_CUDA(ctx, cudaHostAlloc(&hs.meta, (size_t)kHostChunkReads, cudaHostAllocDefault));
+                RT_CUDA(ctx, cudaHostAlloc(&hs.run_start, sizeof(int64_t) * (kChunkRunCap + 1), cudaHostAllocDefault));
+                RT_CUDA(ctx, cudaHostAlloc(&hs.run_ref, sizeof(int32_t) * kChunkRunCap, cudaHostAllocDefault));
+                RT_CUDA(ctx, cudaEventCreateWithFlags(&hs.copied, cudaEventDisableTiming));
+            }
+        }
     // per-slot layout: 4-byte columns first so that every column stays naturally aligned
-    const size_t slot_bytes = (size_t)chunk * kReadBytes + 64;
+    const size_t slot_bytes = (size_t)chunk * kReadBytes + sizeof(int64_t) * (kChunkRunCap + 1) + sizeof(int32_t) * kChunkRunCap + 64;
     int slot = 0;
     for (int64_t at = 0; at < n; at += chunk, slot ^= 1) {
         const int64_t m = std::min(chunk, n - at);
         RT_CUDA(ctx, ctx->read_slot[slot].reserve(slot_bytes));
         char* base = static_cast<char*>(ctx->read_slot[slot].p);
-        int32_t* d_ref = reinterpret_cast<int32_t*>(base);
+        int64_t* d_run_start = reinterpret_cast<int64_t*>(base);
+        int32_t* d_ref = reinterpret_cast<int32_t*>(d_run_start + kChunkRunCap + 1);
         int32_t* d_first = d_ref + chunk;
         int32_t* d_last = d_first + chunk;
-        uint16_t* d_mlen = reinterpret_cast<uint16_t*>(d_last + chunk);
+        int32_t* d_run_ref = d_last + chunk;
+        uint16_t* d_mlen = reinterpret_cast<uint16_t*>(d_run_ref + kChunkRunCap);
         uint16_t* d_flag = d_mlen + chunk;
         uint8_t* d_mapq = reinterpret_cast<uint8_t*>(d_flag + chunk);
         uint8_t* d_nh = d_mapq + chunk;
+        uint8_t* d_meta = d_mapq;                   // a chunk is either packed (meta) or plain (mapq, nh)
         cudaStream_t st = ctx->slot_stream[slot];   // stream order protects the slot's previous use
-        RT_CUDA(ctx, cudaMemcpyAsync(d_ref, h_ref_id + at, 4 * m, cudaMemcpyHostToDevice, st));
+        int64_t runs = -1;
+        rt_ctx::HostStage& hs = ctx->host_stage[slot];
+        if (sorted_hint) {
+            if (hs.busy) RT_CUDA(ctx, cudaEventSynchronize(hs.copied));     // the staging slot's previous copies are done
+            hs.busy = false;
+            runs = pack_chunk(h_ref_id + at, h_flag + at, h_mapq + at, h_nh + at, m, hs.meta, hs.run_start, hs.run_ref,
+                              kChunkRunCap, n_threads);
+        }
         RT_CUDA(ctx, cudaMemcpyAsync(d_first, h_first + at, 4 * m, cudaMemcpyHostToDevice, st));
         RT_CUDA(ctx, cudaMemcpyAsync(d_last, h_last + at, 4 * m, cudaMemcpyHostToDevice, st));
         RT_CUDA(ctx, cudaMemcpyAsync(d_mlen, h_mlen + at, 2 * m, cudaMemcpyHostToDevice, st));
-        RT_CUDA(ctx, cudaMemcpyAsync(d_flag, h_flag + at, 2 * m, cudaMemcpyHostToDevice, st));
-        RT_CUDA(ctx, cudaMemcpyAsync(d_mapq, h_mapq + at, m, cudaMemcpyHostToDevice, st));
-        RT_CUDA(ctx, cudaMemcpyAsync(d_nh, h_nh + at, m, cudaMemcpyHostToDevice, st));
-        int rc = rt_bin_reads(ctx, d_cov, m, d_ref, d_first, d_last, d_mlen, d_flag, d_mapq, d_nh, protocol,
-                              sorted_hint, 1, d_stats, d_len_counts, st);
+        int rc;
+        if (runs >= 0) {
+            RT_CUDA(ctx, cudaMemcpyAsync(d_meta, hs.meta, m, cudaMemcpyHostToDevice, st));
+            RT_CUDA(ctx, cudaMemcpyAsync(d_run_start, hs.run_start, sizeof(int64_t) * (size_t)(runs + 1), cudaMemcpyHostToDevice, st));
+            RT_CUDA(ctx, cudaMemcpyAsync(d_run_ref, hs.run_ref, sizeof(int32_t) * (size_t)runs, cudaMemcpyHostToDevice, st));
+            RT_CUDA(ctx, cudaEventRecord(hs.copied, st));
+            hs.busy = true;
+            rc = rt_bin_reads_packed(ctx, d_cov, m, d_first, d_last, d_mlen, d_meta, 0, runs, d_run_start, d_run_ref, protocol, 1,
+                                     d_stats, d_len_counts, st);
+        } else {
+            RT_CUDA(ctx, cudaMemcpyAsync(d_ref, h_ref_id + at, 4 * m, cudaMemcpyHostToDevice, st));
+            RT_CUDA(ctx, cudaMemcpyAsync(d_flag, h_flag + at, 2 * m, cudaMemcpyHostToDevice, st));
+            RT_CUDA(ctx, cudaMemcpyAsync(d_mapq, h_mapq + at, m, cudaMemcpyHostToDevice, st));
+            RT_CUDA(ctx, cudaMemcpyAsync(d_nh, h_nh + at, m, cudaMemcpyHostToDevice, st));
+            rc = rt_bin_reads(ctx, d_cov, m, d_ref, d_first, d_last, d_mlen, d_flag, d_mapq, d_nh, protocol, sorted_hint, 1,
+                              d_stats, d_len_counts, st);
+        }
         if (rc != RT_OK) return rc;
     }
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[0]));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[1]));
+    ctx->host_stage[0].busy = ctx->host_stage[1].busy = false;
     RT_CUDA(ctx, cudaMemcpy(h_stats, d_stats, sizeof(int64_t) * RT_N_STATS, cudaMemcpyDeviceToHost));
     RT_CUDA(ctx, cudaMemcpy(h_len_counts, d_len_counts, sizeof(int64_t) * RT_LEN_TABLE, cudaMemcpyDeviceToHost));
     return RT_OK;
@@ -1345,6 +1438,48 @@ int rt_gather_profiles(rt_ctx* ctx, const int32_t* d_cov, int64_t n_sel, const i
     const int64_t want = (n_sel + 7) / 8;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->n_sm * 8));
     rt::gather_profiles_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------ dense -> compact
+int rt_compact_from_dense(rt_ctx* ctx, const int32_t* d_dense, int32_t* d_compact, void* stream) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_compact_from_dense: ctx is NULL");
+    if (!d_dense || !d_compact) return fail(ctx, RT_EINVAL, "rt_compact_from_dense: NULL argument");
+    if (ctx->n_orf == 0 || !ctx->d_atoms_c) return fail(ctx, RT_ESTATE, "rt_compact_from_dense: call rt_set_index first");
+    if (ctx->n_atoms == 0) return RT_OK;
+    DeviceGuard guard(ctx->device);
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((ctx->n_atoms + 7) / 8, (int64_t)ctx->n_sm * 16));
+    rt::compact_from_dense_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ctx->d_atoms, ctx->d_atoms_c, ctx->n_atoms, d_dense, d_compact);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------ covered positions (WIG)
+int64_t rt_wig_tiles(int64_t n_slots) { return n_slots <= 0 ? 0 : (n_slots + rt::kWigTile - 1) / rt::kWigTile; }
+
+int rt_wig_count(rt_ctx* ctx, const int32_t* d_cov, int64_t n_slots, uint32_t* d_tile_counts, void* stream) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_wig_count: ctx is NULL");
+    if (n_slots < 0 || (n_slots > 0 && (!d_cov || !d_tile_counts))) return fail(ctx, RT_EINVAL, "rt_wig_count: NULL argument");
+    if (n_slots == 0) return RT_OK;
+    DeviceGuard guard(ctx->device);
+    rt::wig_count_kernel<<<(unsigned)rt_wig_tiles(n_slots), 256, 0, (cudaStream_t)stream>>>(d_cov, n_slots, d_tile_counts);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_wig_fill(rt_ctx* ctx, const int32_t* d_cov, int64_t n_slots, const int64_t* d_tile_offsets, int64_t* d_out_slot,
+                int32_t* d_out_count, void* stream) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_wig_fill: ctx is NULL");
+    if (n_slots < 0 || (n_slots > 0 && (!d_cov || !d_tile_offsets || !d_out_slot || !d_out_count)))
+        return fail(ctx, RT_EINVAL, "rt_wig_fill: NULL argument");
+    if (n_slots == 0) return RT_OK;
+    DeviceGuard guard(ctx->device);
+    rt::wig_fill_kernel<<<(unsigned)rt_wig_tiles(n_slots), 256, 0, (cudaStream_t)stream>>>(
+        d_cov, n_slots, reinterpret_cast<const long long*>(d_tile_offsets), reinterpret_cast<long long*>(d_out_slot), d_out_count);
     ctx->launches++;
     RT_CUDA(ctx, cudaGetLastError());
     return RT_OK;

@@ -2379,6 +2379,91 @@ __global__ void __launch_bounds__(256) clear_touched_kernel(int32_t* cov, const 
     }
 }
 
+// ---- dense planes -> compact buffer ---------------------------------------------------------------
+// The compact layout is the atoms laid end to end: one warp copies one atom.  Lets a library that was binned
+// into the genome-wide planes (the WIG export and the metagene windows need those) be scored by the streamed
+// kernels without binning it a second time.
+__global__ void __launch_bounds__(256) compact_from_dense_kernel(const uint64_t* __restrict__ atoms, const uint64_t* __restrict__ atoms_c,
+                                                                  long long n_atoms, const int32_t* __restrict__ dense,
+                                                                  int32_t* __restrict__ compact) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp0; i < n_atoms; i += n_warps) {
+        const uint64_t a = __ldg(atoms + i), c = __ldg(atoms_c + i);
+        const int32_t* src = dense + (a >> kLenBits);
+        int32_t* dst = compact + (c >> kLenBits);
+        const int len = (int)(a & kLenMask);
+        for (int k = lane; k < len; k += 32) dst[k] = ld_cov(src + k);
+    }
+}
+
+// ---- export_wig (detect_orfs.py:327-351): the covered positions of a stretch of the dense planes, in order ----
+// Two passes over tiles of kWigTile slots: count the non-zero slots of every tile; then, with the exclusive prefix
+// of the counts, every thread writes the non-zero ones among its 16 consecutive slots behind those of the threads
+// before it (block-wide exclusive scan), so the output is in slot order.
+constexpr int kWigPerThread = 16;
+constexpr int kWigTile = 256 * kWigPerThread;
+__device__ __forceinline__ int wig_load(const int32_t* __restrict__ cov, long long n, long long at, int (&v)[kWigPerThread]) {
+    int c = 0;
+    if (at + kWigPerThread <= n && (reinterpret_cast<uintptr_t>(cov + at) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < kWigPerThread / 4; ++q) {
+            const int4 x = __ldg(reinterpret_cast<const int4*>(cov + at) + q);
+            v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kWigPerThread; ++k) v[k] = at + k < n ? ld_cov(cov + at + k) : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kWigPerThread; ++k) c += v[k] != 0;
+    return c;
+}
+__global__ void __launch_bounds__(256) wig_count_kernel(const int32_t* __restrict__ cov, long long n, unsigned* tile_counts) {
+    int v[kWigPerThread];
+    const long long at = (long long)blockIdx.x * kWigTile + (long long)threadIdx.x * kWigPerThread;
+    int c = wig_load(cov, n, at, v);
+    c = (int)__reduce_add_sync(kFull, (unsigned)c);
+    __shared__ unsigned s_part[8];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = (unsigned)c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_part[w];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256) wig_fill_kernel(const int32_t* __restrict__ cov, long long n,
+                                                        const long long* __restrict__ tile_offsets, long long* out_slot,
+                                                        int32_t* out_count) {
+    int v[kWigPerThread];
+    const long long at = (long long)blockIdx.x * kWigTile + (long long)threadIdx.x * kWigPerThread;
+    const int c = wig_load(cov, n, at, v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __shared__ int s_warp[8];
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int before = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) before += w < warp ? s_warp[w] : 0;
+    long long o = tile_offsets[blockIdx.x] + before + incl - c;
+#pragma unroll
+    for (int k = 0; k < kWigPerThread; ++k)
+        if (v[k] != 0) {
+            out_slot[o] = at + k;
+            out_count[o] = v[k];
+            ++o;
+        }
+}
+
 // ---- phasescore of one arbitrary (float) profile --------------------------------------------
 // statistics.py:48-115 for a single sequence of doubles (the metagene profiles are floats,
 // metagene.py:243-244).  One warp; frames in turn; same closed form as accumulate_codon.

@@ -66,18 +66,17 @@ class MergedAlignments:
 
     def nonzero(self):
         """(strand_code, contig_id, pos, count) arrays of every covered position, ordered by
-        strand, contig and position.  Plumbing for the WIG side output and for tests."""
-        eng, t = self.engine, self.engine.torch
+        strand, contig and position: one ordered compaction of each strand plane on the device
+        (``Engine.nonzero_slots``), split by contig on the host.  Dense layout only."""
+        eng = self.engine
         out = []
+        base = np.asarray(eng.contig_base, np.int64)
         for strand in (0, 1):
-            for c in range(len(eng.contig_len)):
-                lo = strand * eng.plane + int(eng.contig_base[c])
-                span = int(eng.contig_len[c]) + 2 * eng.pad + 1
-                seg = self.cov[lo:lo + span]
-                nz = t.nonzero(seg).flatten()
-                if nz.numel():
-                    out.append((np.full(nz.numel(), strand, np.int8), np.full(nz.numel(), c, np.int32),
-                                (nz - eng.pad).cpu().numpy(), seg[nz].cpu().numpy()))
+            slots, vals = eng.nonzero_slots(self.cov, strand * eng.plane, eng.plane)
+            if len(slots) == 0:
+                continue
+            c = np.searchsorted(base, slots, side="right") - 1          # contig of every covered slot
+            out.append((np.full(len(slots), strand, np.int8), c.astype(np.int32), slots - base[c] - eng.pad, vals))
         if not out:
             z = np.zeros(0, np.int64)
             return z.astype(np.int8), z.astype(np.int32), z, z.astype(np.int32)
@@ -97,6 +96,7 @@ def merge_read_lengths(alignments: Alignments, psite_offsets: dict) -> MergedAli
     """detect_orfs.py:54-83: shift every read of a length in ``psite_offsets`` by its offset
     ('+': pos + offset, '-': pos - offset) and sum over lengths -- one K1 launch."""
     eng = alignments.engine
+    eng.ensure_dense()                   # a MergedAlignments holds the genome-wide planes
     cov = eng.new_coverage()
     alignments.bin_into(cov, psite_offsets)
     return MergedAlignments(eng, cov)
@@ -180,21 +180,40 @@ def export_orf_coverages(
     lo, hi = orf_range if orf_range is not None else (0, idx.n_orf)
     params = ScoreParams(phase_score_cutoff, min_valid_codons, min_reads_per_codon, min_valid_codons_ratio,
                          min_density_over_orf)
-    res = eng.score_host(merged_alignments.cov, lo, hi, params)
-    write_tsv(path or f"{prefix}_translating_ORFs.tsv", idx, res, merged_alignments, lo, hi, report_all, write_header)
+    merged = merged_alignments
+    dense_in = eng.layout == "dense" and idx.n_orf > 0
+    if dense_in:
+        # the library arrives in the genome-wide planes (export_wig and the metagene step need those); scoring and
+        # the profile gather only read the exon union of the index: copy that part into a compact-layout buffer and
+        # run the compact-layout kernels on it (same results, see tests/test_gpu_parity.py)
+        eng.set_layout("compact")
+        ccov = eng.torch.empty(eng.coverage_elems(), dtype=eng.torch.int32, device=eng.device)
+        ccov[-64:] = 0                                              # the guard slots behind the last atom
+        eng.compact_from_dense(merged_alignments.cov, ccov)
+        merged = MergedAlignments(eng, ccov)
+    try:
+        res = eng.score_host(merged.cov, lo, hi, params)
+        write_tsv(path or f"{prefix}_translating_ORFs.tsv", idx, res, merged, lo, hi, report_all, write_header)
+    finally:
+        if dense_in:
+            eng.set_layout("dense")
     return res
 
 
 def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: int, hi: int, report_all: bool,
-              write_header: bool = True, chunk_nt: int = 1 << 27):
+              write_header: bool = True, chunk_nt: int = 1 << 27, res_offset: int = 0):
     """Rows exactly as detect_orfs.py:304-323 formats them: np.float64 phase score and read
-    density, Python-float ratio, ``str(list)`` profile."""
+    density, Python-float ratio, ``str(list)`` profile.  Rows [lo, hi) of the index; their results sit at
+    positions ``res_offset ...`` of the result columns, which is also their ORF number in the engine's resident
+    index (0 unless the engine holds a sub-index, see multi_gpu.py)."""
     eng = merged.engine
-    keep = np.arange(lo, hi) if report_all else lo + np.flatnonzero(res["status"])
-    length = res["length"].astype(np.int64)
+    n = hi - lo
+    view = {k: v[res_offset:res_offset + n] for k, v in res.items()}
+    keep = np.arange(lo, hi) if report_all else lo + np.flatnonzero(view["status"])
+    length = view["length"].astype(np.int64)
     n_codons = np.maximum(1, length // 3)                         # detect_orfs.py:281
-    ratio = res["valid"].astype(np.float64) / n_codons           # :285
-    density = res["count"].astype(np.float64) / n_codons         # :287
+    ratio = view["valid"].astype(np.float64) / n_codons          # :285
+    density = view["count"].astype(np.float64) / n_codons        # :287
     native = isinstance(idx, NativeIndex)
     if native:
         import ctypes as C
@@ -203,7 +222,7 @@ def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: i
         handle = C.c_void_p()
         if lib.rt_tsv_open(str(path).encode(), int(write_header), C.byref(handle)) != 0:
             raise OSError(lib.rt_io_last_error().decode())
-        cols = {k: np.ascontiguousarray(res[k]) for k in ("score", "valid", "count", "length", "status")}
+        cols = {k: np.ascontiguousarray(view[k]) for k in ("score", "valid", "count", "length", "status")}
         p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     else:
         out = open(path, "w")
@@ -216,7 +235,7 @@ def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: i
             csum = np.cumsum(length[keep[at:] - lo])
             n_take = max(1, int(np.searchsorted(csum, chunk_nt, side="right")))
             sel = np.ascontiguousarray(keep[at:at + n_take], np.int64)
-            ptr, prof = eng.gather_profiles(merged.cov, sel, length[sel - lo])
+            ptr, prof = eng.gather_profiles(merged.cov, sel - lo + res_offset, length[sel - lo])
             if native:
                 prof = np.ascontiguousarray(prof, np.int32)
                 rc = lib.rt_tsv_write(handle, idx.handle, len(sel), p(sel), int(lo), p(cols["score"]), p(cols["valid"]),
@@ -229,9 +248,9 @@ def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: i
                     k = o - lo
                     f = idx.fields[o]
                     rows.append("\t".join((
-                        idx.oid(o), f[0], "translating" if res["status"][k] else "nontranslating",
-                        str(res["score"][k]), str(int(res["count"][k])), str(int(length[k])),
-                        str(int(res["valid"][k])), repr(float(ratio[k])), str(density[k]),
+                        idx.oid(o), f[0], "translating" if view["status"][k] else "nontranslating",
+                        str(view["score"][k]), str(int(view["count"][k])), str(int(length[k])),
+                        str(int(view["valid"][k])), repr(float(ratio[k])), str(density[k]),
                         f[1], f[2], f[3], f[4], f[5], idx.chrom[o], idx.strand[o],
                         f[6][:3] if len(f[6]) >= 3 else "None",          # ORF.start_codon, orf.py:108-119
                         str(prof[ptr[j]:ptr[j + 1]].tolist()))))

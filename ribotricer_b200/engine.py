@@ -147,6 +147,11 @@ class Engine:
         self._check(self.lib.rt_set_layout(self.ctx, {"dense": 0, "compact": 1}[layout]))
         self.layout = layout
 
+    def ensure_dense(self):
+        """Back to the genome-wide planes (a no-op when they are the current layout)."""
+        if getattr(self, "layout", "dense") != "dense":
+            self.set_layout("dense")
+
     def coverage_elems(self) -> int:
         return int(self.lib.rt_coverage_elems(self.ctx))
 
@@ -390,6 +395,36 @@ class Engine:
         self._check(self.lib.rt_score_host(self.ctx, C.c_void_p(cov.data_ptr()), int(lo), int(hi), C.byref(prm),
                                            C.byref(o)))
         return out
+
+    # ----------------------------------------------- dense planes -> compact buffer, covered positions
+    def compact_from_dense(self, dense_cov, compact_cov):
+        """Copy the slots the resident index reads from genome-wide planes into a compact-layout buffer
+        (``rt_compact_from_dense``; enqueued, no host sync)."""
+        self._check(self.lib.rt_compact_from_dense(self.ctx, C.c_void_p(dense_cov.data_ptr()),
+                                                   C.c_void_p(compact_cov.data_ptr()), self._stream()))
+
+    def nonzero_slots(self, cov, lo: int, n: int):
+        """Non-zero slots of ``cov[lo:lo+n]`` in slot order -> (slot numbers relative to ``lo``, counts) on the host
+        (``rt_wig_count`` / ``rt_wig_fill``: tile counts, an exclusive prefix on the host, ordered compaction)."""
+        t = self.torch
+        n_tiles = int(self.lib.rt_wig_tiles(int(n)))
+        if n_tiles == 0:
+            return np.zeros(0, np.int64), np.zeros(0, np.int32)
+        base = C.c_void_p(cov.data_ptr() + 4 * int(lo))
+        d_counts = t.empty(n_tiles, dtype=t.int32, device=self.device)
+        self._check(self.lib.rt_wig_count(self.ctx, base, int(n), C.c_void_p(d_counts.data_ptr()), self._stream()))
+        counts = d_counts.cpu().numpy().view(np.uint32).astype(np.int64)
+        offsets = np.zeros(n_tiles + 1, np.int64)
+        np.cumsum(counts, out=offsets[1:])
+        total = int(offsets[-1])
+        if total == 0:
+            return np.zeros(0, np.int64), np.zeros(0, np.int32)
+        d_off = t.from_numpy(offsets[:-1].copy()).to(self.device)
+        d_slot = t.empty(total, dtype=t.int64, device=self.device)
+        d_val = t.empty(total, dtype=t.int32, device=self.device)
+        self._check(self.lib.rt_wig_fill(self.ctx, base, int(n), C.c_void_p(d_off.data_ptr()), C.c_void_p(d_slot.data_ptr()),
+                                         C.c_void_p(d_val.data_ptr()), self._stream()))
+        return d_slot.cpu().numpy(), d_val.cpu().numpy()
 
     # ------------------------------------------------------------------- K4
     def gather_profiles(self, cov, orf_ids, lengths):

@@ -168,6 +168,7 @@ def metagene_coverage(cds, alignments, read_lengths: dict, prefix: str, max_posi
     eng = alignments.engine
     metagenes = {}
     if cds and read_lengths:
+        eng.ensure_dense()                                           # the windows address the genome-wide planes
         aux = _aux_engine(eng)
         ptr, st, en, contig, strand, lens = _metagene_windows(cds, eng, max_positions, offset_5p, offset_3p)
         aux.set_index(ptr, st, en, contig, strand)

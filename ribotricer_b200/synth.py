@@ -49,6 +49,8 @@ class SynthConfig:
     n_micro: int = 0                   # C5: ORFs of exactly 20 codons
     expr_shape: float = 0.5            # gamma shape of per-ORF expression (smaller = more skew)
     annotated_rows: int = 0
+    genome_order: bool = True          # rows in transcript order along the genome inside the annotated block and after it,
+                                       # as prepare-orfs writes them from a sorted GTF (prepare_orfs.py:322-365)
 
 
 def config(name: str, scale: float = 1.0, contig_scale: float = 1.0) -> SynthConfig:
@@ -211,7 +213,11 @@ def make_index(cfg: SynthConfig) -> SynthIndex:
     first_rows = np.flatnonzero((o_rank == 0))[: cfg.annotated_rows]
     mask = np.ones(n_total, bool)
     mask[first_rows] = False
-    perm = np.concatenate([first_rows, np.flatnonzero(mask)])
+    rest = np.flatnonzero(mask)
+    if cfg.genome_order:
+        key = lambda rows: np.lexsort((rows, tx_start[orf_tx[rows]], tx_contig[orf_tx[rows]]))  # noqa: E731
+        first_rows, rest = first_rows[key(first_rows)], rest[key(rest)]
+    perm = np.concatenate([first_rows, rest])
     orf_tx, trim = orf_tx[perm], trim[perm]
     # kept genomic-concat range of the transcript: '+' [trim, L), '-' [0, L - trim)
     L_tx = tx_len[orf_tx]

@@ -2,7 +2,8 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
 
-Every rank scores its ORF shard of one synthetic library with detect_orfs_sharded(); rank 0 then
+Every rank scores its genomic block of one synthetic library with detect_orfs_sharded() from its slice of the
+reads; rank 0 then
 runs the single-GPU detect_orfs() and requires byte-identical TSV / WIG / summary files, with and
 without P-site offset inference (the offsets are inferred on rank 0 and broadcast).
 """
@@ -42,9 +43,10 @@ def main():
     for tag, lengths, offsets, meta in (("given", [28, 29, 30], {28: 12, 29: 12, 30: 13}, 10 ** 9),
                                         ("inferred", None, None, 20000)):
         prefix = os.path.join(tmp, f"sharded_{tag}")
-        lo, hi = multi_gpu.detect_orfs_sharded(reads_path, index_path, prefix, "forward", lengths, offsets,
-                                               0.428571428571, 5, 0, 0, 0.0, True, meta_min_reads=meta)
-        print(f"rank {rank}: ORFs [{lo}, {hi}) of {idx.n_orf} ({tag})", flush=True)
+        shard = multi_gpu.detect_orfs_sharded(reads_path, index_path, prefix, "forward", lengths, offsets,
+                                              0.428571428571, 5, 0, 0, 0.0, True, meta_min_reads=meta)
+        print(f"rank {rank}: {len(shard.rows)} of {idx.n_orf} ORFs in {len(shard.runs)} runs, spans {shard.spans} ({tag})",
+              flush=True)
         dist.barrier()
         if rank == 0:
             single = os.path.join(tmp, f"single_{tag}")

@@ -300,3 +300,98 @@ def test_default_flags_on_full_config1(engine, tmp_path):
     assert a.count(b"\n") > 20_000      # header + the translating rows
     for tag in ("pos", "neg"):
         assert open(f"{inferred}_{tag}.wig", "rb").read() == open(f"{explicit}_{tag}.wig", "rb").read()
+
+
+@pytest.mark.gpu
+def test_genomic_shards_reproduce_the_single_run(engine, tmp_path):
+    """The N-rank driver's per-rank work (multi_gpu.score_shard: sub-index of a genomic block in the compact layout,
+    scored from the block's slice of the reads, one TSV part per run of rows) run for every block of a 3-way and a
+    5-way plan on this one GPU: the joined parts must be the single run's TSV byte for byte."""
+    from ribotricer_b200 import detect_orfs as D
+    from ribotricer_b200 import multi_gpu, synth
+    from ribotricer_b200.bam import ReadColumns, split_bam
+    from ribotricer_b200.engine import ScoreParams
+
+    D._ENGINE = engine
+    cfg = synth.config("tiny")
+    idx = synth.make_index(cfg)
+    index_path = str(tmp_path / "index.tsv")
+    idx.write_tsv(index_path)
+    cols = synth.reads_to_numpy(synth.make_reads(cfg, idx, n_reads=300_000))
+    reads = ReadColumns(idx.contig_names, idx.contig_len, cols, True)
+    offsets = {28: 12, 29: 12, 30: 13, 31: 13}
+    single = str(tmp_path / "single")
+    D.detect_orfs(reads, index_path, single, "forward", None, dict(offsets), 0.428571428571, 5, 0, 0, 0.0, True)
+    want = open(f"{single}_translating_ORFs.tsv", "rb").read()
+    nidx = D.load_index(index_path)
+    lut = {n: i for i, n in enumerate(engine.contig_names)}
+    dc = nidx.device_columns(lut)
+    for n in (3, 5):
+        prefix = str(tmp_path / f"sharded{n}")
+        plan = multi_gpu.shard_plan(dc["exon_ptr"], dc["exon_start"], dc["exon_end"], dc["orf_contig"], n)
+        with open(f"{prefix}_translating_ORFs.tsv.header", "w") as fh:
+            fh.write("\t".join(D.TSV_COLUMNS) + "\n")
+        seen = 0
+        for sh in plan:
+            _, n_reads = multi_gpu.score_shard(engine, nidx, sh, reads, "forward", None, offsets, ScoreParams(), prefix, True)
+            seen += n_reads
+        assert seen < 2 * len(reads)          # the blocks' slices overlap at their borders only
+        multi_gpu.join_runs(prefix, plan)
+        assert open(f"{prefix}_translating_ORFs.tsv", "rb").read() == want, n
+
+
+@pytest.mark.gpu
+def test_two_rank_job_is_byte_identical(tmp_path):
+    """tests/multi_gpu_check.py under torchrun on 2 GPUs (skipped on a single-GPU box)."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MGPU_TMP=str(tmp_path), MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29641", os.path.join(root, "tests", "multi_gpu_check.py")],
+                         capture_output=True, text=True, env=env, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.stdout.count("MULTI_GPU_OK") == 2
+
+
+@pytest.mark.gpu
+def test_batch_of_libraries_matches_single_runs(engine, tmp_path):
+    """BASELINE configs[3] in small: eight libraries against one resident index through detect_orfs_batch (index and
+    compact slot map set once, copy / kernels / text pipelined over two coverage buffers).  Every library's TSV and
+    BAM summary must be the bytes detect_orfs() writes for that library alone."""
+    from ribotricer_b200 import detect_orfs as D
+    from ribotricer_b200 import synth
+    from ribotricer_b200.bam import ReadColumns, save_read_columns
+    from ribotricer_b200.batch import detect_orfs_batch
+
+    D._ENGINE = engine
+    cfg = synth.config("tiny")
+    idx = synth.make_index(cfg)
+    index_path = str(tmp_path / "index.tsv")
+    idx.write_tsv(index_path)
+    offsets = {27: 12, 28: 12, 29: 12, 30: 13, 31: 13}
+    lengths = [27, 28, 29, 30, 31]
+    libs, singles, batched = [], [], []
+    for k in range(8):
+        cols = synth.reads_to_numpy(synth.make_reads(cfg, idx, n_reads=40_000 + 15_000 * k, seed_offset=100 + k, sort=k != 5))
+        path = str(tmp_path / f"lib{k}.npz")
+        save_read_columns(path, ReadColumns(idx.contig_names, idx.contig_len, cols, k != 5))
+        libs.append(path)
+        singles.append(str(tmp_path / f"single{k}"))
+        batched.append(str(tmp_path / "batch" / f"lib{k}"))
+    params = (0.3, 3, 0, 0.1, 0.25)
+    for report_all in (False, True):
+        for k in range(8):
+            D.detect_orfs(libs[k], index_path, singles[k], "forward", lengths, dict(offsets), *params, report_all)
+        done = detect_orfs_batch(libs, index_path, batched, "forward", lengths, offsets, *params, report_all=report_all,
+                                 engine=engine)
+        assert [k for k, _ in done] == list(range(8))
+        for k in range(8):
+            for suffix in ("_translating_ORFs.tsv", "_bam_summary.txt"):
+                assert open(batched[k] + suffix, "rb").read() == open(singles[k] + suffix, "rb").read(), (k, suffix)
+    assert engine.layout == "dense"

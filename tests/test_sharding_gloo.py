@@ -1,6 +1,7 @@
-"""N > 1 host logic on CPU: world_size-2 gloo job.  Each rank scores its ORF shard (with the
-oracle standing in for the GPU -- this test is about sharding, ordering and the control-plane
-gather, not about kernels) and rank 0 must end up with exactly the single-process result."""
+"""N > 1 host logic on CPU: world_size-2 gloo job.  Each rank scores its genomic block of the index from its
+slice of the reads (with the oracle standing in for the GPU -- this test is about the shard plan, the read
+slices, ordering and the control-plane gather, not about kernels) and rank 0 must end up with exactly the
+single-process result."""
 import os
 import subprocess
 import sys
@@ -25,28 +26,38 @@ reads = synth.reads_to_numpy(synth.make_reads(cfg, idx, n_reads=40_000))
 pad = 64
 base, plane = CO.genome_layout(idx.contig_len, pad)
 cov, _, _ = CO.bin_reads(reads, 0, CO.make_len_table(synth.TRUE_OFFSETS), base, idx.contig_len, pad, plane)
-bounds = multi_gpu.shard_bounds(idx.orf_len, np.diff(idx.exon_ptr), size)
-lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-local = CO.score(idx.as_dict(), cov, base, idx.contig_len, pad, plane, [0.428571428571, 5, 0, 0, 0.0], lo, hi,
-                 diagnostics=False)
-# TSV parts in rank order
+# each rank: its genomic block of the index (shard_plan), scored from ITS SLICE of the coordinate-sorted reads only
+plan = multi_gpu.shard_plan(idx.exon_ptr, idx.exon_start, idx.exon_end, idx.orf_contig, size)
+sh = plan[rank]
+slices = multi_gpu.read_slices(reads["ref_id"], reads["first"], reads["last"], sh.spans, max(synth.TRUE_OFFSETS.values()))
+mine = {k: np.concatenate([v[a:b] for a, b in slices]) for k, v in reads.items()}
+assert len(mine["ref_id"]) < len(reads["ref_id"])
+cov_mine, _, _ = CO.bin_reads(mine, 0, CO.make_len_table(synth.TRUE_OFFSETS), base, idx.contig_len, pad, plane)
+sub = multi_gpu.sub_index(idx.as_dict(), sh.rows)
+local = CO.score(sub, cov_mine, base, idx.contig_len, pad, plane, [0.428571428571, 5, 0, 0, 0.0], diagnostics=False)
+local["rows"] = sh.rows
+# TSV parts: one per run of consecutive rows, joined in row order
 prefix = sys.argv[2]
-with open(f"{prefix}_translating_ORFs.tsv.part{rank}", "w") as fh:
-    if rank == 0:
-        fh.write("header\n")
-    for k in range(hi - lo):
-        fh.write(f"{lo + k}\t{local['count'][k]}\n")
+if rank == 0:
+    open(f"{prefix}_translating_ORFs.tsv.header", "w").write("header\n")
+for g_lo, g_hi, r_lo in sh.runs:
+    with open(f"{prefix}_translating_ORFs.tsv.rows{g_lo:012d}", "w") as fh:
+        for k in range(g_hi - g_lo):
+            fh.write(f"{g_lo + k}\t{local['count'][r_lo + k]}\n")
 full = multi_gpu.gather_columns(local, dist)
 dist.barrier()
 if rank == 0:
     ref = CO.score(idx.as_dict(), cov, base, idx.contig_len, pad, plane, [0.428571428571, 5, 0, 0, 0.0],
                    diagnostics=False)
+    order = np.argsort(full["rows"], kind="stable")
+    assert np.array_equal(full["rows"][order], np.arange(idx.n_orf))
     for k in ref:
-        assert np.array_equal(full[k], ref[k], equal_nan=True), k
-    multi_gpu.join_parts(prefix, size)
+        assert np.array_equal(full[k][order], ref[k], equal_nan=True), k
+    multi_gpu.join_runs(prefix, plan)
     rows = open(f"{prefix}_translating_ORFs.tsv").read().split("\n")
     assert rows[0] == "header" and [int(r.split("\t")[0]) for r in rows[1:] if r] == list(range(idx.n_orf))
-    print("GLOO_OK", bounds.tolist())
+    assert [int(r.split("\t")[1]) for r in rows[1:] if r] == ref["count"].tolist()
+    print("GLOO_OK", [len(p.rows) for p in plan], [len(p.runs) for p in plan])
 dist.destroy_process_group()
 '''
 
@@ -78,3 +89,47 @@ def test_two_rank_gloo_job(tmp_path, built):
         capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "GLOO_OK" in out.stdout
+
+
+def test_shard_plan_and_read_slices():
+    """Blocks along the genome: a partition of the rows, balanced in bytes, few runs each for a genome-ordered
+    index; the read slices of a block hold every read that can reach it (checked by brute force), also for spliced
+    reads whose two ends lie far apart; an index in random order falls back to contiguous row ranges."""
+    from ribotricer_b200 import multi_gpu, synth
+
+    cfg = synth.config("tiny")
+    idx = synth.make_index(cfg)
+    reads = synth.reads_to_numpy(synth.make_reads(cfg, idx, n_reads=60_000))
+    rng = np.random.default_rng(5)
+    spliced = rng.choice(len(reads["first"]), 500, replace=False)       # long introns: last far to the right of first
+    reads["last"][spliced] += rng.integers(1000, 60_000, 500).astype(np.int32)
+    cost = 4 * idx.orf_len + 8 * np.diff(idx.exon_ptr) + 42
+    for n in (1, 2, 3, 8):
+        plan = multi_gpu.shard_plan(idx.exon_ptr, idx.exon_start, idx.exon_end, idx.orf_contig, n)
+        assert np.array_equal(np.sort(np.concatenate([s.rows for s in plan])), np.arange(idx.n_orf))
+        per = np.array([cost[s.rows].sum() for s in plan])
+        assert per.max() <= cost.sum() / n + cost.max()
+        assert sum(len(s.runs) for s in plan) <= 16 * n
+        for s in plan:
+            assert sum(hi - lo for lo, hi, _ in s.runs) == len(s.rows)
+            assert all(np.array_equal(s.rows[r:r + hi - lo], np.arange(lo, hi)) for lo, hi, r in s.runs)
+            sub = multi_gpu.sub_index(idx.as_dict(), s.rows)
+            assert np.array_equal(np.diff(sub["exon_ptr"]), np.diff(idx.exon_ptr)[s.rows])
+            # brute force: reads that can put a P-site (5' end +- 13) on an exon position of this block
+            off = 13
+            slices = multi_gpu.read_slices(reads["ref_id"], reads["first"], reads["last"], s.spans, off)
+            taken = np.zeros(len(reads["first"]), bool)
+            for a, b in slices:
+                taken[a:b] = True
+            for c, lo, hi in s.spans:
+                m = reads["ref_id"] == c
+                p_first, p_last = reads["first"].astype(np.int64) + 1, reads["last"].astype(np.int64) + 1   # 1-based 5' ends
+                near = m & (((p_first >= lo - off) & (p_first <= hi + off)) | ((p_last >= lo - off) & (p_last <= hi + off)))
+                assert taken[near].all()
+        if n == 8:
+            assert sum(t.sum() for t in [taken]) < len(taken)       # a block does not pull the whole library
+    perm = np.random.default_rng(3).permutation(idx.n_orf)          # an index in random order: contiguous row ranges
+    shuffled = multi_gpu.sub_index(idx.as_dict(), perm)
+    plan = multi_gpu.shard_plan(shuffled["exon_ptr"], shuffled["exon_start"], shuffled["exon_end"], shuffled["orf_contig"], 4,
+                                max_runs_per_shard=8)
+    assert all(len(s.runs) <= 1 for s in plan) and sum(len(s.rows) for s in plan) == idx.n_orf
