@@ -5,11 +5,18 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <thread>
 #include <vector>
 
 #include "rt_kernels.cuh"
+
+// rt_host_io.cpp: filter cascade + run-length code of ref_id for one chunk of host columns
+int64_t rt_pack_chunk(const int32_t* ref_id, const uint16_t* flag, const uint8_t* mapq, const uint8_t* nh, int64_t m, uint8_t* meta,
+                      int64_t* run_start, int32_t* run_ref, int64_t cap);
 
 namespace {
 
@@ -122,9 +129,10 @@ struct rt_ctx {
         int32_t* run_ref = nullptr;
         cudaEvent_t copied = nullptr;
         bool busy = false;
-    } host_stage[2];
-    DevBuf read_slot[2];
-    cudaStream_t slot_stream[2] = {nullptr, nullptr};
+    } host_stage[16];
+    std::mutex launch_mutex;                         // the packing threads of rt_bin_reads_host launch K1 one at a time
+    DevBuf read_slot[16];
+    cudaStream_t slot_stream[16] = {};
     DevBuf stats_buf, score_buf;
 
     // sparse clear: slots touched by K1 since the last rt_clear_touched
@@ -296,45 +304,9 @@ constexpr size_t kReadBytes = 4 + 4 + 4 + 2 + 2 + 1 + 1;
 constexpr size_t kPackedReadBytes = 4 + 4 + 2 + 1;
 constexpr int64_t kHostChunkReads = 4 << 20;
 constexpr int64_t kChunkRunCap = 4096;            // reference runs per chunk of a library that is grouped by reference
+constexpr int64_t kPackChunkReads = 1 << 20;      // reads per chunk of the packing pipelines
+constexpr int64_t kMaxPipes = 16;
 
-// bam.py:77-91 + common.py:33-69 on the host for reads [0, m) of a chunk (same order as classify_read() in
-// rt_kernels.cuh) and the run-length code of ref_id, by several threads.  Returns the number of runs, or -1 when
-// there are more than `cap` (the chunk is not grouped by reference).
-int64_t pack_chunk(const int32_t* ref_id, const uint16_t* flag, const uint8_t* mapq, const uint8_t* nh, int64_t m, uint8_t* meta,
-                   int64_t* run_start, int32_t* run_ref, int64_t cap, int n_threads) {
-    n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, m / (1 << 16)));
-    std::vector<std::vector<int64_t>> starts((size_t)n_threads);
-    auto work = [&](int t) {
-        const int64_t a = m * t / n_threads, b = m * (t + 1) / n_threads;
-        for (int64_t i = a; i < b; ++i) {
-            const unsigned f = flag[i];
-            unsigned code;
-            if (f & 0x200) code = RT_ST_QCFAIL;
-            else if (f & 0x400) code = RT_ST_DUPLICATE;
-            else if (f & 0x100) code = RT_ST_SECONDARY;
-            else if (f & 0x4) code = RT_ST_UNMAPPED;
-            else code = (nh[i] != 0 ? nh[i] == 1 : mapq[i] == 255) ? 0u : (unsigned)RT_ST_MULTI;
-            meta[i] = (uint8_t)(code | ((f & 0x10) ? 8u : 0u));
-            if (i == 0 || ref_id[i] != ref_id[i - 1]) {
-                if ((int64_t)starts[t].size() <= cap) starts[t].push_back(i);
-            }
-        }
-    };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
-    work(0);
-    for (auto& th : pool) th.join();
-    int64_t r = 0;
-    for (int t = 0; t < n_threads; ++t)
-        for (int64_t i : starts[t]) {
-            if (r >= cap) return -1;
-            run_start[r] = i;
-            run_ref[r] = ref_id[i];
-            ++r;
-        }
-    run_start[r] = m;
-    return r;
-}
 
 }  // namespace
 
@@ -435,7 +407,7 @@ void rt_destroy(rt_ctx* ctx) {
         cudaFree(p.d_ref_warps);
         cudaFree(p.d_long_acc);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 16; ++s) {
         if (ctx->host_stage[s].meta) cudaFreeHost(ctx->host_stage[s].meta);
         if (ctx->host_stage[s].run_start) cudaFreeHost(ctx->host_stage[s].run_start);
         if (ctx->host_stage[s].run_ref) cudaFreeHost(ctx->host_stage[s].run_ref);
@@ -693,30 +665,36 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
         int rc = ensure_touched_capacity(ctx, ctx->touched_reserved + n);
         if (rc != RT_OK) return rc;
     }
-    const int64_t chunk = std::min<int64_t>(kHostChunkReads, std::max<int64_t>(n, 1));
-    // Host columns are the 18 B/read a BAM decoder produces.  With `sorted_hint` (reads grouped by reference) every
-    // chunk is turned into 11 B/read packed records on the way: while chunk k is on the wire, host threads evaluate
-    // the filter cascade of chunk k+1 into one meta byte per read and run-length code its ref_id into a page-locked
-    // staging slot; first / last / mlen are copied straight from the caller's columns.  A chunk with too many
-    // reference runs (not grouped after all) is sent as plain columns.
-    const int n_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
-    if (sorted_hint)
-        for (int s = 0; s < 2; ++s) {
-            rt_ctx::HostStage& hs = ctx->host_stage[s];
-            if (!hs.meta) {
-                RT_CUDA(ctx, cudaHostAlloc(&hs.meta, (size_t)kHostChunkReads, cudaHostAllocDefault));
-                RT_CUDA(ctx, cudaHostAlloc(&hs.run_start, sizeof(int64_t) * (kChunkRunCap + 1), cudaHostAllocDefault));
-                RT_CUDA(ctx, cudaHostAlloc(&hs.run_ref, sizeof(int32_t) * kChunkRunCap, cudaHostAllocDefault));
-                RT_CUDA(ctx, cudaEventCreateWithFlags(&hs.copied, cudaEventDisableTiming));
-            }
-        }
-    // per-slot layout: 4-byte columns first so that every column stays naturally aligned
+    // Host columns are the 18 B/read a BAM decoder produces.  With `sorted_hint` (reads grouped by reference) they cross
+    // PCIe as 11 B/read packed records: a few pipeline threads each take the next chunk of the library, evaluate its
+    // filter cascade into one meta byte per read and run-length code its ref_id into their own page-locked staging
+    // slot, start the copies (first / last / mlen straight from the caller's columns) on their own stream and launch
+    // K1 behind them -- so the packing of some chunks, the copies of others and the kernels of yet others overlap.
+    // A chunk with too many reference runs (not grouped after all) is sent as plain columns.
+    const int64_t chunk = sorted_hint ? std::min<int64_t>(kPackChunkReads, std::max<int64_t>(n, 1))
+                                      : std::min<int64_t>(kHostChunkReads, std::max<int64_t>(n, 1));
+    const int64_t n_chunks = (n + chunk - 1) / chunk;
+    const int n_pipes = sorted_hint ? (int)std::max<int64_t>(1, std::min<int64_t>({kMaxPipes, (int64_t)std::thread::hardware_concurrency() / 2, n_chunks})) : 2;
+    // per-slot layout: 8-byte run table first, then the 4-byte columns, so that every column stays naturally aligned
     const size_t slot_bytes = (size_t)chunk * kReadBytes + sizeof(int64_t) * (kChunkRunCap + 1) + sizeof(int32_t) * kChunkRunCap + 64;
-    int slot = 0;
-    for (int64_t at = 0; at < n; at += chunk, slot ^= 1) {
-        const int64_t m = std::min(chunk, n - at);
-        RT_CUDA(ctx, ctx->read_slot[slot].reserve(slot_bytes));
-        char* base = static_cast<char*>(ctx->read_slot[slot].p);
+    for (int s = 0; s < n_pipes; ++s) {
+        if (!ctx->slot_stream[s]) RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking));
+        RT_CUDA(ctx, ctx->read_slot[s].reserve(slot_bytes));
+        rt_ctx::HostStage& hs = ctx->host_stage[s];
+        if (sorted_hint && !hs.meta) {
+            RT_CUDA(ctx, cudaHostAlloc(&hs.meta, (size_t)kPackChunkReads, cudaHostAllocDefault));
+            RT_CUDA(ctx, cudaHostAlloc(&hs.run_start, sizeof(int64_t) * (kChunkRunCap + 1), cudaHostAllocDefault));
+            RT_CUDA(ctx, cudaHostAlloc(&hs.run_ref, sizeof(int32_t) * kChunkRunCap, cudaHostAllocDefault));
+            RT_CUDA(ctx, cudaEventCreateWithFlags(&hs.copied, cudaEventDisableTiming));
+        }
+        hs.busy = false;
+    }
+    std::atomic<int64_t> next_chunk{0};
+    std::atomic<int> status{RT_OK};
+    std::string first_error;
+    auto pipeline = [&](int s) {
+        cudaSetDevice(ctx->device);
+        char* base = static_cast<char*>(ctx->read_slot[s].p);
         int64_t* d_run_start = reinterpret_cast<int64_t*>(base);
         int32_t* d_ref = reinterpret_cast<int32_t*>(d_run_start + kChunkRunCap + 1);
         int32_t* d_first = d_ref + chunk;
@@ -727,40 +705,67 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
         uint8_t* d_mapq = reinterpret_cast<uint8_t*>(d_flag + chunk);
         uint8_t* d_nh = d_mapq + chunk;
         uint8_t* d_meta = d_mapq;                   // a chunk is either packed (meta) or plain (mapq, nh)
-        cudaStream_t st = ctx->slot_stream[slot];   // stream order protects the slot's previous use
-        int64_t runs = -1;
-        rt_ctx::HostStage& hs = ctx->host_stage[slot];
-        if (sorted_hint) {
-            if (hs.busy) RT_CUDA(ctx, cudaEventSynchronize(hs.copied));     // the staging slot's previous copies are done
-            hs.busy = false;
-            runs = pack_chunk(h_ref_id + at, h_flag + at, h_mapq + at, h_nh + at, m, hs.meta, hs.run_start, hs.run_ref,
-                              kChunkRunCap, n_threads);
+        cudaStream_t st = ctx->slot_stream[s];      // stream order protects the device slot's previous use
+        rt_ctx::HostStage& hs = ctx->host_stage[s];
+        auto check = [&](cudaError_t e, const char* what) {
+            if (e == cudaSuccess) return true;
+            std::lock_guard<std::mutex> lock(ctx->launch_mutex);
+            if (status.exchange(RT_ECUDA) == RT_OK) first_error = std::string(what) + ": " + cudaGetErrorString(e);
+            return false;
+        };
+        for (;;) {
+            const int64_t c = next_chunk.fetch_add(1);
+            if (c >= n_chunks || status.load() != RT_OK) break;
+            const int64_t at = c * chunk, m = std::min(chunk, n - at);
+            int64_t runs = -1;
+            if (sorted_hint) {
+                if (hs.busy && !check(cudaEventSynchronize(hs.copied), "cudaEventSynchronize")) break;   // staging slot free again
+                hs.busy = false;
+                runs = rt_pack_chunk(h_ref_id + at, h_flag + at, h_mapq + at, h_nh + at, m, hs.meta, hs.run_start, hs.run_ref, kChunkRunCap);
+            }
+            if (!check(cudaMemcpyAsync(d_first, h_first + at, 4 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+                !check(cudaMemcpyAsync(d_last, h_last + at, 4 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+                !check(cudaMemcpyAsync(d_mlen, h_mlen + at, 2 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync"))
+                break;
+            int rc;
+            if (runs >= 0) {
+                if (!check(cudaMemcpyAsync(d_meta, hs.meta, m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+                    !check(cudaMemcpyAsync(d_run_start, hs.run_start, sizeof(int64_t) * (size_t)(runs + 1), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+                    !check(cudaMemcpyAsync(d_run_ref, hs.run_ref, sizeof(int32_t) * (size_t)runs, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+                    !check(cudaEventRecord(hs.copied, st), "cudaEventRecord"))
+                    break;
+                hs.busy = true;
+                std::lock_guard<std::mutex> lock(ctx->launch_mutex);
+                rc = rt_bin_reads_packed(ctx, d_cov, m, d_first, d_last, d_mlen, d_meta, 0, runs, d_run_start, d_run_ref, protocol, 1,
+                                         d_stats, d_len_counts, st);
+            } else {
+                if (!check(cudaMemcpyAsync(d_ref, h_ref_id + at, 4 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+                    !check(cudaMemcpyAsync(d_flag, h_flag + at, 2 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+                    !check(cudaMemcpyAsync(d_mapq, h_mapq + at, m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+                    !check(cudaMemcpyAsync(d_nh, h_nh + at, m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync"))
+                    break;
+                std::lock_guard<std::mutex> lock(ctx->launch_mutex);
+                rc = rt_bin_reads(ctx, d_cov, m, d_ref, d_first, d_last, d_mlen, d_flag, d_mapq, d_nh, protocol, sorted_hint, 1,
+                                  d_stats, d_len_counts, st);
+            }
+            if (rc != RT_OK) {
+                int expected = RT_OK;
+                status.compare_exchange_strong(expected, rc);
+                break;
+            }
         }
-        RT_CUDA(ctx, cudaMemcpyAsync(d_first, h_first + at, 4 * m, cudaMemcpyHostToDevice, st));
-        RT_CUDA(ctx, cudaMemcpyAsync(d_last, h_last + at, 4 * m, cudaMemcpyHostToDevice, st));
-        RT_CUDA(ctx, cudaMemcpyAsync(d_mlen, h_mlen + at, 2 * m, cudaMemcpyHostToDevice, st));
-        int rc;
-        if (runs >= 0) {
-            RT_CUDA(ctx, cudaMemcpyAsync(d_meta, hs.meta, m, cudaMemcpyHostToDevice, st));
-            RT_CUDA(ctx, cudaMemcpyAsync(d_run_start, hs.run_start, sizeof(int64_t) * (size_t)(runs + 1), cudaMemcpyHostToDevice, st));
-            RT_CUDA(ctx, cudaMemcpyAsync(d_run_ref, hs.run_ref, sizeof(int32_t) * (size_t)runs, cudaMemcpyHostToDevice, st));
-            RT_CUDA(ctx, cudaEventRecord(hs.copied, st));
-            hs.busy = true;
-            rc = rt_bin_reads_packed(ctx, d_cov, m, d_first, d_last, d_mlen, d_meta, 0, runs, d_run_start, d_run_ref, protocol, 1,
-                                     d_stats, d_len_counts, st);
-        } else {
-            RT_CUDA(ctx, cudaMemcpyAsync(d_ref, h_ref_id + at, 4 * m, cudaMemcpyHostToDevice, st));
-            RT_CUDA(ctx, cudaMemcpyAsync(d_flag, h_flag + at, 2 * m, cudaMemcpyHostToDevice, st));
-            RT_CUDA(ctx, cudaMemcpyAsync(d_mapq, h_mapq + at, m, cudaMemcpyHostToDevice, st));
-            RT_CUDA(ctx, cudaMemcpyAsync(d_nh, h_nh + at, m, cudaMemcpyHostToDevice, st));
-            rc = rt_bin_reads(ctx, d_cov, m, d_ref, d_first, d_last, d_mlen, d_flag, d_mapq, d_nh, protocol, sorted_hint, 1,
-                              d_stats, d_len_counts, st);
-        }
-        if (rc != RT_OK) return rc;
+    };
+    {
+        std::vector<std::thread> pipes;
+        for (int s = 1; s < n_pipes; ++s) pipes.emplace_back(pipeline, s);
+        pipeline(0);
+        for (auto& th : pipes) th.join();
     }
-    RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[0]));
-    RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[1]));
-    ctx->host_stage[0].busy = ctx->host_stage[1].busy = false;
+    if (status.load() != RT_OK) return first_error.empty() ? status.load() : fail(ctx, status.load(), "rt_bin_reads_host: %s", first_error.c_str());
+    for (int s = 0; s < n_pipes; ++s) {
+        RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+        ctx->host_stage[s].busy = false;
+    }
     RT_CUDA(ctx, cudaMemcpy(h_stats, d_stats, sizeof(int64_t) * RT_N_STATS, cudaMemcpyDeviceToHost));
     RT_CUDA(ctx, cudaMemcpy(h_len_counts, d_len_counts, sizeof(int64_t) * RT_LEN_TABLE, cudaMemcpyDeviceToHost));
     return RT_OK;
@@ -1123,38 +1128,116 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
         if (!alist.empty())
             RT_CUDA(ctx, cudaMemcpy(p.d_atom_list, alist.data(), sizeof(int32_t) * alist.size(), cudaMemcpyHostToDevice));
     }
-    if (ctx->use_atoms) {   // phase B work list: the atom references of the range in index order, in groups of 32 slots
+    if (ctx->use_atoms) {
+        // Phase B work list.  FAMILIES: candidate ORFs of one transcript that share their stop are suffixes of the
+        // longest one -- same atoms from some reference on (the index is cut into atoms at every ORF start).  The
+        // longest ORF of a family (the parent) lays its references out, one per slot; an ORF whose reference list is a
+        // proper suffix of it (a child) is just marked on the slot where it starts.  compose_refs_kernel forms
+        // suffix sums over the parent's slots, so every reference is visited once per family instead of once per ORF.
+        // Families never straddle a group of 32 slots; ORFs with more than 32 references stay alone and fill whole groups.
         std::vector<rt::RefRec> refs;
         std::vector<rt::RefWarp> warps;
-        refs.reserve((size_t)(ctx->h_ref_ent.size() / std::max<int64_t>(1, ctx->n_orf) * n * 9 / 8 + 64));
+        refs.reserve((size_t)(ctx->h_ref_ent.size() / std::max<int64_t>(1, ctx->n_orf) * n * 3 / 4 + 64));
         const rt::RefRec pad_rec{0xffffffffu, 0u, 0u, -1};
         int n_long = 0;
         auto pad_group = [&]() {
             while (refs.size() % 32) refs.push_back(pad_rec);
-            warps.resize(refs.size() / 32, rt::RefWarp{-1, 0});
+            warps.resize(refs.size() / 32, rt::RefWarp{-1, 0, -1, 0});
         };
-        for (int64_t o = lo; o < hi; ++o) {
+        auto desc_of = [&](int64_t o, uint64_t& rb, uint64_t& cnt, uint32_t& rev) {
             const uint64_t d = ctx->h_orf_refs_desc[o];
-            const uint64_t rb = d & rt::kBeginMask, cnt = (d >> 40) & (uint64_t)rt::kMaxEntriesPerOrf;
-            const uint32_t rev = (uint32_t)(d >> 63);
+            rb = d & rt::kBeginMask;
+            cnt = (d >> 40) & (uint64_t)rt::kMaxEntriesPerOrf;
+            rev = (uint32_t)(d >> 63);
+        };
+        // hash of a reference list, powers counted from its END, so that the hash of a suffix of a parent equals the
+        // hash of the child that is that suffix
+        const uint64_t kB = 0x9E3779B97F4A7C15ull;
+        auto elem = [&](uint64_t k) {
+            uint64_t x = ((uint64_t)ctx->h_ref_atom[k] << 25) ^ (ctx->h_ref_ent[k] & rt::kLenMask);
+            x ^= x >> 31; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 29;
+            return x | 1ull;
+        };
+        std::vector<uint64_t> full_hash((size_t)n);
+        std::unordered_multimap<uint64_t, int64_t> by_hash;
+        by_hash.reserve((size_t)n * 2);
+        for (int64_t o = lo; o < hi; ++o) {
+            uint64_t rb, cnt; uint32_t rev;
+            desc_of(o, rb, cnt, rev);
+            uint64_t h = rev ? 0x5bd1e995ull : 0x1b873593ull, pw = 1;
+            for (uint64_t k = cnt; k-- > 0;) { h += elem(rb + k) * pw; pw *= kB; }
+            full_hash[o - lo] = h;
+            if (cnt >= 1 && cnt <= 31) by_hash.emplace(h, o);          // a child has at most 31 references
+        }
+        std::vector<int32_t> parent_of((size_t)n, -1);                   // -1: not a child
+        std::vector<int64_t> order((size_t)n);
+        for (int64_t i = 0; i < n; ++i) order[i] = lo + i;
+        auto refs_of = [&](int64_t o) { return (ctx->h_orf_refs_desc[o] >> 40) & (uint64_t)rt::kMaxEntriesPerOrf; };
+        std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return refs_of(x) > refs_of(y); });
+        // children[o - lo]: (position in the parent's list, child ORF)
+        std::vector<std::vector<std::pair<int, int64_t>>> children((size_t)n);
+        for (int64_t o : order) {
+            if (parent_of[o - lo] >= 0) continue;
+            uint64_t rb, cnt; uint32_t rev;
+            desc_of(o, rb, cnt, rev);
+            if (cnt < 2 || cnt > 32) continue;
+            uint64_t h = rev ? 0x5bd1e995ull : 0x1b873593ull, pw = 1;
+            for (uint64_t k = cnt; k-- > 1;) {                           // proper suffixes starting at k = cnt-1 .. 1
+                h += elem(rb + k) * pw;
+                pw *= kB;
+                auto range = by_hash.equal_range(h);
+                for (auto it = range.first; it != range.second; ++it) {
+                    const int64_t c = it->second;
+                    if (c == o || parent_of[c - lo] >= 0 || !children[c - lo].empty()) continue;
+                    uint64_t crb, ccnt; uint32_t crev;
+                    desc_of(c, crb, ccnt, crev);
+                    if (crev != rev || ccnt != cnt - k) continue;
+                    // a child's first reference must hold two values: then every seam window of the references after it
+                    // starts inside the child (with one value, the window two before the next reference would not)
+                    if ((ctx->h_ref_ent[crb] & rt::kLenMask) < 2) continue;
+                    bool same = true;
+                    for (uint64_t j = 0; j < ccnt && same; ++j)
+                        same = ctx->h_ref_atom[crb + j] == ctx->h_ref_atom[rb + k + j] &&
+                               (ctx->h_ref_ent[crb + j] & rt::kLenMask) == (ctx->h_ref_ent[rb + k + j] & rt::kLenMask);
+                    if (!same) continue;
+                    parent_of[c - lo] = (int32_t)(o - lo);
+                    children[o - lo].push_back({(int)k, c});
+                    break;                                               // one ORF per starting slot
+                }
+            }
+        }
+        for (int64_t o = lo; o < hi; ++o) {
+            if (parent_of[o - lo] >= 0) continue;                        // laid out with its parent
+            uint64_t rb, cnt; uint32_t rev;
+            desc_of(o, rb, cnt, rev);
             if (cnt > 32 || refs.size() % 32 + std::max<uint64_t>(cnt, 1) > 32) pad_group();
-            const size_t w0 = refs.size() / 32;
+            const size_t w0 = refs.size() / 32, first_slot = refs.size();
             uint64_t P = 0;
             const uint64_t L = (uint64_t)(ctx->nt_prefix[o + 1] - ctx->nt_prefix[o]);
-            auto flags_of = [&](uint64_t len) -> uint32_t {
+            auto flags_of = [&](uint64_t len, uint64_t l_mod3) -> uint32_t {
                 return ((uint32_t)(P % 3) << rt::kRefPmod3Shift) | (P >= 1 ? rt::kRefPge1 : 0u) | (P >= 2 ? rt::kRefPge2 : 0u) |
-                       (P + len == L ? rt::kRefLast : 0u) | ((uint32_t)(L % 3) << rt::kRefLmod3Shift) | (rev ? rt::kRefRev : 0u);
+                       (P + len == L ? rt::kRefLast : 0u) | ((uint32_t)l_mod3 << rt::kRefLmod3Shift) | (rev ? rt::kRefRev : 0u);
             };
             for (uint64_t k = 0; k < cnt; ++k) {
                 const uint32_t len = (uint32_t)(ctx->h_ref_ent[rb + k] & rt::kLenMask);
-                refs.push_back({ctx->h_ref_atom[rb + k], len | flags_of(len), (uint32_t)((len + P) % 3), (int32_t)o});
+                // L mod 3 of the ORF that starts on this slot; a long ORF carries its own on every slot (its last
+                // group applies the trailing partial codon itself)
+                const uint64_t lm3 = (k == 0 || cnt > 32) ? L % 3 : 0;
+                refs.push_back({ctx->h_ref_atom[rb + k], len | flags_of(len, lm3), (uint32_t)((len + P) % 3) | (k == 0 ? rt::kRefFamilyHead : 0u),
+                                k == 0 ? (int32_t)o : -2});
                 P += len;
             }
-            if (cnt == 0) refs.push_back({0xffffffffu, flags_of(0), 0u, (int32_t)o});   // an ORF without intervals still gets its row
+            if (cnt == 0) refs.push_back({0xffffffffu, flags_of(0, L % 3), rt::kRefFamilyHead, (int32_t)o});   // an ORF without intervals still gets its row
+            for (const auto& ch : children[o - lo]) {
+                rt::RefRec& r = refs[first_slot + (size_t)ch.first];
+                const uint64_t Lc = (uint64_t)(ctx->nt_prefix[ch.second + 1] - ctx->nt_prefix[ch.second]);
+                r.orf = (int32_t)ch.second;
+                r.len_flags = (r.len_flags & ~(3u << rt::kRefLmod3Shift)) | ((uint32_t)(Lc % 3) << rt::kRefLmod3Shift);
+            }
             if (cnt > 32) {
                 pad_group();
                 const int groups = (int)(refs.size() / 32 - w0);
-                for (size_t g = w0; g < warps.size(); ++g) warps[g] = rt::RefWarp{n_long, groups};
+                for (size_t g = w0; g < warps.size(); ++g) warps[g] = rt::RefWarp{n_long, groups, (int32_t)o, 0};
                 ++n_long;
             }
         }
@@ -1314,7 +1397,10 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
             ra.long_acc = plan->d_long_acc;
             ra.prm = *params;
             ra.out = *d_out;
-            if (ra.n_warps > 0) rt::compose_refs_kernel<<<(unsigned)((ra.n_warps + 7) / 8), 256, 0, st>>>(ra);
+            if (ra.n_warps > 0) {
+                if (ra.want_min) rt::compose_refs_kernel<true><<<(unsigned)((ra.n_warps + 7) / 8), 256, 0, st>>>(ra);
+                else rt::compose_refs_kernel<false><<<(unsigned)((ra.n_warps + 7) / 8), 256, 0, st>>>(ra);
+            }
         } else {
             rt::score_from_atoms_kernel<<<(unsigned)((ca.n_segs + ca.n_list + 255) / 256), 256, 0, st>>>(ca);
         }

@@ -376,6 +376,50 @@ int rt_wig_close(rt_tsv* t) { return rt_tsv_close(t); }
 // ---- packed read records (11 B/read instead of 18): the filter cascade is decided here, on the host ----
 #include <thread>
 
+// bam.py:77-91 + common.py:33-69 for reads [0, m) of a chunk (same order as classify_read() in rt_kernels.cuh: the
+// EARLIER test wins, so the selects run from the last test to the first) and the run-length code of ref_id.  One
+// thread; branch-free and in blocks so that the compiler vectorises both loops (an AVX2 clone is picked at load time).
+// Returns the number of runs, or -1 when there are more than `cap` (the chunk is not grouped by reference).
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("avx2", "default")))
+#endif
+int64_t rt_pack_chunk(const int32_t* __restrict__ ref_id, const uint16_t* __restrict__ flag, const uint8_t* __restrict__ mapq,
+                      const uint8_t* __restrict__ nh, int64_t m, uint8_t* __restrict__ meta, int64_t* run_start, int32_t* run_ref,
+                      int64_t cap) {
+    for (int64_t i = 0; i < m; ++i) {
+        const unsigned f = flag[i];
+        const unsigned uniq = nh[i] != 0 ? (nh[i] == 1) : (mapq[i] == 255);
+        unsigned code = uniq ? 0u : (unsigned)RT_ST_MULTI;
+        code = (f & 0x4) ? (unsigned)RT_ST_UNMAPPED : code;
+        code = (f & 0x100) ? (unsigned)RT_ST_SECONDARY : code;
+        code = (f & 0x400) ? (unsigned)RT_ST_DUPLICATE : code;
+        code = (f & 0x200) ? (unsigned)RT_ST_QCFAIL : code;
+        meta[i] = (uint8_t)(code | ((f >> 1) & 8u));
+    }
+    int64_t r = 0;
+    if (m > 0) {
+        run_start[0] = 0;
+        run_ref[0] = ref_id[0];
+        r = 1;
+    }
+    constexpr int64_t kBlock = 256;
+    for (int64_t b = 1; b < m; b += kBlock) {
+        const int64_t e = b + kBlock < m ? b + kBlock : m;
+        int32_t diff = 0;
+        for (int64_t i = b; i < e; ++i) diff |= ref_id[i] ^ ref_id[i - 1];
+        if (diff == 0) continue;                    // the usual case: no reference changes inside the block
+        for (int64_t i = b; i < e; ++i)
+            if (ref_id[i] != ref_id[i - 1]) {
+                if (r >= cap) return -1;
+                run_start[r] = i;
+                run_ref[r] = ref_id[i];
+                ++r;
+            }
+    }
+    run_start[r] = m;
+    return r;
+}
+
 extern "C" {
 
 int rt_pack_read_meta(int64_t n, const int32_t* ref_id, const uint16_t* flag, const uint8_t* mapq, const uint8_t* nh,

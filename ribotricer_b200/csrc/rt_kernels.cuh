@@ -1671,31 +1671,39 @@ __global__ void __launch_bounds__(256) score_from_atoms_kernel(const ComposeArgs
     finish_orf(args, orf, L, K, U, RE, IM, mn, count);
 }
 
-// ---- phase B, one lane per atom reference: compose_refs_kernel ---------------------------------------
-// The host lays the atom references of the requested ORFs out in index order, 16 bytes each, with the profile
-// offset of every reference precomputed, and pads so that an ORF of up to 32 references never straddles a group of
-// 32 slots.  A warp takes one group: every lane loads its reference and the summary of its atom (coalesced /
-// independent loads, no serial walk), turns the summary into sums by PROFILE frame, rebuilds the two windows that
-// straddle the seam with the reference before it from the edge values of the neighbouring lanes, and the lanes of
-// an ORF are added up by a segmented shuffle reduction -- the sums are 64-bit integers (uv_grid), so the order of
-// summation is immaterial.  ORFs with more than 32 references fill whole groups; each group adds its sums to the
-// ORF's accumulator with integer atomics and the group that arrives last scores the ORF.
+// ---- phase B, one lane per atom reference of a FAMILY of ORFs: compose_refs_kernel ------------------------
+// Candidate ORFs that share their stop (nested ORFs of a transcript) are suffixes of the longest one: from some
+// reference on they consist of the same atoms.  The host groups such ORFs into families and lays the references of
+// the longest member (the parent) out, 16 bytes each, with everything the kernel needs of the reference's profile
+// offset precomputed, padded so that a family never straddles a group of 32 slots.  A warp takes one group: every
+// lane loads its reference and the summary of its atom (coalesced / independent loads, no serial walk), turns the
+// summary into sums by the PARENT's profile frames and rebuilds the two windows that straddle the seam with the
+// reference before it from the edge values of the neighbouring lanes.  A segmented SUFFIX scan over the lanes of a
+// family then gives, on every lane, the sums from that reference to the end -- the sums are 64-bit integers
+// (uv_grid), so the order of summation is immaterial and a suffix sum can lose its own seam windows again by
+// subtraction.  Every lane on which an ORF starts (the parent on the first, a child anywhere) rotates the sums into
+// that ORF's frames and scores it: a reference is visited once per family, not once per ORF.  ORFs with more than 32
+// references stay alone and fill whole groups; each group adds its sums to the ORF's accumulator with integer
+// atomics and the group that arrives last scores the ORF.
 struct RefRec {                        // 16 bytes
     uint32_t atom;                     // atom id; 0xffffffff: a stretch that reads as zeros
     uint32_t len_flags;                // values of the reference (24 bits) and what the kernel needs of its profile offset P and
                                        //   of the ORF's length L, precomputed: see kRef* below
-    uint32_t aux;                      // (len + P) mod 3
-    int32_t orf;                       // absolute ORF id; -1: padding
+    uint32_t aux;                      // (len + P) mod 3 | kRefFamilyHead on the first reference of a family
+    int32_t orf;                       // the ORF that STARTS on this reference (absolute id); -2: none; -1: padding slot
 };
+constexpr uint32_t kRefFamilyHead = 1u << 2;
 constexpr uint32_t kRefLenMask = (1u << 24) - 1u;
 constexpr int kRefPmod3Shift = 24;     // 2 bits: P mod 3
 constexpr uint32_t kRefPge1 = 1u << 26, kRefPge2 = 1u << 27;
 constexpr uint32_t kRefLast = 1u << 28;    // P + len == L
-constexpr int kRefLmod3Shift = 29;     // 2 bits: L mod 3
+constexpr int kRefLmod3Shift = 29;     // 2 bits: L mod 3 of the ORF that starts here (of the ORF itself on every slot of a long one)
 constexpr uint32_t kRefRev = 1u << 31;     // ORF on the '-' strand
 struct RefWarp {                       // per group of 32 slots
     int32_t long_idx;                  // >= 0: the group belongs to long ORF number long_idx (more than 32 references)
     int32_t n_groups;                  //        ... which spans this many groups
+    int32_t orf;                       //        ... its absolute id
+    int32_t pad;
 };
 struct LongAcc {                       // accumulator of one long ORF; all-zero except mn = 0xffffffff between launches
     unsigned long long RE[3], IM[3];
@@ -1782,21 +1790,26 @@ __device__ __forceinline__ void finish_orf_lean(const Args& args, int orf, int L
     }
 }
 
-__global__ void __launch_bounds__(256) compose_refs_kernel(const RefComposeArgs args) {
+#ifndef RT_COMPOSE_MINBLOCKS
+#define RT_COMPOSE_MINBLOCKS 4
+#endif
+template <bool WantMin>
+__global__ void __launch_bounds__(256, RT_COMPOSE_MINBLOCKS) compose_refs_kernel(const RefComposeArgs args) {
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= args.n_warps) return;
     const int lane = threadIdx.x & 31;
     const long long slot = w * 32 + lane;
     const uint4 rr = __ldg(reinterpret_cast<const uint4*>(args.refs) + slot);
     const RefWarp rw = args.warps[w];
-    const int orf = (int)rr.w;
-    const bool valid = orf >= 0;
+    const bool is_long = rw.long_idx >= 0;
+    const int orf = (int)rr.w;                                            // the ORF that starts here (>= 0), -2, or -1 = padding
+    const bool valid = orf != -1;
     const unsigned atom = rr.x;
     const int len = (int)(rr.y & kRefLenMask);
     const bool rev = (rr.y & kRefRev) != 0;
-    const int pm3 = (int)((rr.y >> kRefPmod3Shift) & 3u);                 // P mod 3
+    const int pm3 = (int)((rr.y >> kRefPmod3Shift) & 3u);                 // P mod 3 (P: offset in the parent's profile)
     const bool p_ge1 = (rr.y & kRefPge1) != 0, p_ge2 = (rr.y & kRefPge2) != 0, last = (rr.y & kRefLast) != 0;
-    const int lm3 = (int)((rr.y >> kRefLmod3Shift) & 3u);                 // L mod 3
+    const int lm3 = (int)((rr.y >> kRefLmod3Shift) & 3u);                 // L mod 3 of the ORF starting here
     // the summary is requested together with the atom's "holds a read" byte, not after it
     const bool has_atom = valid && atom != 0xffffffffu;
     const AtomSummary* s = args.summaries + (has_atom ? atom : 0u);
@@ -1810,13 +1823,14 @@ __global__ void __launch_bounds__(256) compose_refs_kernel(const RefComposeArgs 
         i12 = __ldg(reinterpret_cast<const longlong2*>(s) + 2);      // im[1], im[2]
         edge = __ldg(reinterpret_cast<const int4*>(s) + 3);
         ku = __ldg(reinterpret_cast<const uint4*>(s) + 4);           // kpack, upack, count
-        if (args.want_min) mc = __ldg(reinterpret_cast<const uint4*>(s) + 5);        // mn[0..2]
+        if (WantMin) mc = __ldg(reinterpret_cast<const uint4*>(s) + 5);               // mn[0..2]
     }
     constexpr long long kOne = 1ll << 42, kHalf = 1ll << 41;
 
+    // sums of this reference by the PARENT's profile frames: interior windows (from the summary) ...
     unsigned K[3] = {0, 0, 0}, U[3] = {0, 0, 0};
     long long RE[3] = {0, 0, 0}, IM[3] = {0, 0, 0};
-    unsigned mn = 0xffffffffu;
+    unsigned imn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};      // WantMin: minimum window sum by parent frame, interior
     long long count = 0;
     int ormask = 0;
     bool big = false;
@@ -1839,9 +1853,19 @@ __global__ void __launch_bounds__(256) compose_refs_kernel(const RefComposeArgs 
         RE[2] = sel3(p20, p21, r01.x, r01.y, r2i0.x); IM[2] = sel3(p20, p21, r2i0.y, i12.x, i12.y);
         K[0] = (ku.x >> (10 * i0)) & 1023u; K[1] = (ku.x >> (10 * i1)) & 1023u; K[2] = (ku.x >> (10 * i2)) & 1023u;
         U[0] = (ku.y >> (10 * i0)) & 1023u; U[1] = (ku.y >> (10 * i1)) & 1023u; U[2] = (ku.y >> (10 * i2)) & 1023u;
-        mn = sel3(p00, p01, mc.x, mc.y, mc.z);                           // minimum of the profile-frame-0 windows
-    } else if (valid && len >= 3 && (pm3 == 0 ? 0 : 3 - pm3) <= len - 3) {
-        mn = 0;     // a stretch without a read that holds a whole frame-0 codon
+        if (WantMin) {
+            imn[0] = sel3(p00, p01, mc.x, mc.y, mc.z);
+            imn[1] = sel3(p10, p11, mc.x, mc.y, mc.z);
+            imn[2] = sel3(p20, p21, mc.x, mc.y, mc.z);
+        }
+    } else if (WantMin && valid && len >= 3) {
+        // a stretch without a read: frame q has a whole codon inside it when its first window start, (q - P) mod 3
+        // values in, leaves room for three values
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int d = q - pm3, first = d < 0 ? d + 3 : d;
+            if (first <= len - 3) imn[q] = 0;
+        }
     }
 
     // ---- the last two profile values before this reference: from the lanes to the left ----
@@ -1866,16 +1890,23 @@ __global__ void __launch_bounds__(256) compose_refs_kernel(const RefComposeArgs 
             fetch_tail(slot - 2, d0, pp_z1, dl);
         }
     }
+    // ... and the two seam windows: the one that ENDS on the first value of this reference (profile position P - 2)
+    // and the one that ends on its second value (P - 1); statistics.py:72-90.  Kept apart: an ORF that STARTS on this
+    // reference does not have them.
+    unsigned sK[3] = {0, 0, 0}, sU[3] = {0, 0, 0};
+    long long sRE[3] = {0, 0, 0}, sIM[3] = {0, 0, 0};
+    unsigned smn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
     if (valid) {
-        // the two seam windows: the one that ENDS on the first value of this reference (profile position P - 2) and
-        // the one that ends on its second value (P - 1); statistics.py:72-90
         const int y = p_z1, x = p_len >= 2 ? p_z0 : pp_z1;
 #pragma unroll 1
         for (int k = 0; k < 2; ++k) {
             if (k == 0 ? !p_ge2 : !(len >= 2 && p_ge1)) continue;
             const int v0 = k == 0 ? x : y, v1 = k == 0 ? y : a0, v2 = k == 0 ? a0 : a1;
             const int f = k == 0 ? (pm3 == 2 ? 0 : pm3 + 1) : (pm3 == 0 ? 2 : pm3 - 1);     // (P - 2) mod 3, (P - 1) mod 3
-            if (f == 0) mn = min(mn, (unsigned)v0 + (unsigned)v1 + (unsigned)v2);
+            if (WantMin) {
+                const unsigned sum = (unsigned)v0 + (unsigned)v1 + (unsigned)v2;
+                if (f == 0) smn[0] = min(smn[0], sum); else if (f == 1) smn[1] = min(smn[1], sum); else smn[2] = min(smn[2], sum);
+            }
             if ((v0 | v1 | v2) == 0) continue;
             ormask |= v0 | v1 | v2;
             // '+'-oriented triple (a,b,c): the profile of a '-' ORF runs against the plane
@@ -1893,78 +1924,130 @@ __global__ void __launch_bounds__(256) compose_refs_kernel(const RefComposeArgs 
                 re = __double2ll_rn(u.x * kUvGridScale);
                 im = __double2ll_rn(u.y * kUvGridScale);
             }
-            if (f == 0) { K[0] += 1u; U[0] += uni; RE[0] += re; IM[0] += im; }
-            else if (f == 1) { K[1] += 1u; U[1] += uni; RE[1] += re; IM[1] += im; }
-            else { K[2] += 1u; U[2] += uni; RE[2] += re; IM[2] += im; }
+            if (f == 0) { sK[0] += 1u; sU[0] += uni; sRE[0] += re; sIM[0] += im; }
+            else if (f == 1) { sK[1] += 1u; sU[1] += uni; sRE[1] += re; sIM[1] += im; }
+            else { sK[2] += 1u; sU[2] += uni; sRE[2] += re; sIM[2] += im; }
         }
-        if (last) {
-            // last reference: trailing partial codon (common.py:177-179); the last L % 3 values are (tx,) ty
-            const int ty = len >= 1 ? z1 : p_z1, tx = len >= 2 ? z0 : (len == 1 ? (p_ge1 ? p_z1 : 0) : (p_len >= 2 ? p_z0 : pp_z1));
-            if (lm3 == 1) { mn = min(mn, (unsigned)ty); ormask |= ty; }
-            else if (lm3 == 2) { mn = min(mn, (unsigned)tx + (unsigned)ty); ormask |= tx | ty; }
-        }
+    }
+    // the last two values of the family's profile (the trailing partial codon of every member, common.py:177-179)
+    const int ty = len >= 1 ? z1 : p_z1, tx = len >= 2 ? z0 : (len == 1 ? (p_ge1 ? p_z1 : 0) : (p_len >= 2 ? p_z0 : pp_z1));
+    unsigned tail_mn = 0xffffffffu;
+    if (is_long && valid && last) {          // a long ORF: its last group settles the trailing partial codon itself
+        if (lm3 == 1) { tail_mn = (unsigned)ty; ormask |= ty; }
+        else if (lm3 == 2) { tail_mn = (unsigned)tx + (unsigned)ty; ormask |= tx | ty; }
     }
     big |= (ormask >> kBigShift) != 0;
 
-    // ---- add up the lanes of every ORF (consecutive lanes) ----
-    const int left_orf = __shfl_up_sync(kFull, orf, 1);
-    const unsigned heads = __ballot_sync(kFull, lane == 0 || orf != left_orf);
+    // ---- suffix sums over the lanes of every family (consecutive lanes) ----
+    const unsigned heads = __ballot_sync(kFull, lane == 0 || !valid || (rr.z & kRefFamilyHead) != 0);
     const unsigned after = lane == 31 ? 0u : heads >> (lane + 1);
-    const int end_lane = after ? lane + __ffs(after) : 32;              // lanes [.., end_lane) share my ORF
+    const int end_lane = after ? lane + __ffs(after) : 32;              // lanes [.., end_lane) belong to my family
     const bool head = ((heads >> lane) & 1u) != 0;
     const int max_run = (int)__reduce_max_sync(kFull, head ? (unsigned)(end_lane - lane) : 0u);
-    unsigned long long Kp = (unsigned long long)K[0] | ((unsigned long long)K[1] << 21) | ((unsigned long long)K[2] << 42);
-    unsigned long long Up = (unsigned long long)U[0] | ((unsigned long long)U[1] << 21) | ((unsigned long long)U[2] << 42);
+    long long TRE[3], TIM[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { TRE[q] = RE[q] + sRE[q]; TIM[q] = IM[q] + sIM[q]; }
+    unsigned long long Kp = (unsigned long long)(K[0] + sK[0]) | ((unsigned long long)(K[1] + sK[1]) << 21) | ((unsigned long long)(K[2] + sK[2]) << 42);
+    unsigned long long Up = (unsigned long long)(U[0] + sU[0]) | ((unsigned long long)(U[1] + sU[1]) << 21) | ((unsigned long long)(U[2] + sU[2]) << 42);
     unsigned flags = big ? 1u : 0u;
+    unsigned tmn[3] = {min(imn[0], smn[0]), min(imn[1], smn[1]), min(imn[2], smn[2])};
+    if (WantMin && is_long) tmn[0] = min(tmn[0], tail_mn);              // a long ORF is its own parent: frame 0 is frame 0
     for (int o = 1; o < max_run; o <<= 1) {
         const bool take = lane + o < end_lane;
-        const long long t0 = __shfl_down_sync(kFull, RE[0], o), t1 = __shfl_down_sync(kFull, RE[1], o);
-        const long long t2 = __shfl_down_sync(kFull, RE[2], o), t3 = __shfl_down_sync(kFull, IM[0], o);
-        const long long t4 = __shfl_down_sync(kFull, IM[1], o), t5 = __shfl_down_sync(kFull, IM[2], o);
+        const long long t0 = __shfl_down_sync(kFull, TRE[0], o), t1 = __shfl_down_sync(kFull, TRE[1], o);
+        const long long t2 = __shfl_down_sync(kFull, TRE[2], o), t3 = __shfl_down_sync(kFull, TIM[0], o);
+        const long long t4 = __shfl_down_sync(kFull, TIM[1], o), t5 = __shfl_down_sync(kFull, TIM[2], o);
         const unsigned long long tk = __shfl_down_sync(kFull, Kp, o), tu = __shfl_down_sync(kFull, Up, o);
         const long long tc = __shfl_down_sync(kFull, count, o);
-        const unsigned tm = __shfl_down_sync(kFull, mn, o), tf = __shfl_down_sync(kFull, flags, o);
+        const unsigned tf = __shfl_down_sync(kFull, flags, o);
         if (take) {
-            RE[0] += t0; RE[1] += t1; RE[2] += t2; IM[0] += t3; IM[1] += t4; IM[2] += t5;
-            Kp += tk; Up += tu; count += tc; mn = min(mn, tm); flags |= tf;
+            TRE[0] += t0; TRE[1] += t1; TRE[2] += t2; TIM[0] += t3; TIM[1] += t4; TIM[2] += t5;
+            Kp += tk; Up += tu; count += tc; flags |= tf;
+        }
+        if (WantMin) {
+            const unsigned m0 = __shfl_down_sync(kFull, tmn[0], o), m1 = __shfl_down_sync(kFull, tmn[1], o), m2 = __shfl_down_sync(kFull, tmn[2], o);
+            if (take) { tmn[0] = min(tmn[0], m0); tmn[1] = min(tmn[1], m1); tmn[2] = min(tmn[2], m2); }
         }
     }
-    if (!head || !valid) return;
-    const int L = __ldg(args.orf_len + orf);
+    // the family's last two values, for the members that start further left
+    const int f_tx = __shfl_sync(kFull, tx, end_lane - 1), f_ty = __shfl_sync(kFull, ty, end_lane - 1);
+    // minima of the lanes to the right of this one (an ORF starting here has its own interior windows, not its seam ones)
+    unsigned xmn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+    if (WantMin) {
+        const unsigned m0 = __shfl_down_sync(kFull, tmn[0], 1), m1 = __shfl_down_sync(kFull, tmn[1], 1), m2 = __shfl_down_sync(kFull, tmn[2], 1);
+        if (lane + 1 < end_lane) { xmn[0] = m0; xmn[1] = m1; xmn[2] = m2; }
+    }
     const unsigned kMask = (1u << 21) - 1u;
-    K[0] = (unsigned)Kp & kMask; K[1] = (unsigned)(Kp >> 21) & kMask; K[2] = (unsigned)(Kp >> 42) & kMask;
-    U[0] = (unsigned)Up & kMask; U[1] = (unsigned)(Up >> 21) & kMask; U[2] = (unsigned)(Up >> 42) & kMask;
-    big = flags != 0 || L > 3 * kMaxExactCodons;
-    if (rw.long_idx >= 0) {
+    if (is_long) {
         // one group of a long ORF: integer atomics into the ORF's accumulator; the last group to arrive scores it
+        if (lane != 0) return;
+        unsigned Kt[3] = {(unsigned)Kp & kMask, (unsigned)(Kp >> 21) & kMask, (unsigned)(Kp >> 42) & kMask};
+        unsigned Ut[3] = {(unsigned)Up & kMask, (unsigned)(Up >> 21) & kMask, (unsigned)(Up >> 42) & kMask};
         LongAcc* acc = args.long_acc + rw.long_idx;
 #pragma unroll
         for (int f = 0; f < 3; ++f) {
-            atomicAdd(&acc->RE[f], (unsigned long long)RE[f]);
-            atomicAdd(&acc->IM[f], (unsigned long long)IM[f]);
-            atomicAdd(&acc->K[f], K[f]);
-            atomicAdd(&acc->U[f], U[f]);
+            atomicAdd(&acc->RE[f], (unsigned long long)TRE[f]);
+            atomicAdd(&acc->IM[f], (unsigned long long)TIM[f]);
+            atomicAdd(&acc->K[f], Kt[f]);
+            atomicAdd(&acc->U[f], Ut[f]);
         }
         atomicAdd(&acc->count, (unsigned long long)count);
-        atomicMin(&acc->mn, mn);
-        if (big) atomicOr(&acc->big, 1u);
+        if (WantMin) atomicMin(&acc->mn, tmn[0]);
+        if (flags) atomicOr(&acc->big, 1u);
         __threadfence();
         if (atomicAdd(&acc->done, 1u) != (unsigned)(rw.n_groups - 1)) return;
         __threadfence();
         volatile LongAcc* va = acc;
+        long long RE2[3], IM2[3];
 #pragma unroll
         for (int f = 0; f < 3; ++f) {
-            RE[f] = (long long)va->RE[f]; IM[f] = (long long)va->IM[f]; K[f] = va->K[f]; U[f] = va->U[f];
+            RE2[f] = (long long)va->RE[f]; IM2[f] = (long long)va->IM[f]; Kt[f] = va->K[f]; Ut[f] = va->U[f];
             va->RE[f] = 0; va->IM[f] = 0; va->K[f] = 0; va->U[f] = 0;
         }
-        count = (long long)va->count; mn = va->mn; big = va->big != 0;
+        const long long cnt2 = (long long)va->count;
+        const unsigned mn2 = va->mn;
+        const bool big2 = va->big != 0;
         va->count = 0; va->mn = 0xffffffffu; va->big = 0; va->done = 0;      // ready for the next launch
+        const int L = __ldg(args.orf_len + rw.orf);
+        if (big2 || L > 3 * kMaxExactCodons) {
+            args.fallback[atomicAdd(args.n_fallback, 1u)] = rw.orf;
+            return;
+        }
+        finish_orf_lean(args, rw.orf, L, Kt, Ut, RE2, IM2, mn2, cnt2);
+        return;
     }
-    if (big) {
+    if (orf < 0) return;                    // no ORF starts on this reference
+    // ---- the ORF that starts here: suffix sums without this reference's seam windows, in the ORF's own frames ----
+    const int L = __ldg(args.orf_len + orf);
+    unsigned long long sKp = (unsigned long long)sK[0] | ((unsigned long long)sK[1] << 21) | ((unsigned long long)sK[2] << 42);
+    unsigned long long sUp = (unsigned long long)sU[0] | ((unsigned long long)sU[1] << 21) | ((unsigned long long)sU[2] << 42);
+    Kp -= sKp;                              // field-wise: the seam windows of this lane are part of its suffix sums
+    Up -= sUp;
+    unsigned Kq[3] = {(unsigned)Kp & kMask, (unsigned)(Kp >> 21) & kMask, (unsigned)(Kp >> 42) & kMask};
+    unsigned Uq[3] = {(unsigned)Up & kMask, (unsigned)(Up >> 21) & kMask, (unsigned)(Up >> 42) & kMask};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { TRE[q] -= sRE[q]; TIM[q] -= sIM[q]; }
+    // frame q of this ORF is frame (q + P) mod 3 of the parent
+    const int j0 = pm3, j1 = pm3 == 2 ? 0 : pm3 + 1, j2 = 3 - j0 - j1;
+    const bool q00 = j0 == 0, q01 = j0 == 1, q10 = j1 == 0, q11 = j1 == 1, q20 = j2 == 0, q21 = j2 == 1;
+    unsigned Ko[3] = {sel3(q00, q01, Kq[0], Kq[1], Kq[2]), sel3(q10, q11, Kq[0], Kq[1], Kq[2]), sel3(q20, q21, Kq[0], Kq[1], Kq[2])};
+    unsigned Uo[3] = {sel3(q00, q01, Uq[0], Uq[1], Uq[2]), sel3(q10, q11, Uq[0], Uq[1], Uq[2]), sel3(q20, q21, Uq[0], Uq[1], Uq[2])};
+    long long REo[3] = {sel3(q00, q01, TRE[0], TRE[1], TRE[2]), sel3(q10, q11, TRE[0], TRE[1], TRE[2]), sel3(q20, q21, TRE[0], TRE[1], TRE[2])};
+    long long IMo[3] = {sel3(q00, q01, TIM[0], TIM[1], TIM[2]), sel3(q10, q11, TIM[0], TIM[1], TIM[2]), sel3(q20, q21, TIM[0], TIM[1], TIM[2])};
+    unsigned mn = 0xffffffffu;
+    bool big_o = flags != 0 || L > 3 * kMaxExactCodons;
+    if (WantMin) {
+        mn = min(sel3(q00, q01, imn[0], imn[1], imn[2]), sel3(q00, q01, xmn[0], xmn[1], xmn[2]));       // this ORF's frame 0
+        if (lm3 == 1) mn = min(mn, (unsigned)f_ty);
+        else if (lm3 == 2) mn = min(mn, (unsigned)f_tx + (unsigned)f_ty);
+    }
+    if (lm3 == 1) big_o |= (f_ty >> kBigShift) != 0;
+    else if (lm3 == 2) big_o |= ((f_tx | f_ty) >> kBigShift) != 0;
+    if (big_o) {
         args.fallback[atomicAdd(args.n_fallback, 1u)] = orf;
         return;
     }
-    finish_orf_lean(args, orf, L, K, U, RE, IM, mn, count);
+    finish_orf_lean(args, orf, L, Ko, Uo, REo, IMo, mn, count);
 }
 
 // ---- K4 -------------------------------------------------------------------------------------
@@ -2173,6 +2256,9 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
     // per-thread 4-bit counters of categories RT_ST_QCFAIL..RT_ST_BADREF (<= 8 reads per thread)
     unsigned packed = 0;
     unsigned long long len_packed = 0;
+#ifdef RT_BIN_NO_RED
+    unsigned long long sink = 0;
+#endif
     constexpr int kBatch = RT_BIN_BATCH;     // reads per thread whose columns are in flight together
 #pragma unroll 1
     for (int it0 = 0; it0 < kBinReadsPerThread; it0 += kBatch) {
@@ -2268,7 +2354,11 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
             if (head && slot != kNone) {
                 const unsigned after = lane == 31 ? 0u : heads >> (lane + 1);
                 const int run = after ? __ffs(after) : 32 - lane;
+#ifdef RT_BIN_NO_RED      // A/B build only: everything but the scatter itself (what no change to the atomics can go below)
+                sink += (unsigned long long)slot * (unsigned)run;
+#else
                 atomicAdd(a.cov + slot, a.weight * run);
+#endif
             }
             if (!Compact && a.touched) {   // remember the 32 B sector so the planes can be cleared sparsely afterwards
                 const long long sec = slot != kNone ? (long long)(slot >> 3) : -1;
@@ -2289,6 +2379,9 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
             }
         }
     }
+#ifdef RT_BIN_NO_RED
+    if (sink == 0x123456789abcdefull) a.cov[0] = 1;      // keeps the slot computation alive
+#endif
     {   // flush the register length counters: one REDUX per length, one shared atomic per lane
         unsigned mine_len = 0;
 #pragma unroll

@@ -138,14 +138,16 @@ def test_bin_psites_matches_oracle(engine, protocol, read_lengths, sort, offsets
     assert dict(zip(ref_stats.keys(), st.cpu().tolist())) == ref_stats
 
 
-@pytest.mark.parametrize("name,scale,contig_scale", [("tiny", 1.0, 1.0), ("C1", 0.2, 1.0), ("C5", 0.004, 0.01)])
+@pytest.mark.parametrize("name,scale,contig_scale", [("tiny", 1.0, 1.0), ("C1", 0.2, 1.0), ("C5", 0.004, 0.01),
+                                                     ("C5", 0.1, 0.1)])      # 750 k ORFs, ten 100 k-codon ones, 310 Mb
 def test_score_matches_oracle(engine, name, scale, contig_scale):
     CO = _oracle()
     from ribotricer_b200 import synth
 
     cfg = synth.config(name, scale, contig_scale)
     idx = synth.make_index(cfg)
-    reads = synth.reads_to_numpy(synth.make_reads(cfg, idx, n_reads=min(cfg.n_reads, 2_000_000)))
+    reads = synth.reads_to_numpy(synth.make_reads(cfg, idx, n_reads=min(cfg.n_reads, 2_000_000 if scale < 0.05 else 10_000_000),
+                                                  device=engine.device if scale >= 0.05 else "cpu"))
     pad = 256
     base, plane = _setup(engine, idx.contig_names, idx.contig_len, idx.as_dict(), synth.TRUE_OFFSETS, pad=pad)
     cov = engine.new_coverage()
@@ -277,6 +279,38 @@ def test_full_config1_against_oracle(engine):
     assert np.abs(got["score"] - ref["score"]).max() < 1e-11
 
 
+
+def _oracle_on_subgenome(engine, idx, dreads, contigs, got, what):
+    """The C oracle (bin + score, OpenMP) on the contigs ``contigs`` of a full-size configuration -- their reads,
+    their ORFs, a coverage array of just those contigs on the host -- against the rows the GPU produced for the
+    same ORFs while it scored the WHOLE configuration.  Returns the number of ORFs compared."""
+    CO = _oracle()
+    from ribotricer_b200 import synth
+
+    t = engine.torch
+    contigs = np.asarray(sorted(contigs), np.int64)
+    remap = np.full(len(idx.contig_len), -1, np.int64)
+    remap[contigs] = np.arange(len(contigs))
+    on = np.isin(idx.orf_contig, contigs)
+    rows = np.flatnonzero(on)
+    from ribotricer_b200 import multi_gpu
+    sub = multi_gpu.sub_index(idx.as_dict(), rows)
+    sub["orf_contig"] = remap[sub["orf_contig"]].astype(np.int32)
+    keep = t.isin(dreads["ref_id"], t.as_tensor(contigs, device=dreads["ref_id"].device).to(dreads["ref_id"].dtype))
+    reads = synth.reads_to_numpy({k: v[keep] for k, v in dreads.items()})
+    reads["ref_id"] = remap[reads["ref_id"]].astype(np.int32)
+    sub_len = idx.contig_len[contigs]
+    pad = engine.pad
+    base, plane = CO.genome_layout(sub_len, pad)
+    ref_cov, _, _ = CO.bin_reads(reads, 0, CO.make_len_table(synth.TRUE_OFFSETS), base, sub_len, pad, plane)
+    ref = CO.score(sub, ref_cov, base, sub_len, pad, plane, DEFAULT_PARAMS)
+    tie = CO.tie_mask(ref["frame_K"], ref["frame_s"])
+    mine = {k: v[rows] for k, v in got.items()}
+    n_tie, _ = compare_scores(mine, ref, tie, what=what)
+    assert n_tie < 0.02 * len(rows)
+    return len(rows)
+
+
 def test_full_config2_properties(engine):
     """BASELINE.json configs[1] at full size (2.5 M ORFs, 100 M reads, 24.7 GB coverage) through
     size-independent properties: un-binning returns the planes to zero; binning the library
@@ -316,6 +350,9 @@ def test_full_config2_properties(engine):
     parts = [engine.score_host(cov, int(bounds[i]), int(bounds[i + 1]), min_codon=True) for i in range(8)]
     for k in one:
         assert np.array_equal(np.concatenate([p[k] for p in parts]), one[k], equal_nan=True), k
+    # chr16 .. chrM (15 % of the genome, ~375 k ORFs) against the C oracle: every column of every one of those ORFs
+    n_cmp = _oracle_on_subgenome(engine, idx, dreads, range(15, 25), one, "C2 chr16-chrM: ")
+    assert n_cmp >= 200_000
     # sample against the oracle, through the gathered profiles (bit-exact integers, score 1e-9)
     rng = np.random.default_rng(11)
     sel = np.sort(np.concatenate([rng.choice(idx.n_orf, 20000, replace=False), np.argsort(idx.orf_len)[-20:]]))
@@ -330,6 +367,58 @@ def test_full_config2_properties(engine):
         assert abs(s - one["score"][o]) <= SCORE_TOL
         if not CO.tie_mask(K[None, :], s3[None, :])[0]:
             assert v == one["valid"][o]
+
+
+
+def test_full_config3_against_oracle(engine):
+    """BASELINE.json configs[2] at full size (10 M candidate ORFs, 500 M reads) in the compact layout, as the
+    benchmark runs it, and as two genomic blocks (what two ranks would hold): every ORF of chr13 .. chrM (a third of
+    the genome, > 3 M ORFs) against the C oracle, the per-block results identical to the single run, and the
+    size-independent books (every valid read inside the exon union is one count)."""
+    import psutil
+
+    from ribotricer_b200 import multi_gpu, synth
+
+    if psutil.virtual_memory().available < 80 * 2 ** 30:
+        pytest.skip("needs 80 GB of host memory for the oracle's copy of a third of the genome")
+    t = engine.torch
+    cfg = synth.config("C3")
+    idx = synth.make_index(cfg)
+    dreads = synth.make_reads(cfg, idx, device=engine.device)
+    engine.set_genome(idx.contig_names, idx.contig_len)
+    engine.set_length_table(synth.TRUE_OFFSETS, None)
+    engine.set_index(**idx.as_dict())
+    engine.set_layout("compact")
+    cov = engine.new_coverage()
+    st, lc = engine.new_bin_accumulators()
+    engine.bin_reads_device(cov, dreads, "forward", st, lc, sorted_hint=True)
+    got = engine.score_host(cov, diagnostics=True)
+    assert len(got["score"]) == 10_000_000 and int(st[0].item()) == cfg.n_reads
+    assert int(got["count"].sum()) >= int(cov.sum(dtype=t.int64).item())         # ORFs overlap: every count is seen at least once
+    n_cmp = _oracle_on_subgenome(engine, idx, dreads, range(12, 25), got, "C3 chr13-chrM: ")
+    assert n_cmp >= 3_000_000
+    del cov
+    # two genomic blocks, each from its own slice of the reads
+    plan = multi_gpu.shard_plan(idx.exon_ptr, idx.exon_start, idx.exon_end, idx.orf_contig, 2)
+    reach = max(synth.TRUE_OFFSETS.values()) + int((dreads["last"].long() - dreads["first"].long()).max().item())
+    key = dreads["ref_id"].long() * (1 << 32) + dreads["first"].long()
+    for sh in plan:
+        keep = t.zeros(len(key), dtype=t.bool, device=key.device)
+        for c, lo, hi in sh.spans:
+            a = int(t.searchsorted(key, t.tensor(c * (1 << 32) + max(lo - 1 - reach, 0), device=key.device)))
+            b = int(t.searchsorted(key, t.tensor(c * (1 << 32) + hi + reach, device=key.device), right=True))
+            keep[a:b] = True
+        assert int(keep.sum().item()) < 0.55 * len(key)
+        engine.set_index(**multi_gpu.sub_index(idx.as_dict(), sh.rows))
+        engine.set_layout("compact")
+        bcov = engine.new_coverage()
+        st, lc = engine.new_bin_accumulators()
+        engine.bin_reads_device(bcov, {k: v[keep].contiguous() for k, v in dreads.items()}, "forward", st, lc, sorted_hint=True)
+        part = engine.score_host(bcov, diagnostics=True)
+        for k in got:
+            assert np.array_equal(part[k], got[k][sh.rows], equal_nan=True), k
+        del bcov
+    engine.set_layout("dense")
 
 
 def test_sparse_clear(engine):
