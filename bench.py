@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--libraries", type=int, default=64, help="--config C4: libraries in the batch")
     ap.add_argument("--distinct", type=int, default=4, help="--config C4: distinct libraries generated (cycled through)")
+    ap.add_argument("--min-reads-per-codon", type=float, default=0.0,
+                    help="--min_reads_per_codon of the scoring step (> 0 selects the kernels that also carry per-frame minima)")
     ap.add_argument("--layout", default="compact", choices=["compact", "dense"],
                     help="coverage layout: exon union of the index (default) or genome-wide planes")
     return ap.parse_args()
@@ -314,7 +316,7 @@ def run_ours(args):
     cov = eng.new_coverage()
     stats, len_counts = eng.new_bin_accumulators()
     out = eng.new_score_columns(n_orf)
-    params = ScoreParams()
+    params = ScoreParams(min_reads_per_codon=args.min_reads_per_codon)
     score_bytes = eng.score_bytes()
     total_nt = eng.total_nt()
     bin_bytes = 23 * n_reads   # 15 B columns + 8 B RMW per read (we move 18 + 8)
@@ -407,7 +409,7 @@ def run_ours(args):
         # dram__bytes_read.sum + dram__bytes_write.sum of the scoring kernel from the committed ncu capture
         traffic, traffic_src, bin_traffic = None, None, None
         scan_path = os.environ.get("RT_SCORE_PATH") == "scan"
-        kernel_names = ("score_orfs_packed_kernel",) if scan_path else ("atom_summary_kernel", "score_from_atoms_kernel")
+        kernel_names = ("score_orfs_packed_kernel",) if scan_path else ("atom_pass_kernel", "compose_refs_kernel")
         try:
             t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             same = lambda e: e.get("workload") == args.config and e.get("layout", "dense") == args.layout  # noqa: E731
@@ -434,7 +436,7 @@ def run_ours(args):
                 "per_rank": [{"orfs": c[0], "reads": c[1], "score_bytes": c[2]} for c in per_rank],
                 "l2": "inputs larger than L2 (coverage buffer %.1f GB, read columns %.2f GB)" % (
                     cov.numel() * 4 / 1e9, READ_BYTES * n_reads / 1e9),
-                "coverage_layout": args.layout,
+                "coverage_layout": args.layout, "min_reads_per_codon": args.min_reads_per_codon,
                 "step": "bin P-sites -> gather+score -> clear (resident coverage back to zero: memset of the compact "
                         "buffer, or sparse clear of the touched sectors of the dense planes)",
             },

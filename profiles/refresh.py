@@ -32,8 +32,8 @@ open(os.path.join(HERE, f"{tag}_step_kernels.txt"), "w").write(txt)
 
 # 2. per-line profiles: (mangled symbol substring, ncu regex, file tag)
 KERNELS = [("bin_psites_kernelILb1ELb0E", "bin_psites", "bin_psites_kernel"),
-           ("atom_summary_kernelILi4ELb0E", "atom_summary", "atom_summary_kernel"),
-           ("score_from_atoms_kernel", "score_from_atoms", "score_from_atoms_kernel")]
+           ("atom_pass_kernelILi2ELb0E", "atom_pass", "atom_pass_kernel"),
+           ("compose_refs_kernelILb0E", "compose_refs", "compose_refs_kernel")]
 for sym, rx, name in KERNELS:
     out = subprocess.run([py, os.path.join(HERE, "line_profile.py"), rep, sym, "45", rx], capture_output=True, text=True)
     open(os.path.join(HERE, f"{tag}_{name}_lines.txt"), "w").write(out.stdout + out.stderr)
@@ -76,7 +76,7 @@ for k in per:   # the e2e leg launches K1 in 4 M-read chunks: keep the whole-lib
     g = max(x[0] for x in per[k])
     per[k] = [t for x, t in per[k] if x == g]
 lines = []
-n = len(per.get("atom_summary_kernel", []))
+n = len(per.get("atom_pass_kernel", []))
 tot = sum(sum(v[:n]) / max(1, n) for v in per.values())
 for k, v in per.items():
     m = sum(v[:n]) / max(1, n)

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -76,7 +77,7 @@ struct rt_ctx {
     int atom_lpo = 4;                                // lanes per atom in phase A (RT_ATOM_LPO)
     bool use_ref_kernel = true;                      // phase B with one lane per atom reference (RT_PHASE_B=thread: one thread per ORF)
     bool use_pass_kernel = true;                     // compact layout: streamed phase A (RT_PHASE_A=atoms selects the per-atom kernel)
-    int pass_warps = 16, pass_stages = 2;            // RT_PASS_WARPS (1..32), RT_PASS_STAGES (1..4)
+    int pass_warps = 16, pass_stages = 2;            // RT_PASS_WARPS (1..16), RT_PASS_STAGES (1..3)
     bool use_atoms = true;                           // two-phase scoring (RT_SCORE_PATH=scan selects the scan kernel)
 
     // two-phase scoring: atoms (coverage intervals no ORF exon boundary splits) and per-ORF atom refs
@@ -361,7 +362,7 @@ int rt_create(int device, rt_ctx** out) {
     }
     if (const char* e = getenv("RT_PHASE_A")) ctx->use_pass_kernel = strcmp(e, "atoms") != 0;
     if (const char* e = getenv("RT_PHASE_B")) ctx->use_ref_kernel = strcmp(e, "thread") != 0;
-    if (const char* e = getenv("RT_PASS_WARPS")) ctx->pass_warps = std::min(32, std::max(1, atoi(e)));
+    if (const char* e = getenv("RT_PASS_WARPS")) ctx->pass_warps = std::min(16, std::max(1, atoi(e)));
     if (const char* e = getenv("RT_PASS_STAGES")) ctx->pass_stages = std::min(3, std::max(1, atoi(e)));
     if (const char* e = getenv("RT_PACK_LPO")) {
         const int v = atoi(e);
@@ -671,10 +672,17 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
     // slot, start the copies (first / last / mlen straight from the caller's columns) on their own stream and launch
     // K1 behind them -- so the packing of some chunks, the copies of others and the kernels of yet others overlap.
     // A chunk with too many reference runs (not grouped after all) is sent as plain columns.
-    const int64_t chunk = sorted_hint ? std::min<int64_t>(kPackChunkReads, std::max<int64_t>(n, 1))
+    int64_t pack_chunk_reads = kPackChunkReads;
+    if (const char* e = getenv("RT_PACK_CHUNK")) pack_chunk_reads = std::min<int64_t>(kPackChunkReads, std::max(1 << 16, atoi(e)));
+    const int64_t chunk = sorted_hint ? std::min<int64_t>(pack_chunk_reads, std::max<int64_t>(n, 1))
                                       : std::min<int64_t>(kHostChunkReads, std::max<int64_t>(n, 1));
     const int64_t n_chunks = (n + chunk - 1) / chunk;
-    const int n_pipes = sorted_hint ? (int)std::max<int64_t>(1, std::min<int64_t>({kMaxPipes, (int64_t)std::thread::hardware_concurrency() / 2, n_chunks})) : 2;
+    int64_t want_pipes = std::min<int64_t>(kMaxPipes, (int64_t)std::thread::hardware_concurrency() / 2);
+    if (const char* e = getenv("RT_PACK_PIPES")) want_pipes = std::min<int64_t>(kMaxPipes, std::max(1, atoi(e)));
+    const int n_pipes = sorted_hint ? (int)std::max<int64_t>(1, std::min<int64_t>(want_pipes, n_chunks)) : 2;
+    const bool timing = getenv("RT_HOST_TIMING") != nullptr;
+    std::atomic<long long> pack_ns{0}, wait_ns{0}, issue_ns{0};
+    const auto t_begin = std::chrono::steady_clock::now();
     // per-slot layout: 8-byte run table first, then the 4-byte columns, so that every column stays naturally aligned
     const size_t slot_bytes = (size_t)chunk * kReadBytes + sizeof(int64_t) * (kChunkRunCap + 1) + sizeof(int32_t) * kChunkRunCap + 64;
     for (int s = 0; s < n_pipes; ++s) {
@@ -718,11 +726,18 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
             if (c >= n_chunks || status.load() != RT_OK) break;
             const int64_t at = c * chunk, m = std::min(chunk, n - at);
             int64_t runs = -1;
+            const auto t0 = std::chrono::steady_clock::now();
             if (sorted_hint) {
                 if (hs.busy && !check(cudaEventSynchronize(hs.copied), "cudaEventSynchronize")) break;   // staging slot free again
                 hs.busy = false;
+                const auto t1 = std::chrono::steady_clock::now();
                 runs = rt_pack_chunk(h_ref_id + at, h_flag + at, h_mapq + at, h_nh + at, m, hs.meta, hs.run_start, hs.run_ref, kChunkRunCap);
+                if (timing) {
+                    wait_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+                    pack_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t1).count();
+                }
             }
+            const auto t2 = std::chrono::steady_clock::now();
             if (!check(cudaMemcpyAsync(d_first, h_first + at, 4 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
                 !check(cudaMemcpyAsync(d_last, h_last + at, 4 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
                 !check(cudaMemcpyAsync(d_mlen, h_mlen + at, 2 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync"))
@@ -748,6 +763,7 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
                 rc = rt_bin_reads(ctx, d_cov, m, d_ref, d_first, d_last, d_mlen, d_flag, d_mapq, d_nh, protocol, sorted_hint, 1,
                                   d_stats, d_len_counts, st);
             }
+            if (timing) issue_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t2).count();
             if (rc != RT_OK) {
                 int expected = RT_OK;
                 status.compare_exchange_strong(expected, rc);
@@ -762,9 +778,16 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
         for (auto& th : pipes) th.join();
     }
     if (status.load() != RT_OK) return first_error.empty() ? status.load() : fail(ctx, status.load(), "rt_bin_reads_host: %s", first_error.c_str());
+    const auto t_issued = std::chrono::steady_clock::now();
     for (int s = 0; s < n_pipes; ++s) {
         RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
         ctx->host_stage[s].busy = false;
+    }
+    if (timing) {
+        const auto ms = [](auto d) { return std::chrono::duration<double, std::milli>(d).count(); };
+        fprintf(stderr, "rt_bin_reads_host: %lld reads, %d pipes, chunk %lld: issue phase %.2f ms, drain %.2f ms; thread-ms packing %.2f, waiting for staging %.2f, "
+                        "enqueueing %.2f\n", (long long)n, n_pipes, (long long)chunk, ms(t_issued - t_begin), ms(std::chrono::steady_clock::now() - t_issued),
+                pack_ns.load() / 1e6, wait_ns.load() / 1e6, issue_ns.load() / 1e6);
     }
     RT_CUDA(ctx, cudaMemcpy(h_stats, d_stats, sizeof(int64_t) * RT_N_STATS, cudaMemcpyDeviceToHost));
     RT_CUDA(ctx, cudaMemcpy(h_len_counts, d_len_counts, sizeof(int64_t) * RT_LEN_TABLE, cudaMemcpyDeviceToHost));
@@ -1334,18 +1357,11 @@ int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi, 
                     return cudaSuccess;
                 };
                 cudaError_t e;
-                auto by_threads = [&](auto k512, auto k768, auto k1024) {
-                    return warps <= 16 ? go(k512) : warps <= 24 ? go(k768) : go(k1024);
-                };
-#define RT_PASS_CASE(S)                                                                                              \
-    (want_min ? by_threads(rt::atom_pass_kernel<S, true, 512>, rt::atom_pass_kernel<S, true, 768>,                  \
-                           rt::atom_pass_kernel<S, true, 1024>)                                                      \
-              : by_threads(rt::atom_pass_kernel<S, false, 512>, rt::atom_pass_kernel<S, false, 768>,                \
-                           rt::atom_pass_kernel<S, false, 1024>))
-                if (stages == 1) e = RT_PASS_CASE(1);
-                else if (stages == 2) e = RT_PASS_CASE(2);
-                else e = RT_PASS_CASE(3);
-#undef RT_PASS_CASE
+                // 16 warps x 2 stages measured best on C2 (profiles/README.md): more warps need the 64-register build, which
+                // spills, and a third stage buys nothing -- the kernel is bound by the shared-memory pipe, not by the copies
+                if (stages == 1) e = want_min ? go(rt::atom_pass_kernel<1, true>) : go(rt::atom_pass_kernel<1, false>);
+                else if (stages == 2) e = want_min ? go(rt::atom_pass_kernel<2, true>) : go(rt::atom_pass_kernel<2, false>);
+                else e = want_min ? go(rt::atom_pass_kernel<3, true>) : go(rt::atom_pass_kernel<3, false>);
                 RT_CUDA(ctx, e);
             } else {
             auto launch = [&](auto kmin, auto knomin, int lpo) {

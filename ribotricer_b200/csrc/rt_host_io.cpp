@@ -388,7 +388,8 @@ int64_t rt_pack_chunk(const int32_t* __restrict__ ref_id, const uint16_t* __rest
                       int64_t cap) {
     for (int64_t i = 0; i < m; ++i) {
         const unsigned f = flag[i];
-        const unsigned uniq = nh[i] != 0 ? (nh[i] == 1) : (mapq[i] == 255);
+        const unsigned nn = nh[i], qq = mapq[i];             // both loaded unconditionally: no control flow, the loop vectorises
+        const unsigned uniq = (nn == 1u) | ((nn == 0u) & (qq == 255u));
         unsigned code = uniq ? 0u : (unsigned)RT_ST_MULTI;
         code = (f & 0x4) ? (unsigned)RT_ST_UNMAPPED : code;
         code = (f & 0x100) ? (unsigned)RT_ST_SECONDARY : code;

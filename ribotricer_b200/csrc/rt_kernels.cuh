@@ -1187,8 +1187,8 @@ __device__ __forceinline__ void count_nonzero(unsigned& n, int x) {
     asm("{\n.reg .pred p;\nsetp.ne.s32 p, %1, 0;\n@p add.u32 %0, %0, 1;\n}" : "+r"(n) : "r"(x));
 }
 
-template <int STAGES, bool WantMin, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) atom_pass_kernel(const PassArgs args) {
+template <int STAGES, bool WantMin>
+__global__ void __launch_bounds__(512, 1) atom_pass_kernel(const PassArgs args) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     double2* s_uv = reinterpret_cast<double2*>(s_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
