@@ -1747,19 +1747,18 @@ __device__ __forceinline__ void finish_orf_lean(const Args& args, int orf, int L
     double s3[3];
     double coh = 0.0;
     int valid = -1;
-#pragma unroll 1
+#pragma unroll
     for (int f = 0; f < 3; ++f) {
-        const unsigned Kf = sel3(f == 0, f == 1, K[0], K[1], K[2]), Uf = sel3(f == 0, f == 1, U[0], U[1], U[2]);
         double s = kNaN;
-        if (Kf == 0) { coh = 0.0; valid = 0; }                            // statistics.py:94-95
+        if (K[f] == 0) { coh = 0.0; valid = 0; }                          // statistics.py:94-95
         else {
-            const double re = (double)sel3(f == 0, f == 1, RE[0], RE[1], RE[2]) * (1.0 / kUvGridScale);
-            const double im = kSqrt3 * ((double)sel3(f == 0, f == 1, IM[0], IM[1], IM[2]) * (1.0 / kUvGridScale));
-            s = (re * re + im * im) / ((double)Kf * (double)(Kf - Uf));   // 0/0 -> NaN never wins
-            if (s > coh) { coh = s; valid = (int)Kf; }                    // statistics.py:109-111
-            if (valid == -1) valid = (int)Kf;                             // statistics.py:112-113
+            const double re = (double)RE[f] * (1.0 / kUvGridScale);        // the sums are exact integers (units of 2^-42)
+            const double im = kSqrt3 * ((double)IM[f] * (1.0 / kUvGridScale));
+            s = (re * re + im * im) / ((double)K[f] * (double)(K[f] - U[f]));   // 0/0 -> NaN never wins
+            if (s > coh) { coh = s; valid = (int)K[f]; }                  // statistics.py:109-111
+            if (valid == -1) valid = (int)K[f];                           // statistics.py:112-113
         }
-        if (f == 0) s3[0] = s; else if (f == 1) s3[1] = s; else s3[2] = s;
+        s3[f] = s;
     }
     const double score = sqrt(coh);                                      // statistics.py:115
     bool ok = score >= args.prm.phase_score_cutoff && (double)valid >= args.prm.min_valid_codons &&
