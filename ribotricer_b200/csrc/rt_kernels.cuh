@@ -1309,12 +1309,19 @@ __global__ void __launch_bounds__(512, 1) atom_pass_kernel(const PassArgs args) 
                 for (int q = 0; q < kGroupNt; ++q) {
                     const int a = v[q], b = v[q + 1], c = v[q + 2];
                     const int i16 = (a * kUvStride + b - c * (kUvStride + 1)) * 16;
-                    const double2 u = *reinterpret_cast<const double2*>(center + i16);
                     constexpr int kF0 = 0;
                     const int f = (gq * kGroupNt + q) % 3 + kF0;
-                    if (f == 0) { re0 += u.x; im0 += u.y; count_nonzero(K0, a | b | c); count_nonzero(M0, i16); }
-                    else if (f == 1) { re1 += u.x; im1 += u.y; count_nonzero(K1, a | b | c); count_nonzero(M1, i16); }
-                    else { re2 += u.x; im2 += u.y; count_nonzero(K2, a | b | c); count_nonzero(M2, i16); }
+                    // all-zero windows (most of them) neither load nor add: their lanes take no part in the table access,
+                    // so they cannot collide with the lanes that look something up
+                    if ((a | b | c) != 0) {
+                        const double2 u = *reinterpret_cast<const double2*>(center + i16);
+                        if (f == 0) { re0 += u.x; im0 += u.y; K0 += 1u; }
+                        else if (f == 1) { re1 += u.x; im1 += u.y; K1 += 1u; }
+                        else { re2 += u.x; im2 += u.y; K2 += 1u; }
+                    }
+                    if (f == 0) count_nonzero(M0, i16);
+                    else if (f == 1) count_nonzero(M1, i16);
+                    else count_nonzero(M2, i16);
                     if (WantMin) {
                         const unsigned sum = q + 2 < left ? (unsigned)a + (unsigned)b + (unsigned)c : 0xffffffffu;
                         if (f == 0) mn0 = min(mn0, sum);
