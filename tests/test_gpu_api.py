@@ -275,7 +275,7 @@ def test_learn_cutoff_matches_reference(engine, tmp_path, capsys):
 def test_default_flags_on_full_config1(engine, tmp_path):
     """detect_orfs() with NOTHING given (protocol, read lengths and P-site offsets all inferred) on the full
     BASELINE configs[0] library (100 k ORFs, 10 M reads).  The unmodified reference's infer_protocol says
-    "forward" on this library (profiles/r2_protocol_heuristic_new_synth.txt) and its metagene_coverage /
+    "forward" on this library (profiles/r2_protocol_heuristic.txt) and its metagene_coverage /
     align_metagenes recover the planted offsets {26-29: 12, 30-32: 13} (measured with the
     reference); the inferred run must find the same and write the very TSV of the run with explicit offsets."""
     from ribotricer_b200 import detect_orfs as D
