@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 2
+#define RT_ABI_VERSION 3
 
 /* read-length table: one int32 per matched length = the P-site offset of that length (may be negative:
  * align_metagenes returns lag + 12 with lag in [-min(base, length), ...), metagene.py:319-324; |offset| <=
@@ -135,9 +135,9 @@ int rt_bin_reads(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* d_ref_id
 
 /* Same with HOST columns (what a BAM decoder produces, 18 B/read): chunked, double-buffered H2D overlapped with the
  * kernel; h_stats / h_len_counts receive the totals (they are overwritten, not added to).  With `sorted_hint` every
- * chunk crosses PCIe as 11 B/read packed records: host threads evaluate the filter cascade of chunk k+1 into one
- * meta byte per read and run-length code its ref_id while chunk k is on the wire (a chunk that turns out not to be
- * grouped by reference is sent as plain columns).  Returns after the work has completed. */
+ * chunk crosses PCIe as a 4 B/read record stream (rt_stream_pack below): host threads delta-code chunk k+1 while
+ * chunk k is on the wire and K1 runs on the stream; a chunk that cannot be coded (not sorted after all) is sent as
+ * plain columns.  Returns after the work has completed. */
 int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_ref_id,
                       const int32_t* h_first, const int32_t* h_last, const uint16_t* h_mlen,
                       const uint16_t* h_flag, const uint8_t* h_mapq, const uint8_t* h_nh,
@@ -164,6 +164,53 @@ int rt_bin_reads_packed_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32
                              const uint16_t* h_mlen, const uint8_t* h_meta, int64_t n_runs,
                              const int64_t* h_run_start, const int32_t* h_run_ref, int protocol,
                              int64_t* h_stats, int64_t* h_len_counts);
+
+/*
+ * ---- K1 on a RECORD STREAM: a coordinate-sorted library as 4-byte delta-coded records (a quarter of the 18 B/read
+ *      columns over PCIe and out of HBM).  Same loop as above (bam.py:71-137 + detect_orfs.py:54-83), identical results.
+ * Records come in blocks of RT_STREAM_BLOCK; block b has the header h_hdr[2b] = ref_id of all its reads,
+ * h_hdr[2b+1] = the position its deltas start from.  A record is one little-endian u32:
+ *   read       bits 0-14 delta = first - first of the previous read (or the header position), bit 15 = 0,
+ *              bits 16-23 mlen & 255, bits 24-31 the RAW bits the filter cascade reads (it is evaluated on the
+ *              device): RT_STREAM_UNMAPPED / SECONDARY / QCFAIL / DUPLICATE / REVERSE = SAM flags 0x4 / 0x100 /
+ *              0x200 / 0x400 / 0x10, bits 5-6 = what common.py:33-69 looks at (RT_STREAM_NH_*: NH absent and
+ *              MAPQ != 255, NH absent and MAPQ == 255, NH == 1, NH present and != 1), bit 7 RT_STREAM_EXT = an
+ *              extension record follows (never in another block);
+ *   extension  bits 15,14 = 1,1: bits 0-7 = mlen >> 8, bits 16-31 | bits 8-13 << 16 = last - first + 1 - mlen
+ *              (the reference positions a spliced or deleted-from read skips; < 2^22);
+ *   skip       bits 15,14 = 1,0: advances the position by bits 16-31 | bits 0-13 << 16 without being a read
+ *              (gaps above 32767 nt; RT_STREAM_NULL = skip 0 pads the last block of a range).
+ * Reads whose category the flags decide (unmapped, secondary, qcfail, duplicate) carry delta 0 and mlen 0: the
+ * reference never looks at their position.  rt_stream_pack builds the stream from the decoder's columns with
+ * `n_threads` host threads (<= 0: all cores), every RT_STREAM_RANGE reads starting a fresh block; it returns
+ * RT_ESTATE when the library cannot be coded (first positions not ascending within a reference, or a read spanning
+ * 2^22 nt more than it matches) -- use rt_bin_reads / rt_bin_reads_host then.  With h_records == NULL it only
+ * counts: *n_blocks = the capacity the real call needs.
+ */
+#define RT_STREAM_BLOCK 2048
+#define RT_STREAM_RANGE (1 << 20)
+#define RT_STREAM_SPECIAL 0x8000u
+#define RT_STREAM_KIND_EXT 0x4000u
+#define RT_STREAM_NULL 0x8000u
+#define RT_STREAM_UNMAPPED 0x01u
+#define RT_STREAM_SECONDARY 0x02u
+#define RT_STREAM_QCFAIL 0x04u
+#define RT_STREAM_DUPLICATE 0x08u
+#define RT_STREAM_REVERSE 0x10u
+#define RT_STREAM_NH_ABSENT 0u
+#define RT_STREAM_NH_ABSENT_MAPQ255 1u
+#define RT_STREAM_NH_ONE 2u
+#define RT_STREAM_NH_OTHER 3u
+#define RT_STREAM_EXT 0x80u
+int rt_stream_pack(int64_t n, const int32_t* h_ref_id, const int32_t* h_first, const int32_t* h_last,
+                   const uint16_t* h_mlen, const uint16_t* h_flag, const uint8_t* h_mapq, const uint8_t* h_nh,
+                   int n_threads, int64_t cap_blocks, uint32_t* h_records /* cap_blocks * RT_STREAM_BLOCK */,
+                   int32_t* h_hdr /* 2 * cap_blocks */, int64_t* n_blocks);
+int rt_bin_stream(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t* d_records /* 16-byte aligned */,
+                  const int32_t* d_hdr, int protocol, int weight, int64_t* d_stats, int64_t* d_len_counts,
+                  void* stream);
+int rt_bin_stream_host(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t* h_records, const int32_t* h_hdr,
+                       int protocol, int64_t* h_stats, int64_t* h_len_counts);
 
 int rt_clear_coverage(rt_ctx* ctx, int32_t* d_cov, void* stream);
 

@@ -18,6 +18,9 @@
 // rt_host_io.cpp: filter cascade + run-length code of ref_id for one chunk of host columns
 int64_t rt_pack_chunk(const int32_t* ref_id, const uint16_t* flag, const uint8_t* mapq, const uint8_t* nh, int64_t m, uint8_t* meta,
                       int64_t* run_start, int32_t* run_ref, int64_t cap);
+// rt_host_io.cpp: one chunk of host columns as a run of record-stream blocks (-1: cannot be coded, -2: cap too small)
+int64_t rt_stream_pack_range(const int32_t* ref_id, const int32_t* first, const int32_t* last, const uint16_t* mlen, const uint16_t* flag,
+                             const uint8_t* mapq, const uint8_t* nh, int64_t m, uint32_t* rec, int32_t* hdr, int64_t cap);
 
 namespace {
 
@@ -124,10 +127,9 @@ struct rt_ctx {
     std::vector<ScorePlan> plans;
 
     // scratch for the host-buffer entry points
-    struct HostStage {                               // page-locked staging of one chunk's meta bytes and run table
-        uint8_t* meta = nullptr;
-        int64_t* run_start = nullptr;
-        int32_t* run_ref = nullptr;
+    struct HostStage {                               // page-locked staging of one chunk's record stream
+        uint32_t* rec = nullptr;
+        int32_t* hdr = nullptr;
         cudaEvent_t copied = nullptr;
         bool busy = false;
     } host_stage[16];
@@ -304,8 +306,11 @@ int build_atoms(rt_ctx* ctx, const std::vector<uint64_t>& desc, const std::vecto
 constexpr size_t kReadBytes = 4 + 4 + 4 + 2 + 2 + 1 + 1;
 constexpr size_t kPackedReadBytes = 4 + 4 + 2 + 1;
 constexpr int64_t kHostChunkReads = 4 << 20;
-constexpr int64_t kChunkRunCap = 4096;            // reference runs per chunk of a library that is grouped by reference
 constexpr int64_t kPackChunkReads = 1 << 20;      // reads per chunk of the packing pipelines
+// stream blocks a chunk may fill: 1.5 records per read (every second read spliced or far from its neighbour) + slack;
+// a chunk that needs more goes as plain columns
+constexpr int64_t kChunkBlockCap = kPackChunkReads * 3 / 2 / RT_STREAM_BLOCK + 64;
+static_assert(kChunkBlockCap * (RT_STREAM_BLOCK * 4 + 8) + 64 <= kPackChunkReads * kReadBytes, "a chunk's stream fits its device slot");
 constexpr int64_t kMaxPipes = 16;
 
 
@@ -409,9 +414,8 @@ void rt_destroy(rt_ctx* ctx) {
         cudaFree(p.d_long_acc);
     }
     for (int s = 0; s < 16; ++s) {
-        if (ctx->host_stage[s].meta) cudaFreeHost(ctx->host_stage[s].meta);
-        if (ctx->host_stage[s].run_start) cudaFreeHost(ctx->host_stage[s].run_start);
-        if (ctx->host_stage[s].run_ref) cudaFreeHost(ctx->host_stage[s].run_ref);
+        if (ctx->host_stage[s].rec) cudaFreeHost(ctx->host_stage[s].rec);
+        if (ctx->host_stage[s].hdr) cudaFreeHost(ctx->host_stage[s].hdr);
         if (ctx->host_stage[s].copied) cudaEventDestroy(ctx->host_stage[s].copied);
         ctx->read_slot[s].release();
         if (ctx->slot_stream[s]) cudaStreamDestroy(ctx->slot_stream[s]);
@@ -645,6 +649,79 @@ int rt_bin_reads_packed(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* d
     return launch_bin(ctx, "rt_bin_reads_packed", a, true, d_cov, n, protocol, weight, d_stats, d_len_counts, stream);
 }
 
+int rt_bin_stream(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t* d_records, const int32_t* d_hdr, int protocol,
+                  int weight, int64_t* d_stats, int64_t* d_len_counts, void* stream) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_bin_stream: ctx is NULL");
+    if (weight != 1 && weight != -1) return fail(ctx, RT_EINVAL, "rt_bin_stream: weight must be +1 or -1");
+    if (ctx->plane == 0) return fail(ctx, RT_ESTATE, "rt_bin_stream: call rt_set_genome first");
+    if (!ctx->have_len_table) return fail(ctx, RT_ESTATE, "rt_bin_stream: call rt_set_length_table first");
+    if (n_blocks < 0 || n_blocks > 0x7fffffff || !d_cov || !d_stats || !d_len_counts || (n_blocks > 0 && (!d_records || !d_hdr)))
+        return fail(ctx, RT_EINVAL, "rt_bin_stream: NULL argument or bad n_blocks");
+    if (reinterpret_cast<uintptr_t>(d_records) & 15) return fail(ctx, RT_EINVAL, "rt_bin_stream: d_records must be 16-byte aligned");
+    if (ctx->track_touched && ctx->layout != RT_LAYOUT_COMPACT)
+        return fail(ctx, RT_ESTATE, "rt_bin_stream: the touched-slot list of the dense layout is kept by rt_bin_reads only");
+    if (n_blocks == 0) return RT_OK;
+    DeviceGuard guard(ctx->device);
+    rt::StreamArgs a{};
+    a.cov = d_cov;
+    a.rec = reinterpret_cast<const uint4*>(d_records);
+    a.hdr = reinterpret_cast<const int2*>(d_hdr);
+    a.protocol = protocol;
+    a.weight = weight;
+    a.len_base = ctx->len_base;
+    a.cmap = ctx->layout == RT_LAYOUT_COMPACT ? ctx->d_cmap : nullptr;
+    a.cbits = ctx->d_cbits;
+    a.len_table = ctx->d_len_table;
+    a.contig_tab = ctx->d_contig_tab;
+    a.n_contig = ctx->n_contig;
+    a.pad = ctx->pad;
+    a.plane_words = (unsigned)(ctx->plane >> 5);
+    a.stats = reinterpret_cast<unsigned long long*>(d_stats);
+    a.len_counts = reinterpret_cast<unsigned long long*>(d_len_counts);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a.cmap) rt::bin_stream_kernel<true><<<(unsigned)n_blocks, rt::kStreamThreads, 0, st>>>(a);
+    else rt::bin_stream_kernel<false><<<(unsigned)n_blocks, rt::kStreamThreads, 0, st>>>(a);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_bin_stream_host(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t* h_records, const int32_t* h_hdr, int protocol,
+                       int64_t* h_stats, int64_t* h_len_counts) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_bin_stream_host: ctx is NULL");
+    if (!h_stats || !h_len_counts) return fail(ctx, RT_EINVAL, "rt_bin_stream_host: NULL output");
+    if (n_blocks < 0 || (n_blocks > 0 && (!h_records || !h_hdr))) return fail(ctx, RT_EINVAL, "rt_bin_stream_host: NULL stream");
+    DeviceGuard guard(ctx->device);
+    const size_t acc_bytes = sizeof(int64_t) * (RT_N_STATS + RT_LEN_TABLE);
+    RT_CUDA(ctx, ctx->stats_buf.reserve(acc_bytes));
+    int64_t* d_stats = static_cast<int64_t*>(ctx->stats_buf.p);
+    int64_t* d_len_counts = d_stats + RT_N_STATS;
+    for (int s = 0; s < 2; ++s)
+        if (!ctx->slot_stream[s]) RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking));
+    RT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, acc_bytes, ctx->slot_stream[0]));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[0]));
+    // chunks of 2048 blocks (16 MB of records) alternate between two device slots: copy of one || K1 of the other
+    const int64_t chunk = 2048;
+    const size_t rec_bytes = sizeof(uint32_t) * RT_STREAM_BLOCK * (size_t)chunk;
+    int slot = 0;
+    for (int64_t at = 0; at < n_blocks; at += chunk, slot ^= 1) {
+        const int64_t m = std::min(chunk, n_blocks - at);
+        RT_CUDA(ctx, ctx->read_slot[slot].reserve(rec_bytes + sizeof(int32_t) * 2 * (size_t)chunk));
+        uint32_t* d_rec = static_cast<uint32_t*>(ctx->read_slot[slot].p);
+        int32_t* d_hdr = reinterpret_cast<int32_t*>(static_cast<char*>(ctx->read_slot[slot].p) + rec_bytes);
+        cudaStream_t st = ctx->slot_stream[slot];   // stream order protects the slot's previous use
+        RT_CUDA(ctx, cudaMemcpyAsync(d_rec, h_records + at * RT_STREAM_BLOCK, sizeof(uint32_t) * RT_STREAM_BLOCK * (size_t)m, cudaMemcpyHostToDevice, st));
+        RT_CUDA(ctx, cudaMemcpyAsync(d_hdr, h_hdr + 2 * at, sizeof(int32_t) * 2 * (size_t)m, cudaMemcpyHostToDevice, st));
+        int rc = rt_bin_stream(ctx, d_cov, m, d_rec, d_hdr, protocol, 1, d_stats, d_len_counts, st);
+        if (rc != RT_OK) return rc;
+    }
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[0]));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[1]));
+    RT_CUDA(ctx, cudaMemcpy(h_stats, d_stats, sizeof(int64_t) * RT_N_STATS, cudaMemcpyDeviceToHost));
+    RT_CUDA(ctx, cudaMemcpy(h_len_counts, d_len_counts, sizeof(int64_t) * RT_LEN_TABLE, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
 int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_ref_id, const int32_t* h_first,
                       const int32_t* h_last, const uint16_t* h_mlen, const uint16_t* h_flag,
                       const uint8_t* h_mapq, const uint8_t* h_nh, int protocol, int sorted_hint,
@@ -654,6 +731,8 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
     if (n > 0 && (!h_ref_id || !h_first || !h_last || !h_mlen || !h_flag || !h_mapq || !h_nh))
         return fail(ctx, RT_EINVAL, "rt_bin_reads_host: NULL column");
     DeviceGuard guard(ctx->device);
+    // the sparse-clear list of the dense layout is kept by the column kernel only
+    const bool use_stream = sorted_hint && !(ctx->track_touched && ctx->layout != RT_LAYOUT_COMPACT);
     const size_t acc_bytes = sizeof(int64_t) * (RT_N_STATS + RT_LEN_TABLE);
     RT_CUDA(ctx, ctx->stats_buf.reserve(acc_bytes));
     int64_t* d_stats = static_cast<int64_t*>(ctx->stats_buf.p);
@@ -666,33 +745,31 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
         int rc = ensure_touched_capacity(ctx, ctx->touched_reserved + n);
         if (rc != RT_OK) return rc;
     }
-    // Host columns are the 18 B/read a BAM decoder produces.  With `sorted_hint` (reads grouped by reference) they cross
-    // PCIe as 11 B/read packed records: a few pipeline threads each take the next chunk of the library, evaluate its
-    // filter cascade into one meta byte per read and run-length code its ref_id into their own page-locked staging
-    // slot, start the copies (first / last / mlen straight from the caller's columns) on their own stream and launch
-    // K1 behind them -- so the packing of some chunks, the copies of others and the kernels of yet others overlap.
-    // A chunk with too many reference runs (not grouped after all) is sent as plain columns.
+    // Host columns are the 18 B/read a BAM decoder produces.  With `use_stream` (a coordinate-sorted library) they cross
+    // PCIe as a 4 B/read record stream: a few pipeline threads each take the next chunk of the library, delta-code it
+    // into their own page-locked staging slot, start the copy on their own stream and launch K1 behind it -- so the
+    // coding of some chunks, the copies of others and the kernels of yet others overlap.  A chunk that cannot be coded
+    // (positions descend: not sorted after all) is sent as plain columns.
     int64_t pack_chunk_reads = kPackChunkReads;
     if (const char* e = getenv("RT_PACK_CHUNK")) pack_chunk_reads = std::min<int64_t>(kPackChunkReads, std::max(1 << 16, atoi(e)));
-    const int64_t chunk = sorted_hint ? std::min<int64_t>(pack_chunk_reads, std::max<int64_t>(n, 1))
+    const int64_t chunk = use_stream ? std::min<int64_t>(pack_chunk_reads, std::max<int64_t>(n, 1))
                                       : std::min<int64_t>(kHostChunkReads, std::max<int64_t>(n, 1));
     const int64_t n_chunks = (n + chunk - 1) / chunk;
     int64_t want_pipes = std::min<int64_t>(kMaxPipes, (int64_t)std::thread::hardware_concurrency() / 2);
     if (const char* e = getenv("RT_PACK_PIPES")) want_pipes = std::min<int64_t>(kMaxPipes, std::max(1, atoi(e)));
-    const int n_pipes = sorted_hint ? (int)std::max<int64_t>(1, std::min<int64_t>(want_pipes, n_chunks)) : 2;
+    const int n_pipes = use_stream ? (int)std::max<int64_t>(1, std::min<int64_t>(want_pipes, n_chunks)) : 2;
     const bool timing = getenv("RT_HOST_TIMING") != nullptr;
     std::atomic<long long> pack_ns{0}, wait_ns{0}, issue_ns{0};
     const auto t_begin = std::chrono::steady_clock::now();
     // per-slot layout: 8-byte run table first, then the 4-byte columns, so that every column stays naturally aligned
-    const size_t slot_bytes = (size_t)chunk * kReadBytes + sizeof(int64_t) * (kChunkRunCap + 1) + sizeof(int32_t) * kChunkRunCap + 64;
+    const size_t slot_bytes = std::max((size_t)chunk, (size_t)(use_stream ? kPackChunkReads : 0)) * kReadBytes + 64;
     for (int s = 0; s < n_pipes; ++s) {
         if (!ctx->slot_stream[s]) RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking));
         RT_CUDA(ctx, ctx->read_slot[s].reserve(slot_bytes));
         rt_ctx::HostStage& hs = ctx->host_stage[s];
-        if (sorted_hint && !hs.meta) {
-            RT_CUDA(ctx, cudaHostAlloc(&hs.meta, (size_t)kPackChunkReads, cudaHostAllocDefault));
-            RT_CUDA(ctx, cudaHostAlloc(&hs.run_start, sizeof(int64_t) * (kChunkRunCap + 1), cudaHostAllocDefault));
-            RT_CUDA(ctx, cudaHostAlloc(&hs.run_ref, sizeof(int32_t) * kChunkRunCap, cudaHostAllocDefault));
+        if (use_stream && !hs.rec) {
+            RT_CUDA(ctx, cudaHostAlloc(&hs.rec, sizeof(uint32_t) * RT_STREAM_BLOCK * (size_t)kChunkBlockCap, cudaHostAllocDefault));
+            RT_CUDA(ctx, cudaHostAlloc(&hs.hdr, sizeof(int32_t) * 2 * (size_t)kChunkBlockCap, cudaHostAllocDefault));
             RT_CUDA(ctx, cudaEventCreateWithFlags(&hs.copied, cudaEventDisableTiming));
         }
         hs.busy = false;
@@ -703,16 +780,16 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
     auto pipeline = [&](int s) {
         cudaSetDevice(ctx->device);
         char* base = static_cast<char*>(ctx->read_slot[s].p);
-        int64_t* d_run_start = reinterpret_cast<int64_t*>(base);
-        int32_t* d_ref = reinterpret_cast<int32_t*>(d_run_start + kChunkRunCap + 1);
+        // a chunk is either a record stream (records, then block headers) or plain columns
+        uint32_t* d_rec = reinterpret_cast<uint32_t*>(base);
+        int32_t* d_hdr = reinterpret_cast<int32_t*>(d_rec + RT_STREAM_BLOCK * (size_t)kChunkBlockCap);
+        int32_t* d_ref = reinterpret_cast<int32_t*>(base);
         int32_t* d_first = d_ref + chunk;
         int32_t* d_last = d_first + chunk;
-        int32_t* d_run_ref = d_last + chunk;
-        uint16_t* d_mlen = reinterpret_cast<uint16_t*>(d_run_ref + kChunkRunCap);
+        uint16_t* d_mlen = reinterpret_cast<uint16_t*>(d_last + chunk);
         uint16_t* d_flag = d_mlen + chunk;
         uint8_t* d_mapq = reinterpret_cast<uint8_t*>(d_flag + chunk);
         uint8_t* d_nh = d_mapq + chunk;
-        uint8_t* d_meta = d_mapq;                   // a chunk is either packed (meta) or plain (mapq, nh)
         cudaStream_t st = ctx->slot_stream[s];      // stream order protects the device slot's previous use
         rt_ctx::HostStage& hs = ctx->host_stage[s];
         auto check = [&](cudaError_t e, const char* what) {
@@ -725,42 +802,40 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
             const int64_t c = next_chunk.fetch_add(1);
             if (c >= n_chunks || status.load() != RT_OK) break;
             const int64_t at = c * chunk, m = std::min(chunk, n - at);
-            int64_t runs = -1;
+            int64_t blocks = -1;
             const auto t0 = std::chrono::steady_clock::now();
-            if (sorted_hint) {
+            if (use_stream) {
                 if (hs.busy && !check(cudaEventSynchronize(hs.copied), "cudaEventSynchronize")) break;   // staging slot free again
                 hs.busy = false;
                 const auto t1 = std::chrono::steady_clock::now();
-                runs = rt_pack_chunk(h_ref_id + at, h_flag + at, h_mapq + at, h_nh + at, m, hs.meta, hs.run_start, hs.run_ref, kChunkRunCap);
+                blocks = rt_stream_pack_range(h_ref_id + at, h_first + at, h_last + at, h_mlen + at, h_flag + at, h_mapq + at, h_nh + at, m,
+                                              hs.rec, hs.hdr, kChunkBlockCap);
                 if (timing) {
                     wait_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
                     pack_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t1).count();
                 }
             }
             const auto t2 = std::chrono::steady_clock::now();
-            if (!check(cudaMemcpyAsync(d_first, h_first + at, 4 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
-                !check(cudaMemcpyAsync(d_last, h_last + at, 4 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
-                !check(cudaMemcpyAsync(d_mlen, h_mlen + at, 2 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync"))
-                break;
             int rc;
-            if (runs >= 0) {
-                if (!check(cudaMemcpyAsync(d_meta, hs.meta, m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
-                    !check(cudaMemcpyAsync(d_run_start, hs.run_start, sizeof(int64_t) * (size_t)(runs + 1), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
-                    !check(cudaMemcpyAsync(d_run_ref, hs.run_ref, sizeof(int32_t) * (size_t)runs, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+            if (blocks >= 0) {
+                if (!check(cudaMemcpyAsync(d_rec, hs.rec, sizeof(uint32_t) * RT_STREAM_BLOCK * (size_t)blocks, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+                    !check(cudaMemcpyAsync(d_hdr, hs.hdr, sizeof(int32_t) * 2 * (size_t)blocks, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
                     !check(cudaEventRecord(hs.copied, st), "cudaEventRecord"))
                     break;
                 hs.busy = true;
                 std::lock_guard<std::mutex> lock(ctx->launch_mutex);
-                rc = rt_bin_reads_packed(ctx, d_cov, m, d_first, d_last, d_mlen, d_meta, 0, runs, d_run_start, d_run_ref, protocol, 1,
-                                         d_stats, d_len_counts, st);
+                rc = rt_bin_stream(ctx, d_cov, blocks, d_rec, d_hdr, protocol, 1, d_stats, d_len_counts, st);
             } else {
-                if (!check(cudaMemcpyAsync(d_ref, h_ref_id + at, 4 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+                if (!check(cudaMemcpyAsync(d_first, h_first + at, 4 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+                    !check(cudaMemcpyAsync(d_last, h_last + at, 4 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+                    !check(cudaMemcpyAsync(d_mlen, h_mlen + at, 2 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+                    !check(cudaMemcpyAsync(d_ref, h_ref_id + at, 4 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
                     !check(cudaMemcpyAsync(d_flag, h_flag + at, 2 * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
                     !check(cudaMemcpyAsync(d_mapq, h_mapq + at, m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
                     !check(cudaMemcpyAsync(d_nh, h_nh + at, m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync"))
                     break;
                 std::lock_guard<std::mutex> lock(ctx->launch_mutex);
-                rc = rt_bin_reads(ctx, d_cov, m, d_ref, d_first, d_last, d_mlen, d_flag, d_mapq, d_nh, protocol, sorted_hint, 1,
+                rc = rt_bin_reads(ctx, d_cov, m, d_ref, d_first, d_last, d_mlen, d_flag, d_mapq, d_nh, protocol, 0, 1,
                                   d_stats, d_len_counts, st);
             }
             if (timing) issue_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t2).count();

@@ -5,6 +5,7 @@
 //     them (np.float64 / Python float shortest repr, str(list) profile).
 // No GPU is involved; these entry points also work on a CPU-only box.
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <cstdint>
 #include <cstdio>
@@ -457,6 +458,200 @@ int rt_pack_read_meta(int64_t n, const int32_t* ref_id, const uint16_t* flag, co
         }
     if (n > 0) run_start[r] = n;
     *n_runs = r;
+    return RT_OK;
+}
+
+}  // extern "C"
+
+// ---- record stream (4 B/read, format in ribotricer_b200.h): delta code of a coordinate-sorted library ----
+namespace {
+
+struct StreamWriter {
+    uint32_t* rec;          // NULL: count only
+    int32_t* hdr;
+    int64_t cap;
+    int64_t nb = 0;         // blocks opened so far
+    int fill = RT_STREAM_BLOCK;   // records in the open block (RT_STREAM_BLOCK: none open)
+    bool open(int32_t rid, int32_t at) {
+        if (rec && nb > 0)
+            for (int k = fill; k < RT_STREAM_BLOCK; ++k) rec[(nb - 1) * RT_STREAM_BLOCK + k] = RT_STREAM_NULL;
+        if (rec && nb >= cap) return false;
+        if (rec) {
+            hdr[2 * nb] = rid;
+            hdr[2 * nb + 1] = at;
+        }
+        ++nb;
+        fill = 0;
+        return true;
+    }
+    void put(uint32_t w) {
+        if (rec) rec[(nb - 1) * RT_STREAM_BLOCK + fill] = w;
+        ++fill;
+    }
+    void close() {
+        if (rec && nb > 0)
+            for (int k = fill; k < RT_STREAM_BLOCK; ++k) rec[(nb - 1) * RT_STREAM_BLOCK + k] = RT_STREAM_NULL;
+        fill = RT_STREAM_BLOCK;
+    }
+};
+
+}  // namespace
+
+// The usual group of a sorted library: kStreamGroup reads of one reference, each 0..32767 nt after the one before, none
+// spliced or longer than 255.  Two branch-free loops the compiler vectorises (AVX2 clone picked at load time): the
+// test, then one record per read.
+constexpr int kStreamGroup = 64;
+
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("avx2", "default")))
+#endif
+bool rt_stream_group_plain(const int32_t* __restrict__ ref_id, const int32_t* __restrict__ first, const int32_t* __restrict__ last,
+                           const uint16_t* __restrict__ mlen, int32_t cur_ref, int64_t cur_pos) {
+    const int64_t d0 = (int64_t)first[0] - cur_pos;
+    uint32_t bad = (d0 < 0) | (d0 > 32767);
+    for (int k = 1; k < kStreamGroup; ++k) bad |= (uint32_t)((uint32_t)first[k] - (uint32_t)first[k - 1]) > 32767u;
+    for (int k = 0; k < kStreamGroup; ++k)
+        bad |= (uint32_t)(ref_id[k] ^ cur_ref) | (uint32_t)(mlen[k] > 255) | (uint32_t)(last[k] - first[k] + 1 - (int32_t)mlen[k]);
+    return bad == 0;
+}
+
+// The same test fused with the coding: `out` receives the group's records whether or not the group turns out plain
+// (the caller only keeps them when it does), so every column is read once.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("avx2", "default")))
+#endif
+bool rt_stream_group_code(const int32_t* __restrict__ ref_id, const int32_t* __restrict__ first, const int32_t* __restrict__ last,
+                          const uint16_t* __restrict__ mlen, const uint16_t* __restrict__ flag, const uint8_t* __restrict__ mapq,
+                          const uint8_t* __restrict__ nh, int32_t cur_ref, int64_t cur_pos, uint32_t* __restrict__ out) {
+    const int64_t d0 = (int64_t)first[0] - cur_pos;
+    uint32_t delta[kStreamGroup];
+    delta[0] = (uint32_t)d0;
+    for (int k = 1; k < kStreamGroup; ++k) delta[k] = (uint32_t)first[k] - (uint32_t)first[k - 1];
+    uint32_t bad = (d0 < 0) | (d0 > 32767);
+    for (int k = 0; k < kStreamGroup; ++k) {
+        const uint32_t f = flag[k], nn = nh[k], qq = mapq[k], l = mlen[k];
+        const uint32_t state = nn == 0u ? (uint32_t)(qq == 255u) : 3u - (uint32_t)(nn == 1u);
+        const uint32_t meta = ((f >> 2) & 1u) | ((f >> 7) & 0xeu) | (f & 0x10u) | (state << 5);
+        bad |= (uint32_t)(delta[k] > 32767u) | (uint32_t)(ref_id[k] ^ cur_ref) | (uint32_t)(l > 255u) | (uint32_t)(last[k] - first[k] + 1 - (int32_t)l);
+        out[k] = delta[k] | (l << 16) | (meta << 24);
+    }
+    return bad == 0;
+}
+
+// Reads [0, m) of the decoder's columns as one run of stream blocks.  Returns the number of blocks, -1 when the
+// reads cannot be coded (positions descend inside a reference, or a span beyond the extension's 22 bits), -2 when
+// `cap` blocks are not enough.  rec == NULL counts only.
+int64_t rt_stream_pack_range(const int32_t* __restrict__ ref_id, const int32_t* __restrict__ first, const int32_t* __restrict__ last,
+                             const uint16_t* __restrict__ mlen, const uint16_t* __restrict__ flag, const uint8_t* __restrict__ mapq,
+                             const uint8_t* __restrict__ nh, int64_t m, uint32_t* rec, int32_t* hdr, int64_t cap) {
+    StreamWriter w{rec, hdr, cap};
+    int32_t cur_ref = m > 0 ? ref_id[0] : 0;
+    int64_t cur_pos = m > 0 ? first[0] : 0;
+    int64_t i = 0;
+    while (i < m) {
+        if (i + kStreamGroup <= m && w.fill + kStreamGroup <= RT_STREAM_BLOCK &&
+            (rec ? rt_stream_group_code(ref_id + i, first + i, last + i, mlen + i, flag + i, mapq + i, nh + i, cur_ref, cur_pos,
+                                        rec + (w.nb - 1) * RT_STREAM_BLOCK + w.fill)
+                 : rt_stream_group_plain(ref_id + i, first + i, last + i, mlen + i, cur_ref, cur_pos))) {
+            w.fill += kStreamGroup;
+            i += kStreamGroup;
+            cur_pos = first[i - 1];
+            continue;
+        }
+        const int64_t stop = std::min<int64_t>(m, i + kStreamGroup);
+        for (; i < stop; ++i) {
+            const unsigned f = flag[i];
+            const unsigned nn = nh[i], qq = mapq[i];
+            const unsigned state = nn == 0u ? (qq == 255u ? RT_STREAM_NH_ABSENT_MAPQ255 : RT_STREAM_NH_ABSENT)
+                                            : (nn == 1u ? RT_STREAM_NH_ONE : RT_STREAM_NH_OTHER);
+            // SAM 0x4 -> bit 0, 0x100 / 0x200 / 0x400 -> bits 1-3, 0x10 stays bit 4
+            const unsigned meta = ((f >> 2) & 1u) | ((f >> 7) & 0xeu) | (f & 0x10u) | (state << 5);
+            if (f & 0x704u) {      // the flags decide (bam.py:77-88): the reference never looks at position or length
+                if (w.fill == RT_STREAM_BLOCK && !w.open(cur_ref, (int32_t)cur_pos)) return -2;
+                w.put(meta << 24);
+                continue;
+            }
+            const int32_t rid = ref_id[i];
+            const int64_t at = first[i];
+            const unsigned l = mlen[i];
+            const int64_t extra = (int64_t)last[i] - at + 1 - (int64_t)l;
+            int64_t d = at - cur_pos;
+            const unsigned ext = (l > 255u) | (extra != 0);
+            if (extra < 0 || extra >= (1 << 22)) return -1;
+            bool fresh = w.fill == RT_STREAM_BLOCK || rid != cur_ref || d >= (1ll << 30);
+            if (!fresh) {
+                if (d < 0) return -1;
+                fresh = w.fill + 1 + (int)(d > 32767) + (int)ext > RT_STREAM_BLOCK;
+            }
+            if (fresh) {
+                if (!w.open(rid, (int32_t)at)) return -2;
+                cur_ref = rid;
+                d = 0;
+            }
+            if (d > 32767) {
+                w.put(RT_STREAM_SPECIAL | ((uint32_t)(d & 0xffff) << 16) | (uint32_t)(d >> 16));
+                d = 0;
+            }
+            w.put((uint32_t)d | ((l & 255u) << 16) | ((meta | (ext ? RT_STREAM_EXT : 0u)) << 24));
+            if (ext) w.put(RT_STREAM_SPECIAL | RT_STREAM_KIND_EXT | (l >> 8) | ((uint32_t)(extra >> 16) << 8) | ((uint32_t)(extra & 0xffff) << 16));
+            cur_pos = at;
+        }
+    }
+    w.close();
+    return w.nb;
+}
+
+extern "C" {
+
+int rt_stream_pack(int64_t n, const int32_t* ref_id, const int32_t* first, const int32_t* last, const uint16_t* mlen,
+                   const uint16_t* flag, const uint8_t* mapq, const uint8_t* nh, int n_threads, int64_t cap_blocks,
+                   uint32_t* records, int32_t* hdr, int64_t* n_blocks) {
+    if (n < 0 || !n_blocks || (n > 0 && (!ref_id || !first || !last || !mlen || !flag || !mapq || !nh)) || (records && !hdr))
+        return RT_EINVAL;
+    const int64_t n_ranges = (n + RT_STREAM_RANGE - 1) / RT_STREAM_RANGE;
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, n_ranges));
+    std::vector<int64_t> blocks(n_ranges + 1, 0);
+    auto sweep = [&](bool write) {
+        std::atomic<int64_t> next{0};
+        std::atomic<int64_t> worst{0};
+        auto work = [&]() {
+            for (;;) {
+                const int64_t r = next.fetch_add(1);
+                if (r >= n_ranges) break;
+                const int64_t at = r * RT_STREAM_RANGE, m = std::min<int64_t>(RT_STREAM_RANGE, n - at);
+                int64_t got;
+                if (write)
+                    got = rt_stream_pack_range(ref_id + at, first + at, last + at, mlen + at, flag + at, mapq + at, nh + at, m,
+                                               records + blocks[r] * RT_STREAM_BLOCK, hdr + 2 * blocks[r], blocks[r + 1] - blocks[r]);
+                else
+                    got = blocks[r + 1] = rt_stream_pack_range(ref_id + at, first + at, last + at, mlen + at, flag + at, mapq + at,
+                                                               nh + at, m, nullptr, nullptr, 0);
+                if (got < 0) {
+                    int64_t seen = worst.load();
+                    while (got < seen && !worst.compare_exchange_weak(seen, got)) {}
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+        return worst.load();
+    };
+    if (sweep(false) < 0) {
+        g_io_error = "rt_stream_pack: the library cannot be delta-coded (first positions descend inside a reference, or a read "
+                     "spans 2^22 nt more than it matches); use the column entry points";
+        return RT_ESTATE;
+    }
+    for (int64_t r = 0; r < n_ranges; ++r) blocks[r + 1] += blocks[r];     // counts -> exclusive offsets
+    *n_blocks = blocks[n_ranges];
+    if (!records) return RT_OK;
+    if (cap_blocks < blocks[n_ranges]) {
+        g_io_error = "rt_stream_pack: cap_blocks is smaller than the stream (call with h_records = NULL for the size)";
+        return RT_EINVAL;
+    }
+    if (sweep(true) < 0) return RT_ESTATE;
     return RT_OK;
 }
 

@@ -2426,6 +2426,215 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
         if (s_len[i]) atomicAdd(a.len_counts + i, (unsigned long long)((long long)a.weight * s_len[i]));
 }
 
+// ---- K1 on a record stream ----------------------------------------------------------------------------
+// A coordinate-sorted library as 4-byte delta-coded records in blocks of RT_STREAM_BLOCK (format: ribotricer_b200.h).
+// One CTA per block: a thread takes 8 consecutive records (two 128-bit loads), positions come from a block-wide
+// prefix sum over the records' advances, the contig is a property of the block.  The filter cascade (bam.py:77-91,
+// common.py:33-69) is one shared-memory lookup on the 7 raw bits the record carries; runs of equal slots are merged
+// inside the thread's strip (duplicated 5' ends are adjacent in a sorted library) before the RED.
+struct StreamArgs {
+    int32_t* cov;
+    const uint4* rec;              // n_blocks * RT_STREAM_BLOCK records
+    const int2* hdr;               // per block: (ref_id, position the deltas start from)
+    int protocol;
+    int weight;
+    int len_base;
+    const uint2* cmap;
+    const unsigned* cbits;
+    const int32_t* len_table;
+    const int2* contig_tab;
+    int n_contig;
+    int pad;
+    unsigned plane_words;
+    unsigned long long* stats;
+    unsigned long long* len_counts;
+};
+
+constexpr int kStreamThreads = 256;
+constexpr int kStreamStrip = RT_STREAM_BLOCK / kStreamThreads;      // records per thread
+static_assert(kStreamStrip == 8, "bin_stream_kernel loads a strip as two uint4");
+
+__device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned s) {   // PTX shl: shift amounts above 31 give 0
+    unsigned r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+    return r;
+}
+
+template <bool Compact>
+__global__ void __launch_bounds__(kStreamThreads) bin_stream_kernel(const StreamArgs a) {
+    __shared__ unsigned int s_stats[RT_N_STATS];
+    __shared__ unsigned int s_len[kLenHist];
+    __shared__ unsigned int s_warp[kStreamThreads / 32];
+    __shared__ uint8_t s_cat[128];
+    for (int i = threadIdx.x; i < kLenHist; i += kStreamThreads) s_len[i] = 0;
+    if (threadIdx.x < RT_N_STATS) s_stats[threadIdx.x] = 0;
+    if (threadIdx.x < 128) {       // the cascade on the record's raw bits, once per CTA
+        const unsigned m = threadIdx.x, st = (m >> 5) & 3u;
+        int cat;
+        if (m & RT_STREAM_QCFAIL) cat = RT_ST_QCFAIL;             // bam.py:77
+        else if (m & RT_STREAM_DUPLICATE) cat = RT_ST_DUPLICATE;  // bam.py:80
+        else if (m & RT_STREAM_SECONDARY) cat = RT_ST_SECONDARY;  // bam.py:83
+        else if (m & RT_STREAM_UNMAPPED) cat = RT_ST_UNMAPPED;    // bam.py:86
+        else cat = (st == RT_STREAM_NH_ONE || st == RT_STREAM_NH_ABSENT_MAPQ255) ? RT_ST_VALID : RT_ST_MULTI;   // common.py:53-69
+        s_cat[m] = (uint8_t)cat;
+    }
+
+    using slot_t = typename std::conditional<Compact, unsigned, long long>::type;
+    constexpr slot_t kNone = (slot_t)-1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int2 hd = __ldg(a.hdr + blockIdx.x);
+    const uint4* p = a.rec + (size_t)blockIdx.x * (RT_STREAM_BLOCK / 4) + 2 * threadIdx.x;
+    unsigned w[kStreamStrip + 1];
+    {
+        const uint4 r0 = __ldg(p), r1 = __ldg(p + 1);
+        w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w;
+        w[4] = r1.x; w[5] = r1.y; w[6] = r1.z; w[7] = r1.w;
+        // an extension record follows its read, possibly in the next thread's strip (never in the next block)
+        w[8] = __shfl_down_sync(kFull, w[0], 1);
+        if (lane == 31) w[8] = threadIdx.x == kStreamThreads - 1 ? (unsigned)RT_STREAM_NULL : __ldg(reinterpret_cast<const unsigned*>(p + 2));
+    }
+    // positions: inclusive prefix of the advances inside the strip, exclusive prefix over the strips of the block
+    unsigned pos[kStreamStrip];
+    unsigned run = 0;
+#pragma unroll
+    for (int j = 0; j < kStreamStrip; ++j) {
+        const unsigned x = w[j];
+        const unsigned skip = (x & RT_STREAM_KIND_EXT) ? 0u : ((x >> 16) | ((x & 0x3fffu) << 16));
+        run += (x & RT_STREAM_SPECIAL) ? skip : (x & 0x7fffu);
+        pos[j] = run;
+    }
+    unsigned incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned before = (unsigned)hd.y + incl - run;
+#pragma unroll
+    for (int k = 0; k < kStreamThreads / 32 - 1; ++k) before += k < warp ? s_warp[k] : 0u;
+
+    const int c = hd.x;
+    const bool known = (unsigned)c < (unsigned)a.n_contig;
+    const int2 ct = known ? __ldg(a.contig_tab + c) : make_int2(0, 0);
+    const unsigned span = (unsigned)(ct.x + 2 * a.pad);
+    const bool fwd = a.protocol == RT_PROTOCOL_FORWARD;
+    const bool stores = a.protocol <= RT_PROTOCOL_REVERSE;
+
+    unsigned packed = 0, len_lo = 0, len_hi = 0, n_reads = 0;
+    unsigned wd[kStreamStrip], bit[kStreamStrip], cb[kStreamStrip];
+#pragma unroll
+    for (int j = 0; j < kStreamStrip; ++j) {
+        const unsigned x = w[j];
+        const bool normal = !(x & RT_STREAM_SPECIAL);
+        const unsigned meta = x >> 24;
+        int l = (int)((x >> 16) & 0xffu);
+        int extra = 0;
+        if (normal && (meta & RT_STREAM_EXT)) {
+            const unsigned e = w[j + 1];
+            l |= (int)((e & 0xffu) << 8);
+            extra = (int)((e >> 16) | (((e >> 8) & 0x3fu) << 16));
+        }
+        int cat = normal ? (int)s_cat[meta & 0x7fu] : 0;
+        n_reads += normal ? 1u : 0u;
+        int len = -1;
+        bool live = false;
+        wd[j] = 0; bit[j] = 0;
+        if (cat == RT_ST_VALID) {
+            const int mode = __ldg(a.len_table + l);
+            const bool minus = ((meta & RT_STREAM_REVERSE) != 0) == fwd;          // bam.py:105-131
+            const int first = (int)(before + pos[j]);
+            const int at = minus ? first + l - 1 + extra : first;
+            if (mode == RT_LEN_FILTERED || !stores) {
+                cat = 0;                                                           // bam.py:101 / no protocol branch
+            } else if (!known) {
+                cat = RT_ST_BADREF;                                                // bam.py:133
+            } else {
+                len = l;                                                           // bam.py:136
+                if (mode != RT_LEN_UNUSED) {                                       // detect_orfs.py:74
+                    const unsigned q = (unsigned)(at + (minus ? -mode : mode) + a.pad);
+                    if (q >= span) {
+                        atomicAdd(&s_stats[RT_ST_OOB], 1u);
+                    } else {
+                        const unsigned in_contig = q + 1u;
+                        wd[j] = (minus ? a.plane_words : 0u) + (unsigned)ct.y + (in_contig >> 5);
+                        bit[j] = in_contig & 31u;
+                        live = true;
+                    }
+                }
+            }
+        }
+        packed += shl_clamp(1u, 4u * (unsigned)cat - 4u);         // cat 0 counts nothing
+        const unsigned sh = len >= 0 ? 4u * (unsigned)(len - a.len_base) : 255u;
+        len_lo += shl_clamp(1u, sh);
+        len_hi += shl_clamp(1u, sh - 32u);
+        if (len >= 0 && (unsigned)(len - a.len_base) >= 16u) {
+            if (len < kLenHist) atomicAdd(&s_len[len], 1u);
+            else atomicAdd(a.len_counts + len, (unsigned long long)(long long)a.weight);
+        }
+        if (Compact) cb[j] = live ? __ldg(a.cbits + (wd[j] >> 5)) : 0u;
+        else cb[j] = live ? 0xffffffffu : 0u;
+    }
+    slot_t slot[kStreamStrip];
+    if (Compact) {
+        uint2 m[kStreamStrip];
+#pragma unroll
+        for (int j = 0; j < kStreamStrip; ++j)
+            m[j] = ((cb[j] >> (wd[j] & 31u)) & 1u) ? __ldg(a.cmap + wd[j]) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int j = 0; j < kStreamStrip; ++j) {
+            const unsigned above = m[j].x >> bit[j];
+            slot[j] = (above & 1u) ? (slot_t)(m[j].y - (unsigned)__popc(above)) : kNone;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kStreamStrip; ++j)
+            slot[j] = cb[j] ? (slot_t)(((unsigned long long)wd[j] << 5) | bit[j]) : kNone;
+    }
+    // detect_orfs.py:82 with duplicates merged: one RED per run of equal slots inside the strip
+    slot_t cur = kNone;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kStreamStrip; ++j) {
+        if (slot[j] != cur) {
+            if (cur != kNone) atomicAdd(a.cov + cur, a.weight * cnt);
+            cur = slot[j];
+            cnt = 0;
+        }
+        ++cnt;
+    }
+    if (cur != kNone) atomicAdd(a.cov + cur, a.weight * cnt);
+
+    {   // per-thread 4-bit length counters -> one REDUX per length, one shared atomic per lane
+        unsigned mine_len = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const unsigned v = __reduce_add_sync(kFull, ((k < 8 ? len_lo : len_hi) >> (4 * (k & 7))) & 15u);
+            if (lane == k) mine_len = v;
+        }
+        const int l = a.len_base + lane;
+        if (lane < 16 && mine_len && l >= 0) {
+            if (l < kLenHist) atomicAdd(&s_len[l], mine_len);
+            else atomicAdd(a.len_counts + l, (unsigned long long)((long long)a.weight * mine_len));
+        }
+    }
+    unsigned mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const unsigned v = __reduce_add_sync(kFull, (packed >> (4 * k)) & 15u);
+        if (lane == k) mine = v;
+    }
+    if (lane < 8 && mine) atomicAdd(&s_stats[1 + lane], mine);
+    const unsigned reads = __reduce_add_sync(kFull, n_reads);
+    if (lane == 0 && reads) atomicAdd(&s_stats[RT_ST_TOTAL], reads);
+    __syncthreads();
+    if (threadIdx.x < RT_N_STATS && s_stats[threadIdx.x])
+        atomicAdd(a.stats + threadIdx.x, (unsigned long long)((long long)a.weight * s_stats[threadIdx.x]));
+    for (int i = threadIdx.x; i < kLenHist; i += kStreamThreads)
+        if (s_len[i]) atomicAdd(a.len_counts + i, (unsigned long long)((long long)a.weight * s_len[i]));
+}
+
 // Compact layout: one (mask, top) word per 32 dense slots.  A member slot with bit b maps to
 // top - popc(mask >> b): members keep their genome order and sit back to back in the compact buffer.
 __global__ void __launch_bounds__(256) build_cmap_kernel(const uint64_t* __restrict__ atoms, const uint64_t* __restrict__ atoms_c,

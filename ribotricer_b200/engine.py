@@ -328,6 +328,71 @@ class Engine:
             _np_ptr(packed["run_ref"]), protocol_code(protocol), _np_ptr(stats), _np_ptr(len_counts)))
         return dict(zip(_lib.ST_NAMES, stats.tolist())), len_counts
 
+    def stream_reads(self, cols: dict, pinned: bool = False, n_threads: int = 0) -> dict:
+        """A coordinate-sorted library as the 4 B/read record stream of ``rt_stream_pack`` (blocks of 2,048 delta-coded
+        records; the raw filter bits travel with every read and the cascade runs on the device).  Raises ``RtError``
+        when the library cannot be coded (not sorted): use the column entry points then."""
+        t = self.torch
+        host = {}
+        for name, dt in READ_COLUMNS:
+            v = cols[name]
+            if hasattr(v, "cpu"):                       # torch tensor (16-bit columns are stored as int16)
+                v = v.cpu().numpy()
+                if v.dtype.itemsize == np.dtype(dt).itemsize and v.dtype != dt:
+                    v = v.view(dt)
+            host[name] = np.ascontiguousarray(v, dt)
+        n = len(host["ref_id"])
+        ptrs = [_np_ptr(host[name]) for name, _ in READ_COLUMNS]
+        n_blocks = C.c_int64(0)
+        rc = self.lib.rt_stream_pack(n, *ptrs, int(n_threads), 0, None, None, C.byref(n_blocks))
+        if rc != 0:
+            raise _lib.RtError(self.lib.rt_io_last_error().decode() or f"rt_stream_pack failed ({rc})")
+        nb = int(n_blocks.value)
+        if pinned:
+            rec = t.empty(max(nb, 1) * _lib.RT_STREAM_BLOCK, dtype=t.int32).pin_memory()
+            hdr = t.empty(max(nb, 1) * 2, dtype=t.int32).pin_memory()
+            rp, hp = C.c_void_p(rec.data_ptr()), C.c_void_p(hdr.data_ptr())
+        else:
+            rec = np.empty(max(nb, 1) * _lib.RT_STREAM_BLOCK, np.uint32)
+            hdr = np.empty(max(nb, 1) * 2, np.int32)
+            rp, hp = _np_ptr(rec), _np_ptr(hdr)
+        rc = self.lib.rt_stream_pack(n, *ptrs, int(n_threads), nb, rp, hp, C.byref(n_blocks))
+        if rc != 0:
+            raise _lib.RtError(self.lib.rt_io_last_error().decode() or f"rt_stream_pack failed ({rc})")
+        return dict(records=rec, hdr=hdr, n_blocks=nb, n=n)
+
+    def upload_stream(self, stream: dict) -> dict:
+        """Host record stream (``stream_reads``) -> device tensors (plumbing only)."""
+        t = self.torch
+
+        def dev(a):
+            if hasattr(a, "data_ptr"):
+                return a.to(self.device)
+            return t.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(self.device)
+
+        return dict(records=dev(stream["records"]), hdr=dev(stream["hdr"]), n_blocks=int(stream["n_blocks"]), n=int(stream["n"]))
+
+    def bin_stream_device(self, cov, dstream: dict, protocol, stats, len_counts, weight: int = 1):
+        """Enqueue K1 on a device-resident record stream (4 B/read; no host sync)."""
+        p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        self._check(self.lib.rt_bin_stream(
+            self.ctx, p(cov), int(dstream["n_blocks"]), p(dstream["records"]), p(dstream["hdr"]),
+            protocol_code(protocol), int(weight), p(stats), p(len_counts), self._stream()))
+
+    def bin_stream_host(self, cov, stream: dict, protocol):
+        """K1 on a HOST record stream (see ``stream_reads``): chunked H2D of 4 B/read inside the call.
+        Returns ``(stats, read_length_counts)`` exactly like ``bin_reads_host``."""
+        def ptr(a):
+            return C.c_void_p(a.data_ptr()) if hasattr(a, "data_ptr") else _np_ptr(a)
+
+        stats = np.zeros(_lib.RT_N_STATS, np.int64)
+        len_counts = np.zeros(_lib.RT_LEN_TABLE, np.int64)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        self._check(self.lib.rt_bin_stream_host(
+            self.ctx, C.c_void_p(cov.data_ptr()), int(stream["n_blocks"]), ptr(stream["records"]), ptr(stream["hdr"]),
+            protocol_code(protocol), _np_ptr(stats), _np_ptr(len_counts)))
+        return dict(zip(_lib.ST_NAMES, stats.tolist())), len_counts
+
     # ---------------------------------------------------------------- K2+K3
     def new_score_columns(self, n: int, diagnostics: bool = False, min_codon: bool | None = None) -> dict:
         """Device result columns.  ``min_codon`` (the minimum codon sum, an extra the reference never

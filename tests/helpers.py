@@ -90,3 +90,34 @@ def compare_scores(got, ref, tie, params=DEFAULT_PARAMS, what=""):
     near = np.abs(ref["score"] - params[0]) <= SCORE_TOL
     assert (got["status"] == ref["status"])[~tie & ~near].all(), f"{what}status differs"
     return int(tie.sum()), int(near.sum())
+
+
+def decode_stream(records, hdr, n_blocks, block=2048):
+    """Checker-side decoder of the record stream of include/ribotricer_b200.h (rt_stream_pack): returns one tuple
+    (ref_id, first, last, mlen, meta7) per read record, in order.  Plain Python: small cases only."""
+    out = []
+    rec = np.asarray(records, np.uint32).reshape(-1)
+    hdr = np.asarray(hdr, np.int32).reshape(-1)
+    for b in range(n_blocks):
+        ref, pos = int(hdr[2 * b]), int(hdr[2 * b + 1])
+        words = rec[b * block:(b + 1) * block].tolist()
+        assert len(words) == block
+        k = 0
+        while k < block:
+            w = words[k]
+            k += 1
+            if w & 0x8000:
+                assert not (w & 0x4000), "extension record without a read in front of it"
+                pos += (w >> 16) | ((w & 0x3fff) << 16)
+                continue
+            pos += w & 0x7fff
+            mlen, meta, extra = (w >> 16) & 0xff, w >> 24, 0
+            if meta & 0x80:
+                assert k < block, "extension record in another block"
+                e = words[k]
+                k += 1
+                assert (e & 0xc000) == 0xc000
+                mlen |= (e & 0xff) << 8
+                extra = (e >> 16) | (((e >> 8) & 0x3f) << 16)
+            out.append((ref, pos, pos + mlen - 1 + extra, mlen, meta & 0x7f))
+    return out

@@ -775,3 +775,91 @@ def test_random_many_exon_orfs_both_layouts(engine):
             print("trial", trial, "FAILED:", exc, "orfs", len(orfs), "max exons", max(len(i) for _, _, i in orfs))
             engine.set_layout("dense")
     assert n_bad == 0
+
+
+def _stream_library(idx, n_reads, seed):
+    """A coordinate-sorted library over the synthetic genome with everything the record stream has to code: spliced
+    reads, reads longer than 255, long gaps, all filter categories, reads without NH, an unknown reference, an
+    unmapped tail with junk positions."""
+    from ribotricer_b200 import synth
+
+    cfg = synth.config("tiny")
+    reads = synth.reads_to_numpy(synth.make_reads(cfg, idx, n_reads=n_reads, sort=True, seed_offset=seed))
+    rng = np.random.default_rng(seed)
+    n = len(reads["ref_id"])
+    first = reads["first"].astype(np.int64)
+    mlen = reads["mlen"].astype(np.int64)
+    mlen = np.where(rng.random(n) < 0.02, rng.choice([1, 150, 255, 256, 300, 700], n), mlen)
+    extra = np.where(rng.random(n) < 0.2, rng.choice([1, 3, 85, 6_000, 70_000], n), 0)
+    reads["mlen"] = mlen.astype(np.uint16)
+    reads["last"] = (first + mlen - 1 + extra).astype(np.int32)
+    flag = reads["flag"].astype(np.int64)
+    flag = np.where(rng.random(n) < 0.1, flag | rng.choice([4, 256, 512, 1024, 2048, 0x704], n), flag)
+    reads["flag"] = flag.astype(np.uint16)
+    reads["nh"] = rng.choice([0, 1, 1, 1, 2, 255], n).astype(np.uint8)
+    reads["mapq"] = rng.choice([255, 255, 3, 0], n).astype(np.uint8)
+    junk = (flag & 0x704) != 0
+    reads["first"] = np.where(junk & (rng.random(n) < 0.5), -1, reads["first"]).astype(np.int32)
+    last_contig = int(reads["ref_id"].max())
+    reads["ref_id"][reads["ref_id"] == last_contig] = 99          # sorted, but no such reference
+    tail = slice(n - 3000, n)
+    reads["ref_id"][tail] = -1
+    reads["flag"][tail] |= 4
+    return reads
+
+
+@pytest.mark.parametrize("layout", ["dense", "compact"])
+def test_record_stream_matches_oracle_and_columns(engine, layout):
+    """rt_stream_pack + rt_bin_stream(_host) (4 B/read delta-coded records, cascade on the device) against the C
+    oracle's split_bam + merge_read_lengths and against rt_bin_reads on the columns the stream was made from: stats,
+    length totals, every coverage slot; both protocols; weight -1 takes the library out again; a sparse library
+    (gaps above 32,767 nt between neighbours) and the sorted_hint path of rt_bin_reads_host ride along."""
+    CO = _oracle()
+    from ribotricer_b200 import synth
+
+    cfg = synth.config("tiny")
+    idx = synth.make_index(cfg)
+    offsets = dict(synth.TRUE_OFFSETS)
+    offsets[150] = 40
+    offsets[300] = -7
+    pad = 64
+    base, plane = _setup(engine, idx.contig_names, idx.contig_len, idx.as_dict(), offsets, None, pad=pad)
+    lt = CO.make_len_table(offsets, None)
+    engine.set_layout(layout)
+    try:
+        for n_reads, seed in ((400_000, 1), (900, 2)):
+            reads = _stream_library(idx, n_reads, seed)
+            stream = engine.stream_reads(reads, n_threads=3)
+            assert stream["n"] == len(reads["ref_id"]) and stream["n_blocks"] >= 1
+            for protocol, code in (("forward", 0), ("reverse", 1)):
+                ref_cov, ref_stats, ref_len = CO.bin_reads(reads, code, lt, base, idx.contig_len, pad, plane)
+                want = engine.new_coverage()
+                st_w, lc_w = engine.new_bin_accumulators()
+                engine.bin_reads_device(want, engine.upload_reads(reads), protocol, st_w, lc_w)
+                stats_w = dict(zip(ref_stats.keys(), st_w.cpu().tolist()))
+                assert stats_w == ref_stats and (lc_w.cpu().numpy() == ref_len).all()
+                if layout == "dense":
+                    assert (want.cpu().numpy() == ref_cov).all()
+                got = engine.new_coverage()
+                stats_g, len_g = engine.bin_stream_host(got, stream, protocol)
+                assert stats_g == ref_stats and (len_g == ref_len).all()
+                assert engine.torch.equal(got, want)
+                hinted = engine.new_coverage()                     # the same through rt_bin_reads_host(sorted_hint=1)
+                stats_h, len_h = engine.bin_reads_host(hinted, reads, protocol, sorted_hint=True)
+                assert stats_h == ref_stats and (len_h == ref_len).all() and engine.torch.equal(hinted, want)
+                dstream = engine.upload_stream(stream)             # resident stream, then taken out again
+                st, lc = engine.new_bin_accumulators()
+                engine.bin_stream_device(got, dstream, protocol, st, lc)
+                assert engine.torch.equal(got, 2 * want)
+                engine.bin_stream_device(got, dstream, protocol, st, lc, weight=-1)
+                assert engine.torch.equal(got, want) and int(st.abs().sum().item()) == 0 and int(lc.abs().sum().item()) == 0
+        empty = engine.stream_reads({k: v[:0] for k, v in reads.items()})
+        stats_e, len_e = engine.bin_stream_host(engine.new_coverage(), empty, "forward")
+        assert stats_e["total"] == 0 and not len_e.any()
+        # protocol "no": reads are counted, nothing is stored (bam.py:105-131 has no branch for it)
+        none = engine.new_coverage()
+        stats_n, _ = engine.bin_stream_host(none, stream, "no")
+        ref_cov, ref_stats, _ = CO.bin_reads(reads, 2, lt, base, idx.contig_len, pad, plane)
+        assert stats_n == ref_stats and int(none.abs().max().item()) == 0
+    finally:
+        engine.set_layout("dense")

@@ -302,3 +302,99 @@ def test_count_orfs_text_matches_reference(tmp_path, built):
         assert out.read_text() == c["text"], (c["case"], c["tsv"], c["features"], c["report_all"])
         n += 1
     assert n == 72
+
+
+def _stream_columns(seed=5, n=60_000):
+    """Sorted read columns with everything the record stream has to code: spliced reads, reads longer than 255,
+    gaps above 32,767 and above 2^30, several references, flag-decided reads with junk positions, an unmapped tail."""
+    rng = np.random.default_rng(seed)
+    ref = np.sort(rng.choice([0, 1, 2, 5], n, p=[0.5, 0.3, 0.15, 0.05])).astype(np.int32)
+    step = rng.choice([0, 0, 1, 3, 40, 900, 40_000, 70_000], n, p=[0.3, 0.2, 0.2, 0.15, 0.1, 0.03, 0.015, 0.005]).astype(np.int64)
+    first = np.zeros(n, np.int64)
+    for r in np.unique(ref):
+        m = ref == r
+        first[m] = np.cumsum(step[m])
+    big = np.flatnonzero(ref == 5)
+    first[big[len(big) // 2:]] += (1 << 30) + 12345          # one jump that no skip record holds
+    mlen = rng.choice([0, 1, 26, 28, 29, 30, 32, 150, 255, 256, 300, 5000], n,
+                      p=[0.002, 0.008, 0.2, 0.3, 0.2, 0.1, 0.1, 0.04, 0.02, 0.01, 0.01, 0.01]).astype(np.int64)
+    extra = np.where(rng.random(n) < 0.15, rng.choice([1, 2, 85, 6_000, 70_000, (1 << 22) - 1], n), 0)
+    last = first + mlen - 1 + extra
+    flag = np.where(rng.random(n) < 0.5, 16, 0)
+    flag = np.where(rng.random(n) < 0.12, flag | rng.choice([4, 256, 512, 1024, 2048, 0x704], n), flag).astype(np.uint16)
+    junk = (flag & 0x704) != 0
+    first = np.where(junk & (rng.random(n) < 0.5), -1, first)  # unmapped mates and the like: any position at all
+    nh = rng.choice([0, 1, 1, 1, 2, 255], n).astype(np.uint8)
+    mapq = rng.choice([255, 255, 3, 0], n).astype(np.uint8)
+    tail = slice(n - 700, n)
+    ref[tail] = -1
+    flag[tail] |= 4
+    return dict(ref_id=ref, first=first.astype(np.int32), last=last.astype(np.int32), mlen=mlen.astype(np.uint16), flag=flag,
+                mapq=mapq, nh=nh)
+
+
+def _stream_pack(lib, cols, n_threads=3):
+    import ctypes as C
+
+    p = lambda a: a.ctypes.data_as(C.c_void_p)      # noqa: E731
+    n = len(cols["ref_id"])
+    args = [p(cols[k]) for k in ("ref_id", "first", "last", "mlen", "flag", "mapq", "nh")]
+    nb = C.c_int64(0)
+    rc = lib.rt_stream_pack(n, *args, n_threads, 0, None, None, C.byref(nb))
+    if rc != 0:
+        return rc, None, None, 0
+    rec = np.zeros(max(1, nb.value) * 2048, np.uint32)
+    hdr = np.zeros(max(1, nb.value) * 2, np.int32)
+    rc = lib.rt_stream_pack(n, *args, n_threads, nb.value, p(rec), p(hdr), C.byref(nb))
+    return rc, rec, hdr, nb.value
+
+
+def test_stream_pack_round_trip(built):
+    """rt_stream_pack (4 B/read delta-coded records) decodes back to the columns it was given: every read the flags do
+    not decide keeps ref_id / first / last / mlen, every read keeps the seven raw bits the cascade of bam.py:77-91 +
+    common.py:33-69 looks at (checked against oracle_py), blocks are whole, extensions stay inside their block."""
+    from helpers import decode_stream
+    from oracle import oracle_py as O
+    from ribotricer_b200 import _lib
+
+    lib = _lib.load()
+    cols = _stream_columns()
+    n = len(cols["ref_id"])
+    rc, rec, hdr, nb = _stream_pack(lib, cols)
+    assert rc == 0 and nb >= (n + 2047) // 2048
+    got = decode_stream(rec, hdr, nb)
+    assert len(got) == n
+    n_checked = 0
+    for i, (ref, first, last, mlen, meta) in enumerate(got):
+        flag, mapq, nh = int(cols["flag"][i]), int(cols["mapq"][i]), int(cols["nh"][i])
+        want_meta = (1 if flag & O.FLAG_UNMAPPED else 0) | (2 if flag & O.FLAG_SECONDARY else 0) | (4 if flag & O.FLAG_QCFAIL else 0) \
+            | (8 if flag & O.FLAG_DUPLICATE else 0) | (16 if flag & O.FLAG_REVERSE else 0)
+        state = (1 if mapq == 255 else 0) if nh == 0 else (2 if nh == 1 else 3)
+        assert meta == want_meta | state << 5, i
+        if flag & 0x704:
+            continue
+        # among the reads the flags let through, the two "unique" states are exactly what is_read_uniq_mapping accepts
+        assert (state in (1, 2)) == bool(O.is_read_uniq_mapping(flag, mapq, nh)), i
+        n_checked += 1
+        assert (ref, first, last, mlen) == (int(cols["ref_id"][i]), int(cols["first"][i]), int(cols["last"][i]), int(cols["mlen"][i])), i
+    assert n_checked > n // 2
+    # one thread or many: the same stream
+    rc1, rec1, hdr1, nb1 = _stream_pack(lib, cols, n_threads=1)
+    assert rc1 == 0 and nb1 == nb and (rec1 == rec).all() and (hdr1 == hdr).all()
+    # a library that is not sorted is refused (the caller falls back to the columns), so is a span beyond 22 bits
+    bad = {k: v.copy() for k, v in cols.items()}
+    clean = np.flatnonzero((bad["flag"] & 0x704) == 0)
+    i, j = clean[100], clean[101]
+    bad["first"][j] = bad["first"][i] - 1
+    bad["ref_id"][j] = bad["ref_id"][i]
+    assert _stream_pack(lib, bad)[0] == _lib_estate()
+    wide = {k: v.copy() for k, v in cols.items()}
+    wide["last"][clean[7]] = wide["first"][clean[7]] + int(wide["mlen"][clean[7]]) - 1 + (1 << 22)
+    assert _stream_pack(lib, wide)[0] == _lib_estate()
+    # no reads: no blocks
+    rc0, _, _, nb0 = _stream_pack(lib, {k: v[:0] for k, v in cols.items()})
+    assert rc0 == 0 and nb0 == 0
+
+
+def _lib_estate():
+    return -4
