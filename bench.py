@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--distinct", type=int, default=4, help="--config C4: distinct libraries generated (cycled through)")
     ap.add_argument("--min-reads-per-codon", type=float, default=0.0,
                     help="--min_reads_per_codon of the scoring step (> 0 selects the kernels that also carry per-frame minima)")
+    ap.add_argument("--reads-format", default="stream", choices=["stream", "columns"],
+                    help="resident library of the device-timed step: the 4 B/read record stream (rt_bin_stream, default) or the "
+                         "decoder's 18 B/read columns (rt_bin_reads)")
     ap.add_argument("--layout", default="compact", choices=["compact", "dense"],
                     help="coverage layout: exon union of the index (default) or genome-wide planes")
     return ap.parse_args()
@@ -307,6 +310,16 @@ def run_ours(args):
         del key, keep
         torch.cuda.empty_cache()
     n_reads = int(dreads["ref_id"].numel())
+    # host columns exactly as a BAM decoder produces them (18 B/read: ref_id, first, last, mlen, flag, mapq, nh), page-locked
+    hreads = {k: v.cpu().pin_memory() for k, v in dreads.items()}
+    use_stream = args.reads_format == "stream" and args.layout == "compact"
+    hstream = dstream = None
+    if use_stream:       # the library as a record stream (rt_stream_pack): resident copy for `value`, host copy for e2e_stream
+        hstream = eng.stream_reads({k: v.numpy() for k, v in hreads.items()}, pinned=True)
+        dstream = eng.upload_stream(hstream)
+        del dreads
+        dreads = None
+        torch.cuda.empty_cache()
     n_orf = len(shard.rows)
     n_orf_total = idx.n_orf
     if args.layout == "compact":
@@ -334,7 +347,10 @@ def run_ours(args):
     def step(events=None):
         if events is not None:
             events[0].record()
-        eng.bin_reads_device(cov, dreads, "forward", stats, len_counts, sorted_hint=True)
+        if use_stream:
+            eng.bin_stream_device(cov, dstream, "forward", stats, len_counts)
+        else:
+            eng.bin_reads_device(cov, dreads, "forward", stats, len_counts, sorted_hint=True)
         if events is not None:
             events[1].record()
         eng.score_device(cov, out, 0, n_orf, params)
@@ -370,11 +386,9 @@ def run_ours(args):
     assert int(cov.abs().max().item()) == 0, "coverage did not return to zero after the sparse clear"
 
     # ---- e2e: host buffers in, host buffers out, through the host-buffer C-ABI calls
-    # host columns exactly as a BAM decoder produces them (18 B/read: ref_id, first, last, mlen, flag, mapq, nh),
-    # page-locked.  Nothing is prepared outside the timed region: rt_bin_reads_host evaluates the filter cascade and
-    # run-length codes ref_id per chunk on host threads while the previous chunk is on the wire, so 11 B/read cross PCIe.
-    hreads = {k: v.cpu().pin_memory() for k, v in dreads.items()}
-    del dreads
+    # From the decoder's host columns nothing is prepared outside the timed region: rt_bin_reads_host delta-codes every
+    # chunk into the 4 B/read record stream on host threads while other chunks are on the wire and K1 runs on the stream.
+    del dreads, dstream
     torch.cuda.empty_cache()
     e2e_steps = max(3, min(args.steps, 5))
     hout = eng.new_host_score_columns(n_orf)      # pinned result columns, like the pinned read columns
@@ -392,19 +406,42 @@ def run_ours(args):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    # second line: the library handed over as the record stream itself (what rt_stream_pack makes of a decoded BAM once,
+    # e.g. for a library that is scored against several indexes): no host packing inside the call
+    e2e_stream_ms = None
+    if hstream is not None:
+        for _ in range(2):
+            eng.clear_touched(cov)
+            eng.bin_stream_host(cov, hstream, "forward")
+            eng.score_host(cov, 0, n_orf, params, out=hout)
+        barrier()
+        e0.record()
+        for _ in range(e2e_steps):
+            eng.clear_touched(cov)
+            st_stream, _ = eng.bin_stream_host(cov, hstream, "forward")
+            eng.score_host(cov, 0, n_orf, params, out=hout)
+        e1.record()
+        barrier()
+        e2e_stream_ms = e0.elapsed_time(e1) / e2e_steps
+        assert st_stream == st_host, "record stream and columns disagree"
 
     score_ms_local, bin_ms_local = score_ms, bin_ms       # the roofline is this rank's kernels over this rank's bytes
-    times = torch.tensor([total_ms, e2e_ms, score_ms, bin_ms, unbin_ms], dtype=torch.float64, device=dev)
+    stream_blocks = int(hstream["n_blocks"]) if hstream is not None else 0
+    times = torch.tensor([total_ms, e2e_ms, score_ms, bin_ms, unbin_ms, e2e_stream_ms or 0.0], dtype=torch.float64, device=dev)
+    blocks_all = torch.tensor([stream_blocks], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, score_ms, bin_ms, unbin_ms = times.tolist()
+        dist.all_reduce(blocks_all, op=dist.ReduceOp.SUM)
+    total_ms, e2e_ms, score_ms, bin_ms, unbin_ms, e2e_stream_ms = times.tolist()
+    stream_bytes = int(blocks_all.item()) * (2048 * 4 + 8)
     ms_per_step = total_ms / args.steps
     value = n_orf_total / (ms_per_step * 1e-3)          # the whole index, in the time of the slowest rank
     e2e_value = n_orf_total / (e2e_ms * 1e-3)
 
     if rank == 0:
         achieved = score_bytes / (score_ms_local * 1e-3) / 1e9
-        h2d = sum(11 * c[1] for c in per_rank)                                # all ranks together (+ a run table per chunk)
+        # all ranks together: the record stream when the library codes (4 B/read + block padding), else 18 B/read columns
+        h2d = stream_bytes if stream_bytes else sum(18 * c[1] for c in per_rank)
         d2h = world * 8 * (9 + 65536) + sum(25 * c[0] for c in per_rank)
         # dram__bytes_read.sum + dram__bytes_write.sum of the scoring kernel from the committed ncu capture
         traffic, traffic_src, bin_traffic = None, None, None
@@ -417,8 +454,9 @@ def run_ours(args):
                 traffic = sum(t[k]["dram_bytes"] for k in kernel_names)
                 traffic_src = "; ".join(sorted({t[k]["source"].split(" (")[0] for k in kernel_names})) + \
                     " (ncu --set full, one launch of each kernel inside bench.py's step)"
-            if same(t.get("bin_psites_kernel", {})) and args.scale == 1.0:
-                bin_traffic = t["bin_psites_kernel"]["dram_bytes"]
+            k1_name = "bin_stream_kernel" if use_stream else "bin_psites_kernel"
+            if same(t.get(k1_name, {})) and args.scale == 1.0:
+                bin_traffic = t[k1_name]["dram_bytes"]
         except Exception:
             pass
         line = {
@@ -437,12 +475,14 @@ def run_ours(args):
                 "l2": "inputs larger than L2 (coverage buffer %.1f GB, read columns %.2f GB)" % (
                     cov.numel() * 4 / 1e9, READ_BYTES * n_reads / 1e9),
                 "coverage_layout": args.layout, "min_reads_per_codon": args.min_reads_per_codon,
+                "resident_library": ("record stream, 4 B/read (rt_stream_pack; raw filter bits per read, cascade on the device), "
+                                     "%.2f GB" % (stream_bytes / max(1, world) / 1e9)) if use_stream else "decoder columns, 18 B/read",
                 "step": "bin P-sites -> gather+score -> clear (resident coverage back to zero: memset of the compact "
                         "buffer, or sparse clear of the touched sectors of the dense planes)",
             },
             "reads_binned_per_s": n_reads_total / (ms_per_step * 1e-3),
             "kernels_ms": {"bin_psites": bin_ms, "score_orfs": score_ms, "clear": unbin_ms},
-            "roofline": {"bound": "hbm", "kernel": " + ".join(kernel_names) + " (+ fallback launch)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": " + ".join(kernel_names) + " (+ fallback launch)", "bin_kernel": "bin_stream_kernel" if use_stream else "bin_psites_kernel", "achieved": achieved,
                          "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "traffic_source": traffic_src,
                          "algorithmic_bytes": score_bytes, "peak_source": peak_src,
@@ -452,8 +492,12 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "path": "Engine.clear_touched + bin_reads_host (rt_bin_reads_host on the decoder's 18 B/read host columns; "
-                            "packed to 11 B/read per chunk on host threads inside the call, overlapped with the copies) + "
-                            "score_host (rt_score_host, pinned result columns)"},
+                            "delta-coded to the 4 B/read record stream per chunk on host threads inside the call, overlapped with "
+                            "the copies and K1) + score_host (rt_score_host, pinned result columns)",
+                    "from_record_stream": None if not e2e_stream_ms else {
+                        "value": n_orf_total / (e2e_stream_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_stream_ms,
+                        "path": "Engine.clear_touched + bin_stream_host (rt_bin_stream_host on a host record stream made once "
+                                "by rt_stream_pack) + score_host"}},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "translating": int(res["status"].sum()), "valid_reads": st_host["valid"],
@@ -474,8 +518,8 @@ def run_ours(args):
 def run_batch(args):
     """BASELINE.json configs[3]: 64 libraries against one shared, resident human index; libraries dealt to the ranks
     round-robin (ribotricer_b200.batch.LibraryPipeline: copy of library k+1, kernels of library k and the result
-    copy of library k-1 overlap).  Host records are page-locked 11 B/read packed records as the BAM decoder hands
-    them over; `--distinct` different libraries are generated and cycled through.  Not a driver bench line: an
+    copy of library k-1 overlap).  Host records are the page-locked 4 B/read record stream (rt_stream_pack) the BAM decoder's columns
+    are coded into once; `--distinct` different libraries are generated and cycled through.  Not a driver bench line: an
     artefact for profiles/ (libraries/s at 1 and N GPUs, seconds-long timed region)."""
     import torch
     import torch.distributed as dist
@@ -503,7 +547,7 @@ def run_batch(args):
     libs = []
     for k in range(args.distinct):
         d = synth.make_reads(cfg, idx, device=dev, seed_offset=1000 * k + rank)
-        libs.append(eng.pack_reads({kk: v.cpu() for kk, v in d.items()}, pinned=True))
+        libs.append(eng.stream_reads({kk: v.cpu() for kk, v in d.items()}, pinned=True))
         del d
         torch.cuda.empty_cache()
     n_lib_total = args.libraries
@@ -543,11 +587,11 @@ def run_batch(args):
             "config": {"workload": f"C4: batch of {n_lib_total} synthetic Ribo-seq libraries ({n_reads} reads each, "
                                    f"{args.distinct} distinct ones cycled) against ONE resident human index of {idx.n_orf} "
                                    f"candidate ORFs; libraries dealt round-robin to {world} rank(s)",
-                       "step": "one library: H2D of its 11 B/read packed records (copy stream) | clear + K1 + phase A + B + "
+                       "step": "one library: H2D of its 4 B/read record stream (copy stream) | clear + K1 + phase A + B + "
                                "D2H of the result columns (compute stream), two coverage buffers alternating",
                        "timed_region_s": dt},
             "libraries_per_s": n_lib_total / dt,
-            "e2e": {"value": n_lib_total * idx.n_orf / dt, "unit": UNIT, "h2d_bytes_per_step": 11 * n_reads,
+            "e2e": {"value": n_lib_total * idx.n_orf / dt, "unit": UNIT, "h2d_bytes_per_step": int(libs[0]["n_blocks"]) * (2048 * 4 + 8),
                     "d2h_bytes_per_step": 25 * idx.n_orf + 8 * (9 + 65536),
                     "path": "ribotricer_b200.batch.LibraryPipeline (host records in, host result columns out, every step)"},
             "gpu_launches": eng.launches - launches0, "clocks": clocks.summary(),

@@ -5,7 +5,7 @@ The index, its atoms and the compact slot map are set up once and stay on the GP
 ranks of a torchrun job round-robin; inside a rank they run through a three-stage software pipeline:
 
     stage(i)     decode / pack library i on the host, start its host-to-device copy on the copy stream
-    compute(i-1) clear a coverage buffer, K1 (packed records), phase A + B, start the device-to-host copy of the
+    compute(i-1) clear a coverage buffer, K1 (record stream), phase A + B, start the device-to-host copy of the
                  result columns -- all enqueued on the compute stream behind the copy of library i-1
     finalize(i-2) wait for library i-2, write its _bam_summary.txt and its TSV (K4 gathers the profiles of the
                  reported ORFs from the library's coverage buffer, which the pipeline keeps alive until then)
@@ -48,6 +48,15 @@ class LibraryPipeline:
         t, eng = self.eng.torch, self.eng
         with t.cuda.stream(self.copy_stream):
             dev = {}
+            if "records" in packed:       # a record stream (Engine.stream_reads): 4 B/read
+                for k in ("records", "hdr"):
+                    a = packed[k]
+                    a = a if hasattr(a, "data_ptr") else t.from_numpy(np.ascontiguousarray(a).view(np.int32))
+                    dev[k] = a.to(eng.device, non_blocking=True)
+                dev["n_blocks"], dev["n"] = int(packed["n_blocks"]), int(packed["n"])
+                ev = t.cuda.Event()
+                ev.record(self.copy_stream)
+                return dict(tag=tag, dev=dev, copied=ev, keep=packed)
             for k in ("first", "last", "mlen", "meta"):
                 a = packed[k]
                 a = a if hasattr(a, "data_ptr") else t.from_numpy(np.ascontiguousarray(a).view(np.int16) if a.dtype == np.uint16 else np.ascontiguousarray(a))
@@ -69,7 +78,10 @@ class LibraryPipeline:
             cov = self.cov[slot]
             eng.clear_coverage(cov)
             stats, len_counts = eng.new_bin_accumulators()
-            eng.bin_reads_packed_device(cov, job["dev"], self.protocol, stats, len_counts)
+            if "records" in job["dev"]:
+                eng.bin_stream_device(cov, job["dev"], self.protocol, stats, len_counts)
+            else:
+                eng.bin_reads_packed_device(cov, job["dev"], self.protocol, stats, len_counts)
             out = eng.new_score_columns(n_orf, min_codon=self.want_min)
             eng.score_device(cov, out, 0, n_orf, self.params)
             if self._host_cols[slot] is None:
@@ -105,7 +117,8 @@ class LibraryPipeline:
 
     # -- driver ------------------------------------------------------------------------------------------------
     def submit(self, tag, packed):
-        """``packed``: what ``Engine.pack_reads(cols, pinned=True)`` returns for one library."""
+        """``packed``: what ``Engine.stream_reads(cols, pinned=True)`` (a coordinate-sorted library as 4 B/read records)
+        or ``Engine.pack_reads(cols, pinned=True)`` (11 B/read, any order grouped by reference) returns for one library."""
         nxt = self._stage(tag, packed)
         run = self._compute(self._staged) if self._staged is not None else None
         if self._running is not None:
@@ -120,6 +133,19 @@ class LibraryPipeline:
             self._finalize(run)
         self._staged = self._running = None
         self.compute_stream.synchronize()
+
+
+def _host_records(eng, reads):
+    """The library as page-locked host records: the 4 B/read record stream when it is coordinate-sorted (and codes),
+    else the 11 B/read packed records."""
+    from ._lib import RtError
+
+    if reads.sorted_by_coordinate:
+        try:
+            return eng.stream_reads(reads.cols, pinned=True)
+        except RtError:
+            pass
+    return eng.pack_reads(reads.cols, pinned=True, max_runs=max(64, len(reads) + 1) if not reads.sorted_by_coordinate else None)
 
 
 def detect_orfs_batch(bams, ribotricer_index: str, prefixes, protocol: str, read_lengths, psite_offsets: dict,
@@ -173,7 +199,7 @@ def detect_orfs_batch(bams, ribotricer_index: str, prefixes, protocol: str, read
             reads = first if k == mine[0] else load_reads(bams[k])
             if list(reads.contig_names) != list(eng.contig_names) or not np.array_equal(reads.contig_len, eng.contig_len):
                 raise ValueError(f"library {k}: its reference sequences differ from those of the first library")
-            pipe.submit(k, eng.pack_reads(reads.cols, pinned=True, max_runs=max(64, len(reads) + 1) if not reads.sorted_by_coordinate else None))
+            pipe.submit(k, _host_records(eng, reads))
         pipe.drain()
     finally:
         eng.set_layout("dense")

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in header_symbols():
         assert hasattr(lib, name), name
-    assert _lib.load().rt_abi_version() == 2
+    assert _lib.load().rt_abi_version() == 3
 
 
 def test_no_cpu_fallback(built):
