@@ -433,7 +433,7 @@ def run_ours(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(blocks_all, op=dist.ReduceOp.SUM)
     total_ms, e2e_ms, score_ms, bin_ms, unbin_ms, e2e_stream_ms = times.tolist()
-    stream_bytes = int(blocks_all.item()) * (2048 * 4 + 8)
+    stream_bytes = int(blocks_all.item()) * (256 * 4 + 16)
     ms_per_step = total_ms / args.steps
     value = n_orf_total / (ms_per_step * 1e-3)          # the whole index, in the time of the slowest rank
     e2e_value = n_orf_total / (e2e_ms * 1e-3)
@@ -591,7 +591,7 @@ def run_batch(args):
                                "D2H of the result columns (compute stream), two coverage buffers alternating",
                        "timed_region_s": dt},
             "libraries_per_s": n_lib_total / dt,
-            "e2e": {"value": n_lib_total * idx.n_orf / dt, "unit": UNIT, "h2d_bytes_per_step": int(libs[0]["n_blocks"]) * (2048 * 4 + 8),
+            "e2e": {"value": n_lib_total * idx.n_orf / dt, "unit": UNIT, "h2d_bytes_per_step": int(libs[0]["n_blocks"]) * (256 * 4 + 16),
                     "d2h_bytes_per_step": 25 * idx.n_orf + 8 * (9 + 65536),
                     "path": "ribotricer_b200.batch.LibraryPipeline (host records in, host result columns out, every step)"},
             "gpu_launches": eng.launches - launches0, "clocks": clocks.summary(),

@@ -168,8 +168,10 @@ int rt_bin_reads_packed_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32
 /*
  * ---- K1 on a RECORD STREAM: a coordinate-sorted library as 4-byte delta-coded records (a quarter of the 18 B/read
  *      columns over PCIe and out of HBM).  Same loop as above (bam.py:71-137 + detect_orfs.py:54-83), identical results.
- * Records come in blocks of RT_STREAM_BLOCK; block b has the header h_hdr[2b] = ref_id of all its reads,
- * h_hdr[2b+1] = the position its deltas start from.  A record is one little-endian u32:
+ * Records come in blocks of RT_STREAM_BLOCK; block b has the 16-byte header h_hdr[4b] = ref_id of all its reads,
+ * h_hdr[4b+1] = the position its deltas start from, h_hdr[4b+2] = h_hdr[4b+3] = 0 (reserved).  One warp takes one
+ * block: K1 runs a few persistent CTAs per SM whose warps walk the blocks independently, each with its own
+ * shared-memory ring filled by cp.async.bulk (TMA) one block ahead.  A record is one little-endian u32:
  *   read       bits 0-14 delta = first - first of the previous read (or the header position), bit 15 = 0,
  *              bits 16-23 mlen & 255, bits 24-31 the RAW bits the filter cascade reads (it is evaluated on the
  *              device): RT_STREAM_UNMAPPED / SECONDARY / QCFAIL / DUPLICATE / REVERSE = SAM flags 0x4 / 0x100 /
@@ -187,7 +189,7 @@ int rt_bin_reads_packed_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32
  * 2^22 nt more than it matches) -- use rt_bin_reads / rt_bin_reads_host then.  With h_records == NULL it only
  * counts: *n_blocks = the capacity the real call needs.
  */
-#define RT_STREAM_BLOCK 2048
+#define RT_STREAM_BLOCK 256
 #define RT_STREAM_RANGE (1 << 20)
 #define RT_STREAM_SPECIAL 0x8000u
 #define RT_STREAM_KIND_EXT 0x4000u
@@ -205,9 +207,9 @@ int rt_bin_reads_packed_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32
 int rt_stream_pack(int64_t n, const int32_t* h_ref_id, const int32_t* h_first, const int32_t* h_last,
                    const uint16_t* h_mlen, const uint16_t* h_flag, const uint8_t* h_mapq, const uint8_t* h_nh,
                    int n_threads, int64_t cap_blocks, uint32_t* h_records /* cap_blocks * RT_STREAM_BLOCK */,
-                   int32_t* h_hdr /* 2 * cap_blocks */, int64_t* n_blocks);
+                   int32_t* h_hdr /* 4 * cap_blocks */, int64_t* n_blocks);
 int rt_bin_stream(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t* d_records /* 16-byte aligned */,
-                  const int32_t* d_hdr, int protocol, int weight, int64_t* d_stats, int64_t* d_len_counts,
+                  const int32_t* d_hdr /* 16-byte aligned */, int protocol, int weight, int64_t* d_stats, int64_t* d_len_counts,
                   void* stream);
 int rt_bin_stream_host(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t* h_records, const int32_t* h_hdr,
                        int protocol, int64_t* h_stats, int64_t* h_len_counts);

@@ -18,7 +18,7 @@ RT_LEN_FILTERED = -2147483647
 RT_PROTOCOL_FORWARD, RT_PROTOCOL_REVERSE, RT_PROTOCOL_NONE = 0, 1, 2
 ST_NAMES = ("total", "qcfail", "duplicate", "secondary", "unmapped", "multi", "valid", "oob", "badref")
 RT_N_STATS = len(ST_NAMES)
-RT_STREAM_BLOCK = 2048
+RT_STREAM_BLOCK = 256
 
 EXPORTS = (
     "rt_abi_version", "rt_last_error", "rt_create", "rt_destroy", "rt_device_count",

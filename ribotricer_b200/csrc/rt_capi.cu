@@ -310,7 +310,7 @@ constexpr int64_t kPackChunkReads = 1 << 20;      // reads per chunk of the pack
 // stream blocks a chunk may fill: 1.5 records per read (every second read spliced or far from its neighbour) + slack;
 // a chunk that needs more goes as plain columns
 constexpr int64_t kChunkBlockCap = kPackChunkReads * 3 / 2 / RT_STREAM_BLOCK + 64;
-static_assert(kChunkBlockCap * (RT_STREAM_BLOCK * 4 + 8) + 64 <= kPackChunkReads * kReadBytes, "a chunk's stream fits its device slot");
+static_assert(kChunkBlockCap * (RT_STREAM_BLOCK * 4 + 16) + 64 <= kPackChunkReads * kReadBytes, "a chunk's stream fits its device slot");
 constexpr int64_t kMaxPipes = 16;
 
 
@@ -655,9 +655,10 @@ int rt_bin_stream(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t*
     if (weight != 1 && weight != -1) return fail(ctx, RT_EINVAL, "rt_bin_stream: weight must be +1 or -1");
     if (ctx->plane == 0) return fail(ctx, RT_ESTATE, "rt_bin_stream: call rt_set_genome first");
     if (!ctx->have_len_table) return fail(ctx, RT_ESTATE, "rt_bin_stream: call rt_set_length_table first");
-    if (n_blocks < 0 || n_blocks > 0x7fffffff || !d_cov || !d_stats || !d_len_counts || (n_blocks > 0 && (!d_records || !d_hdr)))
+    if (n_blocks < 0 || !d_cov || !d_stats || !d_len_counts || (n_blocks > 0 && (!d_records || !d_hdr)))
         return fail(ctx, RT_EINVAL, "rt_bin_stream: NULL argument or bad n_blocks");
-    if (reinterpret_cast<uintptr_t>(d_records) & 15) return fail(ctx, RT_EINVAL, "rt_bin_stream: d_records must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(d_records) | reinterpret_cast<uintptr_t>(d_hdr)) & 15)
+        return fail(ctx, RT_EINVAL, "rt_bin_stream: d_records and d_hdr must be 16-byte aligned");
     if (ctx->track_touched && ctx->layout != RT_LAYOUT_COMPACT)
         return fail(ctx, RT_ESTATE, "rt_bin_stream: the touched-slot list of the dense layout is kept by rt_bin_reads only");
     if (n_blocks == 0) return RT_OK;
@@ -665,7 +666,8 @@ int rt_bin_stream(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t*
     rt::StreamArgs a{};
     a.cov = d_cov;
     a.rec = reinterpret_cast<const uint4*>(d_records);
-    a.hdr = reinterpret_cast<const int2*>(d_hdr);
+    a.hdr = reinterpret_cast<const int4*>(d_hdr);
+    a.n_blocks = n_blocks;
     a.protocol = protocol;
     a.weight = weight;
     a.len_base = ctx->len_base;
@@ -679,8 +681,10 @@ int rt_bin_stream(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t*
     a.stats = reinterpret_cast<unsigned long long*>(d_stats);
     a.len_counts = reinterpret_cast<unsigned long long*>(d_len_counts);
     cudaStream_t st = (cudaStream_t)stream;
-    if (a.cmap) rt::bin_stream_kernel<true><<<(unsigned)n_blocks, rt::kStreamThreads, 0, st>>>(a);
-    else rt::bin_stream_kernel<false><<<(unsigned)n_blocks, rt::kStreamThreads, 0, st>>>(a);
+    // persistent: a few CTAs per SM walk the blocks, the next block in flight (cp.async.bulk) while one is processed
+    const unsigned grid = (unsigned)std::min<int64_t>((n_blocks + rt::kStreamWarps - 1) / rt::kStreamWarps, (int64_t)ctx->n_sm * RT_STREAM_CTAS_PER_SM);
+    if (a.cmap) rt::bin_stream_kernel<true><<<grid, rt::kStreamThreads, 0, st>>>(a);
+    else rt::bin_stream_kernel<false><<<grid, rt::kStreamThreads, 0, st>>>(a);
     ctx->launches++;
     RT_CUDA(ctx, cudaGetLastError());
     return RT_OK;
@@ -700,18 +704,18 @@ int rt_bin_stream_host(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint
         if (!ctx->slot_stream[s]) RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking));
     RT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, acc_bytes, ctx->slot_stream[0]));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[0]));
-    // chunks of 2048 blocks (16 MB of records) alternate between two device slots: copy of one || K1 of the other
-    const int64_t chunk = 2048;
+    // chunks of 16 MB of records alternate between two device slots: copy of one || K1 of the other
+    const int64_t chunk = (16 << 20) / (RT_STREAM_BLOCK * 4);
     const size_t rec_bytes = sizeof(uint32_t) * RT_STREAM_BLOCK * (size_t)chunk;
     int slot = 0;
     for (int64_t at = 0; at < n_blocks; at += chunk, slot ^= 1) {
         const int64_t m = std::min(chunk, n_blocks - at);
-        RT_CUDA(ctx, ctx->read_slot[slot].reserve(rec_bytes + sizeof(int32_t) * 2 * (size_t)chunk));
+        RT_CUDA(ctx, ctx->read_slot[slot].reserve(rec_bytes + sizeof(int32_t) * 4 * (size_t)chunk));
         uint32_t* d_rec = static_cast<uint32_t*>(ctx->read_slot[slot].p);
         int32_t* d_hdr = reinterpret_cast<int32_t*>(static_cast<char*>(ctx->read_slot[slot].p) + rec_bytes);
         cudaStream_t st = ctx->slot_stream[slot];   // stream order protects the slot's previous use
         RT_CUDA(ctx, cudaMemcpyAsync(d_rec, h_records + at * RT_STREAM_BLOCK, sizeof(uint32_t) * RT_STREAM_BLOCK * (size_t)m, cudaMemcpyHostToDevice, st));
-        RT_CUDA(ctx, cudaMemcpyAsync(d_hdr, h_hdr + 2 * at, sizeof(int32_t) * 2 * (size_t)m, cudaMemcpyHostToDevice, st));
+        RT_CUDA(ctx, cudaMemcpyAsync(d_hdr, h_hdr + 4 * at, sizeof(int32_t) * 4 * (size_t)m, cudaMemcpyHostToDevice, st));
         int rc = rt_bin_stream(ctx, d_cov, m, d_rec, d_hdr, protocol, 1, d_stats, d_len_counts, st);
         if (rc != RT_OK) return rc;
     }
@@ -755,7 +759,8 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
     const int64_t chunk = use_stream ? std::min<int64_t>(pack_chunk_reads, std::max<int64_t>(n, 1))
                                       : std::min<int64_t>(kHostChunkReads, std::max<int64_t>(n, 1));
     const int64_t n_chunks = (n + chunk - 1) / chunk;
-    int64_t want_pipes = std::min<int64_t>(kMaxPipes, (int64_t)std::thread::hardware_concurrency() / 2);
+    // the delta coding is the bottleneck of this call (about 1.5 ns per read and thread): one pipeline per hardware thread
+    int64_t want_pipes = std::min<int64_t>(kMaxPipes, (int64_t)std::thread::hardware_concurrency());
     if (const char* e = getenv("RT_PACK_PIPES")) want_pipes = std::min<int64_t>(kMaxPipes, std::max(1, atoi(e)));
     const int n_pipes = use_stream ? (int)std::max<int64_t>(1, std::min<int64_t>(want_pipes, n_chunks)) : 2;
     const bool timing = getenv("RT_HOST_TIMING") != nullptr;
@@ -769,7 +774,7 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
         rt_ctx::HostStage& hs = ctx->host_stage[s];
         if (use_stream && !hs.rec) {
             RT_CUDA(ctx, cudaHostAlloc(&hs.rec, sizeof(uint32_t) * RT_STREAM_BLOCK * (size_t)kChunkBlockCap, cudaHostAllocDefault));
-            RT_CUDA(ctx, cudaHostAlloc(&hs.hdr, sizeof(int32_t) * 2 * (size_t)kChunkBlockCap, cudaHostAllocDefault));
+            RT_CUDA(ctx, cudaHostAlloc(&hs.hdr, sizeof(int32_t) * 4 * (size_t)kChunkBlockCap, cudaHostAllocDefault));
             RT_CUDA(ctx, cudaEventCreateWithFlags(&hs.copied, cudaEventDisableTiming));
         }
         hs.busy = false;
@@ -819,7 +824,7 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
             int rc;
             if (blocks >= 0) {
                 if (!check(cudaMemcpyAsync(d_rec, hs.rec, sizeof(uint32_t) * RT_STREAM_BLOCK * (size_t)blocks, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
-                    !check(cudaMemcpyAsync(d_hdr, hs.hdr, sizeof(int32_t) * 2 * (size_t)blocks, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
+                    !check(cudaMemcpyAsync(d_hdr, hs.hdr, sizeof(int32_t) * 4 * (size_t)blocks, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
                     !check(cudaEventRecord(hs.copied, st), "cudaEventRecord"))
                     break;
                 hs.busy = true;

@@ -477,8 +477,9 @@ struct StreamWriter {
             for (int k = fill; k < RT_STREAM_BLOCK; ++k) rec[(nb - 1) * RT_STREAM_BLOCK + k] = RT_STREAM_NULL;
         if (rec && nb >= cap) return false;
         if (rec) {
-            hdr[2 * nb] = rid;
-            hdr[2 * nb + 1] = at;
+            hdr[4 * nb] = rid;
+            hdr[4 * nb + 1] = at;
+            hdr[4 * nb + 2] = hdr[4 * nb + 3] = 0;
         }
         ++nb;
         fill = 0;
@@ -623,7 +624,7 @@ int rt_stream_pack(int64_t n, const int32_t* ref_id, const int32_t* first, const
                 int64_t got;
                 if (write)
                     got = rt_stream_pack_range(ref_id + at, first + at, last + at, mlen + at, flag + at, mapq + at, nh + at, m,
-                                               records + blocks[r] * RT_STREAM_BLOCK, hdr + 2 * blocks[r], blocks[r + 1] - blocks[r]);
+                                               records + blocks[r] * RT_STREAM_BLOCK, hdr + 4 * blocks[r], blocks[r + 1] - blocks[r]);
                 else
                     got = blocks[r + 1] = rt_stream_pack_range(ref_id + at, first + at, last + at, mlen + at, flag + at, mapq + at,
                                                                nh + at, m, nullptr, nullptr, 0);

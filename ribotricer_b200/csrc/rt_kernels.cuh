@@ -2428,14 +2428,15 @@ __global__ void __launch_bounds__(kBinThreads) bin_psites_kernel(const BinArgs a
 
 // ---- K1 on a record stream ----------------------------------------------------------------------------
 // A coordinate-sorted library as 4-byte delta-coded records in blocks of RT_STREAM_BLOCK (format: ribotricer_b200.h).
-// One CTA per block: a thread takes 8 consecutive records (two 128-bit loads), positions come from a block-wide
+// One warp per block: a lane takes 8 consecutive records (two 128-bit loads), positions come from a warp-wide
 // prefix sum over the records' advances, the contig is a property of the block.  The filter cascade (bam.py:77-91,
 // common.py:33-69) is one shared-memory lookup on the 7 raw bits the record carries; runs of equal slots are merged
 // inside the thread's strip (duplicated 5' ends are adjacent in a sorted library) before the RED.
 struct StreamArgs {
     int32_t* cov;
     const uint4* rec;              // n_blocks * RT_STREAM_BLOCK records
-    const int2* hdr;               // per block: (ref_id, position the deltas start from)
+    const int4* hdr;               // per block: (ref_id, position the deltas start from, 0, 0)
+    long long n_blocks;
     int protocol;
     int weight;
     int len_base;
@@ -2451,7 +2452,8 @@ struct StreamArgs {
 };
 
 constexpr int kStreamThreads = 256;
-constexpr int kStreamStrip = RT_STREAM_BLOCK / kStreamThreads;      // records per thread
+constexpr int kStreamWarps = kStreamThreads / 32;
+constexpr int kStreamStrip = RT_STREAM_BLOCK / 32;                  // records per lane: one warp takes one block
 static_assert(kStreamStrip == 8, "bin_stream_kernel loads a strip as two uint4");
 
 __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned s) {   // PTX shl: shift amounts above 31 give 0
@@ -2460,157 +2462,163 @@ __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned s) {   // PTX
     return r;
 }
 
+constexpr int kStreamModes = 512;       // read lengths below this find their offset in shared memory
+constexpr int kStreamFastLens = 256;    // a read without an extension record is shorter than this
+constexpr unsigned kShValid = 4u * RT_ST_VALID - 4u;
+constexpr int kFastCounted = 1, kFastBinned = 2, kFastNoCounter = 4;    // low bits of a fast-path entry's y
+
+// Slots of the strip's records -> coverage.  detect_orfs.py:82 with duplicates merged: one RED per run of equal slots.
+template <typename slot_t>
+__device__ __forceinline__ void stream_scatter(int32_t* cov, const slot_t (&slot)[kStreamStrip], int weight) {
+    constexpr slot_t kNone = (slot_t)-1;
+    slot_t cur = kNone;
+    int cnt = 0;
+#ifdef RT_BIN_NO_RED      // A/B build only: everything but the scatter itself
+    unsigned long long sink = 0;
+#define RT_STREAM_RED(p, v) sink += (unsigned long long)((p) - cov) * (unsigned)(v)
+#elif defined(RT_BIN_RED_L2ONLY)   // A/B build only: the same REDs folded into 256 KB that stay in L2 (wrong coverage)
+#define RT_STREAM_RED(p, v) atomicAdd(cov + (((p) - cov) & 0xffff), (v))
+#else
+#define RT_STREAM_RED(p, v) atomicAdd((p), (v))
+#endif
+#pragma unroll
+    for (int j = 0; j < kStreamStrip; ++j) {
+        if (slot[j] != cur) {
+            if (cur != kNone) RT_STREAM_RED(cov + cur, weight * cnt);
+            cur = slot[j];
+            cnt = 0;
+        }
+        ++cnt;
+    }
+    if (cur != kNone) RT_STREAM_RED(cov + cur, weight * cnt);
+#ifdef RT_BIN_NO_RED
+    if (sink == 0x123456789abcdefull) cov[0] = 1;      // keeps the slot computation alive
+#endif
+#undef RT_STREAM_RED
+}
+
+// (word, bit) of the dense slot -> slot of the current layout (compact: through the member bitmap and the rank word)
+template <bool Compact, typename slot_t>
+__device__ __forceinline__ void stream_slots(const StreamArgs& a, unsigned live, const unsigned (&wd)[kStreamStrip],
+                                             const unsigned (&bit)[kStreamStrip], slot_t (&slot)[kStreamStrip]) {
+    constexpr slot_t kNone = (slot_t)-1;
+    if (Compact) {
+        unsigned cb[kStreamStrip];
+#pragma unroll
+        for (int j = 0; j < kStreamStrip; ++j) cb[j] = (live >> j) & 1u ? __ldg(a.cbits + (wd[j] >> 5)) : 0u;
+#pragma unroll
+        for (int h = 0; h < kStreamStrip; h += 4) {      // the rank words of four records in flight together
+            uint2 m[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                m[j] = ((cb[h + j] >> (wd[h + j] & 31u)) & 1u) ? __ldg(a.cmap + wd[h + j]) : make_uint2(0u, 0u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned above = m[j].x >> bit[h + j];
+                slot[h + j] = (above & 1u) ? (slot_t)(m[j].y - (unsigned)__popc(above)) : kNone;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kStreamStrip; ++j)
+            slot[j] = (live >> j) & 1u ? (slot_t)(((unsigned long long)wd[j] << 5) | bit[j]) : kNone;
+    }
+}
+
+constexpr int kStreamContigs = 256;     // contig table entries kept in shared memory
+#ifndef RT_STREAM_CTAS_PER_SM
+#define RT_STREAM_CTAS_PER_SM 3
+#endif
+
+// Persistent: RT_STREAM_CTAS_PER_SM CTAs per SM; every WARP walks blocks of the stream on its own (no CTA-wide barrier
+// after start-up, so the warps of an SM drift apart and cover each other's load latencies).  A warp owns a ring of two
+// shared-memory stages with one mbarrier each: an elected lane brings block i + 1 (1 KB of records and its header) in
+// with a cp.async.bulk pair while the warp works on block i.  The lookup tables are built once per CTA and the
+// per-thread 4-bit counters are drained into 8-bit ones every block.
 template <bool Compact>
-__global__ void __launch_bounds__(kStreamThreads) bin_stream_kernel(const StreamArgs a) {
+__global__ void __launch_bounds__(kStreamThreads, RT_STREAM_CTAS_PER_SM) bin_stream_kernel(const StreamArgs a) {
+    __shared__ __align__(128) unsigned int s_rec[kStreamWarps][2][RT_STREAM_BLOCK];
+    __shared__ __align__(16) int4 s_hdr[kStreamWarps][2];
+    __shared__ __align__(8) uint64_t s_bar[kStreamWarps][2];
     __shared__ unsigned int s_stats[RT_N_STATS];
     __shared__ unsigned int s_len[kLenHist];
-    __shared__ unsigned int s_warp[kStreamThreads / 32];
+    __shared__ int s_mode[kStreamModes];
+    // fast path, per read length: (offset of a '+' P-site from `first`, of a '-' one and flags, the length's 4-bit counter as two words)
+    __shared__ int4 s_fast[kStreamFastLens];
+    __shared__ int2 s_ctab[kStreamContigs];
     __shared__ uint8_t s_cat[128];
+    __shared__ uint8_t s_sh[256];       // fast path: 4 * category - 4 of a record's meta byte
+    if ((threadIdx.x & 31) == 0) {
+        mbar_init(&s_bar[threadIdx.x >> 5][0], 1);
+        mbar_init(&s_bar[threadIdx.x >> 5][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int i = threadIdx.x; i < kLenHist; i += kStreamThreads) s_len[i] = 0;
+    for (int i = threadIdx.x; i < kStreamModes; i += kStreamThreads) s_mode[i] = __ldg(a.len_table + i);
+    for (int i = threadIdx.x; i < kStreamContigs && i < a.n_contig; i += kStreamThreads) s_ctab[i] = __ldg(a.contig_tab + i);
     if (threadIdx.x < RT_N_STATS) s_stats[threadIdx.x] = 0;
-    if (threadIdx.x < 128) {       // the cascade on the record's raw bits, once per CTA
-        const unsigned m = threadIdx.x, st = (m >> 5) & 3u;
+    {   // the cascade on the record's raw bits, once per CTA
+        const unsigned m = threadIdx.x & 127u, st = (m >> 5) & 3u;
         int cat;
         if (m & RT_STREAM_QCFAIL) cat = RT_ST_QCFAIL;             // bam.py:77
         else if (m & RT_STREAM_DUPLICATE) cat = RT_ST_DUPLICATE;  // bam.py:80
         else if (m & RT_STREAM_SECONDARY) cat = RT_ST_SECONDARY;  // bam.py:83
         else if (m & RT_STREAM_UNMAPPED) cat = RT_ST_UNMAPPED;    // bam.py:86
         else cat = (st == RT_STREAM_NH_ONE || st == RT_STREAM_NH_ABSENT_MAPQ255) ? RT_ST_VALID : RT_ST_MULTI;   // common.py:53-69
-        s_cat[m] = (uint8_t)cat;
+        if (threadIdx.x < 128) s_cat[m] = (uint8_t)cat;
+        s_sh[threadIdx.x] = (uint8_t)(4 * cat - 4);
     }
+    {   // fast-path entry of read length l = threadIdx.x
+        const int l = threadIdx.x;
+        const int mode = __ldg(a.len_table + l);
+        const unsigned dl = (unsigned)(l - a.len_base);
+        const bool filtered = mode == RT_LEN_FILTERED;      // bam.py:101: counted nowhere
+        const bool unused = mode == RT_LEN_UNUSED;          // detect_orfs.py:74: counted, not binned
+        const bool plainlen = !filtered && !unused;
+        int4 e;
+        // pad + p of bam.py:135 / detect_orfs.py:78-81 relative to `first`: '+' reads first + x, '-' reads first + x + (y >> 3)
+        e.x = plainlen ? mode + a.pad + 1 : 0;
+        e.y = ((plainlen ? l - 1 - 2 * mode : 0) << 3) | (dl < 16u || filtered ? 0 : kFastNoCounter) | (plainlen ? kFastBinned : 0) |
+              (filtered ? 0 : kFastCounted);
+        e.z = filtered ? 0 : (int)shl_clamp(1u, dl < 16u ? 4u * dl : 255u);
+        e.w = filtered ? 0 : (int)shl_clamp(1u, dl < 16u ? 4u * dl - 32u : 255u);
+        s_fast[l] = e;
+    }
+    __syncthreads();
 
     using slot_t = typename std::conditional<Compact, unsigned, long long>::type;
-    constexpr slot_t kNone = (slot_t)-1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int2 hd = __ldg(a.hdr + blockIdx.x);
-    const uint4* p = a.rec + (size_t)blockIdx.x * (RT_STREAM_BLOCK / 4) + 2 * threadIdx.x;
-    unsigned w[kStreamStrip + 1];
-    {
-        const uint4 r0 = __ldg(p), r1 = __ldg(p + 1);
-        w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w;
-        w[4] = r1.x; w[5] = r1.y; w[6] = r1.z; w[7] = r1.w;
-        // an extension record follows its read, possibly in the next thread's strip (never in the next block)
-        w[8] = __shfl_down_sync(kFull, w[0], 1);
-        if (lane == 31) w[8] = threadIdx.x == kStreamThreads - 1 ? (unsigned)RT_STREAM_NULL : __ldg(reinterpret_cast<const unsigned*>(p + 2));
-    }
-    // positions: inclusive prefix of the advances inside the strip, exclusive prefix over the strips of the block
-    unsigned pos[kStreamStrip];
-    unsigned run = 0;
-#pragma unroll
-    for (int j = 0; j < kStreamStrip; ++j) {
-        const unsigned x = w[j];
-        const unsigned skip = (x & RT_STREAM_KIND_EXT) ? 0u : ((x >> 16) | ((x & 0x3fffu) << 16));
-        run += (x & RT_STREAM_SPECIAL) ? skip : (x & 0x7fffu);
-        pos[j] = run;
-    }
-    unsigned incl = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned t = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    unsigned before = (unsigned)hd.y + incl - run;
-#pragma unroll
-    for (int k = 0; k < kStreamThreads / 32 - 1; ++k) before += k < warp ? s_warp[k] : 0u;
-
-    const int c = hd.x;
-    const bool known = (unsigned)c < (unsigned)a.n_contig;
-    const int2 ct = known ? __ldg(a.contig_tab + c) : make_int2(0, 0);
-    const unsigned span = (unsigned)(ct.x + 2 * a.pad);
     const bool fwd = a.protocol == RT_PROTOCOL_FORWARD;
     const bool stores = a.protocol <= RT_PROTOCOL_REVERSE;
+    const unsigned prot_bit = fwd ? 0u : 1u;
+    const unsigned char* rec_bytes = reinterpret_cast<const unsigned char*>(a.rec);
+    const unsigned char* hdr_bytes = reinterpret_cast<const unsigned char*>(a.hdr);
+    auto issue = [&](long long blk, unsigned st) {     // lane 0: bring block `blk` into the warp's stage st
+        mbar_expect_tx(&s_bar[warp][st], RT_STREAM_BLOCK * 4u + 16u);
+        tma_load_1d(s_rec[warp][st], rec_bytes + (size_t)blk * (RT_STREAM_BLOCK * 4u), RT_STREAM_BLOCK * 4u, &s_bar[warp][st]);
+        tma_load_1d(&s_hdr[warp][st], hdr_bytes + (size_t)blk * 16u, 16u, &s_bar[warp][st]);
+    };
+    const long long stride = (long long)gridDim.x * kStreamWarps;
+    long long blk = (long long)blockIdx.x * kStreamWarps + warp;
+    if (lane == 0 && blk < a.n_blocks) issue(blk, 0u);
 
-    unsigned packed = 0, len_lo = 0, len_hi = 0, n_reads = 0;
-    unsigned wd[kStreamStrip], bit[kStreamStrip], cb[kStreamStrip];
+    // 8-bit counters, four per word: categories RT_ST_QCFAIL.. (even / odd nibbles of `packed`), read lengths likewise
+    unsigned cat_e = 0, cat_o = 0, len_e0 = 0, len_o0 = 0, len_e1 = 0, len_o1 = 0, total = 0;
+    unsigned drained = 0;
+    auto flush = [&]() {           // byte counters -> shared memory (one REDUX per counter)
+        const unsigned cw[2] = {cat_e, cat_o};
+        unsigned mine = 0;
 #pragma unroll
-    for (int j = 0; j < kStreamStrip; ++j) {
-        const unsigned x = w[j];
-        const bool normal = !(x & RT_STREAM_SPECIAL);
-        const unsigned meta = x >> 24;
-        int l = (int)((x >> 16) & 0xffu);
-        int extra = 0;
-        if (normal && (meta & RT_STREAM_EXT)) {
-            const unsigned e = w[j + 1];
-            l |= (int)((e & 0xffu) << 8);
-            extra = (int)((e >> 16) | (((e >> 8) & 0x3fu) << 16));
+        for (int k = 0; k < 8; ++k) {          // nibble k of `packed` = byte k / 2 of the even or odd word
+            const unsigned v = __reduce_add_sync(kFull, (cw[k & 1] >> (8 * (k >> 1))) & 255u);
+            if (lane == k) mine = v;
         }
-        int cat = normal ? (int)s_cat[meta & 0x7fu] : 0;
-        n_reads += normal ? 1u : 0u;
-        int len = -1;
-        bool live = false;
-        wd[j] = 0; bit[j] = 0;
-        if (cat == RT_ST_VALID) {
-            const int mode = __ldg(a.len_table + l);
-            const bool minus = ((meta & RT_STREAM_REVERSE) != 0) == fwd;          // bam.py:105-131
-            const int first = (int)(before + pos[j]);
-            const int at = minus ? first + l - 1 + extra : first;
-            if (mode == RT_LEN_FILTERED || !stores) {
-                cat = 0;                                                           // bam.py:101 / no protocol branch
-            } else if (!known) {
-                cat = RT_ST_BADREF;                                                // bam.py:133
-            } else {
-                len = l;                                                           // bam.py:136
-                if (mode != RT_LEN_UNUSED) {                                       // detect_orfs.py:74
-                    const unsigned q = (unsigned)(at + (minus ? -mode : mode) + a.pad);
-                    if (q >= span) {
-                        atomicAdd(&s_stats[RT_ST_OOB], 1u);
-                    } else {
-                        const unsigned in_contig = q + 1u;
-                        wd[j] = (minus ? a.plane_words : 0u) + (unsigned)ct.y + (in_contig >> 5);
-                        bit[j] = in_contig & 31u;
-                        live = true;
-                    }
-                }
-            }
-        }
-        packed += shl_clamp(1u, 4u * (unsigned)cat - 4u);         // cat 0 counts nothing
-        const unsigned sh = len >= 0 ? 4u * (unsigned)(len - a.len_base) : 255u;
-        len_lo += shl_clamp(1u, sh);
-        len_hi += shl_clamp(1u, sh - 32u);
-        if (len >= 0 && (unsigned)(len - a.len_base) >= 16u) {
-            if (len < kLenHist) atomicAdd(&s_len[len], 1u);
-            else atomicAdd(a.len_counts + len, (unsigned long long)(long long)a.weight);
-        }
-        if (Compact) cb[j] = live ? __ldg(a.cbits + (wd[j] >> 5)) : 0u;
-        else cb[j] = live ? 0xffffffffu : 0u;
-    }
-    slot_t slot[kStreamStrip];
-    if (Compact) {
-        uint2 m[kStreamStrip];
-#pragma unroll
-        for (int j = 0; j < kStreamStrip; ++j)
-            m[j] = ((cb[j] >> (wd[j] & 31u)) & 1u) ? __ldg(a.cmap + wd[j]) : make_uint2(0u, 0u);
-#pragma unroll
-        for (int j = 0; j < kStreamStrip; ++j) {
-            const unsigned above = m[j].x >> bit[j];
-            slot[j] = (above & 1u) ? (slot_t)(m[j].y - (unsigned)__popc(above)) : kNone;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < kStreamStrip; ++j)
-            slot[j] = cb[j] ? (slot_t)(((unsigned long long)wd[j] << 5) | bit[j]) : kNone;
-    }
-    // detect_orfs.py:82 with duplicates merged: one RED per run of equal slots inside the strip
-    slot_t cur = kNone;
-    int cnt = 0;
-#pragma unroll
-    for (int j = 0; j < kStreamStrip; ++j) {
-        if (slot[j] != cur) {
-            if (cur != kNone) atomicAdd(a.cov + cur, a.weight * cnt);
-            cur = slot[j];
-            cnt = 0;
-        }
-        ++cnt;
-    }
-    if (cur != kNone) atomicAdd(a.cov + cur, a.weight * cnt);
-
-    {   // per-thread 4-bit length counters -> one REDUX per length, one shared atomic per lane
+        if (lane < 8 && mine) atomicAdd(&s_stats[1 + lane], mine);
+        const unsigned lw[4] = {len_e0, len_o0, len_e1, len_o1};
         unsigned mine_len = 0;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const unsigned v = __reduce_add_sync(kFull, ((k < 8 ? len_lo : len_hi) >> (4 * (k & 7))) & 15u);
+        for (int k = 0; k < 16; ++k) {         // length len_base + k: word k / 8, nibble k % 8
+            const unsigned v = __reduce_add_sync(kFull, (lw[2 * (k >> 3) + (k & 1)] >> (8 * ((k & 7) >> 1))) & 255u);
             if (lane == k) mine_len = v;
         }
         const int l = a.len_base + lane;
@@ -2618,16 +2626,156 @@ __global__ void __launch_bounds__(kStreamThreads) bin_stream_kernel(const Stream
             if (l < kLenHist) atomicAdd(&s_len[l], mine_len);
             else atomicAdd(a.len_counts + l, (unsigned long long)((long long)a.weight * mine_len));
         }
-    }
-    unsigned mine = 0;
+        const unsigned reads = __reduce_add_sync(kFull, total);
+        if (lane == 0 && reads) atomicAdd(&s_stats[RT_ST_TOTAL], reads);
+        cat_e = cat_o = len_e0 = len_o0 = len_e1 = len_o1 = total = 0;
+        drained = 0;
+    };
+
+    for (unsigned it = 0; blk < a.n_blocks; ++it, blk += stride) {
+        const unsigned st = it & 1u;
+        __syncwarp();          // every lane has read stage st ^ 1 (previous block): it is free again
+        if (lane == 0 && blk + stride < a.n_blocks) issue(blk + stride, st ^ 1u);
+        mbar_wait(&s_bar[warp][st], (it >> 1) & 1u);
+        const int4 hd = s_hdr[warp][st];
+        unsigned w[kStreamStrip + 1];
+        {
+            const uint4* sp = reinterpret_cast<const uint4*>(s_rec[warp][st]) + 2 * lane;
+            const uint4 r0 = sp[0], r1 = sp[1];
+            w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w;
+            w[4] = r1.x; w[5] = r1.y; w[6] = r1.z; w[7] = r1.w;
+        }
+        // the usual strip: eight reads, none with an extension record
+        const bool plain = __all_sync(kFull, ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) & (RT_STREAM_SPECIAL | (RT_STREAM_EXT << 24))) == 0u);
+        // positions: sum of the advances inside the strip, exclusive prefix over the strips of the block; the
+        // per-record positions are accumulated again where they are used (cheaper than eight live registers)
+        auto advance = [](unsigned x) {
+            const unsigned skip = (x & RT_STREAM_KIND_EXT) ? 0u : ((x >> 16) | ((x & 0x3fffu) << 16));
+            return (x & RT_STREAM_SPECIAL) ? skip : (x & 0x7fffu);
+        };
+        unsigned run = 0;
+        if (plain) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const unsigned v = __reduce_add_sync(kFull, (packed >> (4 * k)) & 15u);
-        if (lane == k) mine = v;
+            for (int j = 0; j < kStreamStrip; ++j) run += w[j] & 0x7fffu;
+        } else {
+            // an extension record follows its read, possibly in the next thread's strip (never in the next block)
+            w[8] = lane == 31 ? (unsigned)RT_STREAM_NULL : s_rec[warp][st][kStreamStrip * (lane + 1)];
+#pragma unroll
+            for (int j = 0; j < kStreamStrip; ++j) run += advance(w[j]);
+        }
+        unsigned incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        unsigned at_first = (unsigned)hd.y + incl - run;      // position the strip's deltas start from
+
+        const int c = hd.x;
+        const bool known = (unsigned)c < (unsigned)a.n_contig;
+        int2 ct = make_int2(0, 0);
+        if (known) ct = c < kStreamContigs ? s_ctab[c] : __ldg(a.contig_tab + c);
+        const unsigned span = (unsigned)(ct.x + 2 * a.pad);
+
+        unsigned packed = 0, len_lo = 0, len_hi = 0, n_reads = 0;
+        unsigned wd[kStreamStrip], bit[kStreamStrip];
+        unsigned live = 0;              // bit j: record j bumps a slot
+        if (plain && known && stores) {
+            // ---- eight plain reads of a known reference: two shared-memory lookups per read, conditions as bit masks ----
+            unsigned odd = 0;           // != 0: some counted read has a length without a register counter
+            unsigned oob = 0;
+#pragma unroll
+            for (int j = 0; j < kStreamStrip; ++j) {
+                const unsigned x = w[j];
+                const unsigned t = s_sh[x >> 24];
+                const int4 e = s_fast[__byte_perm(x, 0u, 0x4442)];
+                const unsigned pm = t == kShValid ? 0xffffffffu : 0u;                 // passed the cascade
+                const unsigned cm = pm & (0u - ((unsigned)e.y & 1u));                 // counted (bam.py:101,136)
+                const unsigned bm = pm & (0u - (((unsigned)e.y >> 1) & 1u));          // binned (detect_orfs.py:74)
+                const unsigned mbit = ((x >> 28) ^ prot_bit) & 1u;                    // '-' strand (bam.py:105-131)
+                at_first += x & 0x7fffu;
+                const unsigned in_contig = at_first + (unsigned)e.x + ((unsigned)(e.y >> 3) & (0u - mbit));
+                const unsigned im = in_contig - 1u < span ? 0xffffffffu : 0u;
+                oob += bm & ~im & 1u;
+                wd[j] = (mbit ? a.plane_words : 0u) + (unsigned)ct.y + (in_contig >> 5);
+                bit[j] = in_contig & 31u;
+                live |= bm & im & (1u << j);
+                packed += shl_clamp(1u, t | (pm & ~cm & 0xe0u));                      // a filtered length counts in `total` only
+                len_lo += (unsigned)e.z & cm;
+                len_hi += (unsigned)e.w & cm;
+                odd |= cm & (unsigned)e.y & (unsigned)kFastNoCounter;
+            }
+            n_reads = kStreamStrip;
+            if (oob) atomicAdd(&s_stats[RT_ST_OOB], oob);
+            if (odd) {                  // rare: a length outside the 16 register counters
+#pragma unroll
+                for (int j = 0; j < kStreamStrip; ++j) {
+                    const int l = (int)__byte_perm(w[j], 0u, 0x4442);
+                    const int4 e = s_fast[l];
+                    if (s_sh[w[j] >> 24] == kShValid && (e.y & kFastCounted) && (e.y & kFastNoCounter)) atomicAdd(&s_len[l], 1u);
+                }
+            }
+        } else {
+            // ---- any record: specials, extensions, unknown reference, protocol without a branch in bam.py:105-131 ----
+            const unsigned sh_passed = known ? kShValid : 4u * RT_ST_BADREF - 4u;   // where a read that passed is counted
+#pragma unroll
+            for (int j = 0; j < kStreamStrip; ++j) {
+                const unsigned x = w[j];
+                const bool normal = !(x & RT_STREAM_SPECIAL);
+                const unsigned meta = x >> 24;
+                int l = (int)__byte_perm(x, 0u, 0x4442);                  // bits 16-23
+                int last_off = l - 1;                                     // last - first
+                if (normal && (meta & RT_STREAM_EXT)) {
+                    const unsigned e = w[j + 1];
+                    l |= (int)((e & 0xffu) << 8);
+                    last_off = l - 1 + (int)((e >> 16) | (((e >> 8) & 0x3fu) << 16));
+                }
+                const int cat = normal ? (int)s_cat[meta & 0x7fu] : 0;
+                n_reads += normal ? 1u : 0u;
+                int mode = s_mode[l & (kStreamModes - 1)];
+                if (l >= kStreamModes) mode = __ldg(a.len_table + l);     // rare: not a Ribo-seq read length
+                const bool passed = cat == RT_ST_VALID;
+                // bam.py:101 and protocols without a branch in bam.py:105-131 count the read in `total` only
+                const bool kept = passed && mode != RT_LEN_FILTERED && stores;
+                const bool counted = kept && known;                       // bam.py:136 (a read without a reference name is dropped, :133)
+                const bool minus = ((meta & RT_STREAM_REVERSE) != 0) == fwd;           // bam.py:105-131
+                at_first += advance(x);
+                const int at = (int)at_first + (minus ? last_off : 0);
+                const unsigned q = (unsigned)(at + (minus ? -mode : mode) + a.pad);    // detect_orfs.py:78-81
+                const bool binned = counted && mode != RT_LEN_UNUSED;                  // detect_orfs.py:74
+                const bool inside = q < span;
+                if (binned && !inside) atomicAdd(&s_stats[RT_ST_OOB], 1u);
+                const unsigned in_contig = q + 1u;
+                wd[j] = (minus ? a.plane_words : 0u) + (unsigned)ct.y + (in_contig >> 5);
+                bit[j] = in_contig & 31u;
+                live |= (binned && inside) ? 1u << j : 0u;
+                // categories: what the cascade said, except that a read that passed is counted as valid / badref / nothing
+                const unsigned sh_cat = passed ? (kept ? sh_passed : 255u) : 4u * (unsigned)cat - 4u;
+                packed += shl_clamp(1u, sh_cat);
+                const unsigned dl = (unsigned)(l - a.len_base);
+                const unsigned sh = counted ? 4u * dl : 255u;
+                len_lo += shl_clamp(1u, sh);
+                len_hi += shl_clamp(1u, sh - 32u);
+                if (counted && dl >= 16u) {
+                    if (l < kLenHist) atomicAdd(&s_len[l], 1u);
+                    else atomicAdd(a.len_counts + l, (unsigned long long)(long long)a.weight);
+                }
+            }
+        }
+        slot_t slot[kStreamStrip];
+        stream_slots<Compact, slot_t>(a, live, wd, bit, slot);
+        stream_scatter<slot_t>(a.cov, slot, a.weight);
+        // drain the 4-bit counters (at most 8 each) into the 8-bit ones; those hold 31 blocks of the warp
+        cat_e += packed & 0x0f0f0f0fu;
+        cat_o += (packed >> 4) & 0x0f0f0f0fu;
+        len_e0 += len_lo & 0x0f0f0f0fu;
+        len_o0 += (len_lo >> 4) & 0x0f0f0f0fu;
+        len_e1 += len_hi & 0x0f0f0f0fu;
+        len_o1 += (len_hi >> 4) & 0x0f0f0f0fu;
+        total += n_reads;
+        if (++drained == 31u) flush();
     }
-    if (lane < 8 && mine) atomicAdd(&s_stats[1 + lane], mine);
-    const unsigned reads = __reduce_add_sync(kFull, n_reads);
-    if (lane == 0 && reads) atomicAdd(&s_stats[RT_ST_TOTAL], reads);
+    flush();
     __syncthreads();
     if (threadIdx.x < RT_N_STATS && s_stats[threadIdx.x])
         atomicAdd(a.stats + threadIdx.x, (unsigned long long)((long long)a.weight * s_stats[threadIdx.x]));

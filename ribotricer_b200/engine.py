@@ -329,7 +329,7 @@ class Engine:
         return dict(zip(_lib.ST_NAMES, stats.tolist())), len_counts
 
     def stream_reads(self, cols: dict, pinned: bool = False, n_threads: int = 0) -> dict:
-        """A coordinate-sorted library as the 4 B/read record stream of ``rt_stream_pack`` (blocks of 2,048 delta-coded
+        """A coordinate-sorted library as the 4 B/read record stream of ``rt_stream_pack`` (blocks of 256 delta-coded
         records; the raw filter bits travel with every read and the cascade runs on the device).  Raises ``RtError``
         when the library cannot be coded (not sorted): use the column entry points then."""
         t = self.torch
@@ -350,11 +350,11 @@ class Engine:
         nb = int(n_blocks.value)
         if pinned:
             rec = t.empty(max(nb, 1) * _lib.RT_STREAM_BLOCK, dtype=t.int32).pin_memory()
-            hdr = t.empty(max(nb, 1) * 2, dtype=t.int32).pin_memory()
+            hdr = t.empty(max(nb, 1) * 4, dtype=t.int32).pin_memory()
             rp, hp = C.c_void_p(rec.data_ptr()), C.c_void_p(hdr.data_ptr())
         else:
             rec = np.empty(max(nb, 1) * _lib.RT_STREAM_BLOCK, np.uint32)
-            hdr = np.empty(max(nb, 1) * 2, np.int32)
+            hdr = np.empty(max(nb, 1) * 4, np.int32)
             rp, hp = _np_ptr(rec), _np_ptr(hdr)
         rc = self.lib.rt_stream_pack(n, *ptrs, int(n_threads), nb, rp, hp, C.byref(n_blocks))
         if rc != 0:

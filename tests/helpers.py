@@ -92,14 +92,15 @@ def compare_scores(got, ref, tie, params=DEFAULT_PARAMS, what=""):
     return int(tie.sum()), int(near.sum())
 
 
-def decode_stream(records, hdr, n_blocks, block=2048):
+def decode_stream(records, hdr, n_blocks, block=256):
     """Checker-side decoder of the record stream of include/ribotricer_b200.h (rt_stream_pack): returns one tuple
     (ref_id, first, last, mlen, meta7) per read record, in order.  Plain Python: small cases only."""
     out = []
     rec = np.asarray(records, np.uint32).reshape(-1)
     hdr = np.asarray(hdr, np.int32).reshape(-1)
     for b in range(n_blocks):
-        ref, pos = int(hdr[2 * b]), int(hdr[2 * b + 1])
+        ref, pos = int(hdr[4 * b]), int(hdr[4 * b + 1])
+        assert hdr[4 * b + 2] == 0 and hdr[4 * b + 3] == 0
         words = rec[b * block:(b + 1) * block].tolist()
         assert len(words) == block
         k = 0

@@ -343,8 +343,8 @@ def _stream_pack(lib, cols, n_threads=3):
     rc = lib.rt_stream_pack(n, *args, n_threads, 0, None, None, C.byref(nb))
     if rc != 0:
         return rc, None, None, 0
-    rec = np.zeros(max(1, nb.value) * 2048, np.uint32)
-    hdr = np.zeros(max(1, nb.value) * 2, np.int32)
+    rec = np.zeros(max(1, nb.value) * _lib_block(), np.uint32)
+    hdr = np.zeros(max(1, nb.value) * 4, np.int32)
     rc = lib.rt_stream_pack(n, *args, n_threads, nb.value, p(rec), p(hdr), C.byref(nb))
     return rc, rec, hdr, nb.value
 
@@ -361,7 +361,7 @@ def test_stream_pack_round_trip(built):
     cols = _stream_columns()
     n = len(cols["ref_id"])
     rc, rec, hdr, nb = _stream_pack(lib, cols)
-    assert rc == 0 and nb >= (n + 2047) // 2048
+    assert rc == 0 and nb >= (n + _lib_block() - 1) // _lib_block()
     got = decode_stream(rec, hdr, nb)
     assert len(got) == n
     n_checked = 0
@@ -398,3 +398,9 @@ def test_stream_pack_round_trip(built):
 
 def _lib_estate():
     return -4
+
+
+def _lib_block():
+    from ribotricer_b200 import _lib
+
+    return _lib.RT_STREAM_BLOCK
