@@ -550,6 +550,11 @@ int64_t rt_stream_pack_range(const int32_t* __restrict__ ref_id, const int32_t* 
     int64_t cur_pos = m > 0 ? first[0] : 0;
     int64_t i = 0;
     while (i < m) {
+        if (i + kStreamGroup <= m && w.fill == RT_STREAM_BLOCK) {     // start the next block here: the group may well be plain
+            if (!w.open(ref_id[i], first[i])) return -2;
+            cur_ref = ref_id[i];
+            cur_pos = first[i];
+        }
         if (i + kStreamGroup <= m && w.fill + kStreamGroup <= RT_STREAM_BLOCK &&
             (rec ? rt_stream_group_code(ref_id + i, first + i, last + i, mlen + i, flag + i, mapq + i, nh + i, cur_ref, cur_pos,
                                         rec + (w.nb - 1) * RT_STREAM_BLOCK + w.fill)
