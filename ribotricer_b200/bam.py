@@ -9,6 +9,7 @@ environment, the same columns can also be loaded from a ``.npz`` file
 """
 from __future__ import annotations
 
+import os
 from collections import Counter, defaultdict
 from dataclasses import dataclass
 
@@ -146,7 +147,8 @@ class Alignments:
     """What ``split_bam`` returns: the library's reads, resident on the GPU.
 
     The reference returns ``alignments[length][strand][(chrom, pos)] -> count``
-    (bam.py:29,135); here the same information stays in HBM as read columns and is
+    (bam.py:29,135); here the same information stays in HBM -- as the 4 B/read record stream of
+    ``rt_stream_pack`` when the library is coordinate-sorted, else as the decoder's 18 B/read columns -- and is
     binned on demand (per length for the metagene step, merged for scoring)."""
 
     def __init__(self, engine: Engine, reads: ReadColumns, protocol: str, read_lengths=None):
@@ -154,9 +156,16 @@ class Alignments:
         self.reads = reads
         self.protocol = protocol
         self.read_lengths = None if read_lengths is None else [int(x) for x in read_lengths]
-        self.dcols = engine.upload_reads(reads.cols)
         self.n = len(reads)
         self.sorted = reads.sorted_by_coordinate
+        self.dcols = self.dstream = None
+        if self.sorted and self.n and os.environ.get("RT_READS_FORMAT", "stream") == "stream":
+            try:
+                self.dstream = engine.upload_stream(engine.stream_reads(reads.cols))
+            except _lib.RtError:       # "sorted" in the header, but the positions descend somewhere: plain columns
+                self.dstream = None
+        if self.dstream is None:
+            self.dcols = engine.upload_reads(reads.cols)
         self.stats: dict = {}
         self.read_length_counts: dict = {}
 
@@ -166,7 +175,7 @@ class Alignments:
         eng.set_length_table(None, self.read_lengths)     # no offsets: nothing is binned
         cov = eng.torch.zeros(1, dtype=eng.torch.int32, device=eng.device)
         stats, lc = eng.new_bin_accumulators()
-        eng.bin_reads_device(cov, self.dcols, self.protocol, stats, lc, self.sorted, n=self.n)
+        self._bin(cov, stats, lc, 1)
         st = stats.cpu().numpy()
         lcn = lc.cpu().numpy()
         self.stats = dict(zip(_lib.ST_NAMES, st.tolist()))
@@ -182,8 +191,15 @@ class Alignments:
         eng = self.engine
         eng.set_length_table(psite_offsets, self.read_lengths)
         stats, lc = eng.new_bin_accumulators()
-        eng.bin_reads_device(cov, self.dcols, self.protocol, stats, lc, self.sorted, n=self.n, weight=weight)
+        self._bin(cov, stats, lc, weight)
         return stats
+
+    def _bin(self, cov, stats, lc, weight):
+        """K1 on the resident library: the stream kernel or the column kernel, same results."""
+        if self.dstream is not None:
+            self.engine.bin_stream_device(cov, self.dstream, self.protocol, stats, lc, weight=weight)
+        else:
+            self.engine.bin_reads_device(cov, self.dcols, self.protocol, stats, lc, self.sorted, n=self.n, weight=weight)
 
 
     def to_dict(self):
