@@ -31,7 +31,7 @@ txt = subprocess.run([py, os.path.join(HERE, "summarize.py"), rep], capture_outp
 open(os.path.join(HERE, f"{tag}_step_kernels.txt"), "w").write(txt)
 
 # 2. per-line profiles: (mangled symbol substring, ncu regex, file tag)
-KERNELS = [("bin_psites_kernelILb1ELb0E", "bin_psites", "bin_psites_kernel"),
+KERNELS = [("bin_stream_kernelILb1E", "bin_stream", "bin_stream_kernel"),
            ("atom_pass_kernelILi2ELb0E", "atom_pass", "atom_pass_kernel"),
            ("compose_refs_kernelILb0E", "compose_refs", "compose_refs_kernel")]
 for sym, rx, name in KERNELS:
@@ -69,10 +69,12 @@ per = collections.OrderedDict()
 n_steps = 0
 for r in csv.reader(open(launches)):
     if len(r) > 14 and r[12] == "gpu__time_duration.sum":
-        k = re.sub(r"^void |<.*|\(.*", "", r[4])
+        k = re.sub(r"^void |rt::|<.*|\(.*", "", r[4])
         grid = int(r[8].strip("()").split(",")[0])
         per.setdefault(k, []).append((grid, float(r[14]) / 1e6))
-for k in per:   # the e2e leg launches K1 in 4 M-read chunks: keep the whole-library launches only
+STEP = ("bin_stream_kernel", "bin_psites_kernel", "atom_pass_kernel", "compose_refs_kernel", "score_orfs_kernel")
+per = collections.OrderedDict((k, v) for k, v in per.items() if k in STEP)   # not the one-time set-up kernels
+for k in per:   # the e2e leg launches K1 in 1 M-read chunks: keep the whole-library launches only
     g = max(x[0] for x in per[k])
     per[k] = [t for x, t in per[k] if x == g]
 lines = []
