@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--reads-format", default="stream", choices=["stream", "columns"],
                     help="resident library of the device-timed step: the 4 B/read record stream (rt_bin_stream, default) or the "
                          "decoder's 18 B/read columns (rt_bin_reads)")
+    ap.add_argument("--k1", default="fresh", choices=["fresh", "red"],
+                    help="K1 of the device-timed step on the record stream: rt_bin_stream_fresh (zones: the call overwrites the "
+                         "buffer, the step has no clear) or rt_bin_stream into a buffer the step clears (A/B)")
     ap.add_argument("--layout", default="compact", choices=["compact", "dense"],
                     help="coverage layout: exon union of the index (default) or genome-wide planes")
     return ap.parse_args()
@@ -314,6 +317,7 @@ def run_ours(args):
     hreads = {k: v.cpu().pin_memory() for k, v in dreads.items()}
     use_stream = args.reads_format == "stream" and args.layout == "compact"
     hstream = dstream = None
+    use_fresh = use_stream and args.k1 == "fresh"
     if use_stream:       # the library as a record stream (rt_stream_pack): resident copy for `value`, host copy for e2e_stream
         hstream = eng.stream_reads({k: v.numpy() for k, v in hreads.items()}, pinned=True)
         dstream = eng.upload_stream(hstream)
@@ -348,7 +352,7 @@ def run_ours(args):
         if events is not None:
             events[0].record()
         if use_stream:
-            eng.bin_stream_device(cov, dstream, "forward", stats, len_counts)
+            eng.bin_stream_device(cov, dstream, "forward", stats, len_counts, fresh=use_fresh)
         else:
             eng.bin_reads_device(cov, dreads, "forward", stats, len_counts, sorted_hint=True)
         if events is not None:
@@ -356,7 +360,8 @@ def run_ours(args):
         eng.score_device(cov, out, 0, n_orf, params)
         if events is not None:
             events[2].record()
-        eng.clear_touched(cov)      # dense: zero exactly the sectors this library touched; compact: memset
+        if not use_fresh:
+            eng.clear_touched(cov)      # dense: zero exactly the sectors this library touched; compact: memset
         if events is not None:
             events[3].record()
 
@@ -383,7 +388,8 @@ def run_ours(args):
     bin_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in per_step_events]))
     score_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in per_step_events]))
     unbin_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in per_step_events]))
-    assert int(cov.abs().max().item()) == 0, "coverage did not return to zero after the sparse clear"
+    if not use_fresh:
+        assert int(cov.abs().max().item()) == 0, "coverage did not return to zero after the sparse clear"
 
     # ---- e2e: host buffers in, host buffers out, through the host-buffer C-ABI calls
     # From the decoder's host columns nothing is prepared outside the timed region: rt_bin_reads_host delta-codes every
@@ -477,8 +483,10 @@ def run_ours(args):
                 "coverage_layout": args.layout, "min_reads_per_codon": args.min_reads_per_codon,
                 "resident_library": ("record stream, 4 B/read (rt_stream_pack; raw filter bits per read, cascade on the device), "
                                      "%.2f GB" % (stream_bytes / max(1, world) / 1e9)) if use_stream else "decoder columns, 18 B/read",
-                "step": "bin P-sites -> gather+score -> clear (resident coverage back to zero: memset of the compact "
-                        "buffer, or sparse clear of the touched sectors of the dense planes)",
+                "step": ("bin P-sites (rt_bin_stream_fresh: every block zeroes its zone of the compact buffer and adds its reads, "
+                         "so the library overwrites the previous one and the step has no clear) -> gather+score") if use_fresh else
+                        ("bin P-sites -> gather+score -> clear (resident coverage back to zero: memset of the compact "
+                         "buffer, or sparse clear of the touched sectors of the dense planes)"),
             },
             "reads_binned_per_s": n_reads_total / (ms_per_step * 1e-3),
             "kernels_ms": {"bin_psites": bin_ms, "score_orfs": score_ms, "clear": unbin_ms},

@@ -213,6 +213,16 @@ int rt_bin_stream(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t*
                   void* stream);
 int rt_bin_stream_host(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t* h_records, const int32_t* h_hdr,
                        int protocol, int64_t* h_stats, int64_t* h_len_counts);
+/* A whole library into a coverage buffer of the COMPACT layout that need NOT be cleared first: the call overwrites
+ * every slot.  The compact buffer is cut into one zone per stream block and strand (from the rank of the block's header
+ * position to that of the next block's); a block zeroes its zones with plain stores and adds its own reads into the
+ * lines it has just written, so neither the clear of the buffer nor the read half of the scatter's read-modify-write
+ * reaches DRAM.  Reads whose P-site falls outside their block's zone (a few per thousand at block edges; any read of
+ * a stream that is not sorted) are added afterwards from a spill list.  Same results as rt_clear_coverage +
+ * rt_bin_stream(weight 1); the stats and length counts are added to, as everywhere. */
+int rt_bin_stream_fresh(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t* d_records /* 16-byte aligned */,
+                        const int32_t* d_hdr /* 16-byte aligned */, int protocol, int64_t* d_stats,
+                        int64_t* d_len_counts, void* stream);
 
 int rt_clear_coverage(rt_ctx* ctx, int32_t* d_cov, void* stream);
 

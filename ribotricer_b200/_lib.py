@@ -23,7 +23,7 @@ RT_STREAM_BLOCK = 256
 EXPORTS = (
     "rt_abi_version", "rt_last_error", "rt_create", "rt_destroy", "rt_device_count",
     "rt_set_genome", "rt_plane_elems", "rt_get_contig_base", "rt_set_length_table",
-    "rt_bin_reads", "rt_bin_reads_host", "rt_pack_read_meta", "rt_bin_reads_packed", "rt_bin_reads_packed_host", "rt_stream_pack", "rt_bin_stream", "rt_bin_stream_host", "rt_clear_coverage", "rt_set_layout", "rt_coverage_elems", "rt_track_touched", "rt_clear_touched", "rt_set_index", "rt_index_orfs",
+    "rt_bin_reads", "rt_bin_reads_host", "rt_pack_read_meta", "rt_bin_reads_packed", "rt_bin_reads_packed_host", "rt_stream_pack", "rt_bin_stream", "rt_bin_stream_host", "rt_bin_stream_fresh", "rt_clear_coverage", "rt_set_layout", "rt_coverage_elems", "rt_track_touched", "rt_clear_touched", "rt_set_index", "rt_index_orfs",
     "rt_index_score_bytes", "rt_index_total_nt", "rt_shard_bounds", "rt_score", "rt_score_host",
     "rt_gather_profiles", "rt_compact_from_dense", "rt_wig_tiles", "rt_wig_count", "rt_wig_fill", "rt_interval_sums", "rt_bootstrap_medians", "rt_launch_count", "rt_phasescore_values", "rt_io_last_error", "rt_index_load",
     "rt_index_free", "rt_index_n_orf", "rt_index_n_exon", "rt_index_n_annotated_prefix", "rt_index_n_chrom",
@@ -82,6 +82,7 @@ def load():
     lib.rt_stream_pack.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, vp, C.POINTER(i64)]
     lib.rt_bin_stream.argtypes = [vp, vp, i64, vp, vp, i32, i32, vp, vp, vp]
     lib.rt_bin_stream_host.argtypes = [vp, vp, i64, vp, vp, i32, vp, vp]
+    lib.rt_bin_stream_fresh.argtypes = [vp, vp, i64, vp, vp, i32, vp, vp, vp]
     lib.rt_clear_coverage.argtypes = [vp, vp, vp]
     lib.rt_track_touched.argtypes = [vp, i32]
     lib.rt_set_layout.argtypes = [vp, i32]

@@ -5,7 +5,7 @@ The index, its atoms and the compact slot map are set up once and stay on the GP
 ranks of a torchrun job round-robin; inside a rank they run through a three-stage software pipeline:
 
     stage(i)     decode / pack library i on the host, start its host-to-device copy on the copy stream
-    compute(i-1) clear a coverage buffer, K1 (record stream), phase A + B, start the device-to-host copy of the
+    compute(i-1) K1 on the record stream (rt_bin_stream_fresh: overwrites a coverage buffer, no clear), phase A + B, start the device-to-host copy of the
                  result columns -- all enqueued on the compute stream behind the copy of library i-1
     finalize(i-2) wait for library i-2, write its _bam_summary.txt and its TSV (K4 gathers the profiles of the
                  reported ORFs from the library's coverage buffer, which the pipeline keeps alive until then)
@@ -76,11 +76,11 @@ class LibraryPipeline:
         with t.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(job["copied"])
             cov = self.cov[slot]
-            eng.clear_coverage(cov)
             stats, len_counts = eng.new_bin_accumulators()
-            if "records" in job["dev"]:
-                eng.bin_stream_device(cov, job["dev"], self.protocol, stats, len_counts)
+            if "records" in job["dev"]:      # overwrites the buffer zone by zone: no clear
+                eng.bin_stream_device(cov, job["dev"], self.protocol, stats, len_counts, fresh=True)
             else:
+                eng.clear_coverage(cov)
                 eng.bin_reads_packed_device(cov, job["dev"], self.protocol, stats, len_counts)
             out = eng.new_score_columns(n_orf, min_codon=self.want_min)
             eng.score_device(cov, out, 0, n_orf, self.params)

@@ -65,6 +65,7 @@ struct rt_ctx {
     int32_t* d_len_table = nullptr;
     bool have_len_table = false;
     int len_base = 20;   // first of the 16 read lengths K1 counts in registers
+    int zone_delta_plus = 0, zone_delta_minus = 0;   // smallest P-site displacement from `first` on either strand
 
     // index
     int64_t n_orf = 0;
@@ -95,6 +96,8 @@ struct rt_ctx {
     int layout = RT_LAYOUT_DENSE;
     int64_t compact_elems = 0;                       // int32 elements of a compact coverage buffer (with guard)
     unsigned* d_cbits = nullptr;                     // one bit per cmap word: the word has members
+    unsigned compact_plus_end = 0, compact_end = 0;  // compact index after the last '+' slot / after the last slot
+    DevBuf zone_buf, spill_buf;                      // rt_bin_stream_fresh: zone boundaries, spill list + its counter
     uint2* d_cmap = nullptr;                         // per 32 dense slots: member mask | compact index after the last member
     uint64_t* d_atoms_c = nullptr;                   // the same tables with compact slot offsets
     uint64_t* d_ref_ent_c = nullptr;
@@ -279,6 +282,13 @@ int build_atoms(rt_ctx* ctx, const std::vector<uint64_t>& desc, const std::vecto
         cat += len;
     }
     ctx->compact_elems = (int64_t)((cat + 31) / 32 * 32 + 32);
+    ctx->compact_end = (unsigned)std::min<uint64_t>(cat, 0xffffffffull);
+    ctx->compact_plus_end = ctx->compact_end;        // atoms are in slot order: the first one of the '-' plane ends the '+' part
+    for (size_t i = 0; i < atoms_c.size(); ++i)
+        if ((ctx->h_atoms[i] >> rt::kLenBits) >= (uint64_t)ctx->plane) {
+            ctx->compact_plus_end = (unsigned)(atoms_c[i] >> rt::kLenBits);
+            break;
+        }
     for (size_t k = 0; k < ref_ent_c.size(); ++k)
         ref_ent_c[k] = ctx->h_ref_atom[k] == 0xffffffffu ? ctx->h_ref_ent[k] : atoms_c[ctx->h_ref_atom[k]];
     for (size_t k = 0; k < entries.size(); ++k) {
@@ -484,6 +494,16 @@ int rt_set_length_table(rt_ctx* ctx, const int32_t* h_len_table) {
             ctx->len_base = i;
             break;
         }
+    // zone boundaries of rt_bin_stream_fresh: how far before / behind `first` a P-site can lie at the least
+    bool any = false;
+    for (int i = 0; i < RT_LEN_TABLE; ++i)
+        if (h_len_table[i] > RT_LEN_FILTERED) {
+            const int plus = h_len_table[i], minus = i - 1 - h_len_table[i];
+            ctx->zone_delta_plus = any ? std::min(ctx->zone_delta_plus, plus) : plus;
+            ctx->zone_delta_minus = any ? std::min(ctx->zone_delta_minus, minus) : minus;
+            any = true;
+        }
+    if (!any) ctx->zone_delta_plus = ctx->zone_delta_minus = 0;
     return RT_OK;
 }
 
@@ -512,6 +532,27 @@ int rt_set_layout(rt_ctx* ctx, int layout) {
                 rt::build_cmap_kernel<<<grid, 256>>>(ctx->d_atoms, ctx->d_atoms_c, ctx->n_atoms, ctx->d_cmap);
                 ctx->launches++;
                 RT_CUDA(ctx, cudaGetLastError());
+            }
+            {   // empty words carry the compact index of the next member (cmap_rank: zone boundaries of rt_bin_stream_fresh)
+                const size_t tiles = (words + rt::kGapTile - 1) / rt::kGapTile;
+                DevBuf tile_buf;
+                RT_CUDA(ctx, tile_buf.reserve(sizeof(unsigned) * tiles));
+                unsigned* d_tile = static_cast<unsigned*>(tile_buf.p);
+                rt::cmap_tile_last_kernel<<<(unsigned)tiles, 256>>>(ctx->d_cmap, (long long)words, d_tile);
+                std::vector<unsigned> h_tile(tiles);
+                RT_CUDA(ctx, cudaMemcpy(h_tile.data(), d_tile, sizeof(unsigned) * tiles, cudaMemcpyDeviceToHost));
+                unsigned carry = 0;
+                for (size_t t = 0; t < tiles; ++t) {      // exclusive prefix maximum
+                    const unsigned last = h_tile[t];
+                    h_tile[t] = carry;
+                    carry = std::max(carry, last);
+                }
+                RT_CUDA(ctx, cudaMemcpy(d_tile, h_tile.data(), sizeof(unsigned) * tiles, cudaMemcpyHostToDevice));
+                rt::cmap_fill_gaps_kernel<<<(unsigned)tiles, 256>>>(ctx->d_cmap, (long long)words, d_tile);
+                ctx->launches += 2;
+                RT_CUDA(ctx, cudaGetLastError());
+                RT_CUDA(ctx, cudaDeviceSynchronize());
+                tile_buf.release();
             }
             RT_CUDA(ctx, cudaMalloc(&ctx->d_cbits, sizeof(unsigned) * ((words + 31) / 32)));
             rt::build_cbits_kernel<<<(unsigned)((words + 255) / 256), 256>>>(ctx->d_cmap, (long long)words, ctx->d_cbits);
@@ -649,20 +690,25 @@ int rt_bin_reads_packed(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* d
     return launch_bin(ctx, "rt_bin_reads_packed", a, true, d_cov, n, protocol, weight, d_stats, d_len_counts, stream);
 }
 
-int rt_bin_stream(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t* d_records, const int32_t* d_hdr, int protocol,
-                  int weight, int64_t* d_stats, int64_t* d_len_counts, void* stream) {
-    if (!ctx) return fail(nullptr, RT_EINVAL, "rt_bin_stream: ctx is NULL");
-    if (weight != 1 && weight != -1) return fail(ctx, RT_EINVAL, "rt_bin_stream: weight must be +1 or -1");
-    if (ctx->plane == 0) return fail(ctx, RT_ESTATE, "rt_bin_stream: call rt_set_genome first");
-    if (!ctx->have_len_table) return fail(ctx, RT_ESTATE, "rt_bin_stream: call rt_set_length_table first");
+static int launch_stream(rt_ctx* ctx, const char* who, bool fresh, int32_t* d_cov, int64_t n_blocks, const uint32_t* d_records,
+                         const int32_t* d_hdr, int protocol, int weight, int64_t* d_stats, int64_t* d_len_counts, void* stream) {
+    if (!ctx) return fail(nullptr, RT_EINVAL, "%s: ctx is NULL", who);
+    if (weight != 1 && weight != -1) return fail(ctx, RT_EINVAL, "%s: weight must be +1 or -1", who);
+    if (ctx->plane == 0) return fail(ctx, RT_ESTATE, "%s: call rt_set_genome first", who);
+    if (!ctx->have_len_table) return fail(ctx, RT_ESTATE, "%s: call rt_set_length_table first", who);
     if (n_blocks < 0 || !d_cov || !d_stats || !d_len_counts || (n_blocks > 0 && (!d_records || !d_hdr)))
-        return fail(ctx, RT_EINVAL, "rt_bin_stream: NULL argument or bad n_blocks");
+        return fail(ctx, RT_EINVAL, "%s: NULL argument or bad n_blocks", who);
     if ((reinterpret_cast<uintptr_t>(d_records) | reinterpret_cast<uintptr_t>(d_hdr)) & 15)
-        return fail(ctx, RT_EINVAL, "rt_bin_stream: d_records and d_hdr must be 16-byte aligned");
+        return fail(ctx, RT_EINVAL, "%s: d_records and d_hdr must be 16-byte aligned", who);
     if (ctx->track_touched && ctx->layout != RT_LAYOUT_COMPACT)
-        return fail(ctx, RT_ESTATE, "rt_bin_stream: the touched-slot list of the dense layout is kept by rt_bin_reads only");
-    if (n_blocks == 0) return RT_OK;
+        return fail(ctx, RT_ESTATE, "%s: the touched-slot list of the dense layout is kept by rt_bin_reads only", who);
+    if (fresh && ctx->layout != RT_LAYOUT_COMPACT) return fail(ctx, RT_ESTATE, "%s: needs the compact layout (rt_set_layout)", who);
     DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_blocks == 0) {
+        if (fresh) RT_CUDA(ctx, cudaMemsetAsync(d_cov, 0, sizeof(int32_t) * (size_t)ctx->compact_elems, st));
+        return RT_OK;
+    }
     rt::StreamArgs a{};
     a.cov = d_cov;
     a.rec = reinterpret_cast<const uint4*>(d_records);
@@ -680,14 +726,59 @@ int rt_bin_stream(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t*
     a.plane_words = (unsigned)(ctx->plane >> 5);
     a.stats = reinterpret_cast<unsigned long long*>(d_stats);
     a.len_counts = reinterpret_cast<unsigned long long*>(d_len_counts);
-    cudaStream_t st = (cudaStream_t)stream;
-    // persistent: a few CTAs per SM walk the blocks, the next block in flight (cp.async.bulk) while one is processed
+    // persistent: a few CTAs per SM; every warp walks blocks with the next one in flight (cp.async.bulk)
     const unsigned grid = (unsigned)std::min<int64_t>((n_blocks + rt::kStreamWarps - 1) / rt::kStreamWarps, (int64_t)ctx->n_sm * RT_STREAM_CTAS_PER_SM);
-    if (a.cmap) rt::bin_stream_kernel<true><<<grid, rt::kStreamThreads, 0, st>>>(a);
-    else rt::bin_stream_kernel<false><<<grid, rt::kStreamThreads, 0, st>>>(a);
-    ctx->launches++;
+    if (fresh) {
+        // zone boundaries of the blocks (rank of the first position a read of the block can reach), made monotone
+        const int64_t tiles = (n_blocks + 1 + rt::kZoneTile - 1) / rt::kZoneTile;
+        RT_CUDA(ctx, ctx->zone_buf.reserve(sizeof(unsigned) * (2 * (size_t)(n_blocks + 1) + 4 * (size_t)tiles)));
+        RT_CUDA(ctx, ctx->spill_buf.reserve(sizeof(unsigned) * (size_t)n_blocks * RT_STREAM_BLOCK + 16));
+        rt::ZoneArgs z{};
+        z.hdr = a.hdr;
+        z.n_blocks = n_blocks;
+        z.bounds = static_cast<unsigned*>(ctx->zone_buf.p);
+        z.cmap = ctx->d_cmap;
+        z.contig_tab = ctx->d_contig_tab;
+        z.n_contig = ctx->n_contig;
+        z.pad = ctx->pad;
+        z.plane_words = a.plane_words;
+        z.delta_plus = ctx->zone_delta_plus;
+        z.delta_minus = ctx->zone_delta_minus;
+        z.plus_end = ctx->compact_plus_end;
+        z.minus_end = ctx->compact_end;
+        unsigned long long* d_n_spill = reinterpret_cast<unsigned long long*>(static_cast<char*>(ctx->spill_buf.p));
+        unsigned* d_tile_max = z.bounds + 2 * (size_t)(n_blocks + 1);
+        unsigned* d_tile_carry = d_tile_max + 2 * (size_t)tiles;
+        a.zone_bounds = z.bounds;
+        a.zone_carry = d_tile_carry;
+        a.zone_tiles = tiles;
+        a.spill = reinterpret_cast<unsigned*>(d_n_spill + 2);
+        a.n_spill = d_n_spill;
+        RT_CUDA(ctx, cudaMemsetAsync(d_n_spill, 0, sizeof(unsigned long long), st));
+        // the few guard slots behind the last zone belong to no block
+        RT_CUDA(ctx, cudaMemsetAsync(d_cov + ctx->compact_end, 0, sizeof(int32_t) * (size_t)(ctx->compact_elems - ctx->compact_end), st));
+        rt::zone_bounds_kernel<<<dim3((unsigned)tiles, 2), rt::kZoneTile, 0, st>>>(z, d_tile_max);
+        rt::zone_carry_kernel<<<2, 1024, 0, st>>>(d_tile_max, d_tile_carry, tiles, z.plus_end);
+        rt::bin_stream_kernel<true, true><<<grid, rt::kStreamThreads, 0, st>>>(a);
+        rt::zone_spill_kernel<<<(unsigned)ctx->n_sm * 4, 256, 0, st>>>(d_cov, a.spill, d_n_spill);
+        ctx->launches += 4;
+    } else {
+        if (a.cmap) rt::bin_stream_kernel<true, false><<<grid, rt::kStreamThreads, 0, st>>>(a);
+        else rt::bin_stream_kernel<false, false><<<grid, rt::kStreamThreads, 0, st>>>(a);
+        ctx->launches++;
+    }
     RT_CUDA(ctx, cudaGetLastError());
     return RT_OK;
+}
+
+int rt_bin_stream(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t* d_records, const int32_t* d_hdr, int protocol,
+                  int weight, int64_t* d_stats, int64_t* d_len_counts, void* stream) {
+    return launch_stream(ctx, "rt_bin_stream", false, d_cov, n_blocks, d_records, d_hdr, protocol, weight, d_stats, d_len_counts, stream);
+}
+
+int rt_bin_stream_fresh(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t* d_records, const int32_t* d_hdr, int protocol,
+                        int64_t* d_stats, int64_t* d_len_counts, void* stream) {
+    return launch_stream(ctx, "rt_bin_stream_fresh", true, d_cov, n_blocks, d_records, d_hdr, protocol, 1, d_stats, d_len_counts, stream);
 }
 
 int rt_bin_stream_host(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint32_t* h_records, const int32_t* h_hdr, int protocol,

@@ -2437,6 +2437,14 @@ struct StreamArgs {
     const uint4* rec;              // n_blocks * RT_STREAM_BLOCK records
     const int4* hdr;               // per block: (ref_id, position the deltas start from, 0, 0)
     long long n_blocks;
+    // zoned launch (rt_bin_stream_fresh): zone_bounds[s * (n_blocks + 1) + b] = first compact slot of block b's zone on
+    // strand s; the block zero-fills [bounds[b], bounds[b + 1]) before it adds its own reads there, reads that fall
+    // outside go to the spill list and are added once every zone has been written
+    const unsigned* zone_bounds;
+    const unsigned* zone_carry;    // per strand and tile of kZoneTile boundaries: the maximum of all boundaries before the tile
+    long long zone_tiles;
+    unsigned* spill;
+    unsigned long long* n_spill;
     int protocol;
     int weight;
     int len_base;
@@ -2530,13 +2538,114 @@ constexpr int kStreamContigs = 256;     // contig table entries kept in shared m
 #define RT_STREAM_CTAS_PER_SM 3
 #endif
 
+// Zero the compact slots [z0, z1): 16-byte stores where the range is aligned, single slots at its two ends.
+__device__ __forceinline__ void stream_zero_zone(int32_t* cov, unsigned z0, unsigned z1, int lane) {
+    if (z1 <= z0) return;
+    const unsigned a0 = min((z0 + 3u) & ~3u, z1), a1 = max(z1 & ~3u, a0);     // [a0, a1) is whole int4s
+    if (z0 + (unsigned)lane < a0) cov[z0 + lane] = 0;
+    int4* v = reinterpret_cast<int4*>(cov);
+    for (unsigned i = (a0 >> 2) + lane; i < (a1 >> 2); i += 32) v[i] = make_int4(0, 0, 0, 0);
+    if (a1 + (unsigned)lane < z1) cov[a1 + lane] = 0;
+}
+
+// Lower-bound rank: compact index of the first member slot at or after bit `bit` of dense word `w` (after
+// fill_cmap_gaps an empty word carries the index its next member will get).
+__device__ __forceinline__ unsigned cmap_rank(const uint2* cmap, unsigned w, unsigned bit) {
+    const uint2 m = __ldg(cmap + w);
+    return m.y - (unsigned)__popc(m.x >> bit);
+}
+
+// Zone boundaries of a stream: boundary of block b on strand s = rank of the first position a read of the block can
+// put a P-site on (its header position + the smallest offset of the strand).  Blocks without a usable reference get the
+// strand's first slot and inherit their predecessor's boundary through the prefix maximum.
+struct ZoneArgs {
+    const int4* hdr;
+    long long n_blocks;
+    unsigned* bounds;              // 2 x (n_blocks + 1)
+    const uint2* cmap;
+    const int2* contig_tab;
+    int n_contig;
+    int pad;
+    unsigned plane_words;
+    int delta_plus, delta_minus;   // smallest P-site displacement from `first` on either strand
+    unsigned plus_end, minus_end;  // compact index after the last '+' / '-' slot
+};
+constexpr int kZoneTile = 256;      // boundaries per CTA of zone_bounds_kernel
+static_assert(kZoneTile == 256, "bin_stream_kernel finds the tile of a boundary with >> 8");
+// grid (tiles, 2 strands): raw boundaries clamped to the strand's range, then the prefix maximum inside the tile;
+// tile_max[s * tiles + t] = the tile's maximum.  zone_carry_kernel turns those into the carry of every tile, and
+// whoever reads boundary b takes max(bounds[b], tile_carry[tile of b]): monotone whatever the stream looks like.
+__global__ void __launch_bounds__(kZoneTile) zone_bounds_kernel(const ZoneArgs z, unsigned* tile_max) {
+    __shared__ unsigned s_w[kZoneTile / 32];
+    const int s = blockIdx.y;
+    const long long b = (long long)blockIdx.x * kZoneTile + threadIdx.x;
+    const unsigned lo = s ? z.plus_end : 0u, hi = s ? z.minus_end : z.plus_end;
+    unsigned r = lo;
+    if (b >= z.n_blocks) r = b == z.n_blocks ? hi : lo;
+    else if (b > 0) {
+        const int4 hd = __ldg(z.hdr + b);
+        if ((unsigned)hd.x < (unsigned)z.n_contig) {
+            const int2 ct = __ldg(z.contig_tab + hd.x);
+            long long q = (long long)hd.y + (s ? z.delta_minus : z.delta_plus) + z.pad + 1;    // in_contig of the first reachable P-site
+            q = q < 0 ? 0 : (q > (long long)ct.x + 2 * z.pad ? (long long)ct.x + 2 * z.pad : q);
+            const unsigned w = (s ? z.plane_words : 0u) + (unsigned)ct.y + (unsigned)(q >> 5);
+            r = min(max(cmap_rank(z.cmap, w, (unsigned)(q & 31)), lo), hi);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(kFull, r, o);
+        if (lane >= o) r = max(r, t);
+    }
+    if (lane == 31) s_w[warp] = r;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kZoneTile / 32 - 1; ++k)
+        if (k < warp) r = max(r, s_w[k]);
+    if (b <= z.n_blocks) z.bounds[(size_t)s * (size_t)(z.n_blocks + 1) + (size_t)b] = r;
+    if (threadIdx.x == kZoneTile - 1) tile_max[(size_t)s * gridDim.x + blockIdx.x] = r;
+}
+// One CTA per strand: exclusive prefix maximum over the tile maxima.
+__global__ void __launch_bounds__(1024) zone_carry_kernel(const unsigned* __restrict__ tile_max, unsigned* tile_carry, long long tiles,
+                                                          unsigned plus_end) {
+    __shared__ unsigned s_max[1024];
+    const unsigned* in = tile_max + (size_t)blockIdx.x * (size_t)tiles;
+    unsigned* out = tile_carry + (size_t)blockIdx.x * (size_t)tiles;
+    const unsigned lo = blockIdx.x ? plus_end : 0u;
+    const long long per = (tiles + 1023) / 1024;
+    const long long t0 = (long long)threadIdx.x * per, t1 = t0 + per < tiles ? t0 + per : tiles;
+    unsigned m = lo;
+    for (long long t = t0; t < t1; ++t) m = max(m, in[t]);
+    s_max[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned v = threadIdx.x >= o ? s_max[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_max[threadIdx.x] = max(s_max[threadIdx.x], v);
+        __syncthreads();
+    }
+    m = threadIdx.x ? s_max[threadIdx.x - 1] : lo;
+    for (long long t = t0; t < t1; ++t) {
+        out[t] = m;
+        m = max(m, in[t]);
+    }
+}
+// The P-sites that fell outside their block's zone, once every zone has been written.
+__global__ void __launch_bounds__(256) zone_spill_kernel(int32_t* cov, const unsigned* __restrict__ spill, const unsigned long long* n_spill) {
+    const unsigned long long n = *n_spill;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+        atomicAdd(cov + spill[i], 1);
+}
+
 // Persistent: RT_STREAM_CTAS_PER_SM CTAs per SM; every WARP walks blocks of the stream on its own (no CTA-wide barrier
 // after start-up, so the warps of an SM drift apart and cover each other's load latencies).  A warp owns a ring of two
 // shared-memory stages with one mbarrier each: an elected lane brings block i + 1 (1 KB of records and its header) in
 // with a cp.async.bulk pair while the warp works on block i.  The lookup tables are built once per CTA and the
 // per-thread 4-bit counters are drained into 8-bit ones every block.
-template <bool Compact>
+template <bool Compact, bool Zoned>
 __global__ void __launch_bounds__(kStreamThreads, RT_STREAM_CTAS_PER_SM) bin_stream_kernel(const StreamArgs a) {
+    static_assert(Compact || !Zoned, "zones are ranges of the compact buffer");
     __shared__ __align__(128) unsigned int s_rec[kStreamWarps][2][RT_STREAM_BLOCK];
     __shared__ __align__(16) int4 s_hdr[kStreamWarps][2];
     __shared__ __align__(8) uint64_t s_bar[kStreamWarps][2];
@@ -2638,6 +2747,20 @@ __global__ void __launch_bounds__(kStreamThreads, RT_STREAM_CTAS_PER_SM) bin_str
         if (lane == 0 && blk + stride < a.n_blocks) issue(blk + stride, st ^ 1u);
         mbar_wait(&s_bar[warp][st], (it >> 1) & 1u);
         const int4 hd = s_hdr[warp][st];
+        unsigned z0p = 0, z1p = 0, z0m = 0, z1m = 0;
+        if (Zoned) {
+            // this block's zone on both strands: zero it with plain stores (whole sectors are written, none is fetched)
+            unsigned zb = 0;
+            if (lane < 4) {
+                const long long zi = blk + (lane & 1);
+                zb = max(__ldg(a.zone_bounds + (size_t)(lane >> 1) * (size_t)(a.n_blocks + 1) + (size_t)zi),
+                         __ldg(a.zone_carry + (size_t)(lane >> 1) * (size_t)a.zone_tiles + (size_t)(zi >> 8)));
+            }
+            z0p = __shfl_sync(kFull, zb, 0); z1p = __shfl_sync(kFull, zb, 1);
+            z0m = __shfl_sync(kFull, zb, 2); z1m = __shfl_sync(kFull, zb, 3);
+            stream_zero_zone(a.cov, z0p, z1p, lane);
+            stream_zero_zone(a.cov, z0m, z1m, lane);
+        }
         unsigned w[kStreamStrip + 1];
         {
             const uint4* sp = reinterpret_cast<const uint4*>(s_rec[warp][st]) + 2 * lane;
@@ -2764,7 +2887,41 @@ __global__ void __launch_bounds__(kStreamThreads, RT_STREAM_CTAS_PER_SM) bin_str
         }
         slot_t slot[kStreamStrip];
         stream_slots<Compact, slot_t>(a, live, wd, bit, slot);
-        stream_scatter<slot_t>(a.cov, slot, a.weight);
+        if (Zoned) {
+            // the zones were zeroed at the top of the iteration: their lines are still in L2, so adding the block's
+            // own reads fetches nothing from DRAM.  P-sites beyond the zones (rare) wait in the spill list.
+            __syncwarp();
+            unsigned out[kStreamStrip];
+            unsigned n_out = 0;
+#pragma unroll
+            for (int j = 0; j < kStreamStrip; ++j) {
+                const unsigned sl = (unsigned)slot[j];
+                const bool mine = (sl - z0p < z1p - z0p) || (sl - z0m < z1m - z0m);
+                const bool spills = sl != 0xffffffffu && !mine;
+                out[j] = spills ? sl : 0xffffffffu;
+                if (spills) {
+                    ++n_out;
+                    slot[j] = (slot_t)-1;
+                }
+            }
+            stream_scatter<slot_t>(a.cov, slot, 1);
+            if (__any_sync(kFull, n_out != 0u)) {
+                unsigned incl_out = n_out;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(kFull, incl_out, o);
+                    if (lane >= o) incl_out += t;
+                }
+                unsigned long long base = 0;
+                if (lane == 31) base = atomicAdd(a.n_spill, (unsigned long long)incl_out);
+                base = __shfl_sync(kFull, base, 31) + incl_out - n_out;
+#pragma unroll
+                for (int j = 0; j < kStreamStrip; ++j)
+                    if (out[j] != 0xffffffffu) a.spill[base++] = out[j];
+            }
+        } else {
+            stream_scatter<slot_t>(a.cov, slot, a.weight);
+        }
         // drain the 4-bit counters (at most 8 each) into the 8-bit ones; those hold 31 blocks of the warp
         cat_e += packed & 0x0f0f0f0fu;
         cat_o += (packed >> 4) & 0x0f0f0f0fu;
@@ -2808,6 +2965,54 @@ __global__ void __launch_bounds__(256) build_cbits_kernel(const uint2* __restric
     const bool member = w < n_words && cmap[w].x != 0u;
     const unsigned bits = __ballot_sync(kFull, member);
     if ((threadIdx.x & 31) == 0 && w < n_words) cbits[w >> 5] = bits;
+}
+
+// Empty cmap words (no member slot) get the compact index of the next member in .y, so that cmap_rank() answers
+// "how many member slots lie before this position" for every position of the genome.  Tiles of kGapTile words:
+// tile_last = .y of the tile's last word with members (0 if none); the host turns that into a carry per tile.
+constexpr int kGapTile = 2048;
+__global__ void __launch_bounds__(256) cmap_tile_last_kernel(const uint2* __restrict__ cmap, long long n_words, unsigned* tile_last) {
+    __shared__ unsigned s_m[256];
+    const long long w0 = (long long)blockIdx.x * kGapTile + (long long)threadIdx.x * (kGapTile / 256);
+    unsigned m = 0;
+    for (int k = 0; k < kGapTile / 256; ++k)
+        if (w0 + k < n_words) {
+            const uint2 e = cmap[w0 + k];
+            if (e.x) m = e.y;          // .y grows along the genome: the last one seen is the largest
+        }
+    s_m[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_m[threadIdx.x] = max(s_m[threadIdx.x], s_m[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_last[blockIdx.x] = s_m[0];
+}
+__global__ void __launch_bounds__(256) cmap_fill_gaps_kernel(uint2* cmap, long long n_words, const unsigned* __restrict__ tile_carry) {
+    __shared__ unsigned s_m[256];
+    constexpr int kPer = kGapTile / 256;
+    const long long w0 = (long long)blockIdx.x * kGapTile + (long long)threadIdx.x * kPer;
+    uint2 e[kPer];
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        e[k] = w0 + k < n_words ? cmap[w0 + k] : make_uint2(0u, 0u);
+        if (e[k].x) m = e[k].y;
+    }
+    s_m[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const unsigned t = threadIdx.x >= o ? s_m[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_m[threadIdx.x] = max(s_m[threadIdx.x], t);
+        __syncthreads();
+    }
+    unsigned carry = max(tile_carry[blockIdx.x], threadIdx.x ? s_m[threadIdx.x - 1] : 0u);
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        if (e[k].x) carry = e[k].y;
+        else if (w0 + k < n_words) cmap[w0 + k].y = carry;
+    }
 }
 
 // Sparse clear: zero the 32-byte sectors (8 slots) K1 touched since the last clear.  Whole sectors

@@ -372,9 +372,17 @@ class Engine:
 
         return dict(records=dev(stream["records"]), hdr=dev(stream["hdr"]), n_blocks=int(stream["n_blocks"]), n=int(stream["n"]))
 
-    def bin_stream_device(self, cov, dstream: dict, protocol, stats, len_counts, weight: int = 1):
-        """Enqueue K1 on a device-resident record stream (4 B/read; no host sync)."""
+    def bin_stream_device(self, cov, dstream: dict, protocol, stats, len_counts, weight: int = 1, fresh: bool = False):
+        """Enqueue K1 on a device-resident record stream (4 B/read; no host sync).  ``fresh=True`` (compact layout):
+        the call overwrites the whole buffer zone by zone (``rt_bin_stream_fresh``), so ``cov`` need not be cleared."""
         p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        if fresh:
+            if weight != 1:
+                raise ValueError("fresh binning adds the library once (weight 1)")
+            self._check(self.lib.rt_bin_stream_fresh(
+                self.ctx, p(cov), int(dstream["n_blocks"]), p(dstream["records"]), p(dstream["hdr"]),
+                protocol_code(protocol), p(stats), p(len_counts), self._stream()))
+            return
         self._check(self.lib.rt_bin_stream(
             self.ctx, p(cov), int(dstream["n_blocks"]), p(dstream["records"]), p(dstream["hdr"]),
             protocol_code(protocol), int(weight), p(stats), p(len_counts), self._stream()))

@@ -853,6 +853,23 @@ def test_record_stream_matches_oracle_and_columns(engine, layout):
                 assert engine.torch.equal(got, 2 * want)
                 engine.bin_stream_device(got, dstream, protocol, st, lc, weight=-1)
                 assert engine.torch.equal(got, want) and int(st.abs().sum().item()) == 0 and int(lc.abs().sum().item()) == 0
+                if layout == "compact":      # rt_bin_stream_fresh: zones instead of a cleared buffer; any previous content goes
+                    fresh = engine.torch.full_like(want, 12345)
+                    st, lc = engine.new_bin_accumulators()
+                    engine.bin_stream_device(fresh, dstream, protocol, st, lc, fresh=True)
+                    assert engine.torch.equal(fresh, want)
+                    assert dict(zip(ref_stats.keys(), st.cpu().tolist())) == ref_stats and (lc.cpu().numpy() == ref_len).all()
+                    # the blocks of the stream in any order: the zone boundaries are made monotone, whatever then falls
+                    # outside its block's zone goes through the spill list -- the coverage is the same
+                    perm = np.random.default_rng(seed).permutation(stream["n_blocks"])
+                    rec = np.asarray(stream["records"]).reshape(-1, 256)[perm].reshape(-1)
+                    hdr = np.asarray(stream["hdr"]).reshape(-1, 4)[perm].reshape(-1)
+                    shuffled = engine.upload_stream(dict(records=rec, hdr=hdr, n_blocks=stream["n_blocks"], n=stream["n"]))
+                    fresh.fill_(-3)
+                    st, lc = engine.new_bin_accumulators()
+                    engine.bin_stream_device(fresh, shuffled, protocol, st, lc, fresh=True)
+                    assert engine.torch.equal(fresh, want)
+                    assert dict(zip(ref_stats.keys(), st.cpu().tolist())) == ref_stats
         empty = engine.stream_reads({k: v[:0] for k, v in reads.items()})
         stats_e, len_e = engine.bin_stream_host(engine.new_coverage(), empty, "forward")
         assert stats_e["total"] == 0 and not len_e.any()
