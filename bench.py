@@ -278,6 +278,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    if world > 1:     # the ranks of one box share its host cores: the coding pipelines of rt_bin_reads_host split them
+        os.environ.setdefault("RT_PACK_PIPES", str(max(2, (os.cpu_count() or 16) // world)))
 
     peaks = {}
     try:

@@ -31,7 +31,7 @@ txt = subprocess.run([py, os.path.join(HERE, "summarize.py"), rep], capture_outp
 open(os.path.join(HERE, f"{tag}_step_kernels.txt"), "w").write(txt)
 
 # 2. per-line profiles: (mangled symbol substring, ncu regex, file tag)
-KERNELS = [("bin_stream_kernelILb1E", "bin_stream", "bin_stream_kernel"),
+KERNELS = [("bin_stream_kernelILb1ELb1E", "bin_stream", "bin_stream_kernel"),
            ("atom_pass_kernelILi2ELb0E", "atom_pass", "atom_pass_kernel"),
            ("compose_refs_kernelILb0E", "compose_refs", "compose_refs_kernel")]
 for sym, rx, name in KERNELS:
@@ -72,7 +72,8 @@ for r in csv.reader(open(launches)):
         k = re.sub(r"^void |rt::|<.*|\(.*", "", r[4])
         grid = int(r[8].strip("()").split(",")[0])
         per.setdefault(k, []).append((grid, float(r[14]) / 1e6))
-STEP = ("bin_stream_kernel", "bin_psites_kernel", "atom_pass_kernel", "compose_refs_kernel", "score_orfs_kernel")
+STEP = ("zone_bounds_kernel", "zone_carry_kernel", "bin_stream_kernel", "zone_spill_kernel", "bin_psites_kernel", "atom_pass_kernel",
+        "compose_refs_kernel", "score_orfs_kernel")
 per = collections.OrderedDict((k, v) for k, v in per.items() if k in STEP)   # not the one-time set-up kernels
 for k in per:   # the e2e leg launches K1 in 1 M-read chunks: keep the whole-library launches only
     g = max(x[0] for x in per[k])
@@ -83,7 +84,7 @@ tot = sum(sum(v[:n]) / max(1, n) for v in per.values())
 for k, v in per.items():
     m = sum(v[:n]) / max(1, n)
     lines.append(f"{k:28s} {m:8.4f} ms  {100 * m / tot:5.1f} %   ({n} launches averaged, serialised, cold cache)")
-lines.append(f"{'sum':28s} {tot:8.4f} ms  (plus the cudaMemset of the compact buffer, which ncu does not list as a kernel)")
+lines.append(f"{'sum':28s} {tot:8.4f} ms  (the step of bench.py: rt_bin_stream_fresh + rt_score; no clear of the buffer)")
 open(os.path.join(HERE, f"{tag}_launch_shares.txt"), "w").write("\n".join(lines) + "\n")
 
 # 5. SASS
