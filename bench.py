@@ -68,7 +68,7 @@ def parse_args():
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, device_index: int, period_s: float = 0.01):
+    def __init__(self, device_index: int, period_s: float = 0.002):
         self.samples, self.reasons = [], set()
         self.max_mhz = None
         self.period = period_s
