@@ -406,6 +406,7 @@ def run_ours(args):
         res = eng.score_host(cov, 0, n_orf, params, out=hout)
     barrier()
     e0, e1 = ev(), ev()
+    h2d0 = eng.h2d_bytes
     e0.record()
     for _ in range(e2e_steps):
         eng.clear_touched(cov)
@@ -414,6 +415,7 @@ def run_ours(args):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    h2d_step = (eng.h2d_bytes - h2d0) // e2e_steps          # counted by the library from the copies it issued
     # second line: the library handed over as the record stream itself (what rt_stream_pack makes of a decoded BAM once,
     # e.g. for a library that is scored against several indexes): no host packing inside the call
     e2e_stream_ms = None
@@ -436,20 +438,22 @@ def run_ours(args):
     score_ms_local, bin_ms_local = score_ms, bin_ms       # the roofline is this rank's kernels over this rank's bytes
     stream_blocks = int(hstream["n_blocks"]) if hstream is not None else 0
     times = torch.tensor([total_ms, e2e_ms, score_ms, bin_ms, unbin_ms, e2e_stream_ms or 0.0], dtype=torch.float64, device=dev)
-    blocks_all = torch.tensor([stream_blocks], dtype=torch.int64, device=dev)
+    blocks_all = torch.tensor([stream_blocks, h2d_step], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(blocks_all, op=dist.ReduceOp.SUM)
     total_ms, e2e_ms, score_ms, bin_ms, unbin_ms, e2e_stream_ms = times.tolist()
-    stream_bytes = int(blocks_all.item()) * (256 * 4 + 16)
+    stream_bytes = int(blocks_all[0].item()) * (256 * 4 + 16)
+    h2d_total = int(blocks_all[1].item())
     ms_per_step = total_ms / args.steps
     value = n_orf_total / (ms_per_step * 1e-3)          # the whole index, in the time of the slowest rank
     e2e_value = n_orf_total / (e2e_ms * 1e-3)
 
     if rank == 0:
         achieved = score_bytes / (score_ms_local * 1e-3) / 1e9
-        # all ranks together: the record stream when the library codes (4 B/read + block padding), else 18 B/read columns
-        h2d = stream_bytes if stream_bytes else sum(18 * c[1] for c in per_rank)
+        # all ranks together, as counted by the library: 4 B/read for the chunks that crossed as a record stream, 18 B/read
+        # for those the plain pipeline shipped
+        h2d = h2d_total
         d2h = world * 8 * (9 + 65536) + sum(25 * c[0] for c in per_rank)
         # dram__bytes_read.sum + dram__bytes_write.sum of the scoring kernel from the committed ncu capture
         traffic, traffic_src, bin_traffic = None, None, None

@@ -380,6 +380,9 @@ int rt_bam_pack(const rt_bam* b, uint8_t* meta, int64_t run_cap, int64_t* run_st
 
 /* number of kernel launches issued through this ctx so far (bench.py's gpu_launches) */
 int64_t rt_launch_count(const rt_ctx* ctx);
+/* bytes of read data the host-buffer entry points (rt_bin_reads_host, rt_bin_stream_host, rt_bin_reads_packed_host) have
+ * copied to the device through this ctx so far (bench.py's e2e.h2d_bytes_per_step) */
+int64_t rt_h2d_bytes(const rt_ctx* ctx);
 
 #ifdef __cplusplus
 }

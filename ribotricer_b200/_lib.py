@@ -25,7 +25,7 @@ EXPORTS = (
     "rt_set_genome", "rt_plane_elems", "rt_get_contig_base", "rt_set_length_table",
     "rt_bin_reads", "rt_bin_reads_host", "rt_pack_read_meta", "rt_bin_reads_packed", "rt_bin_reads_packed_host", "rt_stream_pack", "rt_bin_stream", "rt_bin_stream_host", "rt_bin_stream_fresh", "rt_clear_coverage", "rt_set_layout", "rt_coverage_elems", "rt_track_touched", "rt_clear_touched", "rt_set_index", "rt_index_orfs",
     "rt_index_score_bytes", "rt_index_total_nt", "rt_shard_bounds", "rt_score", "rt_score_host",
-    "rt_gather_profiles", "rt_compact_from_dense", "rt_wig_tiles", "rt_wig_count", "rt_wig_fill", "rt_interval_sums", "rt_bootstrap_medians", "rt_launch_count", "rt_phasescore_values", "rt_io_last_error", "rt_index_load",
+    "rt_gather_profiles", "rt_compact_from_dense", "rt_wig_tiles", "rt_wig_count", "rt_wig_fill", "rt_interval_sums", "rt_bootstrap_medians", "rt_launch_count", "rt_h2d_bytes", "rt_phasescore_values", "rt_io_last_error", "rt_index_load",
     "rt_index_free", "rt_index_n_orf", "rt_index_n_exon", "rt_index_n_annotated_prefix", "rt_index_n_chrom",
     "rt_index_chrom_name", "rt_index_copy", "rt_index_field", "rt_tsv_open", "rt_tsv_write", "rt_tsv_close",
     "rt_repr_double", "rt_wig_open", "rt_wig_block", "rt_wig_close", "rt_bam_last_error", "rt_bam_load", "rt_bam_free", "rt_bam_n_reads", "rt_bam_n_ref",
@@ -145,6 +145,8 @@ def load():
     lib.rt_bam_copy_span.argtypes = [vp, vp, vp]
     lib.rt_bam_pack.argtypes = [vp, vp, i64, vp, vp, C.POINTER(i64)]
     lib.rt_launch_count.restype = i64
+    lib.rt_h2d_bytes.argtypes = [vp]
+    lib.rt_h2d_bytes.restype = i64
     if lib.rt_abi_version() != 3:
         raise RtError(f"ABI mismatch: library reports {lib.rt_abi_version()}, binding expects 3")
     _lib = lib

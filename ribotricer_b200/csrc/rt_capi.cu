@@ -52,6 +52,7 @@ struct rt_ctx {
     int n_sm = 0;
     std::string err;
     int64_t launches = 0;
+    std::atomic<int64_t> h2d_bytes{0};               // copied to the device by the host-buffer entry points so far
 
     // genome
     int n_contig = 0;
@@ -438,6 +439,7 @@ void rt_destroy(rt_ctx* ctx) {
 }
 
 int64_t rt_launch_count(const rt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t rt_h2d_bytes(const rt_ctx* ctx) { return ctx ? ctx->h2d_bytes.load() : 0; }
 
 // ------------------------------------------------------------------------------------ genome
 int rt_set_genome(rt_ctx* ctx, int n_contig, const int64_t* h_contig_len, int pad) {
@@ -807,6 +809,7 @@ int rt_bin_stream_host(rt_ctx* ctx, int32_t* d_cov, int64_t n_blocks, const uint
         cudaStream_t st = ctx->slot_stream[slot];   // stream order protects the slot's previous use
         RT_CUDA(ctx, cudaMemcpyAsync(d_rec, h_records + at * RT_STREAM_BLOCK, sizeof(uint32_t) * RT_STREAM_BLOCK * (size_t)m, cudaMemcpyHostToDevice, st));
         RT_CUDA(ctx, cudaMemcpyAsync(d_hdr, h_hdr + 4 * at, sizeof(int32_t) * 4 * (size_t)m, cudaMemcpyHostToDevice, st));
+        ctx->h2d_bytes += (int64_t)m * (RT_STREAM_BLOCK * 4 + 16);
         int rc = rt_bin_stream(ctx, d_cov, m, d_rec, d_hdr, protocol, 1, d_stats, d_len_counts, st);
         if (rc != RT_OK) return rc;
     }
@@ -919,6 +922,7 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
                     !check(cudaEventRecord(hs.copied, st), "cudaEventRecord"))
                     break;
                 hs.busy = true;
+                ctx->h2d_bytes += (int64_t)blocks * (RT_STREAM_BLOCK * 4 + 16);
                 std::lock_guard<std::mutex> lock(ctx->launch_mutex);
                 rc = rt_bin_stream(ctx, d_cov, blocks, d_rec, d_hdr, protocol, 1, d_stats, d_len_counts, st);
             } else {
@@ -930,6 +934,7 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
                     !check(cudaMemcpyAsync(d_mapq, h_mapq + at, m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync") ||
                     !check(cudaMemcpyAsync(d_nh, h_nh + at, m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync"))
                     break;
+                ctx->h2d_bytes += (int64_t)m * (int64_t)kReadBytes;
                 std::lock_guard<std::mutex> lock(ctx->launch_mutex);
                 rc = rt_bin_reads(ctx, d_cov, m, d_ref, d_first, d_last, d_mlen, d_flag, d_mapq, d_nh, protocol, 0, 1,
                                   d_stats, d_len_counts, st);
@@ -1008,6 +1013,7 @@ int rt_bin_reads_packed_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32
         RT_CUDA(ctx, cudaMemcpyAsync(d_last, h_last + at, 4 * m, cudaMemcpyHostToDevice, st));
         RT_CUDA(ctx, cudaMemcpyAsync(d_mlen, h_mlen + at, 2 * m, cudaMemcpyHostToDevice, st));
         RT_CUDA(ctx, cudaMemcpyAsync(d_meta, h_meta + at, m, cudaMemcpyHostToDevice, st));
+        ctx->h2d_bytes += (int64_t)m * (int64_t)kPackedReadBytes;
         int rc = rt_bin_reads_packed(ctx, d_cov, m, d_first, d_last, d_mlen, d_meta, at, n_runs, d_run_start, d_run_ref,
                                      protocol, 1, d_stats, d_len_counts, st);
         if (rc != RT_OK) return rc;

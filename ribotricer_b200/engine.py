@@ -111,6 +111,11 @@ class Engine:
     def launches(self) -> int:
         return int(self.lib.rt_launch_count(self.ctx))
 
+    @property
+    def h2d_bytes(self) -> int:
+        """Bytes of read data the host-buffer entry points have copied to the device so far."""
+        return int(self.lib.rt_h2d_bytes(self.ctx))
+
     # --------------------------------------------------------------- genome
     def set_genome(self, contig_names, contig_len, pad: int = DEFAULT_PAD):
         self.contig_names = [str(c) for c in contig_names]
