@@ -705,6 +705,7 @@ static int launch_stream(rt_ctx* ctx, const char* who, bool fresh, int32_t* d_co
     if (ctx->track_touched && ctx->layout != RT_LAYOUT_COMPACT)
         return fail(ctx, RT_ESTATE, "%s: the touched-slot list of the dense layout is kept by rt_bin_reads only", who);
     if (fresh && ctx->layout != RT_LAYOUT_COMPACT) return fail(ctx, RT_ESTATE, "%s: needs the compact layout (rt_set_layout)", who);
+    if (fresh && (reinterpret_cast<uintptr_t>(d_cov) & 15)) return fail(ctx, RT_EINVAL, "%s: d_cov must be 16-byte aligned", who);
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (n_blocks == 0) {

@@ -397,7 +397,14 @@ def test_full_config3_against_oracle(engine):
     assert int(got["count"].sum()) >= int(cov.sum(dtype=t.int64).item())         # ORFs overlap: every count is seen at least once
     n_cmp = _oracle_on_subgenome(engine, idx, dreads, range(12, 25), got, "C3 chr13-chrM: ")
     assert n_cmp >= 3_000_000
-    del cov
+    # the library as a record stream (2 M blocks), binned zone by zone over a buffer full of garbage: the same coverage
+    dstream = engine.upload_stream(engine.stream_reads({k: v.cpu() for k, v in dreads.items()}))
+    assert dstream["n"] == cfg.n_reads
+    fresh = t.full_like(cov, -1)
+    st2, lc2 = engine.new_bin_accumulators()
+    engine.bin_stream_device(fresh, dstream, "forward", st2, lc2, fresh=True)
+    assert t.equal(fresh, cov) and t.equal(st2, st) and t.equal(lc2, lc)
+    del cov, fresh, dstream
     # two genomic blocks, each from its own slice of the reads
     plan = multi_gpu.shard_plan(idx.exon_ptr, idx.exon_start, idx.exon_end, idx.orf_contig, 2)
     reach = max(synth.TRUE_OFFSETS.values()) + int((dreads["last"].long() - dreads["first"].long()).max().item())
