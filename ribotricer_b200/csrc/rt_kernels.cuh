@@ -1,8 +1,14 @@
 // rt_kernels.cuh -- sm_100a kernels of the detect-orfs scoring path.
 //
-//   K1 bin_psites_kernel      bam.py:71-137 + detect_orfs.py:54-83
-//   K3 score_orfs_kernel      detect_orfs.py:134-203,274-299 + statistics.py:48-115
-//                             + common.py:164-180 (gather fused in: K2)
+//   K1 bin_stream_kernel      bam.py:71-137 + detect_orfs.py:54-83 on the 4 B/read record stream of a coordinate-sorted
+//                             library (persistent, per-warp cp.async.bulk rings; <Zoned>: every block writes its zone
+//                             of the compact buffer before it adds into it), with zone_bounds / zone_carry / zone_spill
+//      bin_psites_kernel      the same loop on the decoder's columns (any read order, dense planes with the sparse clear)
+//   K2+K3 atom_pass_kernel    detect_orfs.py:134-203 + statistics.py:48-115 per atom of the exon union, streamed by
+//                             cp.async.bulk (compact layout); atom_summary_kernel for the dense planes
+//      compose_refs_kernel    per-ORF columns from the atom summaries (families of nested ORFs, suffix scan),
+//                             detect_orfs.py:274-299 + common.py:164-180; score_from_atoms_kernel (A/B)
+//      score_orfs_kernel      the whole per-ORF loop in one kernel: fallback for counts >= 2^20, A/B (RT_SCORE_PATH=scan)
 //   K4 gather_profiles_kernel detect_orfs.py:134-203 for the reported ORFs (:322)
 //
 // All "file:line" citations are relative to the reference tree.
