@@ -36,6 +36,13 @@ METRIC = "candidate ORFs scored/sec (P-site binning + gather + phase score + fil
 UNIT = "ORFs/s"
 
 
+def workload_text(name: str, n_orf: int, n_reads: int) -> str:
+    """The same words in both arms (ours and --impl reference): the driver compares the configs."""
+    return (f"{name}: synthetic human GENCODE-scale detect-orfs, ONE index of {n_orf} candidate ORFs and ONE library of "
+            f"{n_reads} reads (coordinate-sorted, lengths 26-32), default thresholds (cutoff 0.428571428571, "
+            f"min_valid_codons 5, the other filters at their 0 defaults)")
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -252,8 +259,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.config}: synthetic human GENCODE-scale detect-orfs "
-                               f"({full.n_orf} candidate ORFs, {full.n_reads} reads); bounded sample per step"},
+        "config": {"workload": workload_text(args.config, full.n_orf, full.n_reads), "orfs": full.n_orf, "reads": full.n_reads,
+                   "sample": "bounded sample of this workload per step, see cpu_baseline.sample"},
         "cpu_baseline": dict(desc, value=value, unit=UNIT),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -477,9 +484,7 @@ def run_ours(args):
             "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"{args.config}: synthetic human GENCODE-scale detect-orfs, ONE index of {n_orf_total} candidate "
-                            f"ORFs and ONE library of {n_reads_total} reads (coordinate-sorted, lengths 26-32), default "
-                            f"thresholds (cutoff 0.428571428571, min_valid_codons 5, the other filters at their 0 defaults)",
+                "workload": workload_text(args.config, n_orf_total, n_reads_total),
                 "orfs": n_orf_total, "reads": n_reads_total, "index_order": args.index_order,
                 "sharding": f"{world} byte-balanced block(s) of the index along the genome; a rank bins the slice of the "
                             f"sorted library that can reach its block; no replication, no collective",
