@@ -377,6 +377,9 @@ int rt_bam_copy_span(const rt_bam* b, int32_t* pos, int32_t* ref_end);
 /* the decoded reads as packed records (rt_pack_read_meta on the decoder's own columns): meta[n_reads] and the
  * run table; first / last / mlen come from rt_bam_copy */
 int rt_bam_pack(const rt_bam* b, uint8_t* meta, int64_t run_cap, int64_t* run_start, int32_t* run_ref, int64_t* n_runs);
+/* the decoded reads as a record stream (rt_stream_pack on the decoder's own columns; same arguments, same two-call
+ * pattern: records == NULL counts the blocks).  RT_ESTATE when the BAM is not coordinate-sorted after all */
+int rt_bam_stream(const rt_bam* b, int n_threads, int64_t cap_blocks, uint32_t* records, int32_t* hdr, int64_t* n_blocks);
 
 /* number of kernel launches issued through this ctx so far (bench.py's gpu_launches) */
 int64_t rt_launch_count(const rt_ctx* ctx);

@@ -332,4 +332,10 @@ int rt_bam_pack(const rt_bam* b, uint8_t* meta, int64_t run_cap, int64_t* run_st
                              meta, run_cap, run_start, run_ref, n_runs);
 }
 
+int rt_bam_stream(const rt_bam* b, int n_threads, int64_t cap_blocks, uint32_t* records, int32_t* hdr, int64_t* n_blocks) {
+    if (!b) return RT_EINVAL;
+    return rt_stream_pack((int64_t)b->ref_id.size(), b->ref_id.data(), b->first.data(), b->last.data(), b->mlen.data(), b->flag.data(),
+                          b->mapq.data(), b->nh.data(), n_threads, cap_blocks, records, hdr, n_blocks);
+}
+
 }  // extern "C"

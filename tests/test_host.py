@@ -404,3 +404,46 @@ def _lib_block():
     from ribotricer_b200 import _lib
 
     return _lib.RT_STREAM_BLOCK
+
+
+def test_bam_stream_matches_the_decoder_columns(tmp_path, built):
+    """rt_bam_stream (the decoder hands over the 4 B/read record stream) == rt_stream_pack on the decoder's columns, and
+    the stream decodes back to those columns (a coordinate-sorted golden BAM with spliced reads, reads without CIGAR,
+    unmapped reads that carry coordinates)."""
+    import base64
+    import ctypes as C
+
+    from helpers import decode_stream, load_golden
+    from ribotricer_b200 import _lib
+    from ribotricer_b200.bam import read_bam_columns_native
+
+    case = load_golden("split_bam_case.json.gz")["case"]
+    path = tmp_path / "g.bam"
+    path.write_bytes(base64.b64decode(case["bam_b64"]))
+    rc = read_bam_columns_native(str(path), 2)
+    lib = _lib.load()
+    vp = C.c_void_p
+    p = lambda a: a.ctypes.data_as(vp)      # noqa: E731
+    code, rec, hdr, nb = _stream_pack(lib, rc.cols, n_threads=2)
+    handle = vp()
+    assert lib.rt_bam_load(str(path).encode(), 2, C.byref(handle)) == 0
+    try:
+        nb2 = C.c_int64(0)
+        code2 = lib.rt_bam_stream(handle, 2, 0, None, None, C.byref(nb2))
+        assert code2 == code
+        if code != 0:
+            assert not rc.sorted_by_coordinate or code == _lib_estate()
+            return
+        rec2 = np.zeros(max(1, nb2.value) * _lib_block(), np.uint32)
+        hdr2 = np.zeros(max(1, nb2.value) * 4, np.int32)
+        assert lib.rt_bam_stream(handle, 2, nb2.value, p(rec2), p(hdr2), C.byref(nb2)) == 0
+    finally:
+        lib.rt_bam_free(handle)
+    assert nb2.value == nb and (rec2 == rec).all() and (hdr2 == hdr).all()
+    got = decode_stream(rec, hdr, nb)
+    assert len(got) == len(rc)
+    for i, (ref, first, last, mlen, meta) in enumerate(got):
+        if int(rc.cols["flag"][i]) & 0x704:
+            continue
+        assert (ref, first, last, mlen) == (int(rc.cols["ref_id"][i]), int(rc.cols["first"][i]), int(rc.cols["last"][i]),
+                                            int(rc.cols["mlen"][i])), i
