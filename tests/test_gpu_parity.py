@@ -887,3 +887,45 @@ def test_record_stream_matches_oracle_and_columns(engine, layout):
         assert stats_n == ref_stats and int(none.abs().max().item()) == 0
     finally:
         engine.set_layout("dense")
+
+
+def test_zone_binning_soak(engine):
+    """rt_bin_stream_fresh against rt_bin_stream into a cleared buffer (fixed seed): random length tables (negative
+    offsets, unused and filtered lengths: the zone boundaries move with the smallest displacement), both protocols,
+    piles of reads on few positions (empty zones, long spill lists), sparse and dense libraries, spliced and long reads."""
+    from ribotricer_b200 import synth
+
+    cfg = synth.config("tiny")
+    idx = synth.make_index(cfg)
+    _setup(engine, idx.contig_names, idx.contig_len, idx.as_dict(), synth.TRUE_OFFSETS, None, pad=64)
+    engine.set_layout("compact")
+    t = engine.torch
+    rng = np.random.default_rng(11)
+    binned = 0
+    try:
+        for trial in range(24):
+            n = int(rng.choice([300, 5_000, 80_000, 300_000]))
+            if trial % 2:
+                reads = _stream_library(idx, n, trial)
+            else:
+                reads = synth.reads_to_numpy(synth.make_reads(cfg, idx, n_reads=n, seed_offset=trial))
+                if trial % 4 == 0:
+                    keep = np.sort(rng.choice(len(reads["first"]), size=max(50, n // 50), replace=False))
+                    reads = {k: np.repeat(v[keep], 50)[:n] for k, v in reads.items()}
+            lengths = rng.choice(np.arange(24, 36), size=int(rng.integers(2, 10)), replace=False)
+            offs = {int(length): int(rng.integers(-40, 60)) for length in lengths}
+            rl = None if trial % 3 else [int(x) for x in rng.choice(np.arange(24, 36), size=8, replace=False)]
+            engine.set_length_table(offs, rl)
+            stream = engine.upload_stream(engine.stream_reads(reads))
+            for protocol in ("forward", "reverse"):
+                want = engine.new_coverage()
+                st, lc = engine.new_bin_accumulators()
+                engine.bin_stream_device(want, stream, protocol, st, lc)
+                got = t.full_like(want, 99)
+                st2, lc2 = engine.new_bin_accumulators()
+                engine.bin_stream_device(got, stream, protocol, st2, lc2, fresh=True)
+                assert t.equal(got, want) and t.equal(st, st2) and t.equal(lc, lc2), (trial, protocol, offs, rl)
+                binned += int(want.sum().item())
+        assert binned > 100_000
+    finally:
+        engine.set_layout("dense")
