@@ -16,6 +16,10 @@
 #include <unordered_map>
 #include <vector>
 
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
 #include "ribotricer_b200.h"
 
 struct rt_index {
@@ -527,6 +531,7 @@ bool rt_stream_group_code(const int32_t* __restrict__ ref_id, const int32_t* __r
                           const uint8_t* __restrict__ nh, int32_t cur_ref, int64_t cur_pos, uint32_t* __restrict__ out) {
     const int64_t d0 = (int64_t)first[0] - cur_pos;
     uint32_t delta[kStreamGroup];
+    alignas(16) uint32_t rec[kStreamGroup];
     delta[0] = (uint32_t)d0;
     for (int k = 1; k < kStreamGroup; ++k) delta[k] = (uint32_t)first[k] - (uint32_t)first[k - 1];
     uint32_t bad = (d0 < 0) | (d0 > 32767);
@@ -535,8 +540,18 @@ bool rt_stream_group_code(const int32_t* __restrict__ ref_id, const int32_t* __r
         const uint32_t state = nn == 0u ? (uint32_t)(qq == 255u) : 3u - (uint32_t)(nn == 1u);
         const uint32_t meta = ((f >> 2) & 1u) | ((f >> 7) & 0xeu) | (f & 0x10u) | (state << 5);
         bad |= (uint32_t)(delta[k] > 32767u) | (uint32_t)(ref_id[k] ^ cur_ref) | (uint32_t)(l > 255u) | (uint32_t)(last[k] - first[k] + 1 - (int32_t)l);
-        out[k] = delta[k] | (l << 16) | (meta << 24);
+        rec[k] = delta[k] | (l << 16) | (meta << 24);
     }
+#if defined(__x86_64__)
+    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        // the staging buffer is written once and read by the copy engine: streaming stores keep it out of the caches
+        // and spare the read-for-ownership of every line (rt_stream_pack_range fences before it returns)
+        for (int k = 0; k < kStreamGroup; k += 4)
+            _mm_stream_si128(reinterpret_cast<__m128i*>(out + k), _mm_load_si128(reinterpret_cast<const __m128i*>(rec + k)));
+        return bad == 0;
+    }
+#endif
+    memcpy(out, rec, sizeof rec);
     return bad == 0;
 }
 
@@ -623,6 +638,9 @@ int64_t rt_stream_pack_range(const int32_t* __restrict__ ref_id, const int32_t* 
         }
     }
     w.close();
+#if defined(__x86_64__)
+    _mm_sfence();       // the streaming stores of rt_stream_group_code, before anyone is told the records are there
+#endif
     return w.nb;
 }
 
