@@ -585,9 +585,11 @@ int64_t rt_stream_pack_range(const int32_t* __restrict__ ref_id, const int32_t* 
             __builtin_prefetch(nh + a, 0, 2);
         }
         if (i + kStreamGroup <= m && w.fill == RT_STREAM_BLOCK) {     // start the next block here: the group may well be plain
-            if (!w.open(ref_id[i], first[i])) return -2;
-            cur_ref = ref_id[i];
-            cur_pos = first[i];
+            if (!(flag[i] & 0x704u)) {      // (a read the flags decide may carry any position: it must not become the block's)
+                cur_ref = ref_id[i];
+                cur_pos = first[i];
+            }
+            if (!w.open(cur_ref, (int32_t)cur_pos)) return -2;
         }
         if (i + kStreamGroup <= m && w.fill + kStreamGroup <= RT_STREAM_BLOCK &&
             (rec ? rt_stream_group_code(ref_id + i, first + i, last + i, mlen + i, flag + i, mapq + i, nh + i, cur_ref, cur_pos,

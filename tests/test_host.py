@@ -447,3 +447,29 @@ def test_bam_stream_matches_the_decoder_columns(tmp_path, built):
             continue
         assert (ref, first, last, mlen) == (int(rc.cols["ref_id"][i]), int(rc.cols["first"][i]), int(rc.cols["last"][i]),
                                             int(rc.cols["mlen"][i])), i
+
+
+def test_stream_pack_ignores_positions_of_flag_decided_reads(built):
+    """A read the flags decide (unmapped, secondary, qcfail, duplicate) may carry any position, also as the first read of
+    a block or of the library: the library still codes, and the other reads keep their coordinates."""
+    from helpers import decode_stream
+    from ribotricer_b200 import _lib
+
+    lib = _lib.load()
+    n = 4 * _lib_block() + 17
+    cols = dict(ref_id=np.zeros(n, np.int32), first=(np.arange(n) * 3).astype(np.int32), last=None,
+                mlen=np.full(n, 28, np.uint16), flag=np.zeros(n, np.uint16), mapq=np.full(n, 255, np.uint8),
+                nh=np.ones(n, np.uint8))
+    for k, i in enumerate((0, _lib_block(), 2 * _lib_block() - 1, 3 * _lib_block(), n - 1)):      # block starts and ends among them
+        cols["flag"][i] = 4                                     # e.g. an unmapped mate: same reference, any position
+        cols["first"][i] = 2 ** 31 - 1 if k % 2 else -1
+    cols["last"] = (cols["first"].astype(np.int64) + 27).clip(-2 ** 31, 2 ** 31 - 1).astype(np.int32)
+    rc, rec, hdr, nb = _stream_pack(lib, cols, n_threads=2)
+    assert rc == 0
+    got = decode_stream(rec, hdr, nb)
+    assert len(got) == n
+    for i, (ref, first, last, mlen, meta) in enumerate(got):
+        if cols["flag"][i] & 4:
+            assert meta & 1
+        else:
+            assert (ref, first, last, mlen) == (0, int(cols["first"][i]), int(cols["last"][i]), 28), i
