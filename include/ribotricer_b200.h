@@ -184,9 +184,10 @@ int rt_bin_reads_packed_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32
  *              (gaps above 32767 nt; RT_STREAM_NULL = skip 0 pads the last block of a range).
  * Reads whose category the flags decide (unmapped, secondary, qcfail, duplicate) carry delta 0 and mlen 0: the
  * reference never looks at their position.  rt_stream_pack builds the stream from the decoder's columns with
- * `n_threads` host threads (<= 0: all cores), every RT_STREAM_RANGE reads starting a fresh block; it returns
- * RT_ESTATE when the library cannot be coded (first positions not ascending within a reference, or a read spanning
- * 2^22 nt more than it matches) -- use rt_bin_reads / rt_bin_reads_host then.  With h_records == NULL it only
+ * `n_threads` host threads (<= 0: all cores), every RT_STREAM_RANGE reads starting a fresh block.  A read that
+ * starts before its predecessor (a CIGAR that opens with D or N) starts a block of its own; the call returns
+ * RT_ESTATE when the stream would be more than half padding (the library is not coordinate-sorted) or when a read
+ * spans 2^22 nt more than it matches -- use rt_bin_reads / rt_bin_reads_host then.  With h_records == NULL it only
  * counts: *n_blocks = the capacity the real call needs.
  */
 #define RT_STREAM_BLOCK 256

@@ -556,8 +556,8 @@ bool rt_stream_group_code(const int32_t* __restrict__ ref_id, const int32_t* __r
 }
 
 // Reads [0, m) of the decoder's columns as one run of stream blocks.  Returns the number of blocks, -1 when the
-// reads cannot be coded (positions descend inside a reference, or a span beyond the extension's 22 bits), -2 when
-// `cap` blocks are not enough.  rec == NULL counts only.
+// reads cannot be coded (a span beyond the extension's 22 bits), -2 when `cap` blocks are not enough.  rec == NULL
+// counts only.  Positions that descend inside a reference cost a block each.
 int64_t rt_stream_pack_range(const int32_t* __restrict__ ref_id, const int32_t* __restrict__ first, const int32_t* __restrict__ last,
                              const uint16_t* __restrict__ mlen, const uint16_t* __restrict__ flag, const uint8_t* __restrict__ mapq,
                              const uint8_t* __restrict__ nh, int64_t m, uint32_t* rec, int32_t* hdr, int64_t cap) {
@@ -620,11 +620,10 @@ int64_t rt_stream_pack_range(const int32_t* __restrict__ ref_id, const int32_t* 
             int64_t d = at - cur_pos;
             const unsigned ext = (l > 255u) | (extra != 0);
             if (extra < 0 || extra >= (1 << 22)) return -1;
-            bool fresh = w.fill == RT_STREAM_BLOCK || rid != cur_ref || d >= (1ll << 30);
-            if (!fresh) {
-                if (d < 0) return -1;
-                fresh = w.fill + 1 + (int)(d > 32767) + (int)ext > RT_STREAM_BLOCK;
-            }
+            // a read that starts before its predecessor (a CIGAR that opens with D or N, or a library that is not sorted
+            // after all) starts a block of its own; the callers give up when that happens too often
+            bool fresh = w.fill == RT_STREAM_BLOCK || rid != cur_ref || d >= (1ll << 30) || d < 0;
+            if (!fresh) fresh = w.fill + 1 + (int)(d > 32767) + (int)ext > RT_STREAM_BLOCK;
             if (fresh) {
                 if (!w.open(rid, (int32_t)at)) return -2;
                 cur_ref = rid;
@@ -685,11 +684,17 @@ int rt_stream_pack(int64_t n, const int32_t* ref_id, const int32_t* first, const
         return worst.load();
     };
     if (sweep(false) < 0) {
-        g_io_error = "rt_stream_pack: the library cannot be delta-coded (first positions descend inside a reference, or a read "
-                     "spans 2^22 nt more than it matches); use the column entry points";
+        g_io_error = "rt_stream_pack: the library cannot be delta-coded (a read spans 2^22 nt more than it matches); use the column "
+                     "entry points";
         return RT_ESTATE;
     }
     for (int64_t r = 0; r < n_ranges; ++r) blocks[r + 1] += blocks[r];     // counts -> exclusive offsets
+    // every descent of the positions costs a block: a library that is not coordinate-sorted would be mostly padding
+    if (blocks[n_ranges] * RT_STREAM_BLOCK > 2 * n + 4 * RT_STREAM_BLOCK * n_ranges) {
+        g_io_error = "rt_stream_pack: the stream would be more than half padding (the library is not coordinate-sorted); use the "
+                     "column entry points";
+        return RT_ESTATE;
+    }
     *n_blocks = blocks[n_ranges];
     if (!records) return RT_OK;
     if (cap_blocks < blocks[n_ranges]) {

@@ -381,13 +381,20 @@ def test_stream_pack_round_trip(built):
     # one thread or many: the same stream
     rc1, rec1, hdr1, nb1 = _stream_pack(lib, cols, n_threads=1)
     assert rc1 == 0 and nb1 == nb and (rec1 == rec).all() and (hdr1 == hdr).all()
-    # a library that is not sorted is refused (the caller falls back to the columns), so is a span beyond 22 bits
+    # one read that starts before its predecessor (a CIGAR that opens with D or N) costs a block, not the stream ...
     bad = {k: v.copy() for k, v in cols.items()}
     clean = np.flatnonzero((bad["flag"] & 0x704) == 0)
     i, j = clean[100], clean[101]
     bad["first"][j] = bad["first"][i] - 1
+    bad["last"][j] = bad["first"][j] + int(bad["mlen"][j]) - 1
     bad["ref_id"][j] = bad["ref_id"][i]
-    assert _stream_pack(lib, bad)[0] == _lib_estate()
+    rcb, recb, hdrb, nbb = _stream_pack(lib, bad)
+    assert rcb == 0 and nb <= nbb <= nb + 2
+    back = decode_stream(recb, hdrb, nbb)
+    assert back[j][:4] == (int(bad["ref_id"][j]), int(bad["first"][j]), int(bad["last"][j]), int(bad["mlen"][j]))
+    # ... a library that is not sorted at all is refused (the caller falls back to the columns), so is a span beyond 22 bits
+    order = np.random.default_rng(1).permutation(n)
+    assert _stream_pack(lib, {k: v[order] for k, v in cols.items()})[0] == _lib_estate()
     wide = {k: v.copy() for k, v in cols.items()}
     wide["last"][clean[7]] = wide["first"][clean[7]] + int(wide["mlen"][clean[7]]) - 1 + (1 << 22)
     assert _stream_pack(lib, wide)[0] == _lib_estate()
