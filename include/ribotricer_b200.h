@@ -268,7 +268,8 @@ int rt_shard_bounds(const rt_ctx* ctx, int n_shards, int64_t* h_bounds);
  */
 int rt_score(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi,
              const rt_score_params* params, const rt_score_out* d_out, void* stream);
-/* Same with HOST result columns (device scratch is owned by the ctx; D2H inside). */
+/* Same with HOST result columns (device scratch is owned by the ctx; D2H inside).  A range of a million ORFs or more is
+ * scored in four byte-balanced parts, the columns of one part crossing PCIe while the next is scored. */
 int rt_score_host(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf_hi,
                   const rt_score_params* params, const rt_score_out* h_out);
 

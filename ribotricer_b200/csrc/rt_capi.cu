@@ -74,6 +74,7 @@ struct rt_ctx {
     int32_t* d_orf_len = nullptr;
     cudaStream_t aux_stream = nullptr;               // long ORFs run beside the packed kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_scored = nullptr;                 // rt_score_host: a part's columns are ready for their copy
     uint64_t* d_exon_entries = nullptr;
     std::vector<int64_t> bytes_prefix;  // n_orf + 1: prefix of 4L + 8E + 42
     std::vector<int64_t> nt_prefix;     // n_orf + 1: prefix of L
@@ -412,6 +413,7 @@ void rt_destroy(rt_ctx* ctx) {
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_scored) cudaEventDestroy(ctx->ev_scored);
     for (auto& p : ctx->plans) {
         cudaFree(p.d_list);
         cudaFree(p.d_fallback);
@@ -1661,20 +1663,49 @@ int rt_score_host(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf
     d.min_codon = h_out->min_codon ? reinterpret_cast<int32_t*>(p) : nullptr; p += 4 * n;
     d.frame_K = h_out->frame_K ? reinterpret_cast<int32_t*>(p) : nullptr; p += 12 * n;
     d.status = reinterpret_cast<uint8_t*>(p);
-    int rc = rt_score(ctx, d_cov, orf_lo, orf_hi, params, &d, nullptr);
-    if (rc != RT_OK) return rc;
-    auto back = [&](void* h, const void* dv, size_t b) -> cudaError_t {
-        return h ? cudaMemcpyAsync(h, dv, b, cudaMemcpyDeviceToHost, nullptr) : cudaSuccess;
-    };
-    RT_CUDA(ctx, back(h_out->score, d.score, 8 * n));
-    RT_CUDA(ctx, back(h_out->count, d.count, 8 * n));
-    RT_CUDA(ctx, back(h_out->valid, d.valid, 4 * n));
-    RT_CUDA(ctx, back(h_out->length, d.length, 4 * n));
-    RT_CUDA(ctx, back(h_out->min_codon, d.min_codon, 4 * n));
-    RT_CUDA(ctx, back(h_out->status, d.status, n));
-    if (d.frame_K) RT_CUDA(ctx, back(h_out->frame_K, d.frame_K, 12 * n));
-    if (d.frame_s) RT_CUDA(ctx, back(h_out->frame_s, d.frame_s, 24 * n));
+    // A large range is scored in a few byte-balanced parts so that the result columns of part i cross PCIe (copy stream)
+    // while part i + 1 is being scored; every part has its own cached plan, the columns are the same (sums are exact).
+    int n_parts = n >= (1 << 20) ? 4 : 1;
+    if (const char* e = getenv("RT_SCORE_HOST_PARTS")) n_parts = std::max(1, std::min(16, atoi(e)));
+    n_parts = (int)std::min<int64_t>(n_parts, n);
+    std::vector<int64_t> cut((size_t)n_parts + 1, orf_lo);
+    cut[(size_t)n_parts] = orf_hi;
+    const int64_t* bp = ctx->bytes_prefix.data();
+    for (int i = 1; i < n_parts; ++i) {
+        const int64_t target = bp[orf_lo] + (bp[orf_hi] - bp[orf_lo]) * i / n_parts;
+        cut[(size_t)i] = std::max<int64_t>(cut[(size_t)i - 1], std::lower_bound(bp + orf_lo, bp + orf_hi, target) - bp);
+    }
+    if (!ctx->slot_stream[0]) RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[0], cudaStreamNonBlocking));
+    cudaStream_t copy = n_parts > 1 ? ctx->slot_stream[0] : nullptr;
+    if (n_parts > 1 && !ctx->ev_scored) RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_scored, cudaEventDisableTiming));
+    for (int i = 0; i < n_parts; ++i) {
+        const int64_t a = cut[(size_t)i], b = cut[(size_t)i + 1], m = b - a, k = a - orf_lo;
+        if (m == 0) continue;
+        rt_score_out di{};
+        di.score = d.score + k; di.count = d.count + k; di.valid = d.valid + k; di.length = d.length + k; di.status = d.status + k;
+        di.min_codon = d.min_codon ? d.min_codon + k : nullptr;
+        di.frame_K = d.frame_K ? d.frame_K + 3 * k : nullptr;
+        di.frame_s = d.frame_s ? d.frame_s + 3 * k : nullptr;
+        int rc = rt_score(ctx, d_cov, a, b, params, &di, nullptr);
+        if (rc != RT_OK) return rc;
+        if (copy) {
+            RT_CUDA(ctx, cudaEventRecord(ctx->ev_scored, nullptr));
+            RT_CUDA(ctx, cudaStreamWaitEvent(copy, ctx->ev_scored, 0));
+        }
+        auto back = [&](void* h, const void* dv, size_t elem) -> cudaError_t {
+            return h ? cudaMemcpyAsync(static_cast<char*>(h) + elem * (size_t)k, dv, elem * (size_t)m, cudaMemcpyDeviceToHost, copy) : cudaSuccess;
+        };
+        RT_CUDA(ctx, back(h_out->score, di.score, 8));
+        RT_CUDA(ctx, back(h_out->count, di.count, 8));
+        RT_CUDA(ctx, back(h_out->valid, di.valid, 4));
+        RT_CUDA(ctx, back(h_out->length, di.length, 4));
+        RT_CUDA(ctx, back(h_out->min_codon, di.min_codon, 4));
+        RT_CUDA(ctx, back(h_out->status, di.status, 1));
+        if (di.frame_K) RT_CUDA(ctx, back(h_out->frame_K, di.frame_K, 12));
+        if (di.frame_s) RT_CUDA(ctx, back(h_out->frame_s, di.frame_s, 24));
+    }
     RT_CUDA(ctx, cudaStreamSynchronize(nullptr));
+    if (copy) RT_CUDA(ctx, cudaStreamSynchronize(copy));
     return RT_OK;
 }
 

@@ -929,3 +929,31 @@ def test_zone_binning_soak(engine):
         assert binned > 100_000
     finally:
         engine.set_layout("dense")
+
+
+def test_score_host_in_parts(engine, monkeypatch):
+    """rt_score_host scores a large range in parts (own plan each) so that result copies overlap scoring: the columns
+    are those of the single-range call, bit for bit."""
+    from ribotricer_b200 import synth
+    from ribotricer_b200.engine import ScoreParams
+
+    cfg = synth.config("C1", 0.3)
+    idx = synth.make_index(cfg)
+    reads = synth.reads_to_numpy(synth.make_reads(cfg, idx))
+    _setup(engine, idx.contig_names, idx.contig_len, idx.as_dict(), synth.TRUE_OFFSETS, None, pad=64)
+    engine.set_layout("compact")
+    try:
+        cov = engine.new_coverage()
+        engine.bin_reads_host(cov, reads, "forward", sorted_hint=True)
+        monkeypatch.setenv("RT_SCORE_HOST_PARTS", "1")
+        whole = engine.score_host(cov, params=ScoreParams(min_reads_per_codon=1), diagnostics=True)
+        for parts in ("2", "5", "16"):
+            monkeypatch.setenv("RT_SCORE_HOST_PARTS", parts)
+            got = engine.score_host(cov, params=ScoreParams(min_reads_per_codon=1), diagnostics=True)
+            for k in whole:
+                assert np.array_equal(got[k], whole[k], equal_nan=True), (parts, k)
+            sub = engine.score_host(cov, 1000, idx.n_orf - 777, params=ScoreParams(min_reads_per_codon=1), diagnostics=True)
+            for k in whole:
+                assert np.array_equal(sub[k], whole[k][1000:idx.n_orf - 777], equal_nan=True), (parts, k)
+    finally:
+        engine.set_layout("dense")
