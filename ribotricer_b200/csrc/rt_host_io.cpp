@@ -690,7 +690,7 @@ int rt_stream_pack(int64_t n, const int32_t* ref_id, const int32_t* first, const
     }
     for (int64_t r = 0; r < n_ranges; ++r) blocks[r + 1] += blocks[r];     // counts -> exclusive offsets
     // every descent of the positions costs a block: a library that is not coordinate-sorted would be mostly padding
-    if (blocks[n_ranges] * RT_STREAM_BLOCK > 2 * n + 4 * RT_STREAM_BLOCK * n_ranges) {
+    if (blocks[n_ranges] * RT_STREAM_BLOCK > 2 * n + 1024 * RT_STREAM_BLOCK * n_ranges) {       // (small libraries may be mostly padding)
         g_io_error = "rt_stream_pack: the stream would be more than half padding (the library is not coordinate-sorted); use the "
                      "column entry points";
         return RT_ESTATE;

@@ -912,6 +912,11 @@ def test_zone_binning_soak(engine):
                 if trial % 4 == 0:
                     keep = np.sort(rng.choice(len(reads["first"]), size=max(50, n // 50), replace=False))
                     reads = {k: np.repeat(v[keep], 50)[:n] for k, v in reads.items()}
+            if trial % 3 == 1:          # a few reads that start before their predecessor: each opens a block of its own
+                back = rng.random(len(reads["first"])) < 0.01
+                shift = rng.integers(1, 40, len(back))
+                reads["first"] = np.where(back, np.maximum(reads["first"] - shift, 0), reads["first"]).astype(np.int32)
+                reads["last"] = np.maximum(reads["last"], reads["first"]).astype(np.int32)
             lengths = rng.choice(np.arange(24, 36), size=int(rng.integers(2, 10)), replace=False)
             offs = {int(length): int(rng.integers(-40, 60)) for length in lengths}
             rl = None if trial % 3 else [int(x) for x in rng.choice(np.arange(24, 36), size=8, replace=False)]
@@ -921,6 +926,10 @@ def test_zone_binning_soak(engine):
                 want = engine.new_coverage()
                 st, lc = engine.new_bin_accumulators()
                 engine.bin_stream_device(want, stream, protocol, st, lc)
+                cols = engine.new_coverage()           # the column kernel on the reads the stream was made from
+                st0, lc0 = engine.new_bin_accumulators()
+                engine.bin_reads_device(cols, engine.upload_reads(reads), protocol, st0, lc0)
+                assert t.equal(cols, want) and t.equal(st0, st) and t.equal(lc0, lc), (trial, protocol, "stream vs columns")
                 got = t.full_like(want, 99)
                 st2, lc2 = engine.new_bin_accumulators()
                 engine.bin_stream_device(got, stream, protocol, st2, lc2, fresh=True)

@@ -480,3 +480,50 @@ def test_stream_pack_ignores_positions_of_flag_decided_reads(built):
             assert meta & 1
         else:
             assert (ref, first, last, mlen) == (0, int(cols["first"][i]), int(cols["last"][i]), 28), i
+
+
+def test_stream_pack_random_small_libraries(built):
+    """Many small random libraries (fixed seed) through rt_stream_pack and back: whatever the mix of references, gaps,
+    descents, spliced / long / empty reads and flag-decided reads with junk positions, a stream that is produced decodes
+    to the columns, and a refusal is the documented one (a span the extension record cannot hold)."""
+    from helpers import decode_stream
+    from ribotricer_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(2024)
+    coded = refused = 0
+    for case in range(300):
+        n = int(rng.integers(1, 1200))
+        n_ref = int(rng.integers(1, 6))
+        ref = np.sort(rng.integers(0, n_ref, n)).astype(np.int32)
+        step = rng.choice([0, 1, 5, 300, 33_000, 70_000, 1 << 30], n, p=[0.3, 0.3, 0.2, 0.1, 0.05, 0.04, 0.01]).astype(np.int64)
+        first = np.zeros(n, np.int64)
+        for r in np.unique(ref):
+            m = ref == r
+            first[m] = np.minimum(np.cumsum(step[m]), 2 ** 31 - 70_000)
+        descents = rng.random(n) < rng.choice([0.0, 0.01, 0.6])          # none, a few, or an unsorted library
+        first = np.where(descents, np.maximum(first - rng.integers(1, 50, n), 0), first)
+        mlen = rng.choice([0, 1, 28, 30, 255, 256, 4000], n, p=[0.02, 0.03, 0.5, 0.3, 0.05, 0.05, 0.05]).astype(np.int64)
+        big = rng.random() < 0.05
+        extra = np.where(rng.random(n) < 0.2, rng.choice([1, 900, 60_000, (1 << 22) - 1, (1 << 22) if big else 7], n), 0)
+        last = first + mlen - 1 + extra
+        flag = np.where(rng.random(n) < 0.5, 16, 0) | np.where(rng.random(n) < 0.15, rng.choice([4, 256, 512, 1024], n), 0)
+        junk = (flag & 0x704) != 0
+        first = np.where(junk & (rng.random(n) < 0.5), rng.choice([-1, 0, 2 ** 31 - 1], n), first)
+        cols = dict(ref_id=ref, first=first.astype(np.int32), last=np.clip(last, -2 ** 31, 2 ** 31 - 1).astype(np.int32),
+                    mlen=mlen.astype(np.uint16), flag=flag.astype(np.uint16), mapq=rng.choice([255, 3, 0], n).astype(np.uint8),
+                    nh=rng.choice([0, 1, 2], n).astype(np.uint8))
+        rc, rec, hdr, nb = _stream_pack(lib, cols, n_threads=int(rng.integers(1, 4)))
+        clean = ~junk
+        if rc != 0:
+            refused += 1
+            assert rc == _lib_estate()
+            spans = (cols["last"].astype(np.int64) - cols["first"] + 1 - cols["mlen"])[clean]
+            assert (spans >= 1 << 22).any() or (spans < 0).any(), case     # (too small for the padding rule)
+            continue
+        coded += 1
+        got = decode_stream(rec, hdr, nb)
+        assert len(got) == n, case
+        for i in np.flatnonzero(clean):
+            assert got[i][:4] == (int(cols["ref_id"][i]), int(cols["first"][i]), int(cols["last"][i]), int(cols["mlen"][i])), (case, i)
+    assert coded > 150 and refused > 10
