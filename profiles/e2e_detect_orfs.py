@@ -2,7 +2,7 @@
 """Wall-clock of the whole detect_orfs() call (host stages included) on BASELINE configs[0]
 (yeast R64 scale: 100 k candidate ORFs, 10 M reads), with the stage split.
 
-    python profiles/e2e_detect_orfs.py [scale]
+    python profiles/e2e_detect_orfs.py [scale] [config]
 """
 import json
 import os
@@ -22,7 +22,8 @@ from ribotricer_b200.bam import ReadColumns, load_reads, save_read_columns, spli
 
 def main():
     scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-    cfg = synth.config("C1", scale)
+    name = sys.argv[2] if len(sys.argv) > 2 else "C1"
+    cfg = synth.config(name, scale)
     idx = synth.make_index(cfg)
     tmp = tempfile.mkdtemp(prefix="rt_e2e_")
     index_path, reads_path = os.path.join(tmp, "index.tsv"), os.path.join(tmp, "reads.npz")
@@ -30,7 +31,7 @@ def main():
     eng = D.get_engine(0)
     cols = synth.reads_to_numpy(synth.make_reads(cfg, idx, device=eng.device))
     save_read_columns(reads_path, ReadColumns(idx.contig_names, idx.contig_len, cols, True))
-    out = {"config": f"C1 x{scale}: {idx.n_orf} ORFs ({int(idx.orf_len.sum())} nt), {len(cols['ref_id'])} reads"}
+    out = {"config": f"{name} x{scale}: {idx.n_orf} ORFs ({int(idx.orf_len.sum())} nt), {len(cols['ref_id'])} reads"}
     offsets = {k: v for k, v in synth.TRUE_OFFSETS.items()}
     lengths = sorted(offsets)
     for tag, kw in (("offsets given, translating rows only", dict(read_lengths=lengths, psite_offsets=offsets, report_all=False)),
