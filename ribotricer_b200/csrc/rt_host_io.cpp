@@ -358,6 +358,31 @@ int rt_wig_block(rt_tsv* t, const char* chrom, int64_t n, const int64_t* pos, co
     b += "variableStep chrom=";
     b += chrom;
     b += '\n';
+    if (n >= (1 << 18)) {
+        // a long block (a human chromosome holds millions of covered positions): the lines are formatted by several
+        // threads, a slice of the block each, and written in order
+        const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)16, n >> 16}));
+        std::vector<std::string> part((size_t)n_thr);
+        std::vector<std::thread> pool;
+        for (int k = 0; k < n_thr; ++k)
+            pool.emplace_back([&, k]() {
+                const int64_t lo = n * k / n_thr, hi = n * (k + 1) / n_thr;
+                std::string& o = part[(size_t)k];
+                o.reserve((size_t)(hi - lo) * 14);
+                for (int64_t i = lo; i < hi; ++i) {
+                    append_int(o, pos[i]);
+                    o += '\t';
+                    append_int(o, count[i]);
+                    o += '\n';
+                }
+            });
+        for (auto& th : pool) th.join();
+        if (fwrite(b.data(), 1, b.size(), t->fh) != b.size()) return RT_EINVAL;
+        b.clear();
+        for (const std::string& o : part)
+            if (fwrite(o.data(), 1, o.size(), t->fh) != o.size()) return RT_EINVAL;
+        return RT_OK;
+    }
     for (int64_t i = 0; i < n; ++i) {
         append_int(b, pos[i]);
         b += '\t';

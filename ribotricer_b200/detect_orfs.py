@@ -82,6 +82,22 @@ class MergedAlignments:
             return z.astype(np.int8), z.astype(np.int32), z, z.astype(np.int32)
         return tuple(np.concatenate(x) for x in zip(*out))
 
+    def covered_by_contig(self):
+        """Yields ``(strand_code, contig_id, positions int64, counts int32)`` for every contig that carries coverage on
+        a strand, positions ascending: the ordered compaction of a strand plane cut at the contig bases (no per-position
+        host work: a human library has 10^8 covered positions)."""
+        eng = self.engine
+        base = np.asarray(eng.contig_base, np.int64)
+        for strand in (0, 1):
+            slots, vals = eng.nonzero_slots(self.cov, strand * eng.plane, eng.plane)
+            if len(slots) == 0:
+                continue
+            cuts = np.searchsorted(slots, np.append(base, np.int64(eng.plane)))
+            for ci in range(len(base)):
+                a, b = int(cuts[ci]), int(cuts[ci + 1])
+                if a < b:
+                    yield strand, ci, slots[a:b] - (base[ci] + eng.pad), vals[a:b]
+
     def to_dict(self):
         """The reference's ``merged[strand][(chrom, pos)] -> count`` view (small libraries only)."""
         merged = defaultdict(Counter)
@@ -268,28 +284,24 @@ def export_wig(merged_alignments: MergedAlignments, prefix: str) -> None:
     only strands that carry coverage."""
     import ctypes as C
 
-    s, c, p, n = merged_alignments.nonzero()
     eng = merged_alignments.engine
     names = eng.contig_names
-    order = sorted(range(len(names)), key=lambda i: names[i])
     lib = eng.lib
+    blocks = {0: {}, 1: {}}
+    for strand, ci, pos, cnt in merged_alignments.covered_by_contig():
+        blocks[strand][ci] = (pos, cnt)
     for strand, tag in ((0, "pos"), (1, "neg")):
-        m = s == strand
-        if not m.any():
+        if not blocks[strand]:
             continue
         handle = C.c_void_p()
         if lib.rt_wig_open(f"{prefix}_{tag}.wig".encode(), C.byref(handle)) != 0:
             raise OSError(lib.rt_io_last_error().decode())
         try:
-            cs, ps, ns = c[m], p[m], n[m]          # already ordered by contig id and position
-            bounds = np.searchsorted(cs, np.arange(len(names) + 1))
-            for ci in order:
-                a, b = int(bounds[ci]), int(bounds[ci + 1])
-                if a == b:
-                    continue
-                pos = np.ascontiguousarray(ps[a:b], np.int64)
-                cnt = np.ascontiguousarray(ns[a:b], np.int32)
-                rc = lib.rt_wig_block(handle, names[ci].encode(), b - a, pos.ctypes.data_as(C.c_void_p),
+            for ci in sorted(blocks[strand], key=lambda i: names[i]):        # chromosomes in lexicographic order
+                pos, cnt = blocks[strand][ci]
+                pos = np.ascontiguousarray(pos, np.int64)
+                cnt = np.ascontiguousarray(cnt, np.int32)
+                rc = lib.rt_wig_block(handle, names[ci].encode(), len(pos), pos.ctypes.data_as(C.c_void_p),
                                       cnt.ctypes.data_as(C.c_void_p))
                 if rc != 0:
                     raise OSError("rt_wig_block failed")

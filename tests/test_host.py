@@ -527,3 +527,27 @@ def test_stream_pack_random_small_libraries(built):
         for i in np.flatnonzero(clean):
             assert got[i][:4] == (int(cols["ref_id"][i]), int(cols["first"][i]), int(cols["last"][i]), int(cols["mlen"][i])), (case, i)
     assert coded > 150 and refused > 10
+
+
+def test_wig_long_block_is_formatted_in_order(tmp_path, built):
+    """rt_wig_block formats a long block (a chromosome with hundreds of thousands of covered positions) with several
+    threads; the text is the reference's, line for line (detect_orfs.py:338-345)."""
+    import ctypes as C
+
+    from ribotricer_b200 import _lib
+
+    lib = _lib.load()
+    n = 400_000
+    rng = np.random.default_rng(3)
+    pos = np.cumsum(rng.integers(1, 50, n)).astype(np.int64)
+    cnt = rng.integers(1, 100_000, n).astype(np.int32)
+    path = tmp_path / "x_pos.wig"
+    h = C.c_void_p()
+    assert lib.rt_wig_open(str(path).encode(), C.byref(h)) == 0
+    p = lambda a: a.ctypes.data_as(C.c_void_p)      # noqa: E731
+    assert lib.rt_wig_block(h, b"chr1", n, p(pos), p(cnt)) == 0
+    assert lib.rt_wig_block(h, b"chr2", 1000, p(pos), p(cnt)) == 0
+    lib.rt_wig_close(h)
+    want = "variableStep chrom=chr1\n" + "".join(f"{a}\t{b}\n" for a, b in zip(pos.tolist(), cnt.tolist())) + \
+        "variableStep chrom=chr2\n" + "".join(f"{a}\t{b}\n" for a, b in zip(pos[:1000].tolist(), cnt[:1000].tolist()))
+    assert path.read_text() == want
