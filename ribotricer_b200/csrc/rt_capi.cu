@@ -212,16 +212,43 @@ int build_atoms(rt_ctx* ctx, const std::vector<uint64_t>& desc, const std::vecto
         pts.push_back(off);
         pts.push_back(off + len);
     }
-    std::sort(pts.begin(), pts.end());
+    // a human index has 10^7 boundaries: the sort (chunks, then a tree of merges) and the look-ups below run on all cores
+    const int n_thr = (int)std::max<size_t>(1, std::min<size_t>({(size_t)std::thread::hardware_concurrency(), (size_t)16, pts.size() >> 16}));
+    auto parallel_for = [&](size_t n_items, auto&& body) {          // body(lo, hi) on slices of [0, n_items)
+        std::vector<std::thread> pool;
+        for (int k = 1; k < n_thr; ++k) pool.emplace_back([&, k]() { body(n_items * k / n_thr, n_items * (k + 1) / n_thr); });
+        body(0, n_items / n_thr);
+        for (auto& th : pool) th.join();
+    };
+    parallel_for(pts.size(), [&](size_t lo, size_t hi) { std::sort(pts.begin() + lo, pts.begin() + hi); });
+    for (int width = 1; width < n_thr; width *= 2) {
+        std::vector<std::thread> pool;
+        for (int k = 0; k + width < n_thr; k += 2 * width)
+            pool.emplace_back([&, k, width]() {
+                const size_t a = pts.size() * k / n_thr, m = pts.size() * (k + width) / n_thr;
+                const size_t b = pts.size() * std::min(k + 2 * width, n_thr) / n_thr;
+                std::inplace_merge(pts.begin() + a, pts.begin() + m, pts.begin() + b);
+            });
+        for (auto& th : pool) th.join();
+    }
     pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
     // which elementary intervals [pts[i], pts[i+1]) are covered by an entry
     std::vector<int32_t> diff(pts.size() + 1, 0);
     auto idx_of = [&](uint64_t v) { return (size_t)(std::lower_bound(pts.begin(), pts.end(), v) - pts.begin()); };
-    for (uint64_t ent : entries) {
-        const uint64_t off = ent >> rt::kLenBits, len = ent & rt::kLenMask;
-        if (off == kZero) continue;
-        diff[idx_of(off)]++;
-        diff[idx_of(off + len)]--;
+    // interval numbers of every entry's two ends, looked up once
+    std::vector<uint32_t> ilo(entries.size(), 0), ihi(entries.size(), 0);
+    parallel_for(entries.size(), [&](size_t lo, size_t hi) {
+        for (size_t e = lo; e < hi; ++e) {
+            const uint64_t off = entries[e] >> rt::kLenBits, len = entries[e] & rt::kLenMask;
+            if (off == kZero) continue;
+            ilo[e] = (uint32_t)idx_of(off);
+            ihi[e] = (uint32_t)idx_of(off + len);
+        }
+    });
+    for (size_t e = 0; e < entries.size(); ++e) {
+        if ((entries[e] >> rt::kLenBits) == kZero) continue;
+        diff[ilo[e]]++;
+        diff[ihi[e]]--;
     }
     // atoms of interval i are [atom_begin[i], atom_begin[i+1])
     std::vector<uint32_t> atom_begin(pts.size() + 1, 0);
@@ -254,14 +281,15 @@ int build_atoms(rt_ctx* ctx, const std::vector<uint64_t>& desc, const std::vecto
         const bool rev = (desc[o] >> 63) != 0;
         const size_t ref_begin = ctx->h_ref_ent.size();
         for (int k = 0; k < n_ent; ++k) {
-            const uint64_t ent = entries[begin + (rev ? n_ent - 1 - k : k)];
-            const uint64_t off = ent >> rt::kLenBits, len = ent & rt::kLenMask;
+            const size_t e = begin + (size_t)(rev ? n_ent - 1 - k : k);
+            const uint64_t ent = entries[e];
+            const uint64_t off = ent >> rt::kLenBits;
             if (off == kZero) {
                 ctx->h_ref_ent.push_back(ent);
                 ctx->h_ref_atom.push_back(0xffffffffu);   // reads-as-zero stretch: no atom
                 continue;
             }
-            const uint32_t a0 = atom_begin[idx_of(off)], a1 = atom_begin[idx_of(off + len)];
+            const uint32_t a0 = atom_begin[ilo[e]], a1 = atom_begin[ihi[e]];
             for (uint32_t a = 0; a < a1 - a0; ++a) {
                 const uint32_t atom = rev ? a1 - 1 - a : a0 + a;
                 ctx->h_ref_ent.push_back(ctx->h_atoms[atom]);
@@ -295,7 +323,7 @@ int build_atoms(rt_ctx* ctx, const std::vector<uint64_t>& desc, const std::vecto
         ref_ent_c[k] = ctx->h_ref_atom[k] == 0xffffffffu ? ctx->h_ref_ent[k] : atoms_c[ctx->h_ref_atom[k]];
     for (size_t k = 0; k < entries.size(); ++k) {
         const uint64_t off = entries[k] >> rt::kLenBits, len = entries[k] & rt::kLenMask;
-        entries_c[k] = off == kZero ? entries[k] : ((atoms_c[atom_begin[idx_of(off)]] >> rt::kLenBits) << rt::kLenBits) | len;
+        entries_c[k] = off == kZero ? entries[k] : ((atoms_c[atom_begin[ilo[k]]] >> rt::kLenBits) << rt::kLenBits) | len;
     }
     auto upload = [&](auto** dptr, const auto& vec) -> cudaError_t {
         using T = typename std::remove_reference<decltype(vec)>::type::value_type;
@@ -1142,7 +1170,12 @@ int rt_set_index(rt_ctx* ctx, int64_t n_orf, const int64_t* h_exon_ptr, const in
         RT_CUDA(ctx, cudaMemcpy(ctx->d_exon_entries, entries.data(), sizeof(uint64_t) * entries.size(),
                                 cudaMemcpyHostToDevice));
     {
+        const auto t_atoms = std::chrono::steady_clock::now();
         int rc = build_atoms(ctx, desc, entries);
+        if (getenv("RT_HOST_TIMING"))
+            fprintf(stderr, "rt_set_index: build_atoms %.1f ms (%zu ORFs, %zu exon entries, %zu atoms)\n",
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_atoms).count(), desc.size(), entries.size(),
+                    ctx->h_atoms.size());
         if (rc != RT_OK) return rc;
     }
     ctx->n_orf = n_orf;
@@ -1189,6 +1222,7 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
             return RT_OK;
         }
     const int64_t n = hi - lo;
+    const auto t_plan = std::chrono::steady_clock::now();
     const int64_t* np = ctx->nt_prefix.data();
     auto len_of = [np](int32_t x) { return np[x + 1] - np[x]; };
     std::vector<int32_t> ids;
@@ -1458,6 +1492,9 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
         RT_CUDA(ctx, cudaMalloc(&p.d_long_acc, sizeof(rt::LongAcc) * acc.size()));
         RT_CUDA(ctx, cudaMemcpy(p.d_long_acc, acc.data(), sizeof(rt::LongAcc) * acc.size(), cudaMemcpyHostToDevice));
     }
+    if (getenv("RT_HOST_TIMING"))
+        fprintf(stderr, "get_plan [%lld, %lld): %.1f ms\n", (long long)lo, (long long)hi,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan).count());
     ctx->plans.push_back(p);
     *out = &ctx->plans.back();
     return RT_OK;
