@@ -1287,7 +1287,7 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
             std::stable_sort(ids.begin() + begin, ids.end(), [&](int32_t x, int32_t y) { return len_of(x) > len_of(y); });
         }
     }
-    if (ctx->plans.size() >= 8) {   // bounded cache
+    if (ctx->plans.size() >= 24) {   // bounded cache (rt_score_host keeps four part plans per range it is asked for)
         cudaFree(ctx->plans.front().d_list);
         cudaFree(ctx->plans.front().d_fallback);
         cudaFree(ctx->plans.front().d_atom_list);
