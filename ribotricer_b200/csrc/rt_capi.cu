@@ -1300,6 +1300,15 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
         cudaFree(ctx->plans.front().d_long_acc);
         ctx->plans.erase(ctx->plans.begin());
     }
+    const bool plan_timing = getenv("RT_HOST_TIMING") != nullptr;
+    auto t_mark = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!plan_timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "  get_plan: %-28s %.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_mark).count());
+        t_mark = now;
+    };
+    lap("ORF order");
     rt_ctx::ScorePlan p;
     p.lo = lo;
     p.hi = hi;
@@ -1365,6 +1374,7 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
         if (!alist.empty())
             RT_CUDA(ctx, cudaMemcpy(p.d_atom_list, alist.data(), sizeof(int32_t) * alist.size(), cudaMemcpyHostToDevice));
     }
+    lap("atom list + passes");
     if (ctx->use_atoms) {
         // Phase B work list.  FAMILIES: candidate ORFs of one transcript that share their stop are suffixes of the
         // longest one -- same atoms from some reference on (the index is cut into atoms at every ORF start).  The
@@ -1406,6 +1416,7 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
             full_hash[o - lo] = h;
             if (cnt >= 1 && cnt <= 31) by_hash.emplace(h, o);          // a child has at most 31 references
         }
+        lap("reference-list hashes");
         std::vector<int32_t> parent_of((size_t)n, -1);                   // -1: not a child
         std::vector<int64_t> order((size_t)n);
         for (int64_t i = 0; i < n; ++i) order[i] = lo + i;
@@ -1443,6 +1454,7 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
                 }
             }
         }
+        lap("families (suffix matching)");
         for (int64_t o = lo; o < hi; ++o) {
             if (parent_of[o - lo] >= 0) continue;                        // laid out with its parent
             uint64_t rb, cnt; uint32_t rev;
@@ -1479,6 +1491,7 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
             }
         }
         pad_group();
+        lap("slot layout");
         p.n_ref_warps = (int64_t)warps.size();
         RT_CUDA(ctx, cudaMalloc(&p.d_refs, sizeof(rt::RefRec) * std::max<size_t>(1, refs.size())));
         RT_CUDA(ctx, cudaMalloc(&p.d_ref_warps, sizeof(rt::RefWarp) * std::max<size_t>(1, warps.size())));
