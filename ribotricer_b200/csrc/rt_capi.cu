@@ -891,7 +891,7 @@ int rt_bin_reads_host(rt_ctx* ctx, int32_t* d_cov, int64_t n, const int32_t* h_r
     const bool timing = getenv("RT_HOST_TIMING") != nullptr;
     std::atomic<long long> pack_ns{0}, wait_ns{0}, issue_ns{0};
     const auto t_begin = std::chrono::steady_clock::now();
-    // per-slot layout: 8-byte run table first, then the 4-byte columns, so that every column stays naturally aligned
+    // per-slot layout: a chunk's record stream (records, then block headers) or its plain columns, widest column first
     const size_t slot_bytes = std::max((size_t)chunk, (size_t)(use_stream ? kPackChunkReads : 0)) * kReadBytes + 64;
     for (int s = 0; s < n_pipes; ++s) {
         if (!ctx->slot_stream[s]) RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking));
