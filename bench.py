@@ -489,8 +489,9 @@ def run_ours(args):
                 "sharding": f"{world} byte-balanced block(s) of the index along the genome; a rank bins the slice of the "
                             f"sorted library that can reach its block; no replication, no collective",
                 "per_rank": [{"orfs": c[0], "reads": c[1], "score_bytes": c[2]} for c in per_rank],
-                "l2": "inputs larger than L2 (coverage buffer %.1f GB, read columns %.2f GB)" % (
-                    cov.numel() * 4 / 1e9, READ_BYTES * n_reads / 1e9),
+                "l2": "inputs larger than L2 (coverage buffer %.1f GB, %s %.2f GB)" % (
+                    cov.numel() * 4 / 1e9, "record stream" if use_stream else "read columns",
+                    (stream_blocks * (256 * 4 + 16) if use_stream else READ_BYTES * n_reads) / 1e9),
                 "coverage_layout": args.layout, "min_reads_per_codon": args.min_reads_per_codon,
                 "resident_library": ("record stream, 4 B/read (rt_stream_pack; raw filter bits per read, cascade on the device), "
                                      "%.2f GB" % (stream_bytes / max(1, world) / 1e9)) if use_stream else "decoder columns, 18 B/read",
