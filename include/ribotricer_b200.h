@@ -360,7 +360,10 @@ int rt_wig_close(rt_tsv* t);
  * mapq, the first/last/count of matched reference positions (get_reference_positions() semantics of
  * bam.py:95-99: M, = and X operations only) and the NH tag (see `nh` above, common.py:53-56).
  * Records whose fields run past their block_size are rejected ("corrupt BAM record").
- * BGZF blocks are inflated with `n_threads` threads (<= 0: all cores).
+ * The file is cut into batches of BGZF blocks; `n_threads` threads (<= 0: all cores) each inflate a batch (the DEFLATE
+ * decoder of csrc/rt_inflate.cpp; every block is checked against the CRC-32 of its footer, and a block the decoder
+ * refuses goes to zlib), walk its records in file order and decode them, so the load scales with the cores.
+ * RT_BAM_ZLIB=1 in the environment uses zlib for every block (A/B timing).
  */
 typedef struct rt_bam rt_bam;
 const char* rt_bam_last_error(void);
@@ -382,6 +385,13 @@ int rt_bam_pack(const rt_bam* b, uint8_t* meta, int64_t run_cap, int64_t* run_st
 /* the decoded reads as a record stream (rt_stream_pack on the decoder's own columns; same arguments, same two-call
  * pattern: records == NULL counts the blocks).  RT_ESTATE when the BAM is not coordinate-sorted after all */
 int rt_bam_stream(const rt_bam* b, int n_threads, int64_t cap_blocks, uint32_t* records, int32_t* hdr, int64_t* n_blocks);
+
+/* One raw DEFLATE stream (RFC 1951; the payload of a BGZF block, htslib's bgzf.c under pysam.AlignmentFile, bam.py:65)
+ * that must inflate to exactly n_dst bytes: RT_OK, or RT_EINVAL for anything else (corrupt, truncated, a different
+ * size, or a stream shape the decoder leaves to zlib).  Never writes outside dst[0, n_dst).  rt_crc32 is the gzip CRC-32
+ * of a buffer (PCLMULQDQ folding where the host has it). */
+int rt_inflate_raw(const uint8_t* src, int64_t n_src, uint8_t* dst, int64_t n_dst);
+uint32_t rt_crc32(const uint8_t* p, int64_t n);
 
 /* number of kernel launches issued through this ctx so far (bench.py's gpu_launches) */
 int64_t rt_launch_count(const rt_ctx* ctx);

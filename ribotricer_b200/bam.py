@@ -112,9 +112,9 @@ def read_bam_columns_native(bam_path: str, n_threads: int = 0) -> ReadColumns:
         raise OSError(f"cannot decode {bam_path}: {lib.rt_bam_last_error().decode()}")
     try:
         n = int(lib.rt_bam_n_reads(handle))
-        cols = {name: np.zeros(n, dt) for name, dt in READ_COLUMNS}
+        cols = {name: np.empty(n, dt) for name, dt in READ_COLUMNS}
         lib.rt_bam_copy(handle, *[cols[name].ctypes.data_as(C.c_void_p) for name, _ in READ_COLUMNS])
-        cols["pos"], cols["ref_end"] = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        cols["pos"], cols["ref_end"] = np.empty(n, np.int32), np.empty(n, np.int32)
         lib.rt_bam_copy_span(handle, cols["pos"].ctypes.data_as(C.c_void_p), cols["ref_end"].ctypes.data_as(C.c_void_p))
         n_ref = lib.rt_bam_n_ref(handle)
         names = [lib.rt_bam_ref_name(handle, i).decode() for i in range(n_ref)]

@@ -551,3 +551,131 @@ def test_wig_long_block_is_formatted_in_order(tmp_path, built):
     want = "variableStep chrom=chr1\n" + "".join(f"{a}\t{b}\n" for a, b in zip(pos.tolist(), cnt.tolist())) + \
         "variableStep chrom=chr2\n" + "".join(f"{a}\t{b}\n" for a, b in zip(pos[:1000].tolist(), cnt[:1000].tolist()))
     assert path.read_text() == want
+
+
+def _deflate_payload(rng, kind, n):
+    if kind == 0:
+        return rng.integers(0, 256, n, dtype=np.uint8).tobytes()                      # incompressible: stored blocks
+    if kind == 1:
+        return bytes(n)                                                                 # one long run (distance 1)
+    if kind == 2:
+        return rng.integers(0, 4, n, dtype=np.uint8).tobytes()                          # short codes: literal pairs
+    if kind == 3:
+        per = int(rng.integers(2, 12))
+        return (rng.integers(0, 256, per, dtype=np.uint8).tobytes() * (n // per + 1))[:n]   # overlapping copies
+    if kind == 4:
+        p = 0.5 ** np.arange(1, 257)
+        return bytes(rng.choice(256, n, p=p / p.sum()).astype(np.uint8))              # codes longer than 11 bits
+    words = [bytes(rng.integers(97, 123, int(rng.integers(2, 12)), dtype=np.uint8)) for _ in range(200)]
+    return b" ".join(words[int(i)] for i in rng.integers(0, 200, n // 5 + 1))[:n]      # text-like: long matches
+
+
+def test_inflate_and_crc32_match_zlib(built):
+    """csrc/rt_inflate.cpp against zlib: every compression level and strategy (stored, fixed and dynamic blocks, sync
+    flushes in the middle), sizes around the margins of the fast loop; a wrong announced size, a truncated stream and a
+    flipped bit are refused or decoded, never written past the output; rt_crc32 == zlib.crc32 at every length mod 16."""
+    import ctypes as C
+    import zlib
+
+    from ribotricer_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    for n in list(range(0, 150)) + [1000, 4096, 65280, 65536, (1 << 20) + 13]:
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert lib.rt_crc32(d, n) == zlib.crc32(d), n
+    strategies = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]
+    sizes = [0, 1, 2, 5, 100, 287, 288, 289, 320, 1000, 4099, 65280, 65536, 150000]
+    n_ok = 0
+    for trial in range(600):
+        kind, n = int(rng.integers(0, 6)), int(rng.choice(sizes))
+        data = _deflate_payload(rng, kind, n)
+        co = zlib.compressobj(int(rng.integers(0, 10)), zlib.DEFLATED, -15, int(rng.integers(1, 10)), int(rng.choice(strategies)))
+        if n > 1000 and trial % 3 == 0:
+            k = n // 3
+            comp = (co.compress(data[:k]) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(data[k:2 * k]) + co.flush(zlib.Z_FULL_FLUSH)
+                    + co.compress(data[2 * k:]) + co.flush())
+        else:
+            comp = co.compress(data) + co.flush()
+        out = C.create_string_buffer(n + 64)
+        C.memset(out, 0xAB, n + 64)
+        assert lib.rt_inflate_raw(comp, len(comp), out, n) == 0, (kind, n)
+        assert out.raw[:n] == data and out.raw[n:] == b"\xab" * 64, (kind, n)
+        n_ok += 1
+        if n:
+            assert lib.rt_inflate_raw(comp, len(comp), out, n - 1) != 0            # announced size too small
+            assert lib.rt_inflate_raw(comp, len(comp), out, n + 1) != 0            # ... too large
+            cut = int(rng.integers(0, len(comp)))
+            assert lib.rt_inflate_raw(comp[:cut], cut, out, n) != 0                 # truncated stream
+        if len(comp) > 4:
+            bad = bytearray(comp)
+            bad[int(rng.integers(0, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+            C.memset(out, 0xAB, n + 64)
+            lib.rt_inflate_raw(bytes(bad), len(bad), out, n)                        # any verdict, but inside the buffer
+            assert out.raw[n:] == b"\xab" * 64
+    assert n_ok == 600
+
+
+def test_bam_batches_carry_records_and_header_across_boundaries(tmp_path, built, monkeypatch):
+    """rt_bam_load cuts the file into batches that are inflated and decoded by different threads; the walk hands the
+    unfinished record (or header) from one batch to the next.  With batches of a few hundred bytes every record and the
+    header (300 references) span several batches, a 70 kB record spans hundreds; the columns must not depend on the
+    batch size, the thread count or the inflater.  Damaged files are refused with a message."""
+    import bam_writer as W
+    import pytest
+    from ribotricer_b200.bam import read_bam_columns_native
+
+    rng = np.random.default_rng(5)
+    refs = [("contig_%04d" % i, 100000 + i) for i in range(300)]
+    recs = []
+    for i in range(4000):
+        ref = int(rng.integers(0, len(refs)))
+        cigar = [("M", int(rng.integers(20, 40)))]
+        if rng.random() < 0.2:
+            cigar += [("N", int(rng.integers(50, 500))), ("M", int(rng.integers(5, 30)))]
+        aux = W.aux_field("NH", "C", int(rng.choice([1, 1, 1, 2, 5])))
+        if i == 1234:                                                   # one huge record (a long Z tag)
+            aux = W.aux_field("XL", "Z", "x" * 70000) + aux
+        recs.append(W.record(ref, int(rng.integers(0, 90000)), int(rng.choice([255, 3, 0])), int(rng.choice([0, 16, 256, 4])), cigar,
+                             name=b"q%d" % i, aux=aux))
+    path = tmp_path / "b.bam"
+    W.write_bam(str(path), refs, recs, block_payload=3001)
+    monkeypatch.delenv("RT_BAM_BATCH_BYTES", raising=False)
+    monkeypatch.delenv("RT_BAM_ZLIB", raising=False)
+    want = read_bam_columns_native(str(path), 1)
+    assert len(want) == len(recs) and want.contig_names == [r[0] for r in refs]
+    for batch, threads, zl in ((1, 3, False), (300, 4, False), (7000, 2, True), (1 << 16, 8, False), (1 << 26, 2, True)):
+        monkeypatch.setenv("RT_BAM_BATCH_BYTES", str(batch))
+        if zl:
+            monkeypatch.setenv("RT_BAM_ZLIB", "1")
+        else:
+            monkeypatch.delenv("RT_BAM_ZLIB", raising=False)
+        got = read_bam_columns_native(str(path), threads)
+        assert got.contig_names == want.contig_names and got.contig_len.tolist() == want.contig_len.tolist()
+        for name in want.cols:
+            assert np.array_equal(got.cols[name], want.cols[name]), (batch, threads, name)
+    monkeypatch.setenv("RT_BAM_BATCH_BYTES", "5000")
+    monkeypatch.delenv("RT_BAM_ZLIB", raising=False)
+    raw = path.read_bytes()
+    bad = tmp_path / "bad.bam"
+    for what, data in (("block cut short", raw[:len(raw) // 2]),
+                       ("record cut short", b"".join(W.bgzf_block(x) for x in [_bam_stream_bytes(W, refs, recs)[:50000]]) + W.BGZF_EOF),
+                       ("header cut short", W.bgzf_block(_bam_stream_bytes(W, refs, recs)[:100]) + W.BGZF_EOF),
+                       ("flipped payload bit", raw[:40] + bytes([raw[40] ^ 4]) + raw[41:]),
+                       ("record size below the fixed fields", W.bgzf_block(_bam_stream_bytes(W, refs[:1], [b"\x08\0\0\0" + bytes(8)])) + W.BGZF_EOF)):
+        bad.write_bytes(data)
+        for threads in (1, 4):
+            with pytest.raises(OSError):
+                read_bam_columns_native(str(bad), threads)
+
+
+def _bam_stream_bytes(W, refs, recs):
+    """The uncompressed byte stream bam_writer.write_bam would compress."""
+    import struct
+
+    text = b"@HD\tVN:1.6\tSO:coordinate\n" + b"".join(("@SQ\tSN:%s\tLN:%d\n" % (n, ln)).encode() for n, ln in refs)
+    head = b"BAM\1" + struct.pack("<I", len(text)) + text + struct.pack("<I", len(refs))
+    for n, ln in refs:
+        nb = n.encode() + b"\0"
+        head += struct.pack("<I", len(nb)) + nb + struct.pack("<I", ln)
+    return head + b"".join(recs)
