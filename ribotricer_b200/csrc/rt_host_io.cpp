@@ -10,7 +10,10 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -36,9 +39,90 @@ struct rt_index {
     std::string error;
 };
 
+// Text under construction: a growable char buffer written through a raw pointer (no per-character capacity checks).
+struct TextBuf {
+    char* base = nullptr;
+    size_t len = 0, cap = 0;
+    TextBuf() = default;
+    TextBuf(TextBuf&& o) noexcept : base(o.base), len(o.len), cap(o.cap) { o.base = nullptr; o.len = o.cap = 0; }
+    TextBuf& operator=(TextBuf&& o) noexcept {
+        if (this != &o) { free(base); base = o.base; len = o.len; cap = o.cap; o.base = nullptr; o.len = o.cap = 0; }
+        return *this;
+    }
+    TextBuf(const TextBuf&) = delete;
+    TextBuf& operator=(const TextBuf&) = delete;
+    ~TextBuf() { free(base); }
+    // room for n more bytes; returns where to write them (nullptr: out of memory)
+    char* need(size_t n) {
+        if (cap - len < n) {
+            const size_t want = std::max(len + n, cap + cap / 2 + (1u << 16));
+            char* q = static_cast<char*>(realloc(base, want));
+            if (!q) return nullptr;
+            base = q;
+            cap = want;
+        }
+        return base + len;
+    }
+    void advance_to(char* p) { len = (size_t)(p - base); }
+    void append(const char* d, size_t n) {
+        if (char* p = need(n)) { memcpy(p, d, n); len += n; }
+    }
+};
+
+// An output file with a write-behind thread: formatted text is queued and written in order while the caller formats
+// the next piece (or waits for the GPU).  At most kPendingMax bytes wait in the queue.
 struct rt_tsv {
     FILE* fh = nullptr;
-    std::string buf;
+    std::thread writer;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<TextBuf> queue;
+    size_t pending = 0;
+    bool closing = false, failed = false;
+    static constexpr size_t kPendingMax = 1ull << 30;
+
+    void run() {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv.wait(lk, [&] { return closing || !queue.empty(); });
+            if (queue.empty()) return;
+            TextBuf b = std::move(queue.front());
+            queue.pop_front();
+            lk.unlock();
+            const bool ok = b.len == 0 || fwrite(b.base, 1, b.len, fh) == b.len;
+            lk.lock();
+            pending -= b.len;
+            if (!ok) failed = true;
+            cv.notify_all();
+        }
+    }
+    // false when an earlier write has failed
+    bool put(TextBuf&& b) {
+        std::unique_lock<std::mutex> lk(mu);
+        if (failed) return false;
+        if (b.len == 0) return true;
+        if (!writer.joinable()) writer = std::thread([this] { run(); });
+        cv.wait(lk, [&] { return pending < kPendingMax || failed; });
+        pending += b.len;
+        queue.push_back(std::move(b));
+        cv.notify_all();
+        return !failed;
+    }
+    bool put(const std::string& s) {
+        TextBuf b;
+        b.append(s.data(), s.size());
+        return b.len == s.size() && put(std::move(b));
+    }
+    // drains the queue and stops the thread; false when any write failed
+    bool finish() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            closing = true;
+        }
+        cv.notify_all();
+        if (writer.joinable()) writer.join();
+        return !failed;
+    }
 };
 
 namespace {
@@ -84,10 +168,27 @@ void append_repr(std::string& out, double x) {
     }
 }
 
-void append_int(std::string& out, long long v) {
+// Decimal digits of v at p; returns the end.  Coverage profiles are mostly one-digit numbers.
+inline char* put_int(char* p, long long v) {
+    static const char pairs[] =
+        "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263"
+        "646566676869707172737475767778798081828384858687888990919293949596979899";
+    unsigned long long u = (unsigned long long)v;
+    if (v < 0) { *p++ = '-'; u = 0ull - u; }
+    if (u < 10) { *p++ = (char)('0' + u); return p; }
+    if (u < 100) { memcpy(p, pairs + 2 * u, 2); return p + 2; }
     char tmp[24];
-    auto res = std::to_chars(tmp, tmp + sizeof tmp, v);
-    out.append(tmp, res.ptr);
+    int k = 24;
+    while (u >= 100) {
+        const unsigned r = (unsigned)(u % 100);
+        u /= 100;
+        k -= 2;
+        memcpy(tmp + k, pairs + 2 * r, 2);
+    }
+    if (u >= 10) { k -= 2; memcpy(tmp + k, pairs + 2 * u, 2); }
+    else tmp[--k] = (char)('0' + u);
+    memcpy(p, tmp + k, (size_t)(24 - k));
+    return p + (24 - k);
 }
 
 bool parse_int(const char*& p, const char* end, long long& v) {   // Python int(): optional blanks and sign
@@ -246,48 +347,72 @@ int rt_tsv_open(const char* path, int write_header, rt_tsv** out) {
 namespace {
 
 // Rows [i0, i1) of the selection, formatted as detect_orfs.py:304-323 prints them.
-bool format_rows(std::string& b, const rt_index* ix, int64_t i0, int64_t i1, const int64_t* orf_ids, int64_t orf_lo,
+bool format_rows(TextBuf& b, const rt_index* ix, int64_t i0, int64_t i1, const int64_t* orf_ids, int64_t orf_lo,
                  const double* score, const int32_t* valid, const int64_t* count, const int32_t* length,
                  const uint8_t* status, const int64_t* prof_ptr, const int32_t* prof) {
+    std::string num;                                     // the three doubles of a row
     for (int64_t i = i0; i < i1; ++i) {
         const int64_t o = orf_ids[i], k = o - orf_lo;
-        if (o < 0 || o >= (int64_t)ix->orf_chrom.size() || k < 0) return false;
+        if (o < 0 || o >= (int64_t)ix->orf_chrom.size() || k < 0 || prof_ptr[i + 1] < prof_ptr[i]) return false;
         int flen[10];
         const char* f[10];
-        for (int j = 1; j <= 9; ++j) f[j] = rt_index_field(ix, o, j, &flen[j]);
+        size_t text = 0;
+        for (int j = 1; j <= 9; ++j) {
+            f[j] = rt_index_field(ix, o, j, &flen[j]);
+            text += (size_t)flen[j];
+        }
         const int64_t e0 = ix->exon_ptr[o], e1 = ix->exon_ptr[o + 1];
         long long L = 0;
         for (int64_t e = e0; e < e1; ++e) L += (long long)ix->exon_end[e] - ix->exon_start[e] + 1;
+        const size_t n_prof = (size_t)(prof_ptr[i + 1] - prof_ptr[i]);
+        // everything but the profile: the fields (transcript_id twice), 7 integers of <= 20 characters, 3 doubles of <= 25,
+        // the status word, tabs and brackets; a profile value takes <= 11 characters and ", "
+        char* p = b.need(2 * text + 7 * 21 + 3 * 26 + 64 + 13 * n_prof);
+        if (!p) return false;
+        auto put = [&](const char* d, int n) { memcpy(p, d, (size_t)n); p += n; };
+        auto put_double = [&](double x) {
+            num.clear();
+            append_repr(num, x);
+            put(num.data(), (int)num.size());
+        };
         // oid = tid_start_end_len (orf.py:101-103)
-        b.append(f[2], flen[2]); b += '_';
-        append_int(b, e1 > e0 ? ix->exon_start[e0] : 0); b += '_';
-        append_int(b, e1 > e0 ? ix->exon_end[e1 - 1] : 0); b += '_';
-        append_int(b, L); b += '\t';
-        b.append(f[1], flen[1]); b += '\t';
-        b += status[k] ? "translating" : "nontranslating"; b += '\t';
-        append_repr(b, score[k]); b += '\t';
-        append_int(b, count[k]); b += '\t';
-        append_int(b, length[k]); b += '\t';
-        append_int(b, valid[k]); b += '\t';
+        put(f[2], flen[2]); *p++ = '_';
+        p = put_int(p, e1 > e0 ? ix->exon_start[e0] : 0); *p++ = '_';
+        p = put_int(p, e1 > e0 ? ix->exon_end[e1 - 1] : 0); *p++ = '_';
+        p = put_int(p, L); *p++ = '\t';
+        put(f[1], flen[1]); *p++ = '\t';
+        if (status[k]) put("translating", 11); else put("nontranslating", 14);
+        *p++ = '\t';
+        put_double(score[k]); *p++ = '\t';
+        p = put_int(p, count[k]); *p++ = '\t';
+        p = put_int(p, length[k]); *p++ = '\t';
+        p = put_int(p, valid[k]); *p++ = '\t';
         const long long n_codons = length[k] / 3 > 1 ? length[k] / 3 : 1;        // detect_orfs.py:281
-        append_repr(b, (double)valid[k] / (double)n_codons); b += '\t';           // :285
-        append_repr(b, (double)count[k] / (double)n_codons); b += '\t';           // :287
-        b.append(f[2], flen[2]); b += '\t';
-        b.append(f[3], flen[3]); b += '\t';
-        b.append(f[4], flen[4]); b += '\t';
-        b.append(f[5], flen[5]); b += '\t';
-        b.append(f[6], flen[6]); b += '\t';
-        b.append(f[7], flen[7]); b += '\t';
-        b.append(f[8], flen[8]); b += '\t';
-        if (flen[9] >= 3) b.append(f[9], 3);                                     // ORF.start_codon (orf.py:108-119): seq[:3],
-        else b += "None";                                                        //   None when the field holds fewer than 3 characters
-        b += '\t';
-        b += '[';
-        for (int64_t q = prof_ptr[i]; q < prof_ptr[i + 1]; ++q) {
-            if (q > prof_ptr[i]) b += ", ";
-            append_int(b, prof[q]);
+        put_double((double)valid[k] / (double)n_codons); *p++ = '\t';             // :285
+        put_double((double)count[k] / (double)n_codons); *p++ = '\t';             // :287
+        put(f[2], flen[2]); *p++ = '\t';
+        put(f[3], flen[3]); *p++ = '\t';
+        put(f[4], flen[4]); *p++ = '\t';
+        put(f[5], flen[5]); *p++ = '\t';
+        put(f[6], flen[6]); *p++ = '\t';
+        put(f[7], flen[7]); *p++ = '\t';
+        put(f[8], flen[8]); *p++ = '\t';
+        if (flen[9] >= 3) put(f[9], 3);                                          // ORF.start_codon (orf.py:108-119): seq[:3],
+        else put("None", 4);                                                     //   None when the field holds fewer than 3 characters
+        *p++ = '\t';
+        *p++ = '[';
+        const int32_t* q = prof + prof_ptr[i];
+        for (size_t j = 0; j < n_prof; ++j) {
+            const int32_t v = q[j];
+            if ((uint32_t)v < 10u) *p++ = (char)('0' + v);
+            else p = put_int(p, v);
+            *p++ = ',';
+            *p++ = ' ';
         }
-        b += "]\n";
+        if (n_prof) p -= 2;
+        *p++ = ']';
+        *p++ = '\n';
+        b.advance_to(p);
     }
     return true;
 }
@@ -302,7 +427,7 @@ int rt_tsv_write(rt_tsv* t, const rt_index* ix, int64_t n_sel, const int64_t* or
     if (!t || !ix || n_sel < 0 || (n_sel && (!orf_ids || !score || !valid || !count || !length || !status || !prof_ptr || !prof)))
         return RT_EINVAL;
     // the profile column is most of the text: rows are formatted by several threads in slices balanced by
-    // profile length and written in order
+    // profile length, and handed in order to the file's write-behind thread
     const int64_t total = n_sel ? prof_ptr[n_sel] - prof_ptr[0] : 0;
     const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)16,
                                                                   (total + n_sel * 40) / (1 << 21)}));
@@ -313,7 +438,7 @@ int rt_tsv_write(rt_tsv* t, const rt_index* ix, int64_t n_sel, const int64_t* or
         cut[k] = std::lower_bound(prof_ptr, prof_ptr + n_sel, target) - prof_ptr;
         if (cut[k] < cut[k - 1]) cut[k] = cut[k - 1];
     }
-    std::vector<std::string> parts(n_thr);
+    std::vector<TextBuf> parts(n_thr);
     std::vector<char> ok(n_thr, 1);
     std::vector<std::thread> pool;
     for (int k = 1; k < n_thr; ++k)
@@ -322,18 +447,20 @@ int rt_tsv_write(rt_tsv* t, const rt_index* ix, int64_t n_sel, const int64_t* or
         });
     ok[0] = format_rows(parts[0], ix, cut[0], cut[1], orf_ids, orf_lo, score, valid, count, length, status, prof_ptr, prof);
     for (auto& th : pool) th.join();
-    for (int k = 0; k < n_thr; ++k) {
-        if (!ok[k]) return RT_EINVAL;
-        if (!parts[k].empty() && fwrite(parts[k].data(), 1, parts[k].size(), t->fh) != parts[k].size()) return RT_EINVAL;
-    }
+    for (int k = 0; k < n_thr; ++k)
+        if (!ok[k]) { g_io_error = "rt_tsv_write: ORF id outside the index or the result range, or out of memory"; return RT_EINVAL; }
+    for (int k = 0; k < n_thr; ++k)
+        if (!t->put(std::move(parts[k]))) { g_io_error = "rt_tsv_write: write failed"; return RT_EINVAL; }
     return RT_OK;
 }
 
 int rt_tsv_close(rt_tsv* t) {
     if (!t) return RT_EINVAL;
+    const bool wrote = t->finish();
     const int rc = fclose(t->fh);
     delete t;
-    return rc == 0 ? RT_OK : RT_EINVAL;
+    if (!wrote || rc != 0) g_io_error = "write failed (disk full?)";
+    return wrote && rc == 0 ? RT_OK : RT_EINVAL;
 }
 
 // For tests: Python-style repr of a double into buf (NUL terminated).
@@ -354,49 +481,40 @@ int rt_wig_open(const char* path, rt_tsv** out) { return rt_tsv_open(path, 0, ou
 
 int rt_wig_block(rt_tsv* t, const char* chrom, int64_t n, const int64_t* pos, const int32_t* count) {
     if (!t || !chrom || n < 0 || (n && (!pos || !count))) return RT_EINVAL;
-    std::string& b = t->buf;
-    b += "variableStep chrom=";
-    b += chrom;
-    b += '\n';
-    if (n >= (1 << 18)) {
-        // a long block (a human chromosome holds millions of covered positions): the lines are formatted by several
-        // threads, a slice of the block each, and written in order
-        const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)16, n >> 16}));
-        std::vector<std::string> part((size_t)n_thr);
-        std::vector<std::thread> pool;
-        for (int k = 0; k < n_thr; ++k)
-            pool.emplace_back([&, k]() {
-                const int64_t lo = n * k / n_thr, hi = n * (k + 1) / n_thr;
-                std::string& o = part[(size_t)k];
-                o.reserve((size_t)(hi - lo) * 14);
-                for (int64_t i = lo; i < hi; ++i) {
-                    append_int(o, pos[i]);
-                    o += '\t';
-                    append_int(o, count[i]);
-                    o += '\n';
-                }
-            });
-        for (auto& th : pool) th.join();
-        if (fwrite(b.data(), 1, b.size(), t->fh) != b.size()) return RT_EINVAL;
-        b.clear();
-        for (const std::string& o : part)
-            if (fwrite(o.data(), 1, o.size(), t->fh) != o.size()) return RT_EINVAL;
+    // "pos<TAB>count<NL>" lines of [lo, hi): at most 20 + 11 + 2 characters each
+    auto lines = [&](TextBuf& o, int64_t lo, int64_t hi) {
+        char* p = o.need((size_t)(hi - lo) * 33);
+        if (!p) return false;
+        for (int64_t i = lo; i < hi; ++i) {
+            p = put_int(p, pos[i]);
+            *p++ = '\t';
+            p = put_int(p, count[i]);
+            *p++ = '\n';
+        }
+        o.advance_to(p);
+        return true;
+    };
+    TextBuf head;
+    const std::string title = std::string("variableStep chrom=") + chrom + "\n";
+    head.append(title.data(), title.size());
+    // a long block (a human chromosome holds millions of covered positions) is formatted by several threads, a slice of
+    // the block each; the pieces go to the write-behind thread in order
+    const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)16, n >> 16}));
+    if (n_thr == 1) {
+        if (!lines(head, 0, n) || !t->put(std::move(head))) return RT_EINVAL;
         return RT_OK;
     }
-    for (int64_t i = 0; i < n; ++i) {
-        append_int(b, pos[i]);
-        b += '\t';
-        append_int(b, count[i]);
-        b += '\n';
-        if (b.size() > (1u << 22)) {
-            if (fwrite(b.data(), 1, b.size(), t->fh) != b.size()) return RT_EINVAL;
-            b.clear();
-        }
-    }
-    if (!b.empty()) {
-        if (fwrite(b.data(), 1, b.size(), t->fh) != b.size()) return RT_EINVAL;
-        b.clear();
-    }
+    std::vector<TextBuf> part((size_t)n_thr);
+    std::vector<char> ok((size_t)n_thr, 1);
+    std::vector<std::thread> pool;
+    for (int k = 0; k < n_thr; ++k)
+        pool.emplace_back([&, k]() { ok[(size_t)k] = lines(part[(size_t)k], n * k / n_thr, n * (k + 1) / n_thr); });
+    for (auto& th : pool) th.join();
+    for (char c : ok)
+        if (!c) return RT_EINVAL;
+    if (!t->put(std::move(head))) return RT_EINVAL;
+    for (TextBuf& o : part)
+        if (!t->put(std::move(o))) return RT_EINVAL;
     return RT_OK;
 }
 
