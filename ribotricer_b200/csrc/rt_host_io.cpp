@@ -4,6 +4,10 @@
 //   * {prefix}_translating_ORFs.tsv writer: rows formatted exactly as detect_orfs.py:304-323 prints
 //     them (np.float64 / Python float shortest repr, str(list) profile).
 // No GPU is involved; these entry points also work on a CPU-only box.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <charconv>
@@ -13,6 +17,7 @@
 #include <condition_variable>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -26,12 +31,13 @@
 #include "ribotricer_b200.h"
 
 struct rt_index {
-    std::string text;                    // the whole file; fields point into it
+    char* text = nullptr;                // the whole file (malloc); fields point into it
+    size_t text_size = 0;
+    ~rt_index() { free(text); }
     std::vector<int64_t> exon_ptr{0};
     std::vector<int32_t> exon_start, exon_end;
     std::vector<int32_t> orf_chrom;      // index into chrom_names
     std::vector<uint8_t> orf_strand;     // 0 '+', 1 '-', 2 anything else
-    std::vector<uint32_t> field_off;     // 10 per ORF: offsets of fields 1..9 and of the end of field 9 ... see field()
     std::vector<uint32_t> field_len;     // 9 per ORF: lengths of fields 1..9
     std::vector<uint64_t> line_field;    // per ORF: offset of field 1 (64-bit, files > 4 GB)
     std::vector<std::string> chrom_names;
@@ -212,88 +218,215 @@ const char* rt_io_last_error(void) { return g_io_error.c_str(); }
 int rt_index_load(const char* path, rt_index** out) {
     if (!path || !out) return RT_EINVAL;
     *out = nullptr;
-    FILE* fh = fopen(path, "rb");
-    if (!fh) { g_io_error = std::string("cannot open ") + path; return RT_EINVAL; }
-    rt_index* ix = new rt_index();
-    fseek(fh, 0, SEEK_END);
-    const long size = ftell(fh);
-    fseek(fh, 0, SEEK_SET);
-    ix->text.resize((size_t)size);
-    if (size > 0 && fread(&ix->text[0], 1, (size_t)size, fh) != (size_t)size) {
-        fclose(fh); delete ix; g_io_error = "short read"; return RT_EINVAL;
-    }
-    fclose(fh);
-    const char* base = ix->text.data();
-    const char* end = base + ix->text.size();
-    const char* p = (const char*)memchr(base, '\n', ix->text.size());   // skip the header (detect_orfs.py:273)
-    p = p ? p + 1 : end;
-    std::unordered_map<std::string, int> chrom_id;
-    bool in_prefix = true;
-    std::vector<std::pair<long long, long long>> ivs;
-    int64_t row = 0;
-    while (p < end) {
-        const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
-        const char* line_end = eol ? eol : end;
-        // split on tabs: exactly 11 fields (orf.py:144-151)
-        const char* f[12];
-        int nf = 0;
-        f[0] = p;
-        for (const char* q = p; q < line_end && nf < 11; ++q)
-            if (*q == '\t') f[++nf] = q + 1;
-        int tabs = 0;
-        for (const char* q = p; q < line_end; ++q) tabs += *q == '\t';
-        if (tabs != 10) {
-            g_io_error = "Error: unexpected number of columns found for index file\nplease run ribotricer prepare-orfs to regenerate";
-            delete ix;
-            return RT_ESTATE;
-        }
-        f[11] = line_end + 1;
-        if (in_prefix) {   // detect_orfs.py:104-105 tests the whole line for the substring
-            static const char kAnn[] = "annotated";
-            if (std::search(p, line_end, kAnn, kAnn + 9) != line_end) ix->n_annotated_prefix++;
-            else in_prefix = false;
-        }
-        // coordinate = start-end[,start-end...] (orf.py:166-170)
-        ivs.clear();
-        const char* c = f[10];
-        while (c < line_end) {
-            const char* grp_end = (const char*)memchr(c, ',', (size_t)(line_end - c));
-            if (!grp_end) grp_end = line_end;
-            const char* dash = (const char*)memchr(c + 1, '-', (size_t)(grp_end - c - 1));   // a leading '-' is a sign
-            long long s = 0, e = 0;
-            const char* q = c;
-            bool ok = dash != nullptr && parse_int(q, dash, s) && q == dash;
-            q = dash ? dash + 1 : c;
-            ok = ok && parse_int(q, grp_end, e) && q == grp_end;
-            if (!ok || s < INT32_MIN || s > INT32_MAX || e < INT32_MIN || e > INT32_MAX) {
-                g_io_error = "bad coordinate in index row " + std::to_string(row + 1);
-                delete ix;
-                return RT_EINVAL;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { g_io_error = std::string("cannot open ") + path; return RT_EINVAL; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); g_io_error = std::string("cannot stat ") + path; return RT_EINVAL; }
+    const size_t size = (size_t)st.st_size;
+    std::unique_ptr<rt_index> ix(new rt_index());
+    ix->text = static_cast<char*>(malloc(size + 1));
+    if (!ix->text) { close(fd); g_io_error = "out of memory"; return RT_ENOMEM; }
+    ix->text_size = size;
+    int n_thr = (int)std::max<size_t>(1, std::min<size_t>({(size_t)std::thread::hardware_concurrency(), (size_t)16, size >> 22}));
+    if (const char* e = getenv("RT_INDEX_THREADS")) n_thr = std::max(1, std::min(64, atoi(e)));   // tests: chunked parse of a small file
+    // 1. the file, read in slices by all threads (the buffer's pages are first touched by the thread that fills them)
+    {
+        std::atomic<bool> ok{true};
+        auto read_slice = [&](int k) {
+            size_t at = size * (size_t)k / n_thr;
+            const size_t hi = size * (size_t)(k + 1) / n_thr;
+            while (at < hi) {
+                const ssize_t got = pread(fd, ix->text + at, hi - at, (off_t)at);
+                if (got <= 0) { ok = false; return; }
+                at += (size_t)got;
             }
-            ivs.emplace_back(s, e);
-            c = grp_end + 1;
-        }
-        std::stable_sort(ivs.begin(), ivs.end(), [](const auto& a, const auto& b) { return a.first < b.first; });   // orf.py:100
-        for (auto& iv : ivs) {
-            ix->exon_start.push_back((int32_t)iv.first);
-            ix->exon_end.push_back((int32_t)iv.second);
-        }
-        ix->exon_ptr.push_back((int64_t)ix->exon_start.size());
-        ix->line_field.push_back((uint64_t)(f[1] - base));
-        for (int k = 1; k <= 9; ++k) ix->field_len.push_back((uint32_t)(f[k + 1] - 1 - f[k]));
-        std::string chrom(f[7], f[8] - 1);
-        auto it = chrom_id.find(chrom);
-        if (it == chrom_id.end()) {
-            it = chrom_id.emplace(chrom, (int)ix->chrom_names.size()).first;
-            ix->chrom_names.push_back(chrom);
-        }
-        ix->orf_chrom.push_back(it->second);
-        const size_t slen = (size_t)(f[9] - 1 - f[8]);
-        ix->orf_strand.push_back(slen == 1 && *f[8] == '+' ? 0 : slen == 1 && *f[8] == '-' ? 1 : 2);
-        ++row;
-        p = line_end + 1;
+        };
+        std::vector<std::thread> pool;
+        for (int k = 1; k < n_thr; ++k) pool.emplace_back(read_slice, k);
+        read_slice(0);
+        for (auto& th : pool) th.join();
+        close(fd);
+        if (!ok) { g_io_error = "short read"; return RT_EINVAL; }
     }
-    *out = ix;
+    ix->text[size] = '\0';
+    const char* base = ix->text;
+    const char* end = base + size;
+    const char* body = (const char*)memchr(base, '\n', size);   // skip the header (detect_orfs.py:273)
+    body = body ? body + 1 : end;
+
+    // 2. the rows, parsed in chunks cut at line ends
+    struct Chunk {
+        const char *lo, *hi;
+        std::vector<int32_t> exon_start, exon_end, n_exon, chrom_local;
+        std::vector<uint8_t> strand;
+        std::vector<uint32_t> field_len;
+        std::vector<uint64_t> line_field;
+        std::vector<std::string> chrom_names;          // in order of first appearance within the chunk
+        int64_t annotated_prefix = 0;                  // leading rows that hold the substring "annotated"
+        bool all_annotated = true;
+        int err = RT_OK;                               // first error of the chunk, at local row err_row
+        int64_t err_row = 0;
+    };
+    std::vector<Chunk> chunks((size_t)n_thr);
+    {
+        const size_t span = (size_t)(end - body);
+        const char* lo = body;
+        for (int k = 0; k < n_thr; ++k) {
+            const char* hi = end;
+            if (k + 1 < n_thr) {
+                const char* guess = body + span * (size_t)(k + 1) / n_thr;
+                if (guess < lo) guess = lo;
+                const char* nl = guess < end ? (const char*)memchr(guess, '\n', (size_t)(end - guess)) : nullptr;
+                hi = nl ? nl + 1 : end;
+            }
+            chunks[(size_t)k].lo = lo;
+            chunks[(size_t)k].hi = hi;
+            lo = hi;
+        }
+    }
+    auto parse_chunk = [&](Chunk& ck) {
+        std::unordered_map<std::string, int> chrom_id;
+        std::vector<std::pair<long long, long long>> ivs;
+        const size_t rows_guess = (size_t)(ck.hi - ck.lo) / 96 + 16;
+        ck.n_exon.reserve(rows_guess); ck.chrom_local.reserve(rows_guess); ck.strand.reserve(rows_guess);
+        ck.line_field.reserve(rows_guess); ck.field_len.reserve(9 * rows_guess);
+        ck.exon_start.reserve(4 * rows_guess); ck.exon_end.reserve(4 * rows_guess);
+        int64_t row = 0;
+        for (const char* p = ck.lo; p < ck.hi; ++row) {
+            const char* eol = (const char*)memchr(p, '\n', (size_t)(ck.hi - p));
+            const char* line_end = eol ? eol : ck.hi;
+            // split on tabs: exactly 11 fields (orf.py:144-151)
+            const char* f[12];
+            int tabs = 0;
+            f[0] = p;
+            for (const char* q = p; (q = (const char*)memchr(q, '\t', (size_t)(line_end - q))) != nullptr; ++q) {
+                if (tabs < 10) f[tabs + 1] = q + 1;
+                ++tabs;
+            }
+            if (tabs != 10) { ck.err = RT_ESTATE; ck.err_row = row; return; }
+            f[11] = line_end + 1;
+            if (ck.all_annotated) {   // detect_orfs.py:104-105 tests the whole line for the substring
+                static const char kAnn[] = "annotated";
+                if (std::search(p, line_end, kAnn, kAnn + 9) != line_end) ck.annotated_prefix++;
+                else ck.all_annotated = false;
+            }
+            // coordinate = start-end[,start-end...] (orf.py:166-170)
+            ivs.clear();
+            const char* c = f[10];
+            while (c < line_end) {
+                const char* grp_end = (const char*)memchr(c, ',', (size_t)(line_end - c));
+                if (!grp_end) grp_end = line_end;
+                const char* dash = (const char*)memchr(c + 1, '-', (size_t)(grp_end - c - 1));   // a leading '-' is a sign
+                long long s = 0, e = 0;
+                const char* q = c;
+                bool ok = dash != nullptr && parse_int(q, dash, s) && q == dash;
+                q = dash ? dash + 1 : c;
+                ok = ok && parse_int(q, grp_end, e) && q == grp_end;
+                if (!ok || s < INT32_MIN || s > INT32_MAX || e < INT32_MIN || e > INT32_MAX) { ck.err = RT_EINVAL; ck.err_row = row; return; }
+                ivs.emplace_back(s, e);
+                c = grp_end + 1;
+            }
+            if (ivs.size() > 1)
+                std::stable_sort(ivs.begin(), ivs.end(), [](const auto& a, const auto& b) { return a.first < b.first; });   // orf.py:100
+            for (auto& iv : ivs) {
+                ck.exon_start.push_back((int32_t)iv.first);
+                ck.exon_end.push_back((int32_t)iv.second);
+            }
+            ck.n_exon.push_back((int32_t)ivs.size());
+            ck.line_field.push_back((uint64_t)(f[1] - base));
+            for (int k = 1; k <= 9; ++k) ck.field_len.push_back((uint32_t)(f[k + 1] - 1 - f[k]));
+            std::string chrom(f[7], f[8] - 1);
+            auto it = chrom_id.find(chrom);
+            if (it == chrom_id.end()) {
+                it = chrom_id.emplace(chrom, (int)ck.chrom_names.size()).first;
+                ck.chrom_names.push_back(chrom);
+            }
+            ck.chrom_local.push_back(it->second);
+            const size_t slen = (size_t)(f[9] - 1 - f[8]);
+            ck.strand.push_back(slen == 1 && *f[8] == '+' ? 0 : slen == 1 && *f[8] == '-' ? 1 : 2);
+            p = line_end + 1;
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int k = 1; k < n_thr; ++k) pool.emplace_back([&, k]() { parse_chunk(chunks[(size_t)k]); });
+        parse_chunk(chunks[0]);
+        for (auto& th : pool) th.join();
+    }
+    // 3. the first error in file order, as the row-by-row loop of the reference would meet it
+    {
+        int64_t rows_before = 0;
+        for (const Chunk& ck : chunks) {
+            if (ck.err == RT_ESTATE) {
+                g_io_error = "Error: unexpected number of columns found for index file\nplease run ribotricer prepare-orfs to regenerate";
+                return RT_ESTATE;
+            }
+            if (ck.err != RT_OK) {
+                g_io_error = "bad coordinate in index row " + std::to_string(rows_before + ck.err_row + 1);
+                return ck.err;
+            }
+            rows_before += (int64_t)ck.n_exon.size();
+        }
+    }
+    // 4. merge: chromosome ids in order of first appearance in the file, columns concatenated by all threads
+    std::vector<std::vector<int>> chrom_map(chunks.size());
+    {
+        std::unordered_map<std::string, int> chrom_id;
+        for (size_t k = 0; k < chunks.size(); ++k)
+            for (const std::string& name : chunks[k].chrom_names) {
+                auto it = chrom_id.find(name);
+                if (it == chrom_id.end()) {
+                    it = chrom_id.emplace(name, (int)ix->chrom_names.size()).first;
+                    ix->chrom_names.push_back(name);
+                }
+                chrom_map[k].push_back(it->second);
+            }
+    }
+    std::vector<size_t> row0(chunks.size() + 1, 0), exon0(chunks.size() + 1, 0);
+    bool in_prefix = true;
+    for (size_t k = 0; k < chunks.size(); ++k) {
+        row0[k + 1] = row0[k] + chunks[k].n_exon.size();
+        exon0[k + 1] = exon0[k] + chunks[k].exon_start.size();
+        if (in_prefix) {
+            ix->n_annotated_prefix += chunks[k].annotated_prefix;
+            in_prefix = chunks[k].all_annotated;
+        }
+    }
+    const size_t n_rows = row0.back(), n_exons = exon0.back();
+    ix->exon_ptr.resize(n_rows + 1);
+    ix->exon_start.resize(n_exons); ix->exon_end.resize(n_exons);
+    ix->orf_chrom.resize(n_rows); ix->orf_strand.resize(n_rows);
+    ix->field_len.resize(9 * n_rows); ix->line_field.resize(n_rows);
+    ix->exon_ptr[0] = 0;
+    auto merge_chunk = [&](size_t k) {
+        Chunk& ck = chunks[k];
+        const size_t r0 = row0[k], e0 = exon0[k], m = ck.n_exon.size();
+        if (!ck.exon_start.empty()) {
+            memcpy(&ix->exon_start[e0], ck.exon_start.data(), 4 * ck.exon_start.size());
+            memcpy(&ix->exon_end[e0], ck.exon_end.data(), 4 * ck.exon_end.size());
+        }
+        int64_t at = (int64_t)e0;
+        for (size_t i = 0; i < m; ++i) {
+            at += ck.n_exon[i];
+            ix->exon_ptr[r0 + i + 1] = at;
+            ix->orf_chrom[r0 + i] = chrom_map[k][(size_t)ck.chrom_local[i]];
+        }
+        if (m) {
+            memcpy(&ix->orf_strand[r0], ck.strand.data(), m);
+            memcpy(&ix->field_len[9 * r0], ck.field_len.data(), 4 * 9 * m);
+            memcpy(&ix->line_field[r0], ck.line_field.data(), 8 * m);
+        }
+        Chunk().exon_start.swap(ck.exon_start);        // give the chunk's memory back early
+        Chunk().exon_end.swap(ck.exon_end);
+        Chunk().field_len.swap(ck.field_len);
+    };
+    {
+        std::vector<std::thread> pool;
+        for (size_t k = 1; k < chunks.size(); ++k) pool.emplace_back(merge_chunk, k);
+        merge_chunk(0);
+        for (auto& th : pool) th.join();
+    }
+    *out = ix.release();
     return RT_OK;
 }
 
@@ -323,7 +456,7 @@ const char* rt_index_field(const rt_index* ix, int64_t orf, int k, int* len) {
     uint64_t off = ix->line_field[orf];
     for (int j = 1; j < k; ++j) off += ix->field_len[9 * orf + (j - 1)] + 1;
     if (len) *len = (int)ix->field_len[9 * orf + (k - 1)];
-    return ix->text.data() + off;
+    return ix->text + off;
 }
 
 int rt_tsv_open(const char* path, int write_header, rt_tsv** out) {

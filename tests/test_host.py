@@ -88,6 +88,55 @@ def test_native_index_loader_matches_python_rules(tmp_path, built):
     assert "unexpected number of columns" in str(exc.value)
 
 
+def test_native_index_loader_chunked_parse(tmp_path, built, monkeypatch):
+    """A large index is parsed in chunks by several threads and merged: forced here on small files (RT_INDEX_THREADS).
+    Columns, chromosome order (first appearance in the file), the annotated prefix and every field must equal the
+    one-thread parse; the FIRST bad row in file order decides the error, as in the reference's row-by-row loop."""
+    import pytest
+
+    from ribotricer_b200 import synth
+    from ribotricer_b200.index import NativeIndex
+
+    p = tmp_path / "synth.tsv"
+    synth.make_index(synth.config("tiny")).write_tsv(str(p))
+    lines = p.read_text().split("\n")
+    # a chromosome that first appears late, rows with shuffled and negative coordinates, the annotated prefix broken early
+    row = lines[5].split("\t")
+    lines.insert(900, "\t".join(row[:7] + ["chrLate", "-", "ATG", "300-310,-5-20,100-120"]))
+    lines.insert(3, "\t".join(row[:1] + ["novel"] + row[2:]))
+    p.write_text("\n".join(lines))
+    monkeypatch.setenv("RT_INDEX_THREADS", "1")
+    want = NativeIndex(str(p))
+    assert want.n_annotated_prefix == 2
+    for threads in (2, 3, 7, 16, 64):
+        monkeypatch.setenv("RT_INDEX_THREADS", str(threads))
+        got = NativeIndex(str(p))
+        assert got.n_orf == want.n_orf and got.n_annotated_prefix == want.n_annotated_prefix
+        for k in ("exon_ptr", "exon_start", "exon_end"):
+            assert (getattr(got, k) == getattr(want, k)).all(), (threads, k)
+        assert got.contig_table() == want.contig_table()
+        assert list(got.chrom) == list(want.chrom) and list(got.strand) == list(want.strand)
+        for o in range(0, want.n_orf, 7):
+            assert got.fields[o] == want.fields[o] and got.oid(o) == want.oid(o)
+    # errors: the earlier of a bad coordinate (row 1,501) and a short row (row 2,001) wins, whatever the chunking
+    body = p.read_text().split("\n")
+    body[1501] = body[1501].rsplit("\t", 1)[0] + "\t12-x"
+    body[2001] = "a\tb"
+    p.write_text("\n".join(body))
+    for threads in (1, 5, 16):
+        monkeypatch.setenv("RT_INDEX_THREADS", str(threads))
+        with pytest.raises((SystemExit, OSError, ValueError)) as exc:
+            NativeIndex(str(p))
+        assert "bad coordinate in index row 1501" in str(exc.value), threads
+    body[1000] = "a\tb"
+    p.write_text("\n".join(body))
+    for threads in (1, 5, 16):
+        monkeypatch.setenv("RT_INDEX_THREADS", str(threads))
+        with pytest.raises(SystemExit) as exc:
+            NativeIndex(str(p))
+        assert "unexpected number of columns" in str(exc.value)
+
+
 def test_native_tsv_writer_matches_reference_formatting(tmp_path, built):
     """rt_tsv_write rows against the rows the reference wrote (golden TSV text): feeding the
     writer the reference's own numbers must reproduce its text byte for byte (float repr, int/int
