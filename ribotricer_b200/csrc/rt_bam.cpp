@@ -23,6 +23,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <exception>
 #include <condition_variable>
 #include <cstdlib>
 #include <memory>
@@ -96,6 +97,7 @@ bool parse_block(const uint8_t* base, size_t size, size_t off, Block& b, size_t&
     b.in_off = off + 12 + xlen;
     b.in_len = total - (12 + xlen) - 8;
     b.out_len = rd32(p + total - 4);
+    if (b.out_len > 65536u) return false;              // a BGZF block holds at most 64 KiB (SAM spec 4.1)
     b.crc = rd32(p + total - 8);
     next = off + total;
     return true;
@@ -450,10 +452,17 @@ int rt_bam_load(const char* path, int n_threads, rt_bam** out) {
             done.push_back(std::move(bo));
         }
     };
+    auto guarded = [&]() {
+        try {
+            worker();
+        } catch (const std::exception& e) {              // bad_alloc on a huge record: refuse the file, do not terminate
+            set_fail("out of memory while decoding");
+        }
+    };
     {
         std::vector<std::thread> th;
-        for (int t = 1; t < n_threads; ++t) th.emplace_back(worker);
-        worker();
+        for (int t = 1; t < n_threads; ++t) th.emplace_back(guarded);
+        guarded();
         for (auto& x : th) x.join();
     }
     if (size) munmap((void*)base, size);
@@ -463,6 +472,7 @@ int rt_bam_load(const char* path, int n_threads, rt_bam** out) {
 
     // ---- the batches' columns, concatenated in file order by all threads (first touch of the final arrays included)
     const size_t total = cur.n_before;
+    if (total > (size_t)INT64_MAX / kRowBytes) { g_bam_error = "too many records"; return RT_EINVAL; }
     rt_bam& B = *bam;
     if (!(B.ref_id.alloc(total) && B.first.alloc(total) && B.last.alloc(total) && B.pos.alloc(total) && B.ref_end.alloc(total) &&
           B.mlen.alloc(total) && B.flag.alloc(total) && B.mapq.alloc(total) && B.nh.alloc(total))) {
