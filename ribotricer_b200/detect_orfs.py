@@ -1,9 +1,10 @@
 """``detect-orfs`` on the GPU -- same function surface as ribotricer/detect_orfs.py.
 
-    merge_read_lengths   detect_orfs.py:54     -> K1 (bin_psites_kernel)
+    merge_read_lengths   detect_orfs.py:54     -> K1 (bin_stream_kernel on a coordinate-sorted library, else bin_psites_kernel)
     orf_coverage         detect_orfs.py:134    -> K4 (gather_profiles_kernel)
-    export_orf_coverages detect_orfs.py:206    -> K2+K3 (score_orfs_kernel) + K4 + TSV writer
-    export_wig           detect_orfs.py:327
+    export_orf_coverages detect_orfs.py:206    -> K2+K3 (atom_pass_kernel + compose_refs_kernel; score_orfs_kernel only for
+                                                  the ORFs the plan hands to the fallback launch) + K4 + native TSV writer
+    export_wig           detect_orfs.py:327    -> wig_count_kernel + wig_fill_kernel + native WIG writer
     detect_orfs          detect_orfs.py:354    (same positional signature; learn_cutoff.py:231 calls it)
 
 The dict-of-Counter values of the reference become device-resident objects:
@@ -272,11 +273,17 @@ def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: i
                         str(prof[ptr[j]:ptr[j + 1]].tolist()))))
                 out.write("\n".join(rows) + "\n")
             at += n_take
-    finally:
+    except BaseException:
         if native:
             lib.rt_tsv_close(handle)
         else:
             out.close()
+        raise
+    if native:
+        if lib.rt_tsv_close(handle) != 0:       # the file has a write-behind thread: a failed write shows up here
+            raise OSError(f"cannot write {path}: {lib.rt_io_last_error().decode()}")
+    else:
+        out.close()
 
 
 def export_wig(merged_alignments: MergedAlignments, prefix: str) -> None:
@@ -305,8 +312,11 @@ def export_wig(merged_alignments: MergedAlignments, prefix: str) -> None:
                                       cnt.ctypes.data_as(C.c_void_p))
                 if rc != 0:
                     raise OSError("rt_wig_block failed")
-        finally:
+        except BaseException:
             lib.rt_wig_close(handle)
+            raise
+        if lib.rt_wig_close(handle) != 0:       # the file has a write-behind thread: a failed write shows up here
+            raise OSError(f"cannot write {prefix}_{tag}.wig: {lib.rt_io_last_error().decode()}")
 
 
 def _stamp(msg: str) -> None:
@@ -330,7 +340,7 @@ def detect_orfs(
 ) -> None:
     """Same positional signature and side files as detect_orfs.py:354-526.
 
-    ``bam`` may be a BAM (decoded on the host with pysam), a ``.npz`` of decoded read columns
+    ``bam`` may be a BAM (decoded on the host by the native decoder, csrc/rt_bam.cpp), a ``.npz`` of decoded read columns
     or a ``ReadColumns`` object.
     """
     from . import metagene as mg

@@ -6,8 +6,8 @@ import zlib
 CIGAR_OPS = "MIDNSHP=X"
 
 
-def bgzf_block(payload: bytes) -> bytes:
-    comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+def bgzf_block(payload: bytes, level: int = 6, strategy: int = zlib.Z_DEFAULT_STRATEGY) -> bytes:
+    comp = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
     data = comp.compress(payload) + comp.flush()
     bsize = 12 + 6 + len(data) + 8 - 1
     return (b"\x1f\x8b\x08\x04" + struct.pack("<IBBH", 0, 0, 0xFF, 6) + b"BC" + struct.pack("<HH", 2, bsize)
@@ -47,7 +47,7 @@ def record(ref_id, pos, mapq, flag, cigar, name=b"r", l_seq=None, aux=b"") -> by
     return struct.pack("<I", len(body)) + body
 
 
-def write_bam(path, refs, records, sorted_header=True, block_payload=0xFF00):
+def write_bam(path, refs, records, sorted_header=True, block_payload=0xFF00, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, eof=True):
     """refs: [(name, length)]; records: list of bytes from record()."""
     text = ("@HD\tVN:1.6\tSO:%s\n" % ("coordinate" if sorted_header else "unsorted")).encode()
     text += b"".join(("@SQ\tSN:%s\tLN:%d\n" % (n, l)).encode() for n, l in refs)
@@ -58,5 +58,6 @@ def write_bam(path, refs, records, sorted_header=True, block_payload=0xFF00):
     stream = head + b"".join(records)
     with open(path, "wb") as fh:
         for i in range(0, len(stream), block_payload):     # records straddle block boundaries on purpose
-            fh.write(bgzf_block(stream[i:i + block_payload]))
-        fh.write(BGZF_EOF)
+            fh.write(bgzf_block(stream[i:i + block_payload], level, strategy))
+        if eof:
+            fh.write(BGZF_EOF)

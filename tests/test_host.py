@@ -1,4 +1,6 @@
 """Host-side logic that needs no GPU: CLI validation, index parsing, sharding arithmetic."""
+import os
+
 import numpy as np
 
 
@@ -600,6 +602,12 @@ def test_wig_long_block_is_formatted_in_order(tmp_path, built):
     want = "variableStep chrom=chr1\n" + "".join(f"{a}\t{b}\n" for a, b in zip(pos.tolist(), cnt.tolist())) + \
         "variableStep chrom=chr2\n" + "".join(f"{a}\t{b}\n" for a, b in zip(pos[:1000].tolist(), cnt[:1000].tolist()))
     assert path.read_text() == want
+    # the writers hand their text to a write-behind thread: a disk that refuses it must surface at the latest on close
+    if os.path.exists("/dev/full"):
+        h = C.c_void_p()
+        assert lib.rt_wig_open(b"/dev/full", C.byref(h)) == 0
+        rcs = [lib.rt_wig_block(h, b"chr1", n, p(pos), p(cnt)) for _ in range(3)]
+        assert lib.rt_wig_close(h) != 0 or any(rcs), "a failed write went unnoticed"
 
 
 def _deflate_payload(rng, kind, n):
@@ -703,8 +711,21 @@ def test_bam_batches_carry_records_and_header_across_boundaries(tmp_path, built,
         assert got.contig_names == want.contig_names and got.contig_len.tolist() == want.contig_len.tolist()
         for name in want.cols:
             assert np.array_equal(got.cols[name], want.cols[name]), (batch, threads, name)
-    monkeypatch.setenv("RT_BAM_BATCH_BYTES", "5000")
+    # the same records from other compressors: stored blocks (samtools -u), level 1 and 9, fixed-Huffman and
+    # Huffman-only streams, full-size blocks, a file without the EOF marker
+    import zlib
     monkeypatch.delenv("RT_BAM_ZLIB", raising=False)
+    other = tmp_path / "o.bam"
+    for level, strategy, payload, eof in ((0, zlib.Z_DEFAULT_STRATEGY, 0xFF00, True), (1, zlib.Z_DEFAULT_STRATEGY, 0xFF00, True),
+                                          (9, zlib.Z_DEFAULT_STRATEGY, 777, False), (6, zlib.Z_FIXED, 0xFF00, True),
+                                          (6, zlib.Z_HUFFMAN_ONLY, 5000, True), (4, zlib.Z_RLE, 0xFF00, False)):
+        W.write_bam(str(other), refs, recs, block_payload=payload, level=level, strategy=strategy, eof=eof)
+        for batch in (4000, 1 << 20):
+            monkeypatch.setenv("RT_BAM_BATCH_BYTES", str(batch))
+            got = read_bam_columns_native(str(other), 3)
+            for name in want.cols:
+                assert np.array_equal(got.cols[name], want.cols[name]), (level, strategy, batch, name)
+    monkeypatch.setenv("RT_BAM_BATCH_BYTES", "5000")
     raw = path.read_bytes()
     bad = tmp_path / "bad.bam"
     for what, data in (("block cut short", raw[:len(raw) // 2]),
