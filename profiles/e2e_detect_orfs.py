@@ -34,9 +34,10 @@ def main():
     out = {"config": f"{name} x{scale}: {idx.n_orf} ORFs ({int(idx.orf_len.sum())} nt), {len(cols['ref_id'])} reads"}
     offsets = {k: v for k, v in synth.TRUE_OFFSETS.items()}
     lengths = sorted(offsets)
-    for tag, kw in (("offsets given, translating rows only", dict(read_lengths=lengths, psite_offsets=offsets, report_all=False)),
-                    ("offsets given, --report_all", dict(read_lengths=lengths, psite_offsets=offsets, report_all=True)),
-                    ("default flags (protocol, lengths and offsets inferred)", dict(read_lengths=None, psite_offsets=None, report_all=False))):
+    runs = (("offsets given, translating rows only", dict(read_lengths=lengths, psite_offsets=offsets, report_all=False)),
+            ("offsets given, --report_all", dict(read_lengths=lengths, psite_offsets=offsets, report_all=True)),
+            ("default flags (protocol, lengths and offsets inferred)", dict(read_lengths=None, psite_offsets=None, report_all=False)))
+    for tag, kw in runs[:int(os.environ.get("E2E_RUNS", "3"))]:        # E2E_RUNS=1: a short run on a large configuration
         prefix = os.path.join(tmp, "run", "lib")
         t0 = time.perf_counter()
         try:

@@ -30,16 +30,40 @@
 
 #include "ribotricer_b200.h"
 
+// A column of the parsed index: plain uninitialised storage (the threads that fill a large array also touch its pages
+// first; a std::vector would have one thread zero-fill it)
+template <class T>
+struct Arr {
+    T* p = nullptr;
+    size_t n = 0;
+    Arr() = default;
+    Arr(const Arr&) = delete;
+    Arr& operator=(const Arr&) = delete;
+    ~Arr() { free(p); }
+    bool alloc(size_t m) {
+        free(p);
+        p = static_cast<T*>(malloc(std::max<size_t>(m, 1) * sizeof(T)));
+        n = p ? m : 0;
+        return p != nullptr;
+    }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    T* data() const { return p; }
+    size_t size() const { return n; }
+    T* begin() const { return p; }
+    T* end() const { return p + n; }
+};
+
 struct rt_index {
     char* text = nullptr;                // the whole file (malloc); fields point into it
     size_t text_size = 0;
     ~rt_index() { free(text); }
-    std::vector<int64_t> exon_ptr{0};
-    std::vector<int32_t> exon_start, exon_end;
-    std::vector<int32_t> orf_chrom;      // index into chrom_names
-    std::vector<uint8_t> orf_strand;     // 0 '+', 1 '-', 2 anything else
-    std::vector<uint32_t> field_len;     // 9 per ORF: lengths of fields 1..9
-    std::vector<uint64_t> line_field;    // per ORF: offset of field 1 (64-bit, files > 4 GB)
+    Arr<int64_t> exon_ptr;               // n_orf + 1
+    Arr<int32_t> exon_start, exon_end;
+    Arr<int32_t> orf_chrom;              // index into chrom_names
+    Arr<uint8_t> orf_strand;             // 0 '+', 1 '-', 2 anything else
+    Arr<uint32_t> field_len;             // 9 per ORF: lengths of fields 1..9
+    Arr<uint64_t> line_field;            // per ORF: offset of field 1 (64-bit, files > 4 GB)
     std::vector<std::string> chrom_names;
     int64_t n_annotated_prefix = 0;
     std::string error;
@@ -393,17 +417,18 @@ int rt_index_load(const char* path, rt_index** out) {
         }
     }
     const size_t n_rows = row0.back(), n_exons = exon0.back();
-    ix->exon_ptr.resize(n_rows + 1);
-    ix->exon_start.resize(n_exons); ix->exon_end.resize(n_exons);
-    ix->orf_chrom.resize(n_rows); ix->orf_strand.resize(n_rows);
-    ix->field_len.resize(9 * n_rows); ix->line_field.resize(n_rows);
+    if (!(ix->exon_ptr.alloc(n_rows + 1) && ix->exon_start.alloc(n_exons) && ix->exon_end.alloc(n_exons) && ix->orf_chrom.alloc(n_rows) &&
+          ix->orf_strand.alloc(n_rows) && ix->field_len.alloc(9 * n_rows) && ix->line_field.alloc(n_rows))) {
+        g_io_error = "out of memory";
+        return RT_ENOMEM;
+    }
     ix->exon_ptr[0] = 0;
     auto merge_chunk = [&](size_t k) {
         Chunk& ck = chunks[k];
         const size_t r0 = row0[k], e0 = exon0[k], m = ck.n_exon.size();
         if (!ck.exon_start.empty()) {
-            memcpy(&ix->exon_start[e0], ck.exon_start.data(), 4 * ck.exon_start.size());
-            memcpy(&ix->exon_end[e0], ck.exon_end.data(), 4 * ck.exon_end.size());
+            memcpy(ix->exon_start.p + e0, ck.exon_start.data(), 4 * ck.exon_start.size());
+            memcpy(ix->exon_end.p + e0, ck.exon_end.data(), 4 * ck.exon_end.size());
         }
         int64_t at = (int64_t)e0;
         for (size_t i = 0; i < m; ++i) {
@@ -412,9 +437,9 @@ int rt_index_load(const char* path, rt_index** out) {
             ix->orf_chrom[r0 + i] = chrom_map[k][(size_t)ck.chrom_local[i]];
         }
         if (m) {
-            memcpy(&ix->orf_strand[r0], ck.strand.data(), m);
-            memcpy(&ix->field_len[9 * r0], ck.field_len.data(), 4 * 9 * m);
-            memcpy(&ix->line_field[r0], ck.line_field.data(), 8 * m);
+            memcpy(ix->orf_strand.p + r0, ck.strand.data(), m);
+            memcpy(ix->field_len.p + 9 * r0, ck.field_len.data(), 4 * 9 * m);
+            memcpy(ix->line_field.p + r0, ck.line_field.data(), 8 * m);
         }
         Chunk().exon_start.swap(ck.exon_start);        // give the chunk's memory back early
         Chunk().exon_end.swap(ck.exon_end);
@@ -442,11 +467,19 @@ const char* rt_index_chrom_name(const rt_index* ix, int i) {
 int rt_index_copy(const rt_index* ix, int64_t* exon_ptr, int32_t* exon_start, int32_t* exon_end, int32_t* orf_chrom,
                   uint8_t* orf_strand) {
     if (!ix) return RT_EINVAL;
-    if (exon_ptr) std::copy(ix->exon_ptr.begin(), ix->exon_ptr.end(), exon_ptr);
-    if (exon_start) std::copy(ix->exon_start.begin(), ix->exon_start.end(), exon_start);
-    if (exon_end) std::copy(ix->exon_end.begin(), ix->exon_end.end(), exon_end);
-    if (orf_chrom) std::copy(ix->orf_chrom.begin(), ix->orf_chrom.end(), orf_chrom);
-    if (orf_strand) std::copy(ix->orf_strand.begin(), ix->orf_strand.end(), orf_strand);
+    // one thread per column when the index is large (the destination is usually fresh memory)
+    std::vector<std::thread> pool;
+    auto copy = [&](void* dst, const void* src, size_t bytes) {
+        if (!dst || !bytes) return;
+        if (bytes < (1u << 22)) memcpy(dst, src, bytes);
+        else pool.emplace_back([=]() { memcpy(dst, src, bytes); });
+    };
+    copy(exon_ptr, ix->exon_ptr.p, 8 * ix->exon_ptr.n);
+    copy(exon_start, ix->exon_start.p, 4 * ix->exon_start.n);
+    copy(exon_end, ix->exon_end.p, 4 * ix->exon_end.n);
+    copy(orf_chrom, ix->orf_chrom.p, 4 * ix->orf_chrom.n);
+    copy(orf_strand, ix->orf_strand.p, ix->orf_strand.n);
+    for (auto& th : pool) th.join();
     return RT_OK;
 }
 

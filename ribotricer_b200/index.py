@@ -167,11 +167,11 @@ class NativeIndex:
         self.handle = handle
         n = int(lib.rt_index_n_orf(handle))
         e = int(lib.rt_index_n_exon(handle))
-        self.exon_ptr = np.zeros(n + 1, np.int64)
-        self.exon_start = np.zeros(e, np.int32)
-        self.exon_end = np.zeros(e, np.int32)
-        self.orf_chrom_id = np.zeros(n, np.int32)
-        self.orf_strand_code = np.zeros(n, np.uint8)
+        self.exon_ptr = np.empty(n + 1, np.int64)
+        self.exon_start = np.empty(e, np.int32)
+        self.exon_end = np.empty(e, np.int32)
+        self.orf_chrom_id = np.empty(n, np.int32)
+        self.orf_strand_code = np.empty(n, np.uint8)
         p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
         lib.rt_index_copy(handle, p(self.exon_ptr), p(self.exon_start), p(self.exon_end), p(self.orf_chrom_id),
                           p(self.orf_strand_code))
