@@ -386,6 +386,14 @@ int rt_bam_pack(const rt_bam* b, uint8_t* meta, int64_t run_cap, int64_t* run_st
  * pattern: records == NULL counts the blocks).  RT_ESTATE when the BAM is not coordinate-sorted after all */
 int rt_bam_stream(const rt_bam* b, int n_threads, int64_t cap_blocks, uint32_t* records, int32_t* hdr, int64_t* n_blocks);
 
+/* Metagene sums (metagene.py:204-252, host side of the P-site offset inference): row i of the ragged matrix
+ * flat[ptr[i], ptr[i+1]) holds the coverage of one annotated ORF over its first <= width positions (K4 over the truncated
+ * windows).  Every row that holds a read is divided by its mean and added to the start-aligned sums and, shifted to end
+ * at the last column, to the stop-aligned sums; *_cnt[k] = rows that reach column k.  All four outputs have `width`
+ * entries and are overwritten.  The result does not depend on the number of host threads. */
+int rt_metagene_sums(const int32_t* flat, const int64_t* ptr, int64_t n_rows, int64_t width, double* start_sum,
+                     int64_t* start_cnt, double* stop_sum, int64_t* stop_cnt);
+
 /* One raw DEFLATE stream (RFC 1951; the payload of a BGZF block, htslib's bgzf.c under pysam.AlignmentFile, bam.py:65)
  * that must inflate to exactly n_dst bytes: RT_OK, or RT_EINVAL for anything else (corrupt, truncated, a different
  * size, or a stream shape the decoder leaves to zlib).  Never writes outside dst[0, n_dst).  rt_crc32 is the gzip CRC-32

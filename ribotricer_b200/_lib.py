@@ -30,7 +30,7 @@ EXPORTS = (
     "rt_index_chrom_name", "rt_index_copy", "rt_index_field", "rt_tsv_open", "rt_tsv_write", "rt_tsv_close",
     "rt_repr_double", "rt_wig_open", "rt_wig_block", "rt_wig_close", "rt_bam_last_error", "rt_bam_load", "rt_bam_free", "rt_bam_n_reads", "rt_bam_n_ref",
     "rt_bam_ref_name", "rt_bam_ref_len", "rt_bam_sorted", "rt_bam_copy", "rt_bam_copy_span", "rt_bam_pack", "rt_bam_stream",
-    "rt_inflate_raw", "rt_crc32",
+    "rt_inflate_raw", "rt_crc32", "rt_metagene_sums",
 )
 
 
@@ -147,6 +147,7 @@ def load():
     lib.rt_bam_pack.argtypes = [vp, vp, i64, vp, vp, C.POINTER(i64)]
     lib.rt_bam_stream.argtypes = [vp, i32, i64, vp, vp, C.POINTER(i64)]
     lib.rt_inflate_raw.argtypes = [vp, i64, vp, i64]
+    lib.rt_metagene_sums.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp]
     lib.rt_crc32.argtypes = [vp, i64]
     lib.rt_crc32.restype = C.c_uint32
     lib.rt_launch_count.restype = i64

@@ -640,6 +640,68 @@ int rt_repr_double(double x, char* buf, int cap) {
 
 }  // extern "C"
 
+// ---- metagene sums (metagene.py:204-252) ---------------------------------------------------------------
+// Row i of the ragged matrix flat[ptr[i] .. ptr[i+1]) is the coverage of one annotated ORF over its first <= width
+// positions (leader included).  A row with reads is divided by its mean (metagene.py:214-219) and added, position by
+// position, to the start-aligned sums and -- re-indexed to END at the last column (metagene.py:140-155) -- to the
+// stop-aligned sums; the counts say how many rows reach a column.  Rows are summed in blocks of 2,048 by all cores and the
+// block sums are added in block order, so the result does not depend on the number of threads.
+extern "C" int rt_metagene_sums(const int32_t* flat, const int64_t* ptr, int64_t n_rows, int64_t width, double* start_sum,
+                                int64_t* start_cnt, double* stop_sum, int64_t* stop_cnt) {
+    if (n_rows < 0 || width < 0 || !ptr || !start_sum || !start_cnt || !stop_sum || !stop_cnt || (n_rows && ptr[n_rows] > ptr[0] && !flat))
+        return RT_EINVAL;
+    for (int64_t i = 0; i < n_rows; ++i)
+        if (ptr[i + 1] < ptr[i] || ptr[i + 1] - ptr[i] > width) { g_io_error = "rt_metagene_sums: a row is longer than the matrix is wide"; return RT_EINVAL; }
+    const int64_t kBlock = 2048, n_blocks = (n_rows + kBlock - 1) / kBlock, w = width;
+    std::vector<double> sums((size_t)(n_blocks * 2 * w), 0.0);
+    std::vector<int64_t> cnts((size_t)(n_blocks * 2 * w), 0);
+    std::atomic<int64_t> next{0};
+    auto run = [&]() {
+        for (int64_t b; (b = next.fetch_add(1)) < n_blocks;) {
+            double* s5 = sums.data() + (size_t)(b * 2 * w);
+            double* s3 = s5 + w;
+            int64_t* c5 = cnts.data() + (size_t)(b * 2 * w);
+            int64_t* c3 = c5 + w;
+            for (int64_t i = b * kBlock; i < std::min(n_rows, (b + 1) * kBlock); ++i) {
+                const int32_t* row = flat + ptr[i];
+                const int64_t len = ptr[i + 1] - ptr[i];
+                long long total = 0;
+                for (int64_t k = 0; k < len; ++k) total += row[k];
+                if (len == 0) continue;
+                const double mean = (double)total / (double)len;
+                if (!(mean > 0)) continue;                       // metagene.py:216: ORFs without reads are skipped
+                const int64_t shift = w - len;
+                for (int64_t k = 0; k < len; ++k) {
+                    const double v = (double)row[k] / mean;
+                    s5[k] += v;
+                    s3[shift + k] += v;
+                    c5[k]++;
+                    c3[shift + k]++;
+                }
+            }
+        }
+    };
+    {
+        const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)16, n_blocks}));
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_thr; ++t) pool.emplace_back(run);
+        run();
+        for (auto& th : pool) th.join();
+    }
+    for (int64_t k = 0; k < w; ++k) { start_sum[k] = stop_sum[k] = 0.0; start_cnt[k] = stop_cnt[k] = 0; }
+    for (int64_t b = 0; b < n_blocks; ++b) {
+        const double* s5 = sums.data() + (size_t)(b * 2 * w);
+        const int64_t* c5 = cnts.data() + (size_t)(b * 2 * w);
+        for (int64_t k = 0; k < w; ++k) {
+            start_sum[k] += s5[k];
+            stop_sum[k] += s5[w + k];
+            start_cnt[k] += c5[k];
+            stop_cnt[k] += c5[w + k];
+        }
+    }
+    return RT_OK;
+}
+
 // ---- WIG writer (detect_orfs.py:327-351): one "variableStep chrom=" block per call ------------------
 extern "C" {
 

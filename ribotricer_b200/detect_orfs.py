@@ -123,8 +123,34 @@ def parse_ribotricer_index(ribotricer_index: str):
     """detect_orfs.py:86-131: the leading 'annotated' rows as ORF objects plus, per chromosome,
     the (start, end, strand) spans that infer_protocol needs."""
     idx = load_index(ribotricer_index)
+    n = idx.n_annotated_prefix
     annotated, refseq = [], defaultdict(list)
-    for o in range(idx.n_annotated_prefix):
+    if isinstance(idx, NativeIndex) and n:
+        # the prefix rows are the first n lines behind the header: their text fields are split here in one pass (a
+        # human index has 60 k annotated rows; one native call per field costs more than the split), the intervals come
+        # from the loader's columns (already sorted by start, orf.py:100)
+        with open(ribotricer_index, encoding="utf-8", newline="\n") as fh:
+            fh.readline()
+            rows = [fh.readline().rstrip("\n").split("\t") for _ in range(n)]
+        ptr = idx.exon_ptr[:n + 1].tolist()
+        starts, ends = idx.exon_start[:ptr[-1]].tolist(), idx.exon_end[:ptr[-1]].tolist()
+        import gc
+        gc_was_on = gc.isenabled()
+        gc.disable()        # hundreds of thousands of small objects are made here and none is garbage: the collector's
+        try:                # generation scans would take more time than the loop itself
+            for o, f in enumerate(rows):
+                if f[1] != "annotated":       # detect_orfs.py:120
+                    continue
+                ivs = list(zip(starts[ptr[o]:ptr[o + 1]], ends[ptr[o]:ptr[o + 1]]))
+                orf = ORF(f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8], ivs, f[9])
+                orf.row = o
+                refseq[orf.chrom].append((ivs[0][0], ivs[-1][1], 1 if orf.strand == "+" else -1))
+                annotated.append(orf)
+        finally:
+            if gc_was_on:
+                gc.enable()
+        return annotated, refseq
+    for o in range(n):
         f = idx.fields[o]
         if f[0] != "annotated":       # detect_orfs.py:120
             continue

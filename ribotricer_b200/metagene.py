@@ -153,6 +153,20 @@ def _metagene_windows(cds, engine, max_positions, offset_5p, offset_3p):
             np.array(contig, np.int32), np.array(strand, np.uint8), np.array(lens, np.int64))
 
 
+def metagene_sums(lib, flat, out_ptr, width: int):
+    """``(start_sum, start_cnt, stop_sum, stop_cnt)`` over the rows ``flat[out_ptr[i]:out_ptr[i+1]]`` (metagene.py:204-252)."""
+    import ctypes as C
+
+    flat = np.ascontiguousarray(flat, np.int32)
+    out_ptr = np.ascontiguousarray(out_ptr, np.int64)
+    sums = [np.zeros(width, np.float64), np.zeros(width, np.int64), np.zeros(width, np.float64), np.zeros(width, np.int64)]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)      # noqa: E731
+    rc = lib.rt_metagene_sums(p(flat), p(out_ptr), len(out_ptr) - 1, int(width), *[p(a) for a in sums])
+    if rc != 0:
+        raise ValueError(f"rt_metagene_sums failed ({rc}): {lib.rt_io_last_error().decode()}")
+    return tuple(sums)
+
+
 def metagene_coverage(cds, alignments, read_lengths: dict, prefix: str, max_positions: int = 600,
                       offset_5p: int = 20, offset_3p: int = 0, meta_min_reads: int = 100000):
     """metagene.py:160-265.  Returns ``{length: ((index_5p, profile_5p), (index_3p, profile_3p),
@@ -184,25 +198,9 @@ def metagene_coverage(cds, alignments, read_lengths: dict, prefix: str, max_posi
         alignments.bin_into(cov, {length: 0})                       # alignments[length], bam.py:135
         out_ptr, flat = aux.gather_profiles(cov, sel, lens)
         alignments.bin_into(cov, {length: 0}, weight=-1)            # scratch back to zero
-        # ragged -> matrix aligned at the start (column k <-> index k - offset_5p)
-        mat = np.zeros((len(cds), width), np.float64)
-        have = np.arange(width)[None, :] < lens[:, None]
-        mat[have] = flat
-        mean = mat.sum(1) / np.maximum(lens, 1)                      # metagene.py:214
-        use = mean > 0
-        norm = np.where(have[use], mat[use] / mean[use, None], 0.0)
-        start_sum = norm.sum(0)
-        start_cnt = have[use].sum(0)
-        # the same vectors re-indexed to end at offset_3p (metagene.py:140-155)
-        stop = np.zeros_like(norm)
-        hs = np.zeros_like(have[use])
-        l_use = lens[use]
-        for n in np.unique(l_use):
-            rows = l_use == n
-            stop[rows, width - n:] = norm[rows, :n]
-            hs[rows, width - n:] = True
-        stop_sum = stop.sum(0)
-        stop_cnt = hs.sum(0)
+        # rows normalised by their mean, summed aligned at the start (column k <-> index k - offset_5p) and aligned at
+        # the end (metagene.py:140-155): rt_metagene_sums, all host cores
+        start_sum, start_cnt, stop_sum, stop_cnt = metagene_sums(eng.lib, flat, out_ptr, width)
         ks, ke = start_cnt > 0, stop_cnt > 0
         prof5 = (start_sum[ks] / start_cnt[ks]).tolist()
         prof3 = (stop_sum[ke] / stop_cnt[ke]).tolist()

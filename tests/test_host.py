@@ -749,3 +749,50 @@ def _bam_stream_bytes(W, refs, recs):
         nb = n.encode() + b"\0"
         head += struct.pack("<I", len(nb)) + nb + struct.pack("<I", ln)
     return head + b"".join(recs)
+
+
+def _metagene_sums_numpy(flat, lens, width):
+    """The matrix statement of metagene.py:204-252 the native routine replaced (rows padded to `width`)."""
+    n = len(lens)
+    mat = np.zeros((n, width), np.float64)
+    have = np.arange(width)[None, :] < lens[:, None]
+    mat[have] = flat
+    mean = mat.sum(1) / np.maximum(lens, 1)                      # metagene.py:214
+    use = mean > 0
+    norm = np.where(have[use], mat[use] / mean[use, None], 0.0)
+    stop = np.zeros_like(norm)
+    hs = np.zeros_like(have[use])
+    l_use = lens[use]
+    for k in np.unique(l_use):
+        rows = l_use == k
+        stop[rows, width - k:] = norm[rows, :k]
+        hs[rows, width - k:] = True
+    return norm.sum(0), have[use].sum(0), stop.sum(0), hs.sum(0)
+
+
+def test_metagene_sums_match_the_matrix_statement(built):
+    """rt_metagene_sums (rows normalised by their mean, summed start-aligned and stop-aligned by all cores) against the
+    numpy matrix form: counts exact, sums to 1e-12 relative (the order of the additions differs); rows without reads,
+    empty rows and rows shorter than the matrix; the result must not depend on the number of rows per block."""
+    from ribotricer_b200 import _lib
+    from ribotricer_b200.metagene import metagene_sums
+
+    lib = _lib.load()
+    rng = np.random.default_rng(21)
+    for n, width in ((0, 0), (1, 1), (5, 7), (300, 620), (7000, 620), (5000, 33)):
+        lens = rng.integers(0, width + 1, n).astype(np.int64) if width else np.zeros(n, np.int64)
+        if n:
+            lens[rng.random(n) < 0.5] = width                    # most CDS reach the full width
+            width = int(lens.max())
+        ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        flat = (rng.random(int(ptr[-1])) < 0.2) * rng.integers(1, 50, int(ptr[-1]))
+        for i in np.flatnonzero(rng.random(n) < 0.2):            # ORFs without a single read
+            flat[ptr[i]:ptr[i + 1]] = 0
+        flat = flat.astype(np.int32)
+        got = metagene_sums(lib, flat, ptr, width)
+        want = _metagene_sums_numpy(flat, lens, width) if n else (np.zeros(0),) * 4
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got[3], want[3]), (n, width)
+        assert np.allclose(got[0], want[0], rtol=1e-12, atol=0) and np.allclose(got[2], want[2], rtol=1e-12, atol=0), (n, width)
+    import pytest
+    with pytest.raises(ValueError):
+        metagene_sums(lib, np.zeros(10, np.int32), np.array([0, 10], np.int64), 5)      # a row wider than the matrix
