@@ -522,6 +522,21 @@ def run_ours(args):
             "clocks": clocks.summary(),
             "translating": int(res["status"].sum()), "valid_reads": st_host["valid"],
         }
+        if world > 1 and args.scale == 1.0:
+            # The N > 1 runs split ONE C3 library; the default N = 1 run is C2 (the configuration the metric is quoted on),
+            # so value(N) / value(1) of the default lines compares two workloads.  The single-GPU figure of THIS workload,
+            # measured separately with `python bench.py --config <this>` and committed under profiles/, travels with the line.
+            try:
+                one = json.load(open(os.path.join(ROOT, "profiles", f"r2_bench_{args.config}_n1.json")))
+                if one.get("n_gpus") == 1 and one["config"]["orfs"] == n_orf_total and one["config"]["reads"] == n_reads_total:
+                    line["same_workload_n1"] = {
+                        "value": one["value"], "unit": one["unit"], "ms_per_step": one["ms_per_step"],
+                        "e2e_ms_per_step": one["e2e"]["ms_per_step"],
+                        "e2e_from_record_stream_ms_per_step": (one["e2e"].get("from_record_stream") or {}).get("ms_per_step"),
+                        "source": f"profiles/r2_bench_{args.config}_n1.json (python bench.py --config {args.config} on one B200, "
+                                  f"an earlier run: not measured in this process)"}
+            except Exception:
+                pass
         if world == 1 and not args.no_cpu_baseline:
             try:
                 rates, desc = cpu_reference_run(args.config, args.cpu_seconds)
