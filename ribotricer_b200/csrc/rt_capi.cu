@@ -1215,21 +1215,33 @@ namespace {
 
 // Work lists of the ORF range [lo, hi), cached per range: the ORF order for the scoring kernel and the
 // atoms the range touches for phase A.
-int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
-    for (auto& p : ctx->plans)
-        if (p.lo == lo && p.hi == hi) {
-            *out = &p;
-            return RT_OK;
-        }
+// What get_plan works out on the host for the ORFs [lo, hi) before anything touches the device: pure functions of the
+// index arrays of the ctx, so the part plans of rt_score_host can be built side by side.
+struct PlanHost {
+    int64_t lo = 0, hi = 0;
+    std::vector<int32_t> ids;                 // scoring order (two-phase path: windows sorted by reference count)
+    std::vector<rt::RefSegment> segs;         // segments of the ORFs with more than kSegRefs references
+    int n_long_orfs = 0;                      // ORFs cut into segments
+    int64_t n_long = 0;                       // scan path: ORFs above kPackMaxNt
+    std::vector<rt::PassDesc> passes;         // phase A
+    std::vector<int32_t> alist;               // atoms of the range, similar lengths adjacent
+    std::vector<rt::RefRec> refs;             // phase B slots
+    std::vector<rt::RefWarp> warps;
+    int n_long_b = 0;                         // ORFs with more than 32 references (phase B accumulators)
+};
+
+void build_plan_host(const rt_ctx* ctx, int64_t lo, int64_t hi, PlanHost& ph) {
     const int64_t n = hi - lo;
     const auto t_plan = std::chrono::steady_clock::now();
+    ph.lo = lo;
+    ph.hi = hi;
     const int64_t* np = ctx->nt_prefix.data();
     auto len_of = [np](int32_t x) { return np[x + 1] - np[x]; };
-    std::vector<int32_t> ids;
+    std::vector<int32_t>& ids = ph.ids;
     ids.reserve((size_t)n);
-    std::vector<rt::RefSegment> segs;
-    int n_long_orfs = 0;
-    int64_t n_long = 0;
+    std::vector<rt::RefSegment>& segs = ph.segs;
+    int& n_long_orfs = ph.n_long_orfs;
+    int64_t& n_long = ph.n_long;
     if (ctx->use_atoms) {
         // two-phase path: one thread per ORF walks its atom refs, so the ORFs sharing a warp should hold
         // similar numbers of refs; sort by that inside windows of the index (neighbours share atoms)
@@ -1287,19 +1299,6 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
             std::stable_sort(ids.begin() + begin, ids.end(), [&](int32_t x, int32_t y) { return len_of(x) > len_of(y); });
         }
     }
-    if (ctx->plans.size() >= 24) {   // bounded cache (rt_score_host keeps four part plans per range it is asked for)
-        cudaFree(ctx->plans.front().d_list);
-        cudaFree(ctx->plans.front().d_fallback);
-        cudaFree(ctx->plans.front().d_atom_list);
-        cudaFree(ctx->plans.front().d_segs);
-        cudaFree(ctx->plans.front().d_partials);
-        cudaFree(ctx->plans.front().d_seg_done);
-        cudaFree(ctx->plans.front().d_passes);
-        cudaFree(ctx->plans.front().d_refs);
-        cudaFree(ctx->plans.front().d_ref_warps);
-        cudaFree(ctx->plans.front().d_long_acc);
-        ctx->plans.erase(ctx->plans.begin());
-    }
     const bool plan_timing = getenv("RT_HOST_TIMING") != nullptr;
     auto t_mark = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
@@ -1309,23 +1308,6 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
         t_mark = now;
     };
     lap("ORF order");
-    rt_ctx::ScorePlan p;
-    p.lo = lo;
-    p.hi = hi;
-    p.n_long = n_long;
-    p.n_short = (int64_t)ids.size() - n_long;
-    p.n_segs = (int64_t)segs.size();
-    if (!segs.empty()) {
-        if (ctx->h_ref_ent.size() >= 0xffffffffull) return fail(ctx, RT_EINVAL, "rt_score: too many atom references for 32-bit segment offsets");
-        RT_CUDA(ctx, cudaMalloc(&p.d_segs, sizeof(rt::RefSegment) * segs.size()));
-        RT_CUDA(ctx, cudaMemcpy(p.d_segs, segs.data(), sizeof(rt::RefSegment) * segs.size(), cudaMemcpyHostToDevice));
-        RT_CUDA(ctx, cudaMalloc(&p.d_partials, sizeof(rt::ComposeAcc) * segs.size()));
-        RT_CUDA(ctx, cudaMalloc(&p.d_seg_done, sizeof(unsigned) * (size_t)n_long_orfs));
-        RT_CUDA(ctx, cudaMemset(p.d_seg_done, 0, sizeof(unsigned) * (size_t)n_long_orfs));
-    }
-    RT_CUDA(ctx, cudaMalloc(&p.d_list, sizeof(int32_t) * std::max<int64_t>(1, n)));
-    RT_CUDA(ctx, cudaMalloc(&p.d_fallback, sizeof(int32_t) * std::max<int64_t>(1, n)));
-    if (!ids.empty()) RT_CUDA(ctx, cudaMemcpy(p.d_list, ids.data(), sizeof(int32_t) * ids.size(), cudaMemcpyHostToDevice));
     {   // atoms the ORFs of the range refer to; sorted by length inside windows so that the four atoms of
         // a warp are balanced while genomic neighbours stay close in time
         std::vector<uint8_t> used((size_t)ctx->n_atoms, 0);
@@ -1335,11 +1317,11 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
             for (uint64_t k = b; k < b + c; ++k)
                 if (ctx->h_ref_atom[k] != 0xffffffffu) used[ctx->h_ref_atom[k]] = 1;
         }
-        std::vector<int32_t> alist;
+        std::vector<int32_t>& alist = ph.alist;
         for (int64_t a = 0; a < ctx->n_atoms; ++a)
             if (used[a]) alist.push_back((int32_t)a);
         {   // passes of the streamed phase A: consecutive atom ids are adjacent in the compact buffer
-            std::vector<rt::PassDesc> passes;
+            std::vector<rt::PassDesc>& passes = ph.passes;
             const uint64_t* ac = ctx->h_atoms_c.data();
             size_t i = 0;
             while (i < alist.size()) {
@@ -1357,10 +1339,6 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
                 const uint64_t s0 = ac[a0] >> rt::kLenBits, q0 = s0 & ~3ull, q1 = (s0 + slots + 3) & ~3ull;
                 passes.push_back({a0, n | ((uint32_t)((q1 - q0) >> 2) << 8), (uint32_t)(q0 >> 2), (uint32_t)(s0 - q0)});
             }
-            p.n_passes = (int64_t)passes.size();
-            RT_CUDA(ctx, cudaMalloc(&p.d_passes, sizeof(rt::PassDesc) * std::max<size_t>(1, passes.size())));
-            if (!passes.empty())
-                RT_CUDA(ctx, cudaMemcpy(p.d_passes, passes.data(), sizeof(rt::PassDesc) * passes.size(), cudaMemcpyHostToDevice));
         }
         constexpr size_t kAtomWindow = 4096;
         for (size_t w0 = 0; w0 < alist.size(); w0 += kAtomWindow) {
@@ -1369,10 +1347,6 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
                 return (ctx->h_atoms[x] & rt::kLenMask) > (ctx->h_atoms[y] & rt::kLenMask);
             });
         }
-        p.n_atom_list = (int64_t)alist.size();
-        RT_CUDA(ctx, cudaMalloc(&p.d_atom_list, sizeof(int32_t) * std::max<size_t>(1, alist.size())));
-        if (!alist.empty())
-            RT_CUDA(ctx, cudaMemcpy(p.d_atom_list, alist.data(), sizeof(int32_t) * alist.size(), cudaMemcpyHostToDevice));
     }
     lap("atom list + passes");
     if (ctx->use_atoms) {
@@ -1382,11 +1356,11 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
         // proper suffix of it (a child) is just marked on the slot where it starts.  compose_refs_kernel forms
         // suffix sums over the parent's slots, so every reference is visited once per family instead of once per ORF.
         // Families never straddle a group of 32 slots; ORFs with more than 32 references stay alone and fill whole groups.
-        std::vector<rt::RefRec> refs;
-        std::vector<rt::RefWarp> warps;
+        std::vector<rt::RefRec>& refs = ph.refs;
+        std::vector<rt::RefWarp>& warps = ph.warps;
         refs.reserve((size_t)(ctx->h_ref_ent.size() / std::max<int64_t>(1, ctx->n_orf) * n * 3 / 4 + 64));
         const rt::RefRec pad_rec{0xffffffffu, 0u, 0u, -1};
-        int n_long = 0;
+        int& n_long = ph.n_long_b;
         auto pad_group = [&]() {
             while (refs.size() % 32) refs.push_back(pad_rec);
             warps.resize(refs.size() / 32, rt::RefWarp{-1, 0, -1, 0});
@@ -1492,6 +1466,60 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
         }
         pad_group();
         lap("slot layout");
+    }
+    if (plan_timing)
+        fprintf(stderr, "get_plan [%lld, %lld): %.1f ms on the host\n", (long long)lo, (long long)hi,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan).count());
+}
+
+// The device side of a plan: the host arrays of `ph` uploaded, the plan entered into the (bounded) cache of the ctx.
+int upload_plan(rt_ctx* ctx, PlanHost& ph, rt_ctx::ScorePlan** out) {
+    const int64_t lo = ph.lo, hi = ph.hi, n = hi - lo;
+    const std::vector<int32_t>& ids = ph.ids;
+    const std::vector<rt::RefSegment>& segs = ph.segs;
+    const int n_long_orfs = ph.n_long_orfs;
+    if (ctx->plans.size() >= 24) {   // bounded cache (rt_score_host keeps four part plans per range it is asked for)
+        cudaFree(ctx->plans.front().d_list);
+        cudaFree(ctx->plans.front().d_fallback);
+        cudaFree(ctx->plans.front().d_atom_list);
+        cudaFree(ctx->plans.front().d_segs);
+        cudaFree(ctx->plans.front().d_partials);
+        cudaFree(ctx->plans.front().d_seg_done);
+        cudaFree(ctx->plans.front().d_passes);
+        cudaFree(ctx->plans.front().d_refs);
+        cudaFree(ctx->plans.front().d_ref_warps);
+        cudaFree(ctx->plans.front().d_long_acc);
+        ctx->plans.erase(ctx->plans.begin());
+    }
+    rt_ctx::ScorePlan p;
+    p.lo = lo;
+    p.hi = hi;
+    p.n_long = ph.n_long;
+    p.n_short = (int64_t)ids.size() - ph.n_long;
+    p.n_segs = (int64_t)segs.size();
+    if (!segs.empty()) {
+        if (ctx->h_ref_ent.size() >= 0xffffffffull) return fail(ctx, RT_EINVAL, "rt_score: too many atom references for 32-bit segment offsets");
+        RT_CUDA(ctx, cudaMalloc(&p.d_segs, sizeof(rt::RefSegment) * segs.size()));
+        RT_CUDA(ctx, cudaMemcpy(p.d_segs, segs.data(), sizeof(rt::RefSegment) * segs.size(), cudaMemcpyHostToDevice));
+        RT_CUDA(ctx, cudaMalloc(&p.d_partials, sizeof(rt::ComposeAcc) * segs.size()));
+        RT_CUDA(ctx, cudaMalloc(&p.d_seg_done, sizeof(unsigned) * (size_t)n_long_orfs));
+        RT_CUDA(ctx, cudaMemset(p.d_seg_done, 0, sizeof(unsigned) * (size_t)n_long_orfs));
+    }
+    RT_CUDA(ctx, cudaMalloc(&p.d_list, sizeof(int32_t) * std::max<int64_t>(1, n)));
+    RT_CUDA(ctx, cudaMalloc(&p.d_fallback, sizeof(int32_t) * std::max<int64_t>(1, n)));
+    if (!ids.empty()) RT_CUDA(ctx, cudaMemcpy(p.d_list, ids.data(), sizeof(int32_t) * ids.size(), cudaMemcpyHostToDevice));
+    p.n_passes = (int64_t)ph.passes.size();
+    RT_CUDA(ctx, cudaMalloc(&p.d_passes, sizeof(rt::PassDesc) * std::max<size_t>(1, ph.passes.size())));
+    if (!ph.passes.empty())
+        RT_CUDA(ctx, cudaMemcpy(p.d_passes, ph.passes.data(), sizeof(rt::PassDesc) * ph.passes.size(), cudaMemcpyHostToDevice));
+    p.n_atom_list = (int64_t)ph.alist.size();
+    RT_CUDA(ctx, cudaMalloc(&p.d_atom_list, sizeof(int32_t) * std::max<size_t>(1, ph.alist.size())));
+    if (!ph.alist.empty())
+        RT_CUDA(ctx, cudaMemcpy(p.d_atom_list, ph.alist.data(), sizeof(int32_t) * ph.alist.size(), cudaMemcpyHostToDevice));
+    if (ctx->use_atoms) {
+        const std::vector<rt::RefRec>& refs = ph.refs;
+        const std::vector<rt::RefWarp>& warps = ph.warps;
+        const int n_long = ph.n_long_b;
         p.n_ref_warps = (int64_t)warps.size();
         RT_CUDA(ctx, cudaMalloc(&p.d_refs, sizeof(rt::RefRec) * std::max<size_t>(1, refs.size())));
         RT_CUDA(ctx, cudaMalloc(&p.d_ref_warps, sizeof(rt::RefWarp) * std::max<size_t>(1, warps.size())));
@@ -1505,11 +1533,49 @@ int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
         RT_CUDA(ctx, cudaMalloc(&p.d_long_acc, sizeof(rt::LongAcc) * acc.size()));
         RT_CUDA(ctx, cudaMemcpy(p.d_long_acc, acc.data(), sizeof(rt::LongAcc) * acc.size(), cudaMemcpyHostToDevice));
     }
-    if (getenv("RT_HOST_TIMING"))
-        fprintf(stderr, "get_plan [%lld, %lld): %.1f ms\n", (long long)lo, (long long)hi,
-                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan).count());
     ctx->plans.push_back(p);
     *out = &ctx->plans.back();
+    return RT_OK;
+}
+
+int get_plan(rt_ctx* ctx, int64_t lo, int64_t hi, rt_ctx::ScorePlan** out) {
+    for (auto& p : ctx->plans)
+        if (p.lo == lo && p.hi == hi) {
+            *out = &p;
+            return RT_OK;
+        }
+    PlanHost ph;
+    build_plan_host(ctx, lo, hi, ph);
+    return upload_plan(ctx, ph, out);
+}
+
+// The plans of several ranges at once (the parts of rt_score_host): the host halves are built side by side, one thread per
+// range that is not in the cache yet; the uploads follow one after the other in range order.
+int prebuild_plans(rt_ctx* ctx, const std::vector<int64_t>& cut) {
+    std::vector<PlanHost> todo;
+    for (size_t i = 0; i + 1 < cut.size(); ++i) {
+        const int64_t a = cut[i], b = cut[i + 1];
+        bool cached = a == b;
+        for (auto& p : ctx->plans) cached = cached || (p.lo == a && p.hi == b);
+        if (!cached) {
+            todo.emplace_back();
+            todo.back().lo = a;
+            todo.back().hi = b;
+        }
+    }
+    if (todo.size() < 2) return RT_OK;           // get_plan does a single one just as well
+    {
+        std::vector<std::thread> pool;
+        for (size_t k = 1; k < todo.size(); ++k)
+            pool.emplace_back([ctx, &todo, k]() { build_plan_host(ctx, todo[k].lo, todo[k].hi, todo[k]); });
+        build_plan_host(ctx, todo[0].lo, todo[0].hi, todo[0]);
+        for (auto& th : pool) th.join();
+    }
+    for (PlanHost& ph : todo) {
+        rt_ctx::ScorePlan* unused = nullptr;
+        const int rc = upload_plan(ctx, ph, &unused);
+        if (rc != RT_OK) return rc;
+    }
     return RT_OK;
 }
 
@@ -1724,6 +1790,10 @@ int rt_score_host(rt_ctx* ctx, const int32_t* d_cov, int64_t orf_lo, int64_t orf
     for (int i = 1; i < n_parts; ++i) {
         const int64_t target = bp[orf_lo] + (bp[orf_hi] - bp[orf_lo]) * i / n_parts;
         cut[(size_t)i] = std::max<int64_t>(cut[(size_t)i - 1], std::lower_bound(bp + orf_lo, bp + orf_hi, target) - bp);
+    }
+    if (n_parts > 1) {                 // the parts' plans that are not cached yet: host halves built side by side
+        const int rc = prebuild_plans(ctx, cut);
+        if (rc != RT_OK) return rc;
     }
     if (!ctx->slot_stream[0]) RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[0], cudaStreamNonBlocking));
     cudaStream_t copy = n_parts > 1 ? ctx->slot_stream[0] : nullptr;
