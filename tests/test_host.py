@@ -796,3 +796,85 @@ def test_metagene_sums_match_the_matrix_statement(built):
     import pytest
     with pytest.raises(ValueError):
         metagene_sums(lib, np.zeros(10, np.int32), np.array([0, 10], np.int64), 5)      # a row wider than the matrix
+
+
+def test_metagene_host_logic_against_reference_golden(built, tmp_path, monkeypatch):
+    """The host side of the P-site offset inference on the CPU: metagene_coverage (windows of the annotated ORFs, rows
+    normalised and summed by rt_metagene_sums, profile assembly, the two profile files) and align_metagenes, against
+    what the UNMODIFIED reference returned for the same library (tests/golden/metagene_case).  The three device calls
+    of the step -- K1 per read length, K4 over the windows, phasescore of a float profile -- are stood in for by the
+    oracle (the GPU twin of this test is test_gpu_api.py::test_metagene_and_offset_inference)."""
+    from helpers import SCORE_TOL, alignments_to_reads, load_golden
+    from oracle import c_oracle as CO
+    from oracle import oracle_py as O
+    from ribotricer_b200 import _lib
+    from ribotricer_b200 import detect_orfs as D
+    from ribotricer_b200 import metagene as mg
+    from ribotricer_b200 import statistics as S
+    from ribotricer_b200.const import DEFAULT_PAD
+
+    case = load_golden("metagene_case.json.gz")["case"]
+    names = [c[0] for c in case["contigs"]]
+    cols = alignments_to_reads(case, names)
+
+    class OracleEngine:
+        """What metagene_coverage asks of an Engine, answered by the C oracle on host arrays."""
+
+        def __init__(self):
+            self.contig_names, self.contig_len, self.pad = names, np.array([c[1] for c in case["contigs"]], np.int64), DEFAULT_PAD
+            self.contig_base, self.plane = CO.genome_layout(self.contig_len, self.pad)
+            self.lib, self.device_index, self.ctx, self.index = _lib.load(), 0, object(), None
+
+        def ensure_dense(self):
+            pass
+
+        def contig_id(self, chrom):
+            return names.index(chrom) if chrom in names else -1
+
+        def new_coverage(self):
+            return np.zeros(2 * self.plane, np.int32)
+
+        def set_index(self, ptr, st, en, contig, strand):
+            self.index = dict(exon_ptr=ptr, exon_start=st, exon_end=en, orf_contig=contig, orf_strand=strand)
+
+        def gather_profiles(self, cov, sel, lens):
+            ptr, flat = CO.gather_profiles(self.index, sel, cov, self.contig_base, self.contig_len, self.pad, self.plane)
+            assert (np.diff(ptr) == lens).all()
+            return ptr, flat
+
+    class OracleAlignments:
+        def __init__(self, eng):
+            self.engine = eng
+
+        def bin_into(self, cov, psite_offsets, weight=1):
+            if weight == -1:                 # the step bins a length again with weight -1 to empty its scratch buffer
+                cov[:] = 0
+                return
+            e = self.engine
+            CO.bin_reads(cols, 0, CO.make_len_table(psite_offsets, None), e.contig_base, e.contig_len, e.pad, e.plane, cov=cov)
+
+    eng = OracleEngine()
+    eng._aux = OracleEngine()                # detect_orfs._aux_engine reuses it: same genome, a ctx that is "alive"
+    monkeypatch.setattr(S, "phasescore", lambda values, engine=None: O.phasescore_scipy(list(values)))
+    idx_path = tmp_path / "mg_index.tsv"
+    idx_path.write_text("\n".join(case["index"]) + "\n")
+    prefix = str(tmp_path / "mg")
+    annotated, _ = D.parse_ribotricer_index(str(idx_path))
+    assert len(annotated) == len(case["index"]) - 1
+    rlc = {int(k): v for k, v in sorted(case["read_length_counts_in"].items(), key=lambda kv: int(kv[0]))}
+    metagenes = mg.metagene_coverage(annotated, OracleAlignments(eng), rlc, prefix, meta_min_reads=case["meta_min_reads"])
+    assert list(rlc) == case["kept_lengths"]
+    for length, ref in case["metagenes"].items():
+        m = metagenes[int(length)]
+        assert m[0][0] == ref["idx5"] and m[1][0] == ref["idx3"]
+        assert np.allclose(m[0][1], ref["prof5"], rtol=0, atol=1e-9) and np.allclose(m[1][1], ref["prof3"], rtol=0, atol=1e-9)
+        assert abs(m[2] - ref["ps5"]) <= SCORE_TOL and m[3] == ref["v5"]
+        assert abs(m[4] - ref["ps3"]) <= SCORE_TOL and m[5] == ref["v3"]
+    got_rows = open(f"{prefix}_metagene_profiles_5p.tsv").read().split("\n")
+    want_rows = case["profiles_5p_tsv"].split("\n")
+    assert len(got_rows) == len(want_rows) and got_rows[0] == want_rows[0]
+    for g, w in zip(got_rows[1:], want_rows[1:]):
+        assert g.split("\t")[:2] == w.split("\t")[:2]
+    offsets = mg.align_metagenes(metagenes, rlc, prefix, 0.428571428571, True)
+    assert {str(k): v for k, v in offsets.items()} == case["psite_offsets"]
+    assert open(f"{prefix}_psite_offsets.txt").read() == case["psite_offsets_txt"]
