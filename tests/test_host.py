@@ -801,68 +801,29 @@ def test_metagene_sums_match_the_matrix_statement(built):
 def test_metagene_host_logic_against_reference_golden(built, tmp_path, monkeypatch):
     """The host side of the P-site offset inference on the CPU: metagene_coverage (windows of the annotated ORFs, rows
     normalised and summed by rt_metagene_sums, profile assembly, the two profile files) and align_metagenes, against
-    what the UNMODIFIED reference returned for the same library (tests/golden/metagene_case).  The three device calls
-    of the step -- K1 per read length, K4 over the windows, phasescore of a float profile -- are stood in for by the
-    oracle (the GPU twin of this test is test_gpu_api.py::test_metagene_and_offset_inference)."""
+    what the UNMODIFIED reference returned for the same library (tests/golden/metagene_case).  The device calls of the
+    step -- K1 per read length, K4 over the windows, phasescore of a float profile -- are stood in for by the oracle
+    (tests/oracle_engine.py; the GPU twin of this test is test_gpu_api.py::test_metagene_and_offset_inference)."""
     from helpers import SCORE_TOL, alignments_to_reads, load_golden
-    from oracle import c_oracle as CO
-    from oracle import oracle_py as O
-    from ribotricer_b200 import _lib
+    from oracle_engine import install
     from ribotricer_b200 import detect_orfs as D
     from ribotricer_b200 import metagene as mg
-    from ribotricer_b200 import statistics as S
-    from ribotricer_b200.const import DEFAULT_PAD
+    from ribotricer_b200.bam import ReadColumns, split_bam
 
     case = load_golden("metagene_case.json.gz")["case"]
     names = [c[0] for c in case["contigs"]]
-    cols = alignments_to_reads(case, names)
-
-    class OracleEngine:
-        """What metagene_coverage asks of an Engine, answered by the C oracle on host arrays."""
-
-        def __init__(self):
-            self.contig_names, self.contig_len, self.pad = names, np.array([c[1] for c in case["contigs"]], np.int64), DEFAULT_PAD
-            self.contig_base, self.plane = CO.genome_layout(self.contig_len, self.pad)
-            self.lib, self.device_index, self.ctx, self.index = _lib.load(), 0, object(), None
-
-        def ensure_dense(self):
-            pass
-
-        def contig_id(self, chrom):
-            return names.index(chrom) if chrom in names else -1
-
-        def new_coverage(self):
-            return np.zeros(2 * self.plane, np.int32)
-
-        def set_index(self, ptr, st, en, contig, strand):
-            self.index = dict(exon_ptr=ptr, exon_start=st, exon_end=en, orf_contig=contig, orf_strand=strand)
-
-        def gather_profiles(self, cov, sel, lens):
-            ptr, flat = CO.gather_profiles(self.index, sel, cov, self.contig_base, self.contig_len, self.pad, self.plane)
-            assert (np.diff(ptr) == lens).all()
-            return ptr, flat
-
-    class OracleAlignments:
-        def __init__(self, eng):
-            self.engine = eng
-
-        def bin_into(self, cov, psite_offsets, weight=1):
-            if weight == -1:                 # the step bins a length again with weight -1 to empty its scratch buffer
-                cov[:] = 0
-                return
-            e = self.engine
-            CO.bin_reads(cols, 0, CO.make_len_table(psite_offsets, None), e.contig_base, e.contig_len, e.pad, e.plane, cov=cov)
-
-    eng = OracleEngine()
-    eng._aux = OracleEngine()                # detect_orfs._aux_engine reuses it: same genome, a ctx that is "alive"
-    monkeypatch.setattr(S, "phasescore", lambda values, engine=None: O.phasescore_scipy(list(values)))
+    case = dict(case, alignments=sorted(case["alignments"], key=lambda a: a[0]))     # read_length_counts insertion order
+    reads = ReadColumns(names, np.array([c[1] for c in case["contigs"]], np.int64), alignments_to_reads(case, names))
+    eng = install(monkeypatch)
     idx_path = tmp_path / "mg_index.tsv"
     idx_path.write_text("\n".join(case["index"]) + "\n")
     prefix = str(tmp_path / "mg")
     annotated, _ = D.parse_ribotricer_index(str(idx_path))
     assert len(annotated) == len(case["index"]) - 1
-    rlc = {int(k): v for k, v in sorted(case["read_length_counts_in"].items(), key=lambda kv: int(kv[0]))}
-    metagenes = mg.metagene_coverage(annotated, OracleAlignments(eng), rlc, prefix, meta_min_reads=case["meta_min_reads"])
+    alignments, rlc = split_bam(reads, "forward", prefix, None, engine=eng)
+    assert {str(k): v for k, v in rlc.items()} == case["read_length_counts_in"]
+    rlc = dict(sorted(rlc.items()))
+    metagenes = mg.metagene_coverage(annotated, alignments, rlc, prefix, meta_min_reads=case["meta_min_reads"])
     assert list(rlc) == case["kept_lengths"]
     for length, ref in case["metagenes"].items():
         m = metagenes[int(length)]
@@ -878,3 +839,66 @@ def test_metagene_host_logic_against_reference_golden(built, tmp_path, monkeypat
     offsets = mg.align_metagenes(metagenes, rlc, prefix, 0.428571428571, True)
     assert {str(k): v for k, v in offsets.items()} == case["psite_offsets"]
     assert open(f"{prefix}_psite_offsets.txt").read() == case["psite_offsets_txt"]
+    # the whole default-flag call: protocol, read lengths and offsets inferred on the way
+    D.detect_orfs(reads, str(idx_path), prefix, None, None, None, 0.428571428571, 5, 0, 0, 0.0, True,
+                  meta_min_reads=case["meta_min_reads"])
+    assert open(f"{prefix}_protocol.txt").read().startswith("In total")
+    assert open(f"{prefix}_psite_offsets.txt").read() == case["psite_offsets_txt"]
+    rows = open(f"{prefix}_translating_ORFs.tsv").read().split("\n")
+    assert len(rows) == len(case["index"]) + 1
+    assert sum(1 for r in rows[1:] if r.split("\t")[2:3] == ["translating"]) > 0.5 * (len(case["index"]) - 1)
+
+
+def test_detect_orfs_host_flow_against_reference_golden(built, tmp_path, monkeypatch):
+    """detect_orfs() from end to end on the CPU with the device calls stood in for by the oracle (tests/oracle_engine.py):
+    what is under test is the HOST flow of the product -- index loader, split_bam bookkeeping and summary file, the metagene
+    step, the dense -> compact hand-over, row selection and chunking of write_tsv, the native TSV / WIG writers -- against
+    the files the unmodified reference wrote for the same inputs (four parameter sets per case).  GPU twin:
+    test_gpu_api.py::test_detect_orfs_end_to_end."""
+    from helpers import SCORE_TOL, alignments_to_reads, load_golden
+    from oracle import oracle_py as O
+    from oracle_engine import install
+    from ribotricer_b200 import detect_orfs as D
+    from ribotricer_b200.bam import ReadColumns
+
+    eng = install(monkeypatch)
+    for case in load_golden("pipeline_cases.json.gz")["cases"]:
+        names = [c[0] for c in case["contigs"]]
+        reads = ReadColumns(names, np.array([c[1] for c in case["contigs"]], np.int64), alignments_to_reads(case, names))
+        idx_path = tmp_path / f"{case['name']}_index.tsv"
+        idx_path.write_text("\n".join(case["index"]) + "\n")
+        offsets = {int(k): v for k, v in case["psite_offsets"].items()}
+        for run in case["tsv"]:
+            prm = run["params"]
+            prefix = str(tmp_path / "out" / case["name"])
+            eng.calls.clear()
+            D.detect_orfs(reads, str(idx_path), prefix, "forward", None, dict(offsets), prm["phase_score_cutoff"],
+                          prm["min_valid_codons"], prm["min_reads_per_codon"], prm["min_valid_codons_ratio"],
+                          prm["min_density_over_orf"], prm["report_all"], meta_min_reads=10 ** 9)
+            assert "compact_from_dense" in eng.calls and "score_host" in eng.calls      # scored in the compact layout
+            split = lambda text: {r.split("\t")[0]: r.split("\t") for r in text.split("\n")[1:] if r}     # noqa: E731
+            got_text = open(f"{prefix}_translating_ORFs.tsv").read()
+            assert got_text.split("\n")[0] == run["text"].split("\n")[0]
+            got, ref = split(got_text), split(run["text"])
+            assert [k for k in got if k in ref] == [k for k in ref if k in got]          # ORF ordering
+            n_exc = 0
+            for oid, r in ref.items():
+                tie = O.is_frame_tie(O.frame_spectra(eval(r[17])))
+                near = abs(float(r[3]) - prm["phase_score_cutoff"]) <= SCORE_TOL
+                if oid not in got:
+                    assert tie or near, oid
+                    n_exc += 1
+                    continue
+                g = got[oid]
+                assert abs(float(g[3]) - float(r[3])) <= SCORE_TOL
+                cols = [0, 1, 4, 5, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17]
+                if not tie:
+                    cols += [6, 7] + ([2] if not near else [])
+                for c in cols:
+                    assert g[c] == r[c], (case["name"], oid, c, g[c], r[c])
+            n_exc += sum(1 for oid in got if oid not in ref)
+            assert n_exc <= max(2, len(ref) // 20)
+        for tag, text in case["wig"].items():
+            assert open(f"{prefix}_{tag}.wig").read() == text
+        summary = open(f"{prefix}_bam_summary.txt").read()
+        assert summary.startswith(f"summary:\n\ttotal_reads: {len(reads)}\n\tunique_mapped: {len(reads)}\n")
