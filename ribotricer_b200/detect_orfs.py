@@ -267,6 +267,17 @@ def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: i
             raise OSError(lib.rt_io_last_error().decode())
         cols = {k: np.ascontiguousarray(view[k]) for k in ("score", "valid", "count", "length", "status")}
         p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        # the rows of a chunk are formatted (rt_tsv_write: all host cores, the GIL released) on a helper thread while this
+        # thread gathers the profiles of the next chunk on the GPU; one chunk in flight, rows stay in order
+        from concurrent.futures import ThreadPoolExecutor
+
+        formatter, in_flight = ThreadPoolExecutor(1), None
+
+        def emit(sel, ptr, prof):
+            rc = lib.rt_tsv_write(handle, idx.handle, len(sel), p(sel), int(lo), p(cols["score"]), p(cols["valid"]),
+                                  p(cols["count"]), p(cols["length"]), p(cols["status"]), p(ptr), p(prof))
+            if rc != 0:       # the message is thread-local in the library: read it on this thread
+                raise OSError(f"rt_tsv_write failed ({rc}): {lib.rt_io_last_error().decode()}")
     else:
         out = open(path, "w")
         if write_header:
@@ -280,11 +291,9 @@ def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: i
             sel = np.ascontiguousarray(keep[at:at + n_take], np.int64)
             ptr, prof = eng.gather_profiles(merged.cov, sel - lo + res_offset, length[sel - lo])
             if native:
-                prof = np.ascontiguousarray(prof, np.int32)
-                rc = lib.rt_tsv_write(handle, idx.handle, len(sel), p(sel), int(lo), p(cols["score"]), p(cols["valid"]),
-                                      p(cols["count"]), p(cols["length"]), p(cols["status"]), p(ptr), p(prof))
-                if rc != 0:
-                    raise OSError(f"rt_tsv_write failed ({rc}): {lib.rt_io_last_error().decode()}")
+                if in_flight is not None:
+                    in_flight.result()
+                in_flight = formatter.submit(emit, sel, np.ascontiguousarray(ptr, np.int64), np.ascontiguousarray(prof, np.int32))
             else:
                 rows = []
                 for j, o in enumerate(sel.tolist()):
@@ -299,13 +308,17 @@ def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: i
                         str(prof[ptr[j]:ptr[j + 1]].tolist()))))
                 out.write("\n".join(rows) + "\n")
             at += n_take
+        if native and in_flight is not None:
+            in_flight.result()
     except BaseException:
         if native:
+            formatter.shutdown(wait=True)       # never close the file under a chunk that is still being formatted
             lib.rt_tsv_close(handle)
         else:
             out.close()
         raise
     if native:
+        formatter.shutdown(wait=True)
         if lib.rt_tsv_close(handle) != 0:       # the file has a write-behind thread: a failed write shows up here
             raise OSError(f"cannot write {path}: {lib.rt_io_last_error().decode()}")
     else:

@@ -902,3 +902,15 @@ def test_detect_orfs_host_flow_against_reference_golden(built, tmp_path, monkeyp
             assert open(f"{prefix}_{tag}.wig").read() == text
         summary = open(f"{prefix}_bam_summary.txt").read()
         assert summary.startswith(f"summary:\n\ttotal_reads: {len(reads)}\n\tunique_mapped: {len(reads)}\n")
+        # the same call with the rows cut into many small chunks (one being formatted on the helper thread while the next
+        # is gathered): the file must not change
+        one_chunk = open(f"{prefix}_translating_ORFs.tsv", "rb").read()
+        whole = D.write_tsv
+        eng.calls.clear()
+        with monkeypatch.context() as m:
+            m.setattr(D, "write_tsv", lambda *a, **k: whole(*a, **dict(k, chunk_nt=1)))         # one row per chunk
+            D.detect_orfs(reads, str(idx_path), prefix + "_chunks", "forward", None, dict(offsets), prm["phase_score_cutoff"],
+                          prm["min_valid_codons"], prm["min_reads_per_codon"], prm["min_valid_codons_ratio"],
+                          prm["min_density_over_orf"], prm["report_all"], meta_min_reads=10 ** 9)
+        assert eng.calls.count("gather_profiles") == max(1, one_chunk.count(b"\n") - 1)
+        assert open(f"{prefix}_chunks_translating_ORFs.tsv", "rb").read() == one_chunk
