@@ -914,3 +914,15 @@ def test_detect_orfs_host_flow_against_reference_golden(built, tmp_path, monkeyp
                           prm["min_density_over_orf"], prm["report_all"], meta_min_reads=10 ** 9)
         assert eng.calls.count("gather_profiles") == max(1, one_chunk.count(b"\n") - 1)
         assert open(f"{prefix}_chunks_translating_ORFs.tsv", "rb").read() == one_chunk
+        # and from a BAM file of the same reads (native decoder -> columns -> the same flow)
+        import bam_writer as W
+        c = reads.cols
+        recs = [W.record(int(c["ref_id"][i]), int(c["first"][i]), 255, int(c["flag"][i]), [("M", int(c["mlen"][i]))],
+                         name=b"r%d" % i, aux=W.aux_field("NH", "C", 1)) for i in range(len(reads))]
+        bam_path = tmp_path / f"{case['name']}.bam"
+        W.write_bam(str(bam_path), [(n, int(ln)) for n, ln in zip(names, reads.contig_len)], recs, sorted_header=False)
+        D.detect_orfs(str(bam_path), str(idx_path), prefix + "_bam", "forward", None, dict(offsets), prm["phase_score_cutoff"],
+                      prm["min_valid_codons"], prm["min_reads_per_codon"], prm["min_valid_codons_ratio"],
+                      prm["min_density_over_orf"], prm["report_all"], meta_min_reads=10 ** 9)
+        assert open(f"{prefix}_bam_translating_ORFs.tsv", "rb").read() == one_chunk
+        assert open(f"{prefix}_bam_bam_summary.txt").read() == summary
