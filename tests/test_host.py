@@ -926,3 +926,51 @@ def test_detect_orfs_host_flow_against_reference_golden(built, tmp_path, monkeyp
                       prm["min_density_over_orf"], prm["report_all"], meta_min_reads=10 ** 9)
         assert open(f"{prefix}_bam_translating_ORFs.tsv", "rb").read() == one_chunk
         assert open(f"{prefix}_bam_bam_summary.txt").read() == summary
+
+
+def test_cli_detect_orfs_end_to_end_on_the_cpu_twin(built, tmp_path, monkeypatch):
+    """`ribotricer detect-orfs` flags -> detect_orfs() arguments -> files (cli.py:132-289), driven through click on a BAM
+    file: --stranded yes, --read_lengths / --psite_offsets, the five thresholds and --report_all must give the TSV that the
+    Python call with the same values gives (itself held to the reference's golden files above); --stranded reverse must
+    change the result."""
+    from click.testing import CliRunner
+
+    import bam_writer as W
+    from helpers import alignments_to_reads, load_golden
+    from oracle_engine import install
+    from ribotricer_b200 import detect_orfs as D
+    from ribotricer_b200.bam import ReadColumns
+    from ribotricer_b200.cli import cli
+
+    install(monkeypatch)
+    case = load_golden("pipeline_cases.json.gz")["cases"][0]
+    names = [c[0] for c in case["contigs"]]
+    cols = alignments_to_reads(case, names)
+    reads = ReadColumns(names, np.array([c[1] for c in case["contigs"]], np.int64), cols)
+    recs = [W.record(int(cols["ref_id"][i]), int(cols["first"][i]), 255, int(cols["flag"][i]), [("M", int(cols["mlen"][i]))],
+                     name=b"r%d" % i, aux=W.aux_field("NH", "C", 1)) for i in range(len(reads))]
+    bam = tmp_path / "lib.bam"
+    W.write_bam(str(bam), [(n, int(ln)) for n, ln in zip(names, reads.contig_len)], recs, sorted_header=False)
+    idx_path = tmp_path / "index.tsv"
+    idx_path.write_text("\n".join(case["index"]) + "\n")
+    offsets = {int(k): v for k, v in case["psite_offsets"].items()}
+    lengths = sorted(offsets)
+    base = ["detect-orfs", "--bam", str(bam), "--ribotricer_index", str(idx_path), "--read_lengths", ",".join(map(str, lengths)),
+            "--psite_offsets", ",".join(str(offsets[k]) for k in lengths), "--meta-min-reads", str(10 ** 9)]
+    for run in case["tsv"]:
+        prm = run["params"]
+        flags = ["--phase_score_cutoff", repr(prm["phase_score_cutoff"]), "--min_valid_codons", str(prm["min_valid_codons"]),
+                 "--min_reads_per_codon", str(int(prm["min_reads_per_codon"])), "--min_valid_codons_ratio",
+                 repr(prm["min_valid_codons_ratio"]), "--min_read_density", repr(prm["min_density_over_orf"])]
+        if prm["report_all"]:
+            flags.append("--report_all")
+        r = CliRunner().invoke(cli, base + ["--prefix", str(tmp_path / "cli"), "--stranded", "yes"] + flags)
+        assert r.exit_code == 0, (r.output, r.exception)
+        D.detect_orfs(reads, str(idx_path), str(tmp_path / "api"), "forward", lengths, dict(offsets), prm["phase_score_cutoff"],
+                      prm["min_valid_codons"], int(prm["min_reads_per_codon"]), prm["min_valid_codons_ratio"],
+                      prm["min_density_over_orf"], prm["report_all"], meta_min_reads=10 ** 9)
+        for suffix in ("_translating_ORFs.tsv", "_bam_summary.txt", "_pos.wig"):
+            assert open(str(tmp_path / "cli") + suffix, "rb").read() == open(str(tmp_path / "api") + suffix, "rb").read(), suffix
+    r = CliRunner().invoke(cli, base + ["--prefix", str(tmp_path / "rev"), "--stranded", "reverse", "--report_all"])
+    assert r.exit_code == 0, (r.output, r.exception)
+    assert open(str(tmp_path / "rev") + "_translating_ORFs.tsv", "rb").read() != open(str(tmp_path / "cli") + "_translating_ORFs.tsv", "rb").read()
