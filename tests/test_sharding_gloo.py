@@ -133,3 +133,67 @@ def test_shard_plan_and_read_slices():
     plan = multi_gpu.shard_plan(shuffled["exon_ptr"], shuffled["exon_start"], shuffled["exon_end"], shuffled["orf_contig"], 4,
                                 max_runs_per_shard=8)
     assert all(len(s.runs) <= 1 for s in plan) and sum(len(s.rows) for s in plan) == idx.n_orf
+
+
+SHARDED_WORKER = r'''
+import os, sys
+ROOT, out_dir = sys.argv[1], sys.argv[2]
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch.distributed as dist
+from helpers import alignments_to_reads, load_golden
+from oracle import oracle_py as O
+from oracle_engine import OracleEngine
+from ribotricer_b200 import detect_orfs as D, multi_gpu, statistics as S
+from ribotricer_b200.bam import ReadColumns
+
+dist.init_process_group("gloo")
+rank, size = dist.get_rank(), dist.get_world_size()
+eng = OracleEngine(int(os.environ["LOCAL_RANK"]))           # the device calls of the product answered by the oracle
+eng._aux = OracleEngine(eng.device_index)
+D._ENGINE = eng
+S.phasescore = lambda values, engine=None: O.phasescore_scipy(list(values))
+case = load_golden("metagene_case.json.gz")["case"]
+names = [c[0] for c in case["contigs"]]
+cols = alignments_to_reads(case, names)
+order = np.lexsort((cols["first"], cols["ref_id"]))         # a coordinate-sorted library: ranks take slices of it
+reads = ReadColumns(names, np.array([c[1] for c in case["contigs"]], np.int64), {k: v[order] for k, v in cols.items()}, True)
+idx_path = os.path.join(out_dir, f"index_{rank}.tsv")
+open(idx_path, "w").write("\n".join(case["index"]) + "\n")
+for tag, args in (("default", (None, None, None)), ("given", ("forward", None, {int(k): v for k, v in case["psite_offsets"].items()}))):
+    prefix = os.path.join(out_dir, tag, "job")
+    shard = multi_gpu.detect_orfs_sharded(reads, idx_path, prefix, args[0], args[1], args[2], 0.428571428571, 5, 0, 0, 0.0, True,
+                                          meta_min_reads=case["meta_min_reads"])
+    assert 0 < len(shard.rows) < len(case["index"]) - 1      # a real split
+    dist.barrier()
+    if rank == 0:
+        single = os.path.join(out_dir, tag, "single")
+        D.detect_orfs(reads, idx_path, single, args[0], args[1], args[2], 0.428571428571, 5, 0, 0, 0.0, True,
+                      meta_min_reads=case["meta_min_reads"])
+        for suffix in ("_translating_ORFs.tsv", "_pos.wig", "_neg.wig", "_bam_summary.txt"):
+            a, b = open(prefix + suffix, "rb").read(), open(single + suffix, "rb").read()
+            assert a == b and len(a) > 0, (tag, suffix)
+        left = [f for f in os.listdir(os.path.dirname(prefix)) if ".rows" in f or f.endswith(".header")]
+        assert not left, left
+    dist.barrier()
+if rank == 0:
+    print("SHARDED_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_detect_orfs_sharded_two_rank_gloo_job(tmp_path, built):
+    """The product's multi-rank entry point, multi_gpu.detect_orfs_sharded, as a world-size-2 gloo job on the CPU (the
+    device calls answered by the oracle, tests/oracle_engine.py): rank 0 infers protocol and offsets and broadcasts them,
+    every rank scores its genomic block from its slice of the sorted library and writes its row runs, rank 0 joins them.
+    TSV, WIG and summary must equal the single-process detect_orfs() files byte for byte, with the default flags and
+    with given offsets.  (GPU twin: test_gpu_api.py::test_two_rank_job_is_byte_identical, which needs two GPUs.)"""
+    script = tmp_path / "sharded_worker.py"
+    script.write_text(SHARDED_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+         "--master-port", "29641", str(script), ROOT, str(tmp_path)],
+        capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "SHARDED_OK" in out.stdout
