@@ -244,7 +244,7 @@ def export_orf_coverages(
 
 
 def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: int, hi: int, report_all: bool,
-              write_header: bool = True, chunk_nt: int = 1 << 27, res_offset: int = 0):
+              write_header: bool = True, chunk_nt: int = 1 << 25, res_offset: int = 0):
     """Rows exactly as detect_orfs.py:304-323 formats them: np.float64 phase score and read
     density, Python-float ratio, ``str(list)`` profile.  Rows [lo, hi) of the index; their results sit at
     positions ``res_offset ...`` of the result columns, which is also their ORF number in the engine's resident
@@ -285,7 +285,8 @@ def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: i
     try:
         at = 0
         while at < len(keep):
-            # bounded chunks of reported ORFs so the profile buffer stays small
+            # bounded chunks of reported ORFs (128 MB of profile values): the buffers stay small and the gather of one chunk
+            # hides behind the text of the previous one
             csum = np.cumsum(length[keep[at:] - lo])
             n_take = max(1, int(np.searchsorted(csum, chunk_nt, side="right")))
             sel = np.ascontiguousarray(keep[at:at + n_take], np.int64)
