@@ -284,11 +284,12 @@ def write_tsv(path, idx: PackedIndex, res: dict, merged: MergedAlignments, lo: i
             out.write("\t".join(TSV_COLUMNS) + "\n")
     try:
         at = 0
+        csum = np.cumsum(length[keep - lo])          # profile values up to and including every reported row
         while at < len(keep):
             # bounded chunks of reported ORFs (128 MB of profile values): the buffers stay small and the gather of one chunk
             # hides behind the text of the previous one
-            csum = np.cumsum(length[keep[at:] - lo])
-            n_take = max(1, int(np.searchsorted(csum, chunk_nt, side="right")))
+            before = int(csum[at - 1]) if at else 0
+            n_take = max(1, int(np.searchsorted(csum, before + chunk_nt, side="right")) - at)
             sel = np.ascontiguousarray(keep[at:at + n_take], np.int64)
             ptr, prof = eng.gather_profiles(merged.cov, sel - lo + res_offset, length[sel - lo])
             if native:
