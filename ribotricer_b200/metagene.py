@@ -33,7 +33,14 @@ def infer_protocol(reads, refseq: dict, prefix: str, n_reads: int = 20000) -> st
     by_contig = {}
     for chrom, spans in refseq.items():
         arr = np.array(spans, dtype=np.int64).reshape(-1, 3)
-        by_contig[chrom] = arr[np.argsort(arr[:, 0], kind="stable")]
+        arr = arr[np.argsort(arr[:, 0], kind="stable")]
+        # spans sorted by start; their ends sorted; and, for every prefix of the start order, which span ends last
+        last_end = np.zeros(len(arr), np.int64)
+        if len(arr):
+            running = np.maximum.accumulate(arr[:, 1])
+            is_new = np.concatenate([[True], arr[1:, 1] > running[:-1]])          # a span that ends later than all before it
+            last_end = np.maximum.accumulate(np.where(is_new, np.arange(len(arr)), 0))
+        by_contig[chrom] = (arr, np.sort(arr[:, 1]), last_end, bool((arr[:, 0] > arr[:, 1]).any()))
     names = reads.contig_names
     counts = {"++": 0, "--": 0, "+-": 0, "-+": 0}
     n = len(cols["ref_id"])
@@ -56,20 +63,45 @@ def infer_protocol(reads, refseq: dict, prefix: str, n_reads: int = 20000) -> st
         uniq = ((fl & 0x100) == 0) & np.where(nh != 0, nh == 1, mapq_all[lo:hi] == 255)
         ref = ref_all[lo:hi]
         ok = uniq & (ref >= 0) & (ref < len(names)) & (end_all[lo:hi] >= 0)     # chrom / mapped_end not None (:87)
-        for i in (lo + np.flatnonzero(ok)).tolist():
-            if iteration > n_reads:
-                break
-            spans = by_contig.get(names[int(ref_all[i])])
-            if spans is None:
+        cand = lo + np.flatnonzero(ok)
+        if len(cand) == 0:
+            continue
+        # for every candidate read: does it overlap exactly one annotated span, and on which strand is that span
+        single = np.zeros(len(cand), bool)
+        gene_plus = np.zeros(len(cand), bool)
+        c_ref = np.asarray(ref_all[cand], np.int64)
+        c_start, c_end = np.asarray(start_all[cand], np.int64), np.asarray(end_all[cand], np.int64)
+        for r in np.unique(c_ref).tolist():
+            entry = by_contig.get(names[r])
+            if entry is None:
                 continue
-            start, end = int(start_all[i]), int(end_all[i])
-            # spans are sorted by start: candidates end before the first span that starts after `end`
-            k = int(np.searchsorted(spans[:, 0], end, side="right"))
-            hit = spans[:k][spans[:k, 1] >= start]
-            if len(hit) == 1:                 # infer_protocol.py:98-105
-                gene = "+" if hit[0, 2] == 1 else "-"
-                counts[("-" if int(flag_all[i]) & 0x10 else "+") + gene] += 1
-                iteration += 1
+            spans, ends_sorted, last_end, odd = entry
+            sel = np.flatnonzero(c_ref == r)
+            st, en = c_start[sel], c_end[sel]
+            if odd or (en < st).any():
+                # a span that ends before it starts (or such a read): the inclusive test of the tree, span by span
+                for j, s0, e0 in zip(sel.tolist(), st.tolist(), en.tolist()):
+                    k = int(np.searchsorted(spans[:, 0], e0, side="right"))
+                    hit = spans[:k][spans[:k, 1] >= s0]
+                    single[j] = len(hit) == 1
+                    gene_plus[j] = len(hit) == 1 and hit[0, 2] == 1
+                continue
+            # spans that start at or before the read's end, minus those that end before its start (each of these also
+            # starts before the read's end): the inclusive overlap count of the reference's tree (`find`)
+            k = np.searchsorted(spans[:, 0], en, side="right")
+            n_hit = k - np.searchsorted(ends_sorted, st, side="left")
+            one = n_hit == 1
+            single[sel] = one
+            # the one span that overlaps is the one that ends last among the first k
+            gene_plus[sel[one]] = spans[last_end[k[one] - 1], 2] == 1
+        hits = np.flatnonzero(single)[:max(0, n_reads + 1 - iteration)]           # in read order, until :79 stops the loop
+        minus = (np.asarray(flag_all[cand[hits]], np.int64) & 0x10) != 0
+        gp = gene_plus[hits]
+        counts["++"] += int((~minus & gp).sum())
+        counts["+-"] += int((~minus & ~gp).sum())
+        counts["-+"] += int((minus & gp).sum())
+        counts["--"] += int((minus & ~gp).sum())
+        iteration += len(hits)
     for k in counts:                      # pseudocounts, infer_protocol.py:107-110
         counts[k] += 1
     total = sum(counts.values())
