@@ -11,8 +11,10 @@
 //             occurs twice the LAST one counts, as in dict().
 //   pos / ref_end = reference_start / reference_end of infer_protocol.py:84-85 (ref_end = -1 for None:
 //             unmapped flag or no CIGAR; else pos + reference length of the CIGAR, at least 1 as in htslib)
-// BGZF blocks are inflated in parallel (zlib raw inflate), records are cut sequentially and
-// decoded in parallel.  No GPU is involved.
+// The file is decoded as a pipeline of batches of BGZF blocks (see rt_bam_load): every worker inflates a batch
+// (rt_inflate.cpp, CRC-32 checked, zlib as fallback), takes its turn in the one sequential step -- finding the record
+// boundaries of the batch, which needs the offset the previous batch ended on -- and decodes its records into
+// columns; the columns are concatenated by all threads at the end.  No GPU is involved.
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <fcntl.h>
